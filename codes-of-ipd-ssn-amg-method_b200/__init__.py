@@ -1,0 +1,15 @@
+"""codes-of-ipd-ssn-amg-method_b200 -- B200-native (sm_100a CUDA) semismooth-Newton inner linear
+solve of the IPD-SsN-AMG optimal-transport method.
+
+The directory name is not a Python identifier; import it through the ``ssnamg`` shim at the
+repository root (``import ssnamg``) or ``importlib.import_module``.  ``csrc/`` holds the CUDA
+kernels and the C ABI (``include/ssnamg.h``); ``api.py`` mirrors the reference's MATLAB function
+signatures on top of it; ``problems.py`` has the synthetic configurations of BASELINE.json.
+"""
+from . import problems                                                    # noqa: F401
+from ._lib import LIB_PATH, SIGNATURES, SsnError, load                    # noqa: F401
+from .api import (Ax, Aty, ASAt, ASAtz, invAAt, invHHt, prox_residual,    # noqa: F401
+                  strength, mis_set, cf_split, transfer, amg_setup, amg_clear,
+                  MG_Vcycle, MG_Wcycle, Class_AMG, PCG, components, Hybrid_AMG,
+                  aug_PCG, AMG4POT, PCG4POT, rescaled_system, spmv, spgemm,
+                  transpose, DeviceCSR, rng_reset, rng_drawn, rand, launch_count)

@@ -1,0 +1,491 @@
+"""Host-side mirror of the reference's MATLAB functions on the SsN inner-solve path.
+
+Same names, same positional arguments and the same error behaviour as the reference ``.m``
+files; every function is a thin marshalling layer over one C-ABI entry
+point of ``libssnamg.so`` -- this file stands where the MEX shims stand for MATLAB.
+
+Array arguments may be NumPy arrays (host; copied to the device, results come back as NumPy)
+or torch CUDA tensors (device-resident, the analogue of ``gpuArray``; results are torch CUDA
+tensors).  Sparse matrices are returned as :class:`DeviceCSR` handles (device-resident CSR; use
+``.to_scipy()``); functions taking a sparse matrix accept a :class:`DeviceCSR` or any SciPy
+sparse matrix.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AmgOptions, CSR, PcgOptions, ProbData, SsnError, context
+
+
+def _torch():
+    import torch
+    return torch
+
+
+# ------------------------------------------------------------------ marshalling helpers
+
+def _is_host(*xs):
+    torch = _torch()
+    return not any(isinstance(x, torch.Tensor) for x in xs if x is not None)
+
+
+def _dev(x, dtype=None, count=None):
+    """-> contiguous 1-D CUDA tensor of the given dtype."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    if isinstance(x, torch.Tensor):
+        t = x
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        if not t.is_cuda:
+            t = t.cuda()
+        t = t.reshape(-1) if t.dim() != 1 else t
+        t = t.contiguous()
+    else:
+        a = np.asarray(x)
+        npd = {torch.float64: np.float64, torch.uint8: np.uint8, torch.int32: np.int32}[dtype]
+        if a.dtype == np.bool_ and npd is np.uint8:
+            a = a.view(np.uint8)
+        a = np.ascontiguousarray(a.reshape(-1, order="F"), dtype=npd)
+        t = torch.from_numpy(a).cuda()
+    if count is not None and t.numel() != count:
+        raise ValueError(f"expected {count} elements, got {t.numel()}")
+    return t
+
+
+def _ret(t, host):
+    return t.cpu().numpy() if host else t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DeviceCSR:
+    """Device-resident CSR matrix handle (``ssn_csr``).  Structurally symmetric matrices on this
+    path have CSR arrays == the CSC arrays a MATLAB sparse matrix holds."""
+
+    def __init__(self, ctx, st, owned=True, keepalive=None):
+        self.ctx, self.st, self.owned, self._keep = ctx, st, owned, keepalive
+
+    @property
+    def shape(self):
+        return (int(self.st.nrows), int(self.st.ncols))
+
+    @property
+    def nnz(self):
+        return int(self.st.nnz)
+
+    @classmethod
+    def from_scipy(cls, A, ctx=None):
+        import scipy.sparse as sp
+        ctx = ctx or context()
+        A = sp.csr_matrix(A, dtype=np.float64)
+        A.sort_indices()
+        st = CSR()
+        rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        v = np.ascontiguousarray(A.data, dtype=np.float64)
+        ctx.call("ssn_csr_upload", A.shape[0], A.shape[1], A.nnz, rp.ctypes.data_as(C.c_void_p),
+                 ci.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.byref(st))
+        return cls(ctx, st)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        n, nnz = int(self.st.nrows), int(self.st.nnz)
+        rp = np.empty(n + 1, dtype=np.int32); ci = np.empty(max(nnz, 1), dtype=np.int32)
+        v = np.empty(max(nnz, 1), dtype=np.float64)
+        self.ctx.call("ssn_csr_download", C.byref(self.st), rp.ctypes.data_as(C.c_void_p),
+                      ci.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        return sp.csr_matrix((v[:nnz], ci[:nnz], rp), shape=self.shape)
+
+    def free(self):
+        if self.owned and self.st.rowptr_dev:
+            try:
+                self.ctx.call("ssn_csr_free", C.byref(self.st))
+            except Exception:
+                pass
+        self.owned = False
+
+    def __del__(self):
+        self.free()
+
+
+def _csr(A, ctx):
+    return A if isinstance(A, DeviceCSR) else DeviceCSR.from_scipy(A, ctx)
+
+
+def _empty(v):
+    return v is None or (hasattr(v, "__len__") and not isinstance(v, str) and len(v) == 0)
+
+
+def _amg_options(opts, keep):
+    """dict (MATLAB struct) -> ssn_amg_options; missing/empty field -> 'empty' sentinel."""
+    o = AmgOptions(retol=-1.0, bigph=-1, maxit=-1, theta=-1.0, smoth=-1, cycle=-1, isnsp=-1, inter=-1,
+                   fnode=0, guess_dev=None)
+    if opts is None:
+        return None
+    g = lambda k: None if _empty(opts.get(k)) else opts.get(k)
+    if g("retol") is not None: o.retol = float(g("retol"))
+    if g("bigph") is not None: o.bigph = int(g("bigph"))
+    if g("maxit") is not None: o.maxit = int(g("maxit"))
+    if g("theta") is not None: o.theta = float(g("theta"))
+    if g("smoth") is not None: o.smoth = int(g("smoth"))
+    if g("cycle") is not None:
+        cyc = g("cycle")
+        o.cycle = ord(cyc) if isinstance(cyc, str) else int(cyc)
+    if g("isnsp") is not None: o.isnsp = int(g("isnsp"))
+    if g("inter") is not None: o.inter = int(g("inter"))
+    if g("fnode") is not None: o.fnode = int(g("fnode"))
+    if g("guess") is not None:
+        t = _dev(g("guess")); keep.append(t); o.guess_dev = t.data_ptr()
+    return o
+
+
+def _pcg_options(opts, keep):
+    if opts is None:
+        return None
+    o = PcgOptions(retol=-1.0, maxit=-1, precd=-1, nf=0, guess_dev=None)
+    g = lambda k: None if _empty(opts.get(k)) else opts.get(k)
+    if g("retol") is not None: o.retol = float(g("retol"))
+    if g("maxit") is not None: o.maxit = int(g("maxit"))
+    if g("precd") is not None: o.precd = int(g("precd"))
+    if g("nf") is not None: o.nf = int(g("nf"))
+    if g("guess") is not None:
+        t = _dev(g("guess")); keep.append(t); o.guess_dev = t.data_ptr()
+    return o
+
+
+def _byref_or_null(o):
+    return C.byref(o) if o is not None else None
+
+
+# ------------------------------------------------------------------ random stream
+
+def rng_reset(seed=5489):
+    """Reset the library-owned MATLAB ``rand`` stream (mt19937ar seed 0 == init_genrand(5489))."""
+    context().call("ssn_rng_reset", int(seed))
+
+
+def rng_drawn():
+    ctx = context()
+    return int(ctx.lib.ssn_rng_drawn(ctx.h))
+
+
+def rand(count):
+    torch = _torch()
+    out = torch.empty(int(count), dtype=torch.float64, device="cuda")
+    context().call("ssn_rand", int(count), _ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------ L1: plan operators
+
+def Ax(x, p, q):
+    """``y = Ax(x,p,q)`` -- reference Ax.m:2-14."""
+    torch = _torch(); ctx = context(); host = _is_host(x, p, q)
+    if hasattr(x, "todense"):                      # Class1/warmup_class1.m:29 passes a sparse zero x
+        x = np.asarray(x.todense())
+    pd, qd = _dev(p), _dev(q)
+    m, n = pd.numel(), qd.numel()
+    xd = _dev(x, count=m * n)
+    y = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_ax", _ptr(xd), _ptr(pd), _ptr(qd), m, n, _ptr(y))
+    return _ret(y, host)
+
+
+def Aty(y, p, q):
+    """``z = Aty(y,p,q)`` -- reference Aty.m:2-14."""
+    torch = _torch(); ctx = context(); host = _is_host(y, p, q)
+    pd, qd = _dev(p), _dev(q)
+    m, n = pd.numel(), qd.numel()
+    yd = _dev(y)
+    if yd.numel() < n + m:
+        raise ValueError("y must have at least n+m entries")
+    z = torch.empty(m * n, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_aty", _ptr(yd), _ptr(pd), _ptr(qd), m, n, _ptr(z))
+    return _ret(z, host)
+
+
+def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count")):
+    """Fused SsN residual pieces in one read of ``w`` (Class1/APD_SsN_Class1.m:139-144,184):
+    ``z=(w-Aty(lam))/tk``, ``s=(z>=0)&(z<=gama)``, ``prox=min(max(0,z),gama)``, ``Ax(prox)``,
+    ``||prox||^2``, ``nnz(s)``.  ``want`` selects the outputs; returns a dict."""
+    torch = _torch(); ctx = context(); host = _is_host(w, lam, p, q)
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    wd, ld = _dev(w, count=m * n), _dev(lam)
+    gvec, gs = None, float("inf")
+    if np.isscalar(gama) or (hasattr(gama, "numel") and gama.numel() == 1) or np.size(gama) == 1:
+        gs = float(gama if np.isscalar(gama) else np.asarray(gama.cpu() if hasattr(gama, "cpu") else gama).reshape(-1)[0])
+    else:
+        gvec = _dev(gama, count=m * n)
+    mk = lambda name, shape, dt: torch.empty(shape, dtype=dt, device="cuda") if name in want else None
+    axp = mk("Axprox", n + m, torch.float64); px = mk("prox", m * n, torch.float64)
+    z = mk("z", m * n, torch.float64); s = mk("s", m * n, torch.uint8)
+    n2 = C.c_double(0.0); cnt = C.c_int64(0)
+    ctx.call("ssn_prox_residual", _ptr(wd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(gvec), gs,
+             _ptr(axp), _ptr(px), _ptr(z), _ptr(s), C.byref(n2), C.byref(cnt))
+    out = {"norm2": n2.value, "count": cnt.value}
+    for k, v in (("Axprox", axp), ("prox", px), ("z", z), ("s", s)):
+        if v is not None:
+            out[k] = _ret(v, host)
+    return out
+
+
+def ASAt(s, p, q):
+    """``H = ASAt(s,p,q)`` -- reference ASAt.m:2-20 (``s`` logical, one byte per entry)."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    sd = _dev(s, torch.uint8, count=m * n)
+    st = CSR()
+    ctx.call("ssn_asat", _ptr(sd), _ptr(pd), _ptr(qd), m, n, C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
+def ASAtz(z, s, p, q):
+    """``y = ASAtz(z,s,p,q)`` -- reference ASAtz.m:2-23 (as written, ``Q*p`` at :21)."""
+    torch = _torch(); ctx = context(); host = _is_host(z, s, p, q)
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    zd = _dev(z, count=n + m); sd = _dev(s, torch.uint8, count=m * n)
+    y = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_asatz", _ptr(zd), _ptr(sd), _ptr(pd), _ptr(qd), m, n, _ptr(y))
+    return _ret(y, host)
+
+
+def invAAt(x, p, q, sg1=None, sg2=None):
+    """``y = invAAt(x,p,q[,sg1[,sg2]])`` -- reference invAAt.m:1-21 (nargin defaults :7-12)."""
+    torch = _torch(); ctx = context(); host = _is_host(x, p, q)
+    if sg1 is None:
+        sg1, sg2 = 1.0, 1.0
+    elif sg2 is None:
+        sg2 = sg1
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    xd = _dev(x, count=n + m)
+    y = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_invaat", _ptr(xd), _ptr(pd), _ptr(qd), m, n, float(sg1), float(sg2), _ptr(y))
+    return _ret(y, host)
+
+
+def invHHt(v, p, q, sg, phi):
+    """``y = invHHt(v,p,q,sg,phi)`` -- reference Class2/invHHt.m:1-18."""
+    torch = _torch(); ctx = context(); host = _is_host(v, p, q, phi)
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    vd = _dev(v, count=n + m + 1); ph = _dev(phi, count=m * n)
+    y = torch.empty(n + m + 1, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_invhht", _ptr(vd), _ptr(pd), _ptr(qd), m, n, float(sg), _ptr(ph), _ptr(y))
+    return _ret(y, host)
+
+
+# ------------------------------------------------------------------ L2: AMG setup
+
+def strength(A, which=2):
+    """``S = strength(A[,which])`` -- reference AMG/strength.m:1-19."""
+    ctx = context(); Ad = _csr(A, ctx); st = CSR()
+    ctx.call("ssn_strength", C.byref(Ad.st), int(which), C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
+def mis_set(A, theta=0.025):
+    """``[isC,isF,As] = mis_set(A[,theta])`` -- reference AMG/mis_set.m:1-68."""
+    torch = _torch(); ctx = context(); Ad = _csr(A, ctx)
+    N = Ad.shape[0]
+    isC = torch.empty(N, dtype=torch.uint8, device="cuda"); isF = torch.empty_like(isC)
+    st = CSR()
+    ctx.call("ssn_mis_set", C.byref(Ad.st), float(theta), _ptr(isC), _ptr(isF), C.byref(st))
+    return isC.cpu().numpy().astype(bool), isF.cpu().numpy().astype(bool), DeviceCSR(ctx, st)
+
+
+def cf_split(S):
+    """``[indC,indF,SubG] = cf_split(S)`` -- reference AMG/cf_split.m:1-16.  The third output
+    (a MATLAB ``graph`` object in the reference) is returned as the adjacency handle ``S``."""
+    torch = _torch(); ctx = context(); Sd = _csr(S, ctx)
+    N = Sd.shape[0]
+    indC = torch.empty(N, dtype=torch.uint8, device="cuda"); indF = torch.empty_like(indC)
+    ctx.call("ssn_cf_split", C.byref(Sd.st), _ptr(indC), _ptr(indF))
+    return indC.cpu().numpy().astype(bool), indF.cpu().numpy().astype(bool), Sd
+
+
+def transfer(A, amg_options=None, J=1):
+    """``[Ac,Pro,As,indC] = transfer(A[,amg_options])`` -- reference AMG/transfer.m:1-67.
+    ``J`` stands for the reference's ``global J`` (transfer.m:17)."""
+    torch = _torch(); ctx = context(); Ad = _csr(A, ctx); keep = []
+    o = _amg_options(amg_options, keep)
+    N = Ad.shape[0]
+    indC = torch.empty(N, dtype=torch.uint8, device="cuda")
+    ac, pro, As = CSR(), CSR(), CSR()
+    ctx.call("ssn_transfer", C.byref(Ad.st), _byref_or_null(o), int(J), C.byref(ac), C.byref(pro), C.byref(As), _ptr(indC))
+    return DeviceCSR(ctx, ac), DeviceCSR(ctx, pro), DeviceCSR(ctx, As), indC.cpu().numpy().astype(bool)
+
+
+def amg_setup(A, amg_options):
+    """Setup phase of Class_AMG (AMG/Class_AMG.m:41-85) into the library-owned hierarchy handle
+    (the reference's globals).  Returns the list of (A_k, Pro_k) level views."""
+    ctx = context(); Ad = _csr(A, ctx); keep = []
+    o = _amg_options(amg_options, keep)
+    J = C.c_int(0)
+    ctx.call("ssn_amg_setup", C.byref(Ad.st), _byref_or_null(o), C.byref(J))
+    levels = []
+    for k in range(1, J.value + 1):
+        a, p = CSR(), CSR()
+        ctx.call("ssn_amg_level", k, C.byref(a), C.byref(p))
+        levels.append((DeviceCSR(ctx, a, owned=False), DeviceCSR(ctx, p, owned=False) if k > 1 else None))
+    return levels
+
+
+def amg_clear():
+    context().call("ssn_amg_clear")
+
+
+def MG_Vcycle(r, isnsp=0, k=1):
+    """``e = MG_Vcycle(r[,isnsp[,k]])`` -- reference AMG/MG_Vcycle.m:2-46 (live hierarchy)."""
+    torch = _torch(); ctx = context(); host = _is_host(r)
+    rd = _dev(r); e = torch.zeros_like(rd)
+    ctx.call("ssn_mg_vcycle", _ptr(rd), int(isnsp), int(k), _ptr(e))
+    return _ret(e, host)
+
+
+def MG_Wcycle(r, isnsp=0, k=1, e=None):
+    """``e = MG_Wcycle(r[,isnsp[,k[,e]]])`` -- reference AMG/MG_Wcycle.m:2-47 (live hierarchy)."""
+    torch = _torch(); ctx = context(); host = _is_host(r, e)
+    rd = _dev(r)
+    ed = torch.zeros_like(rd) if e is None else _dev(e).clone()
+    ctx.call("ssn_mg_wcycle", _ptr(rd), int(isnsp), int(k), _ptr(ed))
+    return _ret(ed, host)
+
+
+def Class_AMG(A, b, amg_options=None, keep_hierarchy=False):
+    """``[x,it,rel_res,rel_resk,rhok] = Class_AMG(A,b[,amg_options])`` -- AMG/Class_AMG.m:1-111."""
+    torch = _torch(); ctx = context(); host = _is_host(b); Ad = _csr(A, ctx); keep = []
+    o = _amg_options(amg_options, keep)
+    bd = _dev(b, count=Ad.shape[0])
+    x = torch.empty_like(bd)
+    maxit = 50 if o is None or o.maxit < 0 else o.maxit
+    relk = np.zeros(maxit + 2); rhok = np.zeros(maxit + 2)
+    it = C.c_int(0); rel = C.c_double(0.0); hl = C.c_int(0)
+    ctx.call("ssn_class_amg", C.byref(Ad.st), _ptr(bd), _byref_or_null(o), 1 if keep_hierarchy else 0, _ptr(x),
+             C.byref(it), C.byref(rel), relk.ctypes.data_as(C.c_void_p), rhok.ctypes.data_as(C.c_void_p), C.byref(hl))
+    return _ret(x, host), it.value, rel.value, relk[:hl.value].copy(), rhok[:hl.value].copy()
+
+
+# ------------------------------------------------------------------ L2: Krylov
+
+def PCG(H, e, pcg_options=None):
+    """``[d,it,res,resk] = PCG(H,e[,pcg_options])`` -- reference PCG.m:1-105."""
+    torch = _torch(); ctx = context(); host = _is_host(e); Hd = _csr(H, ctx); keep = []
+    o = _pcg_options(pcg_options, keep)
+    ed = _dev(e, count=Hd.shape[0]); d = torch.empty_like(ed)
+    maxit = 10000 if o is None or o.maxit < 0 else o.maxit
+    resk = np.zeros(max(maxit, 1))
+    it = C.c_int(0); res = C.c_double(0.0)
+    ctx.call("ssn_pcg", C.byref(Hd.st), _ptr(ed), _byref_or_null(o), _ptr(d), C.byref(it), C.byref(res),
+             resk.ctypes.data_as(C.c_void_p))
+    return _ret(d, host), it.value, res.value, resk[:maxit]
+
+
+# ------------------------------------------------------------------ L3: dispatch
+
+def components(A):
+    """``[blocks,sizes,p,r] = components(A)`` -- reference components.m:1-64.  Frozen ordering:
+    components by ascending smallest member, members ascending.  ``blocks`` 1-based labels,
+    ``p`` 0-based node indices, ``r`` 0-based boundaries."""
+    torch = _torch(); ctx = context(); Ad = _csr(A, ctx)
+    if Ad.shape[0] != Ad.shape[1]:
+        raise SsnError(-6, "Adjacency matrix must be square")
+    N = Ad.shape[0]
+    mk = lambda k: torch.empty(k, dtype=torch.int32, device="cuda")
+    blocks, sizes, p, r = mk(N), mk(N), mk(N), mk(N + 1)
+    nc = C.c_int(0)
+    ctx.call("ssn_components", C.byref(Ad.st), _ptr(blocks), _ptr(sizes), _ptr(p), _ptr(r), C.byref(nc))
+    k = nc.value
+    return (blocks.cpu().numpy().astype(np.int64), sizes[:k].cpu().numpy().astype(np.int64),
+            p.cpu().numpy().astype(np.int64), r[:k + 1].cpu().numpy().astype(np.int64))
+
+
+def _prob_data(prob_data, ctx, keep, pot=False):
+    torch = _torch()
+    pd = ProbData()
+    p, q = _dev(prob_data["p"]), _dev(prob_data["q"]); keep += [p, q]
+    m, n = p.numel(), q.numel()
+    pd.bk1, pd.tk, pd.m, pd.n = float(prob_data["bk1"]), float(prob_data["tk"]), m, n
+    pd.p_dev, pd.q_dev = p.data_ptr(), q.data_ptr()
+    T = prob_data.get("T")
+    if T is not None:
+        t = T.diagonal() if hasattr(T, "diagonal") and getattr(T, "ndim", 1) == 2 else T
+        td = _dev(np.asarray(t) if not isinstance(t, torch.Tensor) else t, count=n + m); keep.append(td)
+        pd.t_dev = td.data_ptr()
+    H0 = _csr(prob_data["H0"], ctx); keep.append(H0)
+    pd.H0 = C.pointer(H0.st)
+    z = _dev(prob_data["z"], count=n + m + (1 if pot else 0)); keep.append(z)
+    pd.z_dev = z.data_ptr()
+    if pot:
+        s = _dev(prob_data["s"], torch.uint8, count=m * n); phi = _dev(prob_data["phi"], count=m * n); keep += [s, phi]
+        pd.s_dev, pd.phi_dev = s.data_ptr(), phi.data_ptr()
+    return pd, m, n
+
+
+def _solve(entry, prob_data, options, conv, pot=False):
+    torch = _torch(); ctx = context(); keep = []
+    host = _is_host(prob_data["z"])
+    pd, m, n = _prob_data(prob_data, ctx, keep, pot)
+    o = conv(options, keep)
+    zeta = torch.empty(n + m + (1 if pot else 0), dtype=torch.float64, device="cuda")
+    it = C.c_int(0); res = C.c_double(0.0); info = (C.c_int * 2)()
+    ctx.call(entry, C.byref(pd), _byref_or_null(o), _ptr(zeta), C.byref(it), C.byref(res), info)
+    return _ret(zeta, host), it.value, res.value, np.array([info[0], info[1]])
+
+
+def Hybrid_AMG(prob_data, amg_options):
+    """``[zeta,itamg,resamg,info] = Hybrid_AMG(prob_data,amg_options)`` -- Hybrid_AMG.m:1-114."""
+    return _solve("ssn_hybrid_amg", prob_data, amg_options, _amg_options)
+
+
+def aug_PCG(prob_data, pcg_options):
+    """``[zeta,itpcg,respcg,info] = aug_PCG(prob_data,pcg_options)`` -- aug_PCG.m:1-38."""
+    return _solve("ssn_aug_pcg", prob_data, pcg_options, _pcg_options)
+
+
+def AMG4POT(prob_data, amg_options, str_="amg"):
+    """``[zeta,it,res,info] = AMG4POT(prob_data,amg_options,str)`` -- Class2/AMG4POT.m:1-56."""
+    if str_ != "amg":
+        raise SsnError(-10, "Hybrid_twogrid (inner_solver 5) is out of scope (SURVEY.md 8f)")
+    return _solve("ssn_amg4pot", prob_data, amg_options, _amg_options, pot=True)
+
+
+def PCG4POT(prob_data, pcg_options):
+    """``[zeta,it,res,info] = PCG4POT(prob_data,pcg_options)`` -- Class2/PCG4POT.m:1-40."""
+    return _solve("ssn_pcg4pot", prob_data, pcg_options, _pcg_options, pot=True)
+
+
+def rescaled_system(prob_data):
+    """``Ae, f`` of Hybrid_AMG.m:17-24 (exported for parity tests)."""
+    torch = _torch(); ctx = context(); keep = []
+    pd, m, n = _prob_data(prob_data, ctx, keep)
+    f = torch.empty(n + m, dtype=torch.float64, device="cuda"); st = CSR()
+    ctx.call("ssn_rescaled_system", C.byref(pd), C.byref(st), _ptr(f))
+    return DeviceCSR(ctx, st), f.cpu().numpy()
+
+
+# ------------------------------------------------------------------ sparse utilities
+
+def spmv(A, x):
+    torch = _torch(); ctx = context(); host = _is_host(x); Ad = _csr(A, ctx)
+    xd = _dev(x, count=Ad.shape[1]); y = torch.empty(Ad.shape[0], dtype=torch.float64, device="cuda")
+    ctx.call("ssn_spmv", C.byref(Ad.st), _ptr(xd), _ptr(y))
+    return _ret(y, host)
+
+
+def spgemm(A, B):
+    ctx = context(); Ad, Bd = _csr(A, ctx), _csr(B, ctx); st = CSR()
+    ctx.call("ssn_spgemm", C.byref(Ad.st), C.byref(Bd.st), C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
+def transpose(A):
+    ctx = context(); Ad = _csr(A, ctx); st = CSR()
+    ctx.call("ssn_transpose", C.byref(Ad.st), C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
+def launch_count():
+    return context().launches()

@@ -1,0 +1,78 @@
+// amg.cuh -- the Class_AMG hierarchy (the reference's globals Ack/Prok/Rk/J/smoth_it,
+// AMG/Class_AMG.m:42-43) as a context-owned handle, plus the internal AMG interfaces.
+#pragma once
+#include "common.cuh"
+#include "sparse.cuh"
+
+namespace ssn {
+
+// Device-visible description of one level (array uploaded after setup).
+struct LevelDev {
+    int N, Nf, bigph;                                  // bigph: level-1 block Gauss-Seidel smoother
+    const int* ap; const int* ai; const double* av;    // A_k
+    const int* pp; const int* pi; const double* pv;    // Pro_k   (N_{k-1} x N_k), null at level 1
+    const int* tp; const int* ti; const double* tv;    // Pro_k'  (N_k x N_{k-1})
+    const double* dinv;   // bigph: 1/diag(A) (invV ; invT, Class_AMG.m:56-57); else 0.5*(1/diag) (:72,:84)
+    const double* Axi;    // A*ones
+    double xx;            // ones'*A*ones
+    double* r; double* e; double* g;                   // work vectors
+    double* pcg;                                       // 5*N scratch (small levels)
+};
+
+struct Level {
+    int N = 0, Nf = 0, bigph = 0;
+    Csr A, P, Pt;
+    Buf<double> dinv, Axi, r, e, g, pcg;
+    double xx = 0.0;
+    // setup trace (kept for parity tests: C/F split and strength flags that produced level k+1)
+    Buf<uint8_t> isC;
+};
+
+struct Hierarchy {
+    std::vector<Level> lv;
+    int J = 0;
+    int smoth = 0;
+    int small_from = 0;            // levels >= small_from are solved by the single-block kernel
+    Buf<LevelDev> dev;
+    Buf<double> part;              // reduction partials (multi-block kernels)
+    Buf<double> scal;              // small device scalars
+};
+
+struct AmgOptions {                // amg_options with the isempty() defaults applied
+    double retol; int bigph; int maxit; double theta; int smoth; int cycle; int isnsp; int inter; int fnode;
+    const double* guess;
+};
+AmgOptions resolve_options(const ssn_amg_options* o);
+
+// ---- setup (amg_setup.cu)
+void rng_reset(ssn_ctx* c, uint32_t seed);
+void rng_rand(ssn_ctx* c, int64_t count, double* out_dev);
+Csr strength_matrix(ssn_ctx* c, const CsrView& A, int which);
+// strength flags aligned with A's entries: as[e] = (S(i,j) >= theta)
+void strength_flags(ssn_ctx* c, const CsrView& A, double theta, uint8_t* as_flags);
+void mis_set(ssn_ctx* c, const CsrView& A, double theta, uint8_t* isC, uint8_t* isF, Buf<uint8_t>& as_flags);
+void cf_split(ssn_ctx* c, const CsrView& S, uint8_t* indC, uint8_t* indF);
+Csr flags_to_csr(ssn_ctx* c, const CsrView& A, const uint8_t* as_flags);
+// one coarsening step: returns Ac, Pro (and keeps isC / strength flags if requested)
+void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Csr& Ac, Csr& Pro,
+              Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out);
+void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o);
+void amg_clear(ssn_ctx* c);
+int coarsest_threshold(int64_t N);
+
+// ---- solve (amg_solve.cu)
+void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev, bool wcycle, bool e_is_zero);
+void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, bool keep, double* x, int* it_out,
+               double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
+void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
+               double* res_out, double* resk_host);
+
+// ---- dispatch (solvers.cu)
+void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm, int* r, int* ncomp);
+void rescaled_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Ae, double* f, Buf<double>& qp, Buf<double>& Kd);
+void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* itamg,
+                double* resamg, int* info);
+void aug_pcg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* itpcg,
+             double* respcg, int* info);
+
+}  // namespace ssn

@@ -1,0 +1,538 @@
+// amg_solve.cu -- solve phase: smoothers (block Gauss-Seidel on the bigraph level, damped
+// Jacobi elsewhere, with the kernel-space correction), V/W-cycles, the coarse PCG, Class_AMG's
+// stationary iteration and the general PCG of PCG.m.
+//
+// Large levels run as multi-block kernels (fused residual + partial sums, fused smoother
+// update); the tail of small levels (N <= 2048) is ONE single-block kernel that walks the whole
+// sub-hierarchy -- smoothing, restriction, the 2^(J-k) coarse PCG solves, prolongation -- with
+// block barriers only, because that part of the W-cycle is pure launch latency otherwise.
+#include "amg.cuh"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace ssn {
+
+namespace {
+
+constexpr int kCycleThreads = 512;
+constexpr int kMaxPartBlocks = 296;
+
+// sum over a row's entries, cooperating TPR lanes; result valid in all TPR lanes
+template <int TPR>
+__device__ __forceinline__ double row_dot(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                          const double* __restrict__ val, const double* __restrict__ x,
+                                          int row, int sub, bool valid) {
+    double s = 0.0;
+    if (valid) {
+        const int e1 = ptr[row + 1];
+        for (int e = ptr[row] + sub; e < e1; e += TPR) s = fma(val[e], x[idx[e]], s);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// increment of the smoother for row i:  coef + (R h)_i,  h = g - Axi*coef
+template <int TPR>
+__device__ __forceinline__ double smooth_inc(const LevelDev& L, const double* __restrict__ g, double coef, int post,
+                                             int row, int sub, bool valid) {
+    double hi = 0.0, di = 0.0;
+    if (valid) { hi = g[row] - L.Axi[row] * coef; di = L.dinv[row]; }
+    double s = 0.0;
+    if (L.bigph) {
+        // forward sweep (R, MG_Wcycle.m:19): row nodes see the updated column nodes;
+        // backward sweep (R', MG_Wcycle.m:37): column nodes see the updated row nodes
+        const bool coupled = valid && (post ? (row < L.Nf) : (row >= L.Nf));
+        if (coupled) {
+            const int e1 = L.ap[row + 1];
+            for (int e = L.ap[row] + sub; e < e1; e += TPR) {
+                const int j = L.ai[e];
+                const bool other = post ? (j >= L.Nf) : (j < L.Nf);
+                if (other) s = fma(L.av[e], L.dinv[j] * (g[j] - L.Axi[j] * coef), s);
+            }
+        }
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    return coef + di * (hi - s);
+}
+
+// ------------------------------------------------------------------ multi-block kernels
+
+// g = r - A*e (e == nullptr: g = r); part[2b] = sum g, part[2b+1] = sum g^2 over the block's rows
+template <int TPR>
+__global__ void __launch_bounds__(256) resid_kernel(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                    const double* __restrict__ val, const double* __restrict__ r,
+                                                    const double* __restrict__ e, double* __restrict__ g,
+                                                    double* __restrict__ part) {
+    __shared__ double red[32];
+    const int sub = threadIdx.x % TPR;
+    const int rows_per_pass = gridDim.x * (256 / TPR);
+    double sg = 0.0, sg2 = 0.0;
+    for (int base = 0; base < n; base += rows_per_pass) {
+        const int row = base + blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+        const bool valid = row < n;
+        double d = 0.0;
+        if (e != nullptr) d = row_dot<TPR>(ptr, idx, val, e, row, sub, valid);
+        if (valid && sub == 0) {
+            const double gi = r[row] - d;
+            g[row] = gi; sg += gi; sg2 = fma(gi, gi, sg2);
+        }
+    }
+    sg = block_sum(sg, red);
+    sg2 = block_sum(sg2, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = sg; part[2 * blockIdx.x + 1] = sg2; }
+}
+
+__device__ __forceinline__ double sum_parts(const double* __restrict__ part, int np, int stride, double* red) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s += part[(size_t)i * stride];
+    return block_sum(s, red);
+}
+
+// e += coef + R(g - Axi*coef), coef = isnsp ? sum(g)/xx : 0
+template <int TPR>
+__global__ void __launch_bounds__(256) smooth_apply_kernel(LevelDev L, const double* __restrict__ g, double* __restrict__ e,
+                                                           const double* __restrict__ part, int np, int isnsp, int post,
+                                                           int e_is_zero) {
+    __shared__ double red[32];
+    double coef = 0.0;
+    if (isnsp) coef = sum_parts(part, np, 2, red) / L.xx;
+    const int sub = threadIdx.x % TPR;
+    const int rows_per_pass = gridDim.x * (256 / TPR);
+    for (int base = 0; base < L.N; base += rows_per_pass) {
+        const int row = base + blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+        const bool valid = row < L.N;
+        const double inc = smooth_inc<TPR>(L, g, coef, post, row, sub, valid);
+        if (valid && sub == 0) e[row] = e_is_zero ? inc : (e[row] + inc);
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
+    __shared__ double red[32];
+    const double a = sum_parts(part, np, 2, red);
+    const double b = sum_parts(part + 1, np, 2, red);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+__global__ void axpy_kernel(int n, double a, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+
+// ------------------------------------------------------------------ single-block cycle
+
+constexpr int kBT = 4;                                    // lanes per row inside the block kernel
+
+__device__ void blk_resid(const LevelDev& L, const double* r, const double* e, double* g, double* red, double* sum_out) {
+    const int sub = threadIdx.x % kBT;
+    double sg = 0.0;
+    for (int base = 0; base < L.N; base += kCycleThreads / kBT) {
+        const int row = base + threadIdx.x / kBT;
+        const bool valid = row < L.N;
+        double d = 0.0;
+        if (e != nullptr) d = row_dot<kBT>(L.ap, L.ai, L.av, e, row, sub, valid);
+        if (valid && sub == 0) { const double gi = r[row] - d; g[row] = gi; sg += gi; }
+    }
+    const double t = block_sum(sg, red);                  // barriers inside publish g
+    if (sum_out) *sum_out = t;
+}
+
+__device__ void blk_smooth(const LevelDev& L, const double* r, double* e, bool e_zero, int steps, int isnsp, int post,
+                           double* red) {
+    const int sub = threadIdx.x % kBT;
+    for (int it = 0; it < steps; ++it) {
+        double sg = 0.0;
+        blk_resid(L, r, e_zero ? nullptr : e, L.g, red, &sg);
+        const double coef = isnsp ? sg / L.xx : 0.0;
+        for (int base = 0; base < L.N; base += kCycleThreads / kBT) {
+            const int row = base + threadIdx.x / kBT;
+            const bool valid = row < L.N;
+            const double inc = smooth_inc<kBT>(L, L.g, coef, post, row, sub, valid);
+            if (valid && sub == 0) e[row] = e_zero ? inc : (e[row] + inc);
+        }
+        e_zero = false;
+        __syncthreads();
+    }
+    if (steps == 0 && e_zero) {
+        for (int i = threadIdx.x; i < L.N; i += kCycleThreads) e[i] = 0.0;
+        __syncthreads();
+    }
+}
+
+// y (+)= M*x for a CSR M with nrows rows
+__device__ void blk_spmv(int nrows, const int* ptr, const int* idx, const double* val, const double* x, double* y, bool add) {
+    const int sub = threadIdx.x % kBT;
+    for (int base = 0; base < nrows; base += kCycleThreads / kBT) {
+        const int row = base + threadIdx.x / kBT;
+        const bool valid = row < nrows;
+        const double d = row_dot<kBT>(ptr, idx, val, x, row, sub, valid);
+        if (valid && sub == 0) y[row] = add ? (y[row] + d) : d;
+    }
+    __syncthreads();
+}
+
+// PCG(A,r) with the defaults of PCG.m:18-23 (zero guess, retol 1e-11, maxit 1e4, Jacobi)
+__device__ void blk_pcg(const LevelDev& L, const double* rhs, double* x, double* red) {
+    const int n = L.N;
+    double* r = L.pcg; double* p = r + n; double* q = p + n;
+    double dn = 0.0;
+    for (int i = threadIdx.x; i < n; i += kCycleThreads) {
+        const double ri = rhs[i];
+        const double diag = L.bigph ? (1.0 / L.dinv[i]) : (0.5 / L.dinv[i]);   // recover diag(A)
+        const double pi = ri / diag;
+        r[i] = ri; p[i] = pi; x[i] = 0.0; dn = fma(ri, pi, dn);
+    }
+    double delta_new = block_sum(dn, red);
+    const double delta_0 = delta_new;
+    const double tol2 = 1e-11 * 1e-11;
+    int it = 0;
+    while (it < 10000 && delta_new > tol2 * delta_0) {
+        const double delta_old = delta_new;
+        blk_spmv(n, L.ap, L.ai, L.av, p, q, false);
+        double qp = 0.0;
+        for (int i = threadIdx.x; i < n; i += kCycleThreads) qp = fma(q[i], p[i], qp);
+        qp = block_sum(qp, red);
+        const double alpha = delta_old / qp;
+        double dnew = 0.0;
+        for (int i = threadIdx.x; i < n; i += kCycleThreads) {
+            x[i] += alpha * p[i];
+            const double ri = r[i] - alpha * q[i];
+            const double diag = L.bigph ? (1.0 / L.dinv[i]) : (0.5 / L.dinv[i]);
+            r[i] = ri; q[i] = ri / diag;                  // q now holds w = M^{-1} r
+            dnew = fma(ri, q[i], dnew);
+        }
+        delta_new = block_sum(dnew, red);
+        const double beta = delta_new / delta_old;
+        for (int i = threadIdx.x; i < n; i += kCycleThreads) p[i] = q[i] + beta * p[i];
+        __syncthreads();
+        ++it;
+    }
+    __syncthreads();
+}
+
+// The whole cycle from level k0 down, iteratively (phase machine instead of recursion).
+__global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const LevelDev* __restrict__ levels, int k0, int J,
+                                                                     int smoth, int isnsp, int wcycle, int e0_zero) {
+    __shared__ double red[32];
+    __shared__ LevelDev sl[16];
+    const int nl = J - k0;
+    for (int t = threadIdx.x; t < nl && t < 16; t += kCycleThreads) sl[t] = levels[k0 + t];
+    __syncthreads();
+    int phase[16]; bool zero[16];
+    int k = 0;
+    phase[0] = 0; zero[0] = e0_zero != 0;
+    while (true) {
+        const LevelDev& L = sl[k];
+        if (k == nl - 1) {                                // coarsest: PCG(A,r), guess ignored (MG_Wcycle.m:44)
+            blk_pcg(L, L.r, L.e, red);
+            if (k == 0) break;
+            --k; continue;
+        }
+        if (phase[k] == 0) {
+            blk_smooth(L, L.r, L.e, zero[k], smoth, isnsp, 0, red);                 // presmoothing
+            blk_resid(L, L.r, (zero[k] && smoth == 0) ? nullptr : L.e, L.g, red, nullptr);
+            const LevelDev& Lc = sl[k + 1];
+            blk_spmv(Lc.N, Lc.tp, Lc.ti, Lc.tv, L.g, Lc.r, false);                  // restriction
+            phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ++k; continue;
+        }
+        if (phase[k] == 1 && wcycle) {                                             // correction again
+            phase[k] = 2; phase[k + 1] = 0; zero[k + 1] = false; ++k; continue;
+        }
+        {
+            const LevelDev& Lc = sl[k + 1];
+            blk_spmv(L.N, Lc.pp, Lc.pi, Lc.pv, Lc.e, L.e, true);                    // prolongation
+            blk_smooth(L, L.r, L.e, false, smoth, isnsp, 1, red);                   // postsmoothing
+        }
+        if (k == 0) break;
+        --k;
+    }
+}
+
+// ------------------------------------------------------------------ general PCG (persistent, cooperative)
+
+struct PcgArgs {
+    int n; const int* ptr; const int* idx; const double* val;
+    const double* rhs; const double* guess;
+    double* d; double* r; double* p; double* q; double* w; double* a;   // a: extra vector for bi-SSOR
+    const double* diag;
+    int precd, nf, maxit; double tol2;
+    double* part;            // [3][gridDim]
+    double* resk;            // maxit
+    int* it_out; double* scal_out;   // scal_out[0] = delta_new, [1] = delta_0
+};
+
+__device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, double* part, double* red) {
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    grid.sync();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += part[i];
+    s = block_sum(s, red);
+    return s;
+}
+
+// w = M^{-1} r for precd 1, 2, 5 (PCG.m:90-105); returns this thread's share of r'w
+__device__ double pcg_precond(cg::grid_group& grid, const PcgArgs& a, int gtid, int gsize) {
+    double dn = 0.0;
+    if (a.precd == 1) {
+        for (int i = gtid; i < a.n; i += gsize) { const double ri = a.r[i]; a.w[i] = ri; dn = fma(ri, ri, dn); }
+    } else if (a.precd == 2) {
+        for (int i = gtid; i < a.n; i += gsize) { const double ri = a.r[i]; const double wi = ri / a.diag[i]; a.w[i] = wi; dn = fma(ri, wi, dn); }
+    } else {
+        // bi-SSOR, w = 1.5:  P r = w(2-w) [ aa - w invV U b ; b ],  aa = invV r_c,  b = invT (r_r - w U' aa)
+        const double om = 1.5, sc = om * (2.0 - om);
+        for (int i = gtid; i < a.nf; i += gsize) a.a[i] = a.r[i] / a.diag[i];
+        grid.sync();
+        for (int i = a.nf + gtid; i < a.n; i += gsize) {
+            double s = 0.0;
+            for (int e = a.ptr[i]; e < a.ptr[i + 1]; ++e) { const int j = a.idx[e]; if (j < a.nf) s = fma(a.val[e], a.a[j], s); }
+            a.a[i] = (a.r[i] - om * s) / a.diag[i];
+        }
+        grid.sync();
+        for (int i = gtid; i < a.n; i += gsize) {
+            double wi;
+            if (i < a.nf) {
+                double s = 0.0;
+                for (int e = a.ptr[i]; e < a.ptr[i + 1]; ++e) { const int j = a.idx[e]; if (j >= a.nf) s = fma(a.val[e], a.a[j], s); }
+                wi = sc * (a.a[i] - om * s / a.diag[i]);
+            } else wi = sc * a.a[i];
+            a.w[i] = wi; dn = fma(a.r[i], wi, dn);
+        }
+    }
+    return dn;
+}
+
+__global__ void __launch_bounds__(256) pcg_kernel(PcgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[32];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = gtid >> 5, nwarps = gsize >> 5;
+    double* part0 = a.part; double* part1 = a.part + gridDim.x; double* part2 = a.part + 2 * gridDim.x;
+    // r = e - H*d0 ; d = d0                                   (PCG.m:68-70)
+    for (int i = gtid; i < a.n; i += gsize) a.d[i] = a.guess ? a.guess[i] : 0.0;
+    grid.sync();
+    for (int row = gwarp; row < a.n; row += nwarps) {
+        double s = 0.0;
+        if (a.guess) for (int e = a.ptr[row] + lane; e < a.ptr[row + 1]; e += 32) s = fma(a.val[e], a.d[a.idx[e]], s);
+        s = warp_sum(s);
+        if (lane == 0) a.r[row] = a.rhs[row] - s;
+    }
+    grid.sync();
+    double dn = pcg_precond(grid, a, gtid, gsize);
+    double delta_new = grid_sum(grid, dn, part0, red);
+    for (int i = gtid; i < a.n; i += gsize) a.p[i] = a.w[i];
+    const double delta_0 = delta_new;
+    int it = 0;
+    grid.sync();
+    while (it < a.maxit && delta_new > a.tol2 * delta_0) {           // PCG.m:76
+        const double delta_old = delta_new;
+        double qp = 0.0;
+        for (int row = gwarp; row < a.n; row += nwarps) {            // q = H*p
+            double s = 0.0;
+            for (int e = a.ptr[row] + lane; e < a.ptr[row + 1]; e += 32) s = fma(a.val[e], a.p[a.idx[e]], s);
+            s = warp_sum(s);
+            if (lane == 0) { a.q[row] = s; qp = fma(s, a.p[row], qp); }
+        }
+        qp = grid_sum(grid, qp, part1, red);
+        const double alpha = delta_old / qp;
+        for (int i = gtid; i < a.n; i += gsize) { a.d[i] += alpha * a.p[i]; a.r[i] -= alpha * a.q[i]; }
+        if (a.precd == 5) grid.sync();
+        dn = pcg_precond(grid, a, gtid, gsize);
+        delta_new = grid_sum(grid, dn, (it & 1) ? part0 : part2, red);
+        const double beta = delta_new / delta_old;
+        for (int i = gtid; i < a.n; i += gsize) a.p[i] = a.w[i] + beta * a.p[i];
+        ++it;
+        if (gtid == 0 && a.resk) a.resk[it - 1] = sqrt(fabs(delta_new / delta_0));
+        grid.sync();
+    }
+    if (gtid == 0) { *a.it_out = it; a.scal_out[0] = delta_new; a.scal_out[1] = delta_0; }
+}
+
+template <class F>
+void dispatch_tpr(double avg, F&& f) {
+    if (avg <= 3.0) f(std::integral_constant<int, 2>());
+    else if (avg <= 6.0) f(std::integral_constant<int, 4>());
+    else if (avg <= 12.0) f(std::integral_constant<int, 8>());
+    else if (avg <= 24.0) f(std::integral_constant<int, 16>());
+    else f(std::integral_constant<int, 32>());
+}
+
+int grid_rows(int n, int tpr) {
+    int g = cdiv((int64_t)n * tpr, 256);
+    if (g > kMaxPartBlocks) g = kMaxPartBlocks;
+    if (g < 1) g = 1;
+    return g;
+}
+
+// g = r - A e with partials; returns the number of partial pairs
+int launch_resid(ssn_ctx* c, const Level& L, const double* r, const double* e, double* g, double* part) {
+    const double avg = L.N ? (double)L.A.nnz / L.N : 0.0;
+    int np = 1;
+    dispatch_tpr(avg, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        np = grid_rows(L.N, TPR);
+        SSN_LAUNCH(c, resid_kernel<TPR>, np, 256, 0, L.N, L.A.ptr.p, L.A.idx.p, L.A.val.p, r, e, g, part);
+    });
+    return np;
+}
+
+void launch_apply(ssn_ctx* c, const LevelDev& Ld, const Level& L, const double* g, double* e, const double* part, int np,
+                  int isnsp, int post, bool e_zero) {
+    const double avg = L.N ? (double)L.A.nnz / L.N : 0.0;
+    dispatch_tpr(avg, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        const int gr = grid_rows(L.N, TPR);
+        SSN_LAUNCH(c, smooth_apply_kernel<TPR>, gr, 256, 0, Ld, g, e, part, np, isnsp, post, e_zero ? 1 : 0);
+    });
+}
+
+LevelDev level_dev(const Level& L) {
+    LevelDev d{};
+    d.N = L.N; d.Nf = L.Nf; d.bigph = L.bigph;
+    d.ap = L.A.ptr.p; d.ai = L.A.idx.p; d.av = L.A.val.p;
+    d.pp = L.P.ptr.p; d.pi = L.P.idx.p; d.pv = L.P.val.p;
+    d.tp = L.Pt.ptr.p; d.ti = L.Pt.idx.p; d.tv = L.Pt.val.p;
+    d.dinv = L.dinv.p; d.Axi = L.Axi.p; d.xx = L.xx;
+    d.r = L.r.p; d.e = L.e.p; d.g = L.g.p; d.pcg = L.pcg.p;
+    return d;
+}
+
+void smooth_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, int post, bool e_zero) {
+    Level& L = H.lv[k];
+    const LevelDev Ld = level_dev(L);
+    for (int it = 0; it < H.smoth; ++it) {
+        const int np = launch_resid(c, L, L.r, e_zero ? nullptr : L.e.p, L.g, H.part);
+        launch_apply(c, Ld, L, L.g, L.e, H.part, np, isnsp, post, e_zero);
+        e_zero = false;
+    }
+    if (H.smoth == 0 && e_zero) fill_double(c, L.e, L.N, 0.0);
+}
+
+// cycle on level k (0-based): rhs in lv[k].r, correction in lv[k].e
+void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {
+    if (k >= H.small_from || k == H.J - 1) {
+        SSN_REQUIRE(H.J - k <= 16, SSN_E_INVALID, "hierarchy deeper than 16 small levels");
+        SSN_LAUNCH(c, coarse_cycle_kernel, 1, kCycleThreads, 0, H.dev.p, k, H.J, H.smoth, isnsp, wcycle ? 1 : 0, e_zero ? 1 : 0);
+        return;
+    }
+    Level& L = H.lv[k]; Level& Lc = H.lv[k + 1];
+    smooth_host(c, H, k, isnsp, 0, e_zero);
+    launch_resid(c, L, L.r, (e_zero && H.smoth == 0) ? nullptr : L.e.p, L.g, H.part);
+    spmv(c, Lc.Pt, L.g, Lc.r);                                            // MG_Wcycle.m:26
+    cycle_host(c, H, k + 1, isnsp, wcycle, true);                         // :28
+    if (wcycle) cycle_host(c, H, k + 1, isnsp, wcycle, false);            // :30
+    spmv_add(c, Lc.P, Lc.e, L.e);                                         // :32
+    smooth_host(c, H, k, isnsp, 1, false);                                // :34-42
+}
+
+}  // namespace
+
+void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev, bool wcycle, bool e_is_zero) {
+    SSN_REQUIRE(c->hier != nullptr, SSN_E_NO_HIERARCHY, "MG cycle called without a live hierarchy");
+    Hierarchy& H = *c->hier;
+    SSN_REQUIRE(k1 >= 1 && k1 <= H.J, SSN_E_INVALID, "MG cycle: level out of range");
+    Level& L = H.lv[k1 - 1];
+    SSN_CUDA(cudaMemcpyAsync(L.r.p, r_dev, sizeof(double) * L.N, cudaMemcpyDeviceToDevice, c->stream));
+    if (!e_is_zero) SSN_CUDA(cudaMemcpyAsync(L.e.p, e_dev, sizeof(double) * L.N, cudaMemcpyDeviceToDevice, c->stream));
+    cycle_host(c, H, k1 - 1, isnsp, wcycle, e_is_zero);
+    SSN_CUDA(cudaMemcpyAsync(e_dev, L.e.p, sizeof(double) * L.N, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// Class_AMG.m:41-110
+void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, bool keep, double* x, int* it_out,
+               double* rel_res_out, double* rel_resk, double* rhok, int* hist_len) {
+    amg_setup(c, A, o);
+    Hierarchy& H = *c->hier;
+    Level& L = H.lv[0];
+    const int n = L.N;
+    if (o.guess) SSN_CUDA(cudaMemcpyAsync(x, o.guess, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    else fill_double(c, x, n, 0.0);
+    int it = 0;
+    double rel_res = 0.0;
+    std::vector<double> relk(1, 1.0), rho(1, NAN);
+    // r = b - A*x ; res0 = norm(A*x - b)                                 Class_AMG.m:89
+    double h[2];
+    int np = launch_resid(c, L, b, x, L.r, H.part);
+    SSN_LAUNCH(c, reduce_parts_kernel, 1, 256, 0, H.part.p, np, H.scal.p);
+    read_back(c, H.scal.p, h, 2);
+    const double res0 = std::sqrt(h[1]);
+    double res_prev = res0;
+    if (res0 == 0.0) {
+        rel_res = 0.0; relk.assign(1, 0.0); rho.assign(1, INFINITY);
+    } else {
+        it = 1;
+        const bool isv = (o.cycle == 'v'), isw = (o.cycle == 'w');
+        while (relk[it - 1] > o.retol && it <= o.maxit) {                 // Class_AMG.m:95
+            if (isv || isw) {
+                cycle_host(c, H, 0, o.isnsp, isw, true);                  // e = cycle(r)
+                SSN_LAUNCH(c, axpy_kernel, cdiv(n, 256), 256, 0, n, 1.0, L.e.p, x);
+            }
+            np = launch_resid(c, L, b, x, L.r, H.part);                   // next r, and res = norm(A*x-b)
+            SSN_LAUNCH(c, reduce_parts_kernel, 1, 256, 0, H.part.p, np, H.scal.p);
+            read_back(c, H.scal.p, h, 2);
+            const double res = std::sqrt(h[1]);
+            rel_res = res / res0;
+            relk.push_back(rel_res);
+            rho.push_back(res / res_prev);                                // res/norm(r), r = previous residual
+            res_prev = res;
+            ++it;
+            if (rho[it - 1] > 1.0) break;                                 // Class_AMG.m:106
+        }
+        relk.resize(it); rho.resize(it); --it;
+    }
+    if (it_out) *it_out = it;
+    if (rel_res_out) *rel_res_out = rel_res;
+    if (hist_len) *hist_len = (int)relk.size();
+    if (rel_resk) std::memcpy(rel_resk, relk.data(), sizeof(double) * relk.size());
+    if (rhok) std::memcpy(rhok, rho.data(), sizeof(double) * rho.size());
+    if (!keep) amg_clear(c);                                              // Class_AMG.m:110
+}
+
+// PCG.m:18-105
+void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
+               double* res_out, double* resk_host) {
+    SSN_REQUIRE(H.nrows == H.ncols, SSN_E_NOT_SQUARE, "PCG: matrix must be square");
+    const int n = H.nrows;
+    double retol = 1e-11; int maxit = 10000, precd = 2, nf = 0; const double* guess = nullptr;
+    if (opts) {
+        if (!(opts->retol < 0) && opts->retol == opts->retol) retol = opts->retol;
+        if (opts->maxit >= 0) maxit = opts->maxit;
+        if (opts->precd > 0) precd = opts->precd;
+        nf = opts->nf; guess = opts->guess_dev;
+    }
+    SSN_REQUIRE(precd == 1 || precd == 2 || precd == 5, SSN_E_UNSUPPORTED,
+                "PCG: precd 3 (SSOR) and 4 (ichol) are not supported (SURVEY.md 8f)");
+    if (precd == 5) SSN_REQUIRE(nf > 0 && nf < n, SSN_E_PCG_NF, "SSOR for bigraph requires pcg_options.nf!!!");
+    Buf<double> r(c, n), p(c, n), q(c, n), w(c, n), aux(c, n), diag(c, n), resk(c, maxit > 0 ? maxit : 1), scal(c, 2);
+    Buf<int> itd(c, 1);
+    extract_diag(c, H, diag);
+    resk.zero();
+    PcgArgs a{};
+    a.n = n; a.ptr = H.ptr; a.idx = H.idx; a.val = H.val; a.rhs = e; a.guess = guess;
+    a.d = d; a.r = r; a.p = p; a.q = q; a.w = w; a.a = aux; a.diag = diag;
+    a.precd = precd; a.nf = nf; a.maxit = maxit; a.tol2 = retol * retol;
+    a.resk = resk; a.it_out = itd; a.scal_out = scal;
+    int per_sm = 0;
+    SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = c->num_sms * per_sm;
+    const int need = cdiv((int64_t)n * 32, 256);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    Buf<double> part(c, (size_t)3 * grid);
+    a.part = part;
+    void* args[] = {&a};
+    SSN_CUDA(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(256), args, 0, c->stream));
+    c->launches++;
+    int it = read_scalar(c, itd.p);
+    double s[2]; read_back(c, scal.p, s, 2);
+    if (it_out) *it_out = it;
+    if (res_out) *res_out = std::sqrt(std::fabs(s[0] / s[1]));             // PCG.m:87 (0/0 -> NaN)
+    if (resk_host && maxit > 0) read_back(c, resk.p, resk_host, (size_t)maxit);
+}
+
+}  // namespace ssn

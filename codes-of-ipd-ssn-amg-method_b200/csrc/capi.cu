@@ -1,0 +1,310 @@
+// capi.cu -- the extern "C" boundary of libssnamg.so (include/ssnamg.h).  Every entry point
+// converts internal exceptions into status codes; nothing C++ crosses the ABI.
+#include "amg.cuh"
+#include "plan_ops.cuh"
+#include "solvers.cuh"
+
+using namespace ssn;
+
+namespace {
+
+template <class F>
+int guarded(ssn_ctx* ctx, F&& f) {
+    if (!ctx) return SSN_E_INVALID;
+    try {
+        SSN_CUDA(cudaSetDevice(ctx->device));
+        f();
+        return SSN_OK;
+    } catch (const Error& e) {
+        ctx->err = e.msg;
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return SSN_E_INVALID;
+    } catch (...) {
+        ctx->err = "unknown failure";
+        return SSN_E_INVALID;
+    }
+}
+
+void sync(ssn_ctx* c) { SSN_CUDA(cudaStreamSynchronize(c->stream)); }
+
+}  // namespace
+
+extern "C" {
+
+int ssn_version(void) { return 100; }
+
+int ssn_create(ssn_ctx** out, int device) {
+    if (!out) return SSN_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SSN_E_CUDA;   // no CPU fallback
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return SSN_E_CUDA; }
+    if (device >= ndev) return SSN_E_INVALID;
+    ssn_ctx* c = new ssn_ctx();
+    c->device = device;
+    try {
+        SSN_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SSN_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->num_sms = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        cudaMemPool_t pool;
+        SSN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        SSN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        SSN_CUDA(cudaMallocHost((void**)&c->h_pin, sizeof(double) * ssn_ctx::kPinDoubles));
+        SSN_CUDA(cudaMalloc((void**)&c->mt_state, sizeof(uint32_t) * 625));
+        rng_reset(c, 5489u);
+        SSN_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (const Error& e) {
+        fprintf(stderr, "ssn_create: %s\n", e.msg.c_str());
+        delete c;
+        return e.code;
+    }
+    *out = c;
+    return SSN_OK;
+}
+
+int ssn_destroy(ssn_ctx* c) {
+    if (!c) return SSN_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->hier) { delete c->hier; c->hier = nullptr; }
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->mt_state) cudaFree(c->mt_state);
+    delete c;
+    return SSN_OK;
+}
+
+const char* ssn_last_error(ssn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int ssn_set_stream(ssn_ctx* c, void* s) { if (!c) return SSN_E_INVALID; c->stream = (cudaStream_t)s; return SSN_OK; }
+int ssn_synchronize(ssn_ctx* c) { return guarded(c, [&] { sync(c); }); }
+int64_t ssn_launch_count(ssn_ctx* c) { return c ? c->launches : 0; }
+
+int ssn_rng_reset(ssn_ctx* c, uint32_t seed) { return guarded(c, [&] { rng_reset(c, seed); sync(c); }); }
+int64_t ssn_rng_drawn(ssn_ctx* c) { return c ? c->rng_drawn : 0; }
+int ssn_rand(ssn_ctx* c, int64_t count, double* out) { return guarded(c, [&] { rng_rand(c, count, out); sync(c); }); }
+
+int ssn_malloc(ssn_ctx* c, size_t bytes, void** p) {
+    return guarded(c, [&] { SSN_REQUIRE(p, SSN_E_INVALID, "null"); SSN_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, c->stream)); sync(c); });
+}
+int ssn_free(ssn_ctx* c, void* p) { return guarded(c, [&] { if (p) SSN_CUDA(cudaFreeAsync(p, c->stream)); }); }
+int ssn_memcpy_h2d(ssn_ctx* c, void* d, const void* s, size_t b) {
+    return guarded(c, [&] { if (b) SSN_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, c->stream)); sync(c); });
+}
+int ssn_memcpy_d2h(ssn_ctx* c, void* d, const void* s, size_t b) {
+    return guarded(c, [&] { if (b) SSN_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, c->stream)); sync(c); });
+}
+int ssn_csr_free(ssn_ctx* c, ssn_csr* A) {
+    return guarded(c, [&] {
+        if (!A) return;
+        if (A->rowptr_dev) SSN_CUDA(cudaFreeAsync(A->rowptr_dev, c->stream));
+        if (A->colidx_dev) SSN_CUDA(cudaFreeAsync(A->colidx_dev, c->stream));
+        if (A->val_dev) SSN_CUDA(cudaFreeAsync(A->val_dev, c->stream));
+        A->rowptr_dev = nullptr; A->colidx_dev = nullptr; A->val_dev = nullptr; A->nnz = 0;
+    });
+}
+int ssn_csr_upload(ssn_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* rp, const int32_t* ci, const double* v, ssn_csr* out) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(out && rp && nrows >= 0 && ncols >= 0 && nnz >= 0, SSN_E_INVALID, "csr_upload: bad arguments");
+        SSN_REQUIRE(nnz < ((int64_t)1 << 31), SSN_E_TOO_LARGE, "csr_upload: nnz >= 2^31");
+        Csr A; A.c = c; A.nrows = nrows; A.ncols = ncols; A.nnz = nnz;
+        A.ptr.alloc(c, nrows + 1); A.idx.alloc(c, nnz); A.val.alloc(c, nnz);
+        SSN_CUDA(cudaMemcpyAsync(A.ptr.p, rp, sizeof(int) * (nrows + 1), cudaMemcpyHostToDevice, c->stream));
+        if (nnz) {
+            SSN_CUDA(cudaMemcpyAsync(A.idx.p, ci, sizeof(int) * nnz, cudaMemcpyHostToDevice, c->stream));
+            SSN_CUDA(cudaMemcpyAsync(A.val.p, v, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
+        }
+        sync(c);
+        A.release_to(out);
+    });
+}
+int ssn_csr_download(ssn_ctx* c, const ssn_csr* A, int32_t* rp, int32_t* ci, double* v) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A, SSN_E_INVALID, "csr_download: null");
+        if (rp) SSN_CUDA(cudaMemcpyAsync(rp, A->rowptr_dev, sizeof(int) * (A->nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+        if (ci && A->nnz) SSN_CUDA(cudaMemcpyAsync(ci, A->colidx_dev, sizeof(int) * A->nnz, cudaMemcpyDeviceToHost, c->stream));
+        if (v && A->nnz) SSN_CUDA(cudaMemcpyAsync(v, A->val_dev, sizeof(double) * A->nnz, cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+
+// ------------------------------------------------------------------ plan operators
+
+int ssn_ax(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double* y) {
+    return guarded(c, [&] { plan_ax(c, x, p, q, m, n, y); sync(c); });
+}
+int ssn_aty(ssn_ctx* c, const double* y, const double* p, const double* q, int64_t m, int64_t n, double* z) {
+    return guarded(c, [&] { plan_aty(c, y, p, q, m, n, z); sync(c); });
+}
+
+int ssn_ax_host(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double* y) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(x && p && q && y && m > 0 && n > 0, SSN_E_INVALID, "Ax: bad arguments");
+        Buf<double> dx(c, (size_t)m * n), dp(c, m), dq(c, n), dy(c, m + n);
+        SSN_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * m * n, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        plan_ax(c, dx, dp, dq, m, n, dy);
+        SSN_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(double) * (m + n), cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+int ssn_aty_host(ssn_ctx* c, const double* y, const double* p, const double* q, int64_t m, int64_t n, double* z) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(z && p && q && y && m > 0 && n > 0, SSN_E_INVALID, "Aty: bad arguments");
+        Buf<double> dz(c, (size_t)m * n), dp(c, m), dq(c, n), dy(c, m + n);
+        SSN_CUDA(cudaMemcpyAsync(dy.p, y, sizeof(double) * (m + n), cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        plan_aty(c, dy, dp, dq, m, n, dz);
+        SSN_CUDA(cudaMemcpyAsync(z, dz.p, sizeof(double) * m * n, cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+
+int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
+                      double tk, const double* gama, double gama_s, double* axp, double* prox, double* z, uint8_t* s,
+                      double* norm2_out, int64_t* count_out) {
+    return guarded(c, [&] {
+        Buf<double> scal(c, 2);
+        plan_prox_residual(c, w, lam, p, q, m, n, tk, gama, gama_s, axp, prox, z, s, scal);
+        double h[2]; read_back(c, scal.p, h, 2);
+        if (norm2_out) *norm2_out = h[0];
+        if (count_out) *count_out = (int64_t)h[1];
+    });
+}
+
+int ssn_asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, ssn_csr* H) {
+    return guarded(c, [&] { SSN_REQUIRE(H, SSN_E_INVALID, "ASAt: null output"); Csr h = asat(c, s, p, q, m, n); sync(c); h.release_to(H); });
+}
+int ssn_asat_host(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, ssn_csr* H) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(H && s && p && q && m > 0 && n > 0, SSN_E_INVALID, "ASAt: bad arguments");
+        Buf<uint8_t> ds(c, (size_t)m * n); Buf<double> dp(c, m), dq(c, n);
+        SSN_CUDA(cudaMemcpyAsync(ds.p, s, (size_t)m * n, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        Csr h = asat(c, ds, dp, dq, m, n); sync(c); h.release_to(H);
+    });
+}
+int ssn_asatz(ssn_ctx* c, const double* z, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, double* y) {
+    return guarded(c, [&] { asatz(c, z, s, p, q, m, n, y); sync(c); });
+}
+int ssn_invaat(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double sg1, double sg2, double* y) {
+    return guarded(c, [&] { invaat(c, x, p, q, m, n, sg1, sg2, y); sync(c); });
+}
+int ssn_invhht(ssn_ctx* c, const double* v, const double* p, const double* q, int64_t m, int64_t n, double sg, const double* phi, double* y) {
+    return guarded(c, [&] { invhht(c, v, p, q, m, n, sg, phi, y); sync(c); });
+}
+
+// ------------------------------------------------------------------ AMG setup
+
+int ssn_strength(ssn_ctx* c, const ssn_csr* A, int which, ssn_csr* S) {
+    return guarded(c, [&] { SSN_REQUIRE(A && S, SSN_E_INVALID, "strength: null"); Csr s = strength_matrix(c, *A, which == 1 ? 1 : 2); sync(c); s.release_to(S); });
+}
+int ssn_mis_set(ssn_ctx* c, const ssn_csr* A, double theta, uint8_t* isC, uint8_t* isF, ssn_csr* As) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A && isC && isF, SSN_E_INVALID, "mis_set: null");
+        Buf<uint8_t> flags;
+        mis_set(c, *A, theta, isC, isF, flags);
+        if (As) { Csr s = flags_to_csr(c, *A, flags); sync(c); s.release_to(As); }
+        sync(c);
+    });
+}
+int ssn_cf_split(ssn_ctx* c, const ssn_csr* S, uint8_t* indC, uint8_t* indF) {
+    return guarded(c, [&] { SSN_REQUIRE(S && indC && indF, SSN_E_INVALID, "cf_split: null"); cf_split(c, *S, indC, indF); sync(c); });
+}
+int ssn_transfer(ssn_ctx* c, const ssn_csr* A, const ssn_amg_options* opts, int level_J, ssn_csr* Ac, ssn_csr* Pro, ssn_csr* As, uint8_t* indC) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A && Ac && Pro, SSN_E_INVALID, "transfer: null");
+        AmgOptions o;
+        if (opts) o = resolve_options(opts);
+        else { o = resolve_options(nullptr); o.theta = 1.0 / 40; o.bigph = 0; o.inter = 1; o.isnsp = 0; }   // transfer.m:8-15
+        Csr ac, pro; Buf<uint8_t> isC, flags;
+        transfer(c, *A, o, level_J, ac, pro, &isC, As ? &flags : nullptr);
+        if (indC) SSN_CUDA(cudaMemcpyAsync(indC, isC.p, A->nrows, cudaMemcpyDeviceToDevice, c->stream));
+        if (As) { Csr s = flags_to_csr(c, *A, flags); sync(c); s.release_to(As); }
+        sync(c);
+        ac.release_to(Ac); pro.release_to(Pro);
+    });
+}
+int ssn_amg_setup(ssn_ctx* c, const ssn_csr* A, const ssn_amg_options* opts, int* levels) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A, SSN_E_INVALID, "amg_setup: null");
+        amg_setup(c, *A, resolve_options(opts)); sync(c);
+        if (levels) *levels = c->hier->J;
+    });
+}
+int ssn_amg_level(ssn_ctx* c, int k, ssn_csr* A, ssn_csr* Pro) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(c->hier, SSN_E_NO_HIERARCHY, "no live hierarchy");
+        SSN_REQUIRE(k >= 1 && k <= c->hier->J, SSN_E_INVALID, "level out of range");
+        Level& L = c->hier->lv[k - 1];
+        if (A) *A = L.A.view();
+        if (Pro) { if (k > 1) *Pro = L.P.view(); else std::memset(Pro, 0, sizeof(*Pro)); }
+    });
+}
+int ssn_amg_clear(ssn_ctx* c) { return guarded(c, [&] { amg_clear(c); }); }
+
+int ssn_mg_vcycle(ssn_ctx* c, const double* r, int isnsp, int k, double* e) {
+    return guarded(c, [&] { SSN_REQUIRE(r && e, SSN_E_INVALID, "null"); mg_cycle(c, r, isnsp, k, e, false, true); sync(c); });
+}
+int ssn_mg_wcycle(ssn_ctx* c, const double* r, int isnsp, int k, double* e) {
+    return guarded(c, [&] { SSN_REQUIRE(r && e, SSN_E_INVALID, "null"); mg_cycle(c, r, isnsp, k, e, true, false); sync(c); });
+}
+int ssn_class_amg(ssn_ctx* c, const ssn_csr* A, const double* b, const ssn_amg_options* opts, int keep, double* x, int* it,
+                  double* rel_res, double* rel_resk, double* rhok, int* hist_len) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A && b && x, SSN_E_INVALID, "Class_AMG: null");
+        class_amg(c, *A, b, resolve_options(opts), keep != 0, x, it, rel_res, rel_resk, rhok, hist_len); sync(c);
+    });
+}
+int ssn_pcg(ssn_ctx* c, const ssn_csr* H, const double* e, const ssn_pcg_options* opts, double* d, int* it, double* res, double* resk) {
+    return guarded(c, [&] { SSN_REQUIRE(H && e && d, SSN_E_INVALID, "PCG: null"); pcg_solve(c, *H, e, opts, d, it, res, resk); sync(c); });
+}
+
+// ------------------------------------------------------------------ dispatch
+
+int ssn_components(ssn_ctx* c, const ssn_csr* A, int32_t* blocks, int32_t* sizes, int32_t* p, int32_t* r, int* ncomp) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A && blocks && sizes && p && r, SSN_E_INVALID, "components: null");
+        components(c, *A, blocks, sizes, p, r, ncomp); sync(c);
+    });
+}
+int ssn_hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info) {
+    return guarded(c, [&] { hybrid_amg(c, pd, opts, zeta, it, res, info); });
+}
+int ssn_aug_pcg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* it, double* res, int* info) {
+    return guarded(c, [&] { aug_pcg(c, pd, opts, zeta, it, res, info); });
+}
+int ssn_amg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info) {
+    return guarded(c, [&] { amg4pot(c, pd, opts, zeta, it, res, info); });
+}
+int ssn_pcg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* it, double* res, int* info) {
+    return guarded(c, [&] { pcg4pot(c, pd, opts, zeta, it, res, info); });
+}
+int ssn_rescaled_system(ssn_ctx* c, const ssn_prob_data* pd, ssn_csr* Ae, double* f) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(Ae, SSN_E_INVALID, "rescaled_system: null");
+        Csr ae; Buf<double> qp, Kd;
+        rescaled_system(c, pd, ae, f, qp, Kd); sync(c); ae.release_to(Ae);
+    });
+}
+
+// ------------------------------------------------------------------ sparse utilities
+
+int ssn_spmv(ssn_ctx* c, const ssn_csr* A, const double* x, double* y) {
+    return guarded(c, [&] { SSN_REQUIRE(A && x && y, SSN_E_INVALID, "spmv: null"); spmv(c, *A, x, y); sync(c); });
+}
+int ssn_spgemm(ssn_ctx* c, const ssn_csr* A, const ssn_csr* B, ssn_csr* C) {
+    return guarded(c, [&] { SSN_REQUIRE(A && B && C, SSN_E_INVALID, "spgemm: null"); Csr r = spgemm(c, *A, *B); sync(c); r.release_to(C); });
+}
+int ssn_transpose(ssn_ctx* c, const ssn_csr* A, ssn_csr* At) {
+    return guarded(c, [&] { SSN_REQUIRE(A && At, SSN_E_INVALID, "transpose: null"); Csr r = transpose(c, *A); sync(c); r.release_to(At); });
+}
+
+}  // extern "C"

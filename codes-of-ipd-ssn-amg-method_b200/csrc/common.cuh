@@ -1,0 +1,185 @@
+// common.cuh -- context, error handling, stream-ordered device buffers and small device
+// helpers shared by every translation unit of libssnamg.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <memory>
+#include <stdexcept>
+
+#include "../../include/ssnamg.h"
+
+namespace ssn {
+
+struct Error : std::exception {
+    int code; std::string msg;
+    Error(int c, std::string m) : code(c), msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define SSN_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            throw ::ssn::Error(SSN_E_CUDA, std::string(#call) + ": " +                     \
+                               cudaGetErrorString(e__) + " (" + __FILE__ + ":" +           \
+                               std::to_string(__LINE__) + ")");                            \
+    } while (0)
+
+#define SSN_REQUIRE(cond, code, text)                                                      \
+    do { if (!(cond)) throw ::ssn::Error((code), (text)); } while (0)
+
+struct Hierarchy;   // amg.cuh
+
+}  // namespace ssn
+
+// The opaque context of the C ABI.
+struct ssn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    // pinned host scratch for scalar read-backs
+    double* h_pin = nullptr;              // 4096 doubles
+    static constexpr int kPinDoubles = 4096;
+    // MATLAB random stream (device-resident MT19937 state)
+    uint32_t* mt_state = nullptr;         // 624 words + 1 index word
+    int64_t rng_drawn = 0;
+    // Class_AMG hierarchy (the reference's globals Ack/Prok/Rk/J/smoth_it)
+    ssn::Hierarchy* hier = nullptr;
+};
+
+namespace ssn {
+
+// Stream-ordered device buffer (cudaMallocAsync pool; frees are stream-ordered too).
+template <class T>
+struct Buf {
+    ssn_ctx* c = nullptr; T* p = nullptr; size_t n = 0;
+    Buf() = default;
+    Buf(ssn_ctx* ctx, size_t count) { alloc(ctx, count); }
+    Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete;
+    Buf(Buf&& o) noexcept : c(o.c), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    Buf& operator=(Buf&& o) noexcept {
+        if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~Buf() { reset(); }
+    void alloc(ssn_ctx* ctx, size_t count) {
+        reset(); c = ctx; n = count;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        SSN_CUDA(cudaMallocAsync((void**)&p, bytes, ctx->stream));
+    }
+    void reset() {
+        if (p) { cudaFreeAsync(p, c->stream); p = nullptr; n = 0; }
+    }
+    T* release() { T* r = p; p = nullptr; n = 0; return r; }
+    void zero() { SSN_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), c->stream)); }
+    operator T*() const { return p; }
+    T* get() const { return p; }
+};
+
+// Owning device CSR (internal); converts to / from the ABI's ssn_csr.
+struct Csr {
+    ssn_ctx* c = nullptr;
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    Buf<int> ptr; Buf<int> idx; Buf<double> val;
+    Csr() = default;
+    Csr(Csr&&) = default; Csr& operator=(Csr&&) = default;
+    ssn_csr view() const {
+        ssn_csr v; v.nrows = nrows; v.ncols = ncols; v.nnz = nnz;
+        v.rowptr_dev = ptr.p; v.colidx_dev = idx.p; v.val_dev = val.p; return v;
+    }
+    // hand the arrays over to the ABI struct (caller frees with ssn_csr_free)
+    void release_to(ssn_csr* out) {
+        out->nrows = nrows; out->ncols = ncols; out->nnz = nnz;
+        out->rowptr_dev = ptr.release(); out->colidx_dev = idx.release(); out->val_dev = val.release();
+    }
+};
+
+// Non-owning view used by kernels and internal functions.
+struct CsrView {
+    int nrows = 0, ncols = 0; int64_t nnz = 0;
+    const int* ptr = nullptr; const int* idx = nullptr; const double* val = nullptr;
+    CsrView() = default;
+    CsrView(const ssn_csr& a) : nrows((int)a.nrows), ncols((int)a.ncols), nnz(a.nnz),
+        ptr(a.rowptr_dev), idx(a.colidx_dev), val(a.val_dev) {}
+    CsrView(const Csr& a) : nrows((int)a.nrows), ncols((int)a.ncols), nnz(a.nnz),
+        ptr(a.ptr.p), idx(a.idx.p), val(a.val.p) {}
+};
+
+inline void check_launch(ssn_ctx* c, const char* what) {
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        throw Error(SSN_E_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+
+#define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...)                                    \
+    do {                                                                                   \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                   \
+        ::ssn::check_launch((ctx), #kernel);                                               \
+    } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// read `count` elements (<= pinned scratch) back to the host, synchronously
+template <class T>
+inline void read_back(ssn_ctx* c, const T* dev, T* host, size_t count) {
+    size_t bytes = count * sizeof(T);
+    if (bytes <= sizeof(double) * ssn_ctx::kPinDoubles) {
+        SSN_CUDA(cudaMemcpyAsync(c->h_pin, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(host, c->h_pin, bytes);
+    } else {
+        SSN_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaStreamSynchronize(c->stream));
+    }
+}
+template <class T>
+inline T read_scalar(ssn_ctx* c, const T* dev) { T v; read_back(c, dev, &v, 1); return v; }
+
+// ---- scans / sorts (CUB plumbing, sparse.cu) ----
+void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n);   // out[n] = total if out has n+1: see impl
+// out has n+1 entries: out[0]=0, out[i+1]=sum_{k<=i} in[k]; returns total (host, synchronises)
+int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
+// stable sort of (key,value) int pairs by key, keys < key_limit
+void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int* vals_in,
+                       int* vals_out, int64_t n, int key_limit);
+
+// ---- device helpers ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum, result valid in thread 0 (and broadcast through smem to all); blockDim <= 1024
+__device__ __forceinline__ double block_sum(double v, double* smem32) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (lane < nw) ? smem32[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) smem32[0] = t;
+    }
+    __syncthreads();
+    t = smem32[0];
+    return t;
+}
+
+}  // namespace ssn

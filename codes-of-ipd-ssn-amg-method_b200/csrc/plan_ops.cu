@@ -1,0 +1,442 @@
+// plan_ops.cu -- plan-wide (m x n, column-major, fp64) kernels: Ax, Aty, the fused SsN
+// residual, and the active-set compaction that feeds ASAt.  All are HBM-bound streaming
+// kernels: 128-bit loads/stores with streaming cache hints, >= 8 independent 16-byte
+// requests in flight per lane, deterministic (atomic-free) two-stage reductions.
+//
+// Tiling of the reduction kernels (Ax, fused residual):
+//   a block of 8 warps owns a "group" of 8 strips x 128 rows = 1024 rows and a chunk of
+//   <= 512 columns; warp w owns strip w.  A lane holds 4 rows (two double2) of 4 columns per
+//   iteration.  Row sums stay in registers for the whole chunk; column partials are reduced
+//   over the warp with a 4-value transposing butterfly (6 shuffles per 4 columns) and parked
+//   in shared memory until the block combines its 8 strips.  Partials go to
+//   rowpart[chunk][m] / colpart[group][n]; a tiny finish kernel sums them in fixed order.
+#include "common.cuh"
+#include "plan_ops.cuh"
+
+namespace ssn {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kStripRows = 128;
+constexpr int kGroupRows = kWarps * kStripRows;   // 1024
+constexpr int kMaxChunkCols = 512;
+
+struct PlanArgs {
+    const double* x;        // MODE_AX: x ; MODE_PROX: w
+    const double* p;
+    const double* q;
+    const double* lam;      // MODE_PROX: [y1 (n) ; y2 (m)]
+    const double* gama;     // optional per-entry upper bound
+    double gama_s;
+    double inv_tk;
+    int64_t m, n;
+    int cols_per_chunk, num_chunks, num_groups;
+    double* rowpart;        // [num_chunks][m]
+    double* colpart;        // [num_groups][n]
+    double* scalpart;       // [num_blocks][2]  (norm2, count)
+    double* prox_out;
+    double* z_out;
+    uint8_t* s_out;
+    int want_sums;          // row/col sums wanted
+};
+
+enum { MODE_AX = 0, MODE_PROX = 1 };
+
+// Reduce 4 per-lane values over the warp.  On return the lanes with (lane & 7) == 0 hold the
+// full sum of value number  idx = 2*bit4(lane) + bit3(lane).
+__device__ __forceinline__ double butterfly4(double v0, double v1, double v2, double v3, int lane) {
+    const bool hi = lane & 16;
+    double a0 = hi ? v2 : v0, s0 = hi ? v0 : v2;
+    double a1 = hi ? v3 : v1, s1 = hi ? v1 : v3;
+    a0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    a1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool mid = lane & 8;
+    double b = mid ? a1 : a0, sb = mid ? a0 : a1;
+    b += __shfl_xor_sync(0xffffffffu, sb, 8);
+    b += __shfl_xor_sync(0xffffffffu, b, 4);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    return b;
+}
+
+template <int MODE, bool VEC, bool GVEC>
+__global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs a) {
+    extern __shared__ double colbuf[];                 // [kWarps][cols_per_chunk]
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int64_t m = a.m, n = a.n;
+    const int cpc = a.cols_per_chunk;
+    const int64_t c0 = (int64_t)chunk * cpc;
+    const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
+    const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
+
+    int64_t row[4]; bool rok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        row[k] = VEC ? (rbase + 64 * (k >> 1) + 2 * lane + (k & 1)) : (rbase + 32 * k + lane);
+        rok[k] = row[k] < m;
+    }
+    double pv[4], y2v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pv[k] = rok[k] ? a.p[row[k]] : 0.0;
+        y2v[k] = (MODE == MODE_PROX && rok[k]) ? a.lam[n + row[k]] : 0.0;
+    }
+    double rs[4] = {0.0, 0.0, 0.0, 0.0};
+    double n2 = 0.0;
+    int cnt = 0;
+    constexpr bool has_gvec = (MODE == MODE_PROX) && GVEC;
+
+    for (int64_t c = c0; c < c1; c += 4) {
+        double v[4][4];
+        double g[GVEC ? 4 : 1][4];
+        // ---- issue all loads of this 4-column batch first (8 x 16 B per lane in flight)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int64_t col = c + cc;
+            const bool cok = col < c1;
+            const double* base = a.x + (size_t)col * (size_t)m;
+            if (VEC) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double2 t = make_double2(0.0, 0.0);
+                    if (cok && rok[2 * h]) t = __ldcs(reinterpret_cast<const double2*>(base + row[2 * h]));
+                    v[cc][2 * h] = t.x; v[cc][2 * h + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[cc][k] = (cok && rok[k]) ? __ldcs(base + row[k]) : 0.0;
+            }
+            if (has_gvec) {
+                const double* gb = a.gama + (size_t)col * (size_t)m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[GVEC ? cc : 0][k] = (cok && rok[k]) ? __ldcs(gb + row[k]) : 0.0;
+            }
+        }
+        double cs[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int64_t col = c + cc;
+            const bool cok = col < c1;
+            const double qj = cok ? __ldg(a.q + col) : 0.0;
+            double csum = 0.0;
+            if (MODE == MODE_AX) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    csum = fma(v[cc][k], pv[k], csum);
+                    rs[k] = fma(v[cc][k], qj, rs[k]);
+                }
+            } else {
+                const double y1j = cok ? __ldg(a.lam + col) : 0.0;
+                double px[4], zz[4]; unsigned char sb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // z = (1/tk) * (w - (p_i*y1_j + y2_i*q_j)), rounded like the reference
+                    // expression `1/tk*(wk-Aty(lk,p,q))` (mul, mul, add, sub, mul; no FMA).
+                    const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                    const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
+                    const double gm = has_gvec ? g[GVEC ? cc : 0][k] : a.gama_s;
+                    const bool live = cok && rok[k];
+                    const bool act = live && (z >= 0.0) && (z <= gm);
+                    double pz = fmin(fmax(0.0, z), gm);
+                    pz = live ? pz : 0.0;
+                    px[k] = pz; zz[k] = z; sb[k] = act ? 1 : 0;
+                    cnt += act ? 1 : 0;
+                    n2 = fma(pz, pz, n2);
+                    csum = fma(pz, pv[k], csum);
+                    rs[k] = fma(pz, qj, rs[k]);
+                }
+                if (cok) {
+                    const size_t off = (size_t)col * (size_t)m;
+                    if (VEC) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (rok[2 * h]) {
+                                if (a.prox_out) __stcs(reinterpret_cast<double2*>(a.prox_out + off + row[2 * h]),
+                                                       make_double2(px[2 * h], px[2 * h + 1]));
+                                if (a.z_out) __stcs(reinterpret_cast<double2*>(a.z_out + off + row[2 * h]),
+                                                    make_double2(zz[2 * h], zz[2 * h + 1]));
+                                if (a.s_out) *reinterpret_cast<uchar2*>(a.s_out + off + row[2 * h]) =
+                                                 make_uchar2(sb[2 * h], sb[2 * h + 1]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (rok[k]) {
+                                if (a.prox_out) a.prox_out[off + row[k]] = px[k];
+                                if (a.z_out) a.z_out[off + row[k]] = zz[k];
+                                if (a.s_out) a.s_out[off + row[k]] = sb[k];
+                            }
+                        }
+                    }
+                }
+            }
+            cs[cc] = csum;
+        }
+        if (a.want_sums) {
+            const double tot = butterfly4(cs[0], cs[1], cs[2], cs[3], lane);
+            const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+            if ((lane & 7) == 0 && (c + idx) < c1) colbuf[warp * cpc + (int)(c - c0) + idx] = tot;
+        }
+    }
+    if (a.want_sums) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (rok[k]) a.rowpart[(size_t)chunk * (size_t)m + row[k]] = rs[k];
+        __syncthreads();
+        const int ncols = (int)(c1 - c0);
+        for (int j = threadIdx.x; j < ncols; j += kThreads) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += colbuf[w * cpc + j];
+            a.colpart[(size_t)group * (size_t)n + c0 + j] = s;
+        }
+    }
+    if (MODE == MODE_PROX) {
+        const double t2 = block_sum(n2, red);
+        const double tc = block_sum((double)cnt, red);
+        if (threadIdx.x == 0) {
+            const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            a.scalpart[2 * b] = t2; a.scalpart[2 * b + 1] = tc;
+        }
+    }
+}
+
+// y[0:n] = sum_g colpart[g][j] ; y[n:n+m] = sum_c rowpart[c][i] ; scal_out = sum of scalparts
+__global__ void plan_finish_kernel(const double* __restrict__ rowpart, const double* __restrict__ colpart,
+                                   const double* __restrict__ scalpart, int num_chunks, int num_groups,
+                                   int64_t m, int64_t n, int num_blocks, double* __restrict__ y,
+                                   double* __restrict__ scal_out) {
+    __shared__ double red[32];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y != nullptr) {
+        if (gid < n) {
+            double s = 0.0;
+            for (int g = 0; g < num_groups; ++g) s += colpart[(size_t)g * n + gid];
+            y[gid] = s;
+        } else if (gid < n + m) {
+            const int64_t i = gid - n;
+            double s = 0.0;
+            for (int c = 0; c < num_chunks; ++c) s += rowpart[(size_t)c * m + i];
+            y[gid] = s;
+        }
+    }
+    if (scal_out != nullptr && blockIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) { s0 += scalpart[2 * b]; s1 += scalpart[2 * b + 1]; }
+        s0 = block_sum(s0, red);
+        s1 = block_sum(s1, red);
+        if (threadIdx.x == 0) { scal_out[0] = s0; scal_out[1] = s1; }
+    }
+}
+
+struct Tiling { int groups, chunks, cpc; };
+
+Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n) {
+    Tiling t;
+    t.groups = cdiv(m, kGroupRows);
+    const int64_t target = (int64_t)c->num_sms * 2 * 2;          // two waves at 2 blocks / SM
+    int64_t chunks = target / t.groups; if (chunks < 1) chunks = 1;
+    int64_t cpc = (n + chunks - 1) / chunks;
+    cpc = ((cpc + 3) / 4) * 4;
+    if (cpc > kMaxChunkCols) cpc = kMaxChunkCols;
+    if (cpc < 4) cpc = 4;
+    t.cpc = (int)cpc;
+    t.chunks = cdiv(n, cpc);
+    return t;
+}
+
+inline bool vec_ok(const void* ptr, int64_t m) {
+    return (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
+}
+
+// ------------------------------------------------------------------ Aty
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) aty_kernel(const double* __restrict__ y, const double* __restrict__ p,
+                                                          const double* __restrict__ q, int64_t m, int64_t n,
+                                                          int cpc, double* __restrict__ z) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * cpc;
+    const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
+    const int64_t rbase = ((int64_t)blockIdx.y * kWarps + warp) * kStripRows;
+    int64_t row[4]; bool rok[4]; double pv[4], y2v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        row[k] = VEC ? (rbase + 64 * (k >> 1) + 2 * lane + (k & 1)) : (rbase + 32 * k + lane);
+        rok[k] = row[k] < m;
+        pv[k] = rok[k] ? p[row[k]] : 0.0;
+        y2v[k] = rok[k] ? y[n + row[k]] : 0.0;
+    }
+    if (!rok[0]) return;                                   // whole lane beyond the slab
+    for (int64_t c = c0; c < c1; ++c) {
+        const double y1j = __ldg(y + c), qj = __ldg(q + c);
+        double o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                       // Aty.m:12-13: p*y1' , y2*q' , add
+            o[k] = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+        double* base = z + (size_t)c * (size_t)m;
+        if (VEC) {
+            __stcs(reinterpret_cast<double2*>(base + row[0]), make_double2(o[0], o[1]));
+            if (rok[2]) __stcs(reinterpret_cast<double2*>(base + row[2]), make_double2(o[2], o[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (rok[k]) __stcs(base + row[k], o[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ active-set compaction
+// One warp per column.  Pass 1 counts the active rows of each column, pass 2 (after a scan)
+// writes them in ascending row order with ballot-free packed-mask prefix sums.
+template <bool VEC16>
+__device__ __forceinline__ unsigned load_mask16(const uint8_t* col, int64_t i0, int64_t m) {
+    unsigned mask = 0;
+    if (VEC16) {
+        if (i0 + 16 <= m) {
+            const uint4 t = __ldcs(reinterpret_cast<const uint4*>(col + i0));
+            const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if ((w[k] >> (8 * b)) & 0xffu) mask |= 1u << (4 * k + b);
+            }
+            return mask;
+        }
+    }
+#pragma unroll 4
+    for (int b = 0; b < 16; ++b)
+        if (i0 + b < m && col[i0 + b]) mask |= 1u << b;
+    return mask;
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(256) active_count_kernel(const uint8_t* __restrict__ s, int64_t m, int64_t n,
+                                                           int* __restrict__ colcount) {
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= n) return;
+    const uint8_t* cp = s + (size_t)col * (size_t)m;
+    int cnt = 0;
+    for (int64_t i0 = (int64_t)lane * 16; i0 < m; i0 += 512) cnt += __popc(load_mask16<VEC16>(cp, i0, m));
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) colcount[col] = cnt;
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(256) active_fill_kernel(const uint8_t* __restrict__ s, int64_t m, int64_t n,
+                                                          const int* __restrict__ colptr, int* __restrict__ yrow,
+                                                          int* __restrict__ ycol, int* __restrict__ rowcount) {
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col >= n) return;
+    const uint8_t* cp = s + (size_t)col * (size_t)m;
+    int base = colptr[col];
+    for (int64_t w0 = 0; w0 < m; w0 += 512) {
+        const int64_t i0 = w0 + (int64_t)lane * 16;
+        const unsigned mask = (i0 < m) ? load_mask16<VEC16>(cp, i0, m) : 0u;
+        const int mine = __popc(mask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int pos = base + incl - mine;
+        unsigned mm = mask;
+        while (mm) {
+            const int b = __ffs(mm) - 1; mm &= mm - 1;
+            const int r = (int)(i0 + b);
+            yrow[pos] = r; ycol[pos] = (int)col;
+            atomicAdd(rowcount + r, 1);
+            ++pos;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+}  // namespace
+
+// =================================================================== host entry points
+
+void plan_ax(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double* y) {
+    SSN_REQUIRE(m > 0 && n > 0 && x && p && q && y, SSN_E_INVALID, "Ax: bad arguments");
+    const Tiling t = plan_tiling(c, m, n);
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n);
+    PlanArgs a{};
+    a.x = x; a.p = p; a.q = q; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart; a.colpart = colpart; a.want_sums = 1;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    if (vec_ok(x, m)) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, true, false>), grid, kThreads, smem, a);
+    else              SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, false, false>), grid, kThreads, smem, a);
+    SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, nullptr, t.chunks,
+               t.groups, m, n, 0, y, nullptr);
+}
+
+void plan_aty(ssn_ctx* c, const double* y, const double* p, const double* q, int64_t m, int64_t n, double* z) {
+    SSN_REQUIRE(m > 0 && n > 0 && y && p && q && z, SSN_E_INVALID, "Aty: bad arguments");
+    const Tiling t = plan_tiling(c, m, n);
+    const dim3 grid(t.chunks, t.groups);
+    if (vec_ok(z, m)) SSN_LAUNCH(c, (aty_kernel<true>), grid, kThreads, 0, y, p, q, m, n, t.cpc, z);
+    else              SSN_LAUNCH(c, (aty_kernel<false>), grid, kThreads, 0, y, p, q, m, n, t.cpc, z);
+}
+
+void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q,
+                        int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* axp_out,
+                        double* prox_out, double* z_out, uint8_t* s_out, double* scal2_dev) {
+    SSN_REQUIRE(m > 0 && n > 0 && w && lam && p && q, SSN_E_INVALID, "prox_residual: bad arguments");
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> rowpart, colpart, scalpart(c, (size_t)2 * nblocks);
+    if (axp_out) { rowpart.alloc(c, (size_t)t.chunks * m); colpart.alloc(c, (size_t)t.groups * n); }
+    PlanArgs a{};
+    a.x = w; a.p = p; a.q = q; a.lam = lam; a.gama = gama; a.gama_s = gama_s; a.inv_tk = 1.0 / tk;
+    a.m = m; a.n = n; a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart.p; a.colpart = colpart.p; a.scalpart = scalpart.p;
+    a.prox_out = prox_out; a.z_out = z_out; a.s_out = s_out; a.want_sums = axp_out ? 1 : 0;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    bool vec = vec_ok(w, m) && (!gama || vec_ok(gama, m)) && (!prox_out || vec_ok(prox_out, m)) &&
+               (!z_out || vec_ok(z_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
+    if (gama) {
+        if (vec) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, true, true>), grid, kThreads, smem, a);
+        else     SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, false, true>), grid, kThreads, smem, a);
+    } else {
+        if (vec) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, true, false>), grid, kThreads, smem, a);
+        else     SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, false, false>), grid, kThreads, smem, a);
+    }
+    SSN_LAUNCH(c, plan_finish_kernel, axp_out ? cdiv(m + n, 256) : 1, 256, 0, rowpart.p, colpart.p, scalpart.p,
+               t.chunks, t.groups, m, n, nblocks, axp_out, scal2_dev);
+}
+
+// Y = sparse(reshape(s,m,n)) as two sorted coordinate lists (ASAt.m:15):
+//   CSC: colptr[n+1], yrow[E] (rows ascending inside a column), ycol[E]
+//   row counts rowcount[m] (for the CSR built by the caller with a stable sort by row)
+int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
+                        Buf<int>& ycol, Buf<int>& rowcount) {
+    SSN_REQUIRE(m > 0 && n > 0 && s, SSN_E_INVALID, "active set: bad arguments");
+    SSN_REQUIRE(m < (int64_t)1 << 31 && n < (int64_t)1 << 31, SSN_E_TOO_LARGE, "active set: m or n >= 2^31");
+    Buf<int> colcount(c, n);
+    colptr.alloc(c, n + 1);
+    rowcount.alloc(c, m); rowcount.zero();
+    const bool v16 = (m % 16 == 0) && ((reinterpret_cast<uintptr_t>(s) & 15u) == 0);
+    const int grid = cdiv(n, 8);
+    if (v16) SSN_LAUNCH(c, (active_count_kernel<true>), grid, 256, 0, s, m, n, colcount.p);
+    else     SSN_LAUNCH(c, (active_count_kernel<false>), grid, 256, 0, s, m, n, colcount.p);
+    const int64_t E = scan_counts_to_ptr(c, colcount, colptr, n);
+    SSN_REQUIRE(E < ((int64_t)1 << 30), SSN_E_TOO_LARGE, "active set: nnz(s) >= 2^30");
+    yrow.alloc(c, E); ycol.alloc(c, E);
+    if (E > 0) {
+        if (v16) SSN_LAUNCH(c, (active_fill_kernel<true>), grid, 256, 0, s, m, n, colptr.p, yrow.p, ycol.p, rowcount.p);
+        else     SSN_LAUNCH(c, (active_fill_kernel<false>), grid, 256, 0, s, m, n, colptr.p, yrow.p, ycol.p, rowcount.p);
+    }
+    return E;
+}
+
+}  // namespace ssn

@@ -1,0 +1,12 @@
+// solvers.cuh -- internal interface of solvers.cu
+#pragma once
+#include "common.cuh"
+#include "sparse.cuh"
+namespace ssn {
+Csr asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n);
+void asatz(ssn_ctx* c, const double* z, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, double* y);
+void invaat(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double sg1, double sg2, double* y);
+void invhht(ssn_ctx* c, const double* v, const double* p, const double* q, int64_t m, int64_t n, double sg, const double* phi, double* y);
+void amg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info);
+void pcg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* it, double* res, int* info);
+}  // namespace ssn

@@ -1,0 +1,520 @@
+// sparse.cu -- CSR building blocks: scans / stable sorts (CUB plumbing), SpMV, deterministic
+// transpose, fixed-order SpGEMM with shared-memory dense-window accumulators, sparse add,
+// principal-submatrix extraction and deterministic reductions.
+#include "sparse.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+
+namespace ssn {
+
+// ------------------------------------------------------------------ scans / sorts
+
+int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
+    SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream));
+    if (n == 0) return 0;
+    size_t tmp_bytes = 0;
+    SSN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
+    Buf<unsigned char> tmp(c, tmp_bytes);
+    SSN_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
+    c->launches++;
+    return (int64_t)read_scalar(c, ptr + n);
+}
+
+void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n) {
+    if (n == 0) return;
+    size_t tmp_bytes = 0;
+    SSN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, c->stream));
+    Buf<unsigned char> tmp(c, tmp_bytes);
+    SSN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, c->stream));
+    c->launches++;
+}
+
+void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int* vals_in, int* vals_out,
+                       int64_t n, int key_limit) {
+    if (n == 0) return;
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < (long long)key_limit) ++bits;
+    size_t tmp_bytes = 0;
+    SSN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
+                                             bits, c->stream));
+    Buf<unsigned char> tmp(c, tmp_bytes);
+    SSN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
+                                             bits, c->stream));
+    c->launches += 3;
+}
+
+// ------------------------------------------------------------------ small helpers
+
+namespace {
+
+__global__ void fill_double_kernel(double* p, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_int_kernel(int* p, int64_t n, int v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void iota_kernel(int* p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int)i;
+}
+inline int grid_for(int64_t n, int block = 256, int cap = 148 * 16) {
+    int64_t g = (n + block - 1) / block; if (g < 1) g = 1; if (g > cap) g = cap; return (int)g;
+}
+
+constexpr int kRedBlocks = 296;
+template <int MODE>   // 0 sum, 1 dot
+__global__ void __launch_bounds__(256) reduce_stage1(const double* __restrict__ x, const double* __restrict__ y,
+                                                     int64_t n, double* __restrict__ part) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += (MODE == 0) ? x[i] : x[i] * y[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) reduce_stage2(const double* __restrict__ part, int np, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s += part[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+__global__ void __launch_bounds__(256) count_u8_stage1(const uint8_t* __restrict__ x, int64_t n, double* __restrict__ part) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += x[i] ? 1.0 : 0.0;
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+}  // namespace
+
+void fill_double(ssn_ctx* c, double* p, int64_t n, double v) { if (n > 0) SSN_LAUNCH(c, fill_double_kernel, grid_for(n), 256, 0, p, n, v); }
+void fill_int(ssn_ctx* c, int* p, int64_t n, int v) { if (n > 0) SSN_LAUNCH(c, fill_int_kernel, grid_for(n), 256, 0, p, n, v); }
+void iota_int(ssn_ctx* c, int* p, int64_t n) { if (n > 0) SSN_LAUNCH(c, iota_kernel, grid_for(n), 256, 0, p, n); }
+
+double dev_sum(ssn_ctx* c, const double* x, int64_t n) {
+    if (n <= 0) return 0.0;
+    Buf<double> part(c, kRedBlocks + 1);
+    const int g = grid_for(n, 256, kRedBlocks);
+    SSN_LAUNCH(c, reduce_stage1<0>, g, 256, 0, x, nullptr, n, part.p);
+    SSN_LAUNCH(c, reduce_stage2, 1, 256, 0, part.p, g, part.p + kRedBlocks);
+    return read_scalar(c, part.p + kRedBlocks);
+}
+double dev_dot(ssn_ctx* c, const double* x, const double* y, int64_t n) {
+    if (n <= 0) return 0.0;
+    Buf<double> part(c, kRedBlocks + 1);
+    const int g = grid_for(n, 256, kRedBlocks);
+    SSN_LAUNCH(c, reduce_stage1<1>, g, 256, 0, x, y, n, part.p);
+    SSN_LAUNCH(c, reduce_stage2, 1, 256, 0, part.p, g, part.p + kRedBlocks);
+    return read_scalar(c, part.p + kRedBlocks);
+}
+int64_t dev_count_nonzero_u8(ssn_ctx* c, const uint8_t* x, int64_t n) {
+    if (n <= 0) return 0;
+    Buf<double> part(c, kRedBlocks + 1);
+    const int g = grid_for(n, 256, kRedBlocks);
+    SSN_LAUNCH(c, count_u8_stage1, g, 256, 0, x, n, part.p);
+    SSN_LAUNCH(c, reduce_stage2, 1, 256, 0, part.p, g, part.p + kRedBlocks);
+    return (int64_t)read_scalar(c, part.p + kRedBlocks);
+}
+
+// ------------------------------------------------------------------ SpMV
+
+namespace {
+
+template <int TPR, bool ADD>
+__global__ void __launch_bounds__(256) spmv_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                   const double* __restrict__ val, const double* __restrict__ x,
+                                                   double* __restrict__ y) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gt / TPR, sub = gt % TPR;
+    double s = 0.0;
+    if (row < nrows) {
+        const int e1 = ptr[row + 1];
+        for (int e = ptr[row] + sub; e < e1; e += TPR) s = fma(val[e], x[idx[e]], s);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (row < nrows && sub == 0) y[row] = ADD ? (y[row] + s) : s;
+}
+
+template <bool ADD>
+void spmv_dispatch(ssn_ctx* c, const CsrView& A, const double* x, double* y) {
+    if (A.nrows == 0) return;
+    const double avg = (double)A.nnz / (double)A.nrows;
+    const int n = A.nrows;
+    if (avg <= 3.0)       SSN_LAUNCH(c, (spmv_kernel<2, ADD>), cdiv((int64_t)n * 2, 256), 256, 0, n, A.ptr, A.idx, A.val, x, y);
+    else if (avg <= 6.0)  SSN_LAUNCH(c, (spmv_kernel<4, ADD>), cdiv((int64_t)n * 4, 256), 256, 0, n, A.ptr, A.idx, A.val, x, y);
+    else if (avg <= 12.0) SSN_LAUNCH(c, (spmv_kernel<8, ADD>), cdiv((int64_t)n * 8, 256), 256, 0, n, A.ptr, A.idx, A.val, x, y);
+    else if (avg <= 24.0) SSN_LAUNCH(c, (spmv_kernel<16, ADD>), cdiv((int64_t)n * 16, 256), 256, 0, n, A.ptr, A.idx, A.val, x, y);
+    else                  SSN_LAUNCH(c, (spmv_kernel<32, ADD>), cdiv((int64_t)n * 32, 256), 256, 0, n, A.ptr, A.idx, A.val, x, y);
+}
+
+}  // namespace
+
+void spmv(ssn_ctx* c, const CsrView& A, const double* x, double* y) { spmv_dispatch<false>(c, A, x, y); }
+void spmv_add(ssn_ctx* c, const CsrView& A, const double* x, double* y) { spmv_dispatch<true>(c, A, x, y); }
+
+// ------------------------------------------------------------------ structure helpers
+
+namespace {
+
+__global__ void expand_rows_kernel(int nrows, const int* __restrict__ ptr, int* __restrict__ rowidx) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nrows) return;
+    for (int e = ptr[row] + lane; e < ptr[row + 1]; e += 32) rowidx[e] = row;
+}
+
+__global__ void hist_kernel(const int* __restrict__ keys, int64_t n, int* __restrict__ counts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(counts + keys[i], 1);
+}
+
+__global__ void transpose_gather_kernel(int64_t nnz, const int* __restrict__ perm, const int* __restrict__ rowidx,
+                                        const double* __restrict__ val, int* __restrict__ oidx, double* __restrict__ oval) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = perm[i];
+        oidx[i] = rowidx[e];
+        oval[i] = val[e];
+    }
+}
+
+__global__ void extract_diag_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                    const double* __restrict__ val, double* __restrict__ diag) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    double d = 0.0;
+    for (int e = ptr[row]; e < ptr[row + 1]; ++e) if (idx[e] == row) { d = val[e]; break; }
+    diag[row] = d;
+}
+
+__global__ void count_nonzero_rows_kernel(int nrows, const int* __restrict__ ptr, const double* __restrict__ val,
+                                          int* __restrict__ counts) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int cnt = 0;
+    for (int e = ptr[row]; e < ptr[row + 1]; ++e) cnt += (val[e] != 0.0);
+    counts[row] = cnt;
+}
+__global__ void copy_nonzero_rows_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                         const double* __restrict__ val, const int* __restrict__ optr,
+                                         int* __restrict__ oidx, double* __restrict__ oval) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int o = optr[row];
+    for (int e = ptr[row]; e < ptr[row + 1]; ++e) if (val[e] != 0.0) { oidx[o] = idx[e]; oval[o] = val[e]; ++o; }
+}
+
+__global__ void extract_count_kernel(int nsel, const int* __restrict__ sel, const int* __restrict__ newidx,
+                                     const int* __restrict__ ptr, const int* __restrict__ idx, int* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nsel) return;
+    const int r = sel[i];
+    int cnt = 0;
+    for (int e = ptr[r] + lane; e < ptr[r + 1]; e += 32) cnt += (newidx[idx[e]] >= 0);
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) counts[i] = cnt;
+}
+__global__ void extract_fill_kernel(int nsel, const int* __restrict__ sel, const int* __restrict__ newidx,
+                                    const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                                    const int* __restrict__ optr, int* __restrict__ oidx, double* __restrict__ oval) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nsel) return;
+    const int r = sel[i];
+    int o = optr[i];
+    const int e0 = ptr[r], e1 = ptr[r + 1];
+    for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int ni = -1; double v = 0.0;
+        if (e < e1) { ni = newidx[idx[e]]; v = val[e]; }
+        const unsigned ball = __ballot_sync(0xffffffffu, ni >= 0);
+        if (ni >= 0) {
+            const int pos = o + __popc(ball & ((1u << lane) - 1u));
+            oidx[pos] = ni; oval[pos] = v;
+        }
+        o += __popc(ball);
+    }
+}
+
+// sparse add  C = A + alpha*B, one thread per row (rows of interpolation matrices are short)
+template <bool FILL>
+__global__ void sparse_add_kernel(int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
+                                  double alpha, const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv,
+                                  int* __restrict__ counts, const int* __restrict__ optr, int* __restrict__ oidx,
+                                  double* __restrict__ oval) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int ea = ap[row], ea1 = ap[row + 1], eb = bp[row], eb1 = bp[row + 1];
+    int o = FILL ? optr[row] : 0, cnt = 0;
+    while (ea < ea1 || eb < eb1) {
+        const int ca = (ea < ea1) ? ai[ea] : 0x7fffffff;
+        const int cb = (eb < eb1) ? bi[eb] : 0x7fffffff;
+        double v; int col;
+        if (ca == cb)      { v = __dadd_rn(av[ea], __dmul_rn(alpha, bv[eb])); col = ca; ++ea; ++eb; }
+        else if (ca < cb)  { v = av[ea]; col = ca; ++ea; }
+        else               { v = __dmul_rn(alpha, bv[eb]); col = cb; ++eb; }
+        if (v != 0.0) {
+            if (FILL) { oidx[o] = col; oval[o] = v; ++o; }
+            ++cnt;
+        }
+    }
+    if (!FILL) counts[row] = cnt;
+}
+
+}  // namespace
+
+void expand_rows(ssn_ctx* c, const CsrView& A, int* rowidx) {
+    if (A.nrows > 0 && A.nnz > 0) SSN_LAUNCH(c, expand_rows_kernel, cdiv((int64_t)A.nrows * 32, 256), 256, 0, A.nrows, A.ptr, rowidx);
+}
+
+void extract_diag(ssn_ctx* c, const CsrView& A, double* diag) {
+    if (A.nrows > 0) SSN_LAUNCH(c, extract_diag_kernel, cdiv(A.nrows, 256), 256, 0, A.nrows, A.ptr, A.idx, A.val, diag);
+}
+
+Csr csr_alloc_from_counts(ssn_ctx* c, int nrows, int ncols, const int* counts) {
+    Csr C; C.c = c; C.nrows = nrows; C.ncols = ncols;
+    C.ptr.alloc(c, (size_t)nrows + 1);
+    C.nnz = scan_counts_to_ptr(c, counts, C.ptr, nrows);
+    C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
+    return C;
+}
+
+Csr csr_copy(ssn_ctx* c, const CsrView& A) {
+    Csr C; C.c = c; C.nrows = A.nrows; C.ncols = A.ncols; C.nnz = A.nnz;
+    C.ptr.alloc(c, (size_t)A.nrows + 1); C.idx.alloc(c, A.nnz); C.val.alloc(c, A.nnz);
+    SSN_CUDA(cudaMemcpyAsync(C.ptr.p, A.ptr, sizeof(int) * ((size_t)A.nrows + 1), cudaMemcpyDeviceToDevice, c->stream));
+    if (A.nnz) {
+        SSN_CUDA(cudaMemcpyAsync(C.idx.p, A.idx, sizeof(int) * A.nnz, cudaMemcpyDeviceToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(C.val.p, A.val, sizeof(double) * A.nnz, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return C;
+}
+
+Csr drop_zeros(ssn_ctx* c, const CsrView& A) {
+    Buf<int> counts(c, A.nrows);
+    if (A.nrows) SSN_LAUNCH(c, count_nonzero_rows_kernel, cdiv(A.nrows, 256), 256, 0, A.nrows, A.ptr, A.val, counts.p);
+    Csr C = csr_alloc_from_counts(c, A.nrows, A.ncols, counts);
+    if (A.nrows && C.nnz) SSN_LAUNCH(c, copy_nonzero_rows_kernel, cdiv(A.nrows, 256), 256, 0, A.nrows, A.ptr, A.idx, A.val, C.ptr.p, C.idx.p, C.val.p);
+    return C;
+}
+
+Csr transpose(ssn_ctx* c, const CsrView& A) {
+    Csr T; T.c = c; T.nrows = A.ncols; T.ncols = A.nrows; T.nnz = A.nnz;
+    Buf<int> counts(c, (size_t)A.ncols); counts.zero();
+    T.ptr.alloc(c, (size_t)A.ncols + 1);
+    if (A.nnz > 0) SSN_LAUNCH(c, hist_kernel, grid_for(A.nnz), 256, 0, A.idx, A.nnz, counts.p);
+    scan_counts_to_ptr(c, counts, T.ptr, A.ncols);
+    T.idx.alloc(c, A.nnz); T.val.alloc(c, A.nnz);
+    if (A.nnz == 0) return T;
+    Buf<int> rowidx(c, A.nnz), ent(c, A.nnz), keys_out(c, A.nnz), perm(c, A.nnz);
+    expand_rows(c, A, rowidx);
+    iota_int(c, ent, A.nnz);
+    stable_sort_pairs(c, A.idx, keys_out, ent, perm, A.nnz, A.ncols > 1 ? A.ncols : 2);
+    SSN_LAUNCH(c, transpose_gather_kernel, grid_for(A.nnz), 256, 0, A.nnz, perm.p, rowidx.p, A.val, T.idx.p, T.val.p);
+    return T;
+}
+
+Csr sparse_add(ssn_ctx* c, const CsrView& A, double alpha, const CsrView& B) {
+    SSN_REQUIRE(A.nrows == B.nrows && A.ncols == B.ncols, SSN_E_INVALID, "sparse_add: shape mismatch");
+    Buf<int> counts(c, A.nrows);
+    if (A.nrows) SSN_LAUNCH(c, sparse_add_kernel<false>, cdiv(A.nrows, 128), 128, 0, A.nrows, A.ptr, A.idx, A.val, alpha,
+                            B.ptr, B.idx, B.val, counts.p, nullptr, nullptr, nullptr);
+    Csr C = csr_alloc_from_counts(c, A.nrows, A.ncols, counts);
+    if (A.nrows && C.nnz) SSN_LAUNCH(c, sparse_add_kernel<true>, cdiv(A.nrows, 128), 128, 0, A.nrows, A.ptr, A.idx, A.val, alpha,
+                                     B.ptr, B.idx, B.val, nullptr, C.ptr.p, C.idx.p, C.val.p);
+    return C;
+}
+
+Csr extract_principal(ssn_ctx* c, const CsrView& A, const int* sel, int nsel, const int* newidx) {
+    Buf<int> counts(c, nsel);
+    if (nsel) SSN_LAUNCH(c, extract_count_kernel, cdiv((int64_t)nsel * 32, 256), 256, 0, nsel, sel, newidx, A.ptr, A.idx, counts.p);
+    Csr C = csr_alloc_from_counts(c, nsel, nsel, counts);
+    if (nsel && C.nnz) SSN_LAUNCH(c, extract_fill_kernel, cdiv((int64_t)nsel * 32, 256), 256, 0, nsel, sel, newidx, A.ptr, A.idx,
+                                  A.val, C.ptr.p, C.idx.p, C.val.p);
+    return C;
+}
+
+// ------------------------------------------------------------------ SpGEMM
+
+namespace {
+
+constexpr int kMaxWindow = 16384;
+
+__global__ void spgemm_ub_kernel(int nrows, const int* __restrict__ ap, const int* __restrict__ ai,
+                                 const int* __restrict__ bp, int ncolsB, int* __restrict__ ub) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nrows) return;
+    long long s = 0;
+    for (int e = ap[row] + lane; e < ap[row + 1]; e += 32) { const int k = ai[e]; s += bp[k + 1] - bp[k]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) ub[row] = (s < (long long)ncolsB) ? (int)s : ncolsB;
+}
+
+// One block per output row (grid-stride).  Dense accumulator window acc[W] + touched bitmap
+// in shared memory.  The A-row is walked in ascending k; all threads cooperate on one B-row at
+// a time (distinct columns => race-free) with a barrier between consecutive k, which fixes the
+// per-entry summation order.  Runs of single-entry B-rows with strictly increasing columns
+// (the identity block of an interpolation matrix) are applied in parallel.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) spgemm_numeric_kernel(
+    int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
+    const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, int ncolsB, int W,
+    const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval, int* __restrict__ rownnz) {
+    extern __shared__ unsigned char smem_raw[];
+    double* acc = reinterpret_cast<double*>(smem_raw);
+    unsigned* flags = reinterpret_cast<unsigned*>(acc + W);
+    __shared__ int s_k[THREADS];
+    __shared__ double s_a[THREADS];
+    __shared__ int s_c[THREADS];
+    __shared__ int s_warp[THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nwords = (W + 31) >> 5;
+
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int a0 = ap[row], a1 = ap[row + 1];
+        const int out0 = ubptr[row];
+        int written = 0;
+        if (a1 > a0) {
+            for (int w0 = 0; w0 < ncolsB; w0 += W) {
+                const int w1 = w0 + W;
+                for (int t = tid; t < W; t += THREADS) acc[t] = 0.0;
+                for (int t = tid; t < nwords; t += THREADS) flags[t] = 0u;
+                __syncthreads();
+                for (int eb = a0; eb < a1; eb += THREADS) {
+                    const int e = eb + tid;
+                    const int nb = (a1 - eb < THREADS) ? (a1 - eb) : THREADS;
+                    int k = -1, len = 0, bstart = 0, c1 = -1; double a = 0.0;
+                    if (e < a1) {
+                        k = ai[e]; a = av[e]; bstart = bp[k]; len = bp[k + 1] - bstart;
+                        if (len == 1) c1 = bi[bstart];
+                    }
+                    s_k[tid] = k; s_a[tid] = a; s_c[tid] = c1;
+                    __syncthreads();
+                    bool ok = (e >= a1) || (len == 1 && (tid == 0 || c1 > s_c[tid - 1]));
+                    const int fast = __syncthreads_and(ok ? 1 : 0);
+                    if (fast) {
+                        if (e < a1 && c1 >= w0 && c1 < w1) {
+                            const int cc = c1 - w0;
+                            acc[cc] = __dadd_rn(acc[cc], __dmul_rn(a, bv[bstart]));
+                            atomicOr(flags + (cc >> 5), 1u << (cc & 31));
+                        }
+                        __syncthreads();
+                    } else {
+                        for (int j = 0; j < nb; ++j) {
+                            const int kj = s_k[j];
+                            const int b0 = bp[kj], b1 = bp[kj + 1];
+                            if (b1 == b0) continue;
+                            if (bi[b1 - 1] < w0 || bi[b0] >= w1) continue;   // row misses the window
+                            const double aj = s_a[j];
+                            for (int t = b0 + tid; t < b1; t += THREADS) {
+                                const int col = bi[t];
+                                if (col >= w0 && col < w1) {
+                                    const int cc = col - w0;
+                                    acc[cc] = __dadd_rn(acc[cc], __dmul_rn(aj, bv[t]));
+                                    atomicOr(flags + (cc >> 5), 1u << (cc & 31));
+                                }
+                            }
+                            __syncthreads();
+                        }
+                        __syncthreads();   // skipped rows have no barrier: re-align before s_k is reused
+                    }
+                }
+                // ---- compact the window in ascending column order
+                const int per = (W + THREADS - 1) / THREADS;
+                const int lo = tid * per, hi = (lo + per < W) ? (lo + per) : W;
+                int cnt = 0;
+                for (int t = lo; t < hi; ++t)
+                    if (((flags[t >> 5] >> (t & 31)) & 1u) && acc[t] != 0.0) ++cnt;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (lane == 31) s_warp[wid] = incl;
+                __syncthreads();
+                if (wid == 0) {
+                    int wv = (lane < THREADS / 32) ? s_warp[lane] : 0;
+                    int wi = wv;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+                    if (lane < THREADS / 32) s_warp[lane] = wi - wv;
+                    if (lane == 31) s_total = wi;
+                }
+                __syncthreads();
+                int pos = out0 + written + s_warp[wid] + incl - cnt;
+                for (int t = lo; t < hi; ++t)
+                    if (((flags[t >> 5] >> (t & 31)) & 1u) && acc[t] != 0.0) { tidx[pos] = w0 + t; tval[pos] = acc[t]; ++pos; }
+                written += s_total;
+                __syncthreads();
+            }
+        }
+        if (tid == 0) rownnz[row] = written;
+    }
+}
+
+__global__ void sum_int64_kernel(const int* __restrict__ v, int n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)v[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+__global__ void compact_rows_kernel(int nrows, const int* __restrict__ ubptr, const int* __restrict__ optr,
+                                    const int* __restrict__ tidx, const double* __restrict__ tval,
+                                    int* __restrict__ oidx, double* __restrict__ oval) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nrows) return;
+    const int src = ubptr[row], dst = optr[row], len = optr[row + 1] - dst;
+    for (int t = lane; t < len; t += 32) { oidx[dst + t] = tidx[src + t]; oval[dst + t] = tval[src + t]; }
+}
+
+}  // namespace
+
+Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
+    SSN_REQUIRE(A.ncols == B.nrows, SSN_E_INVALID, "spgemm: inner dimensions differ");
+    const int nrows = A.nrows, ncolsB = B.ncols;
+    Csr C; C.c = c; C.nrows = nrows; C.ncols = ncolsB;
+    if (nrows == 0 || A.nnz == 0 || B.nnz == 0) {
+        C.ptr.alloc(c, (size_t)nrows + 1); C.ptr.zero(); C.nnz = 0; C.idx.alloc(c, 0); C.val.alloc(c, 0);
+        return C;
+    }
+    // upper bounds (64-bit check of the total on the host side through a double sum is overkill:
+    // ub[row] <= ncolsB, so total <= nrows*ncolsB; reject only if that could overflow AND does)
+    Buf<int> ub(c, nrows), ubptr(c, (size_t)nrows + 1), rownnz(c, nrows);
+    SSN_LAUNCH(c, spgemm_ub_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, ncolsB, ub.p);
+    if ((int64_t)nrows * (int64_t)ncolsB >= ((int64_t)1 << 31)) {      // the int32 scan could wrap: check in 64 bit
+        Buf<unsigned long long> tot(c, 1); tot.zero();
+        SSN_LAUNCH(c, sum_int64_kernel, 64, 256, 0, ub.p, nrows, tot.p);
+        const unsigned long long t = read_scalar(c, tot.p);
+        SSN_REQUIRE(t < (1ull << 31), SSN_E_TOO_LARGE, "spgemm: intermediate product exceeds the int32 index range");
+    }
+    const int64_t ub_total = scan_counts_to_ptr(c, ub, ubptr, nrows);
+    Buf<int> tidx(c, (size_t)ub_total); Buf<double> tval(c, (size_t)ub_total);
+    int W = ((ncolsB + 31) / 32) * 32; if (W > kMaxWindow) W = kMaxWindow;
+    const size_t smem = (size_t)W * sizeof(double) + (size_t)((W + 31) / 32) * sizeof(unsigned);
+    if (W > 4096) {
+        auto kern = spgemm_numeric_kernel<512>;
+        SSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = nrows < c->num_sms ? nrows : c->num_sms;
+        SSN_LAUNCH(c, kern, grid, 512, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, ncolsB, W, ubptr.p, tidx.p, tval.p, rownnz.p);
+    } else {
+        auto kern = spgemm_numeric_kernel<128>;
+        const int per_sm = (int)(96 * 1024 / (smem + 4096));
+        int grid = c->num_sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+        if (grid > nrows) grid = nrows;
+        SSN_LAUNCH(c, kern, grid, 128, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, ncolsB, W, ubptr.p, tidx.p, tval.p, rownnz.p);
+    }
+    C.ptr.alloc(c, (size_t)nrows + 1);
+    C.nnz = scan_counts_to_ptr(c, rownnz, C.ptr, nrows);
+    C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
+    if (C.nnz) SSN_LAUNCH(c, compact_rows_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, nrows, ubptr.p, C.ptr.p, tidx.p, tval.p, C.idx.p, C.val.p);
+    return C;
+}
+
+}  // namespace ssn

@@ -1,0 +1,274 @@
+/*
+ * ssnamg.h -- C ABI of libssnamg.so: the B200-native (sm_100a CUDA) semismooth-Newton
+ * inner linear solve of the IPD-SsN-AMG optimal-transport solver.
+ *
+ * The reference has no FFI: its boundary is the set of MATLAB function names on the path
+ * (resolved through `addpath`, Class1/APD_SsN_Class1.m:13-14).  Each entry point below is what
+ * a MEX shim of the same name binds (see INTEGRATION.md and mex/), and cites the reference
+ * function it replaces.  All reference paths are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ types, no exceptions cross this boundary.
+ *   - every function returns an int status: SSN_OK (0) or a negative SSN_E_* code that maps
+ *     1:1 onto a reference `error()` condition or a CUDA failure; ssn_last_error() has text.
+ *   - pointers named *_dev are DEVICE pointers on the context's GPU; *_host are host pointers.
+ *     Functions with the suffix _host take host buffers and do the host<->device copies
+ *     themselves (what a MEX shim holding ordinary mxArrays calls).
+ *   - the plan x = vec(X) is the column-major m x n transport plan (m contiguous), dual /
+ *     right-hand-side vectors are [column part (n) ; row part (m)], p has length m, q length n.
+ *   - sparse matrices are CSR with sorted column indices, 0-based int32 indices.  Every sparse
+ *     matrix on this path is structurally symmetric, so the same arrays are the CSC form a
+ *     MATLAB sparse matrix holds (after widening indices to mwIndex).
+ *   - all floating point is IEEE fp64.  Setup arithmetic follows the frozen summation order of
+ *     DESIGN.md so that sparsity patterns, strength graphs and C/F splittings are bit-exact.
+ *   - entry points are synchronous at return (results visible to the caller) unless stated.
+ */
+#ifndef SSNAMG_H
+#define SSNAMG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SSN_API __attribute__((visibility("default")))
+#else
+#define SSN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status codes */
+enum {
+    SSN_OK                = 0,
+    SSN_E_CUDA            = -1,  /* a CUDA runtime call failed (text in ssn_last_error)           */
+    SSN_E_INVALID         = -2,  /* bad argument (null pointer, negative size, unknown option)     */
+    SSN_E_PQ_ZERO         = -3,  /* "p or q contains 0 !!!!!"               Hybrid_AMG.m:18-19     */
+    SSN_E_BIGPH_FNODE     = -4,  /* "amg_options.bigph = 1 requires Nf > 0" AMG/Class_AMG.m:36-40  */
+    SSN_E_PCG_NF          = -5,  /* "SSOR for bigraph requires pcg_options.nf" PCG.m:64            */
+    SSN_E_NOT_SQUARE      = -6,  /* "Adjacency matrix must be square"       components.m:33        */
+    SSN_E_CF_PARTITION    = -7,  /* C/F split does not partition the nodes: AMG/transfer.m:46-47
+                                    would index out of range in MATLAB                             */
+    SSN_E_COARSEN_STALL   = -8,  /* no F node found: AMG/Class_AMG.m:76 would loop forever         */
+    SSN_E_NOT_BIGRAPH     = -9,  /* A(1:Nf,1:Nf) is not diagonal (check commented out at
+                                    AMG/Class_AMG.m:52-54)                                         */
+    SSN_E_UNSUPPORTED     = -10, /* PCG precd 3/4, Hybrid_twogrid, ...              */
+    SSN_E_TOO_LARGE       = -11, /* a sparse object exceeds the int32 index range                  */
+    SSN_E_NOT_SPD         = -12, /* small-component Cholesky hit a non-positive pivot              */
+    SSN_E_NO_HIERARCHY    = -13, /* MG_Vcycle/MG_Wcycle called without a live hierarchy (the
+                                    reference reads cleared globals, AMG/Class_AMG.m:110)          */
+    SSN_E_ASATZ_DIM       = -14  /* ASAtz.m:21 multiplies the m-by-n Q by p: needs m == n          */
+};
+
+typedef struct ssn_ctx ssn_ctx;
+
+/* Device CSR matrix; arrays are owned by the context that produced them. */
+typedef struct ssn_csr {
+    int64_t  nrows, ncols, nnz;
+    int32_t *rowptr_dev;   /* nrows+1 */
+    int32_t *colidx_dev;   /* nnz, ascending inside every row */
+    double  *val_dev;      /* nnz */
+} ssn_csr;
+
+/* amg_options (AMG/Class_AMG.m:20-34).  A negative / NaN field means "empty" -> the
+ * reference's isempty() default is applied. */
+typedef struct ssn_amg_options {
+    double  retol;     /* default 1e-12 */
+    int32_t bigph;     /* default 0     */
+    int32_t maxit;     /* default 50    */
+    double  theta;     /* default 1/4   */
+    int32_t smoth;     /* default 3     */
+    int32_t cycle;     /* 'v' (118) or 'w' (119); default 'v'; any other value runs no cycle,
+                          like the reference's nargin==2 default `cycle = 1`                  */
+    int32_t isnsp;     /* default 0     */
+    int32_t inter;     /* default 1     */
+    int32_t fnode;     /* required when bigph != 0 */
+    const double *guess_dev;  /* NULL -> zeros */
+} ssn_amg_options;
+
+/* pcg_options (PCG.m:18-27). */
+typedef struct ssn_pcg_options {
+    double  retol;     /* default 1e-11 */
+    int32_t maxit;     /* default 10000 */
+    int32_t precd;     /* 1 none, 2 Jacobi (default), 5 bi-SSOR (needs nf); 3,4 unsupported */
+    int32_t nf;        /* <= 0: absent */
+    const double *guess_dev;  /* NULL -> zeros */
+} ssn_pcg_options;
+
+/* prob_data (Class1/APD_SsN_Class1.m:154-156, Class2/APD_SsN_Class2.m:163-166). */
+typedef struct ssn_prob_data {
+    double  bk1, tk;
+    int64_t m, n;
+    const double  *p_dev, *q_dev;   /* m, n */
+    const double  *t_dev;           /* diag(T), n+m; NULL -> zeros */
+    const ssn_csr *H0;              /* (n+m) x (n+m), from ssn_asat */
+    const double  *z_dev;           /* rhs: n+m (n+m+1 for the POT entry points) */
+    const uint8_t *s_dev;           /* POT only: logical active set, m*n */
+    const double  *phi_dev;         /* POT only: m*n */
+} ssn_prob_data;
+
+/* ------------------------------------------------------------------ context */
+SSN_API int  ssn_create(ssn_ctx **ctx, int device);           /* device < 0: current device */
+SSN_API int  ssn_destroy(ssn_ctx *ctx);
+SSN_API const char *ssn_last_error(ssn_ctx *ctx);
+SSN_API int  ssn_set_stream(ssn_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = default stream */
+SSN_API int  ssn_synchronize(ssn_ctx *ctx);
+SSN_API int  ssn_version(void);
+/* kernels launched by this context since creation (bench.py's gpu_launches claim) */
+SSN_API int64_t ssn_launch_count(ssn_ctx *ctx);
+
+/* The library-owned MATLAB random stream (mt19937ar, init_genrand(5489), genrand_res53):
+ * stands for MATLAB's global `rand` state consumed at AMG/mis_set.m:31,35 and
+ * Hybrid_AMG.m:40,69.  Generated on the device. */
+SSN_API int  ssn_rng_reset(ssn_ctx *ctx, uint32_t seed);
+SSN_API int64_t ssn_rng_drawn(ssn_ctx *ctx);
+SSN_API int  ssn_rand(ssn_ctx *ctx, int64_t count, double *out_dev);
+
+/* device memory helpers for hosts without their own allocator (MEX shim, ctypes tests) */
+SSN_API int  ssn_malloc(ssn_ctx *ctx, size_t bytes, void **ptr_dev);
+SSN_API int  ssn_free(ssn_ctx *ctx, void *ptr_dev);
+SSN_API int  ssn_memcpy_h2d(ssn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+SSN_API int  ssn_memcpy_d2h(ssn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+SSN_API int  ssn_csr_free(ssn_ctx *ctx, ssn_csr *A);
+SSN_API int  ssn_csr_upload(ssn_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+                    const int32_t *rowptr_host, const int32_t *colidx_host,
+                    const double *val_host, ssn_csr *out);
+SSN_API int  ssn_csr_download(ssn_ctx *ctx, const ssn_csr *A, int32_t *rowptr_host,
+                      int32_t *colidx_host, double *val_host);
+
+/* ------------------------------------------------------------------ L1: plan operators */
+
+/* y = Ax(x,p,q)  -- Ax.m:10-13.  y_dev: n+m.  One pass over the plan. */
+SSN_API int ssn_ax(ssn_ctx *ctx, const double *x_dev, const double *p_dev, const double *q_dev,
+           int64_t m, int64_t n, double *y_dev);
+SSN_API int ssn_ax_host(ssn_ctx *ctx, const double *x_host, const double *p_host, const double *q_host,
+                int64_t m, int64_t n, double *y_host);
+
+/* z = Aty(y,p,q) -- Aty.m:10-13.  z_dev: m*n. */
+SSN_API int ssn_aty(ssn_ctx *ctx, const double *y_dev, const double *p_dev, const double *q_dev,
+            int64_t m, int64_t n, double *z_dev);
+SSN_API int ssn_aty_host(ssn_ctx *ctx, const double *y_host, const double *p_host, const double *q_host,
+                 int64_t m, int64_t n, double *z_host);
+
+/* Fused SsN residual pieces, one read of w (Class1/APD_SsN_Class1.m:139-140,144,184,193):
+ *   z   = (1/tk) * (w - Aty(lam))            (rounded exactly like the reference expression)
+ *   s   = (z >= 0) & (z <= gama)             -> s_out_dev   (uint8, m*n)       [optional]
+ *   px  = min(max(0,z),gama)                 -> prox_out_dev (m*n)             [optional]
+ *   Ax(px)                                   -> axp_out_dev  (n+m)             [optional]
+ *   ||px||^2                                 -> *norm2_out (host)              [optional]
+ *   nnz(s)                                   -> *count_out (host)              [optional]
+ * gama_dev == NULL means gama = gama_scalar for every entry (Inf for plain OT). */
+SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *lam_dev,
+                      const double *p_dev, const double *q_dev, int64_t m, int64_t n,
+                      double tk, const double *gama_dev, double gama_scalar,
+                      double *axp_out_dev, double *prox_out_dev, double *z_out_dev,
+                      uint8_t *s_out_dev, double *norm2_out, int64_t *count_out);
+
+/* H = ASAt(s,p,q) -- ASAt.m:14-19.  s: logical m*n (1 byte per entry).  H is
+ * (n+m) x (n+m), column nodes first, explicit zeros dropped. */
+SSN_API int ssn_asat(ssn_ctx *ctx, const uint8_t *s_dev, const double *p_dev, const double *q_dev,
+             int64_t m, int64_t n, ssn_csr *H_out);
+SSN_API int ssn_asat_host(ssn_ctx *ctx, const uint8_t *s_host, const double *p_host,
+                  const double *q_host, int64_t m, int64_t n, ssn_csr *H_out);
+
+/* y = ASAtz(z,s,p,q) -- ASAtz.m:15-22, reproduced as written (Q*p at :21; needs m == n). */
+SSN_API int ssn_asatz(ssn_ctx *ctx, const double *z_dev, const uint8_t *s_dev, const double *p_dev,
+              const double *q_dev, int64_t m, int64_t n, double *y_dev);
+
+/* y = invAAt(x,p,q,sg1,sg2) -- invAAt.m:7-20 (callers resolve the nargin defaults). */
+SSN_API int ssn_invaat(ssn_ctx *ctx, const double *x_dev, const double *p_dev, const double *q_dev,
+               int64_t m, int64_t n, double sg1, double sg2, double *y_dev);
+/* y = invHHt(v,p,q,sg,phi) -- Class2/invHHt.m:7-17.  v, y: n+m+1. */
+SSN_API int ssn_invhht(ssn_ctx *ctx, const double *v_dev, const double *p_dev, const double *q_dev,
+               int64_t m, int64_t n, double sg, const double *phi_dev, double *y_dev);
+
+/* ------------------------------------------------------------------ L2: AMG setup */
+
+/* S = strength(A,which) -- AMG/strength.m:6-18.  S has the pattern of the nonzero
+ * off-diagonal entries of A whose strength value is nonzero. */
+SSN_API int ssn_strength(ssn_ctx *ctx, const ssn_csr *A, int which, ssn_csr *S_out);
+
+/* [isC,isF,As] = mis_set(A,theta) -- AMG/mis_set.m:8-67.  isC/isF: uint8[N] on the device;
+ * As_out (optional) is the logical strength matrix as a CSR with unit values.  Consumes the
+ * context's random stream exactly like the reference consumes `rand`. */
+SSN_API int ssn_mis_set(ssn_ctx *ctx, const ssn_csr *A, double theta, uint8_t *isC_dev,
+                uint8_t *isF_dev, ssn_csr *As_out);
+
+/* [indC,indF] = cf_split(S) -- AMG/cf_split.m:6-15 (S logical; its third output, a MATLAB
+ * graph object, is rebuilt by the .m wrapper from S). */
+SSN_API int ssn_cf_split(ssn_ctx *ctx, const ssn_csr *S, uint8_t *indC_dev, uint8_t *indF_dev);
+
+/* [Ac,Pro,As,indC] = transfer(A,amg_options) -- AMG/transfer.m:8-66.  `level_J` stands for
+ * the reference's `global J` (transfer.m:17).  As_out / indC_dev are optional. */
+SSN_API int ssn_transfer(ssn_ctx *ctx, const ssn_csr *A, const ssn_amg_options *opts, int level_J,
+                 ssn_csr *Ac_out, ssn_csr *Pro_out, ssn_csr *As_out, uint8_t *indC_dev);
+
+/* Setup phase of Class_AMG (AMG/Class_AMG.m:41-85): builds the hierarchy that the reference
+ * keeps in the globals Ack/Prok/Rk/J/smoth_it into the context-owned handle.  *levels_out
+ * receives J.  ssn_amg_level() exposes level k (1-based): A_k, Pro_k (NULL for k=1). */
+SSN_API int ssn_amg_setup(ssn_ctx *ctx, const ssn_csr *A, const ssn_amg_options *opts, int *levels_out);
+SSN_API int ssn_amg_level(ssn_ctx *ctx, int k, ssn_csr *A_out, ssn_csr *Pro_out);
+SSN_API int ssn_amg_clear(ssn_ctx *ctx);
+
+/* e = MG_Vcycle(r,isnsp,k) / e = MG_Wcycle(r,isnsp,k,e) -- AMG/MG_Vcycle.m, AMG/MG_Wcycle.m,
+ * on the context's live hierarchy.  e_dev is in/out for the W-cycle (initial guess, pass
+ * zeros for the reference's default); k is 1-based. */
+SSN_API int ssn_mg_vcycle(ssn_ctx *ctx, const double *r_dev, int isnsp, int k, double *e_dev);
+SSN_API int ssn_mg_wcycle(ssn_ctx *ctx, const double *r_dev, int isnsp, int k, double *e_dev);
+
+/* [x,it,rel_res,rel_resk,rhok] = Class_AMG(A,b,amg_options) -- AMG/Class_AMG.m:20-110.
+ * rel_resk_host / rhok_host: caller buffers of maxit+1 doubles (optional), *hist_len_out
+ * receives the number of valid entries.  The hierarchy is cleared on return (Class_AMG.m:110)
+ * unless keep_hierarchy != 0. */
+SSN_API int ssn_class_amg(ssn_ctx *ctx, const ssn_csr *A, const double *b_dev,
+                  const ssn_amg_options *opts, int keep_hierarchy, double *x_dev, int *it_out,
+                  double *rel_res_out, double *rel_resk_host, double *rhok_host,
+                  int *hist_len_out);
+
+/* ------------------------------------------------------------------ L2: Krylov */
+
+/* [d,it,res,resk] = PCG(H,e,pcg_options) -- PCG.m:18-105.  resk_host: caller buffer of
+ * maxit doubles (optional). */
+SSN_API int ssn_pcg(ssn_ctx *ctx, const ssn_csr *H, const double *e_dev, const ssn_pcg_options *opts,
+            double *d_dev, int *it_out, double *res_out, double *resk_host);
+
+/* ------------------------------------------------------------------ L3: dispatch */
+
+/* [blocks,sizes,p,r] = components(A) -- components.m:32-55.  Component order: ascending
+ * smallest member, members ascending (frozen convention).  blocks_dev: int32[N]
+ * 1-based labels; p_dev: int32[N] 0-based; sizes/r are returned through the context:
+ * *ncomp_out components; sizes_dev int32[N] (first ncomp valid), r_dev int32[N+1]. */
+SSN_API int ssn_components(ssn_ctx *ctx, const ssn_csr *A, int32_t *blocks_dev, int32_t *sizes_dev,
+                   int32_t *p_dev, int32_t *r_dev, int *ncomp_out);
+
+/* [zeta,itamg,resamg,info] = Hybrid_AMG(prob_data,amg_options) -- Hybrid_AMG.m:11-113.
+ * info_out[2] = {num_comp, it_num}. */
+SSN_API int ssn_hybrid_amg(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts,
+                   double *zeta_dev, int *itamg_out, double *resamg_out, int *info_out);
+
+/* [zeta,itpcg,respcg,info] = aug_PCG(prob_data,pcg_options) -- aug_PCG.m:11-37. */
+SSN_API int ssn_aug_pcg(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_options *opts,
+                double *zeta_dev, int *itpcg_out, double *respcg_out, int *info_out);
+
+/* Class2/AMG4POT.m:27-55 and Class2/PCG4POT.m:26-40: bordered partial-OT solves.
+ * pd->z_dev has n+m+1 entries, zeta_dev likewise. */
+SSN_API int ssn_amg4pot(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts,
+                double *zeta_dev, int *it_out, double *res_out, int *info_out);
+SSN_API int ssn_pcg4pot(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_options *opts,
+                double *zeta_dev, int *it_out, double *res_out, int *info_out);
+
+/* The assembled rescaled system of Hybrid_AMG.m:17-24 / aug_PCG.m:16-22 (for parity tests):
+ * Ae = bk1*Q0^2 + (K + Q0*H0*Q0)/tk and f = Q0*z. */
+SSN_API int ssn_rescaled_system(ssn_ctx *ctx, const ssn_prob_data *pd, ssn_csr *Ae_out, double *f_dev);
+
+/* ------------------------------------------------------------------ sparse utilities
+ * (generic building blocks of the path, exported for parity tests) */
+SSN_API int ssn_spmv(ssn_ctx *ctx, const ssn_csr *A, const double *x_dev, double *y_dev);
+SSN_API int ssn_spgemm(ssn_ctx *ctx, const ssn_csr *A, const ssn_csr *B, ssn_csr *C_out);
+SSN_API int ssn_transpose(ssn_ctx *ctx, const ssn_csr *A, ssn_csr *At_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSNAMG_H */

@@ -1,0 +1,53 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/ssnamg.h declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    h = open(os.path.join(ROOT, "include", "ssnamg.h")).read()
+    return sorted(set(re.findall(r"^SSN_API[^;(]*?\b(ssn_\w+)\s*\(", h, flags=re.M)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for name in ["ssn_ax", "ssn_aty", "ssn_asat", "ssn_asatz", "ssn_pcg", "ssn_aug_pcg", "ssn_components",
+                 "ssn_hybrid_amg", "ssn_class_amg", "ssn_transfer", "ssn_strength", "ssn_mis_set", "ssn_cf_split",
+                 "ssn_mg_vcycle", "ssn_mg_wcycle", "ssn_amg4pot", "ssn_pcg4pot", "ssn_invaat", "ssn_invhht"]:
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol(ssnamg):
+    assert os.path.exists(ssnamg.LIB_PATH), "libssnamg.so missing: run __graft_entry__.build()"
+    lib = ctypes.CDLL(ssnamg.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/ssnamg.h but not exported"
+
+
+def test_python_binding_covers_the_header(ssnamg):
+    assert sorted(ssnamg.SIGNATURES) == declared_symbols()
+    ssnamg.load()
+    lib = ctypes.CDLL(ssnamg.LIB_PATH)
+    lib.ssn_version.restype = ctypes.c_int
+    assert lib.ssn_version() >= 100
+
+
+def test_no_cpu_fallback(ssnamg):
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    with pytest.raises(Exception):
+        ssnamg.Ax(np.zeros(6), np.ones(2), np.ones(3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "codes-of-ipd-ssn-amg-method_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f

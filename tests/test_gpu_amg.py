@@ -1,0 +1,230 @@
+"""GPU parity tests, AMG setup / cycles / PCG: CUDA path vs the CPU oracle.  Patterns, strength
+graphs, C/F splittings, level sizes and every setup value are required to be BIT-EXACT; solve
+phase results within 1e-8 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import random_active_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def csc_sorted(A):
+    A = sp.csc_matrix(A); A.sort_indices(); return A
+
+
+def assert_same_matrix(dev, ref, exact=True, what=""):
+    D = csc_sorted(dev.to_scipy() if hasattr(dev, "to_scipy") else dev); R = csc_sorted(ref)
+    assert D.shape == R.shape, what
+    assert np.array_equal(D.indptr, R.indptr), what + ": column pointers differ"
+    assert np.array_equal(D.indices, R.indices), what + ": row indices differ"
+    if exact:
+        bad = np.flatnonzero(D.data != R.data)
+        assert bad.size == 0, f"{what}: {bad.size} values differ, first {D.data[bad[:3]]} vs {R.data[bad[:3]]}"
+    else:
+        assert np.allclose(D.data, R.data, rtol=1e-10, atol=0), what
+
+
+def ssn_matrix(oracle, m, n, density, seed, weights=False, bk1=0.05, tk=0.8):
+    """The rescaled SsN system Ae of a random active set (Hybrid_AMG.m:17-24), from the oracle."""
+    s, p, q = random_active_problem(m, n, density, seed, weights)
+    H0 = oracle.ASAt(s, p, q)
+    pd = {"bk1": bk1, "tk": tk, "p": p, "q": q, "T": sp.diags(np.zeros(m + n)), "H0": H0,
+          "z": np.random.RandomState(seed).standard_normal(m + n)}
+    from oracle.solvers import rescaled_system
+    qp, A0, Qd, Kd, Ae, f = rescaled_system(pd)
+    return pd, Ae, f
+
+
+def rand_sparse(nr, nc, density, seed, single_rows=False):
+    rs = np.random.RandomState(seed)
+    A = sp.random(nr, nc, density=density, random_state=rs, format="csr", data_rvs=rs.standard_normal)
+    if single_rows:
+        A = sp.vstack([A, sp.identity(nc, format="csr")[rs.permutation(nc)[: nc // 2]]]).tocsr()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("shape", [(30, 40, 50, 0.2), (300, 200, 400, 0.03), (1000, 1000, 1000, 0.01),
+                                   (64, 20000, 64, 0.002), (200, 300, 40000, 0.004), (500, 17000, 33000, 0.0005)])
+def test_spgemm_fixed_order_bit_exact(gpu, oracle, shape):
+    from oracle.amg import spgemm
+    nr, nk, nc, d = shape
+    A = rand_sparse(nr, nk, d, 1); B = rand_sparse(nk, nc, d, 2)
+    assert_same_matrix(gpu.spgemm(A, B), spgemm(A, B), what="A*B")
+
+
+def test_spgemm_identity_runs_and_cancellation(gpu, oracle):
+    from oracle.amg import spgemm
+    n = 700
+    P = sp.vstack([rand_sparse(500, n, 0.01, 3), sp.identity(n, format="csr")]).tocsr()   # [W ; I]
+    A = rand_sparse(1200, 1200, 0.01, 4); A = (A + A.T).tocsr()
+    T1 = spgemm(P.T, A)
+    assert_same_matrix(gpu.spgemm(P.T.tocsr(), A), T1, what="P'*A")
+    assert_same_matrix(gpu.spgemm(T1, P), spgemm(T1, P), what="(P'*A)*P")
+    X = sp.csr_matrix(np.array([[1.0, -1.0], [2.0, 3.0]])); Y = sp.csr_matrix(np.array([[1.0, 5.0], [1.0, 7.0]]))
+    assert_same_matrix(gpu.spgemm(X, Y), spgemm(X, Y), what="exact zero dropped")        # (0,0) cancels
+
+
+def test_transpose_and_spmv(gpu):
+    A = rand_sparse(700, 1300, 0.01, 5)
+    At = gpu.transpose(A).to_scipy(); At.sort_indices()
+    R = A.T.tocsr(); R.sort_indices()
+    assert np.array_equal(At.indptr, R.indptr) and np.array_equal(At.indices, R.indices) and np.array_equal(At.data, R.data)
+    x = np.random.RandomState(0).standard_normal(1300)
+    for dens in (0.002, 0.01, 0.05, 0.2):
+        B = rand_sparse(700, 1300, dens, 6)
+        assert np.allclose(gpu.spmv(B, x), B @ x, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("m,n,density,weights", [(40, 30, 0.1, False), (200, 150, 0.03, True), (600, 700, 0.006, False),
+                                                   (300, 300, 0.2, True)])
+def test_strength_bit_exact(gpu, oracle, m, n, density, weights):
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=m, weights=weights)
+    from oracle.amg import transfer
+    o = {"theta": 0.25, "bigph": 1, "inter": 1, "isnsp": 1, "fnode": n}
+    A2, _ = transfer(Ae, o, J=1)                       # level-2 operator: the interesting strength graph
+    for A in (Ae, A2):
+        for which in (1, 2):
+            assert_same_matrix(gpu.strength(A, which), oracle.strength(A, which), what=f"strength which={which}")
+
+
+@pytest.mark.parametrize("m,n,density,weights", [(40, 30, 0.1, False), (200, 150, 0.03, True), (600, 700, 0.006, False),
+                                                   (1500, 1400, 0.002, False), (300, 300, 0.2, True)])
+def test_mis_set_and_transfer_bit_exact(gpu, oracle, m, n, density, weights):
+    from oracle.amg import transfer
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=m + 1, weights=weights)
+    o = {"theta": 0.25, "bigph": 1, "inter": 1, "isnsp": 1, "fnode": n}
+    # level 1 (bigraph branch, transfer.m:19-29)
+    Ac_ref, Pro_ref, As_ref, indC_ref = transfer(Ae, o, J=1, want_aux=True)
+    Ac, Pro, As, indC = gpu.transfer(Ae, o, J=1)
+    assert np.array_equal(indC, indC_ref)
+    assert_same_matrix(Pro, Pro_ref, what="Pro level 1")
+    assert_same_matrix(As, As_ref, what="As level 1")
+    assert_same_matrix(Ac, Ac_ref, what="Ac level 2")
+    # level 2 (MIS branch, transfer.m:41-63), same random stream on both sides
+    oracle.rng_reset(); gpu.rng_reset()
+    isC_ref, isF_ref, As2_ref = oracle.mis_set(Ac_ref, 0.25)
+    isC, isF, As2 = gpu.mis_set(Ac_ref, 0.25)
+    assert np.array_equal(isC, isC_ref) and np.array_equal(isF, isF_ref)
+    assert_same_matrix(As2, As2_ref, what="As level 2")
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    for isnsp in (1, 0):
+        o2 = dict(o, isnsp=isnsp)
+        oracle.rng_reset(); gpu.rng_reset()
+        A3_ref, P3_ref, As3_ref, indC3_ref = transfer(Ac_ref, o2, J=2, want_aux=True)
+        A3, P3, As3, indC3 = gpu.transfer(Ac_ref, o2, J=2)
+        assert np.array_equal(indC3, indC3_ref)
+        assert_same_matrix(P3, P3_ref, what=f"Pro level 2 isnsp={isnsp}")
+        assert_same_matrix(A3, A3_ref, what=f"Ac level 3 isnsp={isnsp}")
+
+
+def test_mis_degenerate_branch(gpu, oracle):
+    # fewer than 0.25*sqrt(N) connected nodes -> random C nodes (mis_set.m:30-34)
+    N = 400
+    A = sp.identity(N, format="lil") * 2.0
+    A[0, 1] = A[1, 0] = -1.0
+    oracle.rng_reset(); gpu.rng_reset()
+    r = oracle.mis_set(A.tocsr(), 0.25); g = gpu.mis_set(A.tocsr(), 0.25)
+    assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1])
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn == min(int(np.sqrt(N)) + 1, 25)
+
+
+def test_cf_split(gpu, oracle):
+    for seed, n, d in [(0, 50, 0.1), (1, 400, 0.01), (2, 300, 0.05)]:
+        S = rand_sparse(n, n, d, seed); S = ((S + S.T) != 0).astype(float).tocsr()
+        c_ref, f_ref, _ = oracle.cf_split(S)
+        c, f, _ = gpu.cf_split(S)
+        assert np.array_equal(c, c_ref) and np.array_equal(f, f_ref)
+    path = sp.diags([np.ones(199), np.ones(199)], [-1, 1], format="csr")     # worst case: a path, depth N
+    c_ref, f_ref, _ = oracle.cf_split(path); c, f, _ = gpu.cf_split(path)
+    assert np.array_equal(c, c_ref) and np.array_equal(f, f_ref)
+
+
+AMG_OPTS = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1,
+            "inter": 1, "guess": None}
+
+
+@pytest.mark.parametrize("m,n,density,weights", [(60, 50, 0.06, False), (400, 300, 0.01, True), (900, 1000, 0.004, False),
+                                                   (2500, 2300, 0.0015, False)])
+def test_hierarchy_bit_exact(gpu, oracle, m, n, density, weights):
+    from oracle.amg import setup_hierarchy, amg_state
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=3 * m, weights=weights)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    o = dict(AMG_OPTS, fnode=n)
+    oracle.rng_reset(); gpu.rng_reset()
+    st = setup_hierarchy(Ae, o)
+    ref = [(A.copy(), P) for A, P in zip(st.Ack, st.Prok)]
+    levels = gpu.amg_setup(Ae, o)
+    assert [a.shape[0] for a, _ in levels] == [A.shape[0] for A, _ in ref]
+    for k, ((a, p), (A, P)) in enumerate(zip(levels, ref)):
+        assert_same_matrix(a, A, what=f"A level {k + 1}")
+        if k > 0:
+            assert_same_matrix(p, P, what=f"Pro level {k + 1}")
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    # one cycle on the live hierarchy (MG_Wcycle.m / MG_Vcycle.m)
+    r = np.random.RandomState(1).standard_normal(m + n)
+    for isnsp in (1, 0):
+        e_ref = oracle.MG_Wcycle(r, isnsp); e = gpu.MG_Wcycle(r, isnsp)
+        assert np.linalg.norm(e - e_ref) <= 1e-8 * np.linalg.norm(e_ref), f"W-cycle isnsp={isnsp}"
+        e_ref = oracle.MG_Vcycle(r, isnsp); e = gpu.MG_Vcycle(r, isnsp)
+        assert np.linalg.norm(e - e_ref) <= 1e-8 * np.linalg.norm(e_ref), f"V-cycle isnsp={isnsp}"
+    amg_state.clear(); gpu.amg_clear()
+
+
+@pytest.mark.parametrize("m,n,density,cycle", [(60, 50, 0.06, "w"), (400, 300, 0.01, "w"), (400, 300, 0.01, "v"),
+                                                 (2500, 2300, 0.0015, "w")])
+def test_class_amg_matches_oracle(gpu, oracle, m, n, density, cycle):
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=5 * m)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    guess = 0.01 * np.random.RandomState(2).random_sample(m + n)
+    o = dict(AMG_OPTS, fnode=n, cycle=cycle, guess=guess)
+    oracle.rng_reset(); gpu.rng_reset()
+    x_ref, it_ref, rel_ref, relk_ref, rho_ref = oracle.Class_AMG(Ae, f, o)
+    x, it, rel, relk, rho = gpu.Class_AMG(Ae, f, o)
+    assert it == it_ref
+    assert len(relk) == len(relk_ref)
+    big = relk_ref > 1e-9                      # histories <= 1e-8 relative until they hit the noise floor
+    assert np.allclose(relk[big], relk_ref[big], rtol=1e-6)
+    assert np.linalg.norm(Ae @ x - f) <= 1e-10 * np.linalg.norm(Ae @ guess - f) * 10
+    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+
+
+@pytest.mark.parametrize("precd", [1, 2, 5])
+def test_pcg_matches_oracle(gpu, oracle, precd):
+    m, n = 300, 260
+    pd, Ae, f = ssn_matrix(oracle, m, n, 0.02, seed=77, bk1=0.3)
+    o = {"retol": 1e-11, "maxit": 5000, "precd": precd, "guess": None}
+    if precd == 5:
+        o["nf"] = n
+    d_ref, it_ref, res_ref, resk_ref = oracle.PCG(Ae, f, o)
+    d, it, res, resk = gpu.PCG(Ae, f, o)
+    assert abs(it - it_ref) <= max(2, it_ref // 50)
+    assert res <= 1e-11 * 1.0001 or it == 5000
+    assert np.linalg.norm(d - d_ref) <= 1e-7 * np.linalg.norm(d_ref)
+    k = min(it, it_ref, 20)
+    assert np.allclose(resk[:k], resk_ref[:k], rtol=1e-6)
+    # defaults (nargin == 2), a guess, and the zero right-hand side (res = NaN, PCG.m:87)
+    d2, it2, res2, _ = gpu.PCG(Ae, f)
+    assert np.linalg.norm(d2 - d_ref) <= 1e-7 * np.linalg.norm(d_ref)
+    d3, it3, _, _ = gpu.PCG(Ae, f, dict(o, guess=d_ref))
+    assert it3 <= 2
+    d0, it0, res0, _ = gpu.PCG(Ae, np.zeros(m + n), {"retol": None, "maxit": None, "precd": None, "guess": None})
+    assert it0 == 0 and np.isnan(res0) and not d0.any()
+
+
+def test_pcg_errors(gpu):
+    A = sp.identity(10, format="csr")
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.PCG(A, np.ones(10), {"precd": 5, "retol": None, "maxit": None, "guess": None})
+    assert ei.value.status == "SSN_E_PCG_NF"
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.PCG(A, np.ones(10), {"precd": 4, "retol": None, "maxit": None, "guess": None})
+    assert ei.value.status == "SSN_E_UNSUPPORTED"
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.Class_AMG(A, np.ones(10), {"bigph": 1, "retol": None, "maxit": None, "theta": None, "smoth": None,
+                                        "cycle": None, "isnsp": None, "inter": None, "guess": None})
+    assert ei.value.status == "SSN_E_BIGPH_FNODE"

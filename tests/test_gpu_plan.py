@@ -1,0 +1,192 @@
+"""GPU parity tests, plan operators: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Tolerances: bit-exact for logical / integer / pattern results and for every
+value whose rounding sequence is fixed (Aty, z, prox, ASAt); <= 1e-10 relative for reductions
+(BASELINE.json north_star: "<=1e-10 on operators")."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, random_active_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+SHAPES = [(1, 1), (2, 3), (7, 5), (128, 64), (250, 130), (500, 500), (1027, 517), (2048, 300), (96, 2500)]
+
+
+def close(a, b, rtol=RTOL):
+    a = np.asarray(a); b = np.asarray(b)
+    scale = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    return np.all(np.abs(a - b) <= rtol * scale)
+
+
+def weights(m, n, seed, unit):
+    rs = np.random.RandomState(seed)
+    return (np.ones(m), np.ones(n)) if unit else (rs.random_sample(m) + 0.5, rs.random_sample(n) + 0.5)
+
+
+@pytest.mark.parametrize("m,n", SHAPES)
+@pytest.mark.parametrize("unit", [True, False])
+def test_ax_matches_oracle(gpu, oracle, m, n, unit):
+    rs = np.random.RandomState(m * 131 + n)
+    x = rs.standard_normal(m * n); p, q = weights(m, n, 1, unit)
+    y = gpu.Ax(x, p, q)
+    assert y.shape == (n + m,)
+    assert close(y, oracle.Ax(x, p, q))
+
+
+@pytest.mark.parametrize("m,n", SHAPES)
+def test_aty_bit_exact(gpu, oracle, m, n):
+    rs = np.random.RandomState(m * 7 + n)
+    y = rs.standard_normal(n + m); p, q = weights(m, n, 2, False)
+    assert np.array_equal(gpu.Aty(y, p, q), oracle.Aty(y, p, q))
+
+
+def test_ax_aty_device_tensors_and_adjointness(gpu):
+    import torch
+    m, n = 1536, 1100
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(m * n, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(n + m, dtype=torch.float64, device="cuda", generator=g)
+    p = torch.rand(m, dtype=torch.float64, device="cuda", generator=g) + 0.5
+    q = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) + 0.5
+    ax = gpu.Ax(x, p, q); aty = gpu.Aty(y, p, q)
+    assert ax.is_cuda and aty.is_cuda
+    lhs = float(ax @ y); rhs = float(x @ aty)
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1.0)
+
+
+def test_ax_equals_explicit_matrix(gpu, oracle):
+    m, n = 23, 17
+    rs = np.random.RandomState(0)
+    p, q = weights(m, n, 3, False)
+    A = oracle.explicit_A(p, q)                      # Class1/APD_SsN_Class1.m:47
+    x = rs.standard_normal(m * n); y = rs.standard_normal(m + n)
+    assert close(gpu.Ax(x, p, q), A @ x)
+    assert close(gpu.Aty(y, p, q), A.T @ y)
+
+
+@pytest.mark.parametrize("m,n", [(7, 5), (128, 64), (500, 500), (1027, 517), (2048, 300)])
+@pytest.mark.parametrize("gmode", ["inf", "scalar", "vector"])
+def test_prox_residual_matches_oracle(gpu, oracle, m, n, gmode):
+    rs = np.random.RandomState(m + 3 * n)
+    p, q = weights(m, n, 4, False)
+    w = rs.standard_normal(m * n); lam = 0.5 * rs.standard_normal(m + n); tk = 0.37
+    gama = {"inf": np.inf, "scalar": 0.8, "vector": rs.random_sample(m * n) + 0.1}[gmode]
+    z = 1 / tk * (w - oracle.Aty(lam, p, q))         # Class1/APD_SsN_Class1.m:139
+    s = (z >= 0) & (z <= gama)                       # :140
+    px = np.minimum(np.maximum(0.0, z), gama)        # :32
+    out = gpu.prox_residual(w, lam, p, q, tk, gama, want=("Axprox", "prox", "z", "s"))
+    assert np.array_equal(out["z"], z)
+    assert np.array_equal(out["s"].astype(bool), s)
+    assert np.array_equal(out["prox"], px)
+    assert out["count"] == int(s.sum())
+    assert close(out["Axprox"], oracle.Ax(px, p, q))
+    assert abs(out["norm2"] - float(px @ px)) <= 1e-12 * float(px @ px) + 1e-300
+    lite = gpu.prox_residual(w, lam, p, q, tk, gama, want=())      # line-search form: norm only
+    assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
+
+
+@pytest.mark.parametrize("m,n,density", [(5, 4, 0.5), (64, 48, 0.1), (300, 500, 0.02), (512, 512, 0.004),
+                                           (1000, 37, 0.3), (130, 2100, 0.01)])
+@pytest.mark.parametrize("unit", [True, False])
+def test_asat_pattern_and_values_exact(gpu, oracle, m, n, density, unit):
+    s, p, q = random_active_problem(m, n, density, seed=m + n, weights=not unit)
+    H_ref = oracle.ASAt(s, p, q)
+    H = gpu.ASAt(s, p, q).to_scipy().tocsc(); H.sort_indices()
+    assert H.shape == (m + n, m + n)
+    assert np.array_equal(H.indptr, H_ref.indptr)
+    assert np.array_equal(H.indices, H_ref.indices)
+    assert np.array_equal(H.data, H_ref.data)
+    # ASAt == A*diag(s)*A'  (ASAt.m:3-12)
+    A = oracle.explicit_A(p, q)
+    import scipy.sparse as sp
+    E = (A @ sp.diags(s.astype(float)) @ A.T).tocsc()
+    assert abs(E - H).max() <= 1e-10 * max(abs(E).max(), 1.0)
+
+
+def test_asat_edge_cases(gpu, oracle):
+    m, n = 40, 24
+    p, q = np.ones(m), np.ones(n)
+    H = gpu.ASAt(np.zeros(m * n, dtype=bool), p, q)
+    assert H.nnz == 0 and H.shape == (m + n, m + n)
+    s = np.ones(m * n, dtype=bool)
+    Hs = gpu.ASAt(s, p, q).to_scipy().tocsc(); Hs.sort_indices()
+    R = oracle.ASAt(s, p, q)
+    assert np.array_equal(Hs.indices, R.indices) and np.array_equal(Hs.data, R.data)
+    s = np.zeros((m, n), dtype=bool); s[3, :] = True; s[:, 5] = True      # isolated rows/cols elsewhere
+    Hs = gpu.ASAt(s.reshape(-1, order="F"), p, q).to_scipy().tocsc(); Hs.sort_indices()
+    R = oracle.ASAt(s.reshape(-1, order="F"), p, q)
+    assert np.array_equal(Hs.indptr, R.indptr) and np.array_equal(Hs.indices, R.indices)
+
+
+def test_asatz(gpu, oracle):
+    m = n = 48
+    s, p, q = random_active_problem(m, n, 0.1, seed=9, weights=True)
+    z = np.random.RandomState(1).standard_normal(m + n)
+    assert close(gpu.ASAtz(z, s, p, q), oracle.ASAtz(z, s, p, q))
+    # with p == q the reference's Q*p typo is harmless: ASAtz == ASAt*z   (ASAtz.m:10-13)
+    assert close(gpu.ASAtz(z, s, p, p), oracle.ASAt(s, p, p) @ z)
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.ASAtz(np.zeros(7), np.zeros(12, dtype=bool), np.ones(3), np.ones(4))
+    assert ei.value.status == "SSN_E_ASATZ_DIM"
+
+
+def test_invaat_invhht(gpu, oracle):
+    import scipy.sparse as sp
+    m, n = 31, 22
+    rs = np.random.RandomState(3)
+    p, q = weights(m, n, 5, False)
+    x = rs.standard_normal(m + n)
+    for args in [(), (0.7,), (0.7, 1.9)]:
+        assert close(gpu.invAAt(x, p, q, *args), oracle.invAAt(x, p, q, *args))
+    A = oracle.explicit_A(p, q)
+    y = gpu.invAAt(x, p, q, 0.7, 1.9)
+    M = sp.diags(np.concatenate([0.7 * np.ones(n), 1.9 * np.ones(m)])) + A @ A.T          # invAAt.m:2
+    assert close(M @ y, x, 1e-9)
+    phi = rs.random_sample(m * n); v = rs.standard_normal(m + n + 1)
+    assert close(gpu.invHHt(v, p, q, 0.6, phi), oracle.invHHt(v, p, q, 0.6, phi))
+
+
+def test_matlab_random_stream(gpu, oracle):
+    first = np.load(os.path.join(GOLDEN, "matlab_rand_first.npz"))["first"]
+    # MATLAB's documented first draws after start-up
+    assert np.allclose(first[:5], [0.8147236863931789, 0.9057919370756192, 0.12698681629350606,
+                                   0.9133758561390194, 0.6323592462254095], rtol=0, atol=1e-15)
+    gpu.rng_reset()
+    a = gpu.rand(313).cpu().numpy(); b = gpu.rand(687).cpu().numpy()          # state carries across calls
+    assert np.array_equal(np.concatenate([a, b]), first)
+    assert gpu.rng_drawn() == 1000
+    gpu.rng_reset(); oracle.rng_reset()
+    assert np.array_equal(gpu.rand(5000).cpu().numpy(), oracle.rand(5000))
+
+
+def test_full_size_properties_64x64_grid(gpu):
+    """Config 2 size (m=n=4096, 16.8M-entry plan): size-independent identities."""
+    import torch
+    m = n = 4096
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(m * n, dtype=torch.float64, device="cuda", generator=g)
+    ones_m = torch.ones(m, dtype=torch.float64, device="cuda"); ones_n = torch.ones(n, dtype=torch.float64, device="cuda")
+    y = gpu.Ax(x, ones_m, ones_n)
+    X = x.view(n, m)                                  # column-major m x n == row-major n x m
+    assert torch.allclose(y[:n], X.sum(dim=1), rtol=1e-11, atol=0)
+    assert torch.allclose(y[n:], X.sum(dim=0), rtol=1e-11, atol=0)
+    assert abs(float(y[:n].sum()) - float(y[n:].sum())) <= 1e-10 * float(y.sum())     # checksum of checksums
+    lam = torch.randn(m + n, dtype=torch.float64, device="cuda", generator=g)
+    z = gpu.Aty(lam, ones_m, ones_n)
+    assert torch.equal(z.view(n, m), lam[:n, None] + lam[None, n:])                   # rank-2 structure
+    lhs = float(gpu.Ax(x, ones_m, ones_n) @ lam); rhs = float(x @ z)
+    assert abs(lhs - rhs) <= 1e-10 * abs(lhs)
+    # fused residual == composition of the plain operators
+    out = gpu.prox_residual(x - 0.5, lam, ones_m, ones_n, 0.9, float("inf"), want=("Axprox", "s", "prox"))
+    zz = (1 / 0.9) * ((x - 0.5) - z)
+    assert torch.equal(out["s"].bool(), zz >= 0)
+    assert torch.equal(out["prox"], torch.clamp(zz, min=0.0))
+    assert torch.allclose(out["Axprox"], gpu.Ax(out["prox"], ones_m, ones_n), rtol=1e-11, atol=0)
+    H = gpu.ASAt(out["s"], ones_m, ones_n).to_scipy()
+    assert H.nnz == 2 * out["count"] + np.count_nonzero(H.diagonal())
+    assert abs(H - H.T).max() == 0
+    rowsum = np.asarray(H.sum(axis=1)).reshape(-1)
+    assert np.array_equal(rowsum, 2 * H.diagonal())   # unit weights: diag = degree, off-diag ones

@@ -1,0 +1,189 @@
+"""GPU parity tests, inner linear-solve dispatch: components, rescaled system, Hybrid_AMG,
+aug_PCG, AMG4POT, PCG4POT -- against the CPU oracle and against the committed golden systems
+(real SsN systems recorded from the reference's bundled input and from a grid problem)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden_systems, load_system, random_active_problem
+from test_gpu_amg import AMG_OPTS, assert_same_matrix, csc_sorted
+
+pytestmark = pytest.mark.gpu
+
+
+def prob(oracle, m, n, density, seed, weights=False, bk1=0.05, tk=0.8, tdiag=None, connect=True):
+    s, p, q = random_active_problem(m, n, density, seed, weights)
+    if not connect:
+        S = s.reshape((m, n), order="F").copy()
+        S[: m // 2, n // 2:] = False; S[m // 2:, : n // 2] = False          # two big blocks
+        S[0, :] = False; S[:, 0] = False; S[0, 0] = True                     # a 2-node component
+        S[1, :] = False                                                      # an isolated row node
+        S[2:6, :] = False; S[:, 2:5] = False; S[2:6, 2:5] = True             # a small dense component
+        s = S.reshape(-1, order="F")
+    H0 = oracle.ASAt(s, p, q)
+    t = np.zeros(m + n) if tdiag is None else tdiag
+    return {"bk1": bk1, "tk": tk, "p": p, "q": q, "T": sp.diags(t), "H0": H0,
+            "z": np.random.RandomState(seed + 1).standard_normal(m + n), "s": s}
+
+
+def test_components_ordering(gpu, oracle):
+    for seed, n, d in [(0, 60, 0.02), (1, 500, 0.002), (2, 300, 0.01)]:
+        rs = np.random.RandomState(seed)
+        A = sp.random(n, n, density=d, random_state=rs, format="csr"); A = (A + A.T + sp.identity(n)).tocsr()
+        b_ref, s_ref, p_ref, r_ref = oracle.components(A)
+        b, s, p, r = gpu.components(A)
+        assert np.array_equal(b, b_ref) and np.array_equal(s, s_ref)
+        assert np.array_equal(p, p_ref) and np.array_equal(r, r_ref)
+    # a long path: label propagation must still converge (pointer jumping)
+    n = 3000
+    P = sp.diags([np.ones(n - 1), np.ones(n - 1), 2 * np.ones(n)], [-1, 1, 0], format="csr")
+    b, s, p, r = gpu.components(P)
+    assert s.tolist() == [n] and np.array_equal(p, np.arange(n))
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.components(sp.random(4, 5, density=0.5, format="csr"))
+    assert ei.value.status == "SSN_E_NOT_SQUARE"
+
+
+@pytest.mark.parametrize("weights", [False, True])
+def test_rescaled_system_bit_exact(gpu, oracle, weights):
+    from oracle.solvers import rescaled_system
+    m, n = 120, 90
+    t = np.random.RandomState(0).random_sample(m + n) * (np.arange(m + n) % 3 == 0)
+    pd = prob(oracle, m, n, 0.04, 11, weights, tdiag=t)
+    qp, A0, Qd, Kd, Ae_ref, f_ref = rescaled_system(pd)
+    Ae, f = gpu.rescaled_system(pd)
+    assert_same_matrix(Ae, Ae_ref, what="Ae")
+    assert np.array_equal(f, f_ref)
+
+
+@pytest.mark.parametrize("m,n,density,weights", [(60, 50, 0.06, False), (400, 300, 0.01, True), (1200, 1000, 0.003, False)])
+def test_hybrid_amg_connected(gpu, oracle, m, n, density, weights):
+    pd = prob(oracle, m, n, density, 21 + m, weights)
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, res_ref, info_ref = oracle.Hybrid_AMG(pd, AMG_OPTS)
+    zeta, it, res, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert list(info) == list(info_ref)
+    assert it == it_ref
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    Jk = pd["bk1"] * sp.identity(m + n) + pd["H0"] / pd["tk"]              # Class1/APD_SsN_Class1.m:143
+    assert np.linalg.norm(Jk @ zeta - pd["z"]) <= 1e-9 * np.linalg.norm(pd["z"])
+    assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+
+
+def test_hybrid_amg_disconnected_large_and_small(gpu, oracle):
+    m, n = 420, 380
+    pd = prob(oracle, m, n, 0.02, 5, connect=False)
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, res_ref, info_ref = oracle.Hybrid_AMG(pd, AMG_OPTS)
+    zeta, it, res, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert info_ref[0] > 3
+    assert list(info) == list(info_ref) and it == it_ref
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    Jk = pd["bk1"] * sp.identity(m + n) + pd["H0"] / pd["tk"]
+    assert np.linalg.norm(Jk @ zeta - pd["z"]) <= 1e-9 * np.linalg.norm(pd["z"])
+    assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+
+
+def test_hybrid_amg_all_isolated(gpu, oracle):
+    # E = 0: every node is its own component, pure diagonal solve (first SsN step of outer it 2)
+    m, n = 50, 40
+    pd = {"bk1": 0.3, "tk": 0.7, "p": np.ones(m), "q": np.ones(n), "T": sp.diags(np.zeros(m + n)),
+          "H0": oracle.ASAt(np.zeros(m * n, dtype=bool), np.ones(m), np.ones(n)),
+          "z": np.random.RandomState(0).standard_normal(m + n)}
+    z_ref, it_ref, res_ref, info_ref = oracle.Hybrid_AMG(pd, AMG_OPTS)
+    zeta, it, res, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert list(info) == list(info_ref) == [m + n, 0] and it == 0
+    assert np.allclose(zeta, z_ref, rtol=1e-14)
+
+
+def test_hybrid_amg_spd_branch_with_T(gpu, oracle):
+    # Class2: T = diag(t) nonzero -> isnsp = 0 (Hybrid_AMG.m:32-35)
+    m, n = 200, 180
+    t = (np.random.RandomState(3).random_sample(m + n) > 0.5).astype(float)
+    pd = prob(oracle, m, n, 0.03, 9, tdiag=t)
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, _, info_ref = oracle.Hybrid_AMG(pd, AMG_OPTS)
+    zeta, it, _, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert list(info) == list(info_ref) and it == it_ref
+    assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+
+
+def test_pq_zero_error(gpu, oracle):
+    m, n = 20, 15
+    pd = prob(oracle, m, n, 0.1, 2)
+    pd["q"] = pd["q"].copy(); pd["q"][3] = 0.0
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert ei.value.status == "SSN_E_PQ_ZERO"                                # Hybrid_AMG.m:18-19
+
+
+@pytest.mark.parametrize("path", golden_systems("bundled500") + golden_systems("grid12"))
+def test_golden_ssn_systems(gpu, path):
+    """Real SsN systems (recorded by tests/golden/make_golden.py): ASAt pattern, hierarchy sizes,
+    C/F vectors, cycle counts and solution against the committed oracle outputs."""
+    d = load_system(path)
+    m, n = d["m"], d["n"]
+    p, q = np.ones(m), np.ones(n)
+    H = gpu.ASAt(d["s"], p, q)
+    Hs = csc_sorted(H.to_scipy())
+    assert np.array_equal(Hs.indptr, d["H_indptr"]) and np.array_equal(Hs.indices, d["H_indices"])
+    assert np.array_equal(Hs.data, d["H_data"])
+    pd = {"bk1": float(d["bk1"]), "tk": float(d["tk"]), "p": p, "q": q, "T": None, "H0": H, "z": d["z"]}
+    gpu.rng_reset()
+    zeta, it, res, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+    assert list(info) == list(d["info"])
+    assert it == int(d["it"])
+    assert gpu.rng_drawn() == int(d["drawn"])
+    assert np.linalg.norm(zeta - d["zeta"]) <= 1e-6 * np.linalg.norm(d["zeta"])
+    Jk = pd["bk1"] * sp.identity(m + n) + Hs / pd["tk"]
+    assert np.linalg.norm(Jk @ zeta - d["z"]) <= 1e-9 * np.linalg.norm(d["z"])
+    if "level_sizes" in d:
+        Ae, f = gpu.rescaled_system(pd)
+        gpu.rng_reset()
+        gpu.rand(m + n)                                  # the initial guess is drawn first (Hybrid_AMG.m:40)
+        levels = gpu.amg_setup(Ae, dict(AMG_OPTS, fnode=n, isnsp=1))
+        assert [a.shape[0] for a, _ in levels] == d["level_sizes"].tolist()
+        assert [a.nnz for a, _ in levels] == d["level_nnz"].tolist()
+        for k in range(2, len(levels)):
+            isC = np.unpackbits(d[f"isC_{k}"])[: levels[k - 1][0].shape[0]].astype(bool)
+            Pk = levels[k][1].to_scipy().tocsr()
+            unit_rows = (np.diff(Pk.indptr) == 1) & (Pk.data[np.minimum(Pk.indptr[:-1], Pk.nnz - 1)] == 1.0)
+            assert np.all(unit_rows[isC]), f"C nodes of level {k} differ from the golden split"
+        gpu.amg_clear()
+
+
+def test_aug_pcg(gpu, oracle):
+    m, n = 150, 130
+    for connect in (True, False):
+        pd = prob(oracle, m, n, 0.03, 31, bk1=0.2, connect=connect)
+        o = {"retol": 1e-11, "maxit": 10000, "precd": 2, "guess": None}
+        z_ref, it_ref, res_ref, info_ref = oracle.aug_PCG(pd, o)
+        zeta, it, res, info = gpu.aug_PCG(pd, o)
+        assert list(info) == list(info_ref)
+        assert abs(it - it_ref) <= max(3, it_ref // 20)
+        assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+
+
+def test_pot_bordered_solves(gpu, oracle):
+    m, n = 140, 120
+    t = (np.random.RandomState(4).random_sample(m + n) > 0.4).astype(float)
+    pd = prob(oracle, m, n, 0.03, 41, bk1=0.2, tdiag=t)
+    pd["phi"] = np.random.RandomState(5).random_sample(m * n) + 0.5
+    pd["z"] = np.random.RandomState(6).standard_normal(m + n + 1)
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, res_ref, info_ref = oracle.AMG4POT(pd, dict(AMG_OPTS, maxit=40, smoth=10), "amg")
+    zeta, it, res, info = gpu.AMG4POT(pd, dict(AMG_OPTS, maxit=40, smoth=10), "amg")
+    assert list(info) == list(info_ref) and it == it_ref
+    assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+    # the bordered system itself (Class2/AMG4POT.m:4-10)
+    s = pd["s"].astype(float); A = oracle.explicit_A(pd["p"], pd["q"])
+    ss = A @ (s * pd["phi"])
+    cH = sp.bmat([[pd["T"] + pd["H0"], ss[:, None]], [ss[None, :], [[pd["phi"] @ (s * pd["phi"])]]]])
+    He = pd["bk1"] * sp.identity(m + n + 1) + cH / pd["tk"]
+    assert np.linalg.norm(He @ zeta - pd["z"]) <= 1e-8 * np.linalg.norm(pd["z"])
+    o = {"retol": 1e-11, "maxit": 10000, "precd": 2, "guess": None}
+    z2_ref, *_ = oracle.PCG4POT(pd, o)
+    z2, *_ = gpu.PCG4POT(pd, o)
+    assert np.linalg.norm(z2 - z2_ref) <= 1e-7 * np.linalg.norm(z2_ref)
+    with pytest.raises(gpu.SsnError):
+        gpu.AMG4POT(pd, AMG_OPTS, "twogrid")
