@@ -58,6 +58,8 @@ SIGNATURES = {
     "ssn_synchronize": (_int, [_vp]),
     "ssn_version": (_int, []),
     "ssn_launch_count": (_i64, [_vp]),
+    "ssn_profile_enable": (_int, [_vp, _int]),
+    "ssn_profile_dump": (C.c_char_p, [_vp]),
     "ssn_rng_reset": (_int, [_vp, C.c_uint32]),
     "ssn_rng_drawn": (_i64, [_vp]),
     "ssn_rand": (_int, [_vp, _i64, _vp]),

@@ -489,3 +489,12 @@ def transpose(A):
 
 def launch_count():
     return context().launches()
+
+
+def profile(enable=True):
+    """Switch the library's phase profiler on/off (development aid)."""
+    ctx = context(); ctx.lib.ssn_profile_enable(ctx.h, 1 if enable else 0)
+
+
+def profile_dump():
+    ctx = context(); return ctx.lib.ssn_profile_dump(ctx.h).decode()

@@ -564,11 +564,13 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     SSN_REQUIRE(o.inter < 2, SSN_E_UNSUPPORTED, "transfer: ideal interpolation (inter = 2) is not supported");
     Buf<uint8_t> isC(c, n), isF(c, n), flags;
     const int g = cdiv(n, 256), gw = cdiv((int64_t)n * 32, 256);
+    Phase ph_all(c, bigraph ? "setup.transfer(level1)" : "setup.transfer(mis levels)");
     if (bigraph) {
         SSN_REQUIRE(o.fnode > 0 && o.fnode <= n, SSN_E_BIGPH_FNODE, "amg_options.bigph = 1 requires Nf > 0");
         SSN_LAUNCH(c, bigraph_cf_kernel, g, 256, 0, n, o.fnode, isC.p, isF.p);
         if (as_out) { flags.alloc(c, A.nnz); strength_flags(c, A, o.theta, flags); }
     } else {
+        Phase ph(c, "setup.mis_set");
         mis_set(c, A, o.theta, isC, isF, flags);                          // transfer.m:41
     }
     // partition check + index maps
@@ -596,6 +598,7 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
                want_m ? M.val.p : nullptr, nullptr);
     Csr W;
     if (want_m) {
+        Phase ph(c, "setup.interp W2 spgemm+add");
         Csr W2 = spgemm(c, M, W1);                                        // transfer.m:51
         W = sparse_add(c, W1, 0.5, W2);                                   // transfer.m:54-55 (always taken)
     } else {
@@ -611,9 +614,10 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     Pro = csr_alloc_from_counts(c, n, Nc, pcnt);
     SSN_LAUNCH(c, pro_fill_kernel, gw, 256, 0, n, isF.p, fidx.p, cidx.p, W.ptr.p, W.idx.p, W.val.p, Pro.ptr.p, Pro.idx.p, Pro.val.p);
     // Ac = (Pro'*A)*Pro                                                  // transfer.m:66
-    Csr Pt = transpose(c, Pro);
-    Csr T1 = spgemm(c, Pt, A);
-    Ac = spgemm(c, T1, Pro);
+    Csr Pt, T1;
+    { Phase ph(c, "setup.transpose Pro"); Pt = transpose(c, Pro); }
+    { Phase ph(c, bigraph ? "setup.galerkin L1 Pt*A" : "setup.galerkin Lk Pt*A"); T1 = spgemm(c, Pt, A); }
+    { Phase ph(c, bigraph ? "setup.galerkin L1 T1*P" : "setup.galerkin Lk T1*P"); Ac = spgemm(c, T1, Pro); }
     if (isC_out) *isC_out = std::move(isC);
     if (as_out) *as_out = std::move(flags);
 }
@@ -634,6 +638,7 @@ static constexpr int kSmallN = 2048;
 static constexpr int64_t kSmallNnz = 1 << 17;
 
 static void finish_level(ssn_ctx* c, Level& L, bool bigph_level, int Nf) {
+    Phase ph(c, "setup.finish_level");
     const int n = L.N = (int)L.A.nrows;
     L.bigph = bigph_level ? 1 : 0; L.Nf = bigph_level ? Nf : 0;
     Buf<double> diag(c, n);
@@ -650,6 +655,7 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
     SSN_REQUIRE(A.nrows == A.ncols, SSN_E_NOT_SQUARE, "Class_AMG: matrix must be square");
     if (o.bigph) SSN_REQUIRE(o.fnode > 0, SSN_E_BIGPH_FNODE, "amg_options.bigph = 1 requires Nf > 0");
     amg_clear(c);
+    Phase ph_setup(c, "amg_setup total");
     std::unique_ptr<Hierarchy> H(new Hierarchy());
     H->smoth = o.smoth;
     H->lv.emplace_back();

@@ -415,6 +415,7 @@ void smooth_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, int post, bool e_ze
 void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {
     if (k >= H.small_from || k == H.J - 1) {
         SSN_REQUIRE(H.J - k <= 16, SSN_E_INVALID, "hierarchy deeper than 16 small levels");
+        Phase ph(c, "solve.coarse_cycle_kernel");
         SSN_LAUNCH(c, coarse_cycle_kernel, 1, kCycleThreads, 0, H.dev.p, k, H.J, H.smoth, isnsp, wcycle ? 1 : 0, e_zero ? 1 : 0);
         return;
     }
@@ -445,9 +446,11 @@ void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev,
 void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, bool keep, double* x, int* it_out,
                double* rel_res_out, double* rel_resk, double* rhok, int* hist_len) {
     amg_setup(c, A, o);
+    Phase ph_solve(c, "class_amg solve loop total");
     Hierarchy& H = *c->hier;
     Level& L = H.lv[0];
     const int n = L.N;
+    if (c->prof) { std::string s = "levels:"; for (auto& l : H.lv) s += " " + std::to_string(l.N) + "/" + std::to_string(l.A.nnz); s += " small_from=" + std::to_string(H.small_from); c->prof_acc[s].second += 1; }
     if (o.guess) SSN_CUDA(cudaMemcpyAsync(x, o.guess, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     else fill_double(c, x, n, 0.0);
     int it = 0;

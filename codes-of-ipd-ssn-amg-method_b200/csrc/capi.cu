@@ -84,6 +84,19 @@ int ssn_set_stream(ssn_ctx* c, void* s) { if (!c) return SSN_E_INVALID; c->strea
 int ssn_synchronize(ssn_ctx* c) { return guarded(c, [&] { sync(c); }); }
 int64_t ssn_launch_count(ssn_ctx* c) { return c ? c->launches : 0; }
 
+int ssn_profile_enable(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->prof = on != 0; return SSN_OK; }
+const char* ssn_profile_dump(ssn_ctx* c) {
+    if (!c) return "";
+    c->prof_text.clear();
+    char line[256];
+    for (auto& kv : c->prof_acc) {
+        snprintf(line, sizeof(line), "%-44s %12.3f  calls %8ld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        c->prof_text += line;
+    }
+    c->prof_acc.clear();
+    return c->prof_text.c_str();
+}
+
 int ssn_rng_reset(ssn_ctx* c, uint32_t seed) { return guarded(c, [&] { rng_reset(c, seed); sync(c); }); }
 int64_t ssn_rng_drawn(ssn_ctx* c) { return c ? c->rng_drawn : 0; }
 int ssn_rand(ssn_ctx* c, int64_t count, double* out) { return guarded(c, [&] { rng_rand(c, count, out); sync(c); }); }

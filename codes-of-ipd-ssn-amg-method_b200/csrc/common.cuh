@@ -11,6 +11,8 @@
 #include <vector>
 #include <memory>
 #include <stdexcept>
+#include <map>
+#include <chrono>
 
 #include "../../include/ssnamg.h"
 
@@ -54,6 +56,10 @@ struct ssn_ctx {
     int64_t rng_drawn = 0;
     // Class_AMG hierarchy (the reference's globals Ack/Prok/Rk/J/smoth_it)
     ssn::Hierarchy* hier = nullptr;
+    // optional phase profiler (ssn_profile_enable): wall time per named phase, stream-synchronised
+    bool prof = false;
+    std::map<std::string, std::pair<double, long>> prof_acc;
+    std::string prof_text;
 };
 
 namespace ssn {
@@ -126,6 +132,21 @@ inline void check_launch(ssn_ctx* c, const char* what) {
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                   \
         ::ssn::check_launch((ctx), #kernel);                                               \
     } while (0)
+
+struct Phase {
+    ssn_ctx* c; const char* name; std::chrono::steady_clock::time_point t0; long l0;
+    Phase(ssn_ctx* ctx, const char* n) : c(ctx), name(n) {
+        if (c->prof) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); l0 = c->launches; }
+    }
+    ~Phase() {
+        if (c->prof) {
+            cudaStreamSynchronize(c->stream);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            auto& a = c->prof_acc[name]; a.first += ms; a.second += 1;
+            auto& b = c->prof_acc[std::string(name) + " #launches"]; b.first += (double)(c->launches - l0); b.second += 1;
+        }
+    }
+};
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

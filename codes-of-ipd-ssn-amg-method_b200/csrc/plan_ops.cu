@@ -61,7 +61,110 @@ __device__ __forceinline__ double butterfly4(double v0, double v1, double v2, do
     return b;
 }
 
-template <int MODE, bool VEC, bool GVEC>
+enum { G_INF = 0, G_SCALAR = 1, G_VECTOR = 2 };
+
+// element offset of row slot k relative to row slot 0 of the lane
+template <bool VEC> __device__ __forceinline__ constexpr int roff(int k) { return VEC ? (64 * (k >> 1) + (k & 1)) : (32 * k); }
+
+// One batch of 4 columns x 4 rows per lane.  `off` is the element offset of (column c, row slot 0).
+// FULL: every row and column of the batch is inside the plan (no predicates in the hot path).
+template <int MODE, bool VEC, int GM, bool FULL>
+__device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_t c, int64_t c1, const bool (&rok)[4],
+                                           const double (&pv)[4], const double (&y2v)[4], double (&rs)[4], double& n2,
+                                           int& cnt, double (&cs)[4]) {
+    const size_t m = (size_t)a.m;
+    double v[4][4];
+    double g[GM == G_VECTOR ? 4 : 1][4];
+    // ---- issue all loads of the batch first (8 x 16 B per lane in flight)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const bool cok = FULL || (c + cc < c1);
+        const double* xp = a.x + off + (size_t)cc * m;
+        if (VEC) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double2 t = make_double2(0.0, 0.0);
+                if (FULL || (cok && rok[2 * h])) t = __ldcs(reinterpret_cast<const double2*>(xp + roff<VEC>(2 * h)));
+                v[cc][2 * h] = t.x; v[cc][2 * h + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[cc][k] = (FULL || (cok && rok[k])) ? __ldcs(xp + roff<VEC>(k)) : 0.0;
+        }
+        if (MODE == MODE_PROX && GM == G_VECTOR) {
+            const double* gp = a.gama + off + (size_t)cc * m;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g[GM == G_VECTOR ? cc : 0][k] = (FULL || (cok && rok[k])) ? __ldcs(gp + roff<VEC>(k)) : 0.0;
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const bool cok = FULL || (c + cc < c1);
+        const double qj = cok ? __ldg(a.q + c + cc) : 0.0;
+        double csum = 0.0;
+        if (MODE == MODE_AX) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                csum = fma(v[cc][k], pv[k], csum);
+                rs[k] = fma(v[cc][k], qj, rs[k]);
+            }
+        } else {
+            const double y1j = cok ? __ldg(a.lam + c + cc) : 0.0;
+            double px[4], zz[4]; unsigned char sb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // z = (1/tk) * (w - (p_i*y1_j + y2_i*q_j)), rounded like the reference expression
+                // `1/tk*(wk-Aty(lk,p,q))` (mul, mul, add, sub, mul; no FMA contraction).
+                const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
+                const bool live = FULL || (cok && rok[k]);
+                const bool nonneg = live && (z >= 0.0);
+                bool act; double pz;
+                if (GM == G_INF) { act = nonneg; pz = nonneg ? z : 0.0; }                 // min(max(0,z),Inf)
+                else {
+                    const double gm = (GM == G_VECTOR) ? g[GM == G_VECTOR ? cc : 0][k] : a.gama_s;
+                    const bool below = (z <= gm);
+                    act = nonneg && below;
+                    pz = nonneg ? (below ? z : gm) : (live ? fmin(0.0, gm) : 0.0);       // min(max(0,z),gama)
+                }
+                px[k] = pz; zz[k] = z; sb[k] = act ? 1 : 0;
+                cnt += act ? 1 : 0;
+                n2 = fma(pz, pz, n2);
+                if (a.want_sums) { csum = fma(pz, pv[k], csum); rs[k] = fma(pz, qj, rs[k]); }
+            }
+            if (a.prox_out || a.z_out || a.s_out) {
+                if (cok) {
+                    const size_t o = off + (size_t)cc * m;
+                    if (VEC) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (FULL || rok[2 * h]) {
+                                if (a.prox_out) __stcs(reinterpret_cast<double2*>(a.prox_out + o + roff<VEC>(2 * h)),
+                                                       make_double2(px[2 * h], px[2 * h + 1]));
+                                if (a.z_out) __stcs(reinterpret_cast<double2*>(a.z_out + o + roff<VEC>(2 * h)),
+                                                    make_double2(zz[2 * h], zz[2 * h + 1]));
+                                if (a.s_out) *reinterpret_cast<uchar2*>(a.s_out + o + roff<VEC>(2 * h)) =
+                                                 make_uchar2(sb[2 * h], sb[2 * h + 1]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (FULL || rok[k]) {
+                                if (a.prox_out) a.prox_out[o + roff<VEC>(k)] = px[k];
+                                if (a.z_out) a.z_out[o + roff<VEC>(k)] = zz[k];
+                                if (a.s_out) a.s_out[o + roff<VEC>(k)] = sb[k];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cs[cc] = csum;
+    }
+}
+
+template <int MODE, bool VEC, int GM>
 __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs a) {
     extern __shared__ double colbuf[];                 // [kWarps][cols_per_chunk]
     __shared__ double red[32];
@@ -72,111 +175,28 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
     const int64_t c0 = (int64_t)chunk * cpc;
     const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
     const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
+    const int64_t row0 = rbase + (VEC ? 2 * lane : lane);
 
-    int64_t row[4]; bool rok[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        row[k] = VEC ? (rbase + 64 * (k >> 1) + 2 * lane + (k & 1)) : (rbase + 32 * k + lane);
-        rok[k] = row[k] < m;
-    }
+    bool rok[4];
     double pv[4], y2v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        pv[k] = rok[k] ? a.p[row[k]] : 0.0;
-        y2v[k] = (MODE == MODE_PROX && rok[k]) ? a.lam[n + row[k]] : 0.0;
+        const int64_t r = row0 + roff<VEC>(k);
+        rok[k] = r < m;
+        pv[k] = rok[k] ? a.p[r] : 0.0;
+        y2v[k] = (MODE == MODE_PROX && rok[k]) ? a.lam[n + r] : 0.0;
     }
     double rs[4] = {0.0, 0.0, 0.0, 0.0};
     double n2 = 0.0;
     int cnt = 0;
-    constexpr bool has_gvec = (MODE == MODE_PROX) && GVEC;
+    const bool strip_full = (rbase + kStripRows <= m);     // warp-uniform
+    size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
+    const size_t step = 4 * (size_t)m;
 
-    for (int64_t c = c0; c < c1; c += 4) {
-        double v[4][4];
-        double g[GVEC ? 4 : 1][4];
-        // ---- issue all loads of this 4-column batch first (8 x 16 B per lane in flight)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int64_t col = c + cc;
-            const bool cok = col < c1;
-            const double* base = a.x + (size_t)col * (size_t)m;
-            if (VEC) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double2 t = make_double2(0.0, 0.0);
-                    if (cok && rok[2 * h]) t = __ldcs(reinterpret_cast<const double2*>(base + row[2 * h]));
-                    v[cc][2 * h] = t.x; v[cc][2 * h + 1] = t.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[cc][k] = (cok && rok[k]) ? __ldcs(base + row[k]) : 0.0;
-            }
-            if (has_gvec) {
-                const double* gb = a.gama + (size_t)col * (size_t)m;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) g[GVEC ? cc : 0][k] = (cok && rok[k]) ? __ldcs(gb + row[k]) : 0.0;
-            }
-        }
+    for (int64_t c = c0; c < c1; c += 4, off += step) {
         double cs[4];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int64_t col = c + cc;
-            const bool cok = col < c1;
-            const double qj = cok ? __ldg(a.q + col) : 0.0;
-            double csum = 0.0;
-            if (MODE == MODE_AX) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    csum = fma(v[cc][k], pv[k], csum);
-                    rs[k] = fma(v[cc][k], qj, rs[k]);
-                }
-            } else {
-                const double y1j = cok ? __ldg(a.lam + col) : 0.0;
-                double px[4], zz[4]; unsigned char sb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // z = (1/tk) * (w - (p_i*y1_j + y2_i*q_j)), rounded like the reference
-                    // expression `1/tk*(wk-Aty(lk,p,q))` (mul, mul, add, sub, mul; no FMA).
-                    const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
-                    const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
-                    const double gm = has_gvec ? g[GVEC ? cc : 0][k] : a.gama_s;
-                    const bool live = cok && rok[k];
-                    const bool act = live && (z >= 0.0) && (z <= gm);
-                    double pz = fmin(fmax(0.0, z), gm);
-                    pz = live ? pz : 0.0;
-                    px[k] = pz; zz[k] = z; sb[k] = act ? 1 : 0;
-                    cnt += act ? 1 : 0;
-                    n2 = fma(pz, pz, n2);
-                    csum = fma(pz, pv[k], csum);
-                    rs[k] = fma(pz, qj, rs[k]);
-                }
-                if (cok) {
-                    const size_t off = (size_t)col * (size_t)m;
-                    if (VEC) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (rok[2 * h]) {
-                                if (a.prox_out) __stcs(reinterpret_cast<double2*>(a.prox_out + off + row[2 * h]),
-                                                       make_double2(px[2 * h], px[2 * h + 1]));
-                                if (a.z_out) __stcs(reinterpret_cast<double2*>(a.z_out + off + row[2 * h]),
-                                                    make_double2(zz[2 * h], zz[2 * h + 1]));
-                                if (a.s_out) *reinterpret_cast<uchar2*>(a.s_out + off + row[2 * h]) =
-                                                 make_uchar2(sb[2 * h], sb[2 * h + 1]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (rok[k]) {
-                                if (a.prox_out) a.prox_out[off + row[k]] = px[k];
-                                if (a.z_out) a.z_out[off + row[k]] = zz[k];
-                                if (a.s_out) a.s_out[off + row[k]] = sb[k];
-                            }
-                        }
-                    }
-                }
-            }
-            cs[cc] = csum;
-        }
+        if (strip_full && c + 4 <= c1) plan_batch<MODE, VEC, GM, true>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs);
+        else                           plan_batch<MODE, VEC, GM, false>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs);
         if (a.want_sums) {
             const double tot = butterfly4(cs[0], cs[1], cs[2], cs[3], lane);
             const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
     if (a.want_sums) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (rok[k]) a.rowpart[(size_t)chunk * (size_t)m + row[k]] = rs[k];
+            if (rok[k]) a.rowpart[(size_t)chunk * (size_t)m + row0 + roff<VEC>(k)] = rs[k];
         __syncthreads();
         const int ncols = (int)(c1 - c0);
         for (int j = threadIdx.x; j < ncols; j += kThreads) {
@@ -373,8 +393,8 @@ void plan_ax(ssn_ctx* c, const double* x, const double* p, const double* q, int6
     a.rowpart = rowpart; a.colpart = colpart; a.want_sums = 1;
     const dim3 grid(t.chunks, t.groups);
     const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
-    if (vec_ok(x, m)) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, true, false>), grid, kThreads, smem, a);
-    else              SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, false, false>), grid, kThreads, smem, a);
+    if (vec_ok(x, m)) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, true, G_INF>), grid, kThreads, smem, a);
+    else              SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, false, G_INF>), grid, kThreads, smem, a);
     SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, nullptr, t.chunks,
                t.groups, m, n, 0, y, nullptr);
 }
@@ -404,13 +424,11 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
     const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
     bool vec = vec_ok(w, m) && (!gama || vec_ok(gama, m)) && (!prox_out || vec_ok(prox_out, m)) &&
                (!z_out || vec_ok(z_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
-    if (gama) {
-        if (vec) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, true, true>), grid, kThreads, smem, a);
-        else     SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, false, true>), grid, kThreads, smem, a);
-    } else {
-        if (vec) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, true, false>), grid, kThreads, smem, a);
-        else     SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, false, false>), grid, kThreads, smem, a);
-    }
+    const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+#define SSN_PROX_LAUNCH(V, G) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, V, G>), grid, kThreads, smem, a)
+    if (vec) { if (gm == G_INF) SSN_PROX_LAUNCH(true, G_INF); else if (gm == G_SCALAR) SSN_PROX_LAUNCH(true, G_SCALAR); else SSN_PROX_LAUNCH(true, G_VECTOR); }
+    else     { if (gm == G_INF) SSN_PROX_LAUNCH(false, G_INF); else if (gm == G_SCALAR) SSN_PROX_LAUNCH(false, G_SCALAR); else SSN_PROX_LAUNCH(false, G_VECTOR); }
+#undef SSN_PROX_LAUNCH
     SSN_LAUNCH(c, plan_finish_kernel, axp_out ? cdiv(m + n, 256) : 1, 256, 0, rowpart.p, colpart.p, scalpart.p,
                t.chunks, t.groups, m, n, nblocks, axp_out, scal2_dev);
 }

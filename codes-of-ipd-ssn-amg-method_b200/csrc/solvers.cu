@@ -376,10 +376,10 @@ void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts
     const int n = (int)pd->n, m = (int)pd->m, N = n + m;
     const double bk1 = pd->bk1, tk = pd->tk;
     Csr Ae; Buf<double> f(c, N), qp, Kd, u(c, N);
-    rescaled_system(c, pd, Ae, f, qp, Kd);                                    // Hybrid_AMG.m:17-24
+    { Phase ph(c, "hybrid.rescaled_system"); rescaled_system(c, pd, Ae, f, qp, Kd); }                                   // Hybrid_AMG.m:17-24
     Buf<int> blocks(c, N), sizes(c, N), perm(c, N), r(c, (size_t)N + 1);
     int ncomp = 0;
-    components(c, Ae, blocks, sizes, perm, r, &ncomp);                        // :27
+    { Phase ph(c, "hybrid.components"); components(c, Ae, blocks, sizes, perm, r, &ncomp); }                       // :27
     AmgOptions o = resolve_options(opts);
     int itamg = 0, it_num = 0; double resamg = 0.0;
     const double gscale = bk1 * tk;

@@ -1,0 +1,186 @@
+"""Device-resident caller of the inner solve: the reference's script bodies
+(Class1/APD_SsN_Class1.m, Class1/warmup_class1.m) with every plan-sized array held as a torch
+CUDA tensor (the analogue of running the MATLAB script on ``gpuArray``s) and every call on the
+hot path going to the CUDA operators of this package.
+
+The script is the CALLER of the hot path, kept here so that realistic
+SsN states exist for the benchmark and so the full solve can be timed end to end.  The
+semismooth-Newton residual, the active set and the line-search objective use the fused
+``prox_residual`` kernel (one read of ``wk`` per evaluation) instead of the reference's
+``Aty`` -> prox -> ``Ax`` chain; the arithmetic per entry is identical.
+"""
+import math
+import time
+
+import numpy as np
+
+from . import api
+
+CLASS1_AMG_OPTIONS = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 1 / 4, "smoth": 5, "cycle": "w",
+                      "isnsp": 1, "inter": 1, "guess": None}            # Class1/APD_SsN_Class1.m:87-88
+CLASS1_PCG_OPTIONS = {"retol": 1e-11, "maxit": 10000, "precd": 2, "guess": None}   # :81
+
+
+def _t(x, torch):
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda", dtype=torch.float64).reshape(-1)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))).cuda()
+
+
+def warmup_class1(c, r, l, p, q, gama, res=0.0, maxit=100):
+    """A-ADMM warm start -- reference Class1/warmup_class1.m:18-96, on the device."""
+    import torch
+    c, r, l, p, q = (_t(v, torch) for v in (c, r, l, p, q))
+    m, n = l.numel(), r.numel()
+    gam = None if (np.isscalar(gama) and math.isinf(gama)) else (gama if np.isscalar(gama) else _t(gama, torch))
+    prox = (lambda x: torch.clamp_min(x, 0.0)) if gam is None else (lambda x: torch.minimum(torch.clamp_min(x, 0.0), gam) if not np.isscalar(gam) else torch.clamp(x, 0.0, gam))
+    b = torch.cat([r, l]); Atb = api.Aty(b, p, q)
+    muf = 0.0; gk = 1.0; bk = 1.0
+    xk = torch.zeros(m * n, dtype=torch.float64, device="cuda"); vk = xk.clone(); wk = xk.clone(); pik = xk.clone()
+    lk1_ = torch.zeros(m + n, dtype=torch.float64, device="cuda"); lk2_ = xk.clone()     # lk = [lk1_ ; lk2_]
+    for _ in range(int(maxit)):                                         # warmup_class1.m:43-95
+        ak = bk; bk1 = bk / (1 + ak)
+        gk1 = (gk + muf * ak) / (1 + ak)
+        etafk = (1 + ak) * gk + muf * ak
+        sgk = 1 / bk1; etagk = (1 + ak) * bk
+        wwk = (ak * pik + wk) / (1 + ak)
+        wxk = (ak * gk * vk + (gk + muf * ak) * xk) / etafk
+        h1 = lk1_ - (api.Ax(xk, p, q) - b) / bk                         # :65
+        h2 = lk2_ - (xk - wk) / bk - (ak / bk) * (pik - wk)
+        cAw = -Atb - wk; cAlk = api.Aty(h1, p, q) + h2                  # :66
+        dd = etafk * wxk - ak ** 2 * (c + cAlk + sgk * cAw)             # :67
+        del h2, cAw, cAlk, wxk
+        tt = sgk * ak ** 2; sg = 1 + etafk / tt
+        xk1 = (dd - api.Aty(api.invAAt(api.Ax(dd, p, q), p, q, sg), p, q)) / (etafk + tt)   # :70
+        del dd
+        vk1 = xk1 + (xk1 - xk) / ak
+        Av = api.Ax(vk1, p, q) - b
+        blk2 = lk2_ + (ak / bk) * (vk1 - pik)                           # :72
+        wk1 = prox(wwk - (ak ** 2 / etagk) * (-blk2))                   # :73
+        del blk2, wwk
+        pik1 = wk1 + (wk1 - wk) / ak
+        lk1_ = lk1_ + (ak / bk) * Av                                    # :75
+        lk2_ = lk2_ + (ak / bk) * (vk1 - pik1)
+        gk = gk1; bk = bk1; xk = xk1; vk = vk1; wk = wk1; pik = pik1
+    return xk, lk1_
+
+
+def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
+                   on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None):
+    """APD outer loop + SsN inner loop -- reference Class1/APD_SsN_Class1.m:32-275, on the device.
+
+    ``on_ssn_step(state)`` is called right before every inner linear solve with a dict holding
+    the tensors the solve reads (``wk, lk, wlk, bk1, tk, s, Fk, H0``).
+    """
+    import torch
+    c, r, l, p, q = (_t(v, torch) for v in (c, r, l, p, q))
+    m, n = l.numel(), r.numel()
+    scalar_gama = np.isscalar(gama) or np.size(gama) == 1
+    gam = float(gama) if scalar_gama else _t(gama, torch)
+    b = torch.cat([r, l])
+    bk = 1.0
+    SsN_IT = 50; SsN_Tol1 = 1e-11; nu = 0.2; delta = 0.9; ll_max = 500   # :36
+    amg_options = dict(amg_options or CLASS1_AMG_OPTIONS); pcg_options = dict(CLASS1_PCG_OPTIONS)
+    t_start = time.time()
+    xk, lk = warmup_class1(c, r, l, p, q, gama, 0.0, warm_maxit)         # :59
+    torch.cuda.synchronize(); t_warm = time.time() - t_start
+    vk = xk.clone()
+
+    def kkt(x, lam):
+        kl = float(torch.linalg.norm(api.Ax(x, p, q) - b))
+        px = api.prox_residual(x - c, lam, p, q, 1.0, gam, want=("prox",))["prox"]           # prox(x-c-Aty(lam))
+        kx = float(torch.linalg.norm(x - px))
+        return kx, kl
+
+    kx0, kl0 = kkt(xk, lk)
+    fxk = [float(c @ xk)]; KKT_xk = [kx0]; KKT_lk = [kl0]
+    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm,
+             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0}
+    t_loop = time.time()
+    rr = [np.inf]
+    k = 0
+    for k in range(1, maxit + 1):                                       # :101
+        resk = max(KKT_xk[k - 1], KKT_lk[k - 1])
+        ak = math.sqrt(k ** 2 * bk)                                     # :113
+        bk1 = bk / (1 + ak); tk = bk * (1 + ak) / ak ** 2               # :120
+        SsN_Tol = max(bk1 / (k ** 2), SsN_Tol1)                         # :123
+        wk = -c + bk * (xk + ak * vk) / ak ** 2                         # :125
+        wlk = bk1 * (lk - 1 / bk * (api.Ax(xk, p, q) - b)) - b          # :126
+        ssn_it = 0; lk_new = lk.clone()
+        ev = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))   # :129-130 (+ s for :140)
+        Fk_new = bk1 * lk_new - ev["Axprox"] - wlk
+        nF = float(torch.linalg.norm(Fk_new))
+        Fk_res = nF
+        its = []
+        while nF > SsN_Tol:                                             # :137
+            ssn_it += 1; lk_old = lk_new
+            Fk_old = Fk_new; s = ev["s"]; n2_old = ev["norm2"]          # z, s, prox of lk_old: already evaluated
+            t0 = time.time()
+            H0 = api.ASAt(s, p, q)                                      # :142
+            torch.cuda.synchronize(); stats["asat_s"] += time.time() - t0
+            if on_ssn_step is not None:
+                on_ssn_step({"k": k, "ssn_it": ssn_it, "wk": wk, "lk": lk_old, "wlk": wlk, "bk1": bk1, "tk": tk,
+                             "s": s, "Fk": Fk_old, "H0": H0, "E": ev["count"]})
+            t0 = time.time()
+            prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
+            if inner_solver == 3:
+                zeta, itpcg, respcg, info = api.aug_PCG(prob_data, pcg_options)
+            elif inner_solver == 4:
+                zeta, itpcg, respcg, info = api.Hybrid_AMG(prob_data, amg_options)
+                stats["amg_calls"] += 1
+            else:
+                raise ValueError("inner_solver must be 3 (aug_PCG) or 4 (Hybrid_AMG)")
+            torch.cuda.synchronize(); stats["solve_s"] += time.time() - t0
+            its.append(itpcg)
+            t0 = time.time()
+            f0 = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old)  # :182
+            cFk_old = f0 + 0.5 * tk * n2_old
+            ress = abs(float(Fk_old @ zeta))
+            ll = 0
+            while True:                                                 # :189-211
+                lk_new = lk_old + delta ** ll * zeta
+                f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
+                n2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=())["norm2"]
+                cFk_new = f0 + 0.5 * tk * n2
+                if not (cFk_new > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
+                    break
+                ll += 1
+            stats["ls_trials"] += ll + 1
+            ev = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))
+            Fk_new = bk1 * lk_new - ev["Axprox"] - wlk                  # :212
+            nFo = float(torch.linalg.norm(Fk_old)); nF = float(torch.linalg.norm(Fk_new))
+            torch.cuda.synchronize(); stats["plan_s"] += time.time() - t0
+            if verbose:
+                print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={ll:3d} info={list(info)} its={itpcg} res={respcg:.2e} E={ev['count']}")
+            if nF <= SsN_Tol:
+                break
+            if abs(nFo - nF) < SsN_Tol / 100:                           # :219
+                break
+            if ssn_it == SsN_IT:
+                break
+            if Fk_res / nF >= 2:
+                Fk_res = nF
+        lk1 = lk_new
+        xk1 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("prox",))["prox"]          # :239
+        vk1 = xk1 + (xk1 - xk) / ak
+        kx, kl = kkt(xk1, lk1)
+        rr = [kx / (1 + KKT_xk[0]), kl / (1 + KKT_lk[0])]
+        if bk1 < 1e-8 and max(rr) > resk:                               # :245-249
+            xk1 = xk; lk1 = lk; vk1 = xk; bk1 = float(api.rand(1)[0])
+            kx, kl = kkt(xk1, lk1)
+        bk = bk1; xk = xk1; lk = lk1; vk = vk1                          # :251
+        fxk.append(float(c @ xk)); KKT_lk.append(kl); KKT_xk.append(kx)
+        stats["ssn_its"].append(ssn_it); stats["lin_its"].append(its)
+        rr = [KKT_xk[k] / (1 + KKT_xk[0]), KKT_lk[k] / (1 + KKT_lk[0])]
+        if verbose:
+            print(f"APD: it={k:3d} KKT(xk)={rr[0]:.2e} KKT(lk)={rr[1]:.2e} fk={fxk[-1]:.8e} t={time.time() - t_loop:.2f}s")
+        if max(rr) <= KKT_Tol:                                          # :266
+            stats["converged"] = True
+            break
+        if max_outer is not None and k >= max_outer:
+            break
+        if max_seconds is not None and time.time() - t_loop > max_seconds:
+            break
+    torch.cuda.synchronize()
+    return {"xk": xk, "lk": lk, "fxk": fxk, "KKT_xk": KKT_xk, "KKT_lk": KKT_lk, "outer_its": k, "rel_kkt": max(rr),
+            "stats": stats, "seconds": time.time() - t_loop, "warmup_seconds": t_warm}

@@ -118,6 +118,11 @@ SSN_API int  ssn_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches claim) */
 SSN_API int64_t ssn_launch_count(ssn_ctx *ctx);
 
+/* Phase profiler (development aid): when enabled, named phases of the solve are timed with the
+ * stream synchronised on both sides; ssn_profile_dump returns a text table and resets it. */
+SSN_API int  ssn_profile_enable(ssn_ctx *ctx, int on);
+SSN_API const char *ssn_profile_dump(ssn_ctx *ctx);
+
 /* The library-owned MATLAB random stream (mt19937ar, init_genrand(5489), genrand_res53):
  * stands for MATLAB's global `rand` state consumed at AMG/mis_set.m:31,35 and
  * Hybrid_AMG.m:40,69.  Generated on the device. */
