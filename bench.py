@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workload on B200: one semismooth-Newton (SsN) inner solve
+step of the SsN-AMG optimal-transport solver on the 128x128-vs-128x128 grid (m = n = 16384,
+268M-entry fp64 plan), at a realistic APD state captured from the device-resident solve.
+
+A "step" is one pass of the hot path (Class1/APD_SsN_Class1.m:137-212 of the reference):
+  fused residual + active set (one read of the plan-sized wk)  ->  ASAt assembly  ->
+  Hybrid_AMG (AMG setup + W-cycles to 1e-11)  ->  Armijo line-search trial(s)  ->  new residual.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                     (the CPU oracle port on the host cores)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ssn_amg_inner_solve_step_time_128x128_grid"
+UNIT = "ms/step"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=128, help="grid side g (m = n = g*g); 128 is the headline config")
+    ap.add_argument("--state-outer", type=int, default=30, help="APD outer iteration whose first SsN step is benchmarked")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-solve", action="store_true", help="also time the whole Class1 solve on the device")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------ CPU oracle arm
+
+def cpu_step_sample(sample, reps=1):
+    """The oracle (CPU port of the reference; MATLAB/Octave are absent) on a bounded sample of the
+    same step: the plan-wide part on a row slab of the plan (scaled to the full plan), the AMG
+    solve on the full (n+m) system.  Returns full-problem-equivalent ms per step."""
+    import oracle
+    from oracle import driver as odrv
+    w, lam, wlk, p_s, q = sample["w_slab"], sample["lam_slab"], sample["wlk"], sample["p_slab"], sample["q"]
+    tk, bk1, scale = sample["tk"], sample["bk1"], sample["scale"]
+    t_plan = t_amg = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for _ev in range(3):                               # residual+active set, line-search trial, new residual
+            z = 1 / tk * (w - oracle.Aty(lam, p_s, q))
+            s = (z >= 0) & (z <= np.inf)
+            px = np.maximum(z, 0.0)
+            oracle.Ax(px, p_s, q); float(px @ px)
+        oracle.ASAt(s, p_s, q)
+        t_plan += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.rng_reset()
+        pd = {"bk1": bk1, "tk": tk, "p": sample["p"], "q": q, "T": sample["T"], "H0": sample["H0"], "z": sample["z"]}
+        oracle.Hybrid_AMG(pd, odrv.CLASS1_AMG_OPTIONS)
+        t_amg += time.perf_counter() - t0
+    return 1e3 * (scale * t_plan + t_amg) / reps, 1e3 * scale * t_plan / reps, 1e3 * t_amg / reps
+
+
+def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows):
+    import scipy.sparse as sp
+    import torch
+    wk = state["wk"].view(n, m)                             # column-major m x n == row-major n x m
+    w_slab = wk[:, :slab_rows].contiguous().cpu().numpy().reshape(-1)      # column-major slab (slab_rows x n)
+    lam = state["lk"].cpu().numpy()
+    lam_slab = np.concatenate([lam[:n], lam[n:n + slab_rows]])
+    return {"w_slab": w_slab, "lam_slab": lam_slab, "wlk": state["wlk"].cpu().numpy(), "p_slab": np.ones(slab_rows),
+            "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "scale": m / slab_rows,
+            "T": sp.diags(np.zeros(m + n)), "H0": H0_scipy.tocsc(), "z": z_host}
+
+
+# ------------------------------------------------------------------------------ main
+
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1 and args.impl == "ours":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ssnamg
+    drv = ssnamg.driver
+    g = args.grid
+    m = n = g * g
+    peak, peak_src = peaks()
+
+    # ---- the APD state of the benchmarked step (identical on every rank: deterministic solve)
+    t0 = time.time()
+    P = ssnamg.problems.grid_problem(g, seed=0)
+    ssnamg.rng_reset()
+    state = drv.capture_state(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], outer=args.state_outer, ssn_it=1)
+    del P
+    torch.cuda.synchronize()
+    t_state = time.time() - t0
+    workload = f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}_outer{state['k']}_ssn{state['ssn_it']}"
+
+    if args.impl == "reference":
+        return run_reference(args, state, m, n, workload)
+
+    if world > 1:
+        from importlib import import_module
+        shard = import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+        step_fn = shard.make_sharded_step(state, rank, world)
+    else:
+        def step_fn():
+            ssnamg.rng_reset()
+            return drv.ssn_step(state)
+
+    ev_k3 = []                                              # CUDA-event timings of the fused residual kernel
+
+    def timed_k3():
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox",))
+        b.record()
+        ev_k3.append((a, b))
+
+    for _ in range(max(args.warmup, 3)):
+        lk_new, Fk_new, info = step_fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = ssnamg.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        lk_new, Fk_new, info = step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = ssnamg.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    # dominant HBM-bound kernel, timed alone with CUDA events on the launching stream (sampler still running)
+    if world == 1:
+        for _ in range(3):
+            timed_k3()
+        ev_k3.clear()
+        for _ in range(10):
+            timed_k3()
+        torch.cuda.synchronize()
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / args.steps
+
+    out = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "ours",
+           "config": {"workload": workload, "E_active": int(info["E"]), "nnz_H0": int(info["nnzH"]), "amg_cycles": int(info["itamg"]),
+                      "components": int(info["info"][0]), "line_search_trials": int(info["ll"]) + 1,
+                      "l2_flush": "inputs larger than L2 (2.1 GB plan vector per pass)", "state_build_s": round(t_state, 1),
+                      "sharding": "plan rows over ranks; AMG replicated" if world > 1 else "single GPU"},
+           "ssn_steps_per_s": 1e3 / ms_step, "gpu_launches": int(launches), "clocks": sampler.summary()}
+
+    if world == 1:
+        k3_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_k3]))
+        bytes_k3 = 8.0 * m * n
+        ach = bytes_k3 / (k3_ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "plan_reduce_kernel<PROX> (fused SsN residual: z, prox, Ax(prox), ||prox||^2)",
+                           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": bytes_k3, "avg_launch_ms": k3_ms,
+                           "traffic": load_traffic(), "frac_of_8TBps_nominal": ach / 8000.0}
+        # ---- e2e: the same step through host buffers (pinned), H2D of the step's inputs + D2H of its result
+        hstate = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in state.items()}
+        h2d = sum(v.numel() * v.element_size() for v in hstate.values() if isinstance(v, torch.Tensor))
+        for _ in range(2):
+            ssnamg.rng_reset(); drv.ssn_step_host(hstate)
+        torch.cuda.synchronize()
+        ke = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            ssnamg.rng_reset(); lk_h, Fk_h, _ = drv.ssn_step_host(hstate)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+        out["e2e"] = {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(lk_h.numel() * 8 + Fk_h.numel() * 8)}
+        del hstate
+        # ---- secondary figures named by the metric: PCG iterations/s on the full KKT system, W-cycles/s
+        out.update(secondary_metrics(ssnamg, drv, state, m, n))
+        if args.full_solve:
+            P = ssnamg.problems.grid_problem(g, seed=0)
+            ssnamg.rng_reset()
+            res = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"])
+            out["full_solve"] = {"loop_s": res["seconds"], "warmup_s": res["warmup_seconds"], "outer_its": res["outer_its"],
+                                 "rel_kkt": res["rel_kkt"], "objective": res["fxk"][-1], "ssn_steps": int(sum(res["stats"]["ssn_its"]))}
+        if not args.no_cpu_baseline:
+            ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
+            H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
+            z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
+            slab = max(64, m // 16)
+            sample = make_cpu_sample(state, H0, z_host, m, n, slab)
+            cpu_ms, cpu_plan, cpu_amg = cpu_step_sample(sample)
+            out["cpu_baseline"] = {"value": cpu_ms, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"oracle (NumPy/SciPy port; MATLAB/Octave absent): plan-wide part on a {slab}-row slab "
+                                             f"of the {m}x{n} plan scaled x{m // slab} ({cpu_plan:.0f} ms), AMG solve on the full "
+                                             f"{m + n}-node system ({cpu_amg:.0f} ms); BLAS threads at default"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
+        return float(d["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def secondary_metrics(ssnamg, drv, state, m, n):
+    import scipy.sparse as sp
+    import torch
+    ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
+    H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"])
+    Fk = state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"]
+    # inner_solver = 2: PCG.m on Jk = bk1*I + H0/tk  (Class1/APD_SsN_Class1.m:149-152)
+    Jk = (state["bk1"] * sp.identity(m + n, format="csr") + H0.to_scipy() / state["tk"]).tocsr()
+    Jd = ssnamg.DeviceCSR.from_scipy(Jk)
+    opts = {"retol": 1e-11, "maxit": 2000, "precd": 2, "guess": None}
+    ssnamg.PCG(Jd, -Fk, opts)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    d, it, res, _ = ssnamg.PCG(Jd, -Fk, opts)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    pd = {"bk1": state["bk1"], "tk": state["tk"], "q": state["q"], "p": state["p"], "T": None, "H0": H0, "z": -Fk}
+    ssnamg.rng_reset(); ssnamg.Hybrid_AMG(pd, drv.CLASS1_AMG_OPTIONS)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ssnamg.rng_reset(); zeta, itamg, resamg, info = ssnamg.Hybrid_AMG(pd, drv.CLASS1_AMG_OPTIONS)
+    torch.cuda.synchronize(); dta = time.perf_counter() - t0
+    return {"pcg_iters_per_s": it / dt, "pcg_iters": it, "pcg_rel_res": res, "pcg_system": f"Jk {m + n}x{m + n}, nnz {Jk.nnz}",
+            "hybrid_amg_ms": dta * 1e3, "wcycles_per_s_incl_setup": itamg / dta}
+
+
+def run_reference(args, state, m, n, workload):
+    """--impl reference: the reference's CPU path (oracle port; MATLAB/Octave are absent) on the host cores."""
+    import torch
+    import ssnamg
+    ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
+    H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
+    z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
+    slab = max(64, m // 16)
+    sample = make_cpu_sample(state, H0, z_host, m, n, slab)
+    del state; torch.cuda.empty_cache()
+    for _ in range(min(args.warmup, 1)):
+        cpu_step_sample(sample)
+    steps = max(1, min(args.steps, 3))
+    vals = [cpu_step_sample(sample) for _ in range(steps)]
+    ms = float(np.mean([v[0] for v in vals]))
+    sample_txt = (f"oracle (NumPy/SciPy port of the reference; MATLAB/Octave absent): plan-wide part on a {slab}-row slab of the "
+                  f"{m}x{n} plan scaled x{m // slab}, AMG solve on the full {m + n}-node system; BLAS threads at default")
+    out = {"metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+           "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "reference", "config": {"workload": workload},
+           "cpu_baseline": {"value": ms, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample_txt},
+           "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

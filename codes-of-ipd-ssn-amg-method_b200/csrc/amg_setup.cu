@@ -684,7 +684,7 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
     std::vector<LevelDev> hd(J);
     for (int k = 0; k < J; ++k) {
         Level& L = H->lv[k];
-        if (k >= sf || k == J - 1) L.pcg.alloc(c, (size_t)5 * L.N);
+        L.pcg.alloc(c, (size_t)5 * L.N);               // ping-pong buffer of the smoother / PCG scratch
         LevelDev d{};
         d.N = L.N; d.Nf = L.Nf; d.bigph = L.bigph;
         d.ap = L.A.ptr.p; d.ai = L.A.idx.p; d.av = L.A.val.p;

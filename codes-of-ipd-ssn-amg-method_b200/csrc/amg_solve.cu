@@ -15,7 +15,7 @@ namespace ssn {
 
 namespace {
 
-constexpr int kCycleThreads = 512;
+constexpr int kCycleThreads = 1024;
 constexpr int kMaxPartBlocks = 296;
 
 // sum over a row's entries, cooperating TPR lanes; result valid in all TPR lanes
@@ -109,6 +109,52 @@ __global__ void __launch_bounds__(256) smooth_apply_kernel(LevelDev L, const dou
     }
 }
 
+// One damped-Jacobi smoothing step with the kernel correction in ONE launch: the coefficient is
+// (sum(r) - Axi'e)/xx, both sums arriving as block partials of earlier launches, and the update
+// is row-local; ealt <- smoothed ecur, dot_out[b] <- partial of Axi'ealt for the next step.
+template <int TPR>
+__global__ void __launch_bounds__(256) smooth_fused_kernel(LevelDev L, const double* __restrict__ r,
+                                                           const double* __restrict__ ecur, double* __restrict__ ealt,
+                                                           const double* __restrict__ part_r, int np_r,
+                                                           const double* __restrict__ dot_in, int np_d,
+                                                           double* __restrict__ dot_out, int isnsp, int e_is_zero) {
+    __shared__ double red[32];
+    double coef = 0.0;
+    if (isnsp) {
+        const double sr = sum_parts(part_r, np_r, 1, red);
+        const double sd = (np_d > 0) ? sum_parts(dot_in, np_d, 1, red) : 0.0;
+        coef = (sr - sd) / L.xx;
+    }
+    const int sub = threadIdx.x % TPR;
+    const int rows_per_pass = gridDim.x * (256 / TPR);
+    double part = 0.0;
+    for (int base = 0; base < L.N; base += rows_per_pass) {
+        const int row = base + blockIdx.x * (256 / TPR) + threadIdx.x / TPR;
+        const bool valid = row < L.N;
+        double d = 0.0;
+        if (!e_is_zero) d = row_dot<TPR>(L.ap, L.ai, L.av, ecur, row, sub, valid);
+        if (valid && sub == 0) {
+            const double axi = L.Axi[row];
+            const double gi = r[row] - d;
+            const double en = (e_is_zero ? 0.0 : ecur[row]) + coef + L.dinv[row] * (gi - axi * coef);
+            ealt[row] = en;
+            part = fma(axi, en, part);
+        }
+    }
+    part = block_sum(part, red);
+    if (threadIdx.x == 0) dot_out[blockIdx.x] = part;
+}
+
+// part[b] = sum over the block's slice of x[i]*(y ? y[i] : 1)
+__global__ void __launch_bounds__(256) dot_parts_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                                        double* __restrict__ part) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += y ? x[i] * y[i] : x[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
     __shared__ double red[32];
     const double a = sum_parts(part, np, 2, red);
@@ -122,43 +168,99 @@ __global__ void axpy_kernel(int n, double a, const double* __restrict__ x, doubl
 }
 
 // ------------------------------------------------------------------ single-block cycle
+//
+// One CTA of 1024 threads walks the whole sub-hierarchy.  Latency is everything here, so:
+//   * a Jacobi smoothing step is ONE pass + ONE single-barrier reduction: with A symmetric,
+//     sum(g) = sum(r) - (A*ones)'e, so the kernel-correction coefficient of step t is known
+//     before its SpMV and the update e_i += coef + dinv_i*(g_i - Axi_i*coef) is row-local
+//     (ping-pong between two buffers);
+//   * the coarsest PCG (N <= 32) runs in a single warp with shuffles only;
+//   * the second coarse solve at depth J-1 is skipped: it repeats the first one exactly
+//     (same right-hand side, guess ignored, MG_Wcycle.m:30,44).
 
 constexpr int kBT = 4;                                    // lanes per row inside the block kernel
 
-__device__ void blk_resid(const LevelDev& L, const double* r, const double* e, double* g, double* red, double* sum_out) {
+// block-wide sum with ONE barrier: warp partials go to the buffer selected by `flip`, which the
+// caller alternates so that slow readers of call n never race with the writers of call n+1.
+__device__ __forceinline__ double block_sum1(double v, double (*red)[32], int& flip) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    double* buf = red[flip & 1];
+    if (lane == 0) buf[w] = v;
+    __syncthreads();
+    double t = buf[lane];                                 // kCycleThreads == 1024: exactly 32 warp partials
+    t = warp_sum(t);
+    ++flip;
+    return t;
+}
+
+__device__ void blk_resid(const LevelDev& L, const double* r, const double* e, double* g) {
     const int sub = threadIdx.x % kBT;
-    double sg = 0.0;
     for (int base = 0; base < L.N; base += kCycleThreads / kBT) {
         const int row = base + threadIdx.x / kBT;
         const bool valid = row < L.N;
         double d = 0.0;
         if (e != nullptr) d = row_dot<kBT>(L.ap, L.ai, L.av, e, row, sub, valid);
-        if (valid && sub == 0) { const double gi = r[row] - d; g[row] = gi; sg += gi; }
+        if (valid && sub == 0) g[row] = r[row] - d;
     }
-    const double t = block_sum(sg, red);                  // barriers inside publish g
-    if (sum_out) *sum_out = t;
+    __syncthreads();
 }
 
-__device__ void blk_smooth(const LevelDev& L, const double* r, double* e, bool e_zero, int steps, int isnsp, int post,
-                           double* red) {
+// Smoothing on level L; returns the buffer that holds e afterwards (ecur or ealt).
+__device__ double* blk_smooth(const LevelDev& L, const double* r, double* ecur, double* ealt, bool e_zero, int steps,
+                              int isnsp, int post, double sum_r, double (*red)[32], int& flip) {
     const int sub = threadIdx.x % kBT;
+    if (steps == 0) {
+        if (e_zero) { for (int i = threadIdx.x; i < L.N; i += kCycleThreads) ecur[i] = 0.0; __syncthreads(); }
+        return ecur;
+    }
+    if (L.bigph) {                                        // block Gauss-Seidel level: residual pass + coupled update
+        for (int it = 0; it < steps; ++it) {
+            blk_resid(L, r, e_zero ? nullptr : ecur, L.g);
+            double coef = 0.0;
+            if (isnsp) {
+                double sg = 0.0;
+                for (int i = threadIdx.x; i < L.N; i += kCycleThreads) sg += L.g[i];
+                coef = block_sum1(sg, red, flip) / L.xx;
+            }
+            for (int base = 0; base < L.N; base += kCycleThreads / kBT) {
+                const int row = base + threadIdx.x / kBT;
+                const bool valid = row < L.N;
+                const double inc = smooth_inc<kBT>(L, L.g, coef, post, row, sub, valid);
+                if (valid && sub == 0) ecur[row] = e_zero ? inc : (ecur[row] + inc);
+            }
+            e_zero = false;
+            __syncthreads();
+        }
+        return ecur;
+    }
+    double dotAe = 0.0;
+    if (isnsp && !e_zero) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < L.N; i += kCycleThreads) s = fma(L.Axi[i], ecur[i], s);
+        dotAe = block_sum1(s, red, flip);
+    }
     for (int it = 0; it < steps; ++it) {
-        double sg = 0.0;
-        blk_resid(L, r, e_zero ? nullptr : e, L.g, red, &sg);
-        const double coef = isnsp ? sg / L.xx : 0.0;
+        const double coef = isnsp ? (sum_r - dotAe) / L.xx : 0.0;
+        double part = 0.0;
         for (int base = 0; base < L.N; base += kCycleThreads / kBT) {
             const int row = base + threadIdx.x / kBT;
             const bool valid = row < L.N;
-            const double inc = smooth_inc<kBT>(L, L.g, coef, post, row, sub, valid);
-            if (valid && sub == 0) e[row] = e_zero ? inc : (e[row] + inc);
+            double d = 0.0;
+            if (!e_zero) d = row_dot<kBT>(L.ap, L.ai, L.av, ecur, row, sub, valid);
+            if (valid && sub == 0) {
+                const double axi = L.Axi[row];
+                const double gi = r[row] - d;
+                const double en = (e_zero ? 0.0 : ecur[row]) + coef + L.dinv[row] * (gi - axi * coef);
+                ealt[row] = en;
+                part = fma(axi, en, part);
+            }
         }
+        dotAe = block_sum1(part, red, flip);              // the barrier inside also publishes ealt
+        double* t = ecur; ecur = ealt; ealt = t;
         e_zero = false;
-        __syncthreads();
     }
-    if (steps == 0 && e_zero) {
-        for (int i = threadIdx.x; i < L.N; i += kCycleThreads) e[i] = 0.0;
-        __syncthreads();
-    }
+    return ecur;
 }
 
 // y (+)= M*x for a CSR M with nrows rows
@@ -173,18 +275,58 @@ __device__ void blk_spmv(int nrows, const int* ptr, const int* idx, const double
     __syncthreads();
 }
 
-// PCG(A,r) with the defaults of PCG.m:18-23 (zero guess, retol 1e-11, maxit 1e4, Jacobi)
-__device__ void blk_pcg(const LevelDev& L, const double* rhs, double* x, double* red) {
+__device__ __forceinline__ double level_diag(const LevelDev& L, int i) {
+    return L.bigph ? (1.0 / L.dinv[i]) : (0.5 / L.dinv[i]);     // recover diag(A) from the smoother scaling
+}
+
+// PCG(A,r) with the defaults of PCG.m:18-23 (zero guess, retol 1e-11, maxit 1e4, Jacobi), N <= 32:
+// one warp, lane i owns row i, vectors live in registers, SpMV gathers through shuffles.
+__device__ void warp_pcg(const LevelDev& L, const double* rhs, double* x) {
+    const int lane = threadIdx.x & 31;
+    const bool valid = lane < L.N;
+    const int e0 = valid ? L.ap[lane] : 0, e1 = valid ? L.ap[lane + 1] : 0;
+    int maxlen = e1 - e0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    const double diag = valid ? level_diag(L, lane) : 1.0;
+    double r = valid ? rhs[lane] : 0.0;
+    double p = r / diag, xi = 0.0;
+    double delta_new = warp_sum(r * p);
+    const double delta_0 = delta_new, tol2 = 1e-11 * 1e-11;
+    int it = 0;
+    while (it < 10000 && delta_new > tol2 * delta_0) {
+        const double delta_old = delta_new;
+        double q = 0.0;
+        for (int t = 0; t < maxlen; ++t) {
+            const int e = e0 + t;
+            const bool has = e < e1;
+            const int j = has ? L.ai[e] : 0;
+            const double a = has ? L.av[e] : 0.0;
+            const double pj = __shfl_sync(0xffffffffu, p, j);
+            q = fma(a, pj, q);
+        }
+        const double alpha = delta_old / warp_sum(q * p);
+        xi += alpha * p;
+        r -= alpha * q;
+        const double w = r / diag;
+        delta_new = warp_sum(r * w);
+        p = w + (delta_new / delta_old) * p;
+        ++it;
+    }
+    if (valid) x[lane] = xi;
+}
+
+// block-wide PCG for a coarsest level with more than 32 unknowns (other problem sizes)
+__device__ void blk_pcg(const LevelDev& L, const double* rhs, double* x, double (*red)[32], int& flip) {
     const int n = L.N;
     double* r = L.pcg; double* p = r + n; double* q = p + n;
     double dn = 0.0;
     for (int i = threadIdx.x; i < n; i += kCycleThreads) {
         const double ri = rhs[i];
-        const double diag = L.bigph ? (1.0 / L.dinv[i]) : (0.5 / L.dinv[i]);   // recover diag(A)
-        const double pi = ri / diag;
+        const double pi = ri / level_diag(L, i);
         r[i] = ri; p[i] = pi; x[i] = 0.0; dn = fma(ri, pi, dn);
     }
-    double delta_new = block_sum(dn, red);
+    double delta_new = block_sum1(dn, red, flip);
     const double delta_0 = delta_new;
     const double tol2 = 1e-11 * 1e-11;
     int it = 0;
@@ -193,17 +335,16 @@ __device__ void blk_pcg(const LevelDev& L, const double* rhs, double* x, double*
         blk_spmv(n, L.ap, L.ai, L.av, p, q, false);
         double qp = 0.0;
         for (int i = threadIdx.x; i < n; i += kCycleThreads) qp = fma(q[i], p[i], qp);
-        qp = block_sum(qp, red);
+        qp = block_sum1(qp, red, flip);
         const double alpha = delta_old / qp;
         double dnew = 0.0;
         for (int i = threadIdx.x; i < n; i += kCycleThreads) {
             x[i] += alpha * p[i];
             const double ri = r[i] - alpha * q[i];
-            const double diag = L.bigph ? (1.0 / L.dinv[i]) : (0.5 / L.dinv[i]);
-            r[i] = ri; q[i] = ri / diag;                  // q now holds w = M^{-1} r
+            r[i] = ri; q[i] = ri / level_diag(L, i);      // q now holds w = M^{-1} r
             dnew = fma(ri, q[i], dnew);
         }
-        delta_new = block_sum(dnew, red);
+        delta_new = block_sum1(dnew, red, flip);
         const double beta = delta_new / delta_old;
         for (int i = threadIdx.x; i < n; i += kCycleThreads) p[i] = q[i] + beta * p[i];
         __syncthreads();
@@ -215,38 +356,54 @@ __device__ void blk_pcg(const LevelDev& L, const double* rhs, double* x, double*
 // The whole cycle from level k0 down, iteratively (phase machine instead of recursion).
 __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const LevelDev* __restrict__ levels, int k0, int J,
                                                                      int smoth, int isnsp, int wcycle, int e0_zero) {
-    __shared__ double red[32];
+    __shared__ double red[2][32];
     __shared__ LevelDev sl[16];
     const int nl = J - k0;
     for (int t = threadIdx.x; t < nl && t < 16; t += kCycleThreads) sl[t] = levels[k0 + t];
     __syncthreads();
-    int phase[16]; bool zero[16];
+    int flip = 0;
+    int phase[16]; bool zero[16]; double* ecur[16]; double* ealt[16]; double sum_r[16];
+    for (int t = 0; t < 16; ++t) { ecur[t] = nullptr; ealt[t] = nullptr; sum_r[t] = 0.0; phase[t] = 0; zero[t] = true; }
+    for (int t = 0; t < nl; ++t) { ecur[t] = sl[t].e; ealt[t] = sl[t].pcg; }
     int k = 0;
-    phase[0] = 0; zero[0] = e0_zero != 0;
+    zero[0] = e0_zero != 0;
     while (true) {
         const LevelDev& L = sl[k];
         if (k == nl - 1) {                                // coarsest: PCG(A,r), guess ignored (MG_Wcycle.m:44)
-            blk_pcg(L, L.r, L.e, red);
+            if (L.N <= 32) { if (threadIdx.x < 32) warp_pcg(L, L.r, L.e); __syncthreads(); }
+            else blk_pcg(L, L.r, L.e, red, flip);
+            ecur[k] = L.e;
             if (k == 0) break;
             --k; continue;
         }
         if (phase[k] == 0) {
-            blk_smooth(L, L.r, L.e, zero[k], smoth, isnsp, 0, red);                 // presmoothing
-            blk_resid(L, L.r, (zero[k] && smoth == 0) ? nullptr : L.e, L.g, red, nullptr);
+            if (isnsp && !L.bigph) {
+                double s = 0.0;
+                for (int i = threadIdx.x; i < L.N; i += kCycleThreads) s += L.r[i];
+                sum_r[k] = block_sum1(s, red, flip);
+            }
+            double* en = blk_smooth(L, L.r, ecur[k], ealt[k], zero[k], smoth, isnsp, 0, sum_r[k], red, flip);   // presmoothing
+            if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
+            blk_resid(L, L.r, ecur[k], L.g);
             const LevelDev& Lc = sl[k + 1];
             blk_spmv(Lc.N, Lc.tp, Lc.ti, Lc.tv, L.g, Lc.r, false);                  // restriction
-            phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ++k; continue;
+            phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ecur[k + 1] = Lc.e; ealt[k + 1] = Lc.pcg; ++k; continue;
         }
-        if (phase[k] == 1 && wcycle) {                                             // correction again
+        if (phase[k] == 1 && wcycle && (k + 1 != nl - 1)) {                         // correction again
             phase[k] = 2; phase[k + 1] = 0; zero[k + 1] = false; ++k; continue;
         }
         {
             const LevelDev& Lc = sl[k + 1];
-            blk_spmv(L.N, Lc.pp, Lc.pi, Lc.pv, Lc.e, L.e, true);                    // prolongation
-            blk_smooth(L, L.r, L.e, false, smoth, isnsp, 1, red);                   // postsmoothing
+            blk_spmv(L.N, Lc.pp, Lc.pi, Lc.pv, ecur[k + 1], ecur[k], true);         // prolongation
+            double* en = blk_smooth(L, L.r, ecur[k], ealt[k], false, smoth, isnsp, 1, sum_r[k], red, flip);   // postsmoothing
+            if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
         }
         if (k == 0) break;
         --k;
+    }
+    // the caller reads level k0's correction from its e buffer
+    if (ecur[0] != sl[0].e) {
+        for (int i = threadIdx.x; i < sl[0].N; i += kCycleThreads) sl[0].e[i] = ecur[0][i];
     }
 }
 
@@ -400,15 +557,44 @@ LevelDev level_dev(const Level& L) {
     return d;
 }
 
+constexpr int kPartR = 2 * kMaxPartBlocks;                 // H.part layout: [resid pairs | sum(r) | dot A | dot B]
+constexpr int kPartDotA = 3 * kMaxPartBlocks;
+constexpr int kPartDotB = 4 * kMaxPartBlocks;
+
 void smooth_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, int post, bool e_zero) {
     Level& L = H.lv[k];
-    const LevelDev Ld = level_dev(L);
+    if (H.smoth == 0) { if (e_zero) fill_double(c, L.e, L.N, 0.0); return; }
+    if (L.bigph) {                                        // block Gauss-Seidel level: residual + coupled update
+        const LevelDev Ld = level_dev(L);
+        for (int it = 0; it < H.smoth; ++it) {
+            const int np = launch_resid(c, L, L.r, e_zero ? nullptr : L.e.p, L.g, H.part);
+            launch_apply(c, Ld, L, L.g, L.e, H.part, np, isnsp, post, e_zero);
+            e_zero = false;
+        }
+        return;
+    }
+    const double avg = L.N ? (double)L.A.nnz / L.N : 0.0;
+    double* part = H.part.p;
+    const int nb1 = std::min(kMaxPartBlocks, std::max(1, cdiv(L.N, 256)));
+    int np_d = 0;
+    if (isnsp) {
+        if (!post) SSN_LAUNCH(c, dot_parts_kernel, nb1, 256, 0, L.N, L.r.p, nullptr, part + kPartR);   // sum(r): once per visit
+        if (!e_zero) { SSN_LAUNCH(c, dot_parts_kernel, nb1, 256, 0, L.N, L.Axi.p, L.e.p, part + kPartDotA); np_d = nb1; }
+    }
+    double* dot_in = part + kPartDotA; double* dot_out = part + kPartDotB;
     for (int it = 0; it < H.smoth; ++it) {
-        const int np = launch_resid(c, L, L.r, e_zero ? nullptr : L.e.p, L.g, H.part);
-        launch_apply(c, Ld, L, L.g, L.e, H.part, np, isnsp, post, e_zero);
+        const LevelDev Ld = level_dev(L);
+        dispatch_tpr(avg, [&](auto T) {
+            constexpr int TPR = decltype(T)::value;
+            const int gr = grid_rows(L.N, TPR);
+            SSN_LAUNCH(c, smooth_fused_kernel<TPR>, gr, 256, 0, Ld, L.r.p, L.e.p, L.pcg.p, part + kPartR, nb1, dot_in, np_d, dot_out,
+                       isnsp, e_zero ? 1 : 0);
+            np_d = gr;
+        });
+        std::swap(L.e.p, L.pcg.p);                        // ping-pong: the smoothed iterate is the level's e again
+        std::swap(dot_in, dot_out);
         e_zero = false;
     }
-    if (H.smoth == 0 && e_zero) fill_double(c, L.e, L.N, 0.0);
 }
 
 // cycle on level k (0-based): rhs in lv[k].r, correction in lv[k].e

@@ -184,3 +184,68 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
     torch.cuda.synchronize()
     return {"xk": xk, "lk": lk, "fxk": fxk, "KKT_xk": KKT_xk, "KKT_lk": KKT_lk, "outer_its": k, "rel_kkt": max(rr),
             "stats": stats, "seconds": time.time() - t_loop, "warmup_seconds": t_warm}
+
+
+def ssn_step(state, amg_options=None, max_ll=500):
+    """One semismooth-Newton step of Class1/APD_SsN_Class1.m:137-212 at a fixed APD state:
+    fused residual + active set -> ASAt -> Hybrid_AMG -> Armijo line search -> new residual.
+    ``state`` holds device tensors ``wk, lk, wlk, p, q`` and scalars ``bk1, tk, gama``.
+    Returns ``(lk_new, Fk_new, info)``."""
+    import torch
+    wk, lk, wlk, p, q = state["wk"], state["lk"], state["wlk"], state["p"], state["q"]
+    bk1, tk, gam = state["bk1"], state["tk"], state.get("gama", float("inf"))
+    nu, delta = 0.2, 0.9
+    ev = api.prox_residual(wk, lk, p, q, tk, gam, want=("Axprox", "s"))          # :139-144
+    Fk_old = bk1 * lk - ev["Axprox"] - wlk
+    H0 = api.ASAt(ev["s"], p, q)                                                 # :142
+    prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
+    zeta, itamg, resamg, info = api.Hybrid_AMG(prob_data, amg_options or CLASS1_AMG_OPTIONS)   # :161
+    f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
+    cFk_old = f0 + 0.5 * tk * ev["norm2"]
+    ress = abs(float(Fk_old @ zeta))
+    ll = 0
+    while True:                                                                  # :189-211
+        lk_new = lk + delta ** ll * zeta
+        f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
+        n2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=())["norm2"]
+        if not (f0 + 0.5 * tk * n2 > cFk_old - nu * delta ** ll * ress) or ll == max_ll:
+            break
+        ll += 1
+    ev2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))     # :212
+    Fk_new = bk1 * lk_new - ev2["Axprox"] - wlk
+    return lk_new, Fk_new, {"E": ev["count"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll,
+                            "nnzH": H0.nnz, "Fk_old_norm": float(torch.linalg.norm(Fk_old)),
+                            "Fk_new_norm": float(torch.linalg.norm(Fk_new))}
+
+
+def ssn_step_host(hstate, amg_options=None):
+    """The same step through host buffers: every input is copied host->device (from pinned memory
+    when the caller pinned it) and the step's result is read back device->host."""
+    import torch
+    dev = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in hstate.items()}
+    lk_new, Fk_new, info = ssn_step(dev, amg_options)
+    return lk_new.cpu(), Fk_new.cpu(), info
+
+
+def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100):
+    """Runs the Class1 solve on the device until SsN step ``ssn_it`` of outer iteration ``outer`` and
+    returns the APD state that step reads (a realistic system for benchmarks / parity tests)."""
+    import torch
+    box = {}
+
+    class _Stop(Exception):
+        pass
+
+    def hook(st):
+        if st["k"] >= outer and st["ssn_it"] >= ssn_it:
+            box.update({"wk": st["wk"].clone(), "lk": st["lk"].clone(), "wlk": st["wlk"].clone(), "bk1": st["bk1"],
+                        "tk": st["tk"], "k": st["k"], "ssn_it": st["ssn_it"], "E": st["E"]})
+            raise _Stop()
+    try:
+        APD_SsN_Class1(c, r, l, p, q, gama, on_ssn_step=hook, warm_maxit=warm_maxit, max_outer=outer + 1)
+    except _Stop:
+        pass
+    if not box:
+        raise RuntimeError("the solve converged before the requested state")
+    box["p"] = _t(p, torch); box["q"] = _t(q, torch); box["gama"] = float(gama) if np.isscalar(gama) else gama
+    return box
