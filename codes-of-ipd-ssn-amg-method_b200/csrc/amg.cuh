@@ -28,11 +28,24 @@ struct Level {
     Buf<uint8_t> isC;
 };
 
+constexpr int kClusterSize = 8;
+constexpr int kClusterLevels = 12;
+struct ClusterPlan {
+    int nl;
+    int staged[kClusterLevels];
+    int smem_off[kClusterLevels];              // byte offset of the staged slice in dynamic smem
+    int rpc[kClusterLevels];                   // rows per CTA = ceil(N / cluster size)
+    int cap[kClusterLevels];                   // capacity (entries) of the staged slice
+};
+
 struct Hierarchy {
     std::vector<Level> lv;
     int J = 0;
     int smoth = 0;
     int small_from = 0;            // levels >= small_from are solved by the single-block kernel
+    int cluster_from = 1 << 30;    // levels >= cluster_from are solved by the 8-CTA cluster kernel
+    ClusterPlan cluster_plan{};
+    size_t cluster_smem = 0;
     Buf<LevelDev> dev;
     Buf<double> part;              // reduction partials (multi-block kernels)
     Buf<double> scal;              // small device scalars
@@ -66,6 +79,9 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
                double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
 void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
                double* res_out, double* resk_host);
+
+void debug_cycles(unsigned long long* out64, bool reset);
+void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
 
 // ---- dispatch (solvers.cu)
 void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm, int* r, int* ncomp);

@@ -699,6 +699,7 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
     SSN_CUDA(cudaStreamSynchronize(c->stream));
     H->part.alloc(c, 4096);
     H->scal.alloc(c, 64);
+    if (!c->no_cluster) build_cluster_plan(c, *H);
     c->hier = H.release();
 }
 

@@ -18,7 +18,9 @@ namespace {
 constexpr int kCycleThreads = 1024;
 constexpr int kMaxPartBlocks = 296;
 
-// sum over a row's entries, cooperating TPR lanes; result valid in all TPR lanes
+// sum over a row's entries, cooperating TPR lanes; result valid in all TPR lanes.  The loop is
+// batched 4 deep (all index/value loads, then all gathers, then the FMAs): the cores issue in
+// order, so without this every iteration pays a full dependent load latency.
 template <int TPR>
 __device__ __forceinline__ double row_dot(const int* __restrict__ ptr, const int* __restrict__ idx,
                                           const double* __restrict__ val, const double* __restrict__ x,
@@ -26,7 +28,14 @@ __device__ __forceinline__ double row_dot(const int* __restrict__ ptr, const int
     double s = 0.0;
     if (valid) {
         const int e1 = ptr[row + 1];
-        for (int e = ptr[row] + sub; e < e1; e += TPR) s = fma(val[e], x[idx[e]], s);
+        int e = ptr[row] + sub;
+        for (; e + 3 * TPR < e1; e += 4 * TPR) {
+            const int i0 = idx[e], i1 = idx[e + TPR], i2 = idx[e + 2 * TPR], i3 = idx[e + 3 * TPR];
+            const double v0 = val[e], v1 = val[e + TPR], v2 = val[e + 2 * TPR], v3 = val[e + 3 * TPR];
+            const double x0 = x[i0], x1 = x[i1], x2 = x[i2], x3 = x[i3];
+            s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
+        }
+        for (; e < e1; e += TPR) s = fma(val[e], x[idx[e]], s);
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -180,6 +189,11 @@ __global__ void axpy_kernel(int n, double a, const double* __restrict__ x, doubl
 
 constexpr int kBT = 4;                                    // lanes per row inside the block kernel
 
+// cycle counters of the single-block kernel (development aid; read through ssn_debug_cycles)
+__device__ unsigned long long g_dbg_cycles[64];
+#define DBG_T0() const long long dbg_t0 = clock64()
+#define DBG_ADD(slot) do { if (threadIdx.x == 0) { g_dbg_cycles[(slot)] += (unsigned long long)(clock64() - dbg_t0); g_dbg_cycles[32 + (slot)] += 1ull; } } while (0)
+
 // block-wide sum with ONE barrier: warp partials go to the buffer selected by `flip`, which the
 // caller alternates so that slow readers of call n never race with the writers of call n+1.
 __device__ __forceinline__ double block_sum1(double v, double (*red)[32], int& flip) {
@@ -289,7 +303,7 @@ __device__ void warp_pcg(const LevelDev& L, const double* rhs, double* x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
     const double diag = valid ? level_diag(L, lane) : 1.0;
-    double r = valid ? rhs[lane] : 0.0;
+    double r = valid ? __ldcg(rhs + lane) : 0.0;
     double p = r / diag, xi = 0.0;
     double delta_new = warp_sum(r * p);
     const double delta_0 = delta_new, tol2 = 1e-11 * 1e-11;
@@ -370,8 +384,10 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
     while (true) {
         const LevelDev& L = sl[k];
         if (k == nl - 1) {                                // coarsest: PCG(A,r), guess ignored (MG_Wcycle.m:44)
+            { DBG_T0();
             if (L.N <= 32) { if (threadIdx.x < 32) warp_pcg(L, L.r, L.e); __syncthreads(); }
             else blk_pcg(L, L.r, L.e, red, flip);
+            DBG_ADD(24 + 0); }
             ecur[k] = L.e;
             if (k == 0) break;
             --k; continue;
@@ -382,11 +398,16 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
                 for (int i = threadIdx.x; i < L.N; i += kCycleThreads) s += L.r[i];
                 sum_r[k] = block_sum1(s, red, flip);
             }
-            double* en = blk_smooth(L, L.r, ecur[k], ealt[k], zero[k], smoth, isnsp, 0, sum_r[k], red, flip);   // presmoothing
+            double* en;
+            { DBG_T0();
+            en = blk_smooth(L, L.r, ecur[k], ealt[k], zero[k], smoth, isnsp, 0, sum_r[k], red, flip);   // presmoothing
+            DBG_ADD(k); }
             if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
-            blk_resid(L, L.r, ecur[k], L.g);
             const LevelDev& Lc = sl[k + 1];
+            { DBG_T0();
+            blk_resid(L, L.r, ecur[k], L.g);
             blk_spmv(Lc.N, Lc.tp, Lc.ti, Lc.tv, L.g, Lc.r, false);                  // restriction
+            DBG_ADD(8 + k); }
             phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ecur[k + 1] = Lc.e; ealt[k + 1] = Lc.pcg; ++k; continue;
         }
         if (phase[k] == 1 && wcycle && (k + 1 != nl - 1)) {                         // correction again
@@ -394,8 +415,13 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
         }
         {
             const LevelDev& Lc = sl[k + 1];
+            { DBG_T0();
             blk_spmv(L.N, Lc.pp, Lc.pi, Lc.pv, ecur[k + 1], ecur[k], true);         // prolongation
-            double* en = blk_smooth(L, L.r, ecur[k], ealt[k], false, smoth, isnsp, 1, sum_r[k], red, flip);   // postsmoothing
+            DBG_ADD(16 + k); }
+            double* en;
+            { DBG_T0();
+            en = blk_smooth(L, L.r, ecur[k], ealt[k], false, smoth, isnsp, 1, sum_r[k], red, flip);   // postsmoothing
+            DBG_ADD(k); }
             if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
         }
         if (k == 0) break;
@@ -405,6 +431,215 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
     if (ecur[0] != sl[0].e) {
         for (int i = threadIdx.x; i < sl[0].N; i += kCycleThreads) sl[0].e[i] = ecur[0][i];
     }
+}
+
+// ------------------------------------------------------------------ cluster cycle kernel
+//
+// The single CTA above is bound by one SM's L2 bandwidth and issue rate.  For the mid-size
+// levels (N <= 4096) a thread-block CLUSTER of 8 CTAs (8 SMs, hardware cluster barrier, DSMEM
+// for the reductions) walks the sub-hierarchy instead: every CTA owns a contiguous row slice of
+// every level and keeps that slice of the matrix in its shared memory when it fits; vectors live
+// in global memory (L2) and are read with ld.global.cg after each cluster barrier.
+
+constexpr int kCS = kClusterSize;              // CTAs per cluster (portable maximum)
+constexpr int kCT = 1024;                      // threads per CTA
+constexpr int kCL = kClusterLevels;            // levels a cluster kernel can hold
+
+struct CLevel {                                // what a CTA uses for one level
+    int r0, r1;                                // my rows
+    const int* rp; const int* ci; const double* cv; int rbase;   // row pointers indexed by (row - rbase)
+};
+
+__device__ __forceinline__ double row_dot_cg(const int* __restrict__ rp, const int* __restrict__ ci,
+                                             const double* __restrict__ cv, const double* __restrict__ x,
+                                             int lrow, int sub, bool valid) {
+    double s = 0.0;
+    if (valid) {
+        const int e1 = rp[lrow + 1];
+        int e = rp[lrow] + sub;
+        for (; e + 3 * kBT < e1; e += 4 * kBT) {
+            const int i0 = ci[e], i1 = ci[e + kBT], i2 = ci[e + 2 * kBT], i3 = ci[e + 3 * kBT];
+            const double v0 = cv[e], v1 = cv[e + kBT], v2 = cv[e + 2 * kBT], v3 = cv[e + 3 * kBT];
+            const double x0 = __ldcg(x + i0), x1 = __ldcg(x + i1), x2 = __ldcg(x + i2), x3 = __ldcg(x + i3);
+            s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
+        }
+        for (; e < e1; e += kBT) s = fma(cv[e], __ldcg(x + ci[e]), s);
+    }
+#pragma unroll
+    for (int o = kBT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+struct ClusterRed { double blk[2][32]; double cl[2][kCS]; };
+
+// cluster-wide sum, identical in every thread; includes one cluster barrier (release/acquire)
+__device__ __forceinline__ double cl_sum(cg::cluster_group& cluster, double v, ClusterRed* red, int& flip, int rank) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = flip & 1;
+    v = warp_sum(v);
+    if (lane == 0) red->blk[b][w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = warp_sum(red->blk[b][lane]);
+        if (lane < kCS) {
+            double* remote = cluster.map_shared_rank(&red->cl[b][rank], lane);
+            *remote = t;
+        }
+    }
+    cluster.sync();
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < kCS; ++r) s += red->cl[b][r];
+    ++flip;
+    return s;
+}
+
+// Jacobi smoothing with the kernel correction on my row slice; returns the buffer holding e
+__device__ double* cl_smooth(cg::cluster_group& cluster, const LevelDev& L, const CLevel& C, const double* r, double* ecur,
+                             double* ealt, bool e_zero, int steps, int isnsp, double sum_r, ClusterRed* red, int& flip, int rank) {
+    const int sub = threadIdx.x % kBT;
+    if (steps == 0) {
+        if (e_zero) { for (int i = C.r0 + threadIdx.x; i < C.r1; i += kCT) ecur[i] = 0.0; cluster.sync(); }
+        return ecur;
+    }
+    double dotAe = 0.0;
+    if (isnsp && !e_zero) {
+        double s = 0.0;
+        for (int i = C.r0 + threadIdx.x; i < C.r1; i += kCT) s = fma(L.Axi[i], __ldcg(ecur + i), s);
+        dotAe = cl_sum(cluster, s, red, flip, rank);
+    }
+    for (int it = 0; it < steps; ++it) {
+        const double coef = isnsp ? (sum_r - dotAe) / L.xx : 0.0;
+        double part = 0.0;
+        for (int base = C.r0; base < C.r1; base += kCT / kBT) {
+            const int row = base + threadIdx.x / kBT;
+            const bool valid = row < C.r1;
+            double d = 0.0;
+            if (!e_zero) d = row_dot_cg(C.rp, C.ci, C.cv, ecur, row - C.rbase, sub, valid);
+            if (valid && sub == 0) {
+                const double axi = L.Axi[row];
+                const double gi = __ldcg(r + row) - d;
+                const double en = (e_zero ? 0.0 : __ldcg(ecur + row)) + coef + L.dinv[row] * (gi - axi * coef);
+                ealt[row] = en;
+                part = fma(axi, en, part);
+            }
+        }
+        dotAe = cl_sum(cluster, part, red, flip, rank);   // its barrier publishes ealt cluster-wide
+        double* t = ecur; ecur = ealt; ealt = t;
+        e_zero = false;
+    }
+    return ecur;
+}
+
+// y[rows of my slice of an nrows-row matrix] (+)= M*x
+__device__ void cl_spmv(cg::cluster_group& cluster, int nrows, int rank, const int* ptr, const int* idx, const double* val,
+                        const double* x, double* y, bool add) {
+    const int rpc = (nrows + kCS - 1) / kCS;
+    const int r0 = min(nrows, rank * rpc), r1 = min(nrows, r0 + rpc);
+    const int sub = threadIdx.x % kBT;
+    for (int base = r0; base < r1; base += kCT / kBT) {
+        const int row = base + threadIdx.x / kBT;
+        const bool valid = row < r1;
+        const double d = row_dot_cg(ptr, idx, val, x, row, sub, valid);
+        if (valid && sub == 0) y[row] = add ? (__ldcg(y + row) + d) : d;
+    }
+    cluster.sync();
+}
+
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kCT)
+cluster_cycle_kernel(const LevelDev* __restrict__ levels, int k0, int J, int smoth, int isnsp, int wcycle, int e0_zero,
+                     const ClusterPlan plan) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ ClusterRed red;
+    __shared__ LevelDev sl[kCL];
+    __shared__ CLevel cls[kCL];
+    const int rank = (int)cluster.block_rank();
+    const int nl = J - k0;
+    for (int t = threadIdx.x; t < nl; t += kCT) sl[t] = levels[k0 + t];
+    __syncthreads();
+    // ---- stage my matrix slices
+    for (int t = 0; t < nl; ++t) {
+        const LevelDev& L = sl[t];
+        const int rpc = plan.rpc[t];
+        const int r0 = min(L.N, rank * rpc), r1 = min(L.N, r0 + rpc);
+        if (plan.staged[t]) {
+            int* sp = reinterpret_cast<int*>(dsm + plan.smem_off[t]);
+            double* sv = reinterpret_cast<double*>(dsm + plan.smem_off[t] + (((rpc + 1) * 4 + 15) / 16) * 16);
+            int* si = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(sv) + (size_t)plan.cap[t] * 8);
+            const int base = L.ap[r0];
+            for (int i = threadIdx.x; i <= r1 - r0; i += kCT) sp[i] = L.ap[r0 + i] - base;
+            const int cnt = L.ap[r1] - base;
+            for (int e = threadIdx.x; e < cnt; e += kCT) { sv[e] = L.av[base + e]; si[e] = L.ai[base + e]; }
+            if (threadIdx.x == 0) { cls[t].r0 = r0; cls[t].r1 = r1; cls[t].rp = sp; cls[t].ci = si; cls[t].cv = sv; cls[t].rbase = r0; }
+        } else if (threadIdx.x == 0) {
+            cls[t].r0 = r0; cls[t].r1 = r1; cls[t].rp = L.ap; cls[t].ci = L.ai; cls[t].cv = L.av; cls[t].rbase = 0;
+        }
+    }
+    cluster.sync();
+    int flip = 0;
+    int phase[kCL]; bool zero[kCL]; double* ecur[kCL]; double* ealt[kCL]; double sum_r[kCL];
+    for (int t = 0; t < kCL; ++t) { ecur[t] = nullptr; ealt[t] = nullptr; sum_r[t] = 0.0; phase[t] = 0; zero[t] = true; }
+    for (int t = 0; t < nl; ++t) { ecur[t] = sl[t].e; ealt[t] = sl[t].pcg; }
+    int k = 0;
+    zero[0] = e0_zero != 0;
+    while (true) {
+        const LevelDev& L = sl[k];
+        const CLevel& C = cls[k];
+        if (k == nl - 1) {                                // coarsest (N <= 32, checked by the host): warp PCG on CTA 0
+            if (rank == 0 && threadIdx.x < 32) warp_pcg(L, L.r, L.e);
+            cluster.sync();
+            ecur[k] = L.e;
+            if (k == 0) break;
+            --k; continue;
+        }
+        if (phase[k] == 0) {
+            if (isnsp) {
+                double s = 0.0;
+                for (int i = C.r0 + threadIdx.x; i < C.r1; i += kCT) s += __ldcg(L.r + i);
+                sum_r[k] = cl_sum(cluster, s, &red, flip, rank);
+            }
+            double* en = cl_smooth(cluster, L, C, L.r, ecur[k], ealt[k], zero[k], smoth, isnsp, sum_r[k], &red, flip, rank);
+            if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
+            {   // g = r - A e on my rows, then the restriction (needs every CTA's g)
+                const int sub = threadIdx.x % kBT;
+                for (int base = C.r0; base < C.r1; base += kCT / kBT) {
+                    const int row = base + threadIdx.x / kBT;
+                    const bool valid = row < C.r1;
+                    const double d = row_dot_cg(C.rp, C.ci, C.cv, ecur[k], row - C.rbase, sub, valid);
+                    if (valid && sub == 0) L.g[row] = __ldcg(L.r + row) - d;
+                }
+                cluster.sync();
+            }
+            const LevelDev& Lc = sl[k + 1];
+            cl_spmv(cluster, Lc.N, rank, Lc.tp, Lc.ti, Lc.tv, L.g, Lc.r, false);
+            phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ecur[k + 1] = Lc.e; ealt[k + 1] = Lc.pcg; ++k; continue;
+        }
+        if (phase[k] == 1 && wcycle && (k + 1 != nl - 1)) {
+            phase[k] = 2; phase[k + 1] = 0; zero[k + 1] = false; ++k; continue;
+        }
+        {
+            const LevelDev& Lc = sl[k + 1];
+            cl_spmv(cluster, L.N, rank, Lc.pp, Lc.pi, Lc.pv, ecur[k + 1], ecur[k], true);
+            double* en = cl_smooth(cluster, L, C, L.r, ecur[k], ealt[k], false, smoth, isnsp, sum_r[k], &red, flip, rank);
+            if (en != ecur[k]) { ealt[k] = ecur[k]; ecur[k] = en; }
+        }
+        if (k == 0) break;
+        --k;
+    }
+    if (ecur[0] != sl[0].e) {
+        const CLevel& C = cls[0];
+        for (int i = C.r0 + threadIdx.x; i < C.r1; i += kCT) sl[0].e[i] = __ldcg(ecur[0] + i);
+    }
+}
+
+__global__ void slice_bounds_kernel(const LevelDev* __restrict__ levels, int J, int* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= J * (kCS + 1)) return;
+    const int k = t / (kCS + 1), r = t % (kCS + 1);
+    const LevelDev& L = levels[k];
+    const int rpc = (L.N + kCS - 1) / kCS;
+    const int row = min(L.N, r * rpc);
+    out[t] = L.ap[row];
 }
 
 // ------------------------------------------------------------------ general PCG (persistent, cooperative)
@@ -598,7 +833,23 @@ void smooth_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, int post, bool e_ze
 }
 
 // cycle on level k (0-based): rhs in lv[k].r, correction in lv[k].e
+ClusterPlan plan_for_level(const Hierarchy& H, int k) {
+    ClusterPlan q = H.cluster_plan;
+    const int sh = k - H.cluster_from;
+    if (sh > 0) {
+        q.nl -= sh;
+        for (int t = 0; t + sh < kCL; ++t) { q.staged[t] = q.staged[t + sh]; q.smem_off[t] = q.smem_off[t + sh]; q.rpc[t] = q.rpc[t + sh]; q.cap[t] = q.cap[t + sh]; }
+    }
+    return q;
+}
+
 void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {
+    if (k >= H.cluster_from && k < H.J - 1) {
+        Phase ph(c, "solve.cluster_cycle_kernel");
+        SSN_LAUNCH(c, cluster_cycle_kernel, kCS, kCT, H.cluster_smem, H.dev.p, k, H.J, H.smoth, isnsp, wcycle ? 1 : 0,
+                   e_zero ? 1 : 0, plan_for_level(H, k));
+        return;
+    }
     if (k >= H.small_from || k == H.J - 1) {
         SSN_REQUIRE(H.J - k <= 16, SSN_E_INVALID, "hierarchy deeper than 16 small levels");
         Phase ph(c, "solve.coarse_cycle_kernel");
@@ -616,6 +867,41 @@ void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_
 }
 
 }  // namespace
+
+// Builds the shared-memory staging plan of the cluster kernel for levels k0..J-1 (once per hierarchy).
+void build_cluster_plan(ssn_ctx* c, Hierarchy& H) {
+    H.cluster_from = H.J;                                  // disabled unless everything below qualifies
+    const int J = H.J;
+    if (J < 2 || H.lv[J - 1].N > 32) return;
+    int k0 = J - 1;
+    while (k0 > 0 && H.lv[k0 - 1].N <= 4096 && H.lv[k0 - 1].A.nnz <= (1 << 18) && !H.lv[k0 - 1].bigph && (J - (k0 - 1)) <= kCL) --k0;
+    if (k0 >= J - 1) return;
+    Buf<int> bounds(c, (size_t)J * (kCS + 1));
+    SSN_LAUNCH(c, slice_bounds_kernel, cdiv(J * (kCS + 1), 128), 128, 0, H.dev.p, J, bounds.p);
+    std::vector<int> hb((size_t)J * (kCS + 1));
+    read_back(c, bounds.p, hb.data(), hb.size());
+    ClusterPlan plan{};
+    plan.nl = J - k0;
+    size_t budget = 200 * 1024, used = 0;
+    for (int t = 0; t < kCL; ++t) { plan.staged[t] = 0; plan.smem_off[t] = 0; plan.rpc[t] = 1; plan.cap[t] = 0; }
+    for (int k = J - 1; k >= k0; --k) {                    // coarsest levels first: they are visited most
+        const int t = k - k0;
+        const int N = H.lv[k].N, rpc = (N + kCS - 1) / kCS;
+        plan.rpc[t] = rpc;
+        int cap = 0;
+        for (int r = 0; r < kCS; ++r) cap = std::max(cap, hb[(size_t)k * (kCS + 1) + r + 1] - hb[(size_t)k * (kCS + 1) + r]);
+        cap = ((cap + 1) / 2) * 2;
+        const size_t bytes = (size_t)(((rpc + 1) * 4 + 15) / 16) * 16 + (size_t)cap * 12 + 16;
+        if (used + bytes <= budget) { plan.staged[t] = 1; plan.smem_off[t] = (int)used; plan.cap[t] = cap; used += ((bytes + 15) / 16) * 16; }
+    }
+    H.cluster_plan = plan; H.cluster_smem = used; H.cluster_from = k0;
+    SSN_CUDA(cudaFuncSetAttribute(cluster_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(used ? used : 16)));
+}
+
+void debug_cycles(unsigned long long* out64, bool reset) {
+    cudaMemcpyFromSymbol(out64, g_dbg_cycles, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_dbg_cycles, z, sizeof(z)); }
+}
 
 void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev, bool wcycle, bool e_is_zero) {
     SSN_REQUIRE(c->hier != nullptr, SSN_E_NO_HIERARCHY, "MG cycle called without a live hierarchy");

@@ -3,6 +3,7 @@
 #include "amg.cuh"
 #include "plan_ops.cuh"
 #include "solvers.cuh"
+#include <cstdlib>
 
 using namespace ssn;
 
@@ -45,6 +46,9 @@ int ssn_create(ssn_ctx** out, int device) {
     if (device >= ndev) return SSN_E_INVALID;
     ssn_ctx* c = new ssn_ctx();
     c->device = device;
+    // the 8-CTA cluster cycle kernel is correct (parity-tested) but not yet faster than the single-CTA
+    // kernel at these level sizes: opt-in with SSN_CLUSTER=1 until its per-phase latency is tuned
+    { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
     try {
         SSN_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -95,6 +99,10 @@ const char* ssn_profile_dump(ssn_ctx* c) {
     }
     c->prof_acc.clear();
     return c->prof_text.c_str();
+}
+
+int ssn_debug_cycles(ssn_ctx* c, unsigned long long* out64, int reset) {
+    return guarded(c, [&] { sync(c); debug_cycles(out64, reset != 0); });
 }
 
 int ssn_rng_reset(ssn_ctx* c, uint32_t seed) { return guarded(c, [&] { rng_reset(c, seed); sync(c); }); }

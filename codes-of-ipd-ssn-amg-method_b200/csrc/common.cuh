@@ -57,6 +57,7 @@ struct ssn_ctx {
     // Class_AMG hierarchy (the reference's globals Ack/Prok/Rk/J/smoth_it)
     ssn::Hierarchy* hier = nullptr;
     // optional phase profiler (ssn_profile_enable): wall time per named phase, stream-synchronised
+    bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
     bool prof = false;
     std::map<std::string, std::pair<double, long>> prof_acc;
     std::string prof_text;

@@ -122,6 +122,8 @@ SSN_API int64_t ssn_launch_count(ssn_ctx *ctx);
  * stream synchronised on both sides; ssn_profile_dump returns a text table and resets it. */
 SSN_API int  ssn_profile_enable(ssn_ctx *ctx, int on);
 SSN_API const char *ssn_profile_dump(ssn_ctx *ctx);
+/* cycle counters of the small-level cycle kernel: out64[0..63] (development aid) */
+SSN_API int  ssn_debug_cycles(ssn_ctx *ctx, unsigned long long *out64, int reset);
 
 /* The library-owned MATLAB random stream (mt19937ar, init_genrand(5489), genrand_res53):
  * stands for MATLAB's global `rand` state consumed at AMG/mis_set.m:31,35 and

@@ -187,3 +187,35 @@ def test_pot_bordered_solves(gpu, oracle):
     assert np.linalg.norm(z2 - z2_ref) <= 1e-7 * np.linalg.norm(z2_ref)
     with pytest.raises(gpu.SsnError):
         gpu.AMG4POT(pd, AMG_OPTS, "twogrid")
+
+
+@pytest.mark.parametrize("tag", ["k12_s2", "k30_s1", "k40_s2", "k80_s2"])
+def test_full_size_128x128_grid_systems(gpu, oracle, tag):
+    """SsN systems of the headline configuration (128x128 grid, N = 32768) recorded from the device
+    solve (tools/save_states.py): ASAt from the recorded active set, then Hybrid_AMG against the
+    oracle -- identical component count, cycle count, random draws; solution <= 1e-6."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "ssn_states_g128.npz"))
+    g = int(d["g"]); m = n = g * g
+    lin = d[tag + "_lin"]
+    s = torch.zeros(m * n, dtype=torch.uint8, device="cuda"); s[torch.from_numpy(lin).cuda()] = 1
+    p = np.ones(m); q = np.ones(n)
+    H = gpu.ASAt(s, torch.ones(m, dtype=torch.float64, device="cuda"), torch.ones(n, dtype=torch.float64, device="cuda"))
+    del s
+    ii, jj = lin % m, lin // m                       # the same matrix for the oracle, from the coordinates
+    rows = np.concatenate([np.arange(n), jj, n + ii, n + np.arange(m)]); cols = np.concatenate([np.arange(n), n + ii, jj, n + np.arange(m)])
+    vals = np.concatenate([np.bincount(jj, minlength=n).astype(float), np.ones(lin.size), np.ones(lin.size), np.bincount(ii, minlength=m).astype(float)])
+    H_ref = sp.csc_matrix((vals, (rows, cols)), shape=(m + n, m + n)); H_ref.eliminate_zeros(); H_ref.sort_indices()
+    Hs = csc_sorted(H.to_scipy())
+    assert np.array_equal(Hs.indptr, H_ref.indptr) and np.array_equal(Hs.indices, H_ref.indices) and np.array_equal(Hs.data, H_ref.data)
+    pd = {"bk1": float(d[tag + "_bk1"]), "tk": float(d[tag + "_tk"]), "p": p, "q": q, "T": sp.diags(np.zeros(m + n)), "H0": H_ref, "z": d[tag + "_z"]}
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, res_ref, info_ref = oracle.Hybrid_AMG(pd, AMG_OPTS)
+    zeta, it, res, info = gpu.Hybrid_AMG(dict(pd, H0=H), AMG_OPTS)
+    assert list(info) == list(info_ref) and it == it_ref
+    assert gpu.rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    assert np.linalg.norm(zeta - z_ref) <= 1e-6 * np.linalg.norm(z_ref)
+    Jk = pd["bk1"] * sp.identity(m + n) + H_ref / pd["tk"]
+    assert np.linalg.norm(Jk @ zeta - pd["z"]) <= 1e-9 * np.linalg.norm(pd["z"])

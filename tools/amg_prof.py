@@ -36,6 +36,16 @@ def main():
         print(f"{tag}: nnz(H0)={pd['H0'].nnz} comps={info[0]} cycles={it} res={res:.1e} ms={(time.time() - t0) * 1e3:.2f} launches={ssnamg.launch_count() - l0}")
     if prof:
         print(ssnamg.profile_dump())
+    import ctypes
+    from importlib import import_module
+    lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
+    ctx = lib.context(); buf = (ctypes.c_ulonglong * 64)()
+    ctx.call("ssn_debug_cycles", ctypes.cast(buf, ctypes.c_void_p), 1)
+    names = {0: "smooth", 8: "resid+restrict", 16: "prolong", 24: "pcg"}
+    for base, nm in names.items():
+        for k in range(8):
+            if buf[32 + base + k]:
+                print(f"  dbg {nm:15s} level+{k}: {buf[base + k] / 1e3:10.1f} kcycles over {buf[32 + base + k]} calls -> {buf[base + k] / buf[32 + base + k]:9.0f} cyc/call")
 
 
 if __name__ == "__main__":
