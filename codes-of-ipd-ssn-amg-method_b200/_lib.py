@@ -68,6 +68,7 @@ SIGNATURES = {
     "ssn_free": (_int, [_vp, _vp]),
     "ssn_memcpy_h2d": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "ssn_memcpy_d2h": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "ssn_memcpy_d2d": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "ssn_csr_free": (_int, [_vp, _pcsr]),
     "ssn_csr_upload": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _pcsr]),
     "ssn_csr_download": (_int, [_vp, _pcsr, _vp, _vp, _vp]),
@@ -79,6 +80,8 @@ SIGNATURES = {
                                  _pdbl, _pi64]),
     "ssn_asat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_asat_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
+    "ssn_active_coo": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_vp), _pi64]),
+    "ssn_asat_coo": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_asatz": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "ssn_invaat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp]),
     "ssn_invhht": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp]),

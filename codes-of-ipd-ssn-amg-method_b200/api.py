@@ -44,7 +44,7 @@ def _dev(x, dtype=None, count=None):
         t = t.contiguous()
     else:
         a = np.asarray(x)
-        npd = {torch.float64: np.float64, torch.uint8: np.uint8, torch.int32: np.int32}[dtype]
+        npd = {torch.float64: np.float64, torch.uint8: np.uint8, torch.int32: np.int32, torch.int64: np.int64}[dtype]
         if a.dtype == np.bool_ and npd is np.uint8:
             a = a.view(np.uint8)
         a = np.ascontiguousarray(a.reshape(-1, order="F"), dtype=npd)
@@ -240,6 +240,31 @@ def ASAt(s, p, q):
     sd = _dev(s, torch.uint8, count=m * n)
     st = CSR()
     ctx.call("ssn_asat", _ptr(sd), _ptr(pd), _ptr(qd), m, n, C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
+def active_coo(s_loc, m_loc, n, row_offset=0, m_global=None):
+    """Global column-major linear indices (int64, 0-based, slab CSC order) of the active entries of a
+    row slab of the plan -- the exchange format of the row-sharded ASAt."""
+    torch = _torch(); ctx = context()
+    sd = _dev(s_loc, torch.uint8, count=m_loc * n)
+    ptr = C.c_void_p(); E = C.c_int64(0)
+    ctx.call("ssn_active_coo", _ptr(sd), int(m_loc), int(n), int(row_offset), int(m_global if m_global is not None else m_loc),
+             C.byref(ptr), C.byref(E))
+    out = torch.empty(E.value, dtype=torch.int64, device="cuda")
+    if E.value:
+        ctx.check(ctx.lib.ssn_memcpy_d2d(ctx.h, C.c_void_p(out.data_ptr()), ptr, C.c_size_t(8 * E.value)))
+    ctx.call("ssn_free", ptr)
+    return out
+
+
+def ASAt_coo(lin_sorted, p, q):
+    """``H = ASAt(s,p,q)`` from ``find(s)-1`` (ascending global linear indices, int64)."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    ld = _dev(lin_sorted, torch.int64)
+    st = CSR()
+    ctx.call("ssn_asat_coo", _ptr(ld), int(ld.numel()), _ptr(pd), _ptr(qd), m, n, C.byref(st))
     return DeviceCSR(ctx, st)
 
 

@@ -119,6 +119,9 @@ int ssn_memcpy_h2d(ssn_ctx* c, void* d, const void* s, size_t b) {
 int ssn_memcpy_d2h(ssn_ctx* c, void* d, const void* s, size_t b) {
     return guarded(c, [&] { if (b) SSN_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, c->stream)); sync(c); });
 }
+int ssn_memcpy_d2d(ssn_ctx* c, void* d, const void* s, size_t b) {
+    return guarded(c, [&] { if (b) SSN_CUDA(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, c->stream)); sync(c); });
+}
 int ssn_csr_free(ssn_ctx* c, ssn_csr* A) {
     return guarded(c, [&] {
         if (!A) return;
@@ -210,6 +213,17 @@ int ssn_asat_host(ssn_ctx* c, const uint8_t* s, const double* p, const double* q
         SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
         SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
         Csr h = asat(c, ds, dp, dq, m, n); sync(c); h.release_to(H);
+    });
+}
+int ssn_asat_coo(ssn_ctx* c, const int64_t* lin, int64_t E, const double* p, const double* q, int64_t m, int64_t n, ssn_csr* H) {
+    return guarded(c, [&] { SSN_REQUIRE(H, SSN_E_INVALID, "ASAt: null output"); Csr h = asat_coo(c, (const long long*)lin, E, p, q, m, n); sync(c); h.release_to(H); });
+}
+int ssn_active_coo(ssn_ctx* c, const uint8_t* s, int64_t m_loc, int64_t n, int64_t row_offset, int64_t m_global, int64_t** lin_out, int64_t* E_out) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(s && lin_out && E_out, SSN_E_INVALID, "active_coo: null");
+        long long* l = nullptr; int64_t E = 0;
+        active_coo(c, s, m_loc, n, row_offset, m_global, &l, &E); sync(c);
+        *lin_out = (int64_t*)l; *E_out = E;
     });
 }
 int ssn_asatz(ssn_ctx* c, const double* z, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, double* y) {

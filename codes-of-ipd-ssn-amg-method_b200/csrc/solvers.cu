@@ -95,6 +95,64 @@ void build_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Active
 
 }  // namespace
 
+namespace {
+
+__global__ void lin_from_coo_kernel(int64_t E, const int* __restrict__ yrow, const int* __restrict__ ycol, int64_t row_offset,
+                                    int64_t m_global, long long* __restrict__ lin) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        lin[e] = (long long)(yrow[e] + row_offset) + (long long)ycol[e] * (long long)m_global;
+}
+__global__ void coo_from_lin_kernel(int64_t E, const long long* __restrict__ lin, int64_t m, int* __restrict__ yrow,
+                                    int* __restrict__ ycol, int* __restrict__ colcount, int* __restrict__ rowcount) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        const long long l = lin[e];
+        const int j = (int)(l / m), i = (int)(l - (long long)j * m);
+        yrow[e] = i; ycol[e] = j;
+        atomicAdd(colcount + j, 1); atomicAdd(rowcount + i, 1);
+    }
+}
+
+Csr asat_from_active(ssn_ctx* c, ActiveSet& a, const double* p, const double* q, int64_t m, int64_t n) {
+    const int N = (int)(m + n);
+    Buf<double> dval(c, N); Buf<int> len(c, N);
+    SSN_LAUNCH(c, asat_rowlen_kernel, cdiv(N, 128), 128, 0, (int)n, (int)m, a.colptr.p, a.yrow.p, a.rowptr.p, a.ycolT.p, p, q, dval.p, len.p);
+    Csr H = csr_alloc_from_counts(c, N, N, len);
+    if (H.nnz) SSN_LAUNCH(c, asat_fill_kernel, cdiv((int64_t)N * 32, 256), 256, 0, (int)n, (int)m, a.colptr.p, a.yrow.p, a.rowptr.p,
+                          a.ycolT.p, p, q, dval.p, H.ptr.p, H.idx.p, H.val.p);
+    return H;
+}
+
+}  // namespace
+
+// The active set of a (row slab of a) plan as global column-major linear indices, in the slab's
+// own CSC order (used by the row-sharded multi-GPU path to exchange active sets, O(E) integers).
+void active_coo(ssn_ctx* c, const uint8_t* s, int64_t m_loc, int64_t n, int64_t row_offset, int64_t m_global,
+                long long** lin_out, int64_t* E_out) {
+    Buf<int> colptr, yrow, ycol, rowcount;
+    const int64_t E = plan_active_set(c, s, m_loc, n, colptr, yrow, ycol, rowcount);
+    Buf<long long> lin(c, E);
+    if (E) SSN_LAUNCH(c, lin_from_coo_kernel, 592, 256, 0, E, yrow.p, ycol.p, row_offset, m_global, lin.p);
+    *E_out = E; *lin_out = lin.release();
+}
+
+// H = ASAt from the sorted global linear indices of the active set (what find(s) returns)
+Csr asat_coo(ssn_ctx* c, const long long* lin_sorted, int64_t E, const double* p, const double* q, int64_t m, int64_t n) {
+    SSN_REQUIRE(p && q && m > 0 && n > 0 && E >= 0 && (E == 0 || lin_sorted), SSN_E_INVALID, "ASAt(coo): bad arguments");
+    SSN_REQUIRE(E < ((int64_t)1 << 30), SSN_E_TOO_LARGE, "ASAt(coo): nnz(s) >= 2^30");
+    ActiveSet a; a.E = E;
+    Buf<int> colcount(c, n), rowcount(c, m);
+    colcount.zero(); rowcount.zero();
+    a.yrow.alloc(c, E); a.ycol.alloc(c, E); a.colptr.alloc(c, n + 1); a.rowptr.alloc(c, m + 1); a.ycolT.alloc(c, E);
+    if (E) SSN_LAUNCH(c, coo_from_lin_kernel, 592, 256, 0, E, lin_sorted, m, a.yrow.p, a.ycol.p, colcount.p, rowcount.p);
+    scan_counts_to_ptr(c, colcount, a.colptr, n);
+    scan_counts_to_ptr(c, rowcount, a.rowptr, m);
+    if (E) {
+        Buf<int> keys_out(c, E);
+        stable_sort_pairs(c, a.yrow, keys_out, a.ycol, a.ycolT, E, (int)(m > 1 ? m : 2));
+    }
+    return asat_from_active(c, a, p, q, m, n);
+}
+
 Csr asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n) {
     SSN_REQUIRE(s && p && q && m > 0 && n > 0, SSN_E_INVALID, "ASAt: bad arguments");
     SSN_REQUIRE(m + n < ((int64_t)1 << 30), SSN_E_TOO_LARGE, "ASAt: m+n too large");

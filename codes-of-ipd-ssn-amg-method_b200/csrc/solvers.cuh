@@ -4,6 +4,8 @@
 #include "sparse.cuh"
 namespace ssn {
 Csr asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n);
+Csr asat_coo(ssn_ctx* c, const long long* lin_sorted, int64_t E, const double* p, const double* q, int64_t m, int64_t n);
+void active_coo(ssn_ctx* c, const uint8_t* s, int64_t m_loc, int64_t n, int64_t row_offset, int64_t m_global, long long** lin_out, int64_t* E_out);
 void asatz(ssn_ctx* c, const double* z, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, double* y);
 void invaat(ssn_ctx* c, const double* x, const double* p, const double* q, int64_t m, int64_t n, double sg1, double sg2, double* y);
 void invhht(ssn_ctx* c, const double* v, const double* p, const double* q, int64_t m, int64_t n, double sg, const double* phi, double* y);

@@ -137,6 +137,7 @@ SSN_API int  ssn_malloc(ssn_ctx *ctx, size_t bytes, void **ptr_dev);
 SSN_API int  ssn_free(ssn_ctx *ctx, void *ptr_dev);
 SSN_API int  ssn_memcpy_h2d(ssn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 SSN_API int  ssn_memcpy_d2h(ssn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+SSN_API int  ssn_memcpy_d2d(ssn_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 SSN_API int  ssn_csr_free(ssn_ctx *ctx, ssn_csr *A);
 SSN_API int  ssn_csr_upload(ssn_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
                     const int32_t *rowptr_host, const int32_t *colidx_host,
@@ -178,6 +179,16 @@ SSN_API int ssn_asat(ssn_ctx *ctx, const uint8_t *s_dev, const double *p_dev, co
              int64_t m, int64_t n, ssn_csr *H_out);
 SSN_API int ssn_asat_host(ssn_ctx *ctx, const uint8_t *s_host, const double *p_host,
                   const double *q_host, int64_t m, int64_t n, ssn_csr *H_out);
+
+/* Row-sharded (multi-GPU) form of ASAt.m:15: ssn_active_coo compacts the logical active set of a
+ * row slab (m_loc x n, rows [row_offset, row_offset+m_loc) of the m_global x n plan) into global
+ * column-major linear indices (what MATLAB's find(s) returns, 0-based; *lin_out is a device
+ * array of *E_out entries, release it with ssn_free); ssn_asat_coo assembles H from the
+ * ascending union of those lists -- O(E) integers cross NVLink instead of m*n bytes. */
+SSN_API int ssn_active_coo(ssn_ctx *ctx, const uint8_t *s_dev, int64_t m_loc, int64_t n, int64_t row_offset,
+                   int64_t m_global, int64_t **lin_out, int64_t *E_out);
+SSN_API int ssn_asat_coo(ssn_ctx *ctx, const int64_t *lin_sorted_dev, int64_t E, const double *p_dev,
+                 const double *q_dev, int64_t m, int64_t n, ssn_csr *H_out);
 
 /* y = ASAtz(z,s,p,q) -- ASAtz.m:15-22, reproduced as written (Q*p at :21; needs m == n). */
 SSN_API int ssn_asatz(ssn_ctx *ctx, const double *z_dev, const uint8_t *s_dev, const double *p_dev,
