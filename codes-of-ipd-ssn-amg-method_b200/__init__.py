@@ -12,5 +12,5 @@ from .api import (Ax, Aty, ASAt, ASAtz, ASAt_coo, active_coo, invAAt, invHHt, pr
                   strength, mis_set, cf_split, transfer, amg_setup, amg_clear,
                   MG_Vcycle, MG_Wcycle, Class_AMG, PCG, components, Hybrid_AMG,
                   aug_PCG, AMG4POT, PCG4POT, rescaled_system, spmv, spgemm,
-                  transpose, DeviceCSR, rng_reset, rng_drawn, rand, launch_count, profile,
+                  transpose, DeviceCSR, rng_reset, rng_drawn, rand, launch_count, profile, set_dense_tail,
                   profile_dump)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ssn_version": (_int, []),
     "ssn_launch_count": (_i64, [_vp]),
     "ssn_profile_enable": (_int, [_vp, _int]),
+    "ssn_set_dense_tail": (_int, [_vp, _int, _int]),
     "ssn_profile_dump": (C.c_char_p, [_vp]),
     "ssn_debug_cycles": (_int, [_vp, _vp, _int]),
     "ssn_rng_reset": (_int, [_vp, C.c_uint32]),

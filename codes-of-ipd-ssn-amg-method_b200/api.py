@@ -516,6 +516,11 @@ def launch_count():
     return context().launches()
 
 
+def set_dense_tail(enable=True, max_n=0):
+    """Collapse the tail of small AMG levels into dense cycle operators (default) or walk it step by step."""
+    ctx = context(); ctx.call("ssn_set_dense_tail", 1 if enable else 0, int(max_n))
+
+
 def profile(enable=True):
     """Switch the library's phase profiler on/off (development aid)."""
     ctx = context(); ctx.lib.ssn_profile_enable(ctx.h, 1 if enable else 0)

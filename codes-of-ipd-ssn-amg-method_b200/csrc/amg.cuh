@@ -26,6 +26,8 @@ struct Level {
     double xx = 0.0;
     // setup trace (kept for parity tests: C/F split and strength flags that produced level k+1)
     Buf<uint8_t> isC;
+    // dense cycle operator of this level (tail levels only; amg_solve.cu "dense tail")
+    Buf<double> B;
 };
 
 constexpr int kClusterSize = 8;
@@ -44,6 +46,8 @@ struct Hierarchy {
     int smoth = 0;
     int small_from = 0;            // levels >= small_from are solved by the single-block kernel
     int cluster_from = 1 << 30;    // levels >= cluster_from are solved by the 8-CTA cluster kernel
+    int dense_from = 1 << 30;      // levels >= dense_from are applied as dense cycle operators B_k
+    int dense_isnsp = -1, dense_w = -1;   // the (isnsp, cycle) the operators were built for
     ClusterPlan cluster_plan{};
     size_t cluster_smem = 0;
     Buf<LevelDev> dev;

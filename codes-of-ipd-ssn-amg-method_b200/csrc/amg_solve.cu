@@ -433,6 +433,308 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
     }
 }
 
+// ------------------------------------------------------------------ dense tail
+//
+// The tail of small levels (N <= kDenseMaxN) is visited 2^k times per W-cycle and every visit is a
+// chain of latency-bound sparse steps.  With a zero guess a cycle on level k is a LINEAR map of
+// its right-hand side, so the tail is collapsed once per hierarchy into explicit dense operators
+// B_k (N_k x N_k, row-major): the coarsest B is PCG(A, e_i) column by column (PCG.m defaults,
+// exactly the solves MG_Wcycle.m:44 performs), and B_k for k < J-1 is ONE level of the cycle
+// (MG_Wcycle.m:15-42: smoth pre-smoothing steps with the kernel correction, restriction, one or
+// two coarse corrections through B_{k+1}, prolongation, smoth post-smoothing steps) applied to the
+// unit vectors, C columns per CTA so the matrix is read once per C columns.  A visit is then one
+// dense matvec, e = B_k r (zero guess) or e += B_k (r - A_k e) (second W visit, MG_Wcycle.m:30).
+// The results differ from the step-by-step kernel by rounding only.
+
+constexpr int kDT = 1024;                                 // threads of the build kernel
+constexpr int kDTW = kDT / 32;
+
+template <int C>
+__device__ __forceinline__ void block_sumC(double (&v)[C], double* red, int& flip) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* buf = red + (flip & 1) * (C * 32);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double t = warp_sum(v[c]);
+        if (lane == 0) buf[c * 32 + w] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = warp_sum(buf[c * 32 + lane]);    // kDT == 1024: 32 warp partials
+    ++flip;
+}
+
+// acc[c] = sum_e val[e] * x[idx[e]][c] over a row, kBT lanes per row, x in shared memory as [n][C]
+template <int C>
+__device__ __forceinline__ void row_dot_multi(const int* __restrict__ ptr, const int* __restrict__ idx,
+                                              const double* __restrict__ val, const double* x, int row, int sub,
+                                              bool valid, double (&acc)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.0;
+    if (valid) {
+        const int e1 = ptr[row + 1];
+        int e = ptr[row] + sub;
+        for (; e + kBT < e1; e += 2 * kBT) {
+            const int j0 = idx[e], j1 = idx[e + kBT];
+            const double a0 = val[e], a1 = val[e + kBT];
+            const double* x0 = x + (size_t)j0 * C; const double* x1 = x + (size_t)j1 * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fma(a1, x1[c], fma(a0, x0[c], acc[c]));
+        }
+        if (e < e1) {
+            const int j0 = idx[e]; const double a0 = val[e]; const double* x0 = x + (size_t)j0 * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fma(a0, x0[c], acc[c]);
+        }
+    }
+#pragma unroll
+    for (int o = kBT / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+}
+
+// y[nrows][C] (+)= M * x[.][C], CSR M, both vectors in shared memory
+template <int C>
+__device__ void spmm_smem(int nrows, const int* ptr, const int* idx, const double* val, const double* x, double* y, int mode) {
+    const int sub = threadIdx.x % kBT;                    // mode 0: y = Mx, 1: y += Mx, 2: y = y - Mx
+    for (int base = 0; base < nrows; base += kDT / kBT) {
+        const int row = base + threadIdx.x / kBT;
+        const bool valid = row < nrows;
+        double acc[C];
+        row_dot_multi<C>(ptr, idx, val, x, row, sub, valid, acc);
+        if (valid && sub == 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                double* yy = y + (size_t)row * C + c;
+                *yy = (mode == 0) ? acc[c] : (mode == 1 ? *yy + acc[c] : *yy - acc[c]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// y[n][C] (+)= B * x[n][C], dense row-major B (global), warp per row
+template <int C>
+__device__ void dense_smem(int n, const double* __restrict__ B, const double* x, double* y, bool add) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int row = w; row < n; row += kDTW) {
+        double acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.0;
+        const double* Br = B + (size_t)row * n;
+        for (int j = lane; j < n; j += 32) {
+            const double b = Br[j];
+            const double* xj = x + (size_t)j * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fma(b, xj[c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) { double* yy = y + (size_t)row * C + c; *yy = add ? (*yy + acc[c]) : acc[c]; }
+        }
+    }
+    __syncthreads();
+}
+
+// `steps` damped-Jacobi steps with the kernel correction on C right-hand sides at once (the
+// multi-column twin of blk_smooth); r is the unit block (col0) when runit, else zero is never used.
+template <int C>
+__device__ double* smooth_multi(const LevelDev& L, int col0, double* ecur, double* ealt, bool e_zero, int steps, int isnsp,
+                                const double (&sum_r)[C], double* red, int& flip) {
+    const int sub = threadIdx.x % kBT;
+    if (steps == 0) {
+        if (e_zero) { for (int i = threadIdx.x; i < L.N * C; i += kDT) ecur[i] = 0.0; __syncthreads(); }
+        return ecur;
+    }
+    double dotAe[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) dotAe[c] = 0.0;
+    if (isnsp && !e_zero) {
+        for (int i = threadIdx.x; i < L.N; i += kDT) {
+            const double axi = L.Axi[i];
+#pragma unroll
+            for (int c = 0; c < C; ++c) dotAe[c] = fma(axi, ecur[(size_t)i * C + c], dotAe[c]);
+        }
+        block_sumC<C>(dotAe, red, flip);
+    }
+    for (int it = 0; it < steps; ++it) {
+        double coef[C], part[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { coef[c] = isnsp ? (sum_r[c] - dotAe[c]) / L.xx : 0.0; part[c] = 0.0; }
+        for (int base = 0; base < L.N; base += kDT / kBT) {
+            const int row = base + threadIdx.x / kBT;
+            const bool valid = row < L.N;
+            double d[C];
+            if (!e_zero) row_dot_multi<C>(L.ap, L.ai, L.av, ecur, row, sub, valid, d);
+            else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) d[c] = 0.0;
+            }
+            if (valid && sub == 0) {
+                const double axi = L.Axi[row], di = L.dinv[row];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double ri = (row == col0 + c) ? 1.0 : 0.0;
+                    const double gi = ri - d[c];
+                    const double en = (e_zero ? 0.0 : ecur[(size_t)row * C + c]) + coef[c] + di * (gi - axi * coef[c]);
+                    ealt[(size_t)row * C + c] = en;
+                    part[c] = fma(axi, en, part[c]);
+                }
+            }
+        }
+        block_sumC<C>(part, red, flip);                   // the barrier inside also publishes ealt
+#pragma unroll
+        for (int c = 0; c < C; ++c) dotAe[c] = part[c];
+        double* t = ecur; ecur = ealt; ealt = t;
+        e_zero = false;
+    }
+    return ecur;
+}
+
+// B_k columns [C*blockIdx.x, +C): one level of the cycle applied to unit vectors
+template <int C>
+__global__ void __launch_bounds__(kDT) dense_build_kernel(LevelDev L, LevelDev Lc, const double* __restrict__ Bc, int smoth,
+                                                          int isnsp, int twice, double* __restrict__ B) {
+    extern __shared__ __align__(16) double dsm_d[];
+    __shared__ double red[2 * C * 32];
+    const int N = L.N, Nc = Lc.N;
+    double* e0 = dsm_d; double* e1 = e0 + (size_t)N * C; double* g = e1 + (size_t)N * C;
+    double* rc = g + (size_t)N * C; double* ec = rc + (size_t)Nc * C; double* dc = ec + (size_t)Nc * C;
+    const int col0 = blockIdx.x * C;
+    int flip = 0;
+    double sum_r[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) sum_r[c] = (col0 + c < N) ? 1.0 : 0.0;
+    double* ecur = smooth_multi<C>(L, col0, e0, e1, true, smoth, isnsp, sum_r, red, flip);     // MG_Wcycle.m:15-24
+    double* ealt = (ecur == e0) ? e1 : e0;
+    {   // g = r - A e                                                                            :26
+        const int sub = threadIdx.x % kBT;
+        for (int base = 0; base < N; base += kDT / kBT) {
+            const int row = base + threadIdx.x / kBT;
+            const bool valid = row < N;
+            double d[C];
+            row_dot_multi<C>(L.ap, L.ai, L.av, ecur, row, sub, valid, d);
+            if (valid && sub == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) g[(size_t)row * C + c] = ((row == col0 + c) ? 1.0 : 0.0) - d[c];
+            }
+        }
+        __syncthreads();
+    }
+    spmm_smem<C>(Nc, Lc.tp, Lc.ti, Lc.tv, g, rc, 0);                                          // rc = Pro' g
+    dense_smem<C>(Nc, Bc, rc, ec, false);                                                     // :28
+    if (twice) {                                                                              // :30
+        for (int i = threadIdx.x; i < Nc * C; i += kDT) dc[i] = rc[i];
+        __syncthreads();
+        spmm_smem<C>(Nc, Lc.ap, Lc.ai, Lc.av, ec, dc, 2);                                     // dc = rc - A_c ec
+        dense_smem<C>(Nc, Bc, dc, ec, true);
+    }
+    spmm_smem<C>(N, Lc.pp, Lc.pi, Lc.pv, ec, ecur, 1);                                        // :32
+    ecur = smooth_multi<C>(L, col0, ecur, ealt, false, smoth, isnsp, sum_r, red, flip);       // :34-42
+    for (int i = threadIdx.x; i < N * C; i += kDT) {
+        const int row = i / C, c = i % C;
+        if (col0 + c < N) B[(size_t)row * N + col0 + c] = ecur[i];
+    }
+}
+
+// coarsest level: column i of B = PCG(A, e_i) with the defaults of PCG.m:18-23 (one warp, N <= 32)
+__device__ double warp_pcg_lane(const LevelDev& L, double r) {
+    const int lane = threadIdx.x & 31;
+    const bool valid = lane < L.N;
+    const int e0 = valid ? L.ap[lane] : 0, e1 = valid ? L.ap[lane + 1] : 0;
+    int maxlen = e1 - e0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    const double diag = valid ? level_diag(L, lane) : 1.0;
+    double p = r / diag, xi = 0.0;
+    double delta_new = warp_sum(r * p);
+    const double delta_0 = delta_new, tol2 = 1e-11 * 1e-11;
+    int it = 0;
+    while (it < 10000 && delta_new > tol2 * delta_0) {
+        const double delta_old = delta_new;
+        double q = 0.0;
+        for (int t = 0; t < maxlen; ++t) {
+            const int e = e0 + t;
+            const bool has = e < e1;
+            const int j = has ? L.ai[e] : 0;
+            const double a = has ? L.av[e] : 0.0;
+            const double pj = __shfl_sync(0xffffffffu, p, j);
+            q = fma(a, pj, q);
+        }
+        const double alpha = delta_old / warp_sum(q * p);
+        xi += alpha * p;
+        r -= alpha * q;
+        const double w = r / diag;
+        delta_new = warp_sum(r * w);
+        p = w + (delta_new / delta_old) * p;
+        ++it;
+    }
+    return xi;
+}
+
+__global__ void __launch_bounds__(32) dense_coarsest_warp_kernel(LevelDev L, double* __restrict__ B) {
+    const int col = blockIdx.x, lane = threadIdx.x;
+    const double xi = warp_pcg_lane(L, (lane == col) ? 1.0 : 0.0);
+    if (lane < L.N) B[(size_t)lane * L.N + col] = xi;
+}
+
+// coarsest level with more than 32 unknowns: block-wide PCG per column, vectors in shared memory
+__global__ void __launch_bounds__(256) dense_coarsest_block_kernel(LevelDev L, double* __restrict__ B) {
+    extern __shared__ __align__(16) double dsm_d[];
+    __shared__ double red[32];
+    const int n = L.N, col = blockIdx.x;
+    double* x = dsm_d; double* r = x + n; double* p = r + n; double* q = p + n;
+    double dn = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double ri = (i == col) ? 1.0 : 0.0, pi = ri / level_diag(L, i);
+        r[i] = ri; p[i] = pi; x[i] = 0.0; dn = fma(ri, pi, dn);
+    }
+    double delta_new = block_sum(dn, red);
+    const double delta_0 = delta_new, tol2 = 1e-11 * 1e-11;
+    int it = 0;
+    while (it < 10000 && delta_new > tol2 * delta_0) {
+        const double delta_old = delta_new;
+        double qp = 0.0;
+        for (int i = threadIdx.x; i < n; i += 256) {
+            double s = 0.0;
+            for (int e = L.ap[i]; e < L.ap[i + 1]; ++e) s = fma(L.av[e], p[L.ai[e]], s);
+            q[i] = s; qp = fma(s, p[i], qp);
+        }
+        qp = block_sum(qp, red);
+        const double alpha = delta_old / qp;
+        double dnew = 0.0;
+        for (int i = threadIdx.x; i < n; i += 256) {
+            x[i] += alpha * p[i];
+            const double ri = r[i] - alpha * q[i];
+            r[i] = ri; q[i] = ri / level_diag(L, i);
+            dnew = fma(ri, q[i], dnew);
+        }
+        delta_new = block_sum(dnew, red);
+        const double beta = delta_new / delta_old;
+        for (int i = threadIdx.x; i < n; i += 256) p[i] = q[i] + beta * p[i];
+        __syncthreads();
+        ++it;
+    }
+    for (int i = threadIdx.x; i < n; i += 256) B[(size_t)i * n + col] = x[i];
+}
+
+// y (+)= B x, dense row-major n x n: one warp per row
+__global__ void __launch_bounds__(256) dense_apply_kernel(int n, const double* __restrict__ B, const double* __restrict__ x,
+                                                          double* __restrict__ y, int add) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const double* Br = B + (size_t)row * n;
+    double s0 = 0.0, s1 = 0.0;
+    int j = lane;
+    for (; j + 32 < n; j += 64) { s0 = fma(Br[j], x[j], s0); s1 = fma(Br[j + 32], x[j + 32], s1); }
+    if (j < n) s0 = fma(Br[j], x[j], s0);
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) y[row] = add ? (y[row] + s) : s;
+}
+
 // ------------------------------------------------------------------ cluster cycle kernel
 //
 // The single CTA above is bound by one SM's L2 bandwidth and issue rate.  For the mid-size
@@ -843,7 +1145,64 @@ ClusterPlan plan_for_level(const Hierarchy& H, int k) {
     return q;
 }
 
+// Builds B_k for the tail levels (coarsest first); (isnsp, cycle) are part of the operator.
+void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
+    H.dense_isnsp = isnsp; H.dense_w = wcycle ? 1 : 0; H.dense_from = H.J;
+    if (!c->dense_tail) return;
+    const int J = H.J;
+    int from = J;
+    for (int k = J - 1; k >= 0; --k) {
+        if (H.lv[k].N <= c->dense_max_n && !H.lv[k].bigph && H.lv[k].N > 0) from = k; else break;
+    }
+    if (from >= J) return;
+    Phase ph(c, "solve.build_dense_tail");
+    for (int k = J - 1; k >= from; --k) {
+        Level& L = H.lv[k];
+        const int N = L.N;
+        L.B.alloc(c, (size_t)N * N);
+        const LevelDev Ld = level_dev(L);
+        if (k == J - 1) {
+            if (N <= 32) SSN_LAUNCH(c, dense_coarsest_warp_kernel, N, 32, 0, Ld, L.B.p);
+            else {
+                const size_t smem = sizeof(double) * 4 * (size_t)N;
+                SSN_LAUNCH(c, dense_coarsest_block_kernel, N, 256, smem, Ld, L.B.p);
+            }
+            continue;
+        }
+        Level& Lc = H.lv[k + 1];
+        const LevelDev Lcd = level_dev(Lc);
+        const int twice = (wcycle && (k + 1 != J - 1)) ? 1 : 0;
+        int C = N > 592 ? 8 : (N > 296 ? 4 : (N > 148 ? 2 : 1));
+        auto smem_for = [&](int cc) { return sizeof(double) * (size_t)cc * (3 * (size_t)N + 3 * (size_t)Lc.N); };
+        while (C > 1 && smem_for(C) > 200 * 1024) C >>= 1;
+        const size_t smem = smem_for(C);
+        const int grid = cdiv(N, C);
+        auto go = [&](auto T) {
+            constexpr int CC = decltype(T)::value;
+            SSN_CUDA(cudaFuncSetAttribute(dense_build_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSN_LAUNCH(c, dense_build_kernel<CC>, grid, kDT, smem, Ld, Lcd, Lc.B.p, H.smoth, isnsp, twice, L.B.p);
+        };
+        if (C == 8) go(std::integral_constant<int, 8>());
+        else if (C == 4) go(std::integral_constant<int, 4>());
+        else if (C == 2) go(std::integral_constant<int, 2>());
+        else go(std::integral_constant<int, 1>());
+    }
+    H.dense_from = from;
+}
+
 void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {
+    if (H.dense_isnsp != isnsp || H.dense_w != (wcycle ? 1 : 0)) build_dense_tail(c, H, isnsp, wcycle);
+    if (k >= H.dense_from) {
+        Level& L = H.lv[k];
+        Phase ph(c, "solve.dense_apply");
+        const int grid = cdiv((int64_t)L.N * 32, 256);
+        if (e_zero) SSN_LAUNCH(c, dense_apply_kernel, grid, 256, 0, L.N, L.B.p, L.r.p, L.e.p, 0);
+        else {
+            launch_resid(c, L, L.r, L.e.p, L.g, H.part);
+            SSN_LAUNCH(c, dense_apply_kernel, grid, 256, 0, L.N, L.B.p, L.g.p, L.e.p, 1);
+        }
+        return;
+    }
     if (k >= H.cluster_from && k < H.J - 1) {
         Phase ph(c, "solve.cluster_cycle_kernel");
         SSN_LAUNCH(c, cluster_cycle_kernel, kCS, kCT, H.cluster_smem, H.dev.p, k, H.J, H.smoth, isnsp, wcycle ? 1 : 0,

@@ -49,6 +49,8 @@ int ssn_create(ssn_ctx** out, int device) {
     // the 8-CTA cluster cycle kernel is correct (parity-tested) but not yet faster than the single-CTA
     // kernel at these level sizes: opt-in with SSN_CLUSTER=1 until its per-phase latency is tuned
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
+    { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
         SSN_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -88,6 +90,12 @@ int ssn_set_stream(ssn_ctx* c, void* s) { if (!c) return SSN_E_INVALID; c->strea
 int ssn_synchronize(ssn_ctx* c) { return guarded(c, [&] { sync(c); }); }
 int64_t ssn_launch_count(ssn_ctx* c) { return c ? c->launches : 0; }
 
+int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
+    if (!c) return SSN_E_INVALID;
+    c->dense_tail = dense_tail != 0;
+    if (dense_max_n > 0) c->dense_max_n = dense_max_n;
+    return SSN_OK;
+}
 int ssn_profile_enable(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->prof = on != 0; return SSN_OK; }
 const char* ssn_profile_dump(ssn_ctx* c) {
     if (!c) return "";

@@ -58,6 +58,8 @@ struct ssn_ctx {
     ssn::Hierarchy* hier = nullptr;
     // optional phase profiler (ssn_profile_enable): wall time per named phase, stream-synchronised
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
+    bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
+    int dense_max_n = 1024;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
     bool prof = false;
     std::map<std::string, std::pair<double, long>> prof_acc;
     std::string prof_text;

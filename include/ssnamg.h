@@ -122,6 +122,10 @@ SSN_API int64_t ssn_launch_count(ssn_ctx *ctx);
  * stream synchronised on both sides; ssn_profile_dump returns a text table and resets it. */
 SSN_API int  ssn_profile_enable(ssn_ctx *ctx, int on);
 SSN_API const char *ssn_profile_dump(ssn_ctx *ctx);
+/* Solver tuning knobs (also read from the environment at ssn_create: SSN_DENSE_TAIL, SSN_DENSE_MAXN):
+ * dense_tail != 0 collapses the tail of small AMG levels (N <= dense_max_n) into dense cycle
+ * operators (one matvec per visit); 0 walks them step by step.  dense_max_n <= 0 keeps the value. */
+SSN_API int  ssn_set_dense_tail(ssn_ctx *ctx, int dense_tail, int dense_max_n);
 /* cycle counters of the small-level cycle kernel: out64[0..63] (development aid) */
 SSN_API int  ssn_debug_cycles(ssn_ctx *ctx, unsigned long long *out64, int reset);
 

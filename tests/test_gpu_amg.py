@@ -193,6 +193,31 @@ def test_class_amg_matches_oracle(gpu, oracle, m, n, density, cycle):
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
 
 
+@pytest.mark.parametrize("cycle", ["w", "v"])
+def test_dense_tail_equals_stepwise(gpu, oracle, cycle):
+    """The tail of small levels applied as dense cycle operators (default) against the step-by-step
+    tail kernel: same cycle counts, same residual histories, solutions equal to rounding."""
+    m, n = 2500, 2300
+    pd, Ae, f = ssn_matrix(oracle, m, n, 0.0015, seed=5 * m)
+    guess = 0.01 * np.random.RandomState(2).random_sample(m + n)
+    out = {}
+    try:
+        for mode in (0, 1):
+            gpu.set_dense_tail(bool(mode))
+            for isnsp in (1, 0):
+                o = dict(AMG_OPTS, fnode=n, cycle=cycle, guess=guess, isnsp=isnsp)
+                gpu.rng_reset()
+                out[mode, isnsp] = gpu.Class_AMG(Ae, f, o)
+    finally:
+        gpu.set_dense_tail(True)
+    for isnsp in (1, 0):
+        x0, it0, rel0, relk0, _ = out[0, isnsp]; x1, it1, rel1, relk1, _ = out[1, isnsp]
+        assert it0 == it1
+        big = relk0 > 1e-9
+        assert np.allclose(relk1[big], relk0[big], rtol=1e-7)
+        assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+
+
 @pytest.mark.parametrize("precd", [1, 2, 5])
 def test_pcg_matches_oracle(gpu, oracle, precd):
     m, n = 300, 260
