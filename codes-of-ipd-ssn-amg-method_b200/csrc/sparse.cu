@@ -342,136 +342,223 @@ Csr extract_principal(ssn_ctx* c, const CsrView& A, const int* sel, int nsel, co
 
 namespace {
 
-constexpr int kMaxWindow = 16384;
+constexpr int kMaxWindow = 8192;
 
-__global__ void spgemm_ub_kernel(int nrows, const int* __restrict__ ap, const int* __restrict__ ai,
-                                 const int* __restrict__ bp, int ncolsB, int* __restrict__ ub) {
-    const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= nrows) return;
-    long long s = 0;
-    for (int e = ap[row] + lane; e < ap[row + 1]; e += 32) { const int k = ai[e]; s += bp[k + 1] - bp[k]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) ub[row] = (s < (long long)ncolsB) ? (int)s : ncolsB;
+__device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
 }
 
-// One block per output row (grid-stride).  Dense accumulator window acc[W] + touched bitmap
-// in shared memory.  The A-row is walked in ascending k; all threads cooperate on one B-row at
-// a time (distinct columns => race-free) with a barrier between consecutive k, which fixes the
-// per-entry summation order.  Runs of single-entry B-rows with strictly increasing columns
-// (the identity block of an interpolation matrix) are applied in parallel.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) spgemm_numeric_kernel(
+// split[k*(nwin+1) + w] = first entry of B-row k with column >= w*W  (w = 0..nwin)
+__global__ void spgemm_split_kernel(int nrowsB, const int* __restrict__ bp, const int* __restrict__ bi, int W, int nwin,
+                                    int* __restrict__ split) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nrowsB * (nwin + 1)) return;
+    const int k = (int)(t / (nwin + 1)), w = (int)(t % (nwin + 1));
+    const int b0 = bp[k], b1 = bp[k + 1];
+    split[t] = (w == 0) ? b0 : (w == nwin ? b1 : lower_bound_dev(bi, b0, b1, w * W));
+}
+
+// upper bound of the number of entries of every work item (output row, column window)
+__global__ void spgemm_ub_kernel(int nrows, const int* __restrict__ ap, const int* __restrict__ ai,
+                                 const int* __restrict__ bp, const int* __restrict__ split, int W, int nwin, int ncolsB,
+                                 int* __restrict__ ub) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= (int64_t)nrows * nwin) return;
+    const int row = (int)(item / nwin), win = (int)(item % nwin);
+    long long s = 0;
+    for (int e = ap[row] + lane; e < ap[row + 1]; e += 32) {
+        const int k = ai[e];
+        s += split ? (split[(size_t)k * (nwin + 1) + win + 1] - split[(size_t)k * (nwin + 1) + win]) : (bp[k + 1] - bp[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int wcols = (win == nwin - 1) ? (ncolsB - win * W) : W;
+    if (lane == 0) ub[item] = (s < (long long)wcols) ? (int)s : wcols;
+}
+
+// One block per work item = (output row, window of W output columns), handed out through an
+// atomic counter.  Dense accumulator acc[W] in shared memory.  The A-row is walked in ascending k
+// in chunks of THREADS entries; the B-rows of a chunk (restricted to the window, pre-multiplied
+// by a_ik) are STAGED into shared memory by all threads at once -- the global-memory latency is
+// paid once per chunk, not once per B-row -- and then accumulated group by group with one
+// barrier between groups.  A group is one B-row, or a maximal run of single-entry B-rows with
+// strictly increasing columns (the identity block of an interpolation matrix): inside a group
+// all columns are distinct, so the adds are race-free, and consecutive groups are ordered by the
+// barrier, which fixes the per-entry summation order (k ascending, multiply then add, no FMA).
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) spgemm_numeric_kernel(
     int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
-    const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, int ncolsB, int W,
-    const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval, int* __restrict__ rownnz) {
+    const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, const int* __restrict__ split,
+    int ncolsB, int W, int nwin, const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval,
+    int* __restrict__ cnt_out, int* __restrict__ item_counter) {
     extern __shared__ unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);
-    unsigned* flags = reinterpret_cast<unsigned*>(acc + W);
-    __shared__ int s_k[THREADS];
+    double* s_prod = acc + W;
+    int* s_col = reinterpret_cast<int*>(s_prod + CAP);
+    constexpr int NW = THREADS / 32;
+    constexpr int U = CAP / THREADS;
+    static_assert(CAP % THREADS == 0, "CAP must be a multiple of THREADS");
+    __shared__ int s_off[THREADS + 1];        // staged-entry offset of every B-row of the chunk
+    __shared__ int s_lo[THREADS];             // first entry of the (window-restricted) B-row in bi/bv
+    __shared__ int s_len[THREADS];
+    __shared__ int s_c[THREADS];              // column of a single-entry row (else -1)
     __shared__ double s_a[THREADS];
-    __shared__ int s_c[THREADS];
-    __shared__ int s_warp[THREADS / 32];
-    __shared__ int s_total;
+    __shared__ int s_gstart[THREADS + 1];     // staged-entry offset of every group
+    __shared__ int s_warp[NW], s_warp2[NW];
+    __shared__ int s_total, s_groups, s_item;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nwords = (W + 31) >> 5;
+    const int nitems = nrows * nwin;
 
-    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(item_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= nitems) break;
+        const int row = item / nwin, win = item - row * nwin;
+        const int w0 = win * W;
+        const int wcols = (ncolsB - w0 < W) ? (ncolsB - w0) : W;
         const int a0 = ap[row], a1 = ap[row + 1];
-        const int out0 = ubptr[row];
+        const int out0 = ubptr[item];
         int written = 0;
         if (a1 > a0) {
-            for (int w0 = 0; w0 < ncolsB; w0 += W) {
-                const int w1 = w0 + W;
-                for (int t = tid; t < W; t += THREADS) acc[t] = 0.0;
-                for (int t = tid; t < nwords; t += THREADS) flags[t] = 0u;
-                __syncthreads();
-                for (int eb = a0; eb < a1; eb += THREADS) {
-                    const int e = eb + tid;
-                    const int nb = (a1 - eb < THREADS) ? (a1 - eb) : THREADS;
-                    int k = -1, len = 0, bstart = 0, c1 = -1; double a = 0.0;
-                    if (e < a1) {
-                        k = ai[e]; a = av[e]; bstart = bp[k]; len = bp[k + 1] - bstart;
-                        if (len == 1) c1 = bi[bstart];
-                    }
-                    s_k[tid] = k; s_a[tid] = a; s_c[tid] = c1;
-                    __syncthreads();
-                    bool ok = (e >= a1) || (len == 1 && (tid == 0 || c1 > s_c[tid - 1]));
-                    const int fast = __syncthreads_and(ok ? 1 : 0);
-                    if (fast) {
-                        if (e < a1 && c1 >= w0 && c1 < w1) {
-                            const int cc = c1 - w0;
-                            acc[cc] = __dadd_rn(acc[cc], __dmul_rn(a, bv[bstart]));
-                            atomicOr(flags + (cc >> 5), 1u << (cc & 31));
-                        }
-                        __syncthreads();
-                    } else {
-                        for (int j = 0; j < nb; ++j) {
-                            const int kj = s_k[j];
-                            const int b0 = bp[kj], b1 = bp[kj + 1];
-                            if (b1 == b0) continue;
-                            if (bi[b1 - 1] < w0 || bi[b0] >= w1) continue;   // row misses the window
-                            const double aj = s_a[j];
-                            for (int t = b0 + tid; t < b1; t += THREADS) {
-                                const int col = bi[t];
-                                if (col >= w0 && col < w1) {
-                                    const int cc = col - w0;
-                                    acc[cc] = __dadd_rn(acc[cc], __dmul_rn(aj, bv[t]));
-                                    atomicOr(flags + (cc >> 5), 1u << (cc & 31));
-                                }
-                            }
-                            __syncthreads();
-                        }
-                        __syncthreads();   // skipped rows have no barrier: re-align before s_k is reused
-                    }
+            for (int t = tid; t < wcols; t += THREADS) acc[t] = 0.0;
+            __syncthreads();
+            for (int eb = a0; eb < a1; eb += THREADS) {
+                const int e = eb + tid;
+                const int nb = (a1 - eb < THREADS) ? (a1 - eb) : THREADS;
+                int lo = 0, len = 0, c1 = -1; double a = 0.0;
+                if (e < a1) {
+                    const int k = ai[e]; a = av[e];
+                    int b0, b1;
+                    if (split) { b0 = split[(size_t)k * (nwin + 1) + win]; b1 = split[(size_t)k * (nwin + 1) + win + 1]; }
+                    else { b0 = bp[k]; b1 = bp[k + 1]; }
+                    lo = b0; len = b1 - b0;
+                    if (len == 1) c1 = bi[b0];
                 }
-                // ---- compact the window in ascending column order
-                const int per = (W + THREADS - 1) / THREADS;
-                const int lo = tid * per, hi = (lo + per < W) ? (lo + per) : W;
-                int cnt = 0;
-                for (int t = lo; t < hi; ++t)
-                    if (((flags[t >> 5] >> (t & 31)) & 1u) && acc[t] != 0.0) ++cnt;
-                int incl = cnt;
+                s_lo[tid] = lo; s_len[tid] = len; s_c[tid] = c1; s_a[tid] = a;
+                __syncthreads();
+                // a row opens a new group unless it extends a run of unit rows with increasing columns
+                int ng = 0;
+                if (len > 0) ng = (tid > 0 && len == 1 && s_len[tid - 1] == 1 && c1 > s_c[tid - 1]) ? 0 : 1;
+                int il = len, ig = ng;                     // inclusive scans of len and ng
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                if (lane == 31) s_warp[wid] = incl;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int vl = __shfl_up_sync(0xffffffffu, il, o), vg = __shfl_up_sync(0xffffffffu, ig, o);
+                    if (lane >= o) { il += vl; ig += vg; }
+                }
+                if (lane == 31) { s_warp[wid] = il; s_warp2[wid] = ig; }
                 __syncthreads();
                 if (wid == 0) {
-                    int wv = (lane < THREADS / 32) ? s_warp[lane] : 0;
-                    int wi = wv;
+                    int wl = (lane < NW) ? s_warp[lane] : 0, wg = (lane < NW) ? s_warp2[lane] : 0;
+                    int xl = wl, xg = wg;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-                    if (lane < THREADS / 32) s_warp[lane] = wi - wv;
-                    if (lane == 31) s_total = wi;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int vl = __shfl_up_sync(0xffffffffu, xl, o), vg = __shfl_up_sync(0xffffffffu, xg, o);
+                        if (lane >= o) { xl += vl; xg += vg; }
+                    }
+                    if (lane < NW) { s_warp[lane] = xl - wl; s_warp2[lane] = xg - wg; }
+                    if (lane == NW - 1) { s_total = xl; s_groups = xg; }
                 }
                 __syncthreads();
-                int pos = out0 + written + s_warp[wid] + incl - cnt;
-                for (int t = lo; t < hi; ++t)
-                    if (((flags[t >> 5] >> (t & 31)) & 1u) && acc[t] != 0.0) { tidx[pos] = w0 + t; tval[pos] = acc[t]; ++pos; }
-                written += s_total;
+                const int off = s_warp[wid] + il - len;                 // exclusive
+                const int gid = s_warp2[wid] + ig - ng;                 // groups before this row
+                s_off[tid] = off;
+                if (ng) s_gstart[gid] = off;
+                const int total = s_total, groups = s_groups;
+                if (tid == 0) { s_off[THREADS] = total; s_gstart[groups] = total; }
+                __syncthreads();
+                int g = 0;
+                for (int P0 = 0; P0 < total; P0 += CAP) {
+                    const int P1 = (P0 + CAP < total) ? (P0 + CAP) : total;
+                    // ---- stage entries [P0, P1): entry t belongs to the last row j with s_off[j] <= t
+                    int src[U]; double aj[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int t = P0 + u * THREADS + tid;
+                        src[u] = -1; aj[u] = 0.0;
+                        if (t < P1) {
+                            int jl = 0, jh = nb;                                // upper_bound over s_off[0..nb)
+                            while (jl < jh) { const int mid = (jl + jh) >> 1; if (s_off[mid] <= t) jl = mid + 1; else jh = mid; }
+                            const int j = jl - 1;
+                            src[u] = s_lo[j] + (t - s_off[j]); aj[u] = s_a[j];
+                        }
+                    }
+                    int col[U]; double bval[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { col[u] = 0; bval[u] = 0.0; if (src[u] >= 0) { col[u] = bi[src[u]]; bval[u] = bv[src[u]]; } }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (src[u] >= 0) { s_col[u * THREADS + tid] = col[u] - w0; s_prod[u * THREADS + tid] = __dmul_rn(aj[u], bval[u]); }
+                    __syncthreads();
+                    // ---- accumulate group by group (g persists across passes: a group may straddle two)
+                    while (g < groups) {
+                        int gs = s_gstart[g];
+                        const int ge_full = s_gstart[g + 1];
+                        if (gs >= P1) break;
+                        if (gs < P0) gs = P0;
+                        const int ge = (ge_full > P1) ? P1 : ge_full;
+                        for (int t = gs + tid; t < ge; t += THREADS) {
+                            const int cc = s_col[t - P0];
+                            acc[cc] = __dadd_rn(acc[cc], s_prod[t - P0]);
+                        }
+                        __syncthreads();
+                        if (ge_full > P1) break;
+                        ++g;
+                    }
+                }
                 __syncthreads();
             }
+            // ---- compact the window in ascending column order (exact zeros dropped)
+            const int per = (wcols + THREADS - 1) / THREADS;
+            const int clo = (tid * per < wcols) ? tid * per : wcols, chi = (clo + per < wcols) ? (clo + per) : wcols;
+            int cnt = 0;
+            for (int t = clo; t < chi; ++t) if (acc[t] != 0.0) ++cnt;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                int wv = (lane < NW) ? s_warp[lane] : 0;
+                int wi = wv;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+                if (lane < NW) s_warp[lane] = wi - wv;
+                if (lane == NW - 1) s_total = wi;
+            }
+            __syncthreads();
+            int pos = out0 + s_warp[wid] + incl - cnt;
+            for (int t = clo; t < chi; ++t)
+                if (acc[t] != 0.0) { tidx[pos] = w0 + t; tval[pos] = acc[t]; ++pos; }
+            written = s_total;
         }
-        if (tid == 0) rownnz[row] = written;
+        if (tid == 0) cnt_out[item] = written;
+        __syncthreads();
     }
 }
 
-__global__ void sum_int64_kernel(const int* __restrict__ v, int n, unsigned long long* __restrict__ out) {
+__global__ void sum_int64_kernel(const int* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
     unsigned long long s = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)v[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += (unsigned long long)v[i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
-__global__ void compact_rows_kernel(int nrows, const int* __restrict__ ubptr, const int* __restrict__ optr,
-                                    const int* __restrict__ tidx, const double* __restrict__ tval,
-                                    int* __restrict__ oidx, double* __restrict__ oval) {
+// item segments (upper-bound layout) -> final CSR arrays; one warp per item
+__global__ void compact_items_kernel(int64_t nitems, const int* __restrict__ ubptr, const int* __restrict__ cptr,
+                                     const int* __restrict__ tidx, const double* __restrict__ tval,
+                                     int* __restrict__ oidx, double* __restrict__ oval) {
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= nrows) return;
-    const int src = ubptr[row], dst = optr[row], len = optr[row + 1] - dst;
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= nitems) return;
+    const int src = ubptr[item], dst = cptr[item], len = cptr[item + 1] - dst;
     for (int t = lane; t < len; t += 32) { oidx[dst + t] = tidx[src + t]; oval[dst + t] = tval[src + t]; }
+}
+__global__ void gather_rowptr_kernel(int nrows, int nwin, const int* __restrict__ cptr, int* __restrict__ optr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nrows) optr[i] = cptr[(size_t)i * nwin];
 }
 
 }  // namespace
@@ -484,36 +571,66 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
         C.ptr.alloc(c, (size_t)nrows + 1); C.ptr.zero(); C.nnz = 0; C.idx.alloc(c, 0); C.val.alloc(c, 0);
         return C;
     }
-    // upper bounds (64-bit check of the total on the host side through a double sum is overkill:
-    // ub[row] <= ncolsB, so total <= nrows*ncolsB; reject only if that could overflow AND does)
-    Buf<int> ub(c, nrows), ubptr(c, (size_t)nrows + 1), rownnz(c, nrows);
-    SSN_LAUNCH(c, spgemm_ub_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, ncolsB, ub.p);
+    // ---- work items: (row, window of W columns).  Few rows with a lot of work each are split into
+    // narrow windows so that every SM gets items.
+    int W = ((ncolsB + 31) / 32) * 32; if (W > kMaxWindow) W = kMaxWindow;
+    int nwin = cdiv(ncolsB, W);
+    const double work = (double)A.nnz * ((double)B.nnz / (double)(B.nrows > 0 ? B.nrows : 1));
+    const int64_t want_items = 4 * (int64_t)c->num_sms;
+    if ((int64_t)nrows * nwin < want_items && work > 2e6 && ncolsB > 512) {
+        int nw = (int)cdiv(want_items, nrows);
+        const int max_nw = cdiv(ncolsB, 256);
+        if (nw > max_nw) nw = max_nw;
+        W = ((cdiv(ncolsB, nw) + 31) / 32) * 32;
+        nwin = cdiv(ncolsB, W);
+    }
+    SSN_REQUIRE((int64_t)nrows * nwin < ((int64_t)1 << 30), SSN_E_TOO_LARGE, "spgemm: too many work items");
+    const int64_t nitems = (int64_t)nrows * nwin;
+    Buf<int> split;
+    if (nwin > 1) {
+        split.alloc(c, (size_t)B.nrows * (nwin + 1));
+        SSN_LAUNCH(c, spgemm_split_kernel, cdiv((int64_t)B.nrows * (nwin + 1), 256), 256, 0, B.nrows, B.ptr, B.idx, W, nwin, split.p);
+    }
+    const int* splitp = nwin > 1 ? split.p : nullptr;
+    Buf<int> ub(c, nitems), ubptr(c, (size_t)nitems + 1), cnt(c, nitems), cptr(c, (size_t)nitems + 1);
+    SSN_LAUNCH(c, spgemm_ub_kernel, cdiv(nitems * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, splitp, W, nwin, ncolsB, ub.p);
     if ((int64_t)nrows * (int64_t)ncolsB >= ((int64_t)1 << 31)) {      // the int32 scan could wrap: check in 64 bit
         Buf<unsigned long long> tot(c, 1); tot.zero();
-        SSN_LAUNCH(c, sum_int64_kernel, 64, 256, 0, ub.p, nrows, tot.p);
+        SSN_LAUNCH(c, sum_int64_kernel, 64, 256, 0, ub.p, nitems, tot.p);
         const unsigned long long t = read_scalar(c, tot.p);
         SSN_REQUIRE(t < (1ull << 31), SSN_E_TOO_LARGE, "spgemm: intermediate product exceeds the int32 index range");
     }
-    const int64_t ub_total = scan_counts_to_ptr(c, ub, ubptr, nrows);
+    const int64_t ub_total = scan_counts_to_ptr(c, ub, ubptr, nitems);
     Buf<int> tidx(c, (size_t)ub_total); Buf<double> tval(c, (size_t)ub_total);
-    int W = ((ncolsB + 31) / 32) * 32; if (W > kMaxWindow) W = kMaxWindow;
-    const size_t smem = (size_t)W * sizeof(double) + (size_t)((W + 31) / 32) * sizeof(unsigned);
-    if (W > 4096) {
-        auto kern = spgemm_numeric_kernel<512>;
+    Buf<int> counter(c, 1); counter.zero();
+    if (W > 2048) {
+        constexpr int CAP = 2560;
+        const size_t smem = (size_t)W * sizeof(double) + (size_t)CAP * (sizeof(double) + sizeof(int));
+        auto kern = spgemm_numeric_kernel<512, CAP>;
         SSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = nrows < c->num_sms ? nrows : c->num_sms;
-        SSN_LAUNCH(c, kern, grid, 512, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, ncolsB, W, ubptr.p, tidx.p, tval.p, rownnz.p);
+        const int per_sm = (smem + 16 * 1024 <= 110 * 1024) ? 2 : 1;
+        int64_t grid = (int64_t)c->num_sms * per_sm; if (grid > nitems) grid = nitems;
+        SSN_LAUNCH(c, kern, (int)grid, 512, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, splitp, ncolsB, W, nwin,
+                   ubptr.p, tidx.p, tval.p, cnt.p, counter.p);
     } else {
-        auto kern = spgemm_numeric_kernel<128>;
-        const int per_sm = (int)(96 * 1024 / (smem + 4096));
-        int grid = c->num_sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
-        if (grid > nrows) grid = nrows;
-        SSN_LAUNCH(c, kern, grid, 128, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, ncolsB, W, ubptr.p, tidx.p, tval.p, rownnz.p);
+        constexpr int CAP = 1024;
+        const size_t smem = (size_t)W * sizeof(double) + (size_t)CAP * (sizeof(double) + sizeof(int));
+        auto kern = spgemm_numeric_kernel<128, CAP>;
+        SSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)(200 * 1024 / (smem + 6 * 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+        int64_t grid = (int64_t)c->num_sms * per_sm; if (grid > nitems) grid = nitems;
+        SSN_LAUNCH(c, kern, (int)grid, 128, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, splitp, ncolsB, W, nwin,
+                   ubptr.p, tidx.p, tval.p, cnt.p, counter.p);
     }
-    C.ptr.alloc(c, (size_t)nrows + 1);
-    C.nnz = scan_counts_to_ptr(c, rownnz, C.ptr, nrows);
+    C.nnz = scan_counts_to_ptr(c, cnt, cptr, nitems);
     C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
-    if (C.nnz) SSN_LAUNCH(c, compact_rows_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, nrows, ubptr.p, C.ptr.p, tidx.p, tval.p, C.idx.p, C.val.p);
+    if (C.nnz) SSN_LAUNCH(c, compact_items_kernel, cdiv(nitems * 32, 256), 256, 0, nitems, ubptr.p, cptr.p, tidx.p, tval.p, C.idx.p, C.val.p);
+    if (nwin == 1) C.ptr = std::move(cptr);
+    else {
+        C.ptr.alloc(c, (size_t)nrows + 1);
+        SSN_LAUNCH(c, gather_rowptr_kernel, cdiv(nrows + 1, 256), 256, 0, nrows, nwin, cptr.p, C.ptr.p);
+    }
     return C;
 }
 

@@ -47,7 +47,8 @@ def rand_sparse(nr, nc, density, seed, single_rows=False):
 
 
 @pytest.mark.parametrize("shape", [(30, 40, 50, 0.2), (300, 200, 400, 0.03), (1000, 1000, 1000, 0.01),
-                                   (64, 20000, 64, 0.002), (200, 300, 40000, 0.004), (500, 17000, 33000, 0.0005)])
+                                   (64, 20000, 64, 0.002), (200, 300, 40000, 0.004), (500, 17000, 33000, 0.0005),
+                                   (14, 4000, 4000, 0.2), (40, 3000, 20000, 0.1), (700, 900, 9000, 0.05)])
 def test_spgemm_fixed_order_bit_exact(gpu, oracle, shape):
     from oracle.amg import spgemm
     nr, nk, nc, d = shape
