@@ -86,22 +86,32 @@ class ClockSampler(threading.Thread):
 
 def cpu_step_sample(sample, reps=1):
     """The oracle (CPU port of the reference; MATLAB/Octave are absent) on a bounded sample of the
-    same step: the plan-wide part on a row slab of the plan (scaled to the full plan), the AMG
-    solve on the full (n+m) system.  Returns full-problem-equivalent ms per step."""
+    same step: the plan-wide part on a row slab of the plan (scaled to the full plan) -- two
+    residual evaluations (Aty, prox, Ax; APD_SsN_Class1.m:139-144,212), the line-search trials of
+    the step (Aty, prox, norm; :189-211; at most 8 are run and scaled to the step's count) and
+    ASAt -- and the AMG solve on the full (n+m) system.  Returns full-problem-equivalent ms per step."""
     import oracle
     from oracle import driver as odrv
-    w, lam, wlk, p_s, q = sample["w_slab"], sample["lam_slab"], sample["wlk"], sample["p_slab"], sample["q"]
-    tk, bk1, scale = sample["tk"], sample["bk1"], sample["scale"]
+    w, lam, p_s, q = sample["w_slab"], sample["lam_slab"], sample["p_slab"], sample["q"]
+    tk, bk1, scale, trials = sample["tk"], sample["bk1"], sample["scale"], sample["trials"]
     t_plan = t_amg = 0.0
     for _ in range(reps):
         t0 = time.perf_counter()
-        for _ev in range(3):                               # residual+active set, line-search trial, new residual
+        for _ev in range(2):                               # residual + active set, new residual
             z = 1 / tk * (w - oracle.Aty(lam, p_s, q))
             s = (z >= 0) & (z <= np.inf)
             px = np.maximum(z, 0.0)
             oracle.Ax(px, p_s, q); float(px @ px)
         oracle.ASAt(s, p_s, q)
-        t_plan += time.perf_counter() - t0
+        t_fixed = time.perf_counter() - t0
+        run_trials = min(trials, 8)
+        t0 = time.perf_counter()
+        for _tr in range(run_trials):                      # one Armijo trial: Aty + prox + norm
+            z = 1 / tk * (w - oracle.Aty(lam, p_s, q))
+            px = np.maximum(z, 0.0)
+            float(px @ px)
+        t_trials = (time.perf_counter() - t0) * (trials / max(run_trials, 1))
+        t_plan += t_fixed + t_trials
         t0 = time.perf_counter()
         oracle.rng_reset()
         pd = {"bk1": bk1, "tk": tk, "p": sample["p"], "q": q, "T": sample["T"], "H0": sample["H0"], "z": sample["z"]}
@@ -110,7 +120,7 @@ def cpu_step_sample(sample, reps=1):
     return 1e3 * (scale * t_plan + t_amg) / reps, 1e3 * scale * t_plan / reps, 1e3 * t_amg / reps
 
 
-def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows):
+def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows, trials):
     import scipy.sparse as sp
     import torch
     wk = state["wk"].view(n, m)                             # column-major m x n == row-major n x m
@@ -118,7 +128,7 @@ def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows):
     lam = state["lk"].cpu().numpy()
     lam_slab = np.concatenate([lam[:n], lam[n:n + slab_rows]])
     return {"w_slab": w_slab, "lam_slab": lam_slab, "wlk": state["wlk"].cpu().numpy(), "p_slab": np.ones(slab_rows),
-            "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "scale": m / slab_rows,
+            "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "scale": m / slab_rows, "trials": int(trials),
             "T": sp.diags(np.zeros(m + n)), "H0": H0_scipy.tocsc(), "z": z_host}
 
 
@@ -166,14 +176,26 @@ def main():
             ssnamg.rng_reset()
             return drv.ssn_step(state)
 
-    ev_k3 = []                                              # CUDA-event timings of the fused residual kernel
+    if world > 1:
+        k3_w, k3_lam, k3_p, k3_rows = step_fn.w_loc, step_fn._lam_loc(state["lk"]), step_fn.p_loc, step_fn.m_loc
+        state["wk"] = None                                  # the full plan vector is not needed any more
+        torch.cuda.empty_cache()
+    else:
+        k3_w, k3_lam, k3_p, k3_rows = state["wk"], state["lk"], state["p"], m
 
-    def timed_k3():
-        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox",))
-        b.record()
-        ev_k3.append((a, b))
+    lam8 = torch.stack([k3_lam + 0.9 ** t * 1e-3 for t in range(8)]).contiguous()      # eight trial vectors
+
+    def kernel_ms(fn, reps=10):
+        """Mean duration of the plan-wide kernel inside fn(), CUDA events on the launching stream
+        around the launch itself (ssn_kernel_timer)."""
+        for _ in range(3):
+            fn()
+        ssnamg.kernel_timer(True)
+        for _ in range(reps):
+            fn()
+        ms, cnt = ssnamg.kernel_timer_read()
+        ssnamg.kernel_timer(False)
+        return ms / max(cnt, 1)
 
     for _ in range(max(args.warmup, 3)):
         lk_new, Fk_new, info = step_fn()
@@ -184,23 +206,23 @@ def main():
     l0 = ssnamg.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    prof_range = os.environ.get("SSN_BENCH_PROFILE") == "1"      # ncu --profile-from-start off: timed region only
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         lk_new, Fk_new, info = step_fn()
     e1.record()
     torch.cuda.synchronize()
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = ssnamg.launch_count() - l0
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     # dominant HBM-bound kernel, timed alone with CUDA events on the launching stream (sampler still running)
-    if world == 1:
-        for _ in range(3):
-            timed_k3()
-        ev_k3.clear()
-        for _ in range(10):
-            timed_k3()
-        torch.cuda.synchronize()
+    k3_ms = kernel_ms(lambda: ssnamg.prox_residual(k3_w, k3_lam, k3_p, state["q"], state["tk"], float("inf"), want=("Axprox",)))
+    tr_ms = kernel_ms(lambda: ssnamg.prox_trials(k3_w, lam8, k3_p, state["q"], state["tk"], float("inf")))
     sampler.stop_flag = True; sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
@@ -212,19 +234,31 @@ def main():
            "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "ours",
            "config": {"workload": workload, "E_active": int(info["E"]), "nnz_H0": int(info["nnzH"]), "amg_cycles": int(info["itamg"]),
-                      "components": int(info["info"][0]), "line_search_trials": int(info["ll"]) + 1,
+                      "components": int(info["info"][0]), "line_search_trials": int(info["ll"]) + 1, "line_search_passes": int(info.get("ls_passes", 0)),
                       "l2_flush": "inputs larger than L2 (2.1 GB plan vector per pass)", "state_build_s": round(t_state, 1),
                       "sharding": "plan rows over ranks; AMG replicated" if world > 1 else "single GPU"},
            "ssn_steps_per_s": 1e3 / ms_step, "gpu_launches": int(launches), "clocks": sampler.summary()}
 
+    bytes_pass = 8.0 * k3_rows * n                          # one read of the (slab of the) plan-sized wk
+    passes = int(info.get("ls_passes", 0))
+    slab_txt = f", rank 0's {k3_rows}-row slab" if world > 1 else ""
+
+    def roof(kernel, ms, launches):
+        ach = bytes_pass / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel + slab_txt, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_pass, "avg_launch_ms": ms,
+                "launches_per_step": launches, "share_of_step": launches * ms / ms_step,
+                "traffic": None, "frac_of_8TBps_nominal": ach / 8000.0}
+    r_k3 = roof("plan_reduce_kernel<PROX> (fused SsN residual: z, prox, Ax(prox), ||prox||^2; one read of wk)", k3_ms, 2)
+    r_tr = roof("plan_trials_kernel<NT=8> (8 Armijo trials per read of wk: z, prox, ||prox||^2 each)", tr_ms, max(passes - 1, 0))
     if world == 1:
-        k3_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_k3]))
-        bytes_k3 = 8.0 * m * n
-        ach = bytes_k3 / (k3_ms * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": "plan_reduce_kernel<PROX> (fused SsN residual: z, prox, Ax(prox), ||prox||^2)",
-                           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                           "algorithmic_bytes_per_launch": bytes_k3, "avg_launch_ms": k3_ms,
-                           "traffic": load_traffic(), "frac_of_8TBps_nominal": ach / 8000.0}
+        r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials")
+    dominant, other = (r_tr, r_k3) if r_tr["share_of_step"] >= r_k3["share_of_step"] else (r_k3, r_tr)
+    out["roofline"] = dominant
+    out["roofline_other"] = [other]
+    if world > 1:
+        out["collectives_per_step"] = int(info.get("collectives", 0)) // max(1, args.steps + max(args.warmup, 3))
+    if world == 1:
         # ---- e2e: the same step through host buffers (pinned), H2D of the step's inputs + D2H of its result
         hstate = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in state.items()}
         h2d = sum(v.numel() * v.element_size() for v in hstate.values() if isinstance(v, torch.Tensor))
@@ -252,13 +286,15 @@ def main():
             ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
             H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
             z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
-            slab = max(64, m // 16)
-            sample = make_cpu_sample(state, H0, z_host, m, n, slab)
+            slab = max(64, m // 32)
+            trials = int(info["ll"]) + 1
+            sample = make_cpu_sample(state, H0, z_host, m, n, slab, trials)
             cpu_ms, cpu_plan, cpu_amg = cpu_step_sample(sample)
             out["cpu_baseline"] = {"value": cpu_ms, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"oracle (NumPy/SciPy port; MATLAB/Octave absent): plan-wide part on a {slab}-row slab "
-                                             f"of the {m}x{n} plan scaled x{m // slab} ({cpu_plan:.0f} ms), AMG solve on the full "
-                                             f"{m + n}-node system ({cpu_amg:.0f} ms); BLAS threads at default"}
+                                   "sample": f"oracle (NumPy/SciPy port; MATLAB/Octave absent): plan-wide part (2 residual "
+                                             f"evaluations, ASAt, {trials} line-search trials of which at most 8 are run and scaled) "
+                                             f"on a {slab}-row slab of the {m}x{n} plan scaled x{m // slab} ({cpu_plan:.0f} ms), AMG "
+                                             f"solve on the full {m + n}-node system ({cpu_amg:.0f} ms); BLAS threads at default"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -266,11 +302,11 @@ def main():
     return 0
 
 
-def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def load_traffic(which):
+    """dram bytes per launch of a plan-wide kernel from the committed ncu capture (profiles/), if any."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
-        return float(d["dram_bytes_per_launch"])
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(d[which]["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -305,16 +341,20 @@ def run_reference(args, state, m, n, workload):
     ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
     H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
     z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
-    slab = max(64, m // 16)
-    sample = make_cpu_sample(state, H0, z_host, m, n, slab)
+    slab = max(64, m // 32)
+    ssnamg.rng_reset()
+    _, _, info = ssnamg.driver.ssn_step(state)               # only to learn the step's line-search length
+    trials = int(info["ll"]) + 1
+    sample = make_cpu_sample(state, H0, z_host, m, n, slab, trials)
     del state; torch.cuda.empty_cache()
     for _ in range(min(args.warmup, 1)):
         cpu_step_sample(sample)
     steps = max(1, min(args.steps, 3))
     vals = [cpu_step_sample(sample) for _ in range(steps)]
     ms = float(np.mean([v[0] for v in vals]))
-    sample_txt = (f"oracle (NumPy/SciPy port of the reference; MATLAB/Octave absent): plan-wide part on a {slab}-row slab of the "
-                  f"{m}x{n} plan scaled x{m // slab}, AMG solve on the full {m + n}-node system; BLAS threads at default")
+    sample_txt = (f"oracle (NumPy/SciPy port of the reference; MATLAB/Octave absent): plan-wide part (2 residual evaluations, "
+                  f"ASAt, {trials} line-search trials of which at most 8 are run and scaled) on a {slab}-row slab of the {m}x{n} "
+                  f"plan scaled x{m // slab}, AMG solve on the full {m + n}-node system; BLAS threads at default")
     out = {"metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "reference", "config": {"workload": workload},

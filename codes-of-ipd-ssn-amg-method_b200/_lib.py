@@ -60,6 +60,8 @@ SIGNATURES = {
     "ssn_launch_count": (_i64, [_vp]),
     "ssn_profile_enable": (_int, [_vp, _int]),
     "ssn_set_dense_tail": (_int, [_vp, _int, _int]),
+    "ssn_kernel_timer": (_int, [_vp, _int]),
+    "ssn_kernel_timer_read": (_int, [_vp, _pdbl, _pi64]),
     "ssn_profile_dump": (C.c_char_p, [_vp]),
     "ssn_debug_cycles": (_int, [_vp, _vp, _int]),
     "ssn_rng_reset": (_int, [_vp, C.c_uint32]),
@@ -79,6 +81,9 @@ SIGNATURES = {
     "ssn_aty_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "ssn_prox_residual": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _vp, _vp, _vp,
                                  _pdbl, _pi64]),
+    "ssn_prox_trials": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp]),
+    "ssn_linesearch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _int, _dbl, _dbl,
+                              _int, _vp, C.POINTER(_int), _pdbl, _pdbl, C.POINTER(_int)]),
     "ssn_asat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_asat_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_active_coo": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_vp), _pi64]),

@@ -233,6 +233,43 @@ def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count
     return out
 
 
+def _gama_args(gama, m, n):
+    if np.isscalar(gama) or (hasattr(gama, "numel") and gama.numel() == 1) or np.size(gama) == 1:
+        gs = float(gama if np.isscalar(gama) else np.asarray(gama.cpu() if hasattr(gama, "cpu") else gama).reshape(-1)[0])
+        return None, gs
+    return _dev(gama, count=m * n), float("inf")
+
+
+def prox_trials(w, lamT, p, q, tk, gama=np.inf):
+    """``||prox((w - Aty(lam_t))/tk)||^2`` for up to 8 trial dual vectors (rows of ``lamT``) in one read
+    of ``w`` -- the objective of the Armijo trials of Class1/APD_SsN_Class1.m:193-207.  Returns a
+    device tensor of ``len(lamT)`` squared norms."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    wd = _dev(w, count=m * n)
+    lt = lamT if isinstance(lamT, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(lamT, dtype=np.float64))).cuda()
+    lt = lt.to(device="cuda", dtype=torch.float64).reshape(-1, n + m).contiguous()
+    gvec, gs = _gama_args(gama, m, n)
+    out = torch.empty(lt.shape[0], dtype=torch.float64, device="cuda")
+    ctx.call("ssn_prox_trials", _ptr(wd), _ptr(lt), int(lt.shape[0]), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(gvec), gs, _ptr(out))
+    return out
+
+
+def linesearch(w, lam_old, zeta, wlk, p, q, tk, bk1, cF_old, ress, gama=np.inf, nu=0.2, delta=0.9, ll_max=500, batch=8):
+    """Armijo backtracking of Class1/APD_SsN_Class1.m:182-211 with ``batch`` backtracking steps per read of
+    ``w`` (the full step ll = 0 is tried alone first).  Returns ``(lk_new, ll, norm2, cF_new, passes)``."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    wd, lo, ze, wl = _dev(w, count=m * n), _dev(lam_old), _dev(zeta), _dev(wlk)
+    gvec, gs = _gama_args(gama, m, n)
+    out = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ll = C.c_int(0); passes = C.c_int(0); n2 = C.c_double(0.0); cF = C.c_double(0.0)
+    ctx.call("ssn_linesearch", _ptr(wd), _ptr(lo), _ptr(ze), _ptr(wl), _ptr(pd), _ptr(qd), m, n, float(tk), float(bk1),
+             _ptr(gvec), gs, float(nu), float(delta), int(ll_max), float(cF_old), float(ress), int(batch), _ptr(out),
+             C.byref(ll), C.byref(n2), C.byref(cF), C.byref(passes))
+    return out, ll.value, n2.value, cF.value, passes.value
+
+
 def ASAt(s, p, q):
     """``H = ASAt(s,p,q)`` -- reference ASAt.m:2-20 (``s`` logical, one byte per entry)."""
     torch = _torch(); ctx = context()
@@ -514,6 +551,18 @@ def transpose(A):
 
 def launch_count():
     return context().launches()
+
+
+def kernel_timer(enable=True):
+    """Switch on (and reset) / off the CUDA-event timer around the plan-wide kernel launches."""
+    ctx = context(); ctx.call("ssn_kernel_timer", 1 if enable else 0)
+
+
+def kernel_timer_read():
+    """``(total_ms, launches)`` accumulated since ``kernel_timer(True)``."""
+    ctx = context(); ms = C.c_double(0.0); cnt = C.c_int64(0)
+    ctx.call("ssn_kernel_timer_read", C.byref(ms), C.byref(cnt))
+    return ms.value, cnt.value
 
 
 def set_dense_tail(enable=True, max_n=0):

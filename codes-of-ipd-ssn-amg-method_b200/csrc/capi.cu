@@ -90,6 +90,13 @@ int ssn_set_stream(ssn_ctx* c, void* s) { if (!c) return SSN_E_INVALID; c->strea
 int ssn_synchronize(ssn_ctx* c) { return guarded(c, [&] { sync(c); }); }
 int64_t ssn_launch_count(ssn_ctx* c) { return c ? c->launches : 0; }
 
+int ssn_kernel_timer(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->ktimer = on != 0; c->kt_ms = 0.0; c->kt_n = 0; return SSN_OK; }
+int ssn_kernel_timer_read(ssn_ctx* c, double* total_ms, int64_t* launches) {
+    if (!c) return SSN_E_INVALID;
+    if (total_ms) *total_ms = c->kt_ms;
+    if (launches) *launches = c->kt_n;
+    return SSN_OK;
+}
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;
@@ -207,6 +214,21 @@ int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const doub
         double h[2]; read_back(c, scal.p, h, 2);
         if (norm2_out) *norm2_out = h[0];
         if (count_out) *count_out = (int64_t)h[1];
+    });
+}
+
+int ssn_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q, int64_t m, int64_t n,
+                    double tk, const double* gama, double gama_s, double* n2_out) {
+    return guarded(c, [&] { plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, n2_out); sync(c); });
+}
+int ssn_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk, const double* p,
+                   const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama, double gama_s, double nu,
+                   double delta, int ll_max, double cF_old, double ress, int batch, double* lam_new, int* ll_out,
+                   double* n2_out, double* cF_out, int* passes_out) {
+    return guarded(c, [&] {
+        plan_linesearch(c, w, lam_old, zeta, wlk, p, q, m, n, tk, bk1, gama, gama_s, nu, delta, ll_max, cF_old, ress, batch,
+                        lam_new, ll_out, n2_out, cF_out, passes_out);
+        sync(c);
     });
 }
 

@@ -59,7 +59,9 @@ struct ssn_ctx {
     // optional phase profiler (ssn_profile_enable): wall time per named phase, stream-synchronised
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
-    int dense_max_n = 1024;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
+    int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
+    // CUDA-event timer around the launches of the plan-wide kernels (ssn_kernel_timer): bench.py's roofline
+    bool ktimer = false; cudaEvent_t kt0 = nullptr, kt1 = nullptr; double kt_ms = 0.0; int64_t kt_n = 0;
     bool prof = false;
     std::map<std::string, std::pair<double, long>> prof_acc;
     std::string prof_text;
@@ -135,6 +137,25 @@ inline void check_launch(ssn_ctx* c, const char* what) {
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                   \
         ::ssn::check_launch((ctx), #kernel);                                               \
     } while (0)
+
+// Times ONE kernel launch with CUDA events on the launching stream when ssn_kernel_timer is on.
+struct KernelTimer {
+    ssn_ctx* c;
+    explicit KernelTimer(ssn_ctx* ctx) : c(ctx) {
+        if (c->ktimer) {
+            if (!c->kt0) { cudaEventCreate(&c->kt0); cudaEventCreate(&c->kt1); }
+            cudaEventRecord(c->kt0, c->stream);
+        }
+    }
+    ~KernelTimer() {
+        if (c->ktimer) {
+            cudaEventRecord(c->kt1, c->stream);
+            cudaEventSynchronize(c->kt1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, c->kt0, c->kt1);
+            c->kt_ms += ms; c->kt_n += 1;
+        }
+    }
+};
 
 struct Phase {
     ssn_ctx* c; const char* name; std::chrono::steady_clock::time_point t0; long l0;

@@ -22,6 +22,7 @@ constexpr int kWarps = 8;
 constexpr int kStripRows = 128;
 constexpr int kGroupRows = kWarps * kStripRows;   // 1024
 constexpr int kMaxChunkCols = 512;
+constexpr int kMaxTrials = 8;
 
 struct PlanArgs {
     const double* x;        // MODE_AX: x ; MODE_PROX: w
@@ -254,6 +255,217 @@ __global__ void plan_finish_kernel(const double* __restrict__ rowpart, const dou
     }
 }
 
+// ------------------------------------------------------------------ batched line-search trials
+// ||prox((w - Aty(lam_t))/tk)||^2 for NT trial dual vectors lam_t in ONE read of w
+// (Class1/APD_SsN_Class1.m:189-207 evaluates them one Aty + prox + norm pass at a time).  The
+// per-entry arithmetic of every trial is the single-trial kernel's, operation for operation.
+struct TrialArgs {
+    const double* w; const double* p; const double* q;
+    const double* lamT;     // [NT][n+m]
+    const double* gama; double gama_s; double inv_tk;
+    int64_t m, n, ldl;      // ldl = n + m
+    int cols_per_chunk;
+    double* scalpart;       // [num_blocks][NT]
+    const int* unitw;       // device flag: p == 1 and q == 1 everywhere
+    int nt_valid;           // trial slots >= nt_valid repeat the last valid trial vector (NT is 1, 2, 4 or 8)
+};
+
+// UNITW: p == 1 and q == 1 everywhere (every configuration the reference ships): p_i*y1_j + y2_i*q_j
+// is then y1_j + y2_i bit for bit, which takes two of the seven fp64 operations per entry and trial
+// off the fp64 pipe -- the pipe that bounds this kernel once NT >= 3.
+template <bool VEC, int GM, int NT, bool UNITW>
+__device__ __forceinline__ void trials_body(const TrialArgs& a, double* dsm) {
+    __shared__ double red[32];
+    double (*y2s)[kGroupRows] = reinterpret_cast<double (*)[kGroupRows]>(dsm);       // [NT][1024] row parts
+    double* y1s = dsm + NT * kGroupRows;                                              // [NT][cpc]   column parts
+    double* qs = y1s + NT * a.cols_per_chunk;                                         // [cpc]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int64_t m = a.m, n = a.n;
+    const int cpc = a.cols_per_chunk;
+    const int64_t c0 = (int64_t)chunk * cpc;
+    const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
+    const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
+    const int lrow0 = warp * kStripRows + (VEC ? 2 * lane : lane);          // row slot 0 inside the group
+    const int64_t row0 = (int64_t)group * kGroupRows + lrow0;
+    bool rok[4];
+    double pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = row0 + roff<VEC>(k);
+        rok[k] = r < m;
+        pv[k] = (!UNITW && rok[k]) ? a.p[r] : 0.0;
+    }
+    // the row parts of the NT trial vectors of this group's rows -> shared memory
+    for (int i = threadIdx.x; i < NT * kGroupRows; i += kThreads) {
+        const int t = i / kGroupRows, lr = i - t * kGroupRows;
+        const int64_t r = (int64_t)group * kGroupRows + lr;
+        const int ts = (t < a.nt_valid) ? t : (a.nt_valid - 1);
+        y2s[t][lr] = (r < m) ? a.lamT[(size_t)ts * a.ldl + n + r] : 0.0;
+    }
+    for (int i = threadIdx.x; i < NT * cpc; i += kThreads) {
+        const int t = i / cpc, j = i - t * cpc;
+        const int ts = (t < a.nt_valid) ? t : (a.nt_valid - 1);
+        y1s[i] = (c0 + j < c1) ? a.lamT[(size_t)ts * a.ldl + c0 + j] : 0.0;
+    }
+    for (int j = threadIdx.x; j < cpc; j += kThreads) qs[j] = (c0 + j < c1) ? a.q[c0 + j] : 0.0;
+    __syncthreads();
+    double n2[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) n2[t] = 0.0;
+    const bool strip_full = (rbase + kStripRows <= m);
+    size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
+    const size_t step = 2 * (size_t)m;
+
+    auto load_batch = [&](double (&v)[2][4], double (&g)[GM == G_VECTOR ? 2 : 1][4], int64_t c, size_t o) {
+        const bool full = strip_full && (c + 2 <= c1);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const bool cok = full || (c + cc < c1);
+            const double* xp = a.w + o + (size_t)cc * m;
+            if (VEC) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double2 t2 = make_double2(0.0, 0.0);
+                    if (full || (cok && rok[2 * h])) t2 = __ldcs(reinterpret_cast<const double2*>(xp + roff<VEC>(2 * h)));
+                    v[cc][2 * h] = t2.x; v[cc][2 * h + 1] = t2.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[cc][k] = (full || (cok && rok[k])) ? __ldcs(xp + roff<VEC>(k)) : 0.0;
+            }
+            if (GM == G_VECTOR) {
+                const double* gp = a.gama + o + (size_t)cc * m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[GM == G_VECTOR ? cc : 0][k] = (full || (cok && rok[k])) ? __ldcs(gp + roff<VEC>(k)) : 0.0;
+            }
+        }
+    };
+
+    // one batch of 2 columns x 4 rows per lane for all NT trials; FULL: no bounds predicates at all
+    auto compute_batch = [&](auto full_tag, const double (&v)[2][4], const double (&g)[GM == G_VECTOR ? 2 : 1][4], int64_t c) {
+        constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const bool cok = FULL || (c + cc < c1);
+            const int jc = (int)(c - c0) + cc;                 // < cpc (cpc is a multiple of 4)
+            const double qj = UNITW ? 0.0 : qs[jc];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double y1j = y1s[t * cpc + jc];
+                double y2v[4];
+                if (VEC) {
+                    const double2 lo = *reinterpret_cast<const double2*>(&y2s[t][lrow0]);
+                    const double2 hi = *reinterpret_cast<const double2*>(&y2s[t][lrow0 + 64]);
+                    y2v[0] = lo.x; y2v[1] = lo.y; y2v[2] = hi.x; y2v[3] = hi.y;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) y2v[k] = y2s[t][lrow0 + 32 * k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double aty = UNITW ? __dadd_rn(y1j, y2v[k]) : __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                    const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
+                    double pz;
+                    if (GM == G_INF) {
+                        // max(0,z) without a branch or an fp64 compare: clear z when its sign bit is set
+                        // (-0.0 and NaN contribute like the compare-based form: 0, resp. NaN-or-0 -> see header)
+                        const int hi = __double2hiint(z), lo = __double2loint(z);
+                        int keep = ~(hi >> 31);
+                        if (!FULL) keep = (cok && rok[k]) ? keep : 0;
+                        pz = __hiloint2double(hi & keep, lo & keep);
+                    } else {
+                        const bool live = FULL || (cok && rok[k]);
+                        const bool nonneg = live && (z >= 0.0);
+                        const double gm = (GM == G_VECTOR) ? g[GM == G_VECTOR ? cc : 0][k] : a.gama_s;
+                        pz = nonneg ? ((z <= gm) ? z : gm) : (live ? fmin(0.0, gm) : 0.0);
+                    }
+                    n2[t] = fma(pz, pz, n2[t]);
+                }
+            }
+        }
+    };
+
+    double vcur[2][4], vnxt[2][4];
+    double gcur[GM == G_VECTOR ? 2 : 1][4], gnxt[GM == G_VECTOR ? 2 : 1][4];
+    if (c0 < c1) load_batch(vcur, gcur, c0, off);
+    for (int64_t c = c0; c < c1; c += 2, off += step) {
+        if (c + 2 < c1) load_batch(vnxt, gnxt, c + 2, off + step);           // prefetch: overlaps the fp64 work below
+        if (strip_full && (c + 2 <= c1)) compute_batch(std::true_type(), vcur, gcur, c);
+        else                             compute_batch(std::false_type(), vcur, gcur, c);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { vcur[cc][k] = vnxt[cc][k]; if (GM == G_VECTOR) gcur[GM == G_VECTOR ? cc : 0][k] = gnxt[GM == G_VECTOR ? cc : 0][k]; }
+        }
+    }
+    const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const double tot = block_sum(n2[t], red);
+        if (threadIdx.x == 0) a.scalpart[b * NT + t] = tot;
+    }
+}
+
+template <bool VEC, int GM, int NT>
+__global__ void __launch_bounds__(kThreads, 2) plan_trials_kernel(const TrialArgs a) {
+    extern __shared__ __align__(16) double trials_dsm[];
+    if (a.unitw != nullptr && *a.unitw != 0) trials_body<VEC, GM, NT, true>(a, trials_dsm);
+    else                                     trials_body<VEC, GM, NT, false>(a, trials_dsm);
+}
+
+// flag[0] = 1 iff every p_i and q_j equals 1.0 (one block)
+__global__ void __launch_bounds__(256) unit_weights_kernel(const double* __restrict__ p, int64_t m, const double* __restrict__ q,
+                                                           int64_t n, int* __restrict__ flag) {
+    int ok = 1;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) ok &= (p[i] == 1.0);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) ok &= (q[i] == 1.0);
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0) flag[0] = ok;
+}
+
+// out[t] = sum_b scalpart[b][t]  (fixed order)
+__global__ void __launch_bounds__(256) trials_finish_kernel(const double* __restrict__ scalpart, int num_blocks, int nt,
+                                                            double* __restrict__ out) {
+    __shared__ double red[32];
+    for (int t = 0; t < nt; ++t) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) s += scalpart[(size_t)b * nt + t];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) out[t] = s;
+    }
+}
+
+// lamT[t] = lam + alpha[t]*zeta ; f0part: per-block partials of ||lamT[t]||^2 and wlk'lamT[t]
+__global__ void __launch_bounds__(256) trial_vectors_kernel(int64_t N, int nt, const double* __restrict__ lam,
+                                                            const double* __restrict__ zeta, const double* __restrict__ wlk,
+                                                            const double* __restrict__ alpha, double* __restrict__ lamT,
+                                                            double* __restrict__ f0part) {
+    __shared__ double red[32];
+    for (int t = 0; t < nt; ++t) {
+        const double al = alpha[t];
+        double s2 = 0.0, sw = 0.0;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+            const double v = __dadd_rn(lam[i], __dmul_rn(al, zeta[i]));      // lk_old + delta^ll*zeta
+            lamT[(size_t)t * N + i] = v;
+            s2 = fma(v, v, s2); sw = fma(wlk[i], v, sw);
+        }
+        s2 = block_sum(s2, red);
+        sw = block_sum(sw, red);
+        if (threadIdx.x == 0) { f0part[((size_t)blockIdx.x * nt + t) * 2] = s2; f0part[((size_t)blockIdx.x * nt + t) * 2 + 1] = sw; }
+    }
+}
+__global__ void __launch_bounds__(256) trial_f0_finish_kernel(const double* __restrict__ f0part, int nblocks, int nt,
+                                                              double* __restrict__ out /* [nt][2] */) {
+    __shared__ double red[32];
+    for (int t = 0; t < 2 * nt; ++t) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += f0part[(size_t)b * 2 * nt + t];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) out[t] = s;
+    }
+}
+
 struct Tiling { int groups, chunks, cpc; };
 
 Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n) {
@@ -426,11 +638,98 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
                (!z_out || vec_ok(z_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
     const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
 #define SSN_PROX_LAUNCH(V, G) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, V, G>), grid, kThreads, smem, a)
+    {
+    KernelTimer kt(c);
     if (vec) { if (gm == G_INF) SSN_PROX_LAUNCH(true, G_INF); else if (gm == G_SCALAR) SSN_PROX_LAUNCH(true, G_SCALAR); else SSN_PROX_LAUNCH(true, G_VECTOR); }
     else     { if (gm == G_INF) SSN_PROX_LAUNCH(false, G_INF); else if (gm == G_SCALAR) SSN_PROX_LAUNCH(false, G_SCALAR); else SSN_PROX_LAUNCH(false, G_VECTOR); }
+    }
 #undef SSN_PROX_LAUNCH
     SSN_LAUNCH(c, plan_finish_kernel, axp_out ? cdiv(m + n, 256) : 1, 256, 0, rowpart.p, colpart.p, scalpart.p,
                t.chunks, t.groups, m, n, nblocks, axp_out, scal2_dev);
+}
+
+// n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 for t < nt (nt <= kMaxTrials), one read of w
+void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q,
+                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev) {
+    SSN_REQUIRE(m > 0 && n > 0 && w && lamT && p && q && n2_out_dev, SSN_E_INVALID, "prox_trials: bad arguments");
+    SSN_REQUIRE(nt >= 1 && nt <= kMaxTrials, SSN_E_INVALID, "prox_trials: 1 <= nt <= 8");
+    Buf<double> n2_scratch(c, kMaxTrials);
+    const int NTk = nt <= 1 ? 1 : (nt <= 2 ? 2 : (nt <= 4 ? 4 : 8));     // compiled batch sizes
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> scalpart(c, (size_t)NTk * nblocks);
+    Buf<int> unitw(c, 1);
+    SSN_LAUNCH(c, unit_weights_kernel, 1, 256, 0, p, m, q, n, unitw.p);
+    TrialArgs a{};
+    a.unitw = unitw.p; a.nt_valid = nt;
+    a.w = w; a.p = p; a.q = q; a.lamT = lamT; a.gama = gama; a.gama_s = gama_s; a.inv_tk = 1.0 / tk;
+    a.m = m; a.n = n; a.ldl = n + m; a.cols_per_chunk = t.cpc; a.scalpart = scalpart.p;
+    const dim3 grid(t.chunks, t.groups);
+    const bool vec = vec_ok(w, m) && (!gama || vec_ok(gama, m));
+    const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+    const size_t tsmem = sizeof(double) * ((size_t)NTk * kGroupRows + (size_t)(NTk + 1) * t.cpc);
+#define SSN_TRIALS_NT(V, G, NT) do { \
+        SSN_CUDA(cudaFuncSetAttribute((plan_trials_kernel<V, G, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
+        SSN_LAUNCH(c, (plan_trials_kernel<V, G, NT>), grid, kThreads, tsmem, a); } while (0)
+#define SSN_TRIALS_G(V, G) do { if (NTk == 1) SSN_TRIALS_NT(V, G, 1); else if (NTk == 2) SSN_TRIALS_NT(V, G, 2); \
+                                else if (NTk == 4) SSN_TRIALS_NT(V, G, 4); else SSN_TRIALS_NT(V, G, 8); } while (0)
+    {
+    KernelTimer kt(c);
+    if (vec) { if (gm == G_INF) SSN_TRIALS_G(true, G_INF); else if (gm == G_SCALAR) SSN_TRIALS_G(true, G_SCALAR); else SSN_TRIALS_G(true, G_VECTOR); }
+    else     { if (gm == G_INF) SSN_TRIALS_G(false, G_INF); else if (gm == G_SCALAR) SSN_TRIALS_G(false, G_SCALAR); else SSN_TRIALS_G(false, G_VECTOR); }
+    }
+#undef SSN_TRIALS_G
+#undef SSN_TRIALS_NT
+    SSN_LAUNCH(c, trials_finish_kernel, 1, 256, 0, scalpart.p, nblocks, NTk, n2_scratch.p);
+    SSN_CUDA(cudaMemcpyAsync(n2_out_dev, n2_scratch.p, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// Armijo backtracking of Class1/APD_SsN_Class1.m:182-211, kMaxTrials trial steps per read of w:
+//   lk_new = lk_old + delta^ll*zeta ; cF_new = bk1/2*||lk_new||^2 - wlk'*lk_new + tk/2*||prox(z)||^2 ;
+//   accept the first ll with  !(cF_new > cF_old - nu*delta^ll*ress)  or  ll == ll_max.
+void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk,
+                     const double* p, const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama,
+                     double gama_s, double nu, double delta, int ll_max, double cF_old, double ress, int batch,
+                     double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out) {
+    SSN_REQUIRE(lam_old && zeta && wlk && lam_new && ll_max >= 0, SSN_E_INVALID, "linesearch: bad arguments");
+    if (batch < 1) batch = 1;
+    if (batch > kMaxTrials) batch = kMaxTrials;
+    const int64_t N = m + n;
+    const int nb = 64;
+    Buf<double> lamT(c, (size_t)batch * N), alpha(c, batch), f0part(c, (size_t)nb * batch * 2), res(c, 3 * (size_t)batch);
+    int ll = 0, passes = 0;
+    while (true) {
+        // most steps accept the full step (ll = 0): the first read of w evaluates that trial alone,
+        // every later read evaluates `batch` backtracking steps at once
+        const int nt = std::min(passes == 0 ? 1 : batch, ll_max - ll + 1);
+        double al[kMaxTrials];
+        for (int t = 0; t < nt; ++t) al[t] = std::pow(delta, (double)(ll + t));
+        for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = al[t];
+        SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
+        SSN_LAUNCH(c, trial_vectors_kernel, nb, 256, 0, N, nt, lam_old, zeta, wlk, alpha.p, lamT.p, f0part.p);
+        SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, res.p + batch);
+        plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p);
+        double h[3 * kMaxTrials];
+        read_back(c, res.p, h, 3 * (size_t)batch);
+        ++passes;
+        int acc = -1;
+        double n2a = 0.0, cFa = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const double f0 = bk1 / 2 * h[batch + 2 * t] - h[batch + 2 * t + 1];
+            const double cF_new = f0 + 0.5 * tk * h[t];
+            if (!(cF_new > cF_old - nu * al[t] * ress) || ll + t == ll_max) { acc = t; n2a = h[t]; cFa = cF_new; break; }
+        }
+        if (acc >= 0) {
+            ll += acc;
+            SSN_CUDA(cudaMemcpyAsync(lam_new, lamT.p + (size_t)acc * N, sizeof(double) * N, cudaMemcpyDeviceToDevice, c->stream));
+            if (n2_out) *n2_out = n2a;
+            if (cF_out) *cF_out = cFa;
+            break;
+        }
+        ll += nt;
+    }
+    if (ll_out) *ll_out = ll;
+    if (passes_out) *passes_out = passes;
 }
 
 // Y = sparse(reshape(s,m,n)) as two sorted coordinate lists (ASAt.m:15):

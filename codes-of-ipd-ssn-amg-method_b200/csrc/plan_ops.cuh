@@ -8,6 +8,13 @@ void plan_aty(ssn_ctx* c, const double* y, const double* p, const double* q, int
 void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q,
                         int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* axp_out,
                         double* prox_out, double* z_out, uint8_t* s_out, double* scal2_dev);
+// batched line-search trials and the Armijo loop built on them (plan_ops.cu)
+void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q,
+                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev);
+void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk,
+                     const double* p, const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama,
+                     double gama_s, double nu, double delta, int ll_max, double cF_old, double ress, int batch,
+                     double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out);
 int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
                         Buf<int>& ycol, Buf<int>& rowcount);
 }  // namespace ssn

@@ -359,23 +359,111 @@ __global__ void spgemm_split_kernel(int nrowsB, const int* __restrict__ bp, cons
     split[t] = (w == 0) ? b0 : (w == nwin ? b1 : lower_bound_dev(bi, b0, b1, w * W));
 }
 
-// upper bound of the number of entries of every work item (output row, column window)
+constexpr int kSmallT = 256;          // rows with at most this many products (and A entries) take the warp path
+
+// Upper bound of the number of entries of every segment (output row, column window), and the
+// classification of the rows: a row with <= kSmallT products is SMALL (one warp, whole row in
+// segment 0); the segments of the other rows are appended to big_list for the windowed kernel.
 __global__ void spgemm_ub_kernel(int nrows, const int* __restrict__ ap, const int* __restrict__ ai,
                                  const int* __restrict__ bp, const int* __restrict__ split, int W, int nwin, int ncolsB,
-                                 int* __restrict__ ub) {
+                                 int small_ok, int* __restrict__ ub, int* __restrict__ big_list, int* __restrict__ nbig) {
     const int lane = threadIdx.x & 31;
     const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (item >= (int64_t)nrows * nwin) return;
     const int row = (int)(item / nwin), win = (int)(item % nwin);
-    long long s = 0;
-    for (int e = ap[row] + lane; e < ap[row + 1]; e += 32) {
+    long long s = 0, tot = 0;
+    const int a0 = ap[row], a1 = ap[row + 1];
+    for (int e = a0 + lane; e < a1; e += 32) {
         const int k = ai[e];
-        s += split ? (split[(size_t)k * (nwin + 1) + win + 1] - split[(size_t)k * (nwin + 1) + win]) : (bp[k + 1] - bp[k]);
+        const int full = bp[k + 1] - bp[k];
+        tot += full;
+        s += split ? (split[(size_t)k * (nwin + 1) + win + 1] - split[(size_t)k * (nwin + 1) + win]) : full;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+    if (lane != 0) return;
+    if (small_ok && (a1 - a0) <= kSmallT && tot <= kSmallT) { ub[item] = (win == 0) ? (int)tot : 0; return; }
     const int wcols = (win == nwin - 1) ? (ncolsB - win * W) : W;
-    if (lane == 0) ub[item] = (s < (long long)wcols) ? (int)s : wcols;
+    ub[item] = (s < (long long)wcols) ? (int)s : wcols;
+    big_list[atomicAdd(nbig, 1)] = (int)item;
+}
+
+// SMALL rows: one warp per output row.  The <= kSmallT products of the row are formed in
+// Gustavson order t = 0,1,... (k ascending, then B's column order), rank-sorted by (column, t) in
+// shared memory and summed sequentially inside every column segment -- the same additions in the
+// same order as the dense-accumulator kernel, without its per-row latency chain.
+__global__ void __launch_bounds__(128) spgemm_small_kernel(
+    int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
+    const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, int nwin,
+    const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval, int* __restrict__ cnt_out) {
+    __shared__ int s_offs[4][kSmallT + 1];
+    __shared__ int s_b0[4][kSmallT];
+    __shared__ double s_a[4][kSmallT];
+    __shared__ unsigned s_key[4][kSmallT];
+    __shared__ double s_val[4][kSmallT];
+    __shared__ unsigned s_skey[4][kSmallT];
+    __shared__ double s_sval[4][kSmallT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int row = blockIdx.x * 4 + w; row < nrows; row += gridDim.x * 4) {
+        const int a0 = ap[row], a1 = ap[row + 1], lenA = a1 - a0;
+        if (lenA == 0 || lenA > kSmallT) continue;
+        int running = 0;
+        for (int base = 0; base < lenA; base += 32) {
+            const int e = a0 + base + lane;
+            int len = 0;
+            if (e < a1) {
+                const int k = ai[e];
+                const int b0 = bp[k];
+                len = bp[k + 1] - b0;
+                s_b0[w][base + lane] = b0; s_a[w][base + lane] = av[e];
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (e < a1) s_offs[w][base + lane] = running + incl - len;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const int T = running;
+        if (T > kSmallT) continue;                          // a big row: the windowed kernel owns it
+        if (lane == 0) s_offs[w][lenA] = T;
+        __syncwarp();
+        for (int t = lane; t < T; t += 32) {
+            int jl = 0, jh = lenA;                          // last j with offs[j] <= t
+            while (jl < jh) { const int mid = (jl + jh) >> 1; if (s_offs[w][mid] <= t) jl = mid + 1; else jh = mid; }
+            const int j = jl - 1;
+            const int src = s_b0[w][j] + (t - s_offs[w][j]);
+            s_key[w][t] = ((unsigned)bi[src] << 8) | (unsigned)t;
+            s_val[w][t] = __dmul_rn(s_a[w][j], bv[src]);
+        }
+        __syncwarp();
+        for (int t = lane; t < T; t += 32) {                // rank sort (keys are distinct)
+            const unsigned key = s_key[w][t];
+            int r = 0;
+            for (int u = 0; u < T; ++u) r += (s_key[w][u] < key) ? 1 : 0;
+            s_skey[w][r] = key; s_sval[w][r] = s_val[w][t];
+        }
+        __syncwarp();
+        const int out0 = ubptr[(size_t)row * nwin];
+        int written = 0;
+        for (int base = 0; base < T; base += 32) {
+            const int i = base + lane;
+            bool keep = false; double acc = 0.0; int col = 0;
+            if (i < T) {
+                col = (int)(s_skey[w][i] >> 8);
+                const bool head = (i == 0) || ((int)(s_skey[w][i - 1] >> 8) != col);
+                if (head) {
+                    acc = __dadd_rn(0.0, s_sval[w][i]);
+                    for (int j = i + 1; j < T && (int)(s_skey[w][j] >> 8) == col; ++j) acc = __dadd_rn(acc, s_sval[w][j]);
+                    keep = (acc != 0.0);
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, keep);
+            if (keep) { const int pos = out0 + written + __popc(ball & ((1u << lane) - 1u)); tidx[pos] = col; tval[pos] = acc; }
+            written += __popc(ball);
+        }
+        if (lane == 0) cnt_out[(size_t)row * nwin] = written;
+        __syncwarp();
+    }
 }
 
 // One block per work item = (output row, window of W output columns), handed out through an
@@ -392,7 +480,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) spgemm_nume
     int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
     const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, const int* __restrict__ split,
     int ncolsB, int W, int nwin, const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval,
-    int* __restrict__ cnt_out, int* __restrict__ item_counter) {
+    int* __restrict__ cnt_out, int* __restrict__ item_counter, const int* __restrict__ big_list,
+    const int* __restrict__ nbig) {
     extern __shared__ unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);
     double* s_prod = acc + W;
@@ -409,13 +498,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) spgemm_nume
     __shared__ int s_warp[NW], s_warp2[NW];
     __shared__ int s_total, s_groups, s_item;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nitems = nrows * nwin;
+    const int nitems = *nbig;
 
     while (true) {
-        if (tid == 0) s_item = atomicAdd(item_counter, 1);
+        if (tid == 0) { const int q = atomicAdd(item_counter, 1); s_item = (q < nitems) ? big_list[q] : -1; }
         __syncthreads();
         const int item = s_item;
-        if (item >= nitems) break;
+        if (item < 0) break;
         const int row = item / nwin, win = item - row * nwin;
         const int w0 = win * W;
         const int wcols = (ncolsB - w0 < W) ? (ncolsB - w0) : W;
@@ -593,7 +682,11 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     }
     const int* splitp = nwin > 1 ? split.p : nullptr;
     Buf<int> ub(c, nitems), ubptr(c, (size_t)nitems + 1), cnt(c, nitems), cptr(c, (size_t)nitems + 1);
-    SSN_LAUNCH(c, spgemm_ub_kernel, cdiv(nitems * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, splitp, W, nwin, ncolsB, ub.p);
+    Buf<int> big_list(c, nitems), counters(c, 2);          // counters[0] = number of big items, [1] = work-item cursor
+    counters.zero(); cnt.zero();
+    const int small_ok = (ncolsB < (1 << 23)) ? 1 : 0;     // (column << 8 | t) must fit 32 bits
+    SSN_LAUNCH(c, spgemm_ub_kernel, cdiv(nitems * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, splitp, W, nwin, ncolsB, small_ok,
+               ub.p, big_list.p, counters.p);
     if ((int64_t)nrows * (int64_t)ncolsB >= ((int64_t)1 << 31)) {      // the int32 scan could wrap: check in 64 bit
         Buf<unsigned long long> tot(c, 1); tot.zero();
         SSN_LAUNCH(c, sum_int64_kernel, 64, 256, 0, ub.p, nitems, tot.p);
@@ -602,7 +695,10 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     }
     const int64_t ub_total = scan_counts_to_ptr(c, ub, ubptr, nitems);
     Buf<int> tidx(c, (size_t)ub_total); Buf<double> tval(c, (size_t)ub_total);
-    Buf<int> counter(c, 1); counter.zero();
+    if (small_ok) {
+        int grid = cdiv(nrows, 4); if (grid > c->num_sms * 16) grid = c->num_sms * 16;
+        SSN_LAUNCH(c, spgemm_small_kernel, grid, 128, 0, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, nwin, ubptr.p, tidx.p, tval.p, cnt.p);
+    }
     if (W > 2048) {
         constexpr int CAP = 2560;
         const size_t smem = (size_t)W * sizeof(double) + (size_t)CAP * (sizeof(double) + sizeof(int));
@@ -611,7 +707,7 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
         const int per_sm = (smem + 16 * 1024 <= 110 * 1024) ? 2 : 1;
         int64_t grid = (int64_t)c->num_sms * per_sm; if (grid > nitems) grid = nitems;
         SSN_LAUNCH(c, kern, (int)grid, 512, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, splitp, ncolsB, W, nwin,
-                   ubptr.p, tidx.p, tval.p, cnt.p, counter.p);
+                   ubptr.p, tidx.p, tval.p, cnt.p, counters.p + 1, big_list.p, counters.p);
     } else {
         constexpr int CAP = 1024;
         const size_t smem = (size_t)W * sizeof(double) + (size_t)CAP * (sizeof(double) + sizeof(int));
@@ -621,7 +717,7 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
         per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
         int64_t grid = (int64_t)c->num_sms * per_sm; if (grid > nitems) grid = nitems;
         SSN_LAUNCH(c, kern, (int)grid, 128, smem, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, splitp, ncolsB, W, nwin,
-                   ubptr.p, tidx.p, tval.p, cnt.p, counter.p);
+                   ubptr.p, tidx.p, tval.p, cnt.p, counters.p + 1, big_list.p, counters.p);
     }
     C.nnz = scan_counts_to_ptr(c, cnt, cptr, nitems);
     C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);

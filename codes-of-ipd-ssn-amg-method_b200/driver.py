@@ -95,7 +95,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
     kx0, kl0 = kkt(xk, lk)
     fxk = [float(c @ xk)]; KKT_xk = [kx0]; KKT_lk = [kl0]
     stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm,
-             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0}
+             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0, "ls_passes": 0}
     t_loop = time.time()
     rr = [np.inf]
     k = 0
@@ -136,16 +136,9 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             f0 = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old)  # :182
             cFk_old = f0 + 0.5 * tk * n2_old
             ress = abs(float(Fk_old @ zeta))
-            ll = 0
-            while True:                                                 # :189-211
-                lk_new = lk_old + delta ** ll * zeta
-                f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
-                n2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=())["norm2"]
-                cFk_new = f0 + 0.5 * tk * n2
-                if not (cFk_new > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
-                    break
-                ll += 1
-            stats["ls_trials"] += ll + 1
+            # :189-211, ll = 0 alone, then eight backtracking steps per read of wk (api.linesearch)
+            lk_new, ll, _, _, passes = api.linesearch(wk, lk_old, zeta, wlk, p, q, tk, bk1, cFk_old, ress, gam, nu, delta, ll_max)
+            stats["ls_trials"] += ll + 1; stats["ls_passes"] += passes
             ev = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))
             Fk_new = bk1 * lk_new - ev["Axprox"] - wlk                  # :212
             nFo = float(torch.linalg.norm(Fk_old)); nF = float(torch.linalg.norm(Fk_new))
@@ -203,17 +196,11 @@ def ssn_step(state, amg_options=None, max_ll=500):
     f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
     cFk_old = f0 + 0.5 * tk * ev["norm2"]
     ress = abs(float(Fk_old @ zeta))
-    ll = 0
-    while True:                                                                  # :189-211
-        lk_new = lk + delta ** ll * zeta
-        f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
-        n2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=())["norm2"]
-        if not (f0 + 0.5 * tk * n2 > cFk_old - nu * delta ** ll * ress) or ll == max_ll:
-            break
-        ll += 1
-    ev2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))     # :212
+    # :189-211, ll = 0 alone, then eight backtracking steps per read of wk
+    lk_new, ll, _, _, passes = api.linesearch(wk, lk, zeta, wlk, p, q, tk, bk1, cFk_old, ress, gam, nu, delta, max_ll)
+    ev2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox",))         # :212
     Fk_new = bk1 * lk_new - ev2["Axprox"] - wlk
-    return lk_new, Fk_new, {"E": ev["count"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll,
+    return lk_new, Fk_new, {"E": ev["count"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
                             "nnzH": H0.nnz, "Fk_old_norm": float(torch.linalg.norm(Fk_old)),
                             "Fk_new_norm": float(torch.linalg.norm(Fk_new))}
 

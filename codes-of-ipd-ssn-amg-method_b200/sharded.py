@@ -1,0 +1,176 @@
+"""Row-sharded SsN step: one process per GPU, the m x n plan split by rows.
+
+Rank g owns rows ``[g*m/G, (g+1)*m/G)`` of every plan-sized vector as a local column-major
+``m_loc x n`` slab.  ``Aty``, prox and the active set are slab-local; the q-weighted row sums are
+owner-local and all-gathered (m doubles in total); the p-weighted column sums need the path's one
+real exchange, an NCCL ``all_reduce`` of n doubles in which the squared norm and the active count
+ride along; the compacted active set crosses NVLink as O(E) global linear indices; the
+(m+n)-sized AMG hierarchy is replicated (deterministic, so every rank computes the same zeta and
+no broadcast is needed).
+
+The collectives go through ``torch.distributed`` (NCCL on the GPUs, gloo in the CPU tests); the
+plan operators come from ``ops`` -- the CUDA operators of ``api.py`` by default.  The tests pass an
+adapter over the CPU oracle instead, which exercises exactly this host logic without a GPU.
+"""
+import numpy as np
+
+
+def row_range(rank, world, m):
+    return (rank * m) // world, ((rank + 1) * m) // world
+
+
+def shard_plan_vector(x, m, n, r0, r1):
+    """Rows [r0, r1) of a column-major m x n plan vector as a column-major slab."""
+    return x.reshape(n, m)[:, r0:r1].contiguous().reshape(-1)
+
+
+class _CudaOps:
+    """The product operators (api.py) under the names the sharded step uses."""
+
+    def __init__(self):
+        from . import api
+        self.api = api
+
+    def prox_residual(self, w, lam, p, q, tk, gama, want):
+        return self.api.prox_residual(w, lam, p, q, tk, gama, want=want)
+
+    def prox_trials(self, w, lamT, p, q, tk, gama):
+        return self.api.prox_trials(w, lamT, p, q, tk, gama)
+
+    def active_lin(self, s, m_loc, n, r0, m):
+        return self.api.active_coo(s, m_loc, n, r0, m)
+
+    def asat_from_lin(self, lin_sorted, p, q):
+        return self.api.ASAt_coo(lin_sorted, p, q)
+
+    def hybrid_amg(self, prob_data, opts):
+        return self.api.Hybrid_AMG(prob_data, opts)
+
+    def rng_reset(self):
+        self.api.rng_reset()
+
+
+class ShardedStep:
+    """One semismooth-Newton step (Class1/APD_SsN_Class1.m:137-212) on a row-sharded plan."""
+
+    def __init__(self, state, rank, world, ops=None, dist=None, amg_options=None, already_sharded=False):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.ops = ops if ops is not None else _CudaOps()
+        if dist is None:
+            import torch.distributed as dist
+        self.dist = dist
+        p, q = state["p"], state["q"]
+        self.m, self.n = m, n = p.numel(), q.numel()
+        self.r0, self.r1 = r0, r1 = row_range(rank, world, m)
+        self.m_loc = r1 - r0
+        self.p, self.q = p, q
+        self.p_loc = p[r0:r1].contiguous()
+        self.w_loc = state["wk"] if already_sharded else shard_plan_vector(state["wk"], m, n, r0, r1)
+        self.lk, self.wlk = state["lk"], state["wlk"]
+        self.bk1, self.tk, self.gama = state["bk1"], state["tk"], state.get("gama", float("inf"))
+        if amg_options is None:
+            from .driver import CLASS1_AMG_OPTIONS as amg_options
+        self.amg_options = amg_options
+        self.counts = [row_range(g, world, m)[1] - row_range(g, world, m)[0] for g in range(world)]
+        self.collectives = 0
+
+    # ---- slab-local view of a dual vector [column part (n) ; row part (m)]
+    def _lam_loc(self, lam):
+        return self.torch.cat([lam[: self.n], lam[self.n + self.r0: self.n + self.r1]])
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t)
+            self.collectives += 1
+        return t
+
+    def _all_gather_rows(self, rows_loc):
+        if self.world == 1:
+            return rows_loc
+        torch = self.torch
+        mx = max(self.counts)
+        pad = torch.zeros(mx, dtype=rows_loc.dtype, device=rows_loc.device)
+        pad[: self.m_loc] = rows_loc
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad)
+        self.collectives += 1
+        return torch.cat([o[:c] for o, c in zip(out, self.counts)])
+
+    def _all_gather_var(self, v):
+        """all-gather of int64 vectors of different lengths (sizes first, then padded payloads)."""
+        if self.world == 1:
+            return v
+        torch = self.torch
+        sz = torch.tensor([v.numel()], dtype=torch.int64, device=v.device)
+        sizes = [torch.empty_like(sz) for _ in range(self.world)]
+        self.dist.all_gather(sizes, sz)
+        sizes = [int(s.item()) for s in sizes]
+        mx = max(max(sizes), 1)
+        pad = torch.zeros(mx, dtype=v.dtype, device=v.device)
+        pad[: v.numel()] = v
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad)
+        self.collectives += 2
+        return torch.cat([o[:c] for o, c in zip(out, sizes)])
+
+    def residual(self, lam, want_s):
+        """Ax(prox(z)) (global, n+m), ||prox(z)||^2, nnz(s) and the local slab of s for z=(w-A'lam)/tk."""
+        torch = self.torch
+        want = ("Axprox", "s") if want_s else ("Axprox",)
+        ev = self.ops.prox_residual(self.w_loc, self._lam_loc(lam), self.p_loc, self.q, self.tk, self.gama, want)
+        ax = ev["Axprox"]
+        buf = torch.cat([ax[: self.n], torch.tensor([ev["norm2"], float(ev["count"])], dtype=ax.dtype, device=ax.device)])
+        self._all_reduce(buf)                                    # the path's one O(n) collective
+        rows = self._all_gather_rows(ax[self.n:])
+        return torch.cat([buf[: self.n], rows]), float(buf[self.n]), int(round(float(buf[self.n + 1]))), ev.get("s")
+
+    def norms2(self, lams):
+        """||prox(z(lam_t))||^2 of a batch of trial vectors: one read of the slab, one all_reduce."""
+        torch = self.torch
+        lt = torch.stack([self._lam_loc(l) for l in lams])
+        part = self.ops.prox_trials(self.w_loc, lt, self.p_loc, self.q, self.tk, self.gama)
+        return [float(v) for v in self._all_reduce(part.clone())]
+
+    def assemble(self, s_loc):
+        """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged."""
+        lin = self.ops.active_lin(s_loc, self.m_loc, self.n, self.r0, self.m)
+        lin_all = self._all_gather_var(lin)
+        if self.world > 1:
+            lin_all = self.torch.sort(lin_all)[0]                # global column-major order == find(s)
+        return self.ops.asat_from_lin(lin_all, self.p, self.q)
+
+    def __call__(self):
+        torch = self.torch
+        bk1, tk, lk, wlk = self.bk1, self.tk, self.lk, self.wlk
+        nu, delta, max_ll = 0.2, 0.9, 500
+        self.ops.rng_reset()
+        Axp, n2_old, E, s_loc = self.residual(lk, True)                              # :139-144
+        Fk_old = bk1 * lk - Axp - wlk
+        H0 = self.assemble(s_loc)                                                    # :142
+        prob_data = {"bk1": bk1, "tk": tk, "q": self.q, "p": self.p, "T": None, "H0": H0, "z": -Fk_old}
+        zeta, itamg, resamg, info = self.ops.hybrid_amg(prob_data, self.amg_options)  # :161 (replicated)
+        f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
+        cFk_old = f0 + 0.5 * tk * n2_old
+        ress = abs(float(Fk_old @ zeta))
+        ll, batch, done, passes = 0, 8, False, 0
+        while not done:                                                              # :189-211, ll = 0 alone, then 8 per pass
+            lls = list(range(ll, min(ll + (1 if passes == 0 else batch), max_ll + 1)))
+            lams = [lk + delta ** t * zeta for t in lls]
+            n2s = self.norms2(lams); passes += 1
+            for t, lam_t, n2 in zip(lls, lams, n2s):
+                f0 = bk1 / 2 * float(lam_t @ lam_t) - float(wlk @ lam_t)
+                if not (f0 + 0.5 * tk * n2 > cFk_old - nu * delta ** t * ress) or t == max_ll:
+                    ll, lk_new, done = t, lam_t, True
+                    break
+            else:
+                ll = lls[-1] + 1
+        Axp2, _, _, _ = self.residual(lk_new, False)                                 # :212
+        Fk_new = bk1 * lk_new - Axp2 - wlk
+        return lk_new, Fk_new, {"E": E, "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
+                                "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives}
+
+
+def make_sharded_step(state, rank, world, **kw):
+    return ShardedStep(state, rank, world, **kw)

@@ -122,6 +122,12 @@ SSN_API int64_t ssn_launch_count(ssn_ctx *ctx);
  * stream synchronised on both sides; ssn_profile_dump returns a text table and resets it. */
 SSN_API int  ssn_profile_enable(ssn_ctx *ctx, int on);
 SSN_API const char *ssn_profile_dump(ssn_ctx *ctx);
+/* CUDA-event timer around the launches of the plan-wide kernels (the fused residual kernel and the
+ * batched line-search kernel), on the launching stream: ssn_kernel_timer(ctx, 1) switches it on and
+ * resets it, ssn_kernel_timer_read returns the accumulated milliseconds and the number of launches.
+ * Each timed launch is synchronised, so leave it off outside measurements (bench.py's roofline). */
+SSN_API int  ssn_kernel_timer(ssn_ctx *ctx, int on);
+SSN_API int  ssn_kernel_timer_read(ssn_ctx *ctx, double *total_ms, int64_t *launches);
 /* Solver tuning knobs (also read from the environment at ssn_create: SSN_DENSE_TAIL, SSN_DENSE_MAXN):
  * dense_tail != 0 collapses the tail of small AMG levels (N <= dense_max_n) into dense cycle
  * operators (one matvec per visit); 0 walks them step by step.  dense_max_n <= 0 keeps the value. */
@@ -176,6 +182,25 @@ SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *l
                       double tk, const double *gama_dev, double gama_scalar,
                       double *axp_out_dev, double *prox_out_dev, double *z_out_dev,
                       uint8_t *s_out_dev, double *norm2_out, int64_t *count_out);
+
+/* Batched line-search trials: n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 for the nt <= 8
+ * trial dual vectors lamT_dev[t*(n+m) .. ] in ONE read of w (Class1/APD_SsN_Class1.m:193-207
+ * evaluates one trial per Aty + prox + norm pass).  Per-entry arithmetic as ssn_prox_residual. */
+SSN_API int ssn_prox_trials(ssn_ctx *ctx, const double *w_dev, const double *lamT_dev, int nt,
+                    const double *p_dev, const double *q_dev, int64_t m, int64_t n, double tk,
+                    const double *gama_dev, double gama_scalar, double *n2_out_dev);
+
+/* The Armijo backtracking of Class1/APD_SsN_Class1.m:182-211 (Class2 :170-200 with its own cF):
+ *   lk_new = lk_old + delta^ll*zeta;  cF_new = bk1/2*||lk_new||^2 - wlk'*lk_new + tk/2*||prox(z)||^2;
+ *   the first ll with !(cF_new > cF_old - nu*delta^ll*ress), or ll == ll_max, is accepted.
+ * The first read of w evaluates ll = 0 alone (most steps accept it); every later read evaluates
+ * `batch` (1..8) backtracking steps at once.  Outputs: lam_new_dev (n+m), *ll_out,
+ * *norm2_out = ||prox(z(lk_new))||^2, *cF_out, *passes_out = number of reads of w. */
+SSN_API int ssn_linesearch(ssn_ctx *ctx, const double *w_dev, const double *lam_old_dev, const double *zeta_dev,
+                   const double *wlk_dev, const double *p_dev, const double *q_dev, int64_t m, int64_t n,
+                   double tk, double bk1, const double *gama_dev, double gama_scalar, double nu, double delta,
+                   int ll_max, double cF_old, double ress, int batch, double *lam_new_dev, int *ll_out,
+                   double *norm2_out, double *cF_out, int *passes_out);
 
 /* H = ASAt(s,p,q) -- ASAt.m:14-19.  s: logical m*n (1 byte per entry).  H is
  * (n+m) x (n+m), column nodes first, explicit zeros dropped. */

@@ -190,3 +190,45 @@ def test_full_size_properties_64x64_grid(gpu):
     assert abs(H - H.T).max() == 0
     rowsum = np.asarray(H.sum(axis=1)).reshape(-1)
     assert np.array_equal(rowsum, 2 * H.diagonal())   # unit weights: diag = degree, off-diag ones
+
+
+@pytest.mark.parametrize("m,n", [(7, 5), (250, 130), (1027, 517), (2048, 300)])
+@pytest.mark.parametrize("gama", [np.inf, 0.4])
+def test_prox_trials_equal_single_trial_kernel(gpu, m, n, gama):
+    """The batched line-search kernel (up to 8 trial vectors per read of w) against the fused
+    single-trial residual kernel: same per-entry arithmetic, same reduction order => same bits."""
+    rs = np.random.RandomState(m + 3 * n)
+    w = rs.standard_normal(m * n); p, q = weights(m, n, 3, False)
+    for nt in (1, 2, 3, 4, 5, 7, 8):
+        lamT = 0.3 * rs.standard_normal((nt, n + m))
+        got = gpu.prox_trials(w, lamT, p, q, 0.8, gama).cpu().numpy()
+        ref = np.array([gpu.prox_residual(w, lamT[t], p, q, 0.8, gama, want=())["norm2"] for t in range(nt)])
+        assert np.array_equal(got, ref), (nt, got, ref)
+
+
+def test_linesearch_matches_trial_by_trial_loop(gpu, oracle):
+    """ssn_linesearch (ll = 0 alone, then 8 trials per pass) against the reference's trial-by-trial Armijo loop
+    (Class1/APD_SsN_Class1.m:182-211) evaluated with the oracle."""
+    m, n = 300, 260
+    rs = np.random.RandomState(9)
+    p, q = np.ones(m), np.ones(n)
+    w = rs.standard_normal(m * n) - 0.5; lam = 0.2 * rs.standard_normal(n + m); wlk = rs.standard_normal(n + m)
+    tk, bk1, nu, delta = 0.7, 0.3, 0.2, 0.9
+    prox = lambda z: np.maximum(z, 0.0)
+    cF = lambda l: bk1 / 2 * (l @ l) - wlk @ l + 0.5 * tk * np.sum(prox((w - oracle.Aty(l, p, q)) / tk) ** 2)
+    z0 = (w - oracle.Aty(lam, p, q)) / tk
+    grad = bk1 * lam - wlk - oracle.Ax(prox(z0), p, q)               # gradient of cF at lam
+    for scale, ll_max in ((0.5, 500), (50.0, 500), (2000.0, 500), (-30.0, 7)):
+        zeta = -scale * grad                                         # descent direction (ascent for scale < 0)
+        cF_old = cF(lam); ress = abs(float(grad @ zeta))
+        ll = 0
+        while True:
+            lk_new = lam + delta ** ll * zeta
+            if not (cF(lk_new) > cF_old - nu * delta ** ll * ress) or ll == ll_max:
+                break
+            ll += 1
+        out, ll_dev, n2, cF_new, passes = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max)
+        assert ll_dev == ll, (scale, ll_dev, ll)
+        assert passes == 1 + (ll + 7) // 8
+        assert np.array_equal(out.cpu().numpy(), lk_new)
+        assert abs(cF_new - cF(lk_new)) <= 1e-10 * max(1.0, abs(cF_new))

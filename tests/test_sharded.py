@@ -1,0 +1,132 @@
+"""Host logic of the row-sharded SsN step (codes-of-ipd-ssn-amg-method_b200/sharded.py) on CPU:
+two gloo ranks, the plan operators supplied by an adapter over the oracle.  The sharded step must
+reproduce the unsharded one: same active set / ASAt, same AMG cycle count, same line-search
+length, iterates equal to rounding (the column-sum reduction order changes with the world size)."""
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+AMG_OPTS = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1,
+            "inter": 1, "guess": None}
+
+
+class OracleOps:
+    """The oracle behind the operator names ShardedStep uses (tests only)."""
+
+    def __init__(self):
+        import oracle
+        self.o = oracle
+
+    @staticmethod
+    def _np(t):
+        return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+    def prox_residual(self, w, lam, p, q, tk, gama, want):
+        w, lam, p, q = (self._np(v) for v in (w, lam, p, q))
+        z = 1 / tk * (w - self.o.Aty(lam, p, q))
+        s = (z >= 0) & (z <= gama)
+        px = np.minimum(np.maximum(z, 0.0), gama)
+        out = {"norm2": float(px @ px), "count": int(s.sum())}
+        if "Axprox" in want:
+            out["Axprox"] = torch.from_numpy(self.o.Ax(px, p, q))
+        if "s" in want:
+            out["s"] = torch.from_numpy(s.astype(np.uint8))
+        return out
+
+    def prox_trials(self, w, lamT, p, q, tk, gama):
+        return torch.tensor([self.prox_residual(w, l, p, q, tk, gama, ())["norm2"] for l in lamT], dtype=torch.float64)
+
+    def active_lin(self, s, m_loc, n, r0, m):
+        S = self._np(s).reshape(n, m_loc)                 # column-major slab: S[j, i]
+        j, i = np.nonzero(S)                              # slab CSC order
+        return torch.from_numpy((i + r0 + j * m).astype(np.int64))
+
+    def asat_from_lin(self, lin_sorted, p, q):
+        p, q = self._np(p), self._np(q)
+        s = np.zeros(p.size * q.size, dtype=bool)
+        s[self._np(lin_sorted)] = True
+        return self.o.ASAt(s, p, q)
+
+    def hybrid_amg(self, pd, opts):
+        N = pd["p"].numel() + pd["q"].numel()
+        d = {"bk1": pd["bk1"], "tk": pd["tk"], "p": self._np(pd["p"]), "q": self._np(pd["q"]),
+             "T": sp.diags(np.zeros(N)), "H0": pd["H0"], "z": self._np(pd["z"])}
+        zeta, it, res, info = self.o.Hybrid_AMG(d, opts)
+        return torch.from_numpy(np.asarray(zeta)), it, res, info
+
+    def rng_reset(self):
+        self.o.rng_reset()
+
+
+def make_state(m, n, seed):
+    rs = np.random.RandomState(seed)
+    c = rs.random_sample(m * n)
+    w = -c + 0.9 * rs.random_sample(m * n)
+    lam = 0.3 * rs.standard_normal(m + n)
+    wlk = rs.standard_normal(m + n)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return {"wk": t(w), "lk": t(lam), "wlk": t(wlk), "p": t(np.ones(m)), "q": t(np.ones(n)), "bk1": 0.25, "tk": 0.7,
+            "gama": float("inf")}
+
+
+def _worker(rank, world, port, m, n, seed, outdir):
+    import importlib
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+    step = sharded.make_sharded_step(make_state(m, n, seed), rank, world, ops=OracleOps(), dist=dist, amg_options=AMG_OPTS)
+    lk_new, Fk_new, info = step()
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), lk=lk_new.numpy(), Fk=Fk_new.numpy(), E=info["E"], it=info["itamg"],
+             ll=info["ll"], nnzH=info["nnzH"], coll=info["collectives"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("m,n", [(24, 20), (37, 30)])
+def test_sharded_step_matches_unsharded_gloo(m, n):
+    import importlib
+    import torch.multiprocessing as mp
+    sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+    seed = 11
+    ref = sharded.make_sharded_step(make_state(m, n, seed), 0, 1, ops=OracleOps(), dist=None, amg_options=AMG_OPTS)
+    lk_ref, Fk_ref, info_ref = ref()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(2, _free_port(), m, n, seed, d), nprocs=2, join=True)
+        outs = [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(2)]
+    for o in outs:
+        assert int(o["E"]) == info_ref["E"] and int(o["nnzH"]) == info_ref["nnzH"]
+        assert int(o["it"]) == info_ref["itamg"] and int(o["ll"]) == info_ref["ll"]
+        assert np.allclose(o["lk"], lk_ref.numpy(), rtol=1e-9, atol=1e-12)
+        assert np.allclose(o["Fk"], Fk_ref.numpy(), rtol=1e-8, atol=1e-10)
+        assert int(o["coll"]) > 0
+    assert np.array_equal(outs[0]["lk"], outs[1]["lk"])          # replicated AMG: identical on every rank
+
+
+def test_row_ranges_and_slab_layout():
+    import importlib
+    sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+    m, n, world = 13, 5, 4
+    X = np.arange(m * n, dtype=np.float64).reshape(n, m).T           # X[i, j] = i + j*m (column-major vec)
+    x = torch.from_numpy(np.ascontiguousarray(X.reshape(-1, order="F")))
+    covered = []
+    for r in range(world):
+        r0, r1 = sharded.row_range(r, world, m)
+        covered += list(range(r0, r1))
+        slab = sharded.shard_plan_vector(x, m, n, r0, r1).numpy()
+        assert np.array_equal(slab.reshape(n, r1 - r0).T, X[r0:r1, :])
+    assert covered == list(range(m))
