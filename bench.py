@@ -251,6 +251,9 @@ def main():
                 "traffic": None, "frac_of_8TBps_nominal": ach / 8000.0}
     r_k3 = roof("plan_reduce_kernel<PROX> (fused SsN residual: z, prox, Ax(prox), ||prox||^2; one read of wk)", k3_ms, 2)
     r_tr = roof("plan_trials_kernel<NT=8> (8 Armijo trials per read of wk: z, prox, ||prox||^2 each)", tr_ms, max(passes - 1, 0))
+    r_tr["note"] = ("reads wk once for 8 trials, so its limiter is the fp64 pipe (8 trials x 5 fp64 ops per entry, unit weights), "
+                    "not HBM: ncu shows sm__pipe_fp64_cycles_active 64 %, issue slots 72 % (profiles/trials_full_r1.csv); "
+                    "per trial it moves 1/8 of the bytes of the one-trial-per-pass reference scheme")
     if world == 1:
         r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials")
     dominant, other = (r_tr, r_k3) if r_tr["share_of_step"] >= r_k3["share_of_step"] else (r_k3, r_tr)

@@ -266,7 +266,7 @@ struct TrialArgs {
     int64_t m, n, ldl;      // ldl = n + m
     int cols_per_chunk;
     double* scalpart;       // [num_blocks][NT]
-    const int* unitw;       // device flag: p == 1 and q == 1 everywhere
+    const int* nonunit;     // device flag: some p_i or q_j differs from 1 (null: assume so)
     int nt_valid;           // trial slots >= nt_valid repeat the last valid trial vector (NT is 1, 2, 4 or 8)
 };
 
@@ -410,18 +410,17 @@ __device__ __forceinline__ void trials_body(const TrialArgs& a, double* dsm) {
 template <bool VEC, int GM, int NT>
 __global__ void __launch_bounds__(kThreads, 2) plan_trials_kernel(const TrialArgs a) {
     extern __shared__ __align__(16) double trials_dsm[];
-    if (a.unitw != nullptr && *a.unitw != 0) trials_body<VEC, GM, NT, true>(a, trials_dsm);
+    if (a.nonunit != nullptr && *a.nonunit == 0) trials_body<VEC, GM, NT, true>(a, trials_dsm);
     else                                     trials_body<VEC, GM, NT, false>(a, trials_dsm);
 }
 
-// flag[0] = 1 iff every p_i and q_j equals 1.0 (one block)
+// nonunit[0] |= 1 if some p_i or q_j differs from 1.0 (nonunit is zeroed by the caller)
 __global__ void __launch_bounds__(256) unit_weights_kernel(const double* __restrict__ p, int64_t m, const double* __restrict__ q,
-                                                           int64_t n, int* __restrict__ flag) {
-    int ok = 1;
-    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) ok &= (p[i] == 1.0);
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) ok &= (q[i] == 1.0);
-    ok = __syncthreads_and(ok);
-    if (threadIdx.x == 0) flag[0] = ok;
+                                                           int64_t n, int* __restrict__ nonunit) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m + n; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= ((i < m ? p[i] : q[i - m]) != 1.0) ? 1 : 0;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nonunit, 1);
 }
 
 // out[t] = sum_b scalpart[b][t]  (fixed order)
@@ -649,8 +648,16 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
 }
 
 // n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 for t < nt (nt <= kMaxTrials), one read of w
+// flag_dev[0] = 1 iff some weight differs from 1 (decides the fp64-lean path of the trials kernel)
+const int* plan_nonunit_flag(ssn_ctx* c, const double* p, const double* q, int64_t m, int64_t n, int* flag_dev) {
+    SSN_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int), c->stream));
+    SSN_LAUNCH(c, unit_weights_kernel, std::min(64, cdiv(m + n, 256)), 256, 0, p, m, q, n, flag_dev);
+    return flag_dev;
+}
+
 void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q,
-                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev) {
+                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev,
+                      const int* nonunit_dev) {
     SSN_REQUIRE(m > 0 && n > 0 && w && lamT && p && q && n2_out_dev, SSN_E_INVALID, "prox_trials: bad arguments");
     SSN_REQUIRE(nt >= 1 && nt <= kMaxTrials, SSN_E_INVALID, "prox_trials: 1 <= nt <= 8");
     Buf<double> n2_scratch(c, kMaxTrials);
@@ -658,10 +665,10 @@ void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, c
     const Tiling t = plan_tiling(c, m, n);
     const int nblocks = t.chunks * t.groups;
     Buf<double> scalpart(c, (size_t)NTk * nblocks);
-    Buf<int> unitw(c, 1);
-    SSN_LAUNCH(c, unit_weights_kernel, 1, 256, 0, p, m, q, n, unitw.p);
+    Buf<int> flag;
+    if (!nonunit_dev) { flag.alloc(c, 1); nonunit_dev = plan_nonunit_flag(c, p, q, m, n, flag.p); }
     TrialArgs a{};
-    a.unitw = unitw.p; a.nt_valid = nt;
+    a.nonunit = nonunit_dev; a.nt_valid = nt;
     a.w = w; a.p = p; a.q = q; a.lamT = lamT; a.gama = gama; a.gama_s = gama_s; a.inv_tk = 1.0 / tk;
     a.m = m; a.n = n; a.ldl = n + m; a.cols_per_chunk = t.cpc; a.scalpart = scalpart.p;
     const dim3 grid(t.chunks, t.groups);
@@ -697,6 +704,8 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
     const int64_t N = m + n;
     const int nb = 64;
     Buf<double> lamT(c, (size_t)batch * N), alpha(c, batch), f0part(c, (size_t)nb * batch * 2), res(c, 3 * (size_t)batch);
+    Buf<int> flag(c, 1);
+    const int* nonunit = plan_nonunit_flag(c, p, q, m, n, flag.p);          // once per line search
     int ll = 0, passes = 0;
     while (true) {
         // most steps accept the full step (ll = 0): the first read of w evaluates that trial alone,
@@ -708,7 +717,7 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
         SSN_LAUNCH(c, trial_vectors_kernel, nb, 256, 0, N, nt, lam_old, zeta, wlk, alpha.p, lamT.p, f0part.p);
         SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, res.p + batch);
-        plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p);
+        plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p, nonunit);
         double h[3 * kMaxTrials];
         read_back(c, res.p, h, 3 * (size_t)batch);
         ++passes;

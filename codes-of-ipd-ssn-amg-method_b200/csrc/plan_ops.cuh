@@ -10,7 +10,8 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
                         double* prox_out, double* z_out, uint8_t* s_out, double* scal2_dev);
 // batched line-search trials and the Armijo loop built on them (plan_ops.cu)
 void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q,
-                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev);
+                      int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev,
+                      const int* nonunit_dev = nullptr);
 void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk,
                      const double* p, const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama,
                      double gama_s, double nu, double delta, int ll_max, double cF_old, double ress, int batch,
