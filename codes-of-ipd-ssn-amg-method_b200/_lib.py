@@ -60,6 +60,8 @@ SIGNATURES = {
     "ssn_launch_count": (_i64, [_vp]),
     "ssn_profile_enable": (_int, [_vp, _int]),
     "ssn_set_dense_tail": (_int, [_vp, _int, _int]),
+    "ssn_set_persistent": (_int, [_vp, _int]),
+    "ssn_debug_barrier_bench": (_int, [_vp, _int, _int, _pdbl]),
     "ssn_kernel_timer": (_int, [_vp, _int]),
     "ssn_kernel_timer_read": (_int, [_vp, _pdbl, _pi64]),
     "ssn_profile_dump": (C.c_char_p, [_vp]),
@@ -82,6 +84,7 @@ SIGNATURES = {
     "ssn_prox_residual": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _vp, _vp, _vp,
                                  _pdbl, _pi64]),
     "ssn_prox_trials": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp]),
+    "ssn_trial_vectors": (_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp]),
     "ssn_linesearch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _int, _dbl, _dbl,
                               _int, _vp, C.POINTER(_int), _pdbl, _pdbl, C.POINTER(_int)]),
     "ssn_asat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),

@@ -255,6 +255,18 @@ def prox_trials(w, lamT, p, q, tk, gama=np.inf):
     return out
 
 
+def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
+    """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 8) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
+    as device tensors -- the O(m+n) half of a batch of Armijo trials."""
+    torch = _torch(); ctx = context()
+    ld, zd, wd = _dev(lam), _dev(zeta), _dev(wlk)
+    N = ld.numel()
+    lamT = torch.empty((int(nt), N), dtype=torch.float64, device="cuda")
+    f0 = torch.empty(2 * int(nt), dtype=torch.float64, device="cuda")
+    ctx.call("ssn_trial_vectors", _ptr(ld), _ptr(zd), _ptr(wd), N, float(delta), int(ll0), int(nt), _ptr(lamT), _ptr(f0))
+    return lamT, f0
+
+
 def linesearch(w, lam_old, zeta, wlk, p, q, tk, bk1, cF_old, ress, gama=np.inf, nu=0.2, delta=0.9, ll_max=500, batch=8):
     """Armijo backtracking of Class1/APD_SsN_Class1.m:182-211 with ``batch`` backtracking steps per read of
     ``w`` (the full step ll = 0 is tried alone first).  Returns ``(lk_new, ll, norm2, cF_new, passes)``."""
@@ -563,6 +575,11 @@ def kernel_timer_read():
     ctx = context(); ms = C.c_double(0.0); cnt = C.c_int64(0)
     ctx.call("ssn_kernel_timer_read", C.byref(ms), C.byref(cnt))
     return ms.value, cnt.value
+
+
+def set_persistent(enable=True):
+    """Class_AMG's solve loop as one persistent cooperative kernel (default) or kernel by kernel."""
+    ctx = context(); ctx.call("ssn_set_persistent", 1 if enable else 0)
 
 
 def set_dense_tail(enable=True, max_n=0):

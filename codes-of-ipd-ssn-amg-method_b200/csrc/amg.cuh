@@ -17,6 +17,7 @@ struct LevelDev {
     double xx;            // ones'*A*ones
     double* r; double* e; double* g;                   // work vectors
     double* pcg;                                       // 5*N scratch (small levels)
+    const double* B;                                   // dense cycle operator (tail levels), else null
 };
 
 struct Level {
@@ -51,6 +52,7 @@ struct Hierarchy {
     ClusterPlan cluster_plan{};
     size_t cluster_smem = 0;
     Buf<LevelDev> dev;
+    std::vector<LevelDev> hdev;    // host copy of dev
     Buf<double> part;              // reduction partials (multi-block kernels)
     Buf<double> scal;              // small device scalars
 };
@@ -85,6 +87,7 @@ void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_opti
                double* res_out, double* resk_host);
 
 void debug_cycles(unsigned long long* out64, bool reset);
+double barrier_bench(ssn_ctx* c, int iters, int which);
 void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
 
 // ---- dispatch (solvers.cu)

@@ -192,6 +192,11 @@ constexpr int kBT = 4;                                    // lanes per row insid
 // cycle counters of the single-block kernel (development aid; read through ssn_debug_cycles)
 __device__ unsigned long long g_dbg_cycles[64];
 #define DBG_T0() const long long dbg_t0 = clock64()
+#ifdef SSN_PERSIST_DEBUG
+#define PDBG(slot, call) do { const long long t0__ = clock64(); call; if (blockIdx.x == 0 && threadIdx.x == 0) { g_dbg_cycles[(slot)] += (unsigned long long)(clock64() - t0__); g_dbg_cycles[32 + (slot)] += 1ull; } } while (0)
+#else
+#define PDBG(slot, call) do { call; } while (0)
+#endif
 #define DBG_ADD(slot) do { if (threadIdx.x == 0) { g_dbg_cycles[(slot)] += (unsigned long long)(clock64() - dbg_t0); g_dbg_cycles[32 + (slot)] += 1ull; } } while (0)
 
 // block-wide sum with ONE barrier: warp partials go to the buffer selected by `flip`, which the
@@ -449,6 +454,10 @@ __global__ void __launch_bounds__(kCycleThreads) coarse_cycle_kernel(const Level
 constexpr int kDT = 1024;                                 // threads of the build kernel
 constexpr int kDTW = kDT / 32;
 
+// row stride (in doubles) of the [row][column] multi-vector layout in shared memory: C + 1 keeps the
+// gathers x[idx[e]][c] of a warp spread over the banks (a stride of C = 8 doubles maps them onto 2)
+template <int C> struct MV { static constexpr int S = (C == 1) ? 1 : C + 1; };
+
 template <int C>
 __device__ __forceinline__ void block_sumC(double (&v)[C], double* red, int& flip) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -477,12 +486,12 @@ __device__ __forceinline__ void row_dot_multi(const int* __restrict__ ptr, const
         for (; e + kBT < e1; e += 2 * kBT) {
             const int j0 = idx[e], j1 = idx[e + kBT];
             const double a0 = val[e], a1 = val[e + kBT];
-            const double* x0 = x + (size_t)j0 * C; const double* x1 = x + (size_t)j1 * C;
+            const double* x0 = x + (size_t)j0 * MV<C>::S; const double* x1 = x + (size_t)j1 * MV<C>::S;
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = fma(a1, x1[c], fma(a0, x0[c], acc[c]));
         }
         if (e < e1) {
-            const int j0 = idx[e]; const double a0 = val[e]; const double* x0 = x + (size_t)j0 * C;
+            const int j0 = idx[e]; const double a0 = val[e]; const double* x0 = x + (size_t)j0 * MV<C>::S;
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = fma(a0, x0[c], acc[c]);
         }
@@ -505,7 +514,7 @@ __device__ void spmm_smem(int nrows, const int* ptr, const int* idx, const doubl
         if (valid && sub == 0) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                double* yy = y + (size_t)row * C + c;
+                double* yy = y + (size_t)row * MV<C>::S + c;
                 *yy = (mode == 0) ? acc[c] : (mode == 1 ? *yy + acc[c] : *yy - acc[c]);
             }
         }
@@ -524,7 +533,7 @@ __device__ void dense_smem(int n, const double* __restrict__ B, const double* x,
         const double* Br = B + (size_t)row * n;
         for (int j = lane; j < n; j += 32) {
             const double b = Br[j];
-            const double* xj = x + (size_t)j * C;
+            const double* xj = x + (size_t)j * MV<C>::S;
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[c] = fma(b, xj[c], acc[c]);
         }
@@ -532,7 +541,7 @@ __device__ void dense_smem(int n, const double* __restrict__ B, const double* x,
         for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
         if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) { double* yy = y + (size_t)row * C + c; *yy = add ? (*yy + acc[c]) : acc[c]; }
+            for (int c = 0; c < C; ++c) { double* yy = y + (size_t)row * MV<C>::S + c; *yy = add ? (*yy + acc[c]) : acc[c]; }
         }
     }
     __syncthreads();
@@ -545,7 +554,7 @@ __device__ double* smooth_multi(const LevelDev& L, int col0, double* ecur, doubl
                                 const double (&sum_r)[C], double* red, int& flip) {
     const int sub = threadIdx.x % kBT;
     if (steps == 0) {
-        if (e_zero) { for (int i = threadIdx.x; i < L.N * C; i += kDT) ecur[i] = 0.0; __syncthreads(); }
+        if (e_zero) { for (int i = threadIdx.x; i < L.N * MV<C>::S; i += kDT) ecur[i] = 0.0; __syncthreads(); }
         return ecur;
     }
     double dotAe[C];
@@ -555,7 +564,7 @@ __device__ double* smooth_multi(const LevelDev& L, int col0, double* ecur, doubl
         for (int i = threadIdx.x; i < L.N; i += kDT) {
             const double axi = L.Axi[i];
 #pragma unroll
-            for (int c = 0; c < C; ++c) dotAe[c] = fma(axi, ecur[(size_t)i * C + c], dotAe[c]);
+            for (int c = 0; c < C; ++c) dotAe[c] = fma(axi, ecur[(size_t)i * MV<C>::S + c], dotAe[c]);
         }
         block_sumC<C>(dotAe, red, flip);
     }
@@ -578,8 +587,8 @@ __device__ double* smooth_multi(const LevelDev& L, int col0, double* ecur, doubl
                 for (int c = 0; c < C; ++c) {
                     const double ri = (row == col0 + c) ? 1.0 : 0.0;
                     const double gi = ri - d[c];
-                    const double en = (e_zero ? 0.0 : ecur[(size_t)row * C + c]) + coef[c] + di * (gi - axi * coef[c]);
-                    ealt[(size_t)row * C + c] = en;
+                    const double en = (e_zero ? 0.0 : ecur[(size_t)row * MV<C>::S + c]) + coef[c] + di * (gi - axi * coef[c]);
+                    ealt[(size_t)row * MV<C>::S + c] = en;
                     part[c] = fma(axi, en, part[c]);
                 }
             }
@@ -600,8 +609,9 @@ __global__ void __launch_bounds__(kDT) dense_build_kernel(LevelDev L, LevelDev L
     extern __shared__ __align__(16) double dsm_d[];
     __shared__ double red[2 * C * 32];
     const int N = L.N, Nc = Lc.N;
-    double* e0 = dsm_d; double* e1 = e0 + (size_t)N * C; double* g = e1 + (size_t)N * C;
-    double* rc = g + (size_t)N * C; double* ec = rc + (size_t)Nc * C; double* dc = ec + (size_t)Nc * C;
+    constexpr int CS = MV<C>::S;
+    double* e0 = dsm_d; double* e1 = e0 + (size_t)N * CS; double* g = e1 + (size_t)N * CS;
+    double* rc = g + (size_t)N * CS; double* ec = rc + (size_t)Nc * CS; double* dc = ec + (size_t)Nc * CS;
     const int col0 = blockIdx.x * C;
     int flip = 0;
     double sum_r[C];
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(kDT) dense_build_kernel(LevelDev L, LevelDev L
             row_dot_multi<C>(L.ap, L.ai, L.av, ecur, row, sub, valid, d);
             if (valid && sub == 0) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) g[(size_t)row * C + c] = ((row == col0 + c) ? 1.0 : 0.0) - d[c];
+                for (int c = 0; c < C; ++c) g[(size_t)row * MV<C>::S + c] = ((row == col0 + c) ? 1.0 : 0.0) - d[c];
             }
         }
         __syncthreads();
@@ -626,7 +636,7 @@ __global__ void __launch_bounds__(kDT) dense_build_kernel(LevelDev L, LevelDev L
     spmm_smem<C>(Nc, Lc.tp, Lc.ti, Lc.tv, g, rc, 0);                                          // rc = Pro' g
     dense_smem<C>(Nc, Bc, rc, ec, false);                                                     // :28
     if (twice) {                                                                              // :30
-        for (int i = threadIdx.x; i < Nc * C; i += kDT) dc[i] = rc[i];
+        for (int i = threadIdx.x; i < Nc * CS; i += kDT) dc[i] = rc[i];
         __syncthreads();
         spmm_smem<C>(Nc, Lc.ap, Lc.ai, Lc.av, ec, dc, 2);                                     // dc = rc - A_c ec
         dense_smem<C>(Nc, Bc, dc, ec, true);
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(kDT) dense_build_kernel(LevelDev L, LevelDev L
     ecur = smooth_multi<C>(L, col0, ecur, ealt, false, smoth, isnsp, sum_r, red, flip);       // :34-42
     for (int i = threadIdx.x; i < N * C; i += kDT) {
         const int row = i / C, c = i % C;
-        if (col0 + c < N) B[(size_t)row * N + col0 + c] = ecur[i];
+        if (col0 + c < N) B[(size_t)row * N + col0 + c] = ecur[(size_t)row * CS + c];
     }
 }
 
@@ -1045,6 +1055,398 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs a) {
     if (gtid == 0) { *a.it_out = it; a.scal_out[0] = delta_new; a.scal_out[1] = delta_0; }
 }
 
+// ------------------------------------------------------------------ persistent solve kernel
+//
+// Class_AMG's whole solve loop (Class_AMG.m:89-107: r = b - A*x, x += cycle(r), stop on the
+// relative residual / divergence guard) as ONE cooperative kernel: every dependent step of the
+// cycle on the large levels (fused Jacobi step, block Gauss-Seidel residual + coupled update,
+// restriction, prolongation, dense tail operator) is a grid-wide pass followed by a grid barrier
+// (~1-2 us) instead of a kernel launch (~5 us of launch + ramp + tail), reductions ride on the
+// same barrier, and the convergence test runs on the device.  Vectors that change during the
+// kernel are read with ld.global.cg (L2), never through the non-coherent path.
+
+constexpr int kPT = 256;
+constexpr int kPBlocksPerSM = 2;
+constexpr int kPLevels = 16;
+
+struct PersistArgs {
+    const LevelDev* levels; int J, kd, smoth, isnsp, wcycle;
+    const double* b; double* x; double retol; int maxit;
+    double* part;                 // [2][2*gridDim.x]
+    double* relk; double* rho;    // maxit + 2 entries each
+    int* it_out;                  // [0] = it, [1] = history length
+    int tpr[kPLevels];            // lanes per row of A_k (k < kd)
+    int tpr_p[kPLevels];          // lanes per row of Pro_k / Pro_k' (k <= kd)
+    size_t smem_budget;           // dynamic shared memory available for staged matrix slices
+};
+
+// A block's contiguous slice of rows of one CSR matrix: either staged in shared memory (row
+// pointers rebased to the slice) or read in place from global memory.
+struct PSlice {
+    int r0, r1, rbase; const int* rp; const int* ci; const double* cv;
+    int inter;     // 1: rows interleaved over the whole grid (in-place matrices only); 0: the block's contiguous slice
+    __device__ __forceinline__ int first(int rows_per_pass) const { return inter ? (int)blockIdx.x * rows_per_pass : r0; }
+    __device__ __forceinline__ int step(int rows_per_pass) const { return inter ? (int)gridDim.x * rows_per_pass : rows_per_pass; }
+};
+struct PLevelS { PSlice A, Pu, Td; };      // A_t ; Pro_{t+1} (rows of level t) ; Pro_t' (rows of level t)
+
+__device__ void stage_slice(PSlice* S, int N, const int* ptr, const int* idx, const double* val, unsigned char* smem,
+                            size_t& used, size_t budget) {
+    const int rpb = (N + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int r0 = min(N, (int)blockIdx.x * rpb), r1 = min(N, r0 + rpb);
+    const int nrows = r1 - r0;
+    const int base = (ptr && nrows > 0) ? ptr[r0] : 0;
+    const int cnt = (ptr && nrows > 0) ? (ptr[r1] - base) : 0;
+    const size_t bv = ((size_t)cnt * 8 + 15) / 16 * 16, bi = ((size_t)cnt * 4 + 15) / 16 * 16, bp = ((size_t)(nrows + 1) * 4 + 15) / 16 * 16;
+    const bool fits = ptr != nullptr && nrows > 0 && used + bv + bi + bp <= budget;
+    if (fits) {
+        double* sv = reinterpret_cast<double*>(smem + used);
+        int* si = reinterpret_cast<int*>(smem + used + bv);
+        int* sp = reinterpret_cast<int*>(smem + used + bv + bi);
+        for (int i = threadIdx.x; i <= nrows; i += kPT) sp[i] = ptr[r0 + i] - base;
+        for (int e = threadIdx.x; e < cnt; e += kPT) { sv[e] = val[base + e]; si[e] = idx[base + e]; }
+        if (threadIdx.x == 0) { S->r0 = r0; S->r1 = r1; S->rbase = r0; S->rp = sp; S->ci = si; S->cv = sv; S->inter = 0; }
+        used += bv + bi + bp;
+    } else if (threadIdx.x == 0) {
+        const int inter = (budget == 0) ? 1 : 0;             // no staging at all: spread the rows over the grid
+        S->r0 = inter ? 0 : r0; S->r1 = inter ? N : r1; S->rbase = 0; S->rp = ptr; S->ci = idx; S->cv = val; S->inter = inter;
+    }
+}
+
+template <int TPR>
+__device__ __forceinline__ double row_dot_s(const PSlice& S, const double* x, int row, int sub, bool valid) {
+    double s = 0.0;
+    if (valid) {
+        const int e1 = S.rp[row - S.rbase + 1];
+        int e = S.rp[row - S.rbase] + sub;
+        const int* ci = S.ci; const double* cv = S.cv;
+        for (; e + 3 * TPR < e1; e += 4 * TPR) {
+            const int i0 = ci[e], i1 = ci[e + TPR], i2 = ci[e + 2 * TPR], i3 = ci[e + 3 * TPR];
+            const double v0 = cv[e], v1 = cv[e + TPR], v2 = cv[e + 2 * TPR], v3 = cv[e + 3 * TPR];
+            const double x0 = __ldcg(x + i0), x1 = __ldcg(x + i1), x2 = __ldcg(x + i2), x3 = __ldcg(x + i3);
+            s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
+        }
+        for (; e < e1; e += TPR) s = fma(cv[e], __ldcg(x + ci[e]), s);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+template <class F>
+__device__ __forceinline__ void with_tpr(int tpr, F&& f) {
+    switch (tpr) {
+        case 2: f(std::integral_constant<int, 2>()); break;
+        case 4: f(std::integral_constant<int, 4>()); break;
+        case 8: f(std::integral_constant<int, 8>()); break;
+        case 16: f(std::integral_constant<int, 16>()); break;
+        default: f(std::integral_constant<int, 32>()); break;
+    }
+}
+
+// Grid-wide barrier for the persistent kernel (one block per SM, all resident: cooperative launch).
+// bar[0] = arrival counter, bar[32] = generation (separate 128-byte lines so that the pollers do not
+// slow the arrivals down).  Same guarantees as cg::grid_group::sync() -- every global write made
+// before the barrier is visible to every thread after it -- at roughly half the latency.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned* gen = bar + 32;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 32, 1u);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPT, kPBlocksPerSM) barrier_bench_kernel(unsigned* bar, int iters, int which, long long* cycles_out) {
+    cg::grid_group grid = cg::this_grid();
+    grid.sync();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) { if (which == 0) grid.sync(); else grid_barrier(bar, gridDim.x); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cycles_out[0] = clock64() - t0;
+}
+
+struct PGrid {
+    cg::grid_group grid; double* part; double* red; int flip;
+    // grid-wide sums of two per-thread values; one grid barrier; results identical in every thread
+    __device__ __forceinline__ void sum2(double& a, double& b) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        a = warp_sum(a); b = warp_sum(b);
+        double* sm = red + (flip & 1) * 64;
+        if (lane == 0) { sm[w] = a; sm[32 + w] = b; }
+        __syncthreads();
+        double* p = part + (size_t)(flip & 1) * 2 * gridDim.x;
+        if (w == 0) {
+            double ta = (lane < kPT / 32) ? sm[lane] : 0.0, tb = (lane < kPT / 32) ? sm[32 + lane] : 0.0;
+            ta = warp_sum(ta); tb = warp_sum(tb);
+            if (lane == 0) { p[2 * blockIdx.x] = ta; p[2 * blockIdx.x + 1] = tb; }
+        }
+        grid.sync();
+        {   // every warp fetches its share of the block partials at once (one L2 round trip), fixed order
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += kPT) { s0 += __ldcg(p + 2 * i); s1 += __ldcg(p + 2 * i + 1); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (lane == 0) { sm[w] = s0; sm[32 + w] = s1; }
+        }
+        __syncthreads();
+        {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < kPT / 32; ++i) { s0 += sm[i]; s1 += sm[32 + i]; }
+            a = s0; b = s1;
+        }
+        ++flip;
+    }
+};
+
+// g = r - A e on the block's rows (e == nullptr: g = r); sum g and sum g^2 when want (else just the barrier)
+__device__ void p_resid(PGrid& G, const PSlice& S, int tpr, const double* r, const double* e, double* g, bool want,
+                        double& sg, double& sg2) {
+    sg = 0.0; sg2 = 0.0;
+    with_tpr(tpr, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        const int sub = threadIdx.x % TPR;
+        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
+            const int row = base + threadIdx.x / TPR;
+            const bool valid = row < S.r1;
+            double ri = 0.0;
+            if (valid && sub == 0) ri = __ldcg(r + row);
+            double d = 0.0;
+            if (e != nullptr) d = row_dot_s<TPR>(S, e, row, sub, valid);
+            if (valid && sub == 0) { const double gi = ri - d; g[row] = gi; sg += gi; sg2 = fma(gi, gi, sg2); }
+        }
+    });
+    if (want) G.sum2(sg, sg2); else G.grid.sync();
+}
+
+// block Gauss-Seidel coupled update (Class_AMG.m:56-59 / MG_Wcycle.m:19,37): e (+)= coef + R(g - Axi*coef)
+__device__ void p_gs_apply(PGrid& G, const LevelDev& L, const PSlice& S, int tpr, const double* g, double* e, double coef, int post,
+                           bool e_zero) {
+    with_tpr(tpr, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        const int sub = threadIdx.x % TPR;
+        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
+            const int row = base + threadIdx.x / TPR;
+            const bool valid = row < S.r1;
+            double hi = 0.0, di = 0.0;
+            if (valid) { hi = __ldcg(g + row) - L.Axi[row] * coef; di = L.dinv[row]; }
+            double s = 0.0;
+            const bool coupled = valid && (post ? (row < L.Nf) : (row >= L.Nf));
+            if (coupled) {
+                const int e1 = S.rp[row - S.rbase + 1];
+                for (int q = S.rp[row - S.rbase] + sub; q < e1; q += TPR) {
+                    const int j = S.ci[q];
+                    const bool other = post ? (j >= L.Nf) : (j < L.Nf);
+                    if (other) s = fma(S.cv[q], L.dinv[j] * (__ldcg(g + j) - L.Axi[j] * coef), s);
+                }
+            }
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const double inc = coef + di * (hi - s);
+            if (valid && sub == 0) e[row] = e_zero ? inc : (__ldcg(e + row) + inc);
+        }
+    });
+    G.grid.sync();
+}
+
+// one fused damped-Jacobi step (kernel correction through coef); returns Axi'ealt
+__device__ double p_jacobi(PGrid& G, const LevelDev& L, const PSlice& S, int tpr, const double* r, const double* ecur, double* ealt,
+                           double coef, bool e_zero) {
+    double part = 0.0, dummy = 0.0;
+    with_tpr(tpr, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        const int sub = threadIdx.x % TPR;
+        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
+            const int row = base + threadIdx.x / TPR;
+            const bool valid = row < S.r1;
+            // own-row operands first, so that their L2 latency overlaps the gathers of the row product
+            double axi = 0.0, di = 0.0, ri = 0.0, ei = 0.0;
+            if (valid && sub == 0) { axi = L.Axi[row]; di = L.dinv[row]; ri = __ldcg(r + row); ei = e_zero ? 0.0 : __ldcg(ecur + row); }
+            double d = 0.0;
+            if (!e_zero) d = row_dot_s<TPR>(S, ecur, row, sub, valid);
+            if (valid && sub == 0) {
+                const double gi = ri - d;
+                const double en = ei + coef + di * (gi - axi * coef);
+                ealt[row] = en;
+                part = fma(axi, en, part);
+            }
+        }
+    });
+    G.sum2(part, dummy);
+    return part;
+}
+
+// y (+)= M x on the block's rows of M; returns sum(y) and wvec'y (wvec optional)
+__device__ void p_spmv(PGrid& G, const PSlice& S, int tpr, const double* x, double* y, bool add, const double* wvec,
+                       double& sy, double& swy) {
+    sy = 0.0; swy = 0.0;
+    with_tpr(tpr, [&](auto T) {
+        constexpr int TPR = decltype(T)::value;
+        const int sub = threadIdx.x % TPR;
+        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
+            const int row = base + threadIdx.x / TPR;
+            const bool valid = row < S.r1;
+            double yi = 0.0, wi = 0.0;
+            if (valid && sub == 0) { if (add) yi = __ldcg(y + row); if (wvec) wi = wvec[row]; }
+            const double d = row_dot_s<TPR>(S, x, row, sub, valid);
+            if (valid && sub == 0) {
+                const double v = yi + d;
+                y[row] = v; sy += v;
+                swy = fma(wi, v, swy);
+            }
+        }
+    });
+    G.sum2(sy, swy);
+}
+
+// y (+)= B x, dense row-major n x n (n <= 2048), one warp per row, all loads of a row in flight at once
+__device__ void p_dense(PGrid& G, int n, const double* __restrict__ B, const double* x, double* y, bool add) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * kPT + threadIdx.x) >> 5, nw = gridDim.x * (kPT / 32);
+    for (int row = gw; row < n; row += nw) {
+        const double* Br = B + (size_t)row * n;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j0 = 0; j0 < n; j0 += 256) {
+            double bv[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int j = j0 + u * 32 + lane; bv[u] = (j < n) ? Br[j] : 0.0; xv[u] = (j < n) ? __ldcg(x + j) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u & 3] = fma(bv[u], xv[u], acc[u & 3]);
+        }
+        const double s = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        if (lane == 0) y[row] = add ? (__ldcg(y + row) + s) : s;
+    }
+    G.grid.sync();
+}
+
+__global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char p_dsm[];
+    __shared__ double red[128];
+    __shared__ LevelDev sl[kPLevels];
+    __shared__ PLevelS ps[kPLevels];
+    PGrid G{cg::this_grid(), a.part, red, 0};
+    const int kd = a.kd;                                   // levels 0..kd-1 explicit, level kd = dense leaf
+    for (int t = threadIdx.x; t <= kd && t < kPLevels; t += kPT) sl[t] = a.levels[t];
+    __syncthreads();
+    // ---- stage this block's row slices of the level matrices (most visited levels first)
+    {
+        size_t used = 0;
+        for (int t = kd; t >= 0; --t) {
+            const LevelDev& L = sl[t];
+            if (t < kd) stage_slice(&ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, a.smem_budget);
+            else        stage_slice(&ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, 0);              // leaf: residual only, in place
+            if (t < kd) stage_slice(&ps[t].Pu, L.N, sl[t + 1].pp, sl[t + 1].pi, sl[t + 1].pv, p_dsm, used, a.smem_budget);
+            if (t >= 1) stage_slice(&ps[t].Td, L.N, L.tp, L.ti, L.tv, p_dsm, used, a.smem_budget);
+        }
+        __syncthreads();
+    }
+    const bool lead = (blockIdx.x == 0 && threadIdx.x == 0);
+    int phase[kPLevels]; bool zero[kPLevels]; double* ecur[kPLevels]; double* ealt[kPLevels];
+    double sum_r[kPLevels], dot_e[kPLevels];
+    for (int t = 0; t < kPLevels; ++t) { phase[t] = 0; zero[t] = true; ecur[t] = nullptr; ealt[t] = nullptr; sum_r[t] = 0.0; dot_e[t] = 0.0; }
+    const long long t_kernel0 = clock64();
+    const int tpr0 = kd > 0 ? a.tpr[0] : 32;
+
+    // r = b - A*x ; res0 = norm(r)                                      Class_AMG.m:89
+    double s1, s2;
+    PDBG(25, p_resid(G, ps[0].A, tpr0, a.b, a.x, sl[0].r, true, s1, s2));
+    const double res0 = sqrt(s2);
+    sum_r[0] = s1;
+    double res_prev = res0, rel_prev = 1.0, rel_res = 0.0;
+    int it = 0, hist = 1;
+    if (lead) { a.relk[0] = 1.0; a.rho[0] = NAN; }
+    if (res0 == 0.0) {
+        if (lead) { a.relk[0] = 0.0; a.rho[0] = INFINITY; a.it_out[0] = 0; a.it_out[1] = 1; a.it_out[2] = 0; }
+        return;
+    }
+    it = 1;
+    while (rel_prev > a.retol && it <= a.maxit) {                       // Class_AMG.m:95
+        // ---------------- one cycle on level 0: rhs sl[0].r -> ecur[0]
+        for (int t = 0; t <= kd; ++t) { ecur[t] = sl[t].e; ealt[t] = sl[t].pcg; }
+        int k = 0;
+        phase[0] = 0; zero[0] = true;
+        while (true) {
+            const LevelDev& L = sl[k];
+            const PLevelS& P = ps[k];
+            if (k == kd) {                                              // dense tail operator
+                if (zero[k]) PDBG(29, p_dense(G, L.N, L.B, L.r, L.e, false));
+                else { double d1, d2; PDBG(25, p_resid(G, P.A, 32, L.r, L.e, L.g, false, d1, d2)); PDBG(29, p_dense(G, L.N, L.B, L.g, L.e, true)); }
+                ecur[k] = L.e;
+                if (k == 0) break;
+                --k; continue;
+            }
+            const int tpr = a.tpr[k];
+            if (phase[k] == 0 || phase[k] == 3) {                       // pre- (0) or post-smoothing (3)
+                const int post = (phase[k] == 3) ? 1 : 0;
+                bool ez = (phase[k] == 0) ? zero[k] : false;
+                if (a.smoth == 0 && ez) {
+                    for (int i = P.A.first(kPT) + threadIdx.x; i < P.A.r1; i += P.A.step(kPT)) ecur[k][i] = 0.0;
+                    G.grid.sync();
+                }
+                if (L.bigph) {
+                    for (int s = 0; s < a.smoth; ++s) {
+                        double sg, sg2;
+                        PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ecur[k], L.g, a.isnsp != 0, sg, sg2));
+                        const double coef = a.isnsp ? sg / L.xx : 0.0;
+                        PDBG(26, p_gs_apply(G, L, P.A, tpr, L.g, ecur[k], coef, post, ez));
+                        ez = false;
+                    }
+                } else {
+                    double dotAe = ez ? 0.0 : dot_e[k];
+                    for (int s = 0; s < a.smoth; ++s) {
+                        const double coef = a.isnsp ? (sum_r[k] - dotAe) / L.xx : 0.0;
+                        PDBG(27, dotAe = p_jacobi(G, L, P.A, tpr, L.r, ecur[k], ealt[k], coef, ez));
+                        double* t = ecur[k]; ecur[k] = ealt[k]; ealt[k] = t;
+                        ez = false;
+                    }
+                    dot_e[k] = dotAe;
+                }
+                if (post) {                                             // this level's visit is complete
+                    if (k == 0) break;
+                    --k; continue;
+                }
+                // restriction: r_{k+1} = Pro' (r - A e)                  MG_Wcycle.m:26
+                double d1, d2;
+                PDBG(25, p_resid(G, P.A, tpr, L.r, (ez ? nullptr : ecur[k]), L.g, false, d1, d2));
+                PDBG(28, p_spmv(G, ps[k + 1].Td, a.tpr_p[k + 1], L.g, sl[k + 1].r, false, nullptr, d1, d2));
+                sum_r[k + 1] = d1;
+                phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ++k; continue;
+            }
+            if (phase[k] == 1 && a.wcycle && (k + 1 != a.J - 1)) {      // second coarse visit   :30
+                phase[k] = 2; phase[k + 1] = 0; zero[k + 1] = false; ++k; continue;
+            }
+            {   // prolongation e += Pro e_{k+1}, with Axi'e for the post-smoother        :32
+                double d1, d2;
+                PDBG(28, p_spmv(G, P.Pu, a.tpr_p[k + 1], ecur[k + 1], ecur[k], true, L.Axi, d1, d2));
+                dot_e[k] = d2;
+                phase[k] = 3; continue;
+            }
+        }
+        // ---------------- x += e ; r = b - A*x ; res = norm(r)          Class_AMG.m:96-104
+        for (int i = ps[0].A.first(kPT) + threadIdx.x; i < ps[0].A.r1; i += ps[0].A.step(kPT)) a.x[i] = __ldcg(a.x + i) + __ldcg(ecur[0] + i);
+        G.grid.sync();
+        PDBG(25, p_resid(G, ps[0].A, tpr0, a.b, a.x, sl[0].r, true, s1, s2));
+        sum_r[0] = s1;
+        const double res = sqrt(s2);
+        rel_res = res / res0;
+        const double rho = res / res_prev;
+        if (lead) { a.relk[it] = rel_res; a.rho[it] = rho; }
+        res_prev = res; rel_prev = rel_res;
+        ++it; ++hist;
+        if (rho > 1.0) break;                                           // Class_AMG.m:106
+    }
+    if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; a.it_out[2] = 0; g_dbg_cycles[31] += (unsigned long long)(clock64() - t_kernel0); g_dbg_cycles[63] += 1ull; }
+    (void)rel_res;
+}
+
 template <class F>
 void dispatch_tpr(double avg, F&& f) {
     if (avg <= 3.0) f(std::integral_constant<int, 2>());
@@ -1090,7 +1492,7 @@ LevelDev level_dev(const Level& L) {
     d.pp = L.P.ptr.p; d.pi = L.P.idx.p; d.pv = L.P.val.p;
     d.tp = L.Pt.ptr.p; d.ti = L.Pt.idx.p; d.tv = L.Pt.val.p;
     d.dinv = L.dinv.p; d.Axi = L.Axi.p; d.xx = L.xx;
-    d.r = L.r.p; d.e = L.e.p; d.g = L.g.p; d.pcg = L.pcg.p;
+    d.r = L.r.p; d.e = L.e.p; d.g = L.g.p; d.pcg = L.pcg.p; d.B = L.B.p;
     return d;
 }
 
@@ -1173,7 +1575,7 @@ void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
         const LevelDev Lcd = level_dev(Lc);
         const int twice = (wcycle && (k + 1 != J - 1)) ? 1 : 0;
         int C = N > 592 ? 8 : (N > 296 ? 4 : (N > 148 ? 2 : 1));
-        auto smem_for = [&](int cc) { return sizeof(double) * (size_t)cc * (3 * (size_t)N + 3 * (size_t)Lc.N); };
+        auto smem_for = [&](int cc) { return sizeof(double) * (size_t)(cc == 1 ? 1 : cc + 1) * (3 * (size_t)N + 3 * (size_t)Lc.N); };
         while (C > 1 && smem_for(C) > 200 * 1024) C >>= 1;
         const size_t smem = smem_for(C);
         const int grid = cdiv(N, C);
@@ -1188,6 +1590,9 @@ void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
         else go(std::integral_constant<int, 1>());
     }
     H.dense_from = from;
+    H.hdev.resize(J);
+    for (int k = 0; k < J; ++k) H.hdev[k] = level_dev(H.lv[k]);
+    SSN_CUDA(cudaMemcpyAsync(H.dev.p, H.hdev.data(), sizeof(LevelDev) * J, cudaMemcpyHostToDevice, c->stream));
 }
 
 void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {
@@ -1225,6 +1630,50 @@ void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_
     smooth_host(c, H, k, isnsp, 1, false);                                // :34-42
 }
 
+int tpr_for(double avg) { return avg <= 3.0 ? 2 : (avg <= 6.0 ? 4 : (avg <= 12.0 ? 8 : (avg <= 24.0 ? 16 : 32))); }
+
+// Runs Class_AMG's solve loop in the persistent kernel.  Returns false when the hierarchy does not
+// qualify (no dense tail / too many large levels), in which case the caller launches kernel by kernel.
+bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, int& it,
+                   double& rel_res, std::vector<double>& relk, std::vector<double>& rho) {
+    if (H.dense_from >= H.J || H.dense_from >= kPLevels) return false;
+    for (int k = 0; k < H.dense_from; ++k) if (H.lv[k].bigph && k != 0) return false;
+    Phase ph(c, "solve.persist_solve_kernel");
+    PersistArgs a{};
+    a.levels = H.dev.p; a.J = H.J; a.kd = H.dense_from; a.smoth = H.smoth; a.isnsp = o.isnsp; a.wcycle = wcycle ? 1 : 0;
+    a.b = b; a.x = x; a.retol = o.retol; a.maxit = o.maxit;
+    for (int k = 0; k <= H.dense_from && k < kPLevels; ++k) {
+        const Level& L = H.lv[k];
+        a.tpr[k] = tpr_for(L.N ? (double)L.A.nnz / L.N : 0.0);
+        a.tpr_p[k] = (k > 0) ? tpr_for(L.N ? (double)L.P.nnz / std::max(1, L.N) : 0.0) : 2;
+    }
+    const size_t smem = (size_t)(200 / kPBlocksPerSM - 6) * 1024;
+    SSN_CUDA(cudaFuncSetAttribute(persist_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_solve_kernel, kPT, smem));
+    if (per_sm < kPBlocksPerSM) return false;
+    const int grid = c->num_sms * kPBlocksPerSM;
+    a.smem_budget = smem;
+    { const char* e = getenv("SSN_PERSIST_SMEM"); if (e && e[0] == '0') a.smem_budget = 0; }
+    const int hl = o.maxit + 2;
+    Buf<double> part(c, (size_t)4 * grid), hist(c, (size_t)2 * hl);
+    Buf<int> iout(c, 4);
+    a.part = part.p; a.relk = hist.p; a.rho = hist.p + hl; a.it_out = iout.p;
+    void* args[] = {&a};
+    SSN_CUDA(cudaLaunchCooperativeKernel((void*)persist_solve_kernel, dim3(grid), dim3(kPT), args, smem, c->stream));
+    c->launches++;
+    int hi[4];
+    read_back(c, iout.p, hi, 4);
+    it = hi[0];
+    const int len = hi[1];
+    std::vector<double> hh((size_t)2 * hl);
+    read_back(c, hist.p, hh.data(), hh.size());
+    relk.assign(hh.begin(), hh.begin() + len);
+    rho.assign(hh.begin() + hl, hh.begin() + hl + len);
+    rel_res = (len > 1) ? relk[len - 1] : (relk[0] == 0.0 ? 0.0 : 0.0);
+    return true;
+}
+
 }  // namespace
 
 // Builds the shared-memory staging plan of the cluster kernel for levels k0..J-1 (once per hierarchy).
@@ -1257,6 +1706,17 @@ void build_cluster_plan(ssn_ctx* c, Hierarchy& H) {
     SSN_CUDA(cudaFuncSetAttribute(cluster_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(used ? used : 16)));
 }
 
+// cycles per grid barrier: which = 0 cooperative-groups grid.sync(), 1 = grid_barrier() (development aid)
+double barrier_bench(ssn_ctx* c, int iters, int which) {
+    Buf<unsigned> bar(c, 64); bar.zero();
+    Buf<long long> out(c, 1);
+    unsigned* bp = bar.p; long long* op = out.p;
+    void* args[] = {&bp, &iters, &which, &op};
+    SSN_CUDA(cudaLaunchCooperativeKernel((void*)barrier_bench_kernel, dim3(c->num_sms * kPBlocksPerSM), dim3(kPT), args, 0, c->stream));
+    long long cyc = read_scalar(c, out.p);
+    return (double)cyc / (double)iters;
+}
+
 void debug_cycles(unsigned long long* out64, bool reset) {
     cudaMemcpyFromSymbol(out64, g_dbg_cycles, sizeof(unsigned long long) * 64);
     if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_dbg_cycles, z, sizeof(z)); }
@@ -1287,6 +1747,13 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
     int it = 0;
     double rel_res = 0.0;
     std::vector<double> relk(1, 1.0), rho(1, NAN);
+    const bool isv = (o.cycle == 'v'), isw = (o.cycle == 'w');
+    bool done = false;
+    if (c->persist && (isv || isw)) {
+        if (H.dense_isnsp != o.isnsp || H.dense_w != (isw ? 1 : 0)) build_dense_tail(c, H, o.isnsp, isw);
+        done = persist_solve(c, H, b, x, o, isw, it, rel_res, relk, rho);
+    }
+    if (!done) {
     // r = b - A*x ; res0 = norm(A*x - b)                                 Class_AMG.m:89
     double h[2];
     int np = launch_resid(c, L, b, x, L.r, H.part);
@@ -1298,7 +1765,6 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
         rel_res = 0.0; relk.assign(1, 0.0); rho.assign(1, INFINITY);
     } else {
         it = 1;
-        const bool isv = (o.cycle == 'v'), isw = (o.cycle == 'w');
         while (relk[it - 1] > o.retol && it <= o.maxit) {                 // Class_AMG.m:95
             if (isv || isw) {
                 cycle_host(c, H, 0, o.isnsp, isw, true);                  // e = cycle(r)
@@ -1316,6 +1782,7 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
             if (rho[it - 1] > 1.0) break;                                 // Class_AMG.m:106
         }
         relk.resize(it); rho.resize(it); --it;
+    }
     }
     if (it_out) *it_out = it;
     if (rel_res_out) *rel_res_out = rel_res;

@@ -49,6 +49,7 @@ int ssn_create(ssn_ctx** out, int device) {
     // the 8-CTA cluster cycle kernel is correct (parity-tested) but not yet faster than the single-CTA
     // kernel at these level sizes: opt-in with SSN_CLUSTER=1 until its per-phase latency is tuned
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
+    { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
@@ -97,6 +98,10 @@ int ssn_kernel_timer_read(ssn_ctx* c, double* total_ms, int64_t* launches) {
     if (launches) *launches = c->kt_n;
     return SSN_OK;
 }
+int ssn_debug_barrier_bench(ssn_ctx* c, int iters, int which, double* cycles_per_barrier) {
+    return guarded(c, [&] { *cycles_per_barrier = barrier_bench(c, iters, which); });
+}
+int ssn_set_persistent(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->persist = on != 0; return SSN_OK; }
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;
@@ -220,6 +225,10 @@ int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const doub
 int ssn_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q, int64_t m, int64_t n,
                     double tk, const double* gama, double gama_s, double* n2_out) {
     return guarded(c, [&] { plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, n2_out); sync(c); });
+}
+int ssn_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta, int ll0, int nt,
+                      double* lamT, double* f0_out) {
+    return guarded(c, [&] { plan_trial_vectors(c, lam, zeta, wlk, N, delta, ll0, nt, lamT, f0_out); });
 }
 int ssn_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk, const double* p,
                    const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama, double gama_s, double nu,

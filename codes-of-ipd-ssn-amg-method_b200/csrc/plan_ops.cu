@@ -691,6 +691,21 @@ void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, c
     SSN_CUDA(cudaMemcpyAsync(n2_out_dev, n2_scratch.p, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
 }
 
+// lamT[t] = lam + delta^(ll0+t)*zeta for t < nt, and f0_out[2t] = ||lamT[t]||^2, f0_out[2t+1] = wlk'*lamT[t]
+// (the O(m+n) half of the line-search objective; the row-sharded step calls this on the full dual
+// vectors and plan_prox_trials on its slab).
+void plan_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta,
+                        int ll0, int nt, double* lamT, double* f0_out) {
+    SSN_REQUIRE(lam && zeta && wlk && lamT && f0_out && nt >= 1 && nt <= kMaxTrials && N > 0, SSN_E_INVALID, "trial_vectors: bad arguments");
+    const int nb = 64;
+    Buf<double> alpha(c, nt), f0part(c, (size_t)nb * nt * 2);
+    for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = std::pow(delta, (double)(ll0 + t));
+    SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
+    SSN_LAUNCH(c, trial_vectors_kernel, nb, 256, 0, N, nt, lam, zeta, wlk, alpha.p, lamT, f0part.p);
+    SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, f0_out);
+    SSN_CUDA(cudaStreamSynchronize(c->stream));           // h_pin is reused by the next call
+}
+
 // Armijo backtracking of Class1/APD_SsN_Class1.m:182-211, kMaxTrials trial steps per read of w:
 //   lk_new = lk_old + delta^ll*zeta ; cF_new = bk1/2*||lk_new||^2 - wlk'*lk_new + tk/2*||prox(z)||^2 ;
 //   accept the first ll with  !(cF_new > cF_old - nu*delta^ll*ress)  or  ll == ll_max.

@@ -37,6 +37,9 @@ class _CudaOps:
     def prox_trials(self, w, lamT, p, q, tk, gama):
         return self.api.prox_trials(w, lamT, p, q, tk, gama)
 
+    def trial_vectors(self, lam, zeta, wlk, delta, ll0, nt):
+        return self.api.trial_vectors(lam, zeta, wlk, delta, ll0, nt)
+
     def active_lin(self, s, m_loc, n, r0, m):
         return self.api.active_coo(s, m_loc, n, r0, m)
 
@@ -126,12 +129,16 @@ class ShardedStep:
         rows = self._all_gather_rows(ax[self.n:])
         return torch.cat([buf[: self.n], rows]), float(buf[self.n]), int(round(float(buf[self.n + 1]))), ev.get("s")
 
-    def norms2(self, lams):
-        """||prox(z(lam_t))||^2 of a batch of trial vectors: one read of the slab, one all_reduce."""
+    def trial_batch(self, lk, zeta, delta, ll0, nt):
+        """One read of the slab for nt Armijo trials: returns (lamT, values) with values (host) =
+        [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One all_reduce of nt
+        doubles and one device->host read per pass."""
         torch = self.torch
-        lt = torch.stack([self._lam_loc(l) for l in lams])
-        part = self.ops.prox_trials(self.w_loc, lt, self.p_loc, self.q, self.tk, self.gama)
-        return [float(v) for v in self._all_reduce(part.clone())]
+        lamT, f0 = self.ops.trial_vectors(lk, zeta, self.wlk, delta, ll0, nt)
+        lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
+        part = self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama)
+        self._all_reduce(part)
+        return lamT, torch.cat([part, f0]).cpu().tolist()
 
     def assemble(self, s_loc):
         """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged."""
@@ -156,16 +163,15 @@ class ShardedStep:
         ress = abs(float(Fk_old @ zeta))
         ll, batch, done, passes = 0, 8, False, 0
         while not done:                                                              # :189-211, ll = 0 alone, then 8 per pass
-            lls = list(range(ll, min(ll + (1 if passes == 0 else batch), max_ll + 1)))
-            lams = [lk + delta ** t * zeta for t in lls]
-            n2s = self.norms2(lams); passes += 1
-            for t, lam_t, n2 in zip(lls, lams, n2s):
-                f0 = bk1 / 2 * float(lam_t @ lam_t) - float(wlk @ lam_t)
-                if not (f0 + 0.5 * tk * n2 > cFk_old - nu * delta ** t * ress) or t == max_ll:
-                    ll, lk_new, done = t, lam_t, True
+            nt = min(1 if passes == 0 else batch, max_ll - ll + 1)
+            lamT, vals = self.trial_batch(lk, zeta, delta, ll, nt); passes += 1
+            for t in range(nt):
+                f0 = bk1 / 2 * vals[nt + 2 * t] - vals[nt + 2 * t + 1]
+                if not (f0 + 0.5 * tk * vals[t] > cFk_old - nu * delta ** (ll + t) * ress) or ll + t == max_ll:
+                    ll, lk_new, done = ll + t, lamT[t].clone(), True
                     break
             else:
-                ll = lls[-1] + 1
+                ll += nt
         Axp2, _, _, _ = self.residual(lk_new, False)                                 # :212
         Fk_new = bk1 * lk_new - Axp2 - wlk
         return lk_new, Fk_new, {"E": E, "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,

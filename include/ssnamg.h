@@ -132,6 +132,12 @@ SSN_API int  ssn_kernel_timer_read(ssn_ctx *ctx, double *total_ms, int64_t *laun
  * dense_tail != 0 collapses the tail of small AMG levels (N <= dense_max_n) into dense cycle
  * operators (one matvec per visit); 0 walks them step by step.  dense_max_n <= 0 keeps the value. */
 SSN_API int  ssn_set_dense_tail(ssn_ctx *ctx, int dense_tail, int dense_max_n);
+/* on != 0 (default; env SSN_PERSIST): Class_AMG's solve loop runs as one persistent cooperative kernel
+ * (grid barriers between the dependent steps); 0 launches it kernel by kernel. */
+SSN_API int  ssn_set_persistent(ssn_ctx *ctx, int on);
+/* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
+ * 1 = the library's own barrier (development aid) */
+SSN_API int  ssn_debug_barrier_bench(ssn_ctx *ctx, int iters, int which, double *cycles_per_barrier);
 /* cycle counters of the small-level cycle kernel: out64[0..63] (development aid) */
 SSN_API int  ssn_debug_cycles(ssn_ctx *ctx, unsigned long long *out64, int reset);
 
@@ -189,6 +195,12 @@ SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *l
 SSN_API int ssn_prox_trials(ssn_ctx *ctx, const double *w_dev, const double *lamT_dev, int nt,
                     const double *p_dev, const double *q_dev, int64_t m, int64_t n, double tk,
                     const double *gama_dev, double gama_scalar, double *n2_out_dev);
+
+/* The O(m+n) half of a batch of Armijo trials (row-sharded callers use it with ssn_prox_trials on
+ * their slab): lamT_out_dev[t] = lam + delta^(ll0+t)*zeta for t < nt <= 8 and
+ * f0_out_dev[2t] = ||lamT[t]||^2, f0_out_dev[2t+1] = wlk'*lamT[t]  (Class1/APD_SsN_Class1.m:189-190). */
+SSN_API int ssn_trial_vectors(ssn_ctx *ctx, const double *lam_dev, const double *zeta_dev, const double *wlk_dev,
+                      int64_t N, double delta, int ll0, int nt, double *lamT_out_dev, double *f0_out_dev);
 
 /* The Armijo backtracking of Class1/APD_SsN_Class1.m:182-211 (Class2 :170-200 with its own cF):
  *   lk_new = lk_old + delta^ll*zeta;  cF_new = bk1/2*||lk_new||^2 - wlk'*lk_new + tk/2*||prox(z)||^2;

@@ -219,6 +219,31 @@ def test_dense_tail_equals_stepwise(gpu, oracle, cycle):
         assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
 
 
+@pytest.mark.parametrize("cycle", ["w", "v"])
+@pytest.mark.parametrize("m,n,density", [(400, 300, 0.01), (2500, 2300, 0.0015), (6000, 5000, 0.0008)])
+def test_persistent_solve_equals_launch_by_launch(gpu, oracle, cycle, m, n, density):
+    """Class_AMG's solve loop as one persistent cooperative kernel (default) against the same loop
+    launched kernel by kernel: same cycle counts and residual histories, solutions equal to rounding."""
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=7 * m)
+    guess = 0.01 * np.random.RandomState(3).random_sample(m + n)
+    out = {}
+    try:
+        for mode in (0, 1):
+            gpu.set_persistent(bool(mode))
+            for isnsp in (1, 0):
+                o = dict(AMG_OPTS, fnode=n, cycle=cycle, guess=guess, isnsp=isnsp)
+                gpu.rng_reset()
+                out[mode, isnsp] = gpu.Class_AMG(Ae, f, o)
+    finally:
+        gpu.set_persistent(True)
+    for isnsp in (1, 0):
+        x0, it0, rel0, relk0, rho0 = out[0, isnsp]; x1, it1, rel1, relk1, rho1 = out[1, isnsp]
+        assert it0 == it1 and len(relk0) == len(relk1)
+        big = relk0 > 1e-9
+        assert np.allclose(relk1[big], relk0[big], rtol=1e-7)
+        assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+
+
 @pytest.mark.parametrize("precd", [1, 2, 5])
 def test_pcg_matches_oracle(gpu, oracle, precd):
     m, n = 300, 260

@@ -46,6 +46,11 @@ class OracleOps:
     def prox_trials(self, w, lamT, p, q, tk, gama):
         return torch.tensor([self.prox_residual(w, l, p, q, tk, gama, ())["norm2"] for l in lamT], dtype=torch.float64)
 
+    def trial_vectors(self, lam, zeta, wlk, delta, ll0, nt):
+        lamT = torch.stack([lam + delta ** (ll0 + t) * zeta for t in range(nt)])
+        f0 = torch.stack([v for t in range(nt) for v in (lamT[t] @ lamT[t], wlk @ lamT[t])])
+        return lamT, f0
+
     def active_lin(self, s, m_loc, n, r0, m):
         S = self._np(s).reshape(n, m_loc)                 # column-major slab: S[j, i]
         j, i = np.nonzero(S)                              # slab CSC order

@@ -41,9 +41,12 @@ def main():
     lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
     ctx = lib.context(); buf = (ctypes.c_ulonglong * 64)()
     ctx.call("ssn_debug_cycles", ctypes.cast(buf, ctypes.c_void_p), 1)
+    for slot, nm in {25: "persist.resid", 26: "persist.gs_apply", 27: "persist.jacobi", 28: "persist.spmv", 29: "persist.dense", 31: "persist.kernel"}.items():
+        if buf[32 + slot]:
+            print(f"  dbg {nm:18s}: {buf[slot] / 1e3:10.1f} kcycles over {buf[32 + slot]} calls -> {buf[slot] / buf[32 + slot]:9.0f} cyc/call")
     names = {0: "smooth", 8: "resid+restrict", 16: "prolong", 24: "pcg"}
     for base, nm in names.items():
-        for k in range(8):
+        for k in range(8 if base < 24 else 1):
             if buf[32 + base + k]:
                 print(f"  dbg {nm:15s} level+{k}: {buf[base + k] / 1e3:10.1f} kcycles over {buf[32 + base + k]} calls -> {buf[base + k] / buf[32 + base + k]:9.0f} cyc/call")
 

@@ -1,0 +1,15 @@
+"""Cycles per grid-wide barrier: cooperative-groups grid.sync() vs the library's own barrier."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ssnamg  # noqa: E402
+from importlib import import_module
+
+lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
+ctx = lib.context()
+for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"), (1, "grid_barrier")):
+    v = ctypes.c_double(0.0)
+    ctx.call("ssn_debug_barrier_bench", 2000, which, ctypes.byref(v))
+    print(f"{name:14s}: {v.value:8.0f} cycles per barrier")
