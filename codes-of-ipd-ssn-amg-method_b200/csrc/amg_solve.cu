@@ -1637,6 +1637,12 @@ int tpr_for(double avg) { return avg <= 3.0 ? 2 : (avg <= 6.0 ? 4 : (avg <= 12.0
 bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, int& it,
                    double& rel_res, std::vector<double>& relk, std::vector<double>& rho) {
     if (H.dense_from >= H.J || H.dense_from >= kPLevels) return false;
+    {   // the persistent kernel trades occupancy for latency: with large level matrices (early SsN steps,
+        // millions of nonzeros) the cycle is bandwidth-bound and the multi-block kernels win
+        int64_t nnz = 0;
+        for (int k = 0; k < H.dense_from; ++k) nnz += H.lv[k].A.nnz;
+        if (nnz > c->persist_max_nnz) return false;
+    }
     for (int k = 0; k < H.dense_from; ++k) if (H.lv[k].bigph && k != 0) return false;
     Phase ph(c, "solve.persist_solve_kernel");
     PersistArgs a{};

@@ -50,6 +50,7 @@ int ssn_create(ssn_ctx** out, int device) {
     // kernel at these level sizes: opt-in with SSN_CLUSTER=1 until its per-phase latency is tuned
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {

@@ -58,6 +58,7 @@ struct ssn_ctx {
     ssn::Hierarchy* hier = nullptr;
     // optional phase profiler (ssn_profile_enable): wall time per named phase, stream-synchronised
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
+    int64_t persist_max_nnz = (int64_t)1 << 40;   // SSN_PERSIST_MAXNNZ: above this the cycle is launched kernel by kernel
     bool persist = true;                  // SSN_PERSIST=0: launch the large-level cycle kernel by kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
