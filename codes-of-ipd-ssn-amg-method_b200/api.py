@@ -255,6 +255,29 @@ def prox_trials(w, lamT, p, q, tk, gama=np.inf):
     return out
 
 
+def warmup_class1(c, r, l, p, q, gama=np.inf, res=None, maxit=None):
+    """``[xk,lk] = warmup_class1(c,r,l,p,q,gama,res,maxit)`` -- reference Class1/warmup_class1.m:2-96
+    (A-ADMM warm start), device resident.  ``nargin`` rules of :3-20: ``res`` defaults to 1e-1 and
+    ``maxit`` to inf, ``res == 0 and maxit == inf`` is an error, ``maxit == inf`` means 500; the
+    residual test itself is commented out in the reference (:83-91), so ``maxit`` iterations run."""
+    torch = _torch(); ctx = context(); host = _is_host(c, r, l, p, q)
+    if res is None:
+        res = 1e-1
+    if maxit is None:
+        maxit = np.inf
+    elif res == 0 and maxit == np.inf:
+        raise ValueError("res = 0 and maxit = inf")                       # warmup_class1.m:11
+    if maxit == np.inf:
+        maxit = 500                                                       # :19
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    cd = _dev(c, count=m * n)
+    b = torch.cat([_dev(r), _dev(l)])
+    gvec, gs = _gama_args(gama, m, n)
+    xk = torch.empty(m * n, dtype=torch.float64, device="cuda"); lk = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_warmup_class1", _ptr(cd), _ptr(b), _ptr(pd), _ptr(qd), m, n, _ptr(gvec), gs, int(maxit), _ptr(xk), _ptr(lk))
+    return _ret(xk, host), _ret(lk, host)
+
+
 def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
     """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 8) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
     as device tensors -- the O(m+n) half of a batch of Armijo trials."""

@@ -227,6 +227,10 @@ int ssn_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, con
                     double tk, const double* gama, double gama_s, double* n2_out) {
     return guarded(c, [&] { plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, n2_out); sync(c); });
 }
+int ssn_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n,
+                      const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out) {
+    return guarded(c, [&] { plan_warmup_class1(c, cost, b, p, q, m, n, gama, gama_s, maxit, xk_out, lk_out); sync(c); });
+}
 int ssn_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta, int ll0, int nt,
                       double* lamT, double* f0_out) {
     return guarded(c, [&] { plan_trial_vectors(c, lam, zeta, wlk, N, delta, ll0, nt, lamT, f0_out); });

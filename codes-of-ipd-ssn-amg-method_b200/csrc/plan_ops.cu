@@ -465,6 +465,189 @@ __global__ void __launch_bounds__(256) trial_f0_finish_kernel(const double* __re
     }
 }
 
+// ------------------------------------------------------------------ fused A-ADMM warm start
+// Class1/warmup_class1.m:59-75 as two plan-wide kernels per iteration instead of ~45 separate
+// plan-sized passes (4 Ax, 2 Aty, prox and a dozen vector updates in the reference):
+//   stage A (:63-67)  reads xk vk wk pik lk2 c, writes dd, accumulates Ax(dd)            (6 r + 1 w)
+//   stage B (:70-75)  reads dd xk wk pik lk2, writes xk vk wk pik lk2 in place,
+//                     accumulates Ax(vk1) and Ax(xk1)                                    (5 r + 5 w)
+// The rank-2 terms Aty(.) are formed on the fly from the (n+m)-vectors; Ax(xk) of the next
+// iteration is the Ax(xk1) accumulated here.  Same tiling as plan_reduce_kernel, one column per
+// step (6 arrays x 2 x 16 B loads in flight per lane).
+struct WarmArgs {
+    double* xk; double* vk; double* wk; double* pik; double* lk2; double* dd; const double* c;
+    const double* p; const double* q; const double* b;      // b = [r ; l]
+    const double* lk1; const double* axk;                  // stage A: h1 = lk1 - (Ax(xk) - b)/bk
+    const double* y;                                        // stage B: invAAt(Ax(dd))
+    const double* gama; double gama_s;
+    double ak, bk, gk, muf, etafk, sgk, etagk, tt;
+    int64_t m, n; int cols_per_chunk, num_chunks, num_groups;
+    double* rowpart; double* colpart;                       // A: Ax(dd)   B: Ax(vk1)
+    double* rowpart2; double* colpart2;                     //             B: Ax(xk1)
+};
+
+template <bool VEC>
+__device__ __forceinline__ void ld4(const double* base, const bool (&rok)[4], bool full, double (&v)[4]) {
+    if (VEC) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double2 t = make_double2(0.0, 0.0);
+            if (full || rok[2 * h]) t = __ldcs(reinterpret_cast<const double2*>(base + roff<VEC>(2 * h)));
+            v[2 * h] = t.x; v[2 * h + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (full || rok[k]) ? __ldcs(base + roff<VEC>(k)) : 0.0;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void st4(double* base, const bool (&rok)[4], bool full, const double (&v)[4]) {
+    if (VEC) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (full || rok[2 * h]) __stcs(reinterpret_cast<double2*>(base + roff<VEC>(2 * h)), make_double2(v[2 * h], v[2 * h + 1]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (full || rok[k]) __stcs(base + roff<VEC>(k), v[k]);
+    }
+}
+
+template <int STAGE, bool VEC, int GM>
+__global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
+    extern __shared__ double colbuf[];                 // [2][kWarps][cols_per_chunk]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int64_t m = a.m, n = a.n;
+    const int cpc = a.cols_per_chunk;
+    const int64_t c0 = (int64_t)chunk * cpc;
+    const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
+    const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
+    const int64_t row0 = rbase + (VEC ? 2 * lane : lane);
+    bool rok[4];
+    double pv[4], b2[4], ur[4];                         // ur: row part of h1 (stage A) / of y (stage B)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = row0 + roff<VEC>(k);
+        rok[k] = r < m;
+        pv[k] = rok[k] ? a.p[r] : 0.0;
+        b2[k] = rok[k] ? a.b[n + r] : 0.0;
+        if (STAGE == 0) ur[k] = rok[k] ? (a.lk1[n + r] - (1.0 / a.bk) * (a.axk[n + r] - b2[k])) : 0.0;
+        else            ur[k] = rok[k] ? a.y[n + r] : 0.0;
+    }
+    double rs[4] = {0.0, 0.0, 0.0, 0.0}, rs2[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool full = (rbase + kStripRows <= m);
+    size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
+    double* colbuf2 = colbuf + (size_t)kWarps * cpc;
+    const double ak = a.ak, bk = a.bk, ak2 = a.ak * a.ak;
+    for (int64_t c = c0; c < c1; ++c, off += (size_t)m) {
+        const double qj = __ldg(a.q + c);
+        double xk[4], wk[4], pik[4], lk2[4];
+        ld4<VEC>(a.xk + off, rok, full, xk); ld4<VEC>(a.wk + off, rok, full, wk);
+        ld4<VEC>(a.pik + off, rok, full, pik); ld4<VEC>(a.lk2 + off, rok, full, lk2);
+        double cs = 0.0, cs2 = 0.0;
+        if (STAGE == 0) {
+            double vk[4], cc[4], dd[4];
+            ld4<VEC>(a.vk + off, rok, full, vk); ld4<VEC>(a.c + off, rok, full, cc);
+            const double b1j = __ldg(a.b + c);
+            const double ucj = __ldg(a.lk1 + c) - (1.0 / bk) * (__ldg(a.axk + c) - b1j);      // h1, column part
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double atb = pv[k] * b1j + b2[k] * qj;                                  // Aty(b)
+                const double ath = pv[k] * ucj + ur[k] * qj;                                  // Aty(h1)
+                const double wxk = (ak * a.gk * vk[k] + (a.gk + a.muf * ak) * xk[k]) / a.etafk;   // :61
+                const double h2 = lk2[k] - (1.0 / bk) * (xk[k] - wk[k]) + (ak / bk) * (-(pik[k] - wk[k]));   // :63
+                const double cAw = -atb - wk[k];                                              // :64
+                const double cAlk = ath + h2;
+                const double d = a.etafk * wxk - ak2 * (cc[k] + cAlk + a.sgk * cAw);          // :65
+                dd[k] = (full || rok[k]) ? d : 0.0;
+                cs = fma(dd[k], pv[k], cs); rs[k] = fma(dd[k], qj, rs[k]);
+            }
+            st4<VEC>(a.dd + off, rok, full, dd);
+        } else {
+            double dd[4], xn[4], vn[4], wn[4], pn[4], ln[4];
+            ld4<VEC>(a.dd + off, rok, full, dd);
+            double g[4];
+            if (GM == G_VECTOR) ld4<VEC>(a.gama + off, rok, full, g);
+            const double ycj = __ldg(a.y + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double aty = pv[k] * ycj + ur[k] * qj;                                  // Aty(invAAt(Ax(dd)))
+                const double x1 = (dd[k] - aty) / (a.etafk + a.tt);                           // :70
+                const double v1 = x1 + (x1 - xk[k]) / ak;                                     // :71
+                const double wwk = (ak * pik[k] + wk[k]) / (1.0 + ak);                        // :60
+                const double blk2 = lk2[k] + (ak / bk) * (v1 - pik[k]);                       // :72
+                const double z = wwk - (ak2 / a.etagk) * (-blk2);                             // :73
+                double w1;
+                if (GM == G_INF) w1 = fmax(0.0, z);
+                else { const double gm = (GM == G_VECTOR) ? g[k] : a.gama_s; w1 = fmin(fmax(0.0, z), gm); }
+                const double p1 = w1 + (w1 - wk[k]) / ak;                                     // :74
+                const double l1 = lk2[k] + (ak / bk) * (v1 - p1);                             // :75
+                const bool live = full || rok[k];
+                xn[k] = live ? x1 : 0.0; vn[k] = live ? v1 : 0.0; wn[k] = w1; pn[k] = p1; ln[k] = l1;
+                cs = fma(vn[k], pv[k], cs); rs[k] = fma(vn[k], qj, rs[k]);
+                cs2 = fma(xn[k], pv[k], cs2); rs2[k] = fma(xn[k], qj, rs2[k]);
+            }
+            st4<VEC>(a.xk + off, rok, full, xn); st4<VEC>(a.vk + off, rok, full, vn); st4<VEC>(a.wk + off, rok, full, wn);
+            st4<VEC>(a.pik + off, rok, full, pn); st4<VEC>(a.lk2 + off, rok, full, ln);
+        }
+        cs = warp_sum(cs);
+        if (STAGE == 1) cs2 = warp_sum(cs2);
+        if (lane == 0) { colbuf[warp * cpc + (int)(c - c0)] = cs; if (STAGE == 1) colbuf2[warp * cpc + (int)(c - c0)] = cs2; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (rok[k]) {
+            a.rowpart[(size_t)chunk * (size_t)m + row0 + roff<VEC>(k)] = rs[k];
+            if (STAGE == 1) a.rowpart2[(size_t)chunk * (size_t)m + row0 + roff<VEC>(k)] = rs2[k];
+        }
+    __syncthreads();
+    const int ncols = (int)(c1 - c0);
+    for (int j = threadIdx.x; j < ncols; j += kThreads) {
+        double s = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { s += colbuf[w * cpc + j]; if (STAGE == 1) s2 += colbuf2[w * cpc + j]; }
+        a.colpart[(size_t)group * (size_t)n + c0 + j] = s;
+        if (STAGE == 1) a.colpart2[(size_t)group * (size_t)n + c0 + j] = s2;
+    }
+}
+
+// y = (diag(sg,sg) + A*A') \ x  (invAAt.m:13-20) in one block, no host round trip; np = ||p||^2, nq = ||q||^2
+__global__ void __launch_bounds__(1024) invaat_block_kernel(int64_t n, int64_t m, const double* __restrict__ x,
+                                                            const double* __restrict__ p, const double* __restrict__ q,
+                                                            double sg1, double sg2, double* __restrict__ y) {
+    __shared__ double red[32];
+    double s_np = 0.0, s_nq = 0.0, s_qv = 0.0, s_pv = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) { const double pi = p[i]; s_np = fma(pi, pi, s_np); s_pv = fma(pi, x[n + i], s_pv); }
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) { const double qj = q[j]; s_nq = fma(qj, qj, s_nq); s_qv = fma(qj, x[j], s_qv); }
+    const double np_ = block_sum(s_np, red), nq = block_sum(s_nq, red), qvn = block_sum(s_qv, red), pvm = block_sum(s_pv, red);
+    const double den = sg1 * sg2 + sg1 * nq + sg2 * np_;
+    for (int64_t v = threadIdx.x; v < n + m; v += blockDim.x) {
+        if (v < n) y[v] = x[v] / (sg1 + np_) + (np_ / (sg1 + np_) * qvn - pvm) * q[v] / den;          // invAAt.m:17
+        else       y[v] = x[v] / (sg2 + nq) + (nq / (sg2 + nq) * pvm - qvn) * p[v - n] / den;          // invAAt.m:18
+    }
+}
+// lk1 += (ak/bk) * (Ax(vk1) - b)      (warmup_class1.m:75, first block of lk)
+__global__ void warm_lk1_kernel(int64_t N, double coef, const double* __restrict__ av, const double* __restrict__ b, double* __restrict__ lk1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) lk1[i] += coef * (av[i] - b[i]);
+}
+// finish kernel for two partial sets at once
+__global__ void plan_finish2_kernel(const double* __restrict__ rowpart, const double* __restrict__ colpart,
+                                    const double* __restrict__ rowpart2, const double* __restrict__ colpart2, int num_chunks,
+                                    int num_groups, int64_t m, int64_t n, double* __restrict__ y, double* __restrict__ y2) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) {
+        double s = 0.0, s2 = 0.0;
+        for (int g = 0; g < num_groups; ++g) { s += colpart[(size_t)g * n + gid]; if (y2) s2 += colpart2[(size_t)g * n + gid]; }
+        y[gid] = s; if (y2) y2[gid] = s2;
+    } else if (gid < n + m) {
+        const int64_t i = gid - n;
+        double s = 0.0, s2 = 0.0;
+        for (int c = 0; c < num_chunks; ++c) { s += rowpart[(size_t)c * m + i]; if (y2) s2 += rowpart2[(size_t)c * m + i]; }
+        y[gid] = s; if (y2) y2[gid] = s2;
+    }
+}
+
 struct Tiling { int groups, chunks, cpc; };
 
 Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n) {
@@ -754,6 +937,54 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
     }
     if (ll_out) *ll_out = ll;
     if (passes_out) *passes_out = passes;
+}
+
+// [xk, lk] = warmup_class1(c,r,l,p,q,gama,0,maxit) -- Class1/warmup_class1.m:18-96 with maxit < inf
+// (the call of Class1/APD_SsN_Class1.m:59), device resident, two plan-wide kernels per iteration.
+void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m,
+                        int64_t n, const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out) {
+    SSN_REQUIRE(cost && b && p && q && xk_out && lk_out && m > 0 && n > 0 && maxit >= 0, SSN_E_INVALID, "warmup_class1: bad arguments");
+    const int64_t N = m + n; const size_t mn = (size_t)m * (size_t)n;
+    const Tiling t = plan_tiling(c, m, n);
+    Buf<double> vk(c, mn), wk(c, mn), pik(c, mn), lk2(c, mn), dd(c, mn);
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), rowpart2(c, (size_t)t.chunks * m), colpart2(c, (size_t)t.groups * n);
+    Buf<double> axk(c, N), axdd(c, N), av(c, N), y(c, N);
+    double* xk = xk_out; double* lk1 = lk_out;
+    SSN_CUDA(cudaMemsetAsync(xk, 0, sizeof(double) * mn, c->stream));
+    vk.zero(); wk.zero(); pik.zero(); lk2.zero(); axk.zero();
+    SSN_CUDA(cudaMemsetAsync(lk1, 0, sizeof(double) * N, c->stream));
+    WarmArgs a{};
+    a.xk = xk; a.vk = vk; a.wk = wk; a.pik = pik; a.lk2 = lk2; a.dd = dd; a.c = cost; a.p = p; a.q = q; a.b = b;
+    a.lk1 = lk1; a.axk = axk; a.y = y; a.gama = gama; a.gama_s = gama_s; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart; a.colpart = colpart; a.rowpart2 = rowpart2; a.colpart2 = colpart2;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)2 * kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(xk, m) && vec_ok(cost, m) && (!gama || vec_ok(gama, m)) && vec_ok(vk.p, m) && vec_ok(dd.p, m);
+    const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+    const double muf = 0.0;
+    double gk = 1.0, bk = 1.0;                                              // warmup_class1.m:27
+    for (int k = 1; k <= maxit; ++k) {
+        const double ak = bk, bk1 = bk / (1 + ak);                          // :59
+        const double gk1 = (gk + muf * ak) / (1 + ak);
+        const double etafk = (1 + ak) * gk + muf * ak;
+        const double sgk = 1 / bk1, etagk = (1 + ak) * bk;
+        const double tt = sgk * ak * ak, sg = 1 + etafk / tt;               // :69
+        a.ak = ak; a.bk = bk; a.gk = gk; a.muf = muf; a.etafk = etafk; a.sgk = sgk; a.etagk = etagk; a.tt = tt;
+        if (vec) SSN_LAUNCH(c, (warm_kernel<0, true, G_INF>), grid, kThreads, smem / 2, a);
+        else     SSN_LAUNCH(c, (warm_kernel<0, false, G_INF>), grid, kThreads, smem / 2, a);
+        SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, nullptr, nullptr, t.chunks, t.groups, m, n, axdd.p, nullptr);
+        SSN_LAUNCH(c, invaat_block_kernel, 1, 1024, 0, n, m, axdd.p, p, q, sg, sg, y.p);          // :70
+#define SSN_WARM_B(V, G) do { \
+        if (k == 1) SSN_CUDA(cudaFuncSetAttribute((warm_kernel<1, V, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SSN_LAUNCH(c, (warm_kernel<1, V, G>), grid, kThreads, smem, a); } while (0)
+        if (vec) { if (gm == G_INF) SSN_WARM_B(true, G_INF); else if (gm == G_SCALAR) SSN_WARM_B(true, G_SCALAR); else SSN_WARM_B(true, G_VECTOR); }
+        else     { if (gm == G_INF) SSN_WARM_B(false, G_INF); else if (gm == G_SCALAR) SSN_WARM_B(false, G_SCALAR); else SSN_WARM_B(false, G_VECTOR); }
+#undef SSN_WARM_B
+        SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, rowpart2.p, colpart2.p, t.chunks, t.groups, m, n, av.p, axk.p);
+        SSN_LAUNCH(c, warm_lk1_kernel, cdiv(N, 256), 256, 0, N, ak / bk, av.p, b, lk1);            // :75
+        gk = gk1; bk = bk1;                                                 // :77
+    }
 }
 
 // Y = sparse(reshape(s,m,n)) as two sorted coordinate lists (ASAt.m:15):

@@ -18,6 +18,8 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
                      const double* p, const double* q, int64_t m, int64_t n, double tk, double bk1, const double* gama,
                      double gama_s, double nu, double delta, int ll_max, double cF_old, double ress, int batch,
                      double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out);
+void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m,
+                        int64_t n, const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out);
 int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
                         Buf<int>& ycol, Buf<int>& rowcount);
 }  // namespace ssn

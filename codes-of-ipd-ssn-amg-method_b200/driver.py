@@ -28,7 +28,15 @@ def _t(x, torch):
 
 
 def warmup_class1(c, r, l, p, q, gama, res=0.0, maxit=100):
-    """A-ADMM warm start -- reference Class1/warmup_class1.m:18-96, on the device."""
+    """A-ADMM warm start -- reference Class1/warmup_class1.m:18-96, on the device (fused kernels)."""
+    import torch
+    c, r, l, p, q = (_t(v, torch) for v in (c, r, l, p, q))
+    return api.warmup_class1(c, r, l, p, q, gama, res, maxit)
+
+
+def warmup_class1_unfused(c, r, l, p, q, gama, res=0.0, maxit=100):
+    """The same warm start written operator by operator (Ax / Aty / invAAt calls and torch vector
+    updates, one line per reference line) -- kept as the readable cross-check of the fused kernels."""
     import torch
     c, r, l, p, q = (_t(v, torch) for v in (c, r, l, p, q))
     m, n = l.numel(), r.numel()
@@ -95,7 +103,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
     kx0, kl0 = kkt(xk, lk)
     fxk = [float(c @ xk)]; KKT_xk = [kx0]; KKT_lk = [kl0]
     stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm,
-             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0, "ls_passes": 0}
+             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0, "ls_passes": 0, "solve_calls": []}
     t_loop = time.time()
     rr = [np.inf]
     k = 0
@@ -131,6 +139,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             else:
                 raise ValueError("inner_solver must be 3 (aug_PCG) or 4 (Hybrid_AMG)")
             torch.cuda.synchronize(); stats["solve_s"] += time.time() - t0
+            stats["solve_calls"].append((int(ev["count"]), time.time() - t0, int(itpcg), int(info[0])))
             its.append(itpcg)
             t0 = time.time()
             f0 = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old)  # :182

@@ -214,6 +214,15 @@ SSN_API int ssn_linesearch(ssn_ctx *ctx, const double *w_dev, const double *lam_
                    int ll_max, double cF_old, double ress, int batch, double *lam_new_dev, int *ll_out,
                    double *norm2_out, double *cF_out, int *passes_out);
 
+/* [xk,lk] = warmup_class1(c,r,l,p,q,gama,0,maxit) -- Class1/warmup_class1.m:18-96, the A-ADMM warm start
+ * called at Class1/APD_SsN_Class1.m:59, device resident: two fused plan-wide kernels per iteration
+ * (17 plan-sized reads/writes instead of the ~45 of the Ax/Aty/prox/vector-update chain).
+ * b_dev = [r ; l] (n+m).  Outputs xk_out_dev (m*n) and lk_out_dev (n+m).  The reference's stopping
+ * test is commented out (warmup_class1.m:83-91), so exactly maxit iterations run. */
+SSN_API int ssn_warmup_class1(ssn_ctx *ctx, const double *c_dev, const double *b_dev, const double *p_dev,
+                      const double *q_dev, int64_t m, int64_t n, const double *gama_dev, double gama_scalar,
+                      int maxit, double *xk_out_dev, double *lk_out_dev);
+
 /* H = ASAt(s,p,q) -- ASAt.m:14-19.  s: logical m*n (1 byte per entry).  H is
  * (n+m) x (n+m), column nodes first, explicit zeros dropped. */
 SSN_API int ssn_asat(ssn_ctx *ctx, const uint8_t *s_dev, const double *p_dev, const double *q_dev,

@@ -29,6 +29,11 @@ def main():
           f"ssn={sum(st['ssn_its'])} ls_trials={st['ls_trials']} amg_calls={st['amg_calls']} loop_s={out['seconds']:.2f} "
           f"warmup_s={out['warmup_seconds']:.2f} solve_s={st['solve_s']:.2f} asat_s={st['asat_s']:.2f} plan_s={st['plan_s']:.2f} "
           f"launches={ssnamg.launch_count() - l0}")
+    calls = np.array([(e, t) for e, t, _, _ in st["solve_calls"]]) if st["solve_calls"] else np.zeros((0, 2))
+    for lo, hi in ((0, 1), (1, 1e5), (1e5, 1e6), (1e6, 4e6), (4e6, 1e9)):
+        sel = (calls[:, 0] >= lo) & (calls[:, 0] < hi)
+        if sel.any():
+            print(f"  AMG calls with E in [{lo:g},{hi:g}): {int(sel.sum()):4d} calls, {calls[sel, 1].sum():7.2f} s, mean {1e3 * calls[sel, 1].mean():7.1f} ms, max {1e3 * calls[sel, 1].max():7.1f} ms")
     E = np.array([r[2] for r in recs])
     if E.size:
         print("E min/median/max", E.min(), np.median(E), E.max(), " lin its", [i for its in st["lin_its"] for i in its][:60])
