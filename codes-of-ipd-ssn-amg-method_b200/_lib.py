@@ -85,6 +85,8 @@ SIGNATURES = {
                                  _pdbl, _pi64]),
     "ssn_prox_trials": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp]),
     "ssn_warmup_class1": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, _int, _vp, _vp]),
+    "ssn_apd_begin": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp]),
+    "ssn_apd_end": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _vp, _vp, _vp, _pdbl, _pdbl]),
     "ssn_trial_vectors": (_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp]),
     "ssn_linesearch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _int, _dbl, _dbl,
                               _int, _vp, C.POINTER(_int), _pdbl, _pdbl, C.POINTER(_int)]),

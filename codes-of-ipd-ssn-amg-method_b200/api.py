@@ -278,6 +278,31 @@ def warmup_class1(c, r, l, p, q, gama=np.inf, res=None, maxit=None):
     return _ret(xk, host), _ret(lk, host)
 
 
+def apd_begin(c, xk, vk, p, q, ak, bk):
+    """``wk = -c + bk*(xk+ak*vk)/ak^2`` and ``Ax(xk)`` in one pass (Class1/APD_SsN_Class1.m:125-126)."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    cd, xd, vd = _dev(c, count=m * n), _dev(xk, count=m * n), _dev(vk, count=m * n)
+    wk = torch.empty(m * n, dtype=torch.float64, device="cuda"); axk = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_apd_begin", _ptr(cd), _ptr(xd), _ptr(vd), _ptr(pd), _ptr(qd), m, n, float(ak), float(bk), _ptr(wk), _ptr(axk))
+    return wk, axk
+
+
+def apd_end(c, wk, xk, lam, p, q, tk, ak, gama=np.inf):
+    """``xk1 = prox((wk-Aty(lam))/tk)``, ``vk1 = xk1+(xk1-xk)/ak``, ``Ax(xk1)``, ``c'xk1`` and
+    ``||xk1-prox(xk1-c-Aty(lam))||^2`` in one pass (Class1/APD_SsN_Class1.m:239-254)."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    cd, wd, xd, ld = _dev(c, count=m * n), _dev(wk, count=m * n), _dev(xk, count=m * n), _dev(lam)
+    gvec, gs = _gama_args(gama, m, n)
+    xk1 = torch.empty(m * n, dtype=torch.float64, device="cuda"); vk1 = torch.empty(m * n, dtype=torch.float64, device="cuda")
+    axk1 = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    cx = C.c_double(0.0); kx2 = C.c_double(0.0)
+    ctx.call("ssn_apd_end", _ptr(cd), _ptr(wd), _ptr(xd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), float(ak), _ptr(gvec), gs,
+             _ptr(xk1), _ptr(vk1), _ptr(axk1), C.byref(cx), C.byref(kx2))
+    return xk1, vk1, axk1, cx.value, kx2.value
+
+
 def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
     """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 8) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
     as device tensors -- the O(m+n) half of a batch of Armijo trials."""

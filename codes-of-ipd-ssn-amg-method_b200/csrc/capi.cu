@@ -231,6 +231,21 @@ int ssn_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const dou
                       const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out) {
     return guarded(c, [&] { plan_warmup_class1(c, cost, b, p, q, m, n, gama, gama_s, maxit, xk_out, lk_out); sync(c); });
 }
+int ssn_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q, int64_t m,
+                  int64_t n, double ak, double bk, double* wk_out, double* axk_out) {
+    return guarded(c, [&] { plan_apd_begin(c, cost, xk, vk, p, q, m, n, ak, bk, wk_out, axk_out); sync(c); });
+}
+int ssn_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double* xk, const double* lam, const double* p, const double* q,
+                int64_t m, int64_t n, double tk, double ak, const double* gama, double gama_s, double* xk1, double* vk1,
+                double* axk1_out, double* cx_out, double* kx2_out) {
+    return guarded(c, [&] {
+        Buf<double> scal(c, 2);
+        plan_apd_end(c, cost, wk, xk, lam, p, q, m, n, tk, ak, gama, gama_s, xk1, vk1, axk1_out, scal);
+        double h[2]; read_back(c, scal.p, h, 2);
+        if (cx_out) *cx_out = h[0];
+        if (kx2_out) *kx2_out = h[1];
+    });
+}
 int ssn_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta, int ll0, int nt,
                       double* lamT, double* f0_out) {
     return guarded(c, [&] { plan_trial_vectors(c, lam, zeta, wlk, N, delta, ll0, nt, lamT, f0_out); });

@@ -611,6 +611,114 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ fused APD outer-iteration updates
+// The plan-wide lines of the outer loop of Class1/APD_SsN_Class1.m around the SsN solve:
+//   stage 0 (:125-126)   wk = -c + bk*(xk+ak*vk)/ak^2  and  Ax(xk)                      (3 r + 1 w)
+//   stage 1 (:239-254)   xk1 = prox((wk-Aty(lk1))/tk), vk1 = xk1+(xk1-xk)/ak, and in the same pass
+//                        Ax(xk1), c'*xk1, ||xk1 - prox(xk1-c-Aty(lk1))||^2               (3 r + 2 w)
+// (as torch expressions these are ~40 plan-sized passes per outer iteration).
+struct ApdArgs {
+    const double* c; const double* xk; const double* vk; const double* wk_in;
+    double* wk_out; double* xk1; double* vk1;
+    const double* p; const double* q; const double* lam;
+    const double* gama; double gama_s;
+    double ak, bk, inv_tk;
+    int64_t m, n; int cols_per_chunk, num_chunks, num_groups;
+    double* rowpart; double* colpart; double* scalpart;
+};
+
+template <int GM>
+__device__ __forceinline__ double prox_of(double z, double gm) {
+    if (GM == G_INF) return (z >= 0.0) ? z : 0.0;
+    return (z >= 0.0) ? ((z <= gm) ? z : gm) : fmin(0.0, gm);
+}
+
+template <int STAGE, bool VEC, int GM>
+__global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
+    extern __shared__ double colbuf[];                 // [kWarps][cols_per_chunk]
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x, group = blockIdx.y;
+    const int64_t m = a.m, n = a.n;
+    const int cpc = a.cols_per_chunk;
+    const int64_t c0 = (int64_t)chunk * cpc;
+    const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
+    const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
+    const int64_t row0 = rbase + (VEC ? 2 * lane : lane);
+    bool rok[4];
+    double pv[4], y2v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = row0 + roff<VEC>(k);
+        rok[k] = r < m;
+        pv[k] = rok[k] ? a.p[r] : 0.0;
+        y2v[k] = (STAGE == 1 && rok[k]) ? a.lam[n + r] : 0.0;
+    }
+    double rs[4] = {0.0, 0.0, 0.0, 0.0};
+    double s_cx = 0.0, s_kx = 0.0;
+    const bool full = (rbase + kStripRows <= m);
+    size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
+    const double ak = a.ak, ak2 = a.ak * a.ak;
+    for (int64_t c = c0; c < c1; ++c, off += (size_t)m) {
+        const double qj = __ldg(a.q + c);
+        double cc[4], xk[4];
+        ld4<VEC>(a.c + off, rok, full, cc); ld4<VEC>(a.xk + off, rok, full, xk);
+        double cs = 0.0;
+        if (STAGE == 0) {
+            double vk[4], w[4];
+            ld4<VEC>(a.vk + off, rok, full, vk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // rounded exactly like the reference expression (no FMA contraction): wk decides the active set
+                w[k] = __dadd_rn(-cc[k], __ddiv_rn(__dmul_rn(a.bk, __dadd_rn(xk[k], __dmul_rn(ak, vk[k]))), ak2));   // :125
+                cs = fma(xk[k], pv[k], cs); rs[k] = fma(xk[k], qj, rs[k]);                      // Ax(xk), :126
+            }
+            st4<VEC>(a.wk_out + off, rok, full, w);
+        } else {
+            double w[4], g[4], x1[4], v1[4];
+            ld4<VEC>(a.wk_in + off, rok, full, w);
+            if (GM == G_VECTOR) ld4<VEC>(a.gama + off, rok, full, g);
+            const double y1j = __ldg(a.lam + c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double gm = (GM == G_VECTOR) ? g[k] : a.gama_s;
+                const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                const double z = __dmul_rn(a.inv_tk, __dsub_rn(w[k], aty));                    // zk, :139 arithmetic
+                const bool live = full || rok[k];
+                const double xn = live ? prox_of<GM>(z, gm) : 0.0;                              // xk1 = prox(zk), :239
+                x1[k] = xn;
+                v1[k] = __dadd_rn(xn, __ddiv_rn(__dsub_rn(xn, xk[k]), ak));                     // vk1, :239 (feeds wk: no FMA)
+                const double z2 = __dsub_rn(__dsub_rn(xn, cc[k]), aty);                         // xk1 - c - Aty(lk1), :242
+                const double dk = live ? (xn - prox_of<GM>(z2, gm)) : 0.0;
+                s_kx = fma(dk, dk, s_kx);
+                s_cx = fma(cc[k], xn, s_cx);                                                    // c'*xk, :253
+                cs = fma(xn, pv[k], cs); rs[k] = fma(xn, qj, rs[k]);                            // Ax(xk1), :241
+            }
+            st4<VEC>(a.xk1 + off, rok, full, x1); st4<VEC>(a.vk1 + off, rok, full, v1);
+        }
+        cs = warp_sum(cs);
+        if (lane == 0) colbuf[warp * cpc + (int)(c - c0)] = cs;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (rok[k]) a.rowpart[(size_t)chunk * (size_t)m + row0 + roff<VEC>(k)] = rs[k];
+    __syncthreads();
+    const int ncols = (int)(c1 - c0);
+    for (int j = threadIdx.x; j < ncols; j += kThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += colbuf[w * cpc + j];
+        a.colpart[(size_t)group * (size_t)n + c0 + j] = s;
+    }
+    if (STAGE == 1) {
+        const double t1 = block_sum(s_cx, red), t2 = block_sum(s_kx, red);
+        if (threadIdx.x == 0) {
+            const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            a.scalpart[2 * b] = t1; a.scalpart[2 * b + 1] = t2;
+        }
+    }
+}
+
 // y = (diag(sg,sg) + A*A') \ x  (invAAt.m:13-20) in one block, no host round trip; np = ||p||^2, nq = ||q||^2
 __global__ void __launch_bounds__(1024) invaat_block_kernel(int64_t n, int64_t m, const double* __restrict__ x,
                                                             const double* __restrict__ p, const double* __restrict__ q,
@@ -985,6 +1093,48 @@ void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const d
         SSN_LAUNCH(c, warm_lk1_kernel, cdiv(N, 256), 256, 0, N, ak / bk, av.p, b, lk1);            // :75
         gk = gk1; bk = bk1;                                                 // :77
     }
+}
+
+// wk = -c + bk*(xk+ak*vk)/ak^2 and axk = Ax(xk)      (Class1/APD_SsN_Class1.m:125-126)
+void plan_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q,
+                    int64_t m, int64_t n, double ak, double bk, double* wk_out, double* axk_out) {
+    SSN_REQUIRE(cost && xk && vk && p && q && wk_out && axk_out && m > 0 && n > 0, SSN_E_INVALID, "apd_begin: bad arguments");
+    const Tiling t = plan_tiling(c, m, n);
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n);
+    ApdArgs a{};
+    a.c = cost; a.xk = xk; a.vk = vk; a.wk_out = wk_out; a.p = p; a.q = q; a.ak = ak; a.bk = bk; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups; a.rowpart = rowpart; a.colpart = colpart;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(cost, m) && vec_ok(xk, m) && vec_ok(vk, m) && vec_ok(wk_out, m);
+    if (vec) SSN_LAUNCH(c, (apd_kernel<0, true, G_INF>), grid, kThreads, smem, a);
+    else     SSN_LAUNCH(c, (apd_kernel<0, false, G_INF>), grid, kThreads, smem, a);
+    SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, nullptr, t.chunks, t.groups, m, n, 0, axk_out, nullptr);
+}
+
+// xk1 = prox((wk-Aty(lam))/tk), vk1 = xk1+(xk1-xk)/ak, axk1 = Ax(xk1), scal2 = {c'*xk1, ||xk1-prox(xk1-c-Aty(lam))||^2}
+// (Class1/APD_SsN_Class1.m:239-254)
+void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double* xk, const double* lam, const double* p,
+                  const double* q, int64_t m, int64_t n, double tk, double ak, const double* gama, double gama_s, double* xk1,
+                  double* vk1, double* axk1_out, double* scal2_dev) {
+    SSN_REQUIRE(cost && wk && xk && lam && p && q && xk1 && vk1 && axk1_out && scal2_dev && m > 0 && n > 0, SSN_E_INVALID, "apd_end: bad arguments");
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), scalpart(c, (size_t)2 * nblocks);
+    ApdArgs a{};
+    a.c = cost; a.xk = xk; a.wk_in = wk; a.xk1 = xk1; a.vk1 = vk1; a.p = p; a.q = q; a.lam = lam; a.gama = gama; a.gama_s = gama_s;
+    a.ak = ak; a.inv_tk = 1.0 / tk; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups; a.rowpart = rowpart; a.colpart = colpart; a.scalpart = scalpart;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(cost, m) && vec_ok(xk, m) && vec_ok(wk, m) && vec_ok(xk1, m) && vec_ok(vk1, m) && (!gama || vec_ok(gama, m));
+    const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+#define SSN_APD_E(V, G) SSN_LAUNCH(c, (apd_kernel<1, V, G>), grid, kThreads, smem, a)
+    if (vec) { if (gm == G_INF) SSN_APD_E(true, G_INF); else if (gm == G_SCALAR) SSN_APD_E(true, G_SCALAR); else SSN_APD_E(true, G_VECTOR); }
+    else     { if (gm == G_INF) SSN_APD_E(false, G_INF); else if (gm == G_SCALAR) SSN_APD_E(false, G_SCALAR); else SSN_APD_E(false, G_VECTOR); }
+#undef SSN_APD_E
+    SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, scalpart.p, t.chunks, t.groups, m, n, nblocks,
+               axk1_out, scal2_dev);
 }
 
 // Y = sparse(reshape(s,m,n)) as two sorted coordinate lists (ASAt.m:15):

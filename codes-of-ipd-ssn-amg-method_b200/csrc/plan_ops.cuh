@@ -20,6 +20,11 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
                      double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out);
 void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m,
                         int64_t n, const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out);
+void plan_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q,
+                    int64_t m, int64_t n, double ak, double bk, double* wk_out, double* axk_out);
+void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double* xk, const double* lam, const double* p,
+                  const double* q, int64_t m, int64_t n, double tk, double ak, const double* gama, double gama_s, double* xk1,
+                  double* vk1, double* axk1_out, double* scal2_dev);
 int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
                         Buf<int>& ycol, Buf<int>& rowcount);
 }  // namespace ssn

@@ -112,8 +112,8 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
         ak = math.sqrt(k ** 2 * bk)                                     # :113
         bk1 = bk / (1 + ak); tk = bk * (1 + ak) / ak ** 2               # :120
         SsN_Tol = max(bk1 / (k ** 2), SsN_Tol1)                         # :123
-        wk = -c + bk * (xk + ak * vk) / ak ** 2                         # :125
-        wlk = bk1 * (lk - 1 / bk * (api.Ax(xk, p, q) - b)) - b          # :126
+        wk, axk = api.apd_begin(c, xk, vk, p, q, ak, bk)               # :125 and Ax(xk) of :126, one pass
+        wlk = bk1 * (lk - 1 / bk * (axk - b)) - b                       # :126
         ssn_it = 0; lk_new = lk.clone()
         ev = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))   # :129-130 (+ s for :140)
         Fk_new = bk1 * lk_new - ev["Axprox"] - wlk
@@ -163,15 +163,15 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             if Fk_res / nF >= 2:
                 Fk_res = nF
         lk1 = lk_new
-        xk1 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("prox",))["prox"]          # :239
-        vk1 = xk1 + (xk1 - xk) / ak
-        kx, kl = kkt(xk1, lk1)
+        # :239-254 in one pass: xk1 = prox(zk), vk1, Ax(xk1), c'xk1 and the KKT residual of xk1
+        xk1, vk1, axk1, cx, kx2 = api.apd_end(c, wk, xk, lk1, p, q, tk, ak, gam)
+        kl = float(torch.linalg.norm(axk1 - b)); kx = math.sqrt(kx2)
         rr = [kx / (1 + KKT_xk[0]), kl / (1 + KKT_lk[0])]
         if bk1 < 1e-8 and max(rr) > resk:                               # :245-249
             xk1 = xk; lk1 = lk; vk1 = xk; bk1 = float(api.rand(1)[0])
-            kx, kl = kkt(xk1, lk1)
+            kx, kl = kkt(xk1, lk1); cx = float(c @ xk1)
         bk = bk1; xk = xk1; lk = lk1; vk = vk1                          # :251
-        fxk.append(float(c @ xk)); KKT_lk.append(kl); KKT_xk.append(kx)
+        fxk.append(cx); KKT_lk.append(kl); KKT_xk.append(kx)
         stats["ssn_its"].append(ssn_it); stats["lin_its"].append(its)
         rr = [KKT_xk[k] / (1 + KKT_xk[0]), KKT_lk[k] / (1 + KKT_lk[0])]
         if verbose:

@@ -223,6 +223,19 @@ SSN_API int ssn_warmup_class1(ssn_ctx *ctx, const double *c_dev, const double *b
                       const double *q_dev, int64_t m, int64_t n, const double *gama_dev, double gama_scalar,
                       int maxit, double *xk_out_dev, double *lk_out_dev);
 
+/* The plan-wide lines of the APD outer iteration around the SsN solve, fused:
+ *   ssn_apd_begin  wk = -c + bk*(xk+ak*vk)/ak^2 and axk = Ax(xk)            Class1/APD_SsN_Class1.m:125-126
+ *   ssn_apd_end    xk1 = prox((wk-Aty(lam))/tk), vk1 = xk1+(xk1-xk)/ak, axk1 = Ax(xk1),
+ *                  *cx_out = c'*xk1, *kx2_out = ||xk1-prox(xk1-c-Aty(lam))||^2   :239-254
+ * one read of each input, one write of each output. */
+SSN_API int ssn_apd_begin(ssn_ctx *ctx, const double *c_dev, const double *xk_dev, const double *vk_dev,
+                  const double *p_dev, const double *q_dev, int64_t m, int64_t n, double ak, double bk,
+                  double *wk_out_dev, double *axk_out_dev);
+SSN_API int ssn_apd_end(ssn_ctx *ctx, const double *c_dev, const double *wk_dev, const double *xk_dev,
+                const double *lam_dev, const double *p_dev, const double *q_dev, int64_t m, int64_t n,
+                double tk, double ak, const double *gama_dev, double gama_scalar, double *xk1_out_dev,
+                double *vk1_out_dev, double *axk1_out_dev, double *cx_out, double *kx2_out);
+
 /* H = ASAt(s,p,q) -- ASAt.m:14-19.  s: logical m*n (1 byte per entry).  H is
  * (n+m) x (n+m), column nodes first, explicit zeros dropped. */
 SSN_API int ssn_asat(ssn_ctx *ctx, const uint8_t *s_dev, const double *p_dev, const double *q_dev,

@@ -232,3 +232,28 @@ def test_linesearch_matches_trial_by_trial_loop(gpu, oracle):
         assert passes == 1 + (ll + 7) // 8
         assert np.array_equal(out.cpu().numpy(), lk_new)
         assert abs(cF_new - cF(lk_new)) <= 1e-10 * max(1.0, abs(cF_new))
+
+
+@pytest.mark.parametrize("m,n", [(7, 5), (250, 130), (1027, 517), (2048, 300)])
+@pytest.mark.parametrize("gama", [np.inf, 0.3])
+def test_fused_apd_outer_updates(gpu, oracle, m, n, gama):
+    """ssn_apd_begin / ssn_apd_end against the reference expressions of
+    Class1/APD_SsN_Class1.m:125-126 and :239-254 evaluated with the oracle operators."""
+    rs = np.random.RandomState(3 * m + n)
+    p, q = weights(m, n, 4, False)
+    c = rs.random_sample(m * n); xk = np.maximum(rs.standard_normal(m * n), 0); vk = rs.standard_normal(m * n)
+    lam = 0.4 * rs.standard_normal(n + m)
+    ak, bk, tk = 1.7, 0.6, 0.45
+    prox = lambda x: np.minimum(np.maximum(0.0, x), gama)
+    wk_ref = -c + bk * (xk + ak * vk) / ak ** 2
+    wk, axk = gpu.apd_begin(c, xk, vk, p, q, ak, bk)
+    assert np.array_equal(wk.cpu().numpy(), wk_ref)
+    assert close(axk.cpu().numpy(), oracle.Ax(xk, p, q))
+    zk = 1 / tk * (wk_ref - oracle.Aty(lam, p, q))
+    x1_ref = prox(zk); v1_ref = x1_ref + (x1_ref - xk) / ak
+    kx_ref = np.linalg.norm(x1_ref - prox(x1_ref - c - oracle.Aty(lam, p, q)))
+    x1, v1, ax1, cx, kx2 = gpu.apd_end(c, wk, xk, lam, p, q, tk, ak, gama)
+    assert np.array_equal(x1.cpu().numpy(), x1_ref) and np.array_equal(v1.cpu().numpy(), v1_ref)
+    assert close(ax1.cpu().numpy(), oracle.Ax(x1_ref, p, q))
+    assert abs(cx - c @ x1_ref) <= 1e-10 * max(abs(c @ x1_ref), 1.0)
+    assert abs(np.sqrt(kx2) - kx_ref) <= 1e-10 * max(kx_ref, 1.0)
