@@ -51,3 +51,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_mex_shims_type_check_against_the_header():
+    """MATLAB is absent, so the MEX shims (one per reference function, mex/*.c) cannot be built here;
+    they are at least type-checked against include/ssnamg.h with a declaration-only mex.h stub."""
+    import glob
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shims = sorted(glob.glob(os.path.join(root, "mex", "*.c")))
+    names = {os.path.splitext(os.path.basename(f))[0] for f in shims}
+    for fn in ("Ax", "Aty", "ASAt", "ASAtz", "PCG", "aug_PCG", "components", "Hybrid_AMG", "Class_AMG", "transfer", "strength",
+               "mis_set", "cf_split_mex", "MG_Vcycle", "MG_Wcycle", "AMG4POT", "PCG4POT", "invAAt", "invHHt", "warmup_class1"):
+        assert fn in names, f"no MEX shim for {fn}"
+    for f in shims:
+        r = subprocess.run([gcc, "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function",
+                            "-I" + os.path.join(root, "tests", "mex_stub"), "-I" + os.path.join(root, "mex"), f],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"{os.path.basename(f)}:\n{r.stderr}"
