@@ -188,6 +188,160 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             "stats": stats, "seconds": time.time() - t_loop, "warmup_seconds": t_warm}
 
 
+# ------------------------------------------------------------------ Class 2: partial optimal transport
+
+CLASS2_AMG_OPTIONS = {"retol": 1e-11, "bigph": 1, "maxit": 40, "theta": 1 / 4, "smoth": 10, "cycle": "w",
+                      "isnsp": 1, "inter": 1, "guess": None}            # Class2/APD_SsN_Class2.m:80-81
+
+
+def warmup_class2(c, r, l, p, q, mu, phi, res=0.0, maxit=100):
+    """A-ADMM warm start for partial OT -- reference Class2/warmup_class2.m:18-108, on the device
+    (operator by operator: Ax, Aty, invHHt and torch vector updates)."""
+    import torch
+    c, r, l, p, q, phi = (_t(v, torch) for v in (c, r, l, p, q, phi))
+    m, n = l.numel(), r.numel(); N = m + n; mn = m * n
+    f64 = dict(dtype=torch.float64, device="cuda")
+    b = torch.cat([r, l, torch.tensor([float(mu)], **f64)])
+    Hmul = lambda u: torch.cat([api.Ax(u[:mn], p, q) + u[mn:], (phi @ u[:mn]).reshape(1)])
+    Htmul = lambda lam: torch.cat([api.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])
+    Htb = Htmul(b)                                                      # :22
+    wc = torch.cat([c, torch.zeros(N, **f64)])
+    muf = 0.0; gk = 1.0; bk = 1.0
+    uk = torch.zeros(mn + N, **f64); vk = uk.clone(); wk = uk.clone(); pik = uk.clone()
+    lkA = torch.zeros(N + 1, **f64); lkB = uk.clone()                   # lk = [lkA ; lkB], :26
+    for _ in range(int(maxit)):                                         # :46-107
+        ak = bk; bk1 = bk / (1 + ak)
+        gk1 = (gk + muf * ak) / (1 + ak)
+        etafk = (1 + ak) * gk + muf * ak
+        sgk = 1 / bk1; etagk = (1 + ak) * bk
+        wwk = (ak * pik + wk) / (1 + ak)
+        wuk = (ak * gk * vk + (gk + muf * ak) * uk) / etafk
+        hA = lkA - (Hmul(uk) - b) / bk                                  # :66
+        hB = lkB - (uk - wk) / bk - (ak / bk) * (pik - wk)
+        cAw = -Htb - wk
+        cAlk = hB + Htmul(hA)                                           # :67-68
+        dd = etafk * wuk - ak ** 2 * (wc + cAlk + sgk * cAw)            # :69
+        del hB, cAw, cAlk, wuk
+        tt = sgk * ak ** 2; sg = 1 + etafk / tt
+        ff = api.invHHt(Hmul(dd), p, q, sg, phi)                        # :71-72
+        uk1 = (dd - Htmul(ff)) / (etafk + tt)                           # :73
+        del dd
+        vk1 = uk1 + (uk1 - uk) / ak
+        b0 = Hmul(vk1) - b                                              # :75
+        blkB = lkB + (ak / bk) * (vk1 - pik)
+        wk1 = torch.clamp_min(wwk - (ak ** 2 / etagk) * (-blkB), 0.0)   # :77
+        del blkB, wwk
+        pik1 = wk1 + (wk1 - wk) / ak
+        lkA = lkA + (ak / bk) * b0                                      # :79
+        lkB = lkB + (ak / bk) * (vk1 - pik1)
+        gk = gk1; bk = bk1; uk = uk1; vk = vk1; wk = wk1; pik = pik1
+    return uk, lkA
+
+
+def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
+                   on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None):
+    """APD outer loop + SsN inner loop for partial OT -- reference Class2/APD_SsN_Class2.m:25-285 on the
+    device (inner solver 3 = PCG4POT, 4 = AMG4POT).  u = [x (mn); y (n); z (m)], duals lk (n+m+1)."""
+    import torch
+    c, r, l, p, q, phi = (_t(v, torch) for v in (c, r, l, p, q, phi))
+    m, n = l.numel(), r.numel(); N = m + n; mn = m * n
+    f64 = dict(dtype=torch.float64, device="cuda")
+    b = torch.cat([r, l, torch.tensor([float(mu)], **f64)]); wc = torch.cat([c, torch.zeros(N, **f64)])
+    bk = 1.0
+    SsN_IT = 50; SsN_Tol1 = 1e-10; nu = 0.2; delta = 0.9; ll_max = 500   # :28
+    amg_options = dict(amg_options or CLASS2_AMG_OPTIONS); pcg_options = dict(CLASS1_PCG_OPTIONS)
+    Hmul = lambda u: torch.cat([api.Ax(u[:mn], p, q) + u[mn:], (phi @ u[:mn]).reshape(1)])
+    Htmul = lambda lam: torch.cat([api.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])
+    nrm = lambda v: float(torch.linalg.norm(v))
+    t_start = time.time()
+    uk, lk = warmup_class2(c, r, l, p, q, mu, phi, 0.0, warm_maxit)     # :50
+    torch.cuda.synchronize(); t_warm = time.time() - t_start
+    vk = uk.clone()
+
+    def kkts(u, lam):
+        x, y, z = u[:mn], u[mn:mn + n], u[mn + n:]
+        return (nrm(x - torch.clamp_min(x - c - (api.Aty(lam[:N], p, q) + lam[N] * phi), 0.0)),
+                nrm(y - torch.clamp_min(y - lam[:n], 0.0)), nrm(z - torch.clamp_min(z - lam[n:N], 0.0)),
+                nrm(Hmul(u) - b))
+
+    KKT = [kkts(uk, lk)]; fxk = [float(c @ uk[:mn])]
+    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm}
+    t_loop = time.time(); rr = [np.inf]; k = 0
+    for k in range(1, maxit + 1):                                       # :95
+        resk = max(KKT[k - 1])
+        ak = math.sqrt(k ** 2 * bk)                                     # :116
+        bk1 = bk / (1 + ak); tk = bk * (1 + ak) / ak ** 2
+        SsN_Tol = max(bk1 / (k ** 2), SsN_Tol1)
+        wk = -wc + bk * (uk + ak * vk) / ak ** 2                        # :121
+        wlk = bk1 * (lk - 1 / bk * (Hmul(uk) - b)) - b                  # :122
+        ssn_it = 0; lk_new = lk.clone()
+        zk = 1 / tk * (wk - Htmul(lk_new))                              # :127
+        Fk_new = bk1 * lk_new - Hmul(torch.clamp_min(zk, 0.0)) - wlk    # :130
+        nF = nrm(Fk_new); Fk_res = nF
+        its = []
+        while nF > SsN_Tol:                                             # :136
+            ssn_it += 1; lk_old = lk_new; Fk_old = Fk_new               # zk is already z(lk_old)
+            s = (zk[:mn] >= 0).to(torch.uint8); t = (zk[mn:] >= 0).to(torch.float64)   # :139
+            H0 = api.ASAt(s, p, q)                                      # :146
+            prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "s": s, "T": t, "H0": H0, "z": -Fk_old, "phi": phi}
+            if on_ssn_step is not None:
+                on_ssn_step(dict(prob_data, k=k, ssn_it=ssn_it))
+            if inner_solver == 3:
+                zeta, itpcg, respcg, info = api.PCG4POT(prob_data, pcg_options)        # :168
+            elif inner_solver == 4:
+                zeta, itpcg, respcg, info = api.AMG4POT(prob_data, amg_options, "amg")   # :171
+                stats["amg_calls"] += 1
+            else:
+                raise ValueError("inner_solver must be 3 (PCG4POT) or 4 (AMG4POT)")
+            its.append(itpcg)
+            pz = torch.clamp_min(zk, 0.0)
+            cFk_old = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old) + 0.5 * tk * float(pz @ pz)   # :196-197
+            ress = abs(float(Fk_old @ zeta))
+            ll = 0
+            while True:                                                 # :199-213
+                lk_new = lk_old + delta ** ll * zeta
+                f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
+                zk = 1 / tk * (wk - Htmul(lk_new)); pz = torch.clamp_min(zk, 0.0)
+                if not (f0 + 0.5 * tk * float(pz @ pz) > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
+                    break
+                ll += 1
+            stats["ls_trials"] += ll + 1
+            Fk_new = bk1 * lk_new - Hmul(pz) - wlk                      # :217
+            nFo = nrm(Fk_old); nF = nrm(Fk_new)
+            if verbose:
+                print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={ll:3d} info={list(info)} its={itpcg} res={respcg:.2e}")
+            if nF <= SsN_Tol:
+                break
+            if abs(nFo - nF) < SsN_Tol:                                 # :224
+                break
+            if ssn_it == SsN_IT:
+                break
+            if Fk_res / nF >= 2:
+                Fk_res = nF
+        lk1 = lk_new; uk1 = torch.clamp_min(zk, 0.0); vk1 = uk1 + (uk1 - uk) / ak      # :244
+        kk = kkts(uk1, lk1)
+        rr = [kk[i] / (1 + KKT[0][i]) for i in range(4)]
+        if bk1 < 1e-8 and max(rr) > resk:                               # :253-257
+            uk1 = uk; lk1 = lk; vk1 = uk; bk1 = 10 * bk1
+            kk = kkts(uk1, lk1)
+        bk = bk1; uk = uk1; lk = lk1; vk = vk1                          # :259
+        fxk.append(float(c @ uk[:mn])); KKT.append(kk)
+        stats["ssn_its"].append(ssn_it); stats["lin_its"].append(its)
+        rr = [KKT[k][i] / (1 + KKT[0][i]) for i in range(4)]
+        if verbose:
+            print(f"APD: it={k:3d} KKT(x,y,z,l)={['%.2e' % v for v in rr]} fk={fxk[-1]:.8e} t={time.time() - t_loop:.2f}s")
+        if max(rr) <= KKT_Tol:                                          # :274
+            stats["converged"] = True
+            break
+        if max_outer is not None and k >= max_outer:
+            break
+        if max_seconds is not None and time.time() - t_loop > max_seconds:
+            break
+    torch.cuda.synchronize()
+    return {"uk": uk, "xk": uk[:mn], "lk": lk, "fxk": fxk, "KKT": KKT, "outer_its": k, "rel_kkt": max(rr), "stats": stats,
+            "seconds": time.time() - t_loop, "warmup_seconds": t_warm}
+
+
 def ssn_step(state, amg_options=None, max_ll=500):
     """One semismooth-Newton step of Class1/APD_SsN_Class1.m:137-212 at a fixed APD state:
     fused residual + active set -> ASAt -> Hybrid_AMG -> Armijo line search -> new residual.

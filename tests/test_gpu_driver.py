@@ -62,3 +62,34 @@ def test_fused_warmup_matches_oracle(gpu, oracle, m, n, gama, weights):
     x2, lam2 = drv.warmup_class1_unfused(P["c"], P["r"], P["l"], p, q, gama, 0.0, 40)
     assert np.linalg.norm(x - x2.cpu().numpy()) <= 1e-10 * np.linalg.norm(x_ref)
     assert np.linalg.norm(lam - lam2.cpu().numpy()) <= 1e-7 * np.linalg.norm(l_ref)
+
+
+@pytest.mark.parametrize("kind,size,solver", [("random", (22, 18), 4), ("grid", 6, 4), ("random", (15, 12), 3)])
+def test_class2_partial_ot_solve_matches_oracle(gpu, oracle, kind, size, solver):
+    """Config 3 of BASELINE.json (Class2/APD_SsN_Class2.m: partial OT through AMG4POT / PCG4POT and
+    the invHHt warm start): the device driver against the oracle's restatement, same inputs."""
+    from oracle import driver as odrv
+    drv = __import__("importlib").import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+    if kind == "grid":
+        P = gpu.problems.grid_problem_pot(size, seed=0)
+    else:
+        rs = np.random.RandomState(4)
+        m, n = size
+        l = rs.random_sample(m) + 0.1; r = rs.random_sample(n) + 0.1
+        P = {"c": rs.random_sample(m * n), "r": r, "l": l, "p": np.ones(m), "q": np.ones(n), "phi": np.ones(m * n),
+             "mu": 0.65 * min(r.sum(), l.sum())}
+    u_ref, l_ref = odrv.warmup_class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], 0, 100)
+    u_w, l_w = drv.warmup_class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], 0.0, 100)
+    assert np.linalg.norm(u_w.cpu().numpy() - u_ref) <= 1e-9 * np.linalg.norm(u_ref)
+    assert np.linalg.norm(l_w.cpu().numpy() - l_ref) <= 1e-6 * np.linalg.norm(l_ref)
+    oracle.rng_reset(); gpu.rng_reset()
+    ref = odrv.APD_SsN_Class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], inner_solver=solver)
+    out = drv.APD_SsN_Class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], inner_solver=solver)
+    assert ref["stats"]["converged"] and out["stats"]["converged"]
+    assert out["rel_kkt"] <= 1e-6
+    f_ref, f = ref["fxk"][-1], out["fxk"][-1]
+    assert abs(f - f_ref) <= 1e-6 * max(abs(f_ref), 1e-3)
+    k = min(3, len(ref["fxk"]), len(out["fxk"]))
+    assert np.allclose(out["fxk"][:k], ref["fxk"][:k], rtol=1e-8)
+    x = out["xk"].cpu().numpy()
+    assert x.min() >= 0 and abs(P["phi"] @ x - P["mu"]) <= 1e-5 * (1 + P["mu"])      # transported mass = mu

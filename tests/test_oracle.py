@@ -210,3 +210,25 @@ def test_bundled_solve_summary_fixture():
     d = np.load(os.path.join(GOLDEN, "bundled500_summary.npz"))
     assert int(d["outer_its"]) == 58 and float(d["rel_kkt"]) <= 1e-6
     assert abs(float(d["f"]) - 1.1260464956) < 1e-9 and int(d["nnz"]) == 999       # basic solution, m+n-1
+
+
+def test_class2_partial_ot_oracle_against_highs(oracle):
+    """The oracle's restatement of Class2/APD_SsN_Class2.m (AMG4POT inner solves, invHHt warm start)
+    reaches the optimum of the partial-OT LP  min c'x  s.t. Ax + [y;z] = [r;l], phi'x = mu, x,y,z >= 0
+    found by an independent solver (SciPy HiGHS)."""
+    import scipy.sparse as sp
+    from scipy.optimize import linprog
+    from oracle import driver as odrv
+    rs = np.random.RandomState(3)
+    m, n = 14, 11; N = m + n
+    c = rs.random_sample(m * n); l = rs.random_sample(m) + 0.1; r = rs.random_sample(n) + 0.1
+    phi = np.ones(m * n); mu = 0.65 * min(r.sum(), l.sum())
+    oracle.rng_reset()
+    out = odrv.APD_SsN_Class2(c, r, l, np.ones(m), np.ones(n), mu, phi)
+    assert out["stats"]["converged"] and out["rel_kkt"] <= 1e-6
+    A = oracle.explicit_A(np.ones(m), np.ones(n))
+    Aeq = sp.bmat([[A, sp.identity(N)], [sp.csr_matrix(phi[None, :]), sp.csr_matrix((1, N))]]).tocsr()
+    res = linprog(np.concatenate([c, np.zeros(N)]), A_eq=Aeq, b_eq=np.concatenate([r, l, [mu]]), bounds=(0, None), method="highs")
+    assert res.status == 0
+    assert abs(out["fxk"][-1] - res.fun) <= 1e-6 * max(1.0, abs(res.fun))
+    assert abs(phi @ out["xk"] - mu) <= 1e-6 * (1 + mu)
