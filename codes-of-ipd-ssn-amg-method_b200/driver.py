@@ -377,9 +377,10 @@ def ssn_step_host(hstate, amg_options=None):
     return lk_new.cpu(), Fk_new.cpu(), info
 
 
-def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100):
+def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100, run_to_end=False):
     """Runs the Class1 solve on the device until SsN step ``ssn_it`` of outer iteration ``outer`` and
-    returns the APD state that step reads (a realistic system for benchmarks / parity tests)."""
+    returns the APD state that step reads (a realistic system for benchmarks / parity tests).
+    ``run_to_end`` lets the solve finish instead of stopping there and returns ``(state, solve_result)``."""
     import torch
     box = {}
 
@@ -387,15 +388,18 @@ def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100
         pass
 
     def hook(st):
-        if st["k"] >= outer and st["ssn_it"] >= ssn_it:
+        if not box and st["k"] >= outer and st["ssn_it"] >= ssn_it:
             box.update({"wk": st["wk"].clone(), "lk": st["lk"].clone(), "wlk": st["wlk"].clone(), "bk1": st["bk1"],
                         "tk": st["tk"], "k": st["k"], "ssn_it": st["ssn_it"], "E": st["E"]})
-            raise _Stop()
+            if not run_to_end:
+                raise _Stop()
+    res = None
     try:
-        APD_SsN_Class1(c, r, l, p, q, gama, on_ssn_step=hook, warm_maxit=warm_maxit, max_outer=outer + 1)
+        res = APD_SsN_Class1(c, r, l, p, q, gama, on_ssn_step=hook, warm_maxit=warm_maxit,
+                             max_outer=None if run_to_end else outer + 1)
     except _Stop:
         pass
     if not box:
         raise RuntimeError("the solve converged before the requested state")
     box["p"] = _t(p, torch); box["q"] = _t(q, torch); box["gama"] = float(gama) if np.isscalar(gama) else gama
-    return box
+    return (box, res) if run_to_end else box

@@ -79,3 +79,23 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def bundled_class2_summary():
+    """Summary of the oracle's Class2 solve on the reference's bundled Class2/InputData/data4-500.mat
+    (objective, iteration counts, transported mass) -> bundled500_class2_summary.npz (about 35 s)."""
+    import scipy.io
+    from oracle import driver as odrv
+    d = scipy.io.loadmat("/root/reference/Class2/InputData/data4-500.mat", mat_dtype=True)
+    f = lambda k: np.ascontiguousarray(d[k], dtype=np.float64).reshape(-1)
+    c, r, l, p, q, phi = f("c"), f("r"), f("l"), f("p"), f("q"), f("phi"); mu = float(d["mu"].reshape(-1)[0])
+    oracle.rng_reset()
+    out = odrv.APD_SsN_Class2(c, r, l, p, q, mu, phi)
+    np.savez_compressed(os.path.join(OUT, "bundled500_class2_summary.npz"), outer_its=out["outer_its"], rel_kkt=out["rel_kkt"],
+                        fxk=np.array(out["fxk"]), ssn_its=np.array(out["stats"]["ssn_its"]),
+                        nnz_x=int((out["xk"] > 1e-9).sum()), mass=float(phi @ out["xk"]), mu=mu)
+
+
+if __name__ == "__main__" and "class2" in sys.argv:
+    bundled_class2_summary()
+

@@ -212,6 +212,15 @@ def test_bundled_solve_summary_fixture():
     assert abs(float(d["f"]) - 1.1260464956) < 1e-9 and int(d["nnz"]) == 999       # basic solution, m+n-1
 
 
+def test_bundled_class2_summary_fixture():
+    """The oracle's Class2 solve on the reference's bundled Class2/InputData/data4-500.mat (generated by
+    tests/golden/make_golden.py class2): converges like the reference claims for its own example."""
+    d = np.load(os.path.join(GOLDEN, "bundled500_class2_summary.npz"))
+    assert int(d["outer_its"]) == 53 and float(d["rel_kkt"]) <= 1e-6
+    assert abs(float(d["fxk"][-1]) - 0.25633496670) < 1e-9
+    assert abs(float(d["mass"]) - float(d["mu"])) <= 1e-5 * float(d["mu"])      # transported mass = mu = 161.2933
+
+
 def test_class2_partial_ot_oracle_against_highs(oracle):
     """The oracle's restatement of Class2/APD_SsN_Class2.m (AMG4POT inner solves, invHHt warm start)
     reaches the optimum of the partial-OT LP  min c'x  s.t. Ax + [y;z] = [r;l], phi'x = mu, x,y,z >= 0
