@@ -136,6 +136,12 @@ def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows, trials):
 
 def main():
     args = parse()
+    # Only the final JSON line may reach stdout: libraries (NCCL's version banner, torch warnings) write
+    # to file descriptor 1 directly, so it is pointed at stderr until the result is printed.
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -147,6 +153,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1 and args.impl == "ours":
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import ssnamg
     drv = ssnamg.driver
@@ -307,10 +314,21 @@ def main():
                                              f"on a {slab}-row slab of the {m}x{n} plan scaled x{m // slab} ({cpu_plan:.0f} ms), AMG "
                                              f"solve on the full {m + n}-node system ({cpu_amg:.0f} ms); BLAS threads at default"}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """Prints the one JSON line on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 def load_traffic(which):
@@ -371,7 +389,7 @@ def run_reference(args, state, m, n, workload):
            "data": "synthetic", "impl": "reference", "config": {"workload": workload},
            "cpu_baseline": {"value": ms, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample_txt},
            "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
