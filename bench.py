@@ -250,6 +250,10 @@ def main():
                       "components": int(info["info"][0]), "line_search_trials": int(info["ll"]) + 1, "line_search_passes": int(info.get("ls_passes", 0)),
                       "l2_flush": "inputs larger than L2 (2.1 GB plan vector per pass)", "state_build_s": round(t_state, 1),
                       "sharding": "plan rows over ranks; AMG replicated" if world > 1 else "single GPU"},
+           "breakdown_ms": {"plan_wide_kernels_and_collectives": info.get("ms_plan"), "asat_assembly": info.get("ms_asat"),
+                            "hybrid_amg_replicated": info.get("ms_amg"),
+                            "note": "host-timed phases of the last step (each closed by a device synchronise): the plan-wide "
+                                    "part is what row-sharding divides, the AMG solve is replicated on every rank"},
            "ssn_steps_per_s": 1e3 / ms_step, "gpu_launches": int(launches), "clocks": sampler.summary()}
 
     bytes_pass = 8.0 * k3_rows * n                          # one read of the (slab of the) plan-sized wk

@@ -351,11 +351,19 @@ def ssn_step(state, amg_options=None, max_ll=500):
     wk, lk, wlk, p, q = state["wk"], state["lk"], state["wlk"], state["p"], state["q"]
     bk1, tk, gam = state["bk1"], state["tk"], state.get("gama", float("inf"))
     nu, delta = 0.2, 0.9
+    tm = {"plan": 0.0, "asat": 0.0, "amg": 0.0}
+
+    def lap(key, t0):
+        torch.cuda.synchronize(); tm[key] += (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
     ev = api.prox_residual(wk, lk, p, q, tk, gam, want=("Axprox", "s"))          # :139-144
     Fk_old = bk1 * lk - ev["Axprox"] - wlk
+    lap("plan", t0); t0 = time.perf_counter()
     H0 = api.ASAt(ev["s"], p, q)                                                 # :142
+    lap("asat", t0); t0 = time.perf_counter()
     prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
     zeta, itamg, resamg, info = api.Hybrid_AMG(prob_data, amg_options or CLASS1_AMG_OPTIONS)   # :161
+    lap("amg", t0); t0 = time.perf_counter()
     f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
     cFk_old = f0 + 0.5 * tk * ev["norm2"]
     ress = abs(float(Fk_old @ zeta))
@@ -363,7 +371,8 @@ def ssn_step(state, amg_options=None, max_ll=500):
     lk_new, ll, _, _, passes = api.linesearch(wk, lk, zeta, wlk, p, q, tk, bk1, cFk_old, ress, gam, nu, delta, max_ll)
     ev2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox",))         # :212
     Fk_new = bk1 * lk_new - ev2["Axprox"] - wlk
-    return lk_new, Fk_new, {"E": ev["count"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
+    lap("plan", t0)
+    return lk_new, Fk_new, {"E": ev["count"], "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
                             "nnzH": H0.nnz, "Fk_old_norm": float(torch.linalg.norm(Fk_old)),
                             "Fk_new_norm": float(torch.linalg.norm(Fk_new))}
 

@@ -130,15 +130,20 @@ class ShardedStep:
         return torch.cat([buf[: self.n], rows]), float(buf[self.n]), int(round(float(buf[self.n + 1]))), ev.get("s")
 
     def trial_batch(self, lk, zeta, delta, ll0, nt):
-        """One read of the slab for nt Armijo trials: returns (lamT, values) with values (host) =
-        [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One all_reduce of nt
-        doubles and one device->host read per pass."""
+        """One read-sweep of the slab for nt Armijo trials (8 per kernel launch): returns (lamT, values)
+        with values (host) = [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One
+        all_reduce of nt doubles and one device->host read per batch, however many launches it takes."""
         torch = self.torch
-        lamT, f0 = self.ops.trial_vectors(lk, zeta, self.wlk, delta, ll0, nt)
-        lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
-        part = self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama)
+        lams, f0s, parts = [], [], []
+        for t0 in range(0, nt, 8):
+            k = min(8, nt - t0)
+            lamT, f0 = self.ops.trial_vectors(lk, zeta, self.wlk, delta, ll0 + t0, k)
+            lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
+            parts.append(self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama))
+            lams.append(lamT); f0s.append(f0)
+        part = torch.cat(parts) if len(parts) > 1 else parts[0]
         self._all_reduce(part)
-        return lamT, torch.cat([part, f0]).cpu().tolist()
+        return (torch.cat(lams) if len(lams) > 1 else lams[0]), torch.cat([part] + f0s).cpu().tolist()
 
     def assemble(self, s_loc):
         """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged."""
@@ -152,17 +157,29 @@ class ShardedStep:
         torch = self.torch
         bk1, tk, lk, wlk = self.bk1, self.tk, self.lk, self.wlk
         nu, delta, max_ll = 0.2, 0.9, 500
+        import time as _time
+        tm = {"plan": 0.0, "asat": 0.0, "amg": 0.0}
+        def _lap(key, t0):
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            tm[key] += (_time.perf_counter() - t0) * 1e3
         self.ops.rng_reset()
+        t0 = _time.perf_counter()
         Axp, n2_old, E, s_loc = self.residual(lk, True)                              # :139-144
         Fk_old = bk1 * lk - Axp - wlk
+        _lap("plan", t0); t0 = _time.perf_counter()
         H0 = self.assemble(s_loc)                                                    # :142
+        _lap("asat", t0); t0 = _time.perf_counter()
         prob_data = {"bk1": bk1, "tk": tk, "q": self.q, "p": self.p, "T": None, "H0": H0, "z": -Fk_old}
         zeta, itamg, resamg, info = self.ops.hybrid_amg(prob_data, self.amg_options)  # :161 (replicated)
+        _lap("amg", t0); t0 = _time.perf_counter()
         f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
         cFk_old = f0 + 0.5 * tk * n2_old
         ress = abs(float(Fk_old @ zeta))
-        ll, batch, done, passes = 0, 8, False, 0
-        while not done:                                                              # :189-211, ll = 0 alone, then 8 per pass
+        # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
+        # all_reduce / host round trip as the world grows
+        ll, batch, done, passes = 0, 8 * min(self.world, 4), False, 0
+        while not done:                                                              # :189-211, ll = 0 alone, then a batch per pass
             nt = min(1 if passes == 0 else batch, max_ll - ll + 1)
             lamT, vals = self.trial_batch(lk, zeta, delta, ll, nt); passes += 1
             for t in range(nt):
@@ -174,7 +191,8 @@ class ShardedStep:
                 ll += nt
         Axp2, _, _, _ = self.residual(lk_new, False)                                 # :212
         Fk_new = bk1 * lk_new - Axp2 - wlk
-        return lk_new, Fk_new, {"E": E, "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
+        _lap("plan", t0)
+        return lk_new, Fk_new, {"E": E, "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
                                 "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives}
 
 
