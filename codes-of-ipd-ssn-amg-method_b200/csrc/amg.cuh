@@ -74,7 +74,7 @@ void cf_split(ssn_ctx* c, const CsrView& S, uint8_t* indC, uint8_t* indF);
 Csr flags_to_csr(ssn_ctx* c, const CsrView& A, const uint8_t* as_flags);
 // one coarsening step: returns Ac, Pro (and keeps isC / strength flags if requested)
 void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Csr& Ac, Csr& Pro,
-              Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out);
+              Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out, Csr* Pt_out = nullptr);
 void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o);
 void amg_clear(ssn_ctx* c);
 int coarsest_threshold(int64_t N);

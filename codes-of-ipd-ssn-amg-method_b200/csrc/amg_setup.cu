@@ -557,7 +557,7 @@ AmgOptions resolve_options(const ssn_amg_options* o) {
 }
 
 void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Csr& Ac, Csr& Pro,
-              Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out) {
+              Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out, Csr* Pt_out) {
     SSN_REQUIRE(A.nrows == A.ncols, SSN_E_NOT_SQUARE, "transfer: matrix must be square");
     const int n = A.nrows;
     const bool bigraph = (level_J == 1 && o.bigph);
@@ -620,6 +620,7 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     { Phase ph(c, bigraph ? "setup.galerkin L1 T1*P" : "setup.galerkin Lk T1*P"); Ac = spgemm(c, T1, Pro); }
     if (isC_out) *isC_out = std::move(isC);
     if (as_out) *as_out = std::move(flags);
+    if (Pt_out) *Pt_out = std::move(Pt);                                  // the hierarchy keeps Pro' for the restriction
 }
 
 int coarsest_threshold(int64_t N) {
@@ -667,10 +668,9 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
         SSN_REQUIRE(J < 64, SSN_E_COARSEN_STALL, "coarsening stalled");
         Level nl;
         Buf<uint8_t> isC;
-        transfer(c, H->lv[J - 1].A, o, J, nl.A, nl.P, &isC, nullptr);
+        transfer(c, H->lv[J - 1].A, o, J, nl.A, nl.P, &isC, nullptr, &nl.Pt);
         SSN_REQUIRE(nl.A.nrows < H->lv[J - 1].N, SSN_E_COARSEN_STALL, "coarsening stalled (no F nodes)");
         H->lv[J - 1].isC = std::move(isC);
-        nl.Pt = transpose(c, nl.P);
         finish_level(c, nl, false, 0);
         H->lv.push_back(std::move(nl));
         ++J;
