@@ -395,7 +395,10 @@ __global__ void spgemm_ub_kernel(int nrows, const int* __restrict__ ap, const in
 __global__ void __launch_bounds__(128) spgemm_small_kernel(
     int nrows, const int* __restrict__ ap, const int* __restrict__ ai, const double* __restrict__ av,
     const int* __restrict__ bp, const int* __restrict__ bi, const double* __restrict__ bv, int nwin,
-    const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval, int* __restrict__ cnt_out) {
+    const int* __restrict__ ubptr, int* __restrict__ tidx, double* __restrict__ tval, int* __restrict__ cnt_out,
+    int* __restrict__ nbig_out) {
+    // ubptr == nullptr: optimistic mode -- row r owns the fixed segment [r*kSmallT, (r+1)*kSmallT) and rows
+    // that do not qualify are only counted in nbig_out (the caller then takes the general path)
     __shared__ int s_offs[4][kSmallT + 1];
     __shared__ int s_b0[4][kSmallT];
     __shared__ double s_a[4][kSmallT];
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int row = blockIdx.x * 4 + w; row < nrows; row += gridDim.x * 4) {
         const int a0 = ap[row], a1 = ap[row + 1], lenA = a1 - a0;
+        if (lenA > kSmallT && nbig_out && lane == 0) atomicAdd(nbig_out, 1);
         if (lenA == 0 || lenA > kSmallT) continue;
         int running = 0;
         for (int base = 0; base < lenA; base += 32) {
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
         const int T = running;
-        if (T > kSmallT) continue;                          // a big row: the windowed kernel owns it
+        if (T > kSmallT) { if (nbig_out && lane == 0) atomicAdd(nbig_out, 1); continue; }   // a big row: the windowed kernel owns it
         if (lane == 0) s_offs[w][lenA] = T;
         __syncwarp();
         for (int t = lane; t < T; t += 32) {
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
             s_skey[w][r] = key; s_sval[w][r] = s_val[w][t];
         }
         __syncwarp();
-        const int out0 = ubptr[(size_t)row * nwin];
+        const int out0 = ubptr ? ubptr[(size_t)row * nwin] : row * kSmallT;
         int written = 0;
         for (int base = 0; base < T; base += 32) {
             const int i = base + lane;
@@ -642,7 +646,7 @@ __global__ void compact_items_kernel(int64_t nitems, const int* __restrict__ ubp
     const int lane = threadIdx.x & 31;
     const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (item >= nitems) return;
-    const int src = ubptr[item], dst = cptr[item], len = cptr[item + 1] - dst;
+    const int src = ubptr ? ubptr[item] : (int)item * kSmallT, dst = cptr[item], len = cptr[item + 1] - dst;
     for (int t = lane; t < len; t += 32) { oidx[dst + t] = tidx[src + t]; oval[dst + t] = tval[src + t]; }
 }
 __global__ void gather_rowptr_kernel(int nrows, int nwin, const int* __restrict__ cptr, int* __restrict__ optr) {
@@ -659,6 +663,27 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     if (nrows == 0 || A.nnz == 0 || B.nnz == 0) {
         C.ptr.alloc(c, (size_t)nrows + 1); C.ptr.zero(); C.nnz = 0; C.idx.alloc(c, 0); C.val.alloc(c, 0);
         return C;
+    }
+    // ---- optimistic path (late SsN steps: every row is short): one warp per row writes into a fixed
+    // kSmallT-entry segment, no upper-bound pass and a single host round trip; rows that do not
+    // qualify are counted and, if there are any, the general path below redoes the product.
+    const double avg_products = ((double)A.nnz / (double)nrows) * ((double)B.nnz / (double)(B.nrows > 0 ? B.nrows : 1));
+    if (ncolsB < (1 << 23) && (int64_t)nrows * kSmallT <= ((int64_t)1 << 24) && avg_products <= 192.0) {
+        Buf<int> cnt(c, nrows), cptr(c, (size_t)nrows + 1), nbig(c, 1);
+        Buf<int> tidx(c, (size_t)nrows * kSmallT); Buf<double> tval(c, (size_t)nrows * kSmallT);
+        cnt.zero(); nbig.zero();
+        int grid = cdiv(nrows, 4); if (grid > c->num_sms * 16) grid = c->num_sms * 16;
+        SSN_LAUNCH(c, spgemm_small_kernel, grid, 128, 0, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, 1, nullptr, tidx.p, tval.p,
+                   cnt.p, nbig.p);
+        const int64_t nnz = scan_counts_to_ptr(c, cnt, cptr, nrows);
+        if (read_scalar(c, nbig.p) == 0) {
+            C.nnz = nnz;
+            C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
+            if (C.nnz) SSN_LAUNCH(c, compact_items_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, (int64_t)nrows, nullptr, cptr.p, tidx.p,
+                                  tval.p, C.idx.p, C.val.p);
+            C.ptr = std::move(cptr);
+            return C;
+        }
     }
     // ---- work items: (row, window of W columns).  Few rows with a lot of work each are split into
     // narrow windows so that every SM gets items.
@@ -697,7 +722,8 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     Buf<int> tidx(c, (size_t)ub_total); Buf<double> tval(c, (size_t)ub_total);
     if (small_ok) {
         int grid = cdiv(nrows, 4); if (grid > c->num_sms * 16) grid = c->num_sms * 16;
-        SSN_LAUNCH(c, spgemm_small_kernel, grid, 128, 0, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, nwin, ubptr.p, tidx.p, tval.p, cnt.p);
+        SSN_LAUNCH(c, spgemm_small_kernel, grid, 128, 0, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, nwin, ubptr.p, tidx.p, tval.p, cnt.p,
+                   nullptr);
     }
     if (W > 2048) {
         constexpr int CAP = 2560;
