@@ -236,6 +236,14 @@ def main():
     # dominant HBM-bound kernel, timed alone with CUDA events on the launching stream (sampler still running)
     k3_ms = kernel_ms(lambda: ssnamg.prox_residual(k3_w, k3_lam, k3_p, state["q"], state["tk"], float("inf"), want=("Axprox",)))
     tr_ms = kernel_ms(lambda: ssnamg.prox_trials(k3_w, lam8, k3_p, state["q"], state["tk"], float("inf")))
+    # the kernel the line search of this step actually runs: the screened one, on the step's own direction
+    zeta = info["zeta"]
+    zeta_loc = step_fn._lam_loc(zeta) if world > 1 else zeta
+    slots = max(1.0, float(k3_rows) * n)
+    dens = float(ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 0, 1)[1]) / slots
+    nt_lin = 32 if dens <= 0.10 else 16
+    lin_ms = kernel_ms(lambda: ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 1, nt_lin))
+    lin1_ms = kernel_ms(lambda: ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 0, 1))
     sampler.stop_flag = True; sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
@@ -267,15 +275,20 @@ def main():
                 "launches_per_step": launches, "share_of_step": launches * ms / ms_step,
                 "traffic": None, "frac_of_8TBps_nominal": ach / 8000.0}
     r_k3 = roof("plan_reduce_kernel<PROX> (fused SsN residual: z, prox, Ax(prox), ||prox||^2; one read of wk)", k3_ms, 2)
-    r_tr = roof("plan_trials_kernel<NT=8> (8 Armijo trials per read of wk: z, prox, ||prox||^2 each)", tr_ms, max(passes - 1, 0))
-    r_tr["note"] = ("reads wk once for 8 trials, so its limiter is the fp64 pipe (8 trials x 5 fp64 ops per entry, unit weights), "
-                    "not HBM: ncu shows sm__pipe_fp64_cycles_active 64 %, issue slots 72 % (profiles/trials_full_r1.csv); "
-                    "per trial it moves 1/8 of the bytes of the one-trial-per-pass reference scheme")
+    r_tr = roof("plan_trials_kernel<NT=8> (dense fallback of the line search: 8 Armijo trials per read of wk, every entry evaluated)", tr_ms, 0)
+    r_tr["note"] = ("not launched in this step; used when more than 25 % of the entries survive the screen.  Reads wk once for "
+                    "8 trials, so its limiter is the fp64 pipe, not HBM (profiles/trials_full_r1.csv)")
+    screened = dens <= 0.25
+    r_lin = roof(f"plan_trials_lin_kernel<NT={nt_lin}> (screened line search: {nt_lin} Armijo steps per read of wk; z, prox, ||prox||^2 "
+                 f"evaluated only for the entries where some step can be active, compacted by warp ballot)", lin_ms, max(passes - 1, 0) if screened else 0)
+    r_lin["surviving_entries"] = dens
+    r_lin["first_pass_NT1_ms"] = lin1_ms
     if world == 1:
-        r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials")
-    dominant, other = (r_tr, r_k3) if r_tr["share_of_step"] >= r_k3["share_of_step"] else (r_k3, r_tr)
+        r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials"); r_lin["traffic"] = load_traffic("trials_lin")
+    cands = sorted([r_lin, r_k3, r_tr], key=lambda r: -r["share_of_step"])
+    dominant, other = cands[0], cands[1:]
     out["roofline"] = dominant
-    out["roofline_other"] = [other]
+    out["roofline_other"] = other
     if world > 1:
         out["collectives_per_step"] = int(info.get("collectives", 0)) // max(1, args.steps + max(args.warmup, 3))
     if world == 1:

@@ -51,6 +51,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
+    { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
@@ -226,6 +227,10 @@ int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const doub
 int ssn_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q, int64_t m, int64_t n,
                     double tk, const double* gama, double gama_s, double* n2_out) {
     return guarded(c, [&] { plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, n2_out); sync(c); });
+}
+int ssn_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const double* zeta, const double* p, const double* q,
+                        int64_t m, int64_t n, double tk, double delta, int ll0, int nt, double* out) {
+    return guarded(c, [&] { plan_prox_trials_lin(c, w, lam, zeta, p, q, m, n, tk, delta, ll0, nt, out, nullptr); sync(c); });
 }
 int ssn_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n,
                       const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out) {

@@ -12,6 +12,8 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
 void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q,
                       int64_t m, int64_t n, double tk, const double* gama, double gama_s, double* n2_out_dev,
                       const int* nonunit_dev = nullptr);
+void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const double* zeta, const double* p, const double* q,
+                          int64_t m, int64_t n, double tk, double delta, int ll0, int nt, double* out_dev, const int* nonunit_dev);
 void plan_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta,
                         int ll0, int nt, double* lamT, double* f0_out);
 void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const double* zeta, const double* wlk,

@@ -367,14 +367,14 @@ def ssn_step(state, amg_options=None, max_ll=500):
     f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
     cFk_old = f0 + 0.5 * tk * ev["norm2"]
     ress = abs(float(Fk_old @ zeta))
-    # :189-211, ll = 0 alone, then eight backtracking steps per read of wk
+    # :189-211, ll = 0 alone, then 8-32 backtracking steps per read of wk (adaptive, api.linesearch)
     lk_new, ll, _, _, passes = api.linesearch(wk, lk, zeta, wlk, p, q, tk, bk1, cFk_old, ress, gam, nu, delta, max_ll)
     ev2 = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox",))         # :212
     Fk_new = bk1 * lk_new - ev2["Axprox"] - wlk
     lap("plan", t0)
     return lk_new, Fk_new, {"E": ev["count"], "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
                             "nnzH": H0.nnz, "Fk_old_norm": float(torch.linalg.norm(Fk_old)),
-                            "Fk_new_norm": float(torch.linalg.norm(Fk_new))}
+                            "Fk_new_norm": float(torch.linalg.norm(Fk_new)), "zeta": zeta}
 
 
 def ssn_step_host(hstate, amg_options=None):

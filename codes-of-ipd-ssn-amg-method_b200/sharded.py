@@ -37,6 +37,9 @@ class _CudaOps:
     def prox_trials(self, w, lamT, p, q, tk, gama):
         return self.api.prox_trials(w, lamT, p, q, tk, gama)
 
+    def prox_trials_lin(self, w, lam, zeta, p, q, tk, delta, ll0, nt):
+        return self.api.prox_trials_lin(w, lam, zeta, p, q, tk, delta, ll0, nt)
+
     def trial_vectors(self, lam, zeta, wlk, delta, ll0, nt):
         return self.api.trial_vectors(lam, zeta, wlk, delta, ll0, nt)
 
@@ -78,6 +81,7 @@ class ShardedStep:
         self.amg_options = amg_options
         self.counts = [row_range(g, world, m)[1] - row_range(g, world, m)[0] for g in range(world)]
         self.collectives = 0
+        self.screen = True
 
     # ---- slab-local view of a dual vector [column part (n) ; row part (m)]
     def _lam_loc(self, lam):
@@ -129,21 +133,37 @@ class ShardedStep:
         rows = self._all_gather_rows(ax[self.n:])
         return torch.cat([buf[: self.n], rows]), float(buf[self.n]), int(round(float(buf[self.n + 1]))), ev.get("s")
 
-    def trial_batch(self, lk, zeta, delta, ll0, nt):
-        """One read-sweep of the slab for nt Armijo trials (8 per kernel launch): returns (lamT, values)
-        with values (host) = [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One
-        all_reduce of nt doubles and one device->host read per batch, however many launches it takes."""
+    def trial_batch(self, lk, zeta, delta, ll0, nt, screened=False):
+        """One read-sweep of the slab for nt Armijo trials: returns (lamT, values, density) with values
+        (host) = [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One all_reduce of nt
+        (+1) doubles and one device->host read per batch, however many launches it takes.  screened: the
+        slab goes through the screened kernel (32 steps per launch, gama = Inf), whose count of surviving
+        entries rides in the same all_reduce and comes back as density = share of the plan's entries."""
         torch = self.torch
         lams, f0s, parts = [], [], []
-        for t0 in range(0, nt, 8):
-            k = min(8, nt - t0)
+        per = 32 if screened else 8
+        votes = None
+        for t0 in range(0, nt, per):
+            k = min(per, nt - t0)
             lamT, f0 = self.ops.trial_vectors(lk, zeta, self.wlk, delta, ll0 + t0, k)
-            lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
-            parts.append(self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama))
+            if screened:
+                out = self.ops.prox_trials_lin(self.w_loc, self._lam_loc(lk), self._lam_loc(zeta), self.p_loc, self.q, self.tk,
+                                               delta, ll0 + t0, k)
+                parts.append(out[:k]); votes = out[k:k + 1] if votes is None else votes + out[k:k + 1]
+            else:
+                lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
+                parts.append(self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama))
             lams.append(lamT); f0s.append(f0)
+        if votes is not None:
+            parts.append(votes)
         part = torch.cat(parts) if len(parts) > 1 else parts[0]
         self._all_reduce(part)
-        return (torch.cat(lams) if len(lams) > 1 else lams[0]), torch.cat([part] + f0s).cpu().tolist()
+        vals = torch.cat([part[:nt]] + f0s).cpu().tolist()
+        dens = None
+        if votes is not None:
+            launches = (nt + per - 1) // per
+            dens = float(part[nt]) / launches / max(1.0, float(self.m) * self.n)
+        return (torch.cat(lams) if len(lams) > 1 else lams[0]), vals, dens
 
     def assemble(self, s_loc):
         """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged."""
@@ -177,11 +197,18 @@ class ShardedStep:
         cFk_old = f0 + 0.5 * tk * n2_old
         ress = abs(float(Fk_old @ zeta))
         # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
-        # all_reduce / host round trip as the world grows
-        ll, batch, done, passes = 0, 8 * min(self.world, 4), False, 0
+        # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernel, whose vote
+        # count says how sparse the trial plans are -- 32 steps per launch while under 10 % of the entries
+        # survive the screen, 16 under 25 %, else the dense 8-step kernel (api.linesearch makes the same choice)
+        screened = np.isinf(self.gama) and self.gama > 0 and hasattr(self.ops, "prox_trials_lin") and self.screen
+        ll, done, passes, dens = 0, False, 0, 1.0
         while not done:                                                              # :189-211, ll = 0 alone, then a batch per pass
-            nt = min(1 if passes == 0 else batch, max_ll - ll + 1)
-            lamT, vals = self.trial_batch(lk, zeta, delta, ll, nt); passes += 1
+            lin = screened and (passes == 0 or dens <= 0.25)
+            per = (32 if dens <= 0.10 else 16) if (lin and passes > 0) else 8
+            nt = min(1 if passes == 0 else per * min(self.world, 4), max_ll - ll + 1)
+            lamT, vals, d = self.trial_batch(lk, zeta, delta, ll, nt, screened=lin); passes += 1
+            if d is not None:
+                dens = d
             for t in range(nt):
                 f0 = bk1 / 2 * vals[nt + 2 * t] - vals[nt + 2 * t + 1]
                 if not (f0 + 0.5 * tk * vals[t] > cFk_old - nu * delta ** (ll + t) * ress) or ll + t == max_ll:
@@ -193,7 +220,7 @@ class ShardedStep:
         Fk_new = bk1 * lk_new - Axp2 - wlk
         _lap("plan", t0)
         return lk_new, Fk_new, {"E": E, "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
-                                "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives}
+                                "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives, "zeta": zeta}
 
 
 def make_sharded_step(state, rank, world, **kw):

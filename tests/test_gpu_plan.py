@@ -206,6 +206,57 @@ def test_prox_trials_equal_single_trial_kernel(gpu, m, n, gama):
         assert np.array_equal(got, ref), (nt, got, ref)
 
 
+@pytest.mark.parametrize("m,n", [(7, 5), (250, 130), (1027, 517), (2048, 300)])
+@pytest.mark.parametrize("unit", [True, False])
+@pytest.mark.parametrize("shift", [0.0, 3.0])
+def test_screened_trials_equal_dense_trials(gpu, m, n, unit, shift):
+    """The screened kernel (up to 32 backtracking steps of one direction per read of w, entries whose
+    first and last trial residuals are safely negative skipped) against the dense batched kernel on the
+    same trial vectors: same per-entry arithmetic on the surviving entries, same reduction order =>
+    the same bits.  shift = 3 makes the trial plans sparse (few entries with z > 0), the regime the
+    screen is for; shift = 0 keeps about half of the entries active."""
+    rs = np.random.RandomState(5 * m + n)
+    w = rs.standard_normal(m * n) - shift
+    p, q = (np.ones(m), np.ones(n)) if unit else weights(m, n, 3, False)
+    lam = 0.3 * rs.standard_normal(n + m); zeta = 0.5 * rs.standard_normal(n + m); wlk = rs.standard_normal(n + m)
+    total = float(m * n)
+    for ll0, nt in ((0, 1), (0, 8), (3, 5), (1, 16), (40, 13), (0, 32), (7, 27)):
+        got = gpu.prox_trials_lin(w, lam, zeta, p, q, 0.8, 0.9, ll0, nt).cpu().numpy()
+        ref = []
+        for t0 in range(0, nt, 8):
+            k = min(8, nt - t0)
+            lamT, _ = gpu.trial_vectors(lam, zeta, wlk, 0.9, ll0 + t0, k)
+            ref.append(gpu.prox_trials(w, lamT, p, q, 0.8, np.inf).cpu().numpy())
+        ref = np.concatenate(ref)
+        assert np.array_equal(got[:nt], ref), (ll0, nt, got[:nt], ref)
+        assert 0 <= got[nt] <= total
+    if shift > 0 and m * n > 10000:
+        assert got[nt] < 0.1 * total                  # the screen does skip most entries when the plan is sparse
+
+
+def test_adaptive_linesearch_equals_fixed_batches(gpu):
+    """ssn_linesearch with batch = 0 (screened kernel, 16/32 steps per pass) accepts the same step with the
+    same bits as batch = 8 (dense kernel)."""
+    import torch
+    m, n = 640, 520
+    rs = np.random.RandomState(11)
+    p, q = np.ones(m), np.ones(n)
+    w = rs.standard_normal(m * n) - 2.5; lam = 0.2 * rs.standard_normal(n + m); wlk = rs.standard_normal(n + m)
+    tk, bk1, nu, delta = 0.7, 0.3, 0.2, 0.9
+    ev = gpu.prox_residual(w, lam, p, q, tk, np.inf, want=("Axprox",))
+    axp = ev["Axprox"]
+    grad = bk1 * lam - wlk - (axp.cpu().numpy() if hasattr(axp, "cpu") else np.asarray(axp))
+    cF_old = bk1 / 2 * (lam @ lam) - wlk @ lam + 0.5 * tk * ev["norm2"]
+    for scale, ll_max in ((0.5, 500), (300.0, 500), (5000.0, 500), (-30.0, 45), (-30.0, 500)):
+        zeta = -scale * grad
+        ress = abs(float(grad @ zeta))
+        a = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max, batch=8)
+        b = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max, batch=0)
+        assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3], (scale, a[1:], b[1:])
+        assert torch.equal(a[0], b[0])
+        assert b[4] <= a[4]
+
+
 def test_linesearch_matches_trial_by_trial_loop(gpu, oracle):
     """ssn_linesearch (ll = 0 alone, then 8 trials per pass) against the reference's trial-by-trial Armijo loop
     (Class1/APD_SsN_Class1.m:182-211) evaluated with the oracle."""
@@ -227,7 +278,7 @@ def test_linesearch_matches_trial_by_trial_loop(gpu, oracle):
             if not (cF(lk_new) > cF_old - nu * delta ** ll * ress) or ll == ll_max:
                 break
             ll += 1
-        out, ll_dev, n2, cF_new, passes = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max)
+        out, ll_dev, n2, cF_new, passes = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max, batch=8)
         assert ll_dev == ll, (scale, ll_dev, ll)
         assert passes == 1 + (ll + 7) // 8
         assert np.array_equal(out.cpu().numpy(), lk_new)

@@ -46,6 +46,12 @@ class OracleOps:
     def prox_trials(self, w, lamT, p, q, tk, gama):
         return torch.tensor([self.prox_residual(w, l, p, q, tk, gama, ())["norm2"] for l in lamT], dtype=torch.float64)
 
+    def prox_trials_lin(self, w, lam, zeta, p, q, tk, delta, ll0, nt):
+        lam, zeta = torch.as_tensor(lam), torch.as_tensor(zeta)
+        vals = [self.prox_residual(w, lam + delta ** (ll0 + t) * zeta, p, q, tk, np.inf, ()) for t in range(nt)]
+        slots = float(self._np(w).size)                                # the oracle screens nothing: every entry survives
+        return torch.tensor([v["norm2"] for v in vals] + [slots], dtype=torch.float64)
+
     def trial_vectors(self, lam, zeta, wlk, delta, ll0, nt):
         lamT = torch.stack([lam + delta ** (ll0 + t) * zeta for t in range(nt)])
         f0 = torch.stack([v for t in range(nt) for v in (lamT[t] @ lamT[t], wlk @ lamT[t])])
