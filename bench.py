@@ -241,9 +241,13 @@ def main():
     zeta_loc = step_fn._lam_loc(zeta) if world > 1 else zeta
     slots = max(1.0, float(k3_rows) * n)
     dens = float(ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 0, 1)[1]) / slots
-    nt_lin = 32 if dens <= 0.10 else 16
-    lin_ms = kernel_ms(lambda: ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 1, nt_lin))
-    lin1_ms = kernel_ms(lambda: ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 0, 1))
+    nt_lin = 64 if dens <= 0.10 else 16
+    lin_call = lambda: ssnamg.prox_trials_lin(k3_w, k3_lam, zeta_loc, k3_p, state["q"], state["tk"], 0.9, 1, nt_lin)
+    lin_ms = kernel_ms(lin_call)                            # plan_trials_screen_kernel alone (the plan-wide kernel of a batch)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10):
+        lin_call()                                          # synchronous: screen + scan + host read + compact + eval + finish
+    torch.cuda.synchronize(); lin_batch_ms = (time.perf_counter() - t0) * 1e3 / 10
     sampler.stop_flag = True; sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
@@ -279,15 +283,22 @@ def main():
     r_tr["note"] = ("not launched in this step; used when more than 25 % of the entries survive the screen.  Reads wk once for "
                     "8 trials, so its limiter is the fp64 pipe, not HBM (profiles/trials_full_r1.csv)")
     screened = dens <= 0.25
-    r_lin = roof(f"plan_trials_lin_kernel<NT={nt_lin}> (screened line search: {nt_lin} Armijo steps per read of wk; z, prox, ||prox||^2 "
-                 f"evaluated only for the entries where some step can be active, compacted by warp ballot)", lin_ms, max(passes - 1, 0) if screened else 0)
+    r_lin = roof("plan_trials_screen_kernel (screened line search: one read of wk per batch of Armijo steps marks the entries where some "
+                 "step of the batch can be active; ~7 fp64 operations per entry whatever the batch size)", lin_ms, max(passes - 1, 0) if screened else 0)
     r_lin["surviving_entries"] = dens
-    r_lin["first_pass_NT1_ms"] = lin1_ms
+    r_lin["batch_steps"] = nt_lin
+    r_lin["batch_ms_host_timed"] = lin_batch_ms
+    r_lin["share_of_step"] = r_lin["launches_per_step"] * lin_batch_ms / ms_step
+    r_lin["note"] = (f"a batch of {nt_lin} steps = this kernel + candidate scan/compact/eval kernels on the surviving entries + the host "
+                     f"round trip that sizes the candidate list: {lin_batch_ms:.3f} ms in all (host-timed, synchronous call); "
+                     "share_of_step uses that figure")
     if world == 1:
         r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials"); r_lin["traffic"] = load_traffic("trials_lin")
     cands = sorted([r_lin, r_k3, r_tr], key=lambda r: -r["share_of_step"])
     dominant, other = cands[0], cands[1:]
     out["roofline"] = dominant
+    if world == 1:
+        out["dominant_by_time"] = amg_kernel_share(ssnamg, drv, state, ms_step)
     out["roofline_other"] = other
     if world > 1:
         out["collectives_per_step"] = int(info.get("collectives", 0)) // max(1, args.steps + max(args.warmup, 3))
@@ -355,6 +366,38 @@ def load_traffic(which):
         return float(d[which]["dram_bytes_per_launch"])
     except Exception:
         return None
+
+
+def amg_kernel_share(ssnamg, drv, state, ms_step):
+    """The kernel with the largest share of the step when the line search is short: Class_AMG's solve loop as one
+    persistent cooperative kernel.  It is latency-bound (about 115 grid-wide passes per W-cycle, each a few
+    microseconds of dependent L2 round trips and one grid barrier), so it is reported by time, not by an HBM
+    fraction.  Times from the library's phase profiler (host-timed, synchronised phases)."""
+    import torch
+    ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
+    H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"])
+    Fk = state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"]
+    pd = {"bk1": state["bk1"], "tk": state["tk"], "q": state["q"], "p": state["p"], "T": None, "H0": H0, "z": -Fk}
+    ssnamg.profile(True)
+    reps = 3
+    for _ in range(reps):
+        ssnamg.rng_reset(); _, itamg, _, _ = ssnamg.Hybrid_AMG(pd, drv.CLASS1_AMG_OPTIONS)
+    torch.cuda.synchronize()
+    dump = ssnamg.profile_dump()
+    ssnamg.profile(False)
+    phases = {}
+    for line in dump.splitlines():
+        parts = line.split()
+        if len(parts) >= 4 and parts[-2] == "calls" and "#launches" not in line:
+            try:
+                phases[" ".join(parts[:-3])] = float(parts[-3]) / reps
+            except ValueError:
+                pass
+    k = phases.get("solve.persist_solve_kernel")
+    return {"kernel": "persist_solve_kernel (Class_AMG.m:89-107 + MG_Wcycle.m as one cooperative kernel)", "bound": "latency (grid barriers)",
+            "ms_per_step": k, "share_of_step": (k / ms_step) if k else None, "wcycles": int(itamg),
+            "ms_per_wcycle": (k / itamg) if k and itamg else None,
+            "amg_setup_ms": phases.get("amg_setup total"), "amg_solve_loop_ms": phases.get("class_amg solve loop total")}
 
 
 def secondary_metrics(ssnamg, drv, state, m, n):

@@ -256,9 +256,10 @@ def prox_trials(w, lamT, p, q, tk, gama=np.inf):
 
 
 def prox_trials_lin(w, lam, zeta, p, q, tk, delta, ll0, nt):
-    """``||prox((w - Aty(lam + delta**(ll0+t)*zeta))/tk)||^2`` for ``t < nt <= 32`` backtracking steps of one
-    search direction in one read of ``w`` (``gama = Inf``), through the screened kernel: the same bits as
-    ``prox_trials`` on the same trial vectors, HBM-bound for any ``nt`` where the trial plans are sparse.
+    """``||prox((w - Aty(lam + delta**(ll0+t)*zeta))/tk)||^2`` for ``t < nt <= 128`` backtracking steps of one
+    search direction in one read of ``w`` (``gama = Inf``), through the screened kernels: the values of
+    ``prox_trials`` on the same trial vectors up to the summation order, HBM-bound for any ``nt`` where the
+    trial plans are sparse.
     Returns a device tensor of ``nt + 1`` doubles: the squared norms and the number of entries that
     survived the screen (out of ``m*n``)."""
     torch = _torch(); ctx = context()
@@ -318,7 +319,7 @@ def apd_end(c, wk, xk, lam, p, q, tk, ak, gama=np.inf):
 
 
 def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
-    """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 32) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
+    """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 128) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
     as device tensors -- the O(m+n) half of a batch of Armijo trials."""
     torch = _torch(); ctx = context()
     ld, zd, wd = _dev(lam), _dev(zeta), _dev(wlk)
@@ -331,9 +332,8 @@ def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
 
 def linesearch(w, lam_old, zeta, wlk, p, q, tk, bk1, cF_old, ress, gama=np.inf, nu=0.2, delta=0.9, ll_max=500, batch=0):
     """Armijo backtracking of Class1/APD_SsN_Class1.m:182-211 with ``batch`` (1..8) backtracking steps per
-    read of ``w`` (the full step ll = 0 is tried alone first); ``batch = 0`` (default) is adaptive: 8, 16
-    or 32 steps per read through the screened kernel, by the measured sparsity of the trial plans --
-    the accepted step and its values are the same bits either way.
+    read of ``w`` (the full step ll = 0 is tried alone first); ``batch = 0`` (default) is adaptive: 8 to 128
+    steps per read through the screened kernels, by the measured sparsity of the trial plans.
     Returns ``(lk_new, ll, norm2, cF_new, passes)``."""
     torch = _torch(); ctx = context()
     pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()

@@ -51,6 +51,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
+    { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }

@@ -61,6 +61,7 @@ struct ssn_ctx {
     int64_t persist_max_nnz = (int64_t)1 << 40;   // SSN_PERSIST_MAXNNZ: above this the cycle is launched kernel by kernel
     bool persist = true;                  // SSN_PERSIST=0: launch the large-level cycle kernel by kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
+    int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
     int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
     // CUDA-event timer around the launches of the plan-wide kernels (ssn_kernel_timer): bench.py's roofline

@@ -416,87 +416,76 @@ __global__ void __launch_bounds__(kThreads, 2) plan_trials_kernel(const TrialArg
 
 // ------------------------------------------------------------------ screened line-search trials
 // The same quantity for NT <= 32 backtracking steps lam_t = lam + alpha_t*zeta of ONE search
-// direction, with per-entry work that does not grow with NT where the trial plans are sparse.
+// direction, with per-entry streaming work that does not depend on NT.
 // An entry contributes to trial t only if z_t > 0.  w - Aty(lam + alpha*zeta) is linear in alpha up
 // to rounding, so if the literal residuals of the FIRST and of the LAST trial of the batch are both
 // below -tol (tol = 2^-40 of the operand magnitudes, ~4000x the rounding of the expression) every
-// trial of the batch has z_t < 0 there and the entry adds exactly 0 to every norm.  Entries that
-// survive the screen ("candidates", a few per column in the late phase of a solve) are compacted by
-// warp ballot into a per-warp queue in shared memory; whenever 32 are queued the warp evaluates
-// them lane-parallel: the NT literal expressions, operation for operation those of the single-trial
-// kernel (lam_t = lam + alpha_t*zeta rounded as trial_vectors_kernel does), accumulated into the
-// OWNER lane's per-trial accumulator (shared memory) in the owner's original entry order -- so the
-// norms are bit-identical to plan_trials_kernel's, while the streaming part of the kernel costs
-// ~7 fp64 operations per entry whatever NT is and stays HBM-bound.
+// trial of the batch has z_t < 0 there and the entry adds exactly 0 to every norm.  Kernels:
+//   screen   streams w once (HBM-bound, ~7 fp64 operations per entry whatever NT is) and writes one
+//            bit per entry -- "candidate": survived the screen -- as coalesced 32-bit words
+//            [block][word][thread], plus the block's candidate count;
+//   compact  turns the bits into ONE list of (column, row) pairs in a fixed order (block, thread,
+//            word, bit) after a scan of the block counts;
+//   eval     walks the list grid-strided: per candidate one gather of w and the literal expression
+//            of every step (lam_t = lam + alpha_t*zeta rounded as trial_vectors_kernel does, then
+//            the operations of the single-trial kernel), per-thread accumulators, fixed-order
+//            reduction -- deterministic, and balanced over the whole GPU.  The candidates of a
+//            late-phase plan sit in the few warps that own its support: evaluating them where
+//            they were streamed (in-kernel queue per warp, or one thread per owner) left the rest
+//            of the grid idle and ran 2-5x slower than the dense kernel it was meant to beat.
+// Only entries that add exactly 0 to every norm are dropped, so the result differs from the dense
+// kernel's by the summation order alone (a few ulp).
 // max(z,0)^2 is accumulated as (z+|z|)^2 = 4*max(z,0)^2 (exact scaling, undone by the finish kernel).
-constexpr int kMaxLinTrials = 32;
-constexpr int kLinQueue = 64;                 // per-warp candidate queue (ring), entries
+constexpr int kMaxLinTrials = 32;            // steps per evaluation launch
+constexpr int kMaxLinBatch = 128;            // steps per screened batch (one read of w)
 struct TrialLinArgs {
     const double* w; const double* p; const double* q;
     const double* lam; const double* zeta;    // [n+m]: [column part ; row part] of lam_old and of the direction
     double inv_tk;
     int64_t m, n;
-    int cols_per_chunk;
-    double* scalpart;       // [num_blocks][NT]   (4x the block's share of ||prox||^2)
-    double* votepart;       // [num_blocks]       candidate entries of the block
+    int cols_per_chunk, words;                // words = ceil(cols_per_chunk / 8): 32-bit mask words per thread
+    unsigned* mask;         // [num_blocks][words][kThreads]
+    double* scalpart;       // [evaluation blocks][NT]   (4x the block's share of ||prox||^2)
+    double* votepart;       // [num_blocks]              candidate entries of the block
     const int* nonunit;
     double alpha[kMaxLinTrials];              // slots >= the valid count repeat the last valid step
 };
 
-template <bool VEC, int NT, bool UNITW>
-__device__ __forceinline__ void trials_lin_body(const TrialLinArgs& a, double* dsm) {
+template <bool VEC, bool UNITW>
+__device__ __forceinline__ void trials_screen_body(const TrialLinArgs& a, double al_f, double al_l, double* dsm) {
     __shared__ double red[32];
     const int cpc = a.cols_per_chunk;
-    constexpr bool COMPACT = NT > 1;          // NT == 1: candidates are evaluated in place (cheap at any density)
-    double* lamr = dsm;                       // [1024] row parts of lam
-    double* zetr = lamr + kGroupRows;         // [1024] row parts of zeta
-    double* lamc = zetr + kGroupRows;         // [cpc] column parts ...
-    double* zetc = lamc + cpc;
-    double* yfc = zetc + cpc;                 // ... of the first and of the last trial vector
+    double* yfc = dsm;                        // [cpc] column parts of the first and of the last trial vector
     double* ylc = yfc + cpc;
     double* qs = ylc + cpc;
-    double* n2s = qs + cpc;                   // COMPACT: [NT][kThreads] accumulators
-    double* qwv = n2s + (COMPACT ? NT * kThreads : 0);                     // COMPACT: [kWarps][kLinQueue] queued w values
-    unsigned* qmeta = reinterpret_cast<unsigned*>(qwv + kWarps * kLinQueue);   //          [kWarps][kLinQueue] column | row slot << 16
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int chunk = blockIdx.x, group = blockIdx.y;
     const int64_t m = a.m, n = a.n;
     const int64_t c0 = (int64_t)chunk * cpc;
     const int64_t c1 = (c0 + cpc < n) ? (c0 + cpc) : n;
     const int64_t rbase = ((int64_t)group * kWarps + warp) * kStripRows;
-    const int lrow0 = warp * kStripRows + (VEC ? 2 * lane : lane);
-    const int64_t row0 = (int64_t)group * kGroupRows + lrow0;
-    const double al_f = a.alpha[0], al_l = a.alpha[NT - 1];
+    const int64_t row0 = rbase + (VEC ? 2 * lane : lane);
     bool rok[4];
-    double pv[4];
+    double pv[4], yfi[4], yli[4];             // weights and first / last trial vector at the lane's four rows
+    double mag = 0.0, wmag = 1.0;             // largest |lam|+|alpha_0*zeta| and largest weight of the block
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t r = row0 + roff<VEC>(k);
         rok[k] = r < m;
         pv[k] = (!UNITW && rok[k]) ? a.p[r] : 0.0;
-    }
-    double mag = 0.0, wmag = 1.0;             // largest |lam|+|alpha_0*zeta| and largest weight of the block
-    for (int i = threadIdx.x; i < kGroupRows; i += kThreads) {
-        const int64_t r = (int64_t)group * kGroupRows + i;
-        const double l = (r < m) ? a.lam[n + r] : 0.0, z = (r < m) ? a.zeta[n + r] : 0.0;
-        lamr[i] = l; zetr[i] = z;
+        const double l = rok[k] ? a.lam[n + r] : 0.0, z = rok[k] ? a.zeta[n + r] : 0.0;
+        yfi[k] = __dadd_rn(l, __dmul_rn(al_f, z)); yli[k] = __dadd_rn(l, __dmul_rn(al_l, z));
         mag = fmax(mag, fabs(l) + fabs(al_f * z));
-        if (!UNITW && r < m) wmag = fmax(wmag, fabs(a.p[r]));
+        if (!UNITW) wmag = fmax(wmag, fabs(pv[k]));
     }
     for (int j = threadIdx.x; j < cpc; j += kThreads) {
         const bool ok = c0 + j < c1;
         const double l = ok ? a.lam[c0 + j] : 0.0, z = ok ? a.zeta[c0 + j] : 0.0;
-        lamc[j] = l; zetc[j] = z;
         yfc[j] = __dadd_rn(l, __dmul_rn(al_f, z)); ylc[j] = __dadd_rn(l, __dmul_rn(al_l, z));
         const double qj = ok ? a.q[c0 + j] : 0.0;
         qs[j] = qj;
         mag = fmax(mag, fabs(l) + fabs(al_f * z));
         if (!UNITW) wmag = fmax(wmag, fabs(qj));
-    }
-    if (COMPACT) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) n2s[t * kThreads + threadIdx.x] = 0.0;
     }
     // block-wide maxima (NaN/Inf only widen the margin)
 #pragma unroll
@@ -512,58 +501,13 @@ __device__ __forceinline__ void trials_lin_body(const TrialLinArgs& a, double* d
     constexpr double kScreen = 9.094947017729282e-13;          // 2^-40
     const double tol0 = kScreen * (2.0 * wmag * mag);
 
-    double n2 = 0.0;                                           // NT == 1 accumulator
-    // row parts of the first and of the last trial vector of the lane's four rows
-    double yfi[4], yli[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int lr = lrow0 + roff<VEC>(k);
-        yfi[k] = __dadd_rn(lamr[lr], __dmul_rn(al_f, zetr[lr])); yli[k] = __dadd_rn(lamr[lr], __dmul_rn(al_l, zetr[lr]));
-    }
-    int cands = 0;                                             // warp-uniform count of candidate entries
-    int qhead = 0, qcount = 0;                                 // warp-uniform ring state
-    double* myq = qwv + warp * kLinQueue;
-    unsigned* mym = qmeta + warp * kLinQueue;
+    const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned* mword = a.mask + b * (size_t)a.words * kThreads + threadIdx.x;
+    unsigned bits = 0u;
+    int cands = 0;
     const bool strip_full = (rbase + kStripRows <= m);
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
     const size_t step = 2 * (size_t)m;
-
-    // literal evaluation of one entry for trial step al:  2*max(z,0)
-    auto eval2 = [&](double wv, double lj, double zj, double li, double zi, double pvv, double qj, double al) {
-        const double y1 = __dadd_rn(lj, __dmul_rn(al, zj));                  // lk_old + delta^ll*zeta
-        const double y2 = __dadd_rn(li, __dmul_rn(al, zi));
-        const double aty = UNITW ? __dadd_rn(y1, y2) : __dadd_rn(__dmul_rn(pvv, y1), __dmul_rn(y2, qj));
-        const double z = __dmul_rn(a.inv_tk, __dsub_rn(wv, aty));
-        return __dadd_rn(z, fabs(z));                                        // 2*max(z,0), exact
-    };
-
-    // evaluates the first cnt (<= 32) queued candidates, one per lane, for all NT steps
-    auto flush = [&](int cnt) {
-        __syncwarp();
-        const bool act = lane < cnt;
-        const int pos = (qhead + lane) & (kLinQueue - 1);
-        const double wv = act ? myq[pos] : 0.0;
-        const unsigned meta = act ? mym[pos] : 0u;
-        const int jc = (int)(meta & 0xffffu), lr = (int)(meta >> 16);
-        const int owner = VEC ? ((lr & 63) >> 1) : (lr & 31);                // lane that streamed the entry
-        // several candidates of one owner in the batch: accumulate them one round at a time, in queue order
-        const unsigned same = __match_any_sync(0xffffffffu, act ? owner : (32 + lane));
-        const int rank = __popc(same & lt_mask);
-        const int rounds = __reduce_max_sync(0xffffffffu, act ? rank + 1 : 0);
-        const double lj = lamc[jc], zj = zetc[jc], li = lamr[lr], zi = zetr[lr];
-        const double qj = UNITW ? 0.0 : qs[jc];
-        const double pvv = (UNITW || !act) ? 0.0 : a.p[(int64_t)group * kGroupRows + lr];
-        double* acc0 = n2s + warp * 32 + owner;
-#pragma unroll 4
-        for (int t = 0; t < NT; ++t) {
-            const double t2 = eval2(wv, lj, zj, li, zi, pvv, qj, a.alpha[t]);
-            double* acc = acc0 + t * kThreads;
-            for (int r = 0; r < rounds; ++r) {
-                if (act && rank == r) *acc = fma(t2, t2, *acc);
-                __syncwarp();
-            }
-        }
-    };
 
     auto load_batch = [&](double (&v)[2][4], int64_t c, size_t o) {
         const bool full = strip_full && (c + 2 <= c1);
@@ -585,8 +529,10 @@ __device__ __forceinline__ void trials_lin_body(const TrialLinArgs& a, double* d
         }
     };
 
+    // screens the 8 entries of a batch into bits [8*(batch & 3) + 4*cc + k] of the current mask word
     auto compute_batch = [&](auto full_tag, const double (&v)[2][4], int64_t c) {
         constexpr bool FULL = decltype(full_tag)::value;
+        const int sh = (int)(((c - c0) >> 1) & 3) * 8;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             const bool cok = FULL || (c + cc < c1);
@@ -604,22 +550,7 @@ __device__ __forceinline__ void trials_lin_body(const TrialLinArgs& a, double* d
                 const double uf = (wv - af) + tol, ul = (wv - a_l) + tol;
                 // both strictly negative (sign bits set) -> no trial of the batch is active at this entry
                 const bool cand = live && ((__double2hiint(uf) & __double2hiint(ul)) >= 0);
-                const unsigned mask = __ballot_sync(0xffffffffu, cand);
-                if (mask != 0u) {
-                    const int lr = lrow0 + roff<VEC>(k);
-                    cands += __popc(mask);
-                    if (COMPACT) {
-                        if (cand) {
-                            const int pos = (qhead + qcount + __popc(mask & lt_mask)) & (kLinQueue - 1);
-                            myq[pos] = wv; mym[pos] = (unsigned)jc | ((unsigned)lr << 16);
-                        }
-                        qcount += __popc(mask);
-                        if (qcount >= 32) { flush(32); qhead = (qhead + 32) & (kLinQueue - 1); qcount -= 32; }
-                    } else {
-                        const double t2 = eval2(wv, lamc[jc], zetc[jc], lamr[lr], zetr[lr], pv[k], qj, a.alpha[0]);
-                        n2 = fma(live ? t2 : 0.0, live ? t2 : 0.0, n2);
-                    }
-                }
+                bits |= (cand ? 1u : 0u) << (sh + 4 * cc + k);
             }
         }
     };
@@ -630,35 +561,135 @@ __device__ __forceinline__ void trials_lin_body(const TrialLinArgs& a, double* d
         if (c + 2 < c1) load_batch(vnxt, c + 2, off + step);
         if (strip_full && (c + 2 <= c1)) compute_batch(std::true_type(), vcur, c);
         else                             compute_batch(std::false_type(), vcur, c);
+        if ((((c - c0) >> 1) & 3) == 3 || c + 2 >= c1) {         // word complete (8 columns) or last batch of the chunk
+            mword[(size_t)((c - c0) >> 3) * kThreads] = bits;
+            cands += __popc(bits);
+            bits = 0u;
+        }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) vcur[cc][k] = vnxt[cc][k];
         }
     }
-    if (COMPACT && qcount > 0) flush(qcount);
-    __syncwarp();
-    const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-#pragma unroll 1
-    for (int t = 0; t < NT; ++t) {
-        const double tot = block_sum(COMPACT ? n2s[t * kThreads + threadIdx.x] : n2, red);
-        if (threadIdx.x == 0) a.scalpart[b * NT + t] = tot;
-    }
-    const double tv = block_sum(lane == 0 ? (double)cands : 0.0, red);
+    const double tv = block_sum((double)cands, red);
     if (threadIdx.x == 0) a.votepart[b] = tv;
 }
 
-template <bool VEC, int NT>
-__global__ void __launch_bounds__(kThreads, 2) plan_trials_lin_kernel(const __grid_constant__ TrialLinArgs a) {
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) plan_trials_screen_kernel(const __grid_constant__ TrialLinArgs a) {
     extern __shared__ __align__(16) double trials_lin_dsm[];
-    if (a.nonunit != nullptr && *a.nonunit == 0) trials_lin_body<VEC, NT, true>(a, trials_lin_dsm);
-    else                                     trials_lin_body<VEC, NT, false>(a, trials_lin_dsm);
+    const double al_f = a.alpha[0], al_l = a.alpha[1];                       // first and last step of the batch
+    if (a.nonunit != nullptr && *a.nonunit == 0) trials_screen_body<VEC, true>(a, al_f, al_l, trials_lin_dsm);
+    else                                     trials_screen_body<VEC, false>(a, al_f, al_l, trials_lin_dsm);
 }
 
-// out[t] = scale * sum_b scalpart[b][t] (fixed order) for t < nt ; out[nt_out] = sum_b votepart[b]
-__global__ void __launch_bounds__(256) trials_lin_finish_kernel(const double* __restrict__ scalpart, const double* __restrict__ votepart,
-                                                                int num_blocks, int nt, int nt_out, double scale,
-                                                                double* __restrict__ out) {
+// off[b] = number of candidates of the blocks before b (fixed order), off[num_blocks] = total
+__global__ void __launch_bounds__(1024) cand_scan_kernel(const double* __restrict__ votepart, int num_blocks,
+                                                         unsigned long long* __restrict__ off) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    for (int base = 0; base < num_blocks; base += 1024) {
+        const int b = base + threadIdx.x;
+        const unsigned long long v = (b < num_blocks) ? (unsigned long long)votepart[b] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        if (b < num_blocks) off[b] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[num_blocks] = carry;
+}
+
+// list[...] = (column, row) of every candidate, in (block, thread, word, bit) order
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) cand_compact_kernel(const TrialLinArgs a, const unsigned long long* __restrict__ off,
+                                                                int2* __restrict__ list) {
+    __shared__ unsigned wsum[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (off[b + 1] == off[b]) return;         // block-uniform: nothing survived the screen here
+    const int cpc = a.cols_per_chunk;
+    const int64_t c0 = (int64_t)blockIdx.x * cpc;
+    const int64_t c1 = (c0 + cpc < a.n) ? (c0 + cpc) : a.n;
+    const int64_t row0 = ((int64_t)blockIdx.y * kWarps + warp) * kStripRows + (VEC ? 2 * lane : lane);
+    const unsigned* mword = a.mask + b * (size_t)a.words * kThreads + threadIdx.x;
+    const int nwords = (int)((c1 - c0 + 7) >> 3);
+    unsigned cnt = 0;
+    for (int wi = 0; wi < nwords; ++wi) cnt += __popc(mword[(size_t)wi * kThreads]);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long pos = off[b] + (incl - cnt);
+    for (int w = 0; w < warp; ++w) pos += wsum[w];
+    if (cnt == 0) return;
+    for (int wi = 0; wi < nwords; ++wi) {
+        unsigned bits = mword[(size_t)wi * kThreads];
+        while (bits != 0u) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int k = bit & 3, cc = (bit >> 2) & 1;
+            const int64_t col = c0 + 8 * wi + 2 * (bit >> 3) + cc;
+            const int64_t r = row0 + (VEC ? (64 * (k >> 1) + (k & 1)) : (32 * k));
+            list[pos++] = make_int2((int)col, (int)r);
+        }
+    }
+}
+
+// scalpart[block][t] = 4 * sum over the block's share of the list of max(z_t,0)^2  (thread g takes g, g+G, ...)
+template <int NT, bool UNITW>
+__device__ __forceinline__ void cand_eval_body(const TrialLinArgs& a, const int2* __restrict__ list, unsigned long long total) {
+    __shared__ double red[32];
+    const int64_t m = a.m, n = a.n;
+    double n2[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) n2[t] = 0.0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int2 cr = list[i];
+        const double wv = __ldg(a.w + (size_t)cr.x * (size_t)m + (size_t)cr.y);
+        const double lj = __ldg(a.lam + cr.x), zj = __ldg(a.zeta + cr.x);
+        const double li = __ldg(a.lam + n + cr.y), zi = __ldg(a.zeta + n + cr.y);
+        const double pvv = UNITW ? 0.0 : __ldg(a.p + cr.y), qj = UNITW ? 0.0 : __ldg(a.q + cr.x);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double al = a.alpha[t];
+            const double y1 = __dadd_rn(lj, __dmul_rn(al, zj));              // lk_old + delta^ll*zeta
+            const double y2 = __dadd_rn(li, __dmul_rn(al, zi));
+            const double aty = UNITW ? __dadd_rn(y1, y2) : __dadd_rn(__dmul_rn(pvv, y1), __dmul_rn(y2, qj));
+            const double z = __dmul_rn(a.inv_tk, __dsub_rn(wv, aty));
+            const double t2 = __dadd_rn(z, fabs(z));                         // 2*max(z,0), exact
+            n2[t] = fma(t2, t2, n2[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const double tot = block_sum(n2[t], red);
+        if (threadIdx.x == 0) a.scalpart[(size_t)blockIdx.x * NT + t] = tot;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads) cand_eval_kernel(const __grid_constant__ TrialLinArgs a, const int2* __restrict__ list,
+                                                             unsigned long long total) {
+    if (a.nonunit != nullptr && *a.nonunit == 0) cand_eval_body<NT, true>(a, list, total);
+    else                                     cand_eval_body<NT, false>(a, list, total);
+}
+
+// out[t] = scale * sum_b scalpart[b][t] (fixed order) for t < nt_out
+__global__ void __launch_bounds__(256) trials_lin_finish_kernel(const double* __restrict__ scalpart, int num_blocks, int nt, int nt_out,
+                                                                double scale, double* __restrict__ out) {
     __shared__ double red[32];
     for (int t = 0; t < nt_out; ++t) {
         double s = 0.0;
@@ -666,10 +697,6 @@ __global__ void __launch_bounds__(256) trials_lin_finish_kernel(const double* __
         s = block_sum(s, red);
         if (threadIdx.x == 0) out[t] = scale * s;
     }
-    double s = 0.0;
-    for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) s += votepart[b];
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) out[nt_out] = s;
 }
 
 // nonunit[0] |= 1 if some p_i or q_j differs from 1.0 (nonunit is zeroed by the caller)
@@ -1240,40 +1267,58 @@ void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, c
     SSN_CUDA(cudaMemcpyAsync(n2_out_dev, n2_scratch.p, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
 }
 
-// Screened trials (plan_trials_lin_kernel): out_dev[t] = ||prox((w - Aty(lam + alpha_t*zeta))/tk)||^2 for t < nt
-// (nt <= 32, alpha_t = delta^(ll0+t), gama = Inf) and out_dev[nt] = number of entries that survived the
-// screen (candidates) -- out of m*n -- which tells the caller how sparse the trial plans are.
+// Screened trials (screen / compact / eval kernels above): out_dev[t] = ||prox((w - Aty(lam + alpha_t*zeta))/tk)||^2
+// for t < nt (nt <= 128, alpha_t = delta^(ll0+t), gama = Inf) and out_dev[nt] = number of entries that
+// survived the screen (candidates) -- out of m*n -- which tells the caller how sparse the trial plans are.
+// One host round trip inside (the candidate count sizes the list).
 void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const double* zeta, const double* p, const double* q,
                           int64_t m, int64_t n, double tk, double delta, int ll0, int nt, double* out_dev, const int* nonunit_dev) {
     SSN_REQUIRE(m > 0 && n > 0 && w && lam && zeta && p && q && out_dev, SSN_E_INVALID, "prox_trials_lin: bad arguments");
-    SSN_REQUIRE(nt >= 1 && nt <= kMaxLinTrials, SSN_E_INVALID, "prox_trials_lin: 1 <= nt <= 32");
-    const int NTk = nt <= 1 ? 1 : (nt <= 8 ? 8 : (nt <= 16 ? 16 : 32));     // compiled batch sizes
+    SSN_REQUIRE(nt >= 1 && nt <= kMaxLinBatch, SSN_E_INVALID, "prox_trials_lin: 1 <= nt <= 128");
+    SSN_REQUIRE(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), SSN_E_TOO_LARGE, "prox_trials_lin: m or n >= 2^31");
     const Tiling t = plan_tiling(c, m, n);
     const int nblocks = t.chunks * t.groups;
-    Buf<double> scalpart(c, (size_t)NTk * nblocks), votepart(c, nblocks), scratch(c, kMaxLinTrials + 1);
+    const int words = cdiv(t.cpc, 8);
+    const int egrid = c->num_sms * 4;                                       // evaluation grid (fixed: the summation order depends on it)
+    Buf<double> scalpart(c, (size_t)kMaxLinTrials * egrid), votepart(c, nblocks), scratch(c, kMaxLinBatch + 1);
+    Buf<unsigned> mask(c, (size_t)nblocks * words * kThreads);
+    Buf<unsigned long long> off(c, (size_t)nblocks + 1);
     Buf<int> flag;
     if (!nonunit_dev) { flag.alloc(c, 1); nonunit_dev = plan_nonunit_flag(c, p, q, m, n, flag.p); }
     TrialLinArgs a{};
     a.w = w; a.p = p; a.q = q; a.lam = lam; a.zeta = zeta; a.inv_tk = 1.0 / tk; a.m = m; a.n = n;
-    a.cols_per_chunk = t.cpc; a.scalpart = scalpart.p; a.votepart = votepart.p; a.nonunit = nonunit_dev;
-    for (int i = 0; i < kMaxLinTrials; ++i) a.alpha[i] = std::pow(delta, (double)(ll0 + std::min(i, nt - 1)));
+    a.cols_per_chunk = t.cpc; a.words = words; a.mask = mask.p; a.scalpart = scalpart.p; a.votepart = votepart.p; a.nonunit = nonunit_dev;
+    a.alpha[0] = std::pow(delta, (double)ll0); a.alpha[1] = std::pow(delta, (double)(ll0 + nt - 1));      // first and last step of the batch
     const dim3 grid(t.chunks, t.groups);
     const bool vec = vec_ok(w, m);
-    const size_t tsmem = sizeof(double) * ((size_t)2 * kGroupRows + (size_t)5 * t.cpc + (NTk > 1 ? (size_t)NTk * kThreads + kWarps * kLinQueue : 0))
-                         + (NTk > 1 ? sizeof(unsigned) * kWarps * kLinQueue : 0);
-#define SSN_TLIN_NT(V, NT) do { \
-        SSN_CUDA(cudaFuncSetAttribute((plan_trials_lin_kernel<V, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)); \
-        SSN_LAUNCH(c, (plan_trials_lin_kernel<V, NT>), grid, kThreads, tsmem, a); } while (0)
-#define SSN_TLIN(V) do { if (NTk == 1) SSN_TLIN_NT(V, 1); else if (NTk == 8) SSN_TLIN_NT(V, 8); \
-                         else if (NTk == 16) SSN_TLIN_NT(V, 16); else SSN_TLIN_NT(V, 32); } while (0)
+    const size_t tsmem = sizeof(double) * (size_t)3 * t.cpc;
     {
-    KernelTimer kt(c);
-    if (vec) SSN_TLIN(true); else SSN_TLIN(false);
+    KernelTimer kt(c);                                   // the plan-wide (HBM-bound) kernel of the batch
+    if (vec) SSN_LAUNCH(c, (plan_trials_screen_kernel<true>), grid, kThreads, tsmem, a);
+    else     SSN_LAUNCH(c, (plan_trials_screen_kernel<false>), grid, kThreads, tsmem, a);
     }
-#undef SSN_TLIN
-#undef SSN_TLIN_NT
-    SSN_LAUNCH(c, trials_lin_finish_kernel, 1, 256, 0, scalpart.p, votepart.p, nblocks, NTk, nt, 0.25, scratch.p);
+    SSN_LAUNCH(c, cand_scan_kernel, 1, 1024, 0, votepart.p, nblocks, off.p);
+    unsigned long long total = 0;
+    read_back(c, off.p + nblocks, &total, 1);
+    Buf<int2> list(c, (size_t)std::max<unsigned long long>(total, 1ull));
+    if (total > 0) {
+        if (vec) SSN_LAUNCH(c, (cand_compact_kernel<true>), grid, kThreads, 0, a, off.p, list.p);
+        else     SSN_LAUNCH(c, (cand_compact_kernel<false>), grid, kThreads, 0, a, off.p, list.p);
+    }
+    for (int t0 = 0; t0 < nt; t0 += kMaxLinTrials) {      // 32 steps per evaluation launch
+        const int k = std::min(kMaxLinTrials, nt - t0);
+        const int NTk = k <= 1 ? 1 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32));
+        for (int i = 0; i < kMaxLinTrials; ++i) a.alpha[i] = std::pow(delta, (double)(ll0 + t0 + std::min(i, k - 1)));
+        if (NTk == 1) SSN_LAUNCH(c, (cand_eval_kernel<1>), egrid, kThreads, 0, a, list.p, total);
+        else if (NTk == 8) SSN_LAUNCH(c, (cand_eval_kernel<8>), egrid, kThreads, 0, a, list.p, total);
+        else if (NTk == 16) SSN_LAUNCH(c, (cand_eval_kernel<16>), egrid, kThreads, 0, a, list.p, total);
+        else SSN_LAUNCH(c, (cand_eval_kernel<32>), egrid, kThreads, 0, a, list.p, total);
+        SSN_LAUNCH(c, trials_lin_finish_kernel, 1, 256, 0, scalpart.p, egrid, NTk, k, 0.25, scratch.p + t0);
+    }
+    c->h_pin[2048] = (double)total;
+    SSN_CUDA(cudaMemcpyAsync(scratch.p + nt, c->h_pin + 2048, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SSN_CUDA(cudaMemcpyAsync(out_dev, scratch.p, sizeof(double) * (nt + 1), cudaMemcpyDeviceToDevice, c->stream));
+    SSN_CUDA(cudaStreamSynchronize(c->stream));          // h_pin is reused by the next call
 }
 
 // lamT[t] = lam + delta^(ll0+t)*zeta for t < nt, and f0_out[2t] = ||lamT[t]||^2, f0_out[2t+1] = wlk'*lamT[t]
@@ -1281,7 +1326,7 @@ void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const 
 // vectors and plan_prox_trials on its slab).
 void plan_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const double* wlk, int64_t N, double delta,
                         int ll0, int nt, double* lamT, double* f0_out) {
-    SSN_REQUIRE(lam && zeta && wlk && lamT && f0_out && nt >= 1 && nt <= kMaxLinTrials && N > 0, SSN_E_INVALID, "trial_vectors: bad arguments");
+    SSN_REQUIRE(lam && zeta && wlk && lamT && f0_out && nt >= 1 && nt <= kMaxLinBatch && N > 0, SSN_E_INVALID, "trial_vectors: bad arguments");
     const int nb = 64;
     Buf<double> alpha(c, nt), f0part(c, (size_t)nb * nt * 2);
     for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = std::pow(delta, (double)(ll0 + t));
@@ -1299,14 +1344,15 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
                      double gama_s, double nu, double delta, int ll_max, double cF_old, double ress, int batch,
                      double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out) {
     SSN_REQUIRE(lam_old && zeta && wlk && lam_new && ll_max >= 0, SSN_E_INVALID, "linesearch: bad arguments");
-    // batch <= 0: adaptive.  With gama = Inf every pass goes through the screened kernel, whose candidate
-    // count says how sparse the trial plans are: 32 backtracking steps per read of w while fewer than
-    // 10 % of the entries survive the screen, 16 below 25 %, else 8 through the dense kernel.
+    // batch <= 0: adaptive.  With gama = Inf every pass goes through the screened kernels, whose candidate
+    // count says how sparse the trial plans are: while fewer than 10 % of the entries survive the screen
+    // a read of w evaluates 32, then 64, then 128 backtracking steps (the evaluation of the candidates
+    // is a few microseconds per 32 steps), 16 below 25 %, else 8 through the dense kernel.
     const bool adaptive = batch <= 0;
     const bool screened = adaptive && c->ls_screen && gama == nullptr && std::isinf(gama_s) && gama_s > 0;
     if (adaptive) batch = kMaxTrials;
     if (batch > kMaxTrials) batch = kMaxTrials;
-    const int cap = screened ? kMaxLinTrials : batch;
+    const int cap = screened ? kMaxLinBatch : batch;
     const int64_t N = m + n;
     const int nb = 64;
     Buf<double> lamT(c, (size_t)cap * N), alpha(c, cap), f0part(c, (size_t)nb * cap * 2), res(c, 3 * (size_t)cap + 1);
@@ -1321,10 +1367,12 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         int want = batch;
         bool lin = screened;
         if (screened && passes > 0) {
-            if (dens <= 0.10) want = 32; else if (dens <= 0.25) want = 16; else { want = kMaxTrials; lin = false; }
+            if (dens <= 0.10) want = std::min(c->ls_max_nt, passes == 1 ? 32 : (passes == 2 ? 64 : 128));
+            else if (dens <= 0.25) want = std::min(16, c->ls_max_nt);
+            else { want = kMaxTrials; lin = false; }
         }
         const int nt = std::min(passes == 0 ? 1 : want, ll_max - ll + 1);
-        double al[kMaxLinTrials];
+        double al[kMaxLinBatch];
         for (int t = 0; t < nt; ++t) al[t] = std::pow(delta, (double)(ll + t));
         for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = al[t];
         SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
@@ -1332,7 +1380,7 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, res.p + cap + 1);
         if (lin) plan_prox_trials_lin(c, w, lam_old, zeta, p, q, m, n, tk, delta, ll, nt, res.p, nonunit);
         else     plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p, nonunit);
-        double h[3 * kMaxLinTrials + 1];
+        double h[3 * kMaxLinBatch + 1];
         read_back(c, res.p, h, 3 * (size_t)cap + 1);
         if (lin) dens = h[nt] / slots;
         ++passes;

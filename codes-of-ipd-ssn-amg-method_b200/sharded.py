@@ -137,11 +137,11 @@ class ShardedStep:
         """One read-sweep of the slab for nt Armijo trials: returns (lamT, values, density) with values
         (host) = [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One all_reduce of nt
         (+1) doubles and one device->host read per batch, however many launches it takes.  screened: the
-        slab goes through the screened kernel (32 steps per launch, gama = Inf), whose count of surviving
+        slab goes through the screened kernels (up to 128 steps per read of the slab, gama = Inf), whose count of surviving
         entries rides in the same all_reduce and comes back as density = share of the plan's entries."""
         torch = self.torch
         lams, f0s, parts = [], [], []
-        per = 32 if screened else 8
+        per = 128 if screened else 8
         votes = None
         for t0 in range(0, nt, per):
             k = min(per, nt - t0)
@@ -198,14 +198,17 @@ class ShardedStep:
         ress = abs(float(Fk_old @ zeta))
         # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
         # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernel, whose vote
-        # count says how sparse the trial plans are -- 32 steps per launch while under 10 % of the entries
-        # survive the screen, 16 under 25 %, else the dense 8-step kernel (api.linesearch makes the same choice)
+        # count says how sparse the trial plans are -- 32, 64, then 128 steps per read while under 10 % of the
+        # entries survive the screen, 16 under 25 %, else the dense 8-step kernel (as ssn_linesearch does)
         screened = np.isinf(self.gama) and self.gama > 0 and hasattr(self.ops, "prox_trials_lin") and self.screen
         ll, done, passes, dens = 0, False, 0, 1.0
         while not done:                                                              # :189-211, ll = 0 alone, then a batch per pass
             lin = screened and (passes == 0 or dens <= 0.25)
-            per = (32 if dens <= 0.10 else 16) if (lin and passes > 0) else 8
-            nt = min(1 if passes == 0 else per * min(self.world, 4), max_ll - ll + 1)
+            if lin and passes > 0:
+                nt = (32 if passes == 1 else (64 if passes == 2 else 128)) if dens <= 0.10 else 16
+            else:
+                nt = 8 * min(self.world, 4)
+            nt = min(1 if passes == 0 else nt, max_ll - ll + 1)
             lamT, vals, d = self.trial_batch(lk, zeta, delta, ll, nt, screened=lin); passes += 1
             if d is not None:
                 dens = d

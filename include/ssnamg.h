@@ -197,17 +197,18 @@ SSN_API int ssn_prox_trials(ssn_ctx *ctx, const double *w_dev, const double *lam
                     const double *gama_dev, double gama_scalar, double *n2_out_dev);
 
 /* Screened batched trials of ONE search direction (gama = Inf): out_dev[t] = ||prox((w - Aty(lam +
- * delta^(ll0+t)*zeta))/tk)||^2 for t < nt <= 32, bit-identical to ssn_prox_trials on the same trial
- * vectors, and out_dev[nt] = number of entries at which some trial of the batch may be active (out
- * of m*n).  Entries whose first and last trial residuals are both safely negative are skipped (the
- * residual is linear in the step), the others are compacted and evaluated lane-parallel, so where
- * the trial plans are sparse the pass is HBM-bound for any nt.  lam_dev / zeta_dev: [column part (n) ; row part (m)]. */
+ * delta^(ll0+t)*zeta))/tk)||^2 for t < nt <= 128 -- the values of ssn_prox_trials on the same trial
+ * vectors up to the summation order -- and out_dev[nt] = number of entries at which some trial of
+ * the batch may be active (out of m*n).  Entries whose first and last trial residuals are both
+ * safely negative add exactly 0 and are dropped (the residual is linear in the step); the others are
+ * listed and evaluated by a second, grid-balanced kernel, so where the trial plans are sparse the
+ * pass is HBM-bound for any nt.  Deterministic.  lam_dev / zeta_dev: [column part (n) ; row part (m)]. */
 SSN_API int ssn_prox_trials_lin(ssn_ctx *ctx, const double *w_dev, const double *lam_dev, const double *zeta_dev,
                         const double *p_dev, const double *q_dev, int64_t m, int64_t n, double tk,
                         double delta, int ll0, int nt, double *out_dev);
 
 /* The O(m+n) half of a batch of Armijo trials (row-sharded callers use it with ssn_prox_trials on
- * their slab): lamT_out_dev[t] = lam + delta^(ll0+t)*zeta for t < nt <= 32 and
+ * their slab): lamT_out_dev[t] = lam + delta^(ll0+t)*zeta for t < nt <= 128 and
  * f0_out_dev[2t] = ||lamT[t]||^2, f0_out_dev[2t+1] = wlk'*lamT[t]  (Class1/APD_SsN_Class1.m:189-190). */
 SSN_API int ssn_trial_vectors(ssn_ctx *ctx, const double *lam_dev, const double *zeta_dev, const double *wlk_dev,
                       int64_t N, double delta, int ll0, int nt, double *lamT_out_dev, double *f0_out_dev);
@@ -216,8 +217,8 @@ SSN_API int ssn_trial_vectors(ssn_ctx *ctx, const double *lam_dev, const double 
  *   lk_new = lk_old + delta^ll*zeta;  cF_new = bk1/2*||lk_new||^2 - wlk'*lk_new + tk/2*||prox(z)||^2;
  *   the first ll with !(cF_new > cF_old - nu*delta^ll*ress), or ll == ll_max, is accepted.
  * The first read of w evaluates ll = 0 alone (most steps accept it); every later read evaluates
- * `batch` (1..8) backtracking steps at once; batch <= 0 = adaptive: 8, 16 or 32 steps per read
- * through the screened kernel of ssn_prox_trials_lin, by the measured sparsity (results identical).  Outputs: lam_new_dev (n+m), *ll_out,
+ * `batch` (1..8) backtracking steps at once; batch <= 0 = adaptive: 8 to 128 steps per read through
+ * the screened kernels of ssn_prox_trials_lin, by the measured sparsity of the trial plans.  Outputs: lam_new_dev (n+m), *ll_out,
  * *norm2_out = ||prox(z(lk_new))||^2, *cF_out, *passes_out = number of reads of w. */
 SSN_API int ssn_linesearch(ssn_ctx *ctx, const double *w_dev, const double *lam_old_dev, const double *zeta_dev,
                    const double *wlk_dev, const double *p_dev, const double *q_dev, int64_t m, int64_t n,
