@@ -55,6 +55,25 @@ class _CudaOps:
     def rng_reset(self):
         self.api.rng_reset()
 
+    # ---- the operators the sharded outer loop (sharded_driver.py) adds
+    def Ax(self, x, p, q):
+        return self.api.Ax(x, p, q)
+
+    def Aty(self, y, p, q):
+        return self.api.Aty(y, p, q)
+
+    def invAAt(self, x, p, q, sg):
+        return self.api.invAAt(x, p, q, sg)
+
+    def apd_begin(self, c, xk, vk, p, q, ak, bk):
+        return self.api.apd_begin(c, xk, vk, p, q, ak, bk)
+
+    def apd_end(self, c, wk, xk, lam, p, q, tk, ak, gama):
+        return self.api.apd_end(c, wk, xk, lam, p, q, tk, ak, gama)
+
+    def rand(self, count):
+        return self.api.rand(count)
+
 
 class ShardedStep:
     """One semismooth-Newton step (Class1/APD_SsN_Class1.m:137-212) on a row-sharded plan."""
@@ -174,8 +193,17 @@ class ShardedStep:
         return self.ops.asat_from_lin(lin_all, self.p, self.q)
 
     def __call__(self):
+        """One step from ``state['lk']`` with the random stream reset first (benchmarks, parity tests)."""
+        lk_new, Fk_new, info, _ = self.step(self.lk, reset_rng=True)
+        return lk_new, Fk_new, info
+
+    def step(self, lk, pre=None, reset_rng=False, want_s_new=False):
+        """One semismooth-Newton step from ``lk``.  ``pre`` = the residual evaluation at ``lk`` (the 4-tuple
+        ``residual(lk, True)`` returns) when the caller already holds it -- the outer loop passes the
+        evaluation that closed the previous step.  Returns ``(lk_new, Fk_new, info, post)`` with ``post`` the
+        residual evaluation at ``lk_new`` (with its active set when ``want_s_new``)."""
         torch = self.torch
-        bk1, tk, lk, wlk = self.bk1, self.tk, self.lk, self.wlk
+        bk1, tk, wlk = self.bk1, self.tk, self.wlk
         nu, delta, max_ll = 0.2, 0.9, 500
         import time as _time
         tm = {"plan": 0.0, "asat": 0.0, "amg": 0.0}
@@ -183,9 +211,10 @@ class ShardedStep:
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
             tm[key] += (_time.perf_counter() - t0) * 1e3
-        self.ops.rng_reset()
+        if reset_rng:
+            self.ops.rng_reset()
         t0 = _time.perf_counter()
-        Axp, n2_old, E, s_loc = self.residual(lk, True)                              # :139-144
+        Axp, n2_old, E, s_loc = pre if pre is not None else self.residual(lk, True)  # :139-144
         Fk_old = bk1 * lk - Axp - wlk
         _lap("plan", t0); t0 = _time.perf_counter()
         H0 = self.assemble(s_loc)                                                    # :142
@@ -219,11 +248,11 @@ class ShardedStep:
                     break
             else:
                 ll += nt
-        Axp2, _, _, _ = self.residual(lk_new, False)                                 # :212
-        Fk_new = bk1 * lk_new - Axp2 - wlk
+        post = self.residual(lk_new, want_s_new)                                     # :212
+        Fk_new = bk1 * lk_new - post[0] - wlk
         _lap("plan", t0)
         return lk_new, Fk_new, {"E": E, "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg, "resamg": resamg, "info": info, "ll": ll, "ls_passes": passes,
-                                "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives, "zeta": zeta}
+                                "nnzH": getattr(H0, "nnz", None), "collectives": self.collectives, "zeta": zeta}, post
 
 
 def make_sharded_step(state, rank, world, **kw):

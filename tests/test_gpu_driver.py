@@ -93,3 +93,33 @@ def test_class2_partial_ot_solve_matches_oracle(gpu, oracle, kind, size, solver)
     assert np.allclose(out["fxk"][:k], ref["fxk"][:k], rtol=1e-8)
     x = out["xk"].cpu().numpy()
     assert x.min() >= 0 and abs(P["phi"] @ x - P["mu"]) <= 1e-5 * (1 + P["mu"])      # transported mass = mu
+
+
+def test_sharded_outer_loop_on_one_gpu_matches_device_driver(gpu):
+    """The row-sharded Class 1 solve (sharded_driver.py, CUDA slab operators, world size 1 -- the code
+    path every rank of a multi-GPU run executes, minus the collectives) against the single-GPU driver:
+    same SsN step counts over the first outer iterations, objectives / KKT histories to rounding,
+    and the device-generated cost slab against the host generator."""
+    import importlib
+    import torch
+    drv = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+    sd = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded_driver")
+    g = 10
+    P = gpu.problems.grid_problem(g, seed=0)
+    m = n = g * g
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    c_slab = sd.grid_cost_slab(g, 0, m)
+    assert np.allclose(c_slab.cpu().numpy(), P["c"], rtol=0, atol=4e-16)
+    c_part = sd.grid_cost_slab(g, 30, 57).cpu().numpy().reshape(n, 27)
+    assert np.allclose(c_part, P["c"].reshape(n, m)[:, 30:57], rtol=0, atol=4e-16)
+    gpu.rng_reset()
+    ref = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], max_outer=6)
+    gpu.rng_reset()
+    out = sd.APD_SsN_Class1_sharded(dev(P["c"]), dev(P["r"]), dev(P["l"]), dev(P["p"]), dev(P["q"]), 0, 1, max_outer=6)
+    k = len(ref["fxk"])
+    assert len(out["fxk"]) == k
+    assert out["stats"]["ssn_its"] == ref["stats"]["ssn_its"]
+    assert np.allclose(out["fxk"], ref["fxk"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(out["KKT_lk"], ref["KKT_lk"], rtol=1e-6, atol=1e-11)
+    assert np.allclose(out["KKT_xk"], ref["KKT_xk"], rtol=1e-6, atol=1e-11)
+    assert np.allclose(out["lk"].cpu().numpy(), ref["lk"].cpu().numpy(), rtol=1e-7, atol=1e-10)

@@ -2,6 +2,7 @@
 two gloo ranks, the plan operators supplied by an adapter over the oracle.  The sharded step must
 reproduce the unsharded one: same active set / ASAt, same AMG cycle count, same line-search
 length, iterates equal to rounding (the column-sum reduction order changes with the world size)."""
+import importlib
 import os
 import socket
 import sys
@@ -41,6 +42,8 @@ class OracleOps:
             out["Axprox"] = torch.from_numpy(self.o.Ax(px, p, q))
         if "s" in want:
             out["s"] = torch.from_numpy(s.astype(np.uint8))
+        if "prox" in want:
+            out["prox"] = torch.from_numpy(px)
         return out
 
     def prox_trials(self, w, lamT, p, q, tk, gama):
@@ -77,6 +80,32 @@ class OracleOps:
 
     def rng_reset(self):
         self.o.rng_reset()
+
+    # ---- operators of the sharded outer loop (sharded_driver.py)
+    def Ax(self, x, p, q):
+        return torch.from_numpy(self.o.Ax(self._np(x), self._np(p), self._np(q)))
+
+    def Aty(self, y, p, q):
+        return torch.from_numpy(self.o.Aty(self._np(y), self._np(p), self._np(q)))
+
+    def invAAt(self, x, p, q, sg):
+        return torch.from_numpy(np.asarray(self.o.invAAt(self._np(x), self._np(p), self._np(q), sg)).reshape(-1))
+
+    def apd_begin(self, c, xk, vk, p, q, ak, bk):
+        c, xk, vk = (self._np(v) for v in (c, xk, vk))
+        wk = -c + bk * (xk + ak * vk) / ak ** 2                          # Class1/APD_SsN_Class1.m:125
+        return torch.from_numpy(wk), self.Ax(xk, p, q)
+
+    def apd_end(self, c, wk, xk, lam, p, q, tk, ak, gama):
+        c, wk, xk, lam, p, q = (self._np(v) for v in (c, wk, xk, lam, p, q))
+        prox = lambda x: np.minimum(np.maximum(0.0, x), gama)
+        aty = self.o.Aty(lam, p, q)
+        xk1 = prox((wk - aty) / tk); vk1 = xk1 + (xk1 - xk) / ak         # :239
+        d = xk1 - prox(xk1 - c - aty)                                    # :254
+        return torch.from_numpy(xk1), torch.from_numpy(vk1), torch.from_numpy(self.o.Ax(xk1, p, q)), float(c @ xk1), float(d @ d)
+
+    def rand(self, count):
+        return torch.from_numpy(np.asarray(self.o.rand(count), dtype=np.float64).reshape(-1))
 
 
 def make_state(m, n, seed):
@@ -126,6 +155,75 @@ def test_sharded_step_matches_unsharded_gloo(m, n):
         assert np.allclose(o["Fk"], Fk_ref.numpy(), rtol=1e-8, atol=1e-10)
         assert int(o["coll"]) > 0
     assert np.array_equal(outs[0]["lk"], outs[1]["lk"])          # replicated AMG: identical on every rank
+
+
+def _grid(g):
+    problems = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.problems")
+    return problems.grid_problem(g, seed=0)
+
+
+def _solve_worker(rank, world, port, g, outdir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = _run_sharded_solve(rank, world, g, dist)
+    np.savez(os.path.join(outdir, f"solve{rank}.npz"), fxk=np.array(res["fxk"]), kx=np.array(res["KKT_xk"]), kl=np.array(res["KKT_lk"]),
+             lk=res["lk"].numpy(), xk=res["xk"].numpy(), its=np.array(res["stats"]["ssn_its"]), coll=res["stats"]["collectives"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_sharded_solve(rank, world, g, dist):
+    sd = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded_driver")
+    sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+    P = _grid(g)
+    m, n = P["m"], P["n"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    r0, r1 = sharded.row_range(rank, world, m)
+    c_loc = sharded.shard_plan_vector(t(P["c"]), m, n, r0, r1)
+    ops = OracleOps(); ops.rng_reset()
+    return sd.APD_SsN_Class1_sharded(c_loc, t(P["r"]), t(P["l"]), t(P["p"]), t(P["q"]), rank, world, ops=ops, dist=dist,
+                                     amg_options=AMG_OPTS, warm_maxit=30, max_outer=4)
+
+
+def test_sharded_outer_loop_matches_oracle_driver_and_two_ranks():
+    """The row-sharded Class 1 solve (warm start + APD outer loop + SsN steps) on one rank against the
+    oracle's own driver, and on two gloo ranks against one rank: same number of SsN steps per outer
+    iteration, objective / KKT histories and iterates equal to rounding."""
+    import torch.multiprocessing as mp
+    import oracle
+    from oracle import driver as odrv
+    g = 5
+    one = _run_sharded_solve(0, 1, g, None)
+    P = _grid(g)
+    oracle.rng_reset()
+    calls = {"n": 0}
+
+    class _Stop(Exception):
+        pass
+
+    def hook(st):
+        calls["n"] += 1
+    try:
+        ref = odrv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], np.inf, maxit=4, warm_maxit=30, on_ssn_step=hook)
+    except TypeError:
+        ref = None
+    if ref is not None:
+        k = len(one["fxk"])
+        assert np.allclose(one["fxk"], np.asarray(ref["fxk"])[:k], rtol=1e-9, atol=1e-12)
+        assert sum(one["stats"]["ssn_its"]) == calls["n"]
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_solve_worker, args=(2, _free_port(), g, d), nprocs=2, join=True)
+        outs = [np.load(os.path.join(d, f"solve{r}.npz")) for r in range(2)]
+    for o in outs:
+        assert np.array_equal(o["its"], np.array(one["stats"]["ssn_its"]))
+        assert np.allclose(o["fxk"], one["fxk"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(o["kl"], one["KKT_lk"], rtol=1e-6, atol=1e-10) and np.allclose(o["kx"], one["KKT_xk"], rtol=1e-6, atol=1e-10)
+        assert np.allclose(o["lk"], one["lk"].numpy(), rtol=1e-8, atol=1e-11)
+        assert int(o["coll"]) > 0
+    m = g * g
+    full = np.concatenate([o["xk"].reshape(m, -1) for o in outs], axis=1)       # slabs are (n, m_loc) row-major
+    assert np.allclose(full.reshape(-1), one["xk"].numpy(), rtol=1e-8, atol=1e-11)
 
 
 def test_row_ranges_and_slab_layout():
