@@ -289,9 +289,8 @@ def main():
     r_lin["batch_steps"] = nt_lin
     r_lin["batch_ms_host_timed"] = lin_batch_ms
     r_lin["share_of_step"] = r_lin["launches_per_step"] * lin_batch_ms / ms_step
-    r_lin["note"] = (f"a batch of {nt_lin} steps = this kernel + candidate scan/compact/eval kernels on the surviving entries + the host "
-                     f"round trip that sizes the candidate list: {lin_batch_ms:.3f} ms in all (host-timed, synchronous call); "
-                     "share_of_step uses that figure")
+    r_lin["note"] = (f"a batch of {nt_lin} steps = this kernel + the candidate scan / compact / eval kernels on the surviving entries: "
+                     f"{lin_batch_ms:.3f} ms in all (host-timed, synchronous call through the Python binding); share_of_step uses that figure")
     if world == 1:
         r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials"); r_lin["traffic"] = load_traffic("trials_lin")
     cands = sorted([r_lin, r_k3, r_tr], key=lambda r: -r["share_of_step"])

@@ -507,36 +507,33 @@ __device__ __forceinline__ void trials_screen_body(const TrialLinArgs& a, double
     int cands = 0;
     const bool strip_full = (rbase + kStripRows <= m);
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
-    const size_t step = 2 * (size_t)m;
 
-    auto load_batch = [&](double (&v)[2][4], int64_t c, size_t o) {
-        const bool full = strip_full && (c + 2 <= c1);
+    // one batch = 4 columns x 4 rows per lane, all 8 x 16 B loads issued before the first use (as plan_batch);
+    // the screen bits of the batch go to bits [16*half + 4*cc + k] of the current mask word (8 columns per word)
+    auto batch = [&](auto full_tag, int64_t c, size_t o) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        double v[4][4];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const bool cok = full || (c + cc < c1);
+        for (int cc = 0; cc < 4; ++cc) {
+            const bool cok = FULL || (c + cc < c1);
             const double* xp = a.w + o + (size_t)cc * m;
             if (VEC) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double2 t2 = make_double2(0.0, 0.0);
-                    if (full || (cok && rok[2 * h])) t2 = __ldcs(reinterpret_cast<const double2*>(xp + roff<VEC>(2 * h)));
+                    if (FULL || (cok && rok[2 * h])) t2 = __ldcs(reinterpret_cast<const double2*>(xp + roff<VEC>(2 * h)));
                     v[cc][2 * h] = t2.x; v[cc][2 * h + 1] = t2.y;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[cc][k] = (full || (cok && rok[k])) ? __ldcs(xp + roff<VEC>(k)) : 0.0;
+                for (int k = 0; k < 4; ++k) v[cc][k] = (FULL || (cok && rok[k])) ? __ldcs(xp + roff<VEC>(k)) : 0.0;
             }
         }
-    };
-
-    // screens the 8 entries of a batch into bits [8*(batch & 3) + 4*cc + k] of the current mask word
-    auto compute_batch = [&](auto full_tag, const double (&v)[2][4], int64_t c) {
-        constexpr bool FULL = decltype(full_tag)::value;
-        const int sh = (int)(((c - c0) >> 1) & 3) * 8;
+        const int sh = (int)(((c - c0) >> 2) & 1) * 16;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
             const bool cok = FULL || (c + cc < c1);
-            const int jc = (int)(c - c0) + cc;
+            const int jc = (int)(c - c0) + cc;                 // < cpc (cpc is a multiple of 4)
             const double yfj = yfc[jc], ylj = ylc[jc];
             const double qj = UNITW ? 0.0 : qs[jc];
 #pragma unroll
@@ -555,21 +552,14 @@ __device__ __forceinline__ void trials_screen_body(const TrialLinArgs& a, double
         }
     };
 
-    double vcur[2][4], vnxt[2][4];
-    if (c0 < c1) load_batch(vcur, c0, off);
-    for (int64_t c = c0; c < c1; c += 2, off += step) {
-        if (c + 2 < c1) load_batch(vnxt, c + 2, off + step);
-        if (strip_full && (c + 2 <= c1)) compute_batch(std::true_type(), vcur, c);
-        else                             compute_batch(std::false_type(), vcur, c);
-        if ((((c - c0) >> 1) & 3) == 3 || c + 2 >= c1) {         // word complete (8 columns) or last batch of the chunk
+    const size_t step = 4 * (size_t)m;
+    for (int64_t c = c0; c < c1; c += 4, off += step) {
+        if (strip_full && c + 4 <= c1) batch(std::true_type(), c, off);
+        else                           batch(std::false_type(), c, off);
+        if ((((c - c0) >> 2) & 1) == 1 || c + 4 >= c1) {         // word complete (8 columns) or last batch of the chunk
             mword[(size_t)((c - c0) >> 3) * kThreads] = bits;
             cands += __popc(bits);
             bits = 0u;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) vcur[cc][k] = vnxt[cc][k];
         }
     }
     const double tv = block_sum((double)cands, red);
@@ -586,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 2) plan_trials_screen_kernel(const _
 
 // off[b] = number of candidates of the blocks before b (fixed order), off[num_blocks] = total
 __global__ void __launch_bounds__(1024) cand_scan_kernel(const double* __restrict__ votepart, int num_blocks,
-                                                         unsigned long long* __restrict__ off) {
+                                                         unsigned long long* __restrict__ off, double* __restrict__ total_out) {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -607,16 +597,17 @@ __global__ void __launch_bounds__(1024) cand_scan_kernel(const double* __restric
         if (threadIdx.x == 1023) carry = before + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) off[num_blocks] = carry;
+    if (threadIdx.x == 0) { off[num_blocks] = carry; total_out[0] = (double)carry; }
 }
 
 // list[...] = (column, row) of every candidate, in (block, thread, word, bit) order
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) cand_compact_kernel(const TrialLinArgs a, const unsigned long long* __restrict__ off,
-                                                                int2* __restrict__ list) {
+                                                                int2* __restrict__ list, unsigned long long cap) {
     __shared__ unsigned wsum[kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (off[(size_t)gridDim.x * gridDim.y] > cap) return;    // the list does not fit: the host repeats the call with the exact size
     if (off[b + 1] == off[b]) return;         // block-uniform: nothing survived the screen here
     const int cpc = a.cols_per_chunk;
     const int64_t c0 = (int64_t)blockIdx.x * cpc;
@@ -649,8 +640,15 @@ __global__ void __launch_bounds__(kThreads) cand_compact_kernel(const TrialLinAr
 
 // scalpart[block][t] = 4 * sum over the block's share of the list of max(z_t,0)^2  (thread g takes g, g+G, ...)
 template <int NT, bool UNITW>
-__device__ __forceinline__ void cand_eval_body(const TrialLinArgs& a, const int2* __restrict__ list, unsigned long long total) {
+__device__ __forceinline__ void cand_eval_body(const TrialLinArgs& a, const int2* __restrict__ list, const unsigned long long* __restrict__ total_dev,
+                                               unsigned long long cap) {
     __shared__ double red[32];
+    unsigned long long total = *total_dev;
+    if (total > cap) total = 0;               // overflow: the host repeats the call
+    if ((unsigned long long)blockIdx.x * blockDim.x >= total) {               // block-uniform: no candidate for this block
+        if (threadIdx.x < NT) a.scalpart[(size_t)blockIdx.x * NT + threadIdx.x] = 0.0;
+        return;
+    }
     const int64_t m = a.m, n = a.n;
     double n2[NT];
 #pragma unroll
@@ -682,21 +680,20 @@ __device__ __forceinline__ void cand_eval_body(const TrialLinArgs& a, const int2
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads) cand_eval_kernel(const __grid_constant__ TrialLinArgs a, const int2* __restrict__ list,
-                                                             unsigned long long total) {
-    if (a.nonunit != nullptr && *a.nonunit == 0) cand_eval_body<NT, true>(a, list, total);
-    else                                     cand_eval_body<NT, false>(a, list, total);
+                                                             const unsigned long long* __restrict__ total_dev, unsigned long long cap) {
+    if (a.nonunit != nullptr && *a.nonunit == 0) cand_eval_body<NT, true>(a, list, total_dev, cap);
+    else                                     cand_eval_body<NT, false>(a, list, total_dev, cap);
 }
 
-// out[t] = scale * sum_b scalpart[b][t] (fixed order) for t < nt_out
-__global__ void __launch_bounds__(256) trials_lin_finish_kernel(const double* __restrict__ scalpart, int num_blocks, int nt, int nt_out,
+// out[t] = scale * sum_b scalpart[b][t] (fixed order) for t = blockIdx.x < nt_out
+__global__ void __launch_bounds__(256) trials_lin_finish_kernel(const double* __restrict__ scalpart, int num_blocks, int nt,
                                                                 double scale, double* __restrict__ out) {
     __shared__ double red[32];
-    for (int t = 0; t < nt_out; ++t) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) s += scalpart[(size_t)b * nt + t];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) out[t] = scale * s;
-    }
+    const int t = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < num_blocks; b += blockDim.x) s += scalpart[(size_t)b * nt + t];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[t] = scale * s;
 }
 
 // nonunit[0] |= 1 if some p_i or q_j differs from 1.0 (nonunit is zeroed by the caller)
@@ -1270,7 +1267,7 @@ void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, c
 // Screened trials (screen / compact / eval kernels above): out_dev[t] = ||prox((w - Aty(lam + alpha_t*zeta))/tk)||^2
 // for t < nt (nt <= 128, alpha_t = delta^(ll0+t), gama = Inf) and out_dev[nt] = number of entries that
 // survived the screen (candidates) -- out of m*n -- which tells the caller how sparse the trial plans are.
-// One host round trip inside (the candidate count sizes the list).
+// No host round trip before the last kernel is enqueued (the candidate list has a fixed capacity; see below).
 void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const double* zeta, const double* p, const double* q,
                           int64_t m, int64_t n, double tk, double delta, int ll0, int nt, double* out_dev, const int* nonunit_dev) {
     SSN_REQUIRE(m > 0 && n > 0 && w && lam && zeta && p && q && out_dev, SSN_E_INVALID, "prox_trials_lin: bad arguments");
@@ -1297,28 +1294,35 @@ void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const 
     if (vec) SSN_LAUNCH(c, (plan_trials_screen_kernel<true>), grid, kThreads, tsmem, a);
     else     SSN_LAUNCH(c, (plan_trials_screen_kernel<false>), grid, kThreads, tsmem, a);
     }
-    SSN_LAUNCH(c, cand_scan_kernel, 1, 1024, 0, votepart.p, nblocks, off.p);
-    unsigned long long total = 0;
-    read_back(c, off.p + nblocks, &total, 1);
-    Buf<int2> list(c, (size_t)std::max<unsigned long long>(total, 1ull));
-    if (total > 0) {
-        if (vec) SSN_LAUNCH(c, (cand_compact_kernel<true>), grid, kThreads, 0, a, off.p, list.p);
-        else     SSN_LAUNCH(c, (cand_compact_kernel<false>), grid, kThreads, 0, a, off.p, list.p);
+    SSN_LAUNCH(c, cand_scan_kernel, 1, 1024, 0, votepart.p, nblocks, off.p, scratch.p + nt);
+    // The candidate list is sized for 1/16 of the plan (the caller leaves the screened path long before the
+    // trial plans are that dense), so the whole batch is enqueued without a host round trip; if the list
+    // does not fit, the kernels do nothing and the list pass is repeated with the exact size.
+    auto list_pass = [&](int2* list, unsigned long long cap) {
+        if (vec) SSN_LAUNCH(c, (cand_compact_kernel<true>), grid, kThreads, 0, a, off.p, list, cap);
+        else     SSN_LAUNCH(c, (cand_compact_kernel<false>), grid, kThreads, 0, a, off.p, list, cap);
+        for (int t0 = 0; t0 < nt; t0 += kMaxLinTrials) {      // 32 steps per evaluation launch
+            const int k = std::min(kMaxLinTrials, nt - t0);
+            const int NTk = k <= 1 ? 1 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32));
+            for (int i = 0; i < kMaxLinTrials; ++i) a.alpha[i] = std::pow(delta, (double)(ll0 + t0 + std::min(i, k - 1)));
+            if (NTk == 1) SSN_LAUNCH(c, (cand_eval_kernel<1>), egrid, kThreads, 0, a, list, off.p + nblocks, cap);
+            else if (NTk == 8) SSN_LAUNCH(c, (cand_eval_kernel<8>), egrid, kThreads, 0, a, list, off.p + nblocks, cap);
+            else if (NTk == 16) SSN_LAUNCH(c, (cand_eval_kernel<16>), egrid, kThreads, 0, a, list, off.p + nblocks, cap);
+            else SSN_LAUNCH(c, (cand_eval_kernel<32>), egrid, kThreads, 0, a, list, off.p + nblocks, cap);
+            SSN_LAUNCH(c, trials_lin_finish_kernel, k, 256, 0, scalpart.p, egrid, NTk, 0.25, scratch.p + t0);
+        }
+    };
+    const unsigned long long cap0 = std::max<unsigned long long>(1ull << 16, (unsigned long long)m * (unsigned long long)n / 16);
+    {
+        Buf<int2> list(c, (size_t)cap0);
+        list_pass(list.p, cap0);
     }
-    for (int t0 = 0; t0 < nt; t0 += kMaxLinTrials) {      // 32 steps per evaluation launch
-        const int k = std::min(kMaxLinTrials, nt - t0);
-        const int NTk = k <= 1 ? 1 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32));
-        for (int i = 0; i < kMaxLinTrials; ++i) a.alpha[i] = std::pow(delta, (double)(ll0 + t0 + std::min(i, k - 1)));
-        if (NTk == 1) SSN_LAUNCH(c, (cand_eval_kernel<1>), egrid, kThreads, 0, a, list.p, total);
-        else if (NTk == 8) SSN_LAUNCH(c, (cand_eval_kernel<8>), egrid, kThreads, 0, a, list.p, total);
-        else if (NTk == 16) SSN_LAUNCH(c, (cand_eval_kernel<16>), egrid, kThreads, 0, a, list.p, total);
-        else SSN_LAUNCH(c, (cand_eval_kernel<32>), egrid, kThreads, 0, a, list.p, total);
-        SSN_LAUNCH(c, trials_lin_finish_kernel, 1, 256, 0, scalpart.p, egrid, NTk, k, 0.25, scratch.p + t0);
+    const double total = read_scalar(c, scratch.p + nt);
+    if (total > (double)cap0) {
+        Buf<int2> list(c, (size_t)total);
+        list_pass(list.p, (unsigned long long)total);
     }
-    c->h_pin[2048] = (double)total;
-    SSN_CUDA(cudaMemcpyAsync(scratch.p + nt, c->h_pin + 2048, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SSN_CUDA(cudaMemcpyAsync(out_dev, scratch.p, sizeof(double) * (nt + 1), cudaMemcpyDeviceToDevice, c->stream));
-    SSN_CUDA(cudaStreamSynchronize(c->stream));          // h_pin is reused by the next call
 }
 
 // lamT[t] = lam + delta^(ll0+t)*zeta for t < nt, and f0_out[2t] = ||lamT[t]||^2, f0_out[2t+1] = wlk'*lamT[t]
