@@ -1350,8 +1350,8 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
     SSN_REQUIRE(lam_old && zeta && wlk && lam_new && ll_max >= 0, SSN_E_INVALID, "linesearch: bad arguments");
     // batch <= 0: adaptive.  With gama = Inf every pass goes through the screened kernels, whose candidate
     // count says how sparse the trial plans are: while fewer than 10 % of the entries survive the screen
-    // a read of w evaluates 32, then 64, then 128 backtracking steps (the evaluation of the candidates
-    // is a few microseconds per 32 steps), 16 below 25 %, else 8 through the dense kernel.
+    // a read of w evaluates 64, then 128 backtracking steps (the evaluation of the candidates is a few
+    // tens of microseconds per 32 steps), 16 below 25 %, else 8 through the dense kernel.
     const bool adaptive = batch <= 0;
     const bool screened = adaptive && c->ls_screen && gama == nullptr && std::isinf(gama_s) && gama_s > 0;
     if (adaptive) batch = kMaxTrials;
@@ -1371,7 +1371,7 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         int want = batch;
         bool lin = screened;
         if (screened && passes > 0) {
-            if (dens <= 0.10) want = std::min(c->ls_max_nt, passes == 1 ? 32 : (passes == 2 ? 64 : 128));
+            if (dens <= 0.10) want = std::min(c->ls_max_nt, passes == 1 ? 64 : 128);
             else if (dens <= 0.25) want = std::min(16, c->ls_max_nt);
             else { want = kMaxTrials; lin = false; }
         }

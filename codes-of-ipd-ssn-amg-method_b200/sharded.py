@@ -227,14 +227,14 @@ class ShardedStep:
         ress = abs(float(Fk_old @ zeta))
         # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
         # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernel, whose vote
-        # count says how sparse the trial plans are -- 32, 64, then 128 steps per read while under 10 % of the
+        # count says how sparse the trial plans are -- 64, then 128 steps per read while under 10 % of the
         # entries survive the screen, 16 under 25 %, else the dense 8-step kernel (as ssn_linesearch does)
         screened = np.isinf(self.gama) and self.gama > 0 and hasattr(self.ops, "prox_trials_lin") and self.screen
         ll, done, passes, dens = 0, False, 0, 1.0
         while not done:                                                              # :189-211, ll = 0 alone, then a batch per pass
             lin = screened and (passes == 0 or dens <= 0.25)
             if lin and passes > 0:
-                nt = (32 if passes == 1 else (64 if passes == 2 else 128)) if dens <= 0.10 else 16
+                nt = (64 if passes == 1 else 128) if dens <= 0.10 else 16
             else:
                 nt = 8 * min(self.world, 4)
             nt = min(1 if passes == 0 else nt, max_ll - ll + 1)
