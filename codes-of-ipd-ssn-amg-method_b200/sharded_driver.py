@@ -152,7 +152,7 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
     kx0, kl0, cx0 = kkt(xk, lk)
     fxk = [cx0]; KKT_xk = [kx0]; KKT_lk = [kl0]
     stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "ls_passes": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm,
-             "solve_ms": 0.0, "asat_ms": 0.0, "plan_ms": 0.0, "E": []}
+             "solve_ms": 0.0, "asat_ms": 0.0, "plan_ms": 0.0, "E": [], "steps": [], "amg_diverged": None}
     t_loop = time.time()
     bk = 1.0
     rr = [np.inf]
@@ -180,8 +180,18 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
             stats["amg_calls"] += 1; stats["ls_trials"] += info["ll"] + 1; stats["ls_passes"] += info["ls_passes"]
             stats["solve_ms"] += info["ms_amg"]; stats["asat_ms"] += info["ms_asat"]; stats["plan_ms"] += info["ms_plan"]
             stats["E"].append(int(info["E"]))
+            stats["steps"].append({"k": k, "ssn_it": ssn_it, "E": int(info["E"]), "nnzH": info["nnzH"], "amg_cycles": int(info["itamg"]),
+                                   "amg_res": float(info["resamg"]), "ll": int(info["ll"]), "ms_plan": info["ms_plan"], "ms_asat": info["ms_asat"],
+                                   "ms_amg": info["ms_amg"]})
             its.append(info["itamg"])
             nF = float(torch.linalg.norm(Fk_new))
+            if not (info["resamg"] <= 1.0) or not math.isfinite(nF):
+                # Class_AMG left its loop on rho > 1 (AMG/Class_AMG.m:106) with a residual above the initial one: the
+                # W-cycle of the reference diverges on this system (the oracle reproduces it: the damped-Jacobi smoother
+                # 0.5*D^-1 of a coarse Galerkin level has lambda_max(R*A) > 2).  The reference would carry on with the
+                # useless direction; the solve is stopped here and says so.
+                stats["amg_diverged"] = {"k": k, "ssn_it": ssn_it, "E": int(info["E"]), "amg_res": float(info["resamg"]), "Fk": nF}
+                break
             if verbose and rank == 0:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={info['ll']:3d} info={list(info['info'])} its={info['itamg']} "
                       f"res={info['resamg']:.2e} E={info['E']}", flush=True)
@@ -194,6 +204,9 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
             if Fk_res / nF >= 2:
                 Fk_res = nF
         A.collectives += step.collectives
+        if stats["amg_diverged"] is not None:
+            stats["ssn_its"].append(ssn_it); stats["lin_its"].append(its)
+            break
         lk1 = lk_new
         # :239-254 in one pass over the slab: xk1 = prox(zk), vk1, Ax(xk1), c'xk1 and the KKT residual of xk1
         xk1, vk1, ax1_loc, cx, kx2 = ops.apd_end(c_loc, wk, xk, A.lam_loc(lk1), A.p_loc, q, tk, ak, gam)

@@ -282,3 +282,52 @@ def test_pcg_errors(gpu):
         gpu.Class_AMG(A, np.ones(10), {"bigph": 1, "retol": None, "maxit": None, "theta": None, "smoth": None,
                                         "cycle": None, "isnsp": None, "inter": None, "guess": None})
     assert ei.value.status == "SSN_E_BIGPH_FNODE"
+
+
+def _disc_active_set(g, r):
+    """(i, j) pairs of the active set ``|x_i - y_j| <= r`` grid cells between two g x g grids (the structure of
+    an early-phase grid OT step); row-major numpy index arrays."""
+    m = g * g
+    idx = np.arange(m); a = idx // g; b = idx % g
+    rows, cols = [], []
+    R = int(np.floor(r))
+    for da in range(-R, R + 1):
+        for db in range(-R, R + 1):
+            if da * da + db * db <= r * r:
+                ok = (a + da >= 0) & (a + da < g) & (b + db >= 0) & (b + db < g)
+                rows.append(idx[ok]); cols.append((a[ok] + da) * g + (b[ok] + db))
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+@pytest.mark.parametrize("g,expect_converged", [(64, True), (181, False)])
+def test_wcycle_behaviour_on_large_disc_systems_matches_oracle(gpu, oracle, g, expect_converged):
+    """Where the reference's W-cycle stops working, the CUDA path must stop working the same way.  On the
+    65522-node system of the 181 x 181 grids the damped-Jacobi smoother 0.5*D^-1 of a coarse Galerkin level
+    has lambda_max(R*A) > 2: Class_AMG leaves its loop after ONE cycle on rho > 1 (AMG/Class_AMG.m:106) with a
+    residual far above the initial one -- in the oracle and on the GPU alike; on the 64 x 64 grids both
+    converge in the same number of cycles.  (This is what stops the 256 x 256 configuration at SsN step 6.)"""
+    import scipy.sparse as sp
+    import torch
+    m = n = g * g
+    i, j = _disc_active_set(g, 4.0)
+    Y = sp.csr_matrix((np.ones(i.size), (i, j)), shape=(m, n))
+    H0 = sp.bmat([[sp.diags(np.asarray(Y.sum(0)).ravel()), Y.T], [Y, sp.diags(np.asarray(Y.sum(1)).ravel())]], format="csc")
+    z = np.random.RandomState(0).standard_normal(m + n)
+    opts = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1, "inter": 1, "guess": None}
+    oracle.rng_reset()
+    _, it_o, res_o, info_o = oracle.Hybrid_AMG({"bk1": 0.5, "tk": 2.0, "p": np.ones(m), "q": np.ones(n), "T": sp.diags(np.zeros(m + n)),
+                                                "H0": H0, "z": z}, opts)
+    s = torch.zeros(m * n, dtype=torch.uint8, device="cuda")
+    s[torch.from_numpy(i + j * m).cuda()] = 1                              # column-major linear index
+    p = torch.ones(m, dtype=torch.float64, device="cuda"); q = torch.ones(n, dtype=torch.float64, device="cuda")
+    Hd = gpu.ASAt(s, p, q)
+    del s
+    assert Hd.nnz == H0.nnz
+    gpu.rng_reset()
+    _, it_g, res_g, info_g = gpu.Hybrid_AMG({"bk1": 0.5, "tk": 2.0, "p": p, "q": q, "T": None, "H0": Hd, "z": torch.from_numpy(z).cuda()}, opts)
+    assert int(info_g[0]) == int(info_o[0]) == 1
+    assert it_g == it_o
+    if expect_converged:
+        assert res_o <= 1e-11 and res_g <= 1e-11
+    else:
+        assert it_o == 1 and res_o > 1e6 and res_g > 1e6

@@ -61,7 +61,7 @@ def main():
                "line_search_trials": st["ls_trials"], "line_search_passes": st["ls_passes"],
                "phase_ms": {"plan_wide_kernels_and_collectives": st["plan_ms"], "asat_assembly": st["asat_ms"], "hybrid_amg_replicated": st["solve_ms"]},
                "E_min_median_max": [int(np.min(st["E"])), int(np.median(st["E"])), int(np.max(st["E"]))] if st["E"] else None,
-               "collectives": st["collectives"], "torch_peak_GB_rank0": peak}
+               "collectives": st["collectives"], "torch_peak_GB_rank0": peak, "steps": st["steps"], "amg_diverged": st["amg_diverged"]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
