@@ -292,7 +292,7 @@ def main():
     r_lin["note"] = (f"a batch of {nt_lin} steps = this kernel + the candidate scan / compact / eval kernels on the surviving entries: "
                      f"{lin_batch_ms:.3f} ms in all (host-timed, synchronous call through the Python binding); share_of_step uses that figure")
     if world == 1:
-        r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials"); r_lin["traffic"] = load_traffic("trials_lin")
+        r_k3["traffic"] = load_traffic("k3"); r_tr["traffic"] = load_traffic("trials"); r_lin["traffic"] = load_traffic("screen")
     cands = sorted([r_lin, r_k3, r_tr], key=lambda r: -r["share_of_step"])
     dominant, other = cands[0], cands[1:]
     out["roofline"] = dominant

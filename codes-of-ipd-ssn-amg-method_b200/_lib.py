@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssnamg.so")
+LIB_PATH = os.environ.get("SSN_LIB_PATH") or os.path.join(_HERE, "libssnamg.so")     # SSN_LIB_PATH: a development build
 
 STATUS = {
     0: "SSN_OK", -1: "SSN_E_CUDA", -2: "SSN_E_INVALID", -3: "SSN_E_PQ_ZERO", -4: "SSN_E_BIGPH_FNODE",

@@ -1065,8 +1065,14 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs a) {
 // same barrier, and the convergence test runs on the device.  Vectors that change during the
 // kernel are read with ld.global.cg (L2), never through the non-coherent path.
 
-constexpr int kPT = 256;
-constexpr int kPBlocksPerSM = 2;
+#ifndef SSN_PT
+#define SSN_PT 256
+#endif
+#ifndef SSN_PBPS
+#define SSN_PBPS 2
+#endif
+constexpr int kPT = SSN_PT;                   // threads per block of the persistent kernel
+constexpr int kPBlocksPerSM = SSN_PBPS;       // resident blocks per SM (the grid is num_sms * kPBlocksPerSM)
 constexpr int kPLevels = 16;
 
 struct PersistArgs {

@@ -50,6 +50,32 @@ def main():
                                     max_seconds=args.max_seconds, verbose=args.verbose)
     st = res["stats"]
     peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    # ---- slab kernels of the plan operators at this size (CUDA events around the launches, rank-local)
+    opb = {}
+    m_loc = r1 - r0
+    p_loc = torch.ones(m_loc, dtype=torch.float64, device="cuda"); qd = torch.ones(n, dtype=torch.float64, device="cuda")
+    lam = torch.randn(n + m_loc, dtype=torch.float64, device="cuda") * 0.01
+    zeta = torch.randn(n + m_loc, dtype=torch.float64, device="cuda") * 0.01
+    w = c_loc - 1.0
+    slab_bytes = 8.0 * m_loc * n
+
+    def ktime(fn, reps=5):
+        for _ in range(2):
+            fn()
+        ssnamg.kernel_timer(True)
+        for _ in range(reps):
+            fn()
+        ms, cnt = ssnamg.kernel_timer_read(); ssnamg.kernel_timer(False)
+        return ms / max(cnt, 1)
+    for name, fn in (("Ax", lambda: ssnamg.Ax(w, p_loc, qd)),
+                     ("prox_residual(Axprox)", lambda: ssnamg.prox_residual(w, lam, p_loc, qd, 0.9, float("inf"), want=("Axprox",))),
+                     ("trials_screen(64 steps)", lambda: ssnamg.prox_trials_lin(w, lam, zeta, p_loc, qd, 0.9, 0.9, 1, 64))):
+        try:
+            ms = ktime(fn)
+            opb[name] = {"ms": ms, "GBps_per_gpu": slab_bytes / ms / 1e6, "GBps_all_gpus": world * slab_bytes / ms / 1e6}
+        except Exception as e:                                          # keep the solve's record even if a microbenchmark fails
+            opb[name] = {"error": str(e)[:200]}
+    del w
     if rank == 0:
         out = {"config": f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}", "n_gpus": world, "plan_entries": m * n,
                "slab_rows": r1 - r0, "slab_GB_per_plan_vector": 8.0 * (r1 - r0) * n / 1e9, "cost_gen_s": t_gen,
@@ -61,7 +87,7 @@ def main():
                "line_search_trials": st["ls_trials"], "line_search_passes": st["ls_passes"],
                "phase_ms": {"plan_wide_kernels_and_collectives": st["plan_ms"], "asat_assembly": st["asat_ms"], "hybrid_amg_replicated": st["solve_ms"]},
                "E_min_median_max": [int(np.min(st["E"])), int(np.median(st["E"])), int(np.max(st["E"]))] if st["E"] else None,
-               "collectives": st["collectives"], "torch_peak_GB_rank0": peak, "steps": st["steps"], "amg_diverged": st["amg_diverged"]}
+               "collectives": st["collectives"], "torch_peak_GB_rank0": peak, "steps": st["steps"], "amg_diverged": st["amg_diverged"], "slab_kernels_rank0": opb}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

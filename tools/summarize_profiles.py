@@ -86,7 +86,7 @@ def main():
     launch_summary(tag)
     tpath = os.path.join(OUT, "traffic.json")
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    for name in ("k3", "trials", "trials_lin", "spgemm", "cycle"):
+    for name in ("k3", "trials", "screen", "spgemm", "cycle"):
         full_capture(name, tag, traffic)
     json.dump(traffic, open(tpath, "w"), indent=1)
 
