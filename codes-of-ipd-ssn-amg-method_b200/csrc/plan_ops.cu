@@ -717,34 +717,33 @@ __global__ void __launch_bounds__(256) trials_finish_kernel(const double* __rest
     }
 }
 
-// lamT[t] = lam + alpha[t]*zeta ; f0part: per-block partials of ||lamT[t]||^2 and wlk'lamT[t]
+// lamT[t] = lam + alpha[t]*zeta ; f0part: per-block partials of ||lamT[t]||^2 and wlk'lamT[t]   (grid: blocks x trials)
 __global__ void __launch_bounds__(256) trial_vectors_kernel(int64_t N, int nt, const double* __restrict__ lam,
                                                             const double* __restrict__ zeta, const double* __restrict__ wlk,
                                                             const double* __restrict__ alpha, double* __restrict__ lamT,
                                                             double* __restrict__ f0part) {
     __shared__ double red[32];
-    for (int t = 0; t < nt; ++t) {
-        const double al = alpha[t];
-        double s2 = 0.0, sw = 0.0;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-            const double v = __dadd_rn(lam[i], __dmul_rn(al, zeta[i]));      // lk_old + delta^ll*zeta
-            lamT[(size_t)t * N + i] = v;
-            s2 = fma(v, v, s2); sw = fma(wlk[i], v, sw);
-        }
-        s2 = block_sum(s2, red);
-        sw = block_sum(sw, red);
-        if (threadIdx.x == 0) { f0part[((size_t)blockIdx.x * nt + t) * 2] = s2; f0part[((size_t)blockIdx.x * nt + t) * 2 + 1] = sw; }
+    const int t = blockIdx.y;
+    const double al = alpha[t];
+    double s2 = 0.0, sw = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = __dadd_rn(lam[i], __dmul_rn(al, zeta[i]));      // lk_old + delta^ll*zeta
+        lamT[(size_t)t * N + i] = v;
+        s2 = fma(v, v, s2); sw = fma(wlk[i], v, sw);
     }
+    s2 = block_sum(s2, red);
+    sw = block_sum(sw, red);
+    if (threadIdx.x == 0) { f0part[((size_t)blockIdx.x * nt + t) * 2] = s2; f0part[((size_t)blockIdx.x * nt + t) * 2 + 1] = sw; }
 }
+// out[v] = sum over blocks of f0part[block][v]  (fixed order), one block per value v < 2*nt
 __global__ void __launch_bounds__(256) trial_f0_finish_kernel(const double* __restrict__ f0part, int nblocks, int nt,
                                                               double* __restrict__ out /* [nt][2] */) {
     __shared__ double red[32];
-    for (int t = 0; t < 2 * nt; ++t) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += f0part[(size_t)b * 2 * nt + t];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) out[t] = s;
-    }
+    const int t = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += f0part[(size_t)b * 2 * nt + t];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[t] = s;
 }
 
 // ------------------------------------------------------------------ fused A-ADMM warm start
@@ -1335,8 +1334,8 @@ void plan_trial_vectors(ssn_ctx* c, const double* lam, const double* zeta, const
     Buf<double> alpha(c, nt), f0part(c, (size_t)nb * nt * 2);
     for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = std::pow(delta, (double)(ll0 + t));
     SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
-    SSN_LAUNCH(c, trial_vectors_kernel, nb, 256, 0, N, nt, lam, zeta, wlk, alpha.p, lamT, f0part.p);
-    SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, f0_out);
+    SSN_LAUNCH(c, trial_vectors_kernel, dim3(nb, nt), 256, 0, N, nt, lam, zeta, wlk, alpha.p, lamT, f0part.p);
+    SSN_LAUNCH(c, trial_f0_finish_kernel, 2 * nt, 256, 0, f0part.p, nb, nt, f0_out);
     SSN_CUDA(cudaStreamSynchronize(c->stream));           // h_pin is reused by the next call
 }
 
@@ -1380,8 +1379,8 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         for (int t = 0; t < nt; ++t) al[t] = std::pow(delta, (double)(ll + t));
         for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = al[t];
         SSN_CUDA(cudaMemcpyAsync(alpha.p, c->h_pin + 1024, sizeof(double) * nt, cudaMemcpyHostToDevice, c->stream));
-        SSN_LAUNCH(c, trial_vectors_kernel, nb, 256, 0, N, nt, lam_old, zeta, wlk, alpha.p, lamT.p, f0part.p);
-        SSN_LAUNCH(c, trial_f0_finish_kernel, 1, 256, 0, f0part.p, nb, nt, res.p + cap + 1);
+        SSN_LAUNCH(c, trial_vectors_kernel, dim3(nb, nt), 256, 0, N, nt, lam_old, zeta, wlk, alpha.p, lamT.p, f0part.p);
+        SSN_LAUNCH(c, trial_f0_finish_kernel, 2 * nt, 256, 0, f0part.p, nb, nt, res.p + cap + 1);
         if (lin) plan_prox_trials_lin(c, w, lam_old, zeta, p, q, m, n, tk, delta, ll, nt, res.p, nonunit);
         else     plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p, nonunit);
         double h[3 * kMaxLinBatch + 1];

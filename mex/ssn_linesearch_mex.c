@@ -1,6 +1,8 @@
 /* [lk_new,ll,cFk_new] = ssn_linesearch_mex(wk,lk_old,zeta,wlk,p,q,tk,bk1,gama,nu,delta,ll_max,cFk_old,ress)
- * -- the Armijo loop of Class1/APD_SsN_Class1.m:189-211 in one call (8 backtracking steps per read of
- * wk).  Optional: the unmodified script keeps working with its own loop over Aty/prox/norm. */
+ * -- the Armijo loop of Class1/APD_SsN_Class1.m:189-211 in one call (batch = 0: the adaptive schedule,
+ * 64-128 backtracking steps per read of wk through the screened kernels while the trial plans are sparse,
+ * 8 through the dense kernel otherwise).  Optional: the unmodified script keeps working with its own loop
+ * over Aty/prox/norm. */
 #include <math.h>
 #include "ssn_mex_common.h"
 
@@ -16,7 +18,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     int ll = 0, passes = 0; double n2 = 0, cF = 0;
     int st = ssn_linesearch(c, w, lo, ze, wl, p, q, (int64_t)m, (int64_t)n, mxGetScalar(prhs[6]), mxGetScalar(prhs[7]), gama,
                             scalar_gama ? mxGetScalar(prhs[8]) : INFINITY, mxGetScalar(prhs[9]), mxGetScalar(prhs[10]),
-                            (int)mxGetScalar(prhs[11]), mxGetScalar(prhs[12]), mxGetScalar(prhs[13]), 8, out, &ll, &n2, &cF, &passes);
+                            (int)mxGetScalar(prhs[11]), mxGetScalar(prhs[12]), mxGetScalar(prhs[13]), 0, out, &ll, &n2, &cF, &passes);
     plhs[0] = ssn_mex_from_device(c, out, N, &st);
     if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(ll);
     if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(cF);
