@@ -10,9 +10,43 @@ namespace ssn {
 
 // ------------------------------------------------------------------ scans / sorts
 
+namespace {
+constexpr int kSmallScanMax = 1 << 18;
+// out[i] = in[0] + ... + in[i-1] for i < n (and out[n] = total when with_total): ONE block, one launch, no
+// temporary storage -- the AMG setup runs ~70 scans of a few thousand counts per hierarchy, where the two
+// kernels + temporary allocation of cub::DeviceScan cost more than the scan itself.  In-place safe.
+__global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* out, int n, int with_total) {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + 1023) / 1024;
+    const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
+    int s = 0;
+    for (int i = i0; i < i1; ++i) s += in[i];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+        wsum[lane] = wi - w;                                 // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    int run = wsum[warp] + incl - s;
+    for (int i = i0; i < i1; ++i) { const int v = in[i]; out[i] = run; run += v; }
+    if (with_total && threadIdx.x == 1023) out[n] = run;
+}
+}  // namespace
+
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
+    if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return 0; }
+    if (n <= kSmallScanMax) {
+        SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1);
+        return (int64_t)read_scalar(c, ptr + n);
+    }
     SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream));
-    if (n == 0) return 0;
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
     Buf<unsigned char> tmp(c, tmp_bytes);
@@ -23,6 +57,7 @@ int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
 
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n) {
     if (n == 0) return;
+    if (n <= kSmallScanMax) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, in, out, (int)n, 0); return; }
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, c->stream));
     Buf<unsigned char> tmp(c, tmp_bytes);
