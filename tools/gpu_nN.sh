@@ -1,3 +1,4 @@
+# bench.py on N GPUs of one box (N = 1: also the plan-operator GPU tests).  Usage: bash tools/gpu_nN.sh N
 cd $GRAFT_REPO_ROOT
 N=$1
 if [ "$N" = "1" ]; then
