@@ -507,6 +507,26 @@ def Class_AMG(A, b, amg_options=None, keep_hierarchy=False):
     return _ret(x, host), it.value, rel.value, relk[:hl.value].copy(), rhok[:hl.value].copy()
 
 
+def twogrid_bigph(A, b, amg_options=None):
+    """``[x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b[,amg_options])`` -- AMG/twogrid_bigph.m:1-116.
+    ``nargin == 2`` defaults of :14-18 and the ``isempty`` defaults of :19-23 are applied here."""
+    torch = _torch(); ctx = context(); host = _is_host(b); Ad = _csr(A, ctx); keep = []
+    if amg_options is None:
+        amg_options = {"retol": 1e-12, "maxit": 20, "fnode": 0, "smoth": 10, "isnsp": 1, "guess": None}
+    opts = dict(amg_options)
+    for k, v in (("retol", 0.0), ("maxit", 50), ("smoth", 3), ("isnsp", 0)):
+        if _empty(opts.get(k)):
+            opts[k] = v
+    o = _amg_options(opts, keep)
+    bd = _dev(b, count=Ad.shape[0])
+    x = torch.empty_like(bd)
+    relk = np.zeros(o.maxit + 2); rhok = np.zeros(o.maxit + 2)
+    it = C.c_int(0); rel = C.c_double(0.0); hl = C.c_int(0)
+    ctx.call("ssn_twogrid_bigph", C.byref(Ad.st), _ptr(bd), C.byref(o), _ptr(x), C.byref(it), C.byref(rel),
+             relk.ctypes.data_as(C.c_void_p), rhok.ctypes.data_as(C.c_void_p), C.byref(hl))
+    return _ret(x, host), it.value, rel.value, relk[:hl.value].copy(), rhok[:hl.value].copy()
+
+
 # ------------------------------------------------------------------ L2: Krylov
 
 def PCG(H, e, pcg_options=None):
@@ -577,6 +597,12 @@ def _solve(entry, prob_data, options, conv, pot=False):
 def Hybrid_AMG(prob_data, amg_options):
     """``[zeta,itamg,resamg,info] = Hybrid_AMG(prob_data,amg_options)`` -- Hybrid_AMG.m:1-114."""
     return _solve("ssn_hybrid_amg", prob_data, amg_options, _amg_options)
+
+
+def Hybrid_twogrid(prob_data, amg_options):
+    """``[zeta,itamg,resamg,info] = Hybrid_twogrid(prob_data,amg_options)`` -- Hybrid_twogrid.m:1-90
+    (``inner_solver = 5``)."""
+    return _solve("ssn_hybrid_twogrid", prob_data, amg_options, _amg_options)
 
 
 def aug_PCG(prob_data, pcg_options):

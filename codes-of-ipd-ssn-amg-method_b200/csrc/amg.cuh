@@ -75,7 +75,8 @@ Csr flags_to_csr(ssn_ctx* c, const CsrView& A, const uint8_t* as_flags);
 // one coarsening step: returns Ac, Pro (and keeps isC / strength flags if requested)
 void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Csr& Ac, Csr& Pro,
               Buf<uint8_t>* isC_out, Buf<uint8_t>* as_out, Csr* Pt_out = nullptr);
-void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o);
+// max_levels > 0 stops the coarsening after that many levels (twogrid_bigph builds exactly two)
+void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels = 0);
 void amg_clear(ssn_ctx* c);
 int coarsest_threshold(int64_t N);
 
@@ -83,6 +84,9 @@ int coarsest_threshold(int64_t N);
 void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev, bool wcycle, bool e_is_zero);
 void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, bool keep, double* x, int* it_out,
                double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
+// [x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b,amg_options) -- AMG/twogrid_bigph.m
+void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, double* x, int* it_out,
+                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
 void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
                double* res_out, double* resk_host);
 
@@ -93,8 +97,9 @@ void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
 // ---- dispatch (solvers.cu)
 void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm, int* r, int* ncomp);
 void rescaled_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Ae, double* f, Buf<double>& qp, Buf<double>& Kd);
+// twogrid = false: Hybrid_AMG.m (Class_AMG per component); true: Hybrid_twogrid.m (twogrid_bigph per component)
 void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* itamg,
-                double* resamg, int* info);
+                double* resamg, int* info, bool twogrid = false);
 void aug_pcg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* itpcg,
              double* respcg, int* info);
 

@@ -652,7 +652,7 @@ static void finish_level(ssn_ctx* c, Level& L, bool bigph_level, int Nf) {
     L.r.alloc(c, n); L.e.alloc(c, n); L.g.alloc(c, n);
 }
 
-void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
+void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels) {
     SSN_REQUIRE(A.nrows == A.ncols, SSN_E_NOT_SQUARE, "Class_AMG: matrix must be square");
     if (o.bigph) SSN_REQUIRE(o.fnode > 0, SSN_E_BIGPH_FNODE, "amg_options.bigph = 1 requires Nf > 0");
     amg_clear(c);
@@ -664,7 +664,8 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o) {
     finish_level(c, H->lv[0], o.bigph != 0, o.fnode);
     const int thr = coarsest_threshold(A.nrows);
     int J = 1;
-    while (H->lv[J - 1].N > thr) {                                        // Class_AMG.m:76
+    // Class_AMG.m:76 coarsens down to the threshold; twogrid_bigph.m:41-47 (max_levels = 2) coarsens exactly once
+    while (max_levels > 0 ? (J < max_levels) : (H->lv[J - 1].N > thr)) {
         SSN_REQUIRE(J < 64, SSN_E_COARSEN_STALL, "coarsening stalled");
         Level nl;
         Buf<uint8_t> isC;

@@ -1804,6 +1804,71 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
     if (!keep) amg_clear(c);                                              // Class_AMG.m:110
 }
 
+// [x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b,amg_options) -- AMG/twogrid_bigph.m:24-116: the two-level
+// method behind Hybrid_twogrid (inner_solver = 5).  Setup (:26-47) is the first coarsening step of
+// Class_AMG with bigph = 1 -- the same block Gauss-Seidel smoother R (:35 == Class_AMG.m:56-59), the same
+// interpolation W = -Aff\Afc, row-normalised when isnsp (:44-46 == transfer.m:20-25), Ac = Pro'*A*Pro --
+// so the hierarchy code builds it with max_levels = 2.  One iteration (twogrid_it, :79-116): `smoth`
+// pre-smoothing steps with R (kernel correction when isnsp), restriction, coarse correction by
+// PCG(Ac, rrc, {retol [] -> 1e-11, maxit 100, precd 2}) (:98-99), prolongation, `smoth` post-smoothing
+// steps with R'.  The outer loop (:62-76) is Class_AMG's.
+void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o_in, double* x, int* it_out,
+                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len) {
+    AmgOptions o = o_in;
+    o.bigph = 1;
+    SSN_REQUIRE(o.fnode > 0 && o.fnode < A.nrows, SSN_E_BIGPH_FNODE, "twogrid_bigph requires 0 < amg_options.fnode < N");
+    amg_setup(c, A, o, 2);
+    Phase ph_solve(c, "twogrid solve loop total");
+    Hierarchy& H = *c->hier;
+    SSN_REQUIRE(H.J == 2, SSN_E_INVALID, "twogrid_bigph: the system is too small for a coarse level");
+    Level& L = H.lv[0]; Level& Lc = H.lv[1];
+    const int n = L.N;
+    if (o.guess) SSN_CUDA(cudaMemcpyAsync(x, o.guess, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    else fill_double(c, x, n, 0.0);
+    ssn_pcg_options po{};
+    po.retol = -1.0; po.maxit = 100; po.precd = 2; po.nf = 0; po.guess_dev = nullptr;       // twogrid_bigph.m:98
+    int it = 0;
+    double rel_res = 0.0;
+    std::vector<double> relk(1, 1.0), rho(1, NAN);
+    double h[2];
+    int np = launch_resid(c, L, b, x, L.r, H.part);                          // r = b - A*x ; res0 = norm(A*x-b)   :61
+    SSN_LAUNCH(c, reduce_parts_kernel, 1, 256, 0, H.part.p, np, H.scal.p);
+    read_back(c, H.scal.p, h, 2);
+    const double res0 = std::sqrt(h[1]);
+    double res_prev = res0;
+    if (res0 == 0.0) {
+        rel_res = 0.0; relk.assign(1, 0.0); rho.assign(1, INFINITY);
+    } else {
+        it = 1;
+        while (relk[it - 1] > o.retol && it <= o.maxit) {                     // :65
+            smooth_host(c, H, 0, o.isnsp, 0, true);                           // :82-90
+            launch_resid(c, L, L.r, (H.smoth == 0) ? nullptr : L.e.p, L.g, H.part);
+            spmv(c, Lc.Pt, L.g, Lc.r);                                        // rrc = Pro'*(r-A*e)   :92
+            pcg_solve(c, Lc.A, Lc.r, &po, Lc.e, nullptr, nullptr, nullptr);   // :99
+            spmv_add(c, Lc.P, Lc.e, L.e);                                     // :107
+            smooth_host(c, H, 0, o.isnsp, 1, false);                          // :109-116
+            SSN_LAUNCH(c, axpy_kernel, cdiv(n, 256), 256, 0, n, 1.0, L.e.p, x);
+            np = launch_resid(c, L, b, x, L.r, H.part);
+            SSN_LAUNCH(c, reduce_parts_kernel, 1, 256, 0, H.part.p, np, H.scal.p);
+            read_back(c, H.scal.p, h, 2);
+            const double res = std::sqrt(h[1]);
+            rel_res = res / res0;
+            relk.push_back(rel_res);
+            rho.push_back(res / res_prev);                                    // res/norm(r)   :71
+            res_prev = res;
+            ++it;
+            if (rho[it - 1] > 1.0) break;                                     // :72
+        }
+        relk.resize(it); rho.resize(it); --it;
+    }
+    if (it_out) *it_out = it;
+    if (rel_res_out) *rel_res_out = rel_res;
+    if (hist_len) *hist_len = (int)relk.size();
+    if (rel_resk) std::memcpy(rel_resk, relk.data(), sizeof(double) * relk.size());
+    if (rhok) std::memcpy(rhok, rho.data(), sizeof(double) * rho.size());
+    amg_clear(c);
+}
+
 // PCG.m:18-105
 void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
                double* res_out, double* resk_host) {

@@ -428,8 +428,11 @@ __global__ void count_less_kernel(int n, const int* __restrict__ sel, int bound,
 
 // =================================================================== Hybrid_AMG
 
+// Hybrid_AMG.m and Hybrid_twogrid.m are the same dispatch (rescaled system, components, large components by the
+// multilevel solver with a random guess, small ones directly); they differ in the solver: Class_AMG
+// (Hybrid_AMG.m:41,70) or twogrid_bigph (Hybrid_twogrid.m:39,67).
 void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* itamg_out,
-                double* resamg_out, int* info) {
+                double* resamg_out, int* info, bool twogrid) {
     SSN_REQUIRE(pd && zeta && pd->z_dev, SSN_E_INVALID, "Hybrid_AMG: bad arguments");
     const int n = (int)pd->n, m = (int)pd->m, N = n + m;
     const double bk1 = pd->bk1, tk = pd->tk;
@@ -448,7 +451,8 @@ void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts
         rng_rand(c, N, guess);                                                // :40
         SSN_LAUNCH(c, scale_kernel, cdiv(N, 256), 256, 0, N, gscale, guess.p);
         o.guess = guess;
-        class_amg(c, Ae, f, o, false, u, &itamg, &resamg, nullptr, nullptr, nullptr);
+        if (twogrid) twogrid_bigph(c, Ae, f, o, u, &itamg, &resamg, nullptr, nullptr, nullptr);
+        else         class_amg(c, Ae, f, o, false, u, &itamg, &resamg, nullptr, nullptr, nullptr);
         it_num = 1;
     } else {                                                                  // :50-107
         std::vector<int> hs(ncomp), hr(ncomp + 1);
@@ -477,7 +481,8 @@ void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts
             SSN_LAUNCH(c, scale_kernel, cdiv(sz, 256), 256, 0, sz, gscale, guess.p);
             o.guess = guess;
             int itk = 0; double resk = 0.0;
-            class_amg(c, Aek, fk, o, false, dk, &itk, &resk, nullptr, nullptr, nullptr);
+            if (twogrid) twogrid_bigph(c, Aek, fk, o, dk, &itk, &resk, nullptr, nullptr, nullptr);
+            else         class_amg(c, Aek, fk, o, false, dk, &itk, &resk, nullptr, nullptr, nullptr);
             SSN_LAUNCH(c, scatter_kernel, cdiv(sz, 256), 256, 0, sz, pk, dk.p, u.p);
             itamg = std::max(itamg, itk); resamg = std::max(resamg, resk);
             it_num = k + 1;                                                   // :80

@@ -136,8 +136,11 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             elif inner_solver == 4:
                 zeta, itpcg, respcg, info = api.Hybrid_AMG(prob_data, amg_options)
                 stats["amg_calls"] += 1
+            elif inner_solver == 5:
+                zeta, itpcg, respcg, info = api.Hybrid_twogrid(prob_data, amg_options)          # :178
+                stats["amg_calls"] += 1
             else:
-                raise ValueError("inner_solver must be 3 (aug_PCG) or 4 (Hybrid_AMG)")
+                raise ValueError("inner_solver must be 3 (aug_PCG), 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
             torch.cuda.synchronize(); stats["solve_s"] += time.time() - t0
             stats["solve_calls"].append((int(ev["count"]), time.time() - t0, int(itpcg), int(info[0])))
             its.append(itpcg)

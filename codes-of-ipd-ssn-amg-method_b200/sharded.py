@@ -52,6 +52,9 @@ class _CudaOps:
     def hybrid_amg(self, prob_data, opts):
         return self.api.Hybrid_AMG(prob_data, opts)
 
+    def hybrid_twogrid(self, prob_data, opts):
+        return self.api.Hybrid_twogrid(prob_data, opts)
+
     def rng_reset(self):
         self.api.rng_reset()
 
@@ -78,7 +81,7 @@ class _CudaOps:
 class ShardedStep:
     """One semismooth-Newton step (Class1/APD_SsN_Class1.m:137-212) on a row-sharded plan."""
 
-    def __init__(self, state, rank, world, ops=None, dist=None, amg_options=None, already_sharded=False):
+    def __init__(self, state, rank, world, ops=None, dist=None, amg_options=None, already_sharded=False, inner_solver=4):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
@@ -101,6 +104,9 @@ class ShardedStep:
         self.counts = [row_range(g, world, m)[1] - row_range(g, world, m)[0] for g in range(world)]
         self.collectives = 0
         self.screen = True
+        if inner_solver not in (4, 5):
+            raise ValueError("inner_solver must be 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
+        self.inner_solver = inner_solver
 
     # ---- slab-local view of a dual vector [column part (n) ; row part (m)]
     def _lam_loc(self, lam):
@@ -220,7 +226,8 @@ class ShardedStep:
         H0 = self.assemble(s_loc)                                                    # :142
         _lap("asat", t0); t0 = _time.perf_counter()
         prob_data = {"bk1": bk1, "tk": tk, "q": self.q, "p": self.p, "T": None, "H0": H0, "z": -Fk_old}
-        zeta, itamg, resamg, info = self.ops.hybrid_amg(prob_data, self.amg_options)  # :161 (replicated)
+        solve = self.ops.hybrid_amg if self.inner_solver == 4 else self.ops.hybrid_twogrid                # :161 / :178
+        zeta, itamg, resamg, info = solve(prob_data, self.amg_options)                # (replicated)
         _lap("amg", t0); t0 = _time.perf_counter()
         f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
         cFk_old = f0 + 0.5 * tk * n2_old

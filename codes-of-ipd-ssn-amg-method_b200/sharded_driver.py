@@ -119,10 +119,11 @@ def warmup_class1_sharded(A, c, b, gama, maxit):
 
 
 def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
-                           ops=None, dist=None, amg_options=None, max_outer=None, max_seconds=None, verbose=False):
+                           ops=None, dist=None, amg_options=None, max_outer=None, max_seconds=None, verbose=False, inner_solver=4):
     """APD outer loop + SsN inner loop of Class1/APD_SsN_Class1.m:32-275 on a row-sharded plan.
     ``c_loc``: this rank's slab of the cost (column-major ``m_loc x n``); ``r, l, p, q``: full vectors,
-    replicated.  Returns the same dictionary on every rank (``xk`` is the rank's slab)."""
+    replicated; ``inner_solver``: 4 = Hybrid_AMG (the reference's default), 5 = Hybrid_twogrid
+    (Class1/APD_SsN_Class1.m:70,161,178).  Returns the same dictionary on every rank (``xk`` is the rank's slab)."""
     import torch
     if dist is None:
         import torch.distributed as dist
@@ -166,7 +167,7 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
         axk = A.finish_ax(ax_loc)
         wlk = bk1 * (lk - 1 / bk * (axk - b)) - b                       # :126
         step = ShardedStep({"wk": wk, "lk": lk, "wlk": wlk, "p": p, "q": q, "bk1": bk1, "tk": tk, "gama": gam}, rank, world,
-                           ops=ops, dist=dist, amg_options=amg_options, already_sharded=True)
+                           ops=ops, dist=dist, amg_options=amg_options, already_sharded=True, inner_solver=inner_solver)
         ssn_it = 0; lk_new = lk.clone()
         ev = step.residual(lk_new, True)                                # :129-130 (+ s for :140)
         Fk_new = bk1 * lk_new - ev[0] - wlk

@@ -319,6 +319,16 @@ SSN_API int ssn_class_amg(ssn_ctx *ctx, const ssn_csr *A, const double *b_dev,
                   double *rel_res_out, double *rel_resk_host, double *rhok_host,
                   int *hist_len_out);
 
+/* [x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b,amg_options) -- AMG/twogrid_bigph.m:24-116, the two-level
+ * method behind Hybrid_twogrid: block Gauss-Seidel smoother and interpolation of the first Class_AMG
+ * level (bigph), coarse correction by PCG(Ac, ., maxit 100, Jacobi).  amg_options.fnode is required;
+ * the caller applies twogrid_bigph.m's own defaults (:14-22: nargin == 2 -> retol 1e-12, maxit 20,
+ * smoth 10, isnsp 1; empty fields -> retol 0, maxit 50, smoth 3, isnsp 0) before the call -- fields
+ * left "empty" here fall back to Class_AMG's.  History buffers as ssn_class_amg. */
+SSN_API int ssn_twogrid_bigph(ssn_ctx *ctx, const ssn_csr *A, const double *b_dev,
+                      const ssn_amg_options *opts, double *x_dev, int *it_out, double *rel_res_out,
+                      double *rel_resk_host, double *rhok_host, int *hist_len_out);
+
 /* ------------------------------------------------------------------ L2: Krylov */
 
 /* [d,it,res,resk] = PCG(H,e,pcg_options) -- PCG.m:18-105.  resk_host: caller buffer of
@@ -339,6 +349,11 @@ SSN_API int ssn_components(ssn_ctx *ctx, const ssn_csr *A, int32_t *blocks_dev, 
  * info_out[2] = {num_comp, it_num}. */
 SSN_API int ssn_hybrid_amg(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts,
                    double *zeta_dev, int *itamg_out, double *resamg_out, int *info_out);
+
+/* [zeta,itamg,resamg,info] = Hybrid_twogrid(prob_data,amg_options) -- Hybrid_twogrid.m:11-89 (inner_solver = 5,
+ * Class1/APD_SsN_Class1.m:178): Hybrid_AMG's dispatch with twogrid_bigph in place of Class_AMG. */
+SSN_API int ssn_hybrid_twogrid(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts,
+                       double *zeta_dev, int *itamg_out, double *resamg_out, int *info_out);
 
 /* [zeta,itpcg,respcg,info] = aug_PCG(prob_data,pcg_options) -- aug_PCG.m:11-37. */
 SSN_API int ssn_aug_pcg(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_options *opts,

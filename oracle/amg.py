@@ -405,3 +405,68 @@ def Class_AMG(A, b, amg_options=None):
                "trace": list(st.trace)}
     st.clear()                                                 # Class_AMG.m:110
     return x, it, rel_res, rel_resk, rhok
+
+
+# ---------------------------------------------------------------- two-grid (Hybrid_twogrid, inner_solver = 5)
+
+def twogrid_bigph(A, b, amg_options=None):
+    """``[x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b[,amg_options])`` -- AMG/twogrid_bigph.m:1-116.
+
+    Setup (:26-47): block Gauss-Seidel smoother ``R = [invV 0; -invT*Afc'*invV invT]``, interpolation
+    ``W = -Aff\\Afc`` (diagonal ``Aff``), row-normalised when ``isnsp``, ``Ac = Pro'*A*Pro``.  One iteration
+    (``twogrid_it``, :79-116): ``smoth`` pre-smoothing steps with ``R``, restriction, coarse correction
+    ``PCG(Ac, rrc, retol [] -> 1e-11, maxit 100, Jacobi)``, prolongation, ``smoth`` post-smoothing steps with ``R'``."""
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    if amg_options is None:                                    # :14-18
+        amg_options = {"retol": 1e-12, "maxit": 20, "fnode": 0, "smoth": 10, "isnsp": 1, "guess": np.zeros_like(b)}
+    o = dict(amg_options)
+    o["retol"] = _opt(o, "retol", 0.0); o["maxit"] = int(_opt(o, "maxit", 50))         # :19-23
+    o["smoth"] = int(_opt(o, "smoth", 3)); o["isnsp"] = _opt(o, "isnsp", 0)
+    o["guess"] = np.asarray(_opt(o, "guess", np.zeros_like(b)), dtype=np.float64).reshape(-1)
+    A = _csc(A)
+    N = A.shape[0]
+    Nf = int(_opt(o, "fnode", 0)); Nc = N - Nf                 # :28
+    if not (0 < Nf < N):
+        raise AMGError("twogrid_bigph requires 0 < amg_options.fnode < N")
+    Aff = A[:Nf, :Nf]; Afc = _csc(A[:Nf, Nf:]); Acc = A[Nf:, Nf:]
+    with np.errstate(divide="ignore"):
+        invV = sp.diags(1.0 / Aff.diagonal(), format="csc")
+        invT = sp.diags(1.0 / Acc.diagonal(), format="csc")
+    R = _csc(sp.bmat([[invV, None], [_csc(-(invT @ Afc.T @ invV)), invT]], format="csc"))      # :35
+    W = _diag_solve(-Aff.diagonal(), Afc)                      # :42  W = -Aff\Afc (Aff diagonal on a bigraph)
+    if o["isnsp"] == 1:
+        W = _diag_solve(spmv(W, np.ones(Nc)), W)               # :44
+    Pro = _csc(sp.vstack([W, sp.identity(Nc, format="csc")]))
+    Ac = spgemm(spgemm(_csc(Pro.T), A), Pro)                   # :47
+    Rt = _csc(R.T)
+    aux = _kernel_aux(A) if o["isnsp"] else None
+    pcg_options = {"retol": None, "maxit": 100, "precd": 2, "guess": None}              # :98
+
+    def twogrid_it(r):
+        e = _smooth(A, R, r, np.zeros_like(r), o["isnsp"], o["smoth"], aux)            # :82-90
+        rrc = Pro.T @ (r - A @ e)                              # :92
+        eec = PCG(Ac, rrc, pcg_options)[0]                     # :99
+        e = e + Pro @ eec                                      # :107
+        return _smooth(A, Rt, r, e, o["isnsp"], o["smoth"], aux)                       # :109-116
+
+    it = 0
+    rhok = [np.nan]; rel_resk = [1.0]
+    x = o["guess"].copy()
+    res0 = np.linalg.norm(A @ x - b)                           # :61
+    rel_res = None
+    if res0 == 0:
+        rel_res = 0.0; rel_resk = np.array([0.0]); rhok = np.array([np.inf])
+    else:
+        it = 1
+        while rel_resk[it - 1] > o["retol"] and it <= o["maxit"]:                      # :65
+            r = b - A @ x
+            x = x + twogrid_it(r)
+            res = np.linalg.norm(A @ x - b); rel_res = res / res0
+            rel_resk.append(rel_res)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rhok.append(res / np.linalg.norm(r))
+            it += 1
+            if rhok[it - 1] > 1:
+                break
+        rel_resk = np.array(rel_resk[:it]); rhok = np.array(rhok[:it]); it -= 1
+    return x, it, rel_res, rel_resk, rhok

@@ -6,7 +6,7 @@ import scipy.sparse.csgraph as csgraph
 import scipy.sparse.linalg as spla
 
 from . import rng as _rng
-from .amg import Class_AMG, _csc
+from .amg import Class_AMG, twogrid_bigph, _csc
 from .pcg import PCG
 from .plan_ops import Ax
 
@@ -65,8 +65,15 @@ def rescaled_system(prob_data):
     return qp, A0, Qd, Kd, Ae, f
 
 
-def Hybrid_AMG(prob_data, amg_options):
+def Hybrid_twogrid(prob_data, amg_options):
+    """``[zeta,itamg,resamg,info] = Hybrid_twogrid(prob_data,amg_options)`` -- Hybrid_twogrid.m:11-89: the
+    dispatch of Hybrid_AMG with ``twogrid_bigph`` (:39, :67) in place of ``Class_AMG``."""
+    return Hybrid_AMG(prob_data, amg_options, _solver=twogrid_bigph)
+
+
+def Hybrid_AMG(prob_data, amg_options, _solver=None):
     """``[zeta,itamg,resamg,info] = Hybrid_AMG(prob_data,amg_options)`` -- Hybrid_AMG.m:11-113."""
+    solver = _solver or Class_AMG
     bk1 = float(prob_data["bk1"]); tk = float(prob_data["tk"])
     q = np.asarray(prob_data["q"]).reshape(-1)
     qp, A0, Qd, Kd, Ae, f = rescaled_system(prob_data)
@@ -81,7 +88,7 @@ def Hybrid_AMG(prob_data, amg_options):
         opts["isnsp"] = 0 if Kd.sum() else 1
         opts["fnode"] = n
         opts["guess"] = (bk1 * tk) * _rng.rand(M)                        # :40
-        u, itamg, resamg, _, _ = Class_AMG(Ae, f, opts)
+        u, itamg, resamg, _, _ = solver(Ae, f, opts)
         it_num = 1
     if num_comp > 1:                                                     # :50-107
         N0 = 100
@@ -92,7 +99,7 @@ def Hybrid_AMG(prob_data, amg_options):
             opts["isnsp"] = 0 if Kd[pk].sum() else 1
             opts["fnode"] = int(np.count_nonzero(pk < n))                # :68  sum(pk<=n), 1-based
             opts["guess"] = (bk1 * tk) * _rng.rand(pk.size)              # :69
-            dk, itk, resk, _, _ = Class_AMG(Aek, fk, opts)
+            dk, itk, resk, _, _ = solver(Aek, fk, opts)
             u[pk] = dk; itamg = max(itamg, itk); resamg = max(resamg, resk)
             it_num = int(k) + 1                                          # :80 (1-based k)
         b2s = sizes[blocks - 1]

@@ -219,3 +219,47 @@ def test_full_size_128x128_grid_systems(gpu, oracle, tag):
     assert np.linalg.norm(zeta - z_ref) <= 1e-6 * np.linalg.norm(z_ref)
     Jk = pd["bk1"] * sp.identity(m + n) + H_ref / pd["tk"]
     assert np.linalg.norm(Jk @ zeta - pd["z"]) <= 1e-9 * np.linalg.norm(pd["z"])
+
+
+
+@pytest.mark.parametrize("dens,unit", [(0.25, True), (0.25, False), (0.02, False)])
+def test_hybrid_twogrid_matches_oracle(gpu, oracle, dens, unit):
+    """Hybrid_twogrid.m / AMG/twogrid_bigph.m (inner_solver = 5) through the C ABI against the oracle: same
+    components, same number of two-grid iterations, solution <= 1e-7 relative, KKT residual <= 1e-8."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(14)
+    m, n = 150, 130
+    s = rs.random_sample(m * n) < dens
+    p, q = (np.ones(m), np.ones(n)) if unit else (rs.random_sample(m) + 0.5, rs.random_sample(n) + 0.5)
+    H0 = oracle.ASAt(s, p, q)
+    z = rs.standard_normal(m + n)
+    opts = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1, "inter": 1, "guess": None}
+    pd = {"bk1": 0.3, "tk": 0.8, "p": p, "q": q, "T": sp.diags(np.zeros(m + n)), "H0": H0, "z": z}
+    oracle.rng_reset(); gpu.rng_reset()
+    z_ref, it_ref, res_ref, info_ref = oracle.Hybrid_twogrid(pd, opts)
+    zeta, it, res, info = gpu.Hybrid_twogrid(pd, opts)
+    assert list(info) == list(info_ref)
+    assert it == it_ref
+    assert np.linalg.norm(zeta - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
+    Jk = 0.3 * sp.identity(m + n) + H0 / 0.8
+    assert np.linalg.norm(Jk @ zeta - z) <= 1e-8 * np.linalg.norm(z)
+
+
+def test_twogrid_bigph_matches_oracle(gpu, oracle):
+    """twogrid_bigph on its own, with explicit options and with the function's own defaults for empty fields
+    (retol [] -> 0, i.e. run to maxit): iteration counts and residual histories as the oracle's."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(3)
+    m, n = 120, 100
+    s = rs.random_sample(m * n) < 0.2
+    H0 = oracle.ASAt(s, np.ones(m), np.ones(n))
+    A = (0.1 * sp.identity(m + n) + H0).tocsc()
+    A = (sp.diags(A.diagonal()) - (A - sp.diags(A.diagonal()))).tocsc()          # [V -U; -U' T]
+    b = rs.standard_normal(m + n)
+    for o in ({"retol": 1e-10, "maxit": 40, "fnode": n, "smoth": 3, "isnsp": 0, "guess": None},
+              {"retol": None, "maxit": 4, "fnode": n, "smoth": None, "isnsp": None, "guess": None}):
+        x_ref, it_ref, rel_ref, relk_ref, rhok_ref = oracle.twogrid_bigph(A, b, o)
+        x, it, rel, relk, rhok = gpu.twogrid_bigph(A, b, o)
+        assert it == it_ref and len(relk) == len(relk_ref)
+        assert np.allclose(relk, relk_ref, rtol=1e-5, atol=1e-13)
+        assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)

@@ -241,3 +241,39 @@ def test_class2_partial_ot_oracle_against_highs(oracle):
     assert res.status == 0
     assert abs(out["fxk"][-1] - res.fun) <= 1e-6 * max(1.0, abs(res.fun))
     assert abs(phi @ out["xk"] - mu) <= 1e-6 * (1 + mu)
+
+
+
+def test_twogrid_bigph_and_hybrid_twogrid_solve_the_kkt_system():
+    """AMG/twogrid_bigph.m and Hybrid_twogrid.m (inner_solver = 5) in the oracle: the two-level method solves
+    the rescaled KKT system of a connected and of a disconnected active set to its tolerance, returns the
+    same solution as Hybrid_AMG, and honours the function's own option defaults."""
+    import scipy.sparse as sp
+    import oracle
+    rs = np.random.RandomState(4)
+    m, n = 60, 50
+    opts = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1, "inter": 1, "guess": None}
+    for dens in (0.25, 0.02):
+        s = rs.random_sample(m * n) < dens
+        p = rs.random_sample(m) + 0.5; q = rs.random_sample(n) + 0.5
+        H0 = oracle.ASAt(s, p, q)
+        z = rs.standard_normal(m + n)
+        pd = {"bk1": 0.3, "tk": 0.8, "p": p, "q": q, "T": sp.diags(np.zeros(m + n)), "H0": H0, "z": z}
+        oracle.rng_reset()
+        zeta, it, res, info = oracle.Hybrid_twogrid(pd, opts)
+        Jk = 0.3 * sp.identity(m + n) + H0 / 0.8
+        assert np.linalg.norm(Jk @ zeta - z) <= 1e-8 * np.linalg.norm(z)
+        oracle.rng_reset()
+        zeta2, _, _, info2 = oracle.Hybrid_AMG(pd, opts)
+        assert np.array_equal(info, info2)
+        assert np.allclose(zeta, zeta2, rtol=1e-7, atol=1e-10)
+    # twogrid_bigph on its own: a bigraph system [V -U; -U' T] with the first Nf nodes as F nodes
+    s = rs.random_sample(m * n) < 0.3
+    H0 = oracle.ASAt(s, np.ones(m), np.ones(n))
+    A = (0.1 * sp.identity(m + n) + H0.multiply(1.0) ).tocsc()
+    A = (sp.diags(A.diagonal()) - (A - sp.diags(A.diagonal()))).tocsc()          # Laplacian sign pattern
+    b = rs.standard_normal(m + n)
+    x, it, rel, relk, rhok = oracle.twogrid_bigph(A, b, {"retol": 1e-10, "maxit": 40, "fnode": n, "smoth": 3, "isnsp": 0, "guess": None})
+    assert rel <= 1e-10 and len(relk) == it + 1 and np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
+    x2, it2, rel2, _, _ = oracle.twogrid_bigph(A, b, {"retol": None, "maxit": 3, "fnode": n, "smoth": None, "isnsp": None, "guess": None})
+    assert it2 == 3 and rel2 > 0                              # retol [] -> 0: runs to maxit

@@ -78,6 +78,13 @@ class OracleOps:
         zeta, it, res, info = self.o.Hybrid_AMG(d, opts)
         return torch.from_numpy(np.asarray(zeta)), it, res, info
 
+    def hybrid_twogrid(self, pd, opts):
+        N = pd["p"].numel() + pd["q"].numel()
+        d = {"bk1": pd["bk1"], "tk": pd["tk"], "p": self._np(pd["p"]), "q": self._np(pd["q"]),
+             "T": sp.diags(np.zeros(N)), "H0": pd["H0"], "z": self._np(pd["z"])}
+        zeta, it, res, info = self.o.Hybrid_twogrid(d, opts)
+        return torch.from_numpy(np.asarray(zeta)), it, res, info
+
     def rng_reset(self):
         self.o.rng_reset()
 

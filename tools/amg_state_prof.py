@@ -34,6 +34,13 @@ def main():
                   f"launches={ssnamg.launch_count() - l0}")
         if prof:
             print(ssnamg.profile_dump())
+    ssnamg.profile(False)
+    for rep in range(3):                                    # the two-level alternative (inner_solver = 5) on the same system
+        ssnamg.rng_reset(); l0 = ssnamg.launch_count(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        zeta2, it2, res2, info2 = ssnamg.Hybrid_twogrid(pd, opts)
+        torch.cuda.synchronize()
+        print(f"Hybrid_twogrid: comps={info2[0]} its={it2} res={res2:.1e} ms={(time.perf_counter() - t0) * 1e3:.2f} "
+              f"launches={ssnamg.launch_count() - l0} |zeta - zeta_amg|/|zeta_amg|={float(torch.linalg.norm(zeta2 - zeta) / torch.linalg.norm(zeta)):.1e}")
 
 
 if __name__ == "__main__":

@@ -33,12 +33,13 @@ def main():
     pd = {"bk1": 0.5, "tk": 2.0, "q": q, "p": p, "T": None, "H0": H0, "z": z}
     opts = ssnamg.driver.CLASS1_AMG_OPTIONS
     ssnamg.profile(True)
-    for rep in range(2):
-        ssnamg.rng_reset(); torch.cuda.synchronize(); t0 = time.perf_counter()
-        zeta, it, res, info = ssnamg.Hybrid_AMG(pd, opts)
-        torch.cuda.synchronize()
-        print(f"g={g} r={r} E={E} nnz(H0)={H0.nnz} comps={info[0]} cycles={it} res={res:.2e} |zeta|={float(torch.linalg.norm(zeta)):.3e} "
-              f"ms={(time.perf_counter() - t0) * 1e3:.1f}", flush=True)
+    for name, solver in (("Hybrid_AMG", ssnamg.Hybrid_AMG), ("Hybrid_twogrid", ssnamg.Hybrid_twogrid)):
+        for rep in range(2):
+            ssnamg.rng_reset(); torch.cuda.synchronize(); t0 = time.perf_counter()
+            zeta, it, res, info = solver(pd, opts)
+            torch.cuda.synchronize()
+            print(f"{name}: g={g} r={r} E={E} nnz(H0)={H0.nnz} comps={info[0]} its={it} res={res:.2e} |zeta|={float(torch.linalg.norm(zeta)):.3e} "
+                  f"ms={(time.perf_counter() - t0) * 1e3:.1f}", flush=True)
     dump = ssnamg.profile_dump()
     print("\n".join(l for l in dump.splitlines() if "levels" in l or "solve." in l or "total" in l))
 

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--max-seconds", type=float, default=None)
     ap.add_argument("--warm-maxit", type=int, default=100)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--inner-solver", type=int, default=4, help="4 = Hybrid_AMG (reference default), 5 = Hybrid_twogrid")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,7 +48,7 @@ def main():
     ssnamg.rng_reset()
     res = sd.APD_SsN_Class1_sharded(c_loc, dev(r), dev(l), dev(np.ones(m)), dev(np.ones(n)), rank, world,
                                     dist=dist if world > 1 else None, warm_maxit=args.warm_maxit, max_outer=args.max_outer,
-                                    max_seconds=args.max_seconds, verbose=args.verbose)
+                                    max_seconds=args.max_seconds, verbose=args.verbose, inner_solver=args.inner_solver)
     st = res["stats"]
     peak = torch.cuda.max_memory_allocated() / 2 ** 30
     # ---- slab kernels of the plan operators at this size (CUDA events around the launches, rank-local)
@@ -77,7 +78,7 @@ def main():
             opb[name] = {"error": str(e)[:200]}
     del w
     if rank == 0:
-        out = {"config": f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}", "n_gpus": world, "plan_entries": m * n,
+        out = {"config": f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}", "n_gpus": world, "inner_solver": args.inner_solver, "plan_entries": m * n,
                "slab_rows": r1 - r0, "slab_GB_per_plan_vector": 8.0 * (r1 - r0) * n / 1e9, "cost_gen_s": t_gen,
                "warmup_s": res["warmup_seconds"], "loop_s": res["seconds"], "outer_its": res["outer_its"],
                "converged": bool(st["converged"]), "rel_kkt": res["rel_kkt"], "objective": res["fxk"][-1],
