@@ -113,6 +113,7 @@ SIGNATURES = {
     "ssn_hybrid_amg": (_int, [_vp, C.POINTER(ProbData), C.POINTER(AmgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_hybrid_twogrid": (_int, [_vp, C.POINTER(ProbData), C.POINTER(AmgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_twogrid_bigph": (_int, [_vp, _pcsr, _vp, C.POINTER(AmgOptions), _vp, _pint, _pdbl, _vp, _vp, _pint]),
+    "ssn_twogrid": (_int, [_vp, _pcsr, _vp, C.POINTER(AmgOptions), _vp, _pint, _pdbl, _vp, _vp, _pint]),
     "ssn_aug_pcg": (_int, [_vp, C.POINTER(ProbData), C.POINTER(PcgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_amg4pot": (_int, [_vp, C.POINTER(ProbData), C.POINTER(AmgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_pcg4pot": (_int, [_vp, C.POINTER(ProbData), C.POINTER(PcgOptions), _vp, _pint, _pdbl, _pint]),

@@ -507,14 +507,12 @@ def Class_AMG(A, b, amg_options=None, keep_hierarchy=False):
     return _ret(x, host), it.value, rel.value, relk[:hl.value].copy(), rhok[:hl.value].copy()
 
 
-def twogrid_bigph(A, b, amg_options=None):
-    """``[x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b[,amg_options])`` -- AMG/twogrid_bigph.m:1-116.
-    ``nargin == 2`` defaults of :14-18 and the ``isempty`` defaults of :19-23 are applied here."""
+def _twogrid_call(symbol, A, b, amg_options, nargin2_defaults, empty_defaults):
     torch = _torch(); ctx = context(); host = _is_host(b); Ad = _csr(A, ctx); keep = []
     if amg_options is None:
-        amg_options = {"retol": 1e-12, "maxit": 20, "fnode": 0, "smoth": 10, "isnsp": 1, "guess": None}
+        amg_options = nargin2_defaults
     opts = dict(amg_options)
-    for k, v in (("retol", 0.0), ("maxit", 50), ("smoth", 3), ("isnsp", 0)):
+    for k, v in empty_defaults:
         if _empty(opts.get(k)):
             opts[k] = v
     o = _amg_options(opts, keep)
@@ -522,9 +520,25 @@ def twogrid_bigph(A, b, amg_options=None):
     x = torch.empty_like(bd)
     relk = np.zeros(o.maxit + 2); rhok = np.zeros(o.maxit + 2)
     it = C.c_int(0); rel = C.c_double(0.0); hl = C.c_int(0)
-    ctx.call("ssn_twogrid_bigph", C.byref(Ad.st), _ptr(bd), C.byref(o), _ptr(x), C.byref(it), C.byref(rel),
+    ctx.call(symbol, C.byref(Ad.st), _ptr(bd), C.byref(o), _ptr(x), C.byref(it), C.byref(rel),
              relk.ctypes.data_as(C.c_void_p), rhok.ctypes.data_as(C.c_void_p), C.byref(hl))
     return _ret(x, host), it.value, rel.value, relk[:hl.value].copy(), rhok[:hl.value].copy()
+
+
+def twogrid_bigph(A, b, amg_options=None):
+    """``[x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b[,amg_options])`` -- AMG/twogrid_bigph.m:1-116.
+    ``nargin == 2`` defaults of :14-18 and the ``isempty`` defaults of :19-23 are applied here."""
+    return _twogrid_call("ssn_twogrid_bigph", A, b, amg_options,
+                         {"retol": 1e-12, "maxit": 20, "fnode": 0, "smoth": 10, "isnsp": 1, "guess": None},
+                         (("retol", 0.0), ("maxit", 50), ("smoth", 3), ("isnsp", 0)))
+
+
+def twogrid(A, b, amg_options=None):
+    """``[x,it,rel_res,rel_resk,rhok] = twogrid(A,b[,amg_options])`` -- AMG/twogrid.m:1-150 (``nargin == 2``
+    defaults of :16-21, ``isempty`` defaults of :22-34)."""
+    return _twogrid_call("ssn_twogrid", A, b, amg_options,
+                         {"retol": 1e-12, "bigph": 0, "maxit": 20, "smoth": 10, "isnsp": 1, "guess": None},
+                         (("retol", 0.0), ("bigph", 0), ("maxit", 50), ("smoth", 3), ("isnsp", 0), ("fnode", 0)))
 
 
 # ------------------------------------------------------------------ L2: Krylov

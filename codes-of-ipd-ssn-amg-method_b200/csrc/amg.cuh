@@ -84,9 +84,9 @@ int coarsest_threshold(int64_t N);
 void mg_cycle(ssn_ctx* c, const double* r_dev, int isnsp, int k1, double* e_dev, bool wcycle, bool e_is_zero);
 void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, bool keep, double* x, int* it_out,
                double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
-// [x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b,amg_options) -- AMG/twogrid_bigph.m
+// [x,it,rel_res,rel_resk,rhok] = twogrid_bigph(A,b,amg_options) -- AMG/twogrid_bigph.m; generic: AMG/twogrid.m
 void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o, double* x, int* it_out,
-                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len);
+                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len, bool generic = false);
 void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
                double* res_out, double* resk_host);
 

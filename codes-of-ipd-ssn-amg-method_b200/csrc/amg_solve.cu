@@ -1812,11 +1812,21 @@ void class_amg(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& 
 // pre-smoothing steps with R (kernel correction when isnsp), restriction, coarse correction by
 // PCG(Ac, rrc, {retol [] -> 1e-11, maxit 100, precd 2}) (:98-99), prolongation, `smoth` post-smoothing
 // steps with R'.  The outer loop (:62-76) is Class_AMG's.
+//
+// generic = true is AMG/twogrid.m:1-150, the same method for a general graph Laplacian: with bigph = 0 the
+// smoother is damped Jacobi 0.5*D^-1 (:59) and the coarse level comes from mis_set(A,1/4) + the standard
+// interpolation W1 + 0.5*W2 (:73-92) -- the MIS step of transfer.m with theta = 1/4; with bigph = 1 it is
+// twogrid_bigph after the checks of :36-38,46-48.
 void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptions& o_in, double* x, int* it_out,
-                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len) {
+                   double* rel_res_out, double* rel_resk, double* rhok, int* hist_len, bool generic) {
     AmgOptions o = o_in;
-    o.bigph = 1;
-    SSN_REQUIRE(o.fnode > 0 && o.fnode < A.nrows, SSN_E_BIGPH_FNODE, "twogrid_bigph requires 0 < amg_options.fnode < N");
+    if (generic) {
+        o.theta = 0.25; o.inter = 1;                                          // twogrid.m:73,84-88
+        if (o.bigph) SSN_REQUIRE(o.fnode > 0, SSN_E_BIGPH_FNODE, "bigph = 1 requires fnode > 0");      // :36-38
+    } else {
+        o.bigph = 1;
+    }
+    if (o.bigph) SSN_REQUIRE(o.fnode > 0 && o.fnode < A.nrows, SSN_E_BIGPH_FNODE, "twogrid_bigph requires 0 < amg_options.fnode < N");
     amg_setup(c, A, o, 2);
     Phase ph_solve(c, "twogrid solve loop total");
     Hierarchy& H = *c->hier;

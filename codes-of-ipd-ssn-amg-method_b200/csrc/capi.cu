@@ -388,6 +388,13 @@ int ssn_twogrid_bigph(ssn_ctx* c, const ssn_csr* A, const double* b, const ssn_a
         twogrid_bigph(c, *A, b, resolve_options(opts), x, it, rel_res, rel_resk, rhok, hist_len); sync(c);
     });
 }
+int ssn_twogrid(ssn_ctx* c, const ssn_csr* A, const double* b, const ssn_amg_options* opts, double* x, int* it,
+                double* rel_res, double* rel_resk, double* rhok, int* hist_len) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(A && b && x, SSN_E_INVALID, "twogrid: null");
+        twogrid_bigph(c, *A, b, resolve_options(opts), x, it, rel_res, rel_resk, rhok, hist_len, true); sync(c);
+    });
+}
 int ssn_aug_pcg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* it, double* res, int* info) {
     return guarded(c, [&] { aug_pcg(c, pd, opts, zeta, it, res, info); });
 }

@@ -329,6 +329,15 @@ SSN_API int ssn_twogrid_bigph(ssn_ctx *ctx, const ssn_csr *A, const double *b_de
                       const ssn_amg_options *opts, double *x_dev, int *it_out, double *rel_res_out,
                       double *rel_resk_host, double *rhok_host, int *hist_len_out);
 
+/* [x,it,rel_res,rel_resk,rhok] = twogrid(A,b,amg_options) -- AMG/twogrid.m:1-150, the two-grid method for a
+ * general graph Laplacian: bigph = 1 is twogrid_bigph (fnode required, "bigph = 1 requires fnode > 0" :37
+ * <-> SSN_E_BIGPH_FNODE, "Nf is not right for the bigraph" :47 <-> SSN_E_NOT_BIGRAPH); bigph = 0 smooths
+ * with damped Jacobi 0.5*D^-1 and coarsens with mis_set(A,1/4) + standard interpolation (consumes the
+ * random stream like transfer).  Defaults as twogrid_bigph (plus bigph 0), applied by the caller. */
+SSN_API int ssn_twogrid(ssn_ctx *ctx, const ssn_csr *A, const double *b_dev, const ssn_amg_options *opts,
+                double *x_dev, int *it_out, double *rel_res_out, double *rel_resk_host,
+                double *rhok_host, int *hist_len_out);
+
 /* ------------------------------------------------------------------ L2: Krylov */
 
 /* [d,it,res,resk] = PCG(H,e,pcg_options) -- PCG.m:18-105.  resk_host: caller buffer of

@@ -21,6 +21,6 @@ from .rng import MatlabRand, GLOBAL_STREAM, rand, rng_reset          # noqa: F40
 from .plan_ops import Ax, Aty, ASAt, ASAtz, invAAt, invHHt, explicit_A  # noqa: F401
 from .pcg import PCG                                                  # noqa: F401
 from .amg import (strength, mis_set, cf_split, transfer, Class_AMG,   # noqa: F401
-                  MG_Vcycle, MG_Wcycle, amg_state, twogrid_bigph)
+                  MG_Vcycle, MG_Wcycle, amg_state, twogrid_bigph, twogrid)
 from .solvers import (components, Hybrid_AMG, Hybrid_twogrid, aug_PCG, AMG4POT,       # noqa: F401
                       PCG4POT)

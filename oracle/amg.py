@@ -438,27 +438,32 @@ def twogrid_bigph(A, b, amg_options=None):
         W = _diag_solve(spmv(W, np.ones(Nc)), W)               # :44
     Pro = _csc(sp.vstack([W, sp.identity(Nc, format="csc")]))
     Ac = spgemm(spgemm(_csc(Pro.T), A), Pro)                   # :47
+    return _twogrid_solve(A, b, o, R, Pro, Ac)
+
+
+def _twogrid_solve(A, b, o, R, Pro, Ac):
+    """Solve phase shared by twogrid_bigph.m:57-116 and twogrid.m:95-150 (identical text)."""
     Rt = _csc(R.T)
     aux = _kernel_aux(A) if o["isnsp"] else None
-    pcg_options = {"retol": None, "maxit": 100, "precd": 2, "guess": None}              # :98
+    pcg_options = {"retol": None, "maxit": 100, "precd": 2, "guess": None}              # twogrid_bigph.m:98, twogrid.m:136
 
     def twogrid_it(r):
-        e = _smooth(A, R, r, np.zeros_like(r), o["isnsp"], o["smoth"], aux)            # :82-90
-        rrc = Pro.T @ (r - A @ e)                              # :92
-        eec = PCG(Ac, rrc, pcg_options)[0]                     # :99
-        e = e + Pro @ eec                                      # :107
-        return _smooth(A, Rt, r, e, o["isnsp"], o["smoth"], aux)                       # :109-116
+        e = _smooth(A, R, r, np.zeros_like(r), o["isnsp"], o["smoth"], aux)            # pre-smoothing
+        rrc = Pro.T @ (r - A @ e)                              # restriction
+        eec = PCG(Ac, rrc, pcg_options)[0]                     # coarse correction
+        e = e + Pro @ eec                                      # prolongation
+        return _smooth(A, Rt, r, e, o["isnsp"], o["smoth"], aux)                       # post-smoothing with R'
 
     it = 0
     rhok = [np.nan]; rel_resk = [1.0]
     x = o["guess"].copy()
-    res0 = np.linalg.norm(A @ x - b)                           # :61
+    res0 = np.linalg.norm(A @ x - b)
     rel_res = None
     if res0 == 0:
         rel_res = 0.0; rel_resk = np.array([0.0]); rhok = np.array([np.inf])
     else:
         it = 1
-        while rel_resk[it - 1] > o["retol"] and it <= o["maxit"]:                      # :65
+        while rel_resk[it - 1] > o["retol"] and it <= o["maxit"]:
             r = b - A @ x
             x = x + twogrid_it(r)
             res = np.linalg.norm(A @ x - b); rel_res = res / res0
@@ -470,3 +475,31 @@ def twogrid_bigph(A, b, amg_options=None):
                 break
         rel_resk = np.array(rel_resk[:it]); rhok = np.array(rhok[:it]); it -= 1
     return x, it, rel_res, rel_resk, rhok
+
+
+def twogrid(A, b, amg_options=None):
+    """``[x,it,rel_res,rel_resk,rhok] = twogrid(A,b[,amg_options])`` -- AMG/twogrid.m:1-150: the two-grid method
+    for a general graph Laplacian.  ``bigph = 1``: the bigraph setup of twogrid_bigph after the checks of
+    :36-38 and :46-48; ``bigph = 0``: damped Jacobi ``0.5*D^-1`` (:59) and ``mis_set(A,1/4)`` + the standard
+    interpolation ``W1 + 0.5*W2`` (:73-92, the MIS step of transfer.m with theta = 1/4)."""
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    if amg_options is None:                                    # :16-21
+        amg_options = {"retol": 1e-12, "bigph": 0, "maxit": 20, "smoth": 10, "isnsp": 1, "guess": np.zeros_like(b)}
+    o = dict(amg_options)
+    o["retol"] = _opt(o, "retol", 0.0); o["bigph"] = _opt(o, "bigph", 0)               # :22-34
+    o["maxit"] = int(_opt(o, "maxit", 50)); o["smoth"] = int(_opt(o, "smoth", 3)); o["isnsp"] = _opt(o, "isnsp", 0)
+    o["guess"] = np.asarray(_opt(o, "guess", np.zeros_like(b)), dtype=np.float64).reshape(-1)
+    o["fnode"] = int(_opt(o, "fnode", 0))
+    if o["bigph"] and o["fnode"] <= 0:
+        raise AMGError("bigph = 1 requires fnode > 0")                                  # :36-38
+    A = _csc(A)
+    if o["bigph"]:
+        Nf = o["fnode"]
+        Aff = _csc(A[:Nf, :Nf])
+        if _csc(Aff - sp.diags(Aff.diagonal())).nnz and abs(Aff - sp.diags(Aff.diagonal())).max() != 0:
+            raise AMGError("Nf is not right for the bigraph")                           # :46-48
+        return twogrid_bigph(A, b, o)
+    with np.errstate(divide="ignore"):
+        R = _csc(0.5 * sp.diags(1.0 / A.diagonal(), format="csc"))                      # :59
+    Ac, Pro = transfer(A, {"theta": 1 / 4, "bigph": 0, "inter": 1, "isnsp": o["isnsp"]}, J=2)       # :73-94
+    return _twogrid_solve(A, b, o, R, Pro, Ac)

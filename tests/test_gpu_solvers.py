@@ -263,3 +263,34 @@ def test_twogrid_bigph_matches_oracle(gpu, oracle):
         assert it == it_ref and len(relk) == len(relk_ref)
         assert np.allclose(relk, relk_ref, rtol=1e-5, atol=1e-13)
         assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+
+
+def test_generic_twogrid_matches_oracle(gpu, oracle):
+    """AMG/twogrid.m: bigph = 0 (damped Jacobi, mis_set(A,1/4) + standard interpolation; consumes the random
+    stream) on a shifted grid Laplacian and bigph = 1 (the twogrid_bigph path) on a bigraph system, both
+    against the oracle: iteration counts, histories, solutions."""
+    import scipy.sparse as sp
+    g = 20
+    T = sp.diags([-np.ones(g - 1), 2 * np.ones(g), -np.ones(g - 1)], [-1, 0, 1])
+    A = (sp.kron(sp.identity(g), T) + sp.kron(T, sp.identity(g)) + 1e-3 * sp.identity(g * g)).tocsc()
+    b = np.random.RandomState(1).standard_normal(g * g)
+    o = {"retol": 1e-10, "bigph": 0, "maxit": 60, "smoth": 3, "isnsp": 1, "guess": None}
+    oracle.rng_reset(); gpu.rng_reset()
+    x_ref, it_ref, rel_ref, relk_ref, _ = oracle.twogrid(A, b, o)
+    x, it, rel, relk, _ = gpu.twogrid(A, b, o)
+    assert it == it_ref and np.allclose(relk, relk_ref, rtol=1e-5, atol=1e-13)
+    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+    rs = np.random.RandomState(3)
+    m, n = 90, 70
+    s = rs.random_sample(m * n) < 0.2
+    H0 = oracle.ASAt(s, np.ones(m), np.ones(n))
+    B = (0.1 * sp.identity(m + n) + H0).tocsc()
+    B = (sp.diags(B.diagonal()) - (B - sp.diags(B.diagonal()))).tocsc()
+    b2 = rs.standard_normal(m + n)
+    o2 = {"retol": 1e-10, "bigph": 1, "maxit": 40, "fnode": n, "smoth": 3, "isnsp": 0, "guess": None}
+    x_ref, it_ref, _, relk_ref, _ = oracle.twogrid(B, b2, o2)
+    x, it, _, relk, _ = gpu.twogrid(B, b2, o2)
+    assert it == it_ref and np.allclose(relk, relk_ref, rtol=1e-5, atol=1e-13)
+    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+    with pytest.raises(Exception):
+        gpu.twogrid(B, b2, {"retol": 1e-10, "bigph": 1, "maxit": 4, "smoth": 3, "isnsp": 0, "guess": None})   # fnode missing

@@ -277,3 +277,20 @@ def test_twogrid_bigph_and_hybrid_twogrid_solve_the_kkt_system():
     assert rel <= 1e-10 and len(relk) == it + 1 and np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
     x2, it2, rel2, _, _ = oracle.twogrid_bigph(A, b, {"retol": None, "maxit": 3, "fnode": n, "smoth": None, "isnsp": None, "guess": None})
     assert it2 == 3 and rel2 > 0                              # retol [] -> 0: runs to maxit
+
+
+def test_generic_twogrid_on_a_grid_laplacian():
+    """AMG/twogrid.m with bigph = 0 in the oracle: damped Jacobi + MIS coarsening on a (nearly singular,
+    hence isnsp = 1) shifted 2-D grid Laplacian converges; bigph = 1 without fnode is the reference's error."""
+    import scipy.sparse as sp
+    import oracle
+    from oracle.amg import AMGError
+    g = 14
+    T = sp.diags([-np.ones(g - 1), 2 * np.ones(g), -np.ones(g - 1)], [-1, 0, 1])
+    A = (sp.kron(sp.identity(g), T) + sp.kron(T, sp.identity(g)) + 1e-3 * sp.identity(g * g)).tocsc()
+    b = np.random.RandomState(1).standard_normal(g * g)
+    oracle.rng_reset()
+    x, it, rel, relk, rhok = oracle.twogrid(A, b, {"retol": 1e-10, "bigph": 0, "maxit": 60, "smoth": 3, "isnsp": 1, "guess": None})
+    assert rel <= 1e-10 and it < 60 and np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
+    with pytest.raises(AMGError):
+        oracle.twogrid(A, b, {"retol": 1e-10, "bigph": 1, "maxit": 5, "smoth": 3, "isnsp": 0, "guess": None})
