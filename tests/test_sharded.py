@@ -180,7 +180,7 @@ def _solve_worker(rank, world, port, g, outdir):
     dist.destroy_process_group()
 
 
-def _run_sharded_solve(rank, world, g, dist):
+def _run_sharded_solve(rank, world, g, dist, inner_solver=4):
     sd = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded_driver")
     sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
     P = _grid(g)
@@ -190,7 +190,7 @@ def _run_sharded_solve(rank, world, g, dist):
     c_loc = sharded.shard_plan_vector(t(P["c"]), m, n, r0, r1)
     ops = OracleOps(); ops.rng_reset()
     return sd.APD_SsN_Class1_sharded(c_loc, t(P["r"]), t(P["l"]), t(P["p"]), t(P["q"]), rank, world, ops=ops, dist=dist,
-                                     amg_options=AMG_OPTS, warm_maxit=30, max_outer=4)
+                                     amg_options=AMG_OPTS, warm_maxit=30, max_outer=4, inner_solver=inner_solver)
 
 
 def test_sharded_outer_loop_matches_oracle_driver_and_two_ranks():
@@ -231,6 +231,19 @@ def test_sharded_outer_loop_matches_oracle_driver_and_two_ranks():
     m = g * g
     full = np.concatenate([o["xk"].reshape(m, -1) for o in outs], axis=1)       # slabs are (n, m_loc) row-major
     assert np.allclose(full.reshape(-1), one["xk"].numpy(), rtol=1e-8, atol=1e-11)
+
+
+def test_sharded_outer_loop_with_the_two_grid_solver():
+    """inner_solver = 5 (Hybrid_twogrid) in the sharded outer loop: the inner systems are solved to the same
+    tolerance by a different multilevel method, so the outer iteration follows the inner_solver = 4 run."""
+    g = 5
+    a = _run_sharded_solve(0, 1, g, None, inner_solver=4)
+    b = _run_sharded_solve(0, 1, g, None, inner_solver=5)
+    assert a["stats"]["ssn_its"] == b["stats"]["ssn_its"]
+    assert np.allclose(a["fxk"], b["fxk"], rtol=1e-7, atol=1e-10)
+    assert np.allclose(a["lk"].numpy(), b["lk"].numpy(), rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        _run_sharded_solve(0, 1, g, None, inner_solver=3)
 
 
 def test_row_ranges_and_slab_layout():
