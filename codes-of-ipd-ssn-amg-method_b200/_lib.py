@@ -86,6 +86,8 @@ SIGNATURES = {
     "ssn_prox_trials": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp]),
     "ssn_prox_trials_lin": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _int, _int, _vp]),
     "ssn_warmup_class1": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, _int, _vp, _vp]),
+    "ssn_warm_stage": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, _dbl, _dbl, _dbl,
+                              _vp, _vp]),
     "ssn_apd_begin": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp]),
     "ssn_apd_end": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _vp, _vp, _vp, _pdbl, _pdbl]),
     "ssn_trial_vectors": (_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp]),

@@ -293,6 +293,31 @@ def warmup_class1(c, r, l, p, q, gama=np.inf, res=None, maxit=None):
     return _ret(xk, host), _ret(lk, host)
 
 
+def warm_stage(stage, xk, vk, wk, pik, lk2, dd, c, p, q, b, lk1, axk, y, ak, bk, gk, gama=np.inf):
+    """One fused stage of a warm-start iteration (Class1/warmup_class1.m:63-67 / :70-75) on CUDA tensors that
+    are updated IN PLACE (``xk vk wk pik lk2 dd``: contiguous float64 CUDA tensors of ``m*n`` entries).
+    Stage 0 returns ``Ax(dd)``; stage 1 returns ``(Ax(vk1), Ax(xk1))`` -- column sums over the rows held here,
+    then those rows' sums.  For callers that own the loop (the row-sharded driver)."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    for t in (xk, vk, wk, pik, lk2, dd):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == m * n):
+            raise ValueError("warm_stage updates contiguous float64 CUDA tensors of m*n entries in place")
+    cd, bd = _dev(c, count=m * n), _dev(b, count=m + n)
+    gvec, gs = _gama_args(gama, m, n)
+    out1 = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    if stage == 0:
+        l1, ax = _dev(lk1, count=m + n), _dev(axk, count=m + n)
+        ctx.call("ssn_warm_stage", 0, _ptr(xk), _ptr(vk), _ptr(wk), _ptr(pik), _ptr(lk2), _ptr(dd), _ptr(cd), _ptr(pd), _ptr(qd), _ptr(bd),
+                 _ptr(l1), _ptr(ax), None, m, n, _ptr(gvec), gs, float(ak), float(bk), float(gk), _ptr(out1), None)
+        return out1
+    yd = _dev(y, count=m + n)
+    out2 = torch.empty(n + m, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_warm_stage", 1, _ptr(xk), _ptr(vk), _ptr(wk), _ptr(pik), _ptr(lk2), _ptr(dd), _ptr(cd), _ptr(pd), _ptr(qd), _ptr(bd),
+             None, None, _ptr(yd), m, n, _ptr(gvec), gs, float(ak), float(bk), float(gk), _ptr(out1), _ptr(out2))
+    return out1, out2
+
+
 def apd_begin(c, xk, vk, p, q, ak, bk):
     """``wk = -c + bk*(xk+ak*vk)/ak^2`` and ``Ax(xk)`` in one pass (Class1/APD_SsN_Class1.m:125-126)."""
     torch = _torch(); ctx = context()

@@ -237,6 +237,11 @@ int ssn_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const dou
                       const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out) {
     return guarded(c, [&] { plan_warmup_class1(c, cost, b, p, q, m, n, gama, gama_s, maxit, xk_out, lk_out); sync(c); });
 }
+int ssn_warm_stage(ssn_ctx* c, int stage, double* xk, double* vk, double* wk, double* pik, double* lk2, double* dd, const double* cost,
+                   const double* p, const double* q, const double* b, const double* lk1, const double* axk, const double* y, int64_t m,
+                   int64_t n, const double* gama, double gama_s, double ak, double bk, double gk, double* out1, double* out2) {
+    return guarded(c, [&] { plan_warm_stage(c, stage, xk, vk, wk, pik, lk2, dd, cost, p, q, b, lk1, axk, y, m, n, gama, gama_s, ak, bk, gk, out1, out2); sync(c); });
+}
 int ssn_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q, int64_t m,
                   int64_t n, double ak, double bk, double* wk_out, double* axk_out) {
     return guarded(c, [&] { plan_apd_begin(c, cost, xk, vk, p, q, m, n, ak, bk, wk_out, axk_out); sync(c); });

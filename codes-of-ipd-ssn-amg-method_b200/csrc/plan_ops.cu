@@ -1455,6 +1455,52 @@ void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const d
     }
 }
 
+// ONE fused stage of an A-ADMM warm-start iteration (the kernels of plan_warmup_class1) for callers that own
+// the loop: the row-sharded driver runs it on its slab and exchanges the column sums between the stages.
+// Dual vectors in the slab's own form [column part (n) ; row part of the slab's rows (m)].
+//   stage 0 (warmup_class1.m:63-67): reads xk vk wk pik lk2 c, lk1, axk = Ax(xk), b; writes dd; out1 = Ax(dd)
+//   stage 1 (:70-75): reads dd xk wk pik lk2, y = invAAt(Ax(dd)); rewrites xk vk wk pik lk2 in place;
+//                     out1 = Ax(vk1), out2 = Ax(xk1)
+// out1 / out2: column sums over the slab's rows (partial when the plan is sharded), then the rows' own sums.
+void plan_warm_stage(ssn_ctx* c, int stage, double* xk, double* vk, double* wk, double* pik, double* lk2, double* dd,
+                     const double* cost, const double* p, const double* q, const double* b, const double* lk1, const double* axk,
+                     const double* y, int64_t m, int64_t n, const double* gama, double gama_s, double ak, double bk, double gk,
+                     double* out1, double* out2) {
+    SSN_REQUIRE(xk && vk && wk && pik && lk2 && dd && cost && p && q && b && out1 && m > 0 && n > 0, SSN_E_INVALID, "warm_stage: bad arguments");
+    SSN_REQUIRE(stage == 0 ? (lk1 && axk) : (stage == 1 && y && out2), SSN_E_INVALID, "warm_stage: stage 0 needs lk1, axk; stage 1 needs y, out2");
+    const int64_t N = m + n;
+    const Tiling t = plan_tiling(c, m, n);
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), rowpart2, colpart2;
+    if (stage == 1) { rowpart2.alloc(c, (size_t)t.chunks * m); colpart2.alloc(c, (size_t)t.groups * n); }
+    const double muf = 0.0;                                                 // warmup_class1.m:27
+    const double bk1 = bk / (1 + ak);
+    WarmArgs a{};
+    a.xk = xk; a.vk = vk; a.wk = wk; a.pik = pik; a.lk2 = lk2; a.dd = dd; a.c = cost; a.p = p; a.q = q; a.b = b;
+    a.lk1 = lk1; a.axk = axk; a.y = y; a.gama = gama; a.gama_s = gama_s; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart; a.colpart = colpart; a.rowpart2 = rowpart2; a.colpart2 = colpart2;
+    a.ak = ak; a.bk = bk; a.gk = gk; a.muf = muf; a.etafk = (1 + ak) * gk + muf * ak; a.sgk = 1 / bk1; a.etagk = (1 + ak) * bk;
+    a.tt = a.sgk * ak * ak;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)2 * kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(xk, m) && vec_ok(cost, m) && (!gama || vec_ok(gama, m)) && vec_ok(vk, m) && vec_ok(dd, m) &&
+                     vec_ok(wk, m) && vec_ok(pik, m) && vec_ok(lk2, m);
+    const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+    if (stage == 0) {
+        if (vec) SSN_LAUNCH(c, (warm_kernel<0, true, G_INF>), grid, kThreads, smem / 2, a);
+        else     SSN_LAUNCH(c, (warm_kernel<0, false, G_INF>), grid, kThreads, smem / 2, a);
+        SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, nullptr, nullptr, t.chunks, t.groups, m, n, out1, nullptr);
+        return;
+    }
+#define SSN_WARM_B(V, G) do { \
+        SSN_CUDA(cudaFuncSetAttribute((warm_kernel<1, V, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SSN_LAUNCH(c, (warm_kernel<1, V, G>), grid, kThreads, smem, a); } while (0)
+    if (vec) { if (gm == G_INF) SSN_WARM_B(true, G_INF); else if (gm == G_SCALAR) SSN_WARM_B(true, G_SCALAR); else SSN_WARM_B(true, G_VECTOR); }
+    else     { if (gm == G_INF) SSN_WARM_B(false, G_INF); else if (gm == G_SCALAR) SSN_WARM_B(false, G_SCALAR); else SSN_WARM_B(false, G_VECTOR); }
+#undef SSN_WARM_B
+    SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, rowpart2.p, colpart2.p, t.chunks, t.groups, m, n, out1, out2);
+}
+
 // wk = -c + bk*(xk+ak*vk)/ak^2 and axk = Ax(xk)      (Class1/APD_SsN_Class1.m:125-126)
 void plan_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q,
                     int64_t m, int64_t n, double ak, double bk, double* wk_out, double* axk_out) {

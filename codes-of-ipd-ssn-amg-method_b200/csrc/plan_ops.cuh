@@ -22,6 +22,10 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
                      double* lam_new, int* ll_out, double* n2_out, double* cF_out, int* passes_out);
 void plan_warmup_class1(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m,
                         int64_t n, const double* gama, double gama_s, int maxit, double* xk_out, double* lk_out);
+void plan_warm_stage(ssn_ctx* c, int stage, double* xk, double* vk, double* wk, double* pik, double* lk2, double* dd,
+                     const double* cost, const double* p, const double* q, const double* b, const double* lk1, const double* axk,
+                     const double* y, int64_t m, int64_t n, const double* gama, double gama_s, double ak, double bk, double gk,
+                     double* out1, double* out2);
 void plan_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const double* vk, const double* p, const double* q,
                     int64_t m, int64_t n, double ak, double bk, double* wk_out, double* axk_out);
 void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double* xk, const double* lam, const double* p,

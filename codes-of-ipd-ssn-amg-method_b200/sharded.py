@@ -77,6 +77,9 @@ class _CudaOps:
     def rand(self, count):
         return self.api.rand(count)
 
+    def warm_stage(self, stage, xk, vk, wk, pik, lk2, dd, c, p, q, b, lk1, axk, y, ak, bk, gk, gama):
+        return self.api.warm_stage(stage, xk, vk, wk, pik, lk2, dd, c, p, q, b, lk1, axk, y, ak, bk, gk, gama)
+
 
 class ShardedStep:
     """One semismooth-Newton step (Class1/APD_SsN_Class1.m:137-212) on a row-sharded plan."""

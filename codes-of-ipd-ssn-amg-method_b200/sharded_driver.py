@@ -10,9 +10,10 @@ small ``all_reduce`` calls; the semismooth-Newton step is ``sharded.ShardedStep`
 The operators come from ``ops`` (the CUDA operators by default; the CPU tests pass an adapter over
 the oracle and run two gloo ranks).
 
-The A-ADMM warm start is the operator-by-operator form of ``driver.warmup_class1_unfused`` (one
-line per reference line) with the sharded ``Ax``; the fused warm-up kernels of the single-GPU
-driver run a whole iteration without leaving the device and have no exchange point yet.
+The A-ADMM warm start runs the fused stage kernels of the single-GPU warm start on the slab
+(``ssn_warm_stage``: 17 plan-sized reads / writes per iteration instead of ~45) with the column sums
+exchanged between the two stages; the operator-by-operator form of ``driver.warmup_class1_unfused``
+(one line per reference line, sharded ``Ax``) is kept as the cross-check (``fused_warmup=False``).
 """
 import math
 import time
@@ -80,8 +81,38 @@ class SlabAlgebra:
         return [float(v) for v in t]
 
 
+def warmup_class1_sharded_fused(A, c, b, gama, maxit):
+    """Class1/warmup_class1.m:43-95 on row slabs with the fused stage kernels (``ops.warm_stage``): two
+    plan-wide kernels per iteration on the slab, the column sums of ``Ax(dd)`` and of ``Ax(vk1), Ax(xk1)``
+    exchanged in between (2 all_reduce + 2 all_gather calls per iteration), ``invAAt`` and the update of
+    the dual block replicated on the (n+m)-vectors."""
+    torch = A.torch
+    ops, p, q = A.ops, A.p, A.q
+    xk = torch.zeros_like(c); vk = torch.zeros_like(c); wk = torch.zeros_like(c); pik = torch.zeros_like(c)
+    lk2 = torch.zeros_like(c); dd = torch.empty_like(c)
+    lk1 = torch.zeros_like(b); axk = torch.zeros_like(b)
+    b_loc = A.lam_loc(b)
+    muf = 0.0; gk = 1.0; bk = 1.0                                       # :27
+    for _ in range(int(maxit)):
+        ak = bk; bk1 = bk / (1 + ak)                                    # :59
+        gk1 = (gk + muf * ak) / (1 + ak)
+        etafk = (1 + ak) * gk + muf * ak
+        sgk = 1 / bk1
+        tt = sgk * ak ** 2; sg = 1 + etafk / tt                         # :69
+        ax_loc = ops.warm_stage(0, xk, vk, wk, pik, lk2, dd, c, A.p_loc, q, b_loc, A.lam_loc(lk1), A.lam_loc(axk), None,
+                                ak, bk, gk, gama)                       # :63-67, Ax(dd)
+        y = ops.invAAt(A.finish_ax(ax_loc), p, q, sg)                   # :70
+        av_loc, axk_loc = ops.warm_stage(1, xk, vk, wk, pik, lk2, dd, c, A.p_loc, q, b_loc, None, None, A.lam_loc(y),
+                                         ak, bk, gk, gama)              # :70-75, Ax(vk1), Ax(xk1)
+        av = A.finish_ax(av_loc); axk = A.finish_ax(axk_loc)
+        lk1 = lk1 + (ak / bk) * (av - b)                                # :75
+        gk = gk1; bk = bk1                                              # :77
+    return xk, lk1
+
+
 def warmup_class1_sharded(A, c, b, gama, maxit):
-    """Class1/warmup_class1.m:43-95 on row slabs (``A``: SlabAlgebra, ``c``: cost slab, ``b = [r ; l]``)."""
+    """Class1/warmup_class1.m:43-95 on row slabs (``A``: SlabAlgebra, ``c``: cost slab, ``b = [r ; l]``),
+    operator by operator."""
     torch = A.torch
     p, q = A.p, A.q
     inf_gama = np.isscalar(gama) and math.isinf(gama)
@@ -119,7 +150,8 @@ def warmup_class1_sharded(A, c, b, gama, maxit):
 
 
 def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
-                           ops=None, dist=None, amg_options=None, max_outer=None, max_seconds=None, verbose=False, inner_solver=4):
+                           ops=None, dist=None, amg_options=None, max_outer=None, max_seconds=None, verbose=False, inner_solver=4,
+                           fused_warmup=True):
     """APD outer loop + SsN inner loop of Class1/APD_SsN_Class1.m:32-275 on a row-sharded plan.
     ``c_loc``: this rank's slab of the cost (column-major ``m_loc x n``); ``r, l, p, q``: full vectors,
     replicated; ``inner_solver``: 4 = Hybrid_AMG (the reference's default), 5 = Hybrid_twogrid
@@ -139,7 +171,8 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
     SsN_IT = 50; SsN_Tol1 = 1e-11                                       # :36
     sync = (lambda: torch.cuda.synchronize()) if torch.cuda.is_available() else (lambda: None)
     t_start = time.time()
-    xk, lk = warmup_class1_sharded(A, c_loc, b, gama, warm_maxit)        # :59
+    warm = warmup_class1_sharded_fused if (fused_warmup and hasattr(ops, "warm_stage")) else warmup_class1_sharded
+    xk, lk = warm(A, c_loc, b, gama, warm_maxit)                         # :59
     sync(); t_warm = time.time() - t_start
     vk = xk.clone()
 

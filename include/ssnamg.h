@@ -235,6 +235,20 @@ SSN_API int ssn_warmup_class1(ssn_ctx *ctx, const double *c_dev, const double *b
                       const double *q_dev, int64_t m, int64_t n, const double *gama_dev, double gama_scalar,
                       int maxit, double *xk_out_dev, double *lk_out_dev);
 
+/* One fused stage of a warm-start iteration, for callers that own the loop (the row-sharded driver runs it on
+ * its row slab and exchanges the column sums between the stages; single-GPU callers use ssn_warmup_class1).
+ * Plan-sized arrays are updated in place; dual vectors are in the slab's own form [column part (n) ; row part
+ * of the slab's m rows].  Scalars ak, bk, gk of the iteration (Class1/warmup_class1.m:59-62).
+ *   stage 0 (:63-67)  reads xk vk wk pik lk2 c, lk1, axk = Ax(xk), b; writes dd; out1 = Ax(dd)
+ *   stage 1 (:70-75)  reads dd xk wk pik lk2, y = invAAt(Ax(dd)); rewrites xk vk wk pik lk2;
+ *                     out1 = Ax(vk1), out2 = Ax(xk1)
+ * out1 / out2 (n+m): column sums over the slab's rows (partial when sharded), then the rows' own sums. */
+SSN_API int ssn_warm_stage(ssn_ctx *ctx, int stage, double *xk_dev, double *vk_dev, double *wk_dev, double *pik_dev,
+                   double *lk2_dev, double *dd_dev, const double *c_dev, const double *p_dev, const double *q_dev,
+                   const double *b_dev, const double *lk1_dev, const double *axk_dev, const double *y_dev,
+                   int64_t m, int64_t n, const double *gama_dev, double gama_scalar, double ak, double bk,
+                   double gk, double *out1_dev, double *out2_dev);
+
 /* The plan-wide lines of the APD outer iteration around the SsN solve, fused:
  *   ssn_apd_begin  wk = -c + bk*(xk+ak*vk)/ak^2 and axk = Ax(xk)            Class1/APD_SsN_Class1.m:125-126
  *   ssn_apd_end    xk1 = prox((wk-Aty(lam))/tk), vk1 = xk1+(xk1-xk)/ak, axk1 = Ax(xk1),

@@ -123,3 +123,23 @@ def test_sharded_outer_loop_on_one_gpu_matches_device_driver(gpu):
     assert np.allclose(out["KKT_lk"], ref["KKT_lk"], rtol=1e-6, atol=1e-11)
     assert np.allclose(out["KKT_xk"], ref["KKT_xk"], rtol=1e-6, atol=1e-11)
     assert np.allclose(out["lk"].cpu().numpy(), ref["lk"].cpu().numpy(), rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("m,n,gama", [(100, 100, np.inf), (77, 53, np.inf), (64, 48, 0.02)])
+def test_staged_warm_start_equals_the_fused_warm_start(gpu, m, n, gama):
+    """ssn_warm_stage (one fused stage per call, the loop and the (n+m)-sized updates on the host side, as the
+    row-sharded driver runs it) against ssn_warmup_class1 (the whole loop in the library): same kernels, same
+    scalars => the same iterates up to the rounding of invAAt / the dual update, which the two paths evaluate
+    with different small kernels."""
+    import importlib
+    import torch
+    sd = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded_driver")
+    sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
+    P = gpu.problems.random_problem(m, n, seed=5)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    c, r, l, p, q = (dev(P[k]) for k in ("c", "r", "l", "p", "q"))
+    x_ref, lk_ref = gpu.warmup_class1(c, r, l, p, q, gama, 0.0, 25)
+    A = sd.SlabAlgebra(0, 1, p, q, sharded._CudaOps(), None, torch)
+    x, lk = sd.warmup_class1_sharded_fused(A, c, torch.cat([r, l]), gama, 25)
+    assert torch.allclose(x, x_ref, rtol=1e-10, atol=1e-13)
+    assert torch.allclose(lk, lk_ref, rtol=1e-10, atol=1e-13)

@@ -114,6 +114,34 @@ class OracleOps:
     def rand(self, count):
         return torch.from_numpy(np.asarray(self.o.rand(count), dtype=np.float64).reshape(-1))
 
+    def warm_stage(self, stage, xk, vk, wk, pik, lk2, dd, c, p, q, b, lk1, axk, y, ak, bk, gk, gama):
+        """The two fused stages of a warm-start iteration restated line by line (Class1/warmup_class1.m:59-75),
+        updating the torch tensors in place like the CUDA kernels."""
+        X, V, W, PI, L2, C_ = (self._np(t) for t in (xk, vk, wk, pik, lk2, c))
+        pn, qn, bn = self._np(p), self._np(q), self._np(b)
+        muf = 0.0
+        bk1 = bk / (1 + ak); etafk = (1 + ak) * gk + muf * ak; sgk = 1 / bk1; etagk = (1 + ak) * bk
+        if stage == 0:
+            wxk = (ak * gk * V + (gk + muf * ak) * X) / etafk                       # :62
+            h1 = self._np(lk1) - (self._np(axk) - bn) / bk                          # :65
+            h2 = L2 - (X - W) / bk - (ak / bk) * (PI - W)
+            cAw = -self.o.Aty(bn, pn, qn) - W; cAlk = self.o.Aty(h1, pn, qn) + h2   # :66
+            d = etafk * wxk - ak ** 2 * (C_ + cAlk + sgk * cAw)                     # :67
+            dd.copy_(torch.from_numpy(d))
+            return torch.from_numpy(self.o.Ax(d, pn, qn))
+        tt = sgk * ak ** 2
+        prox = lambda v: np.minimum(np.maximum(0.0, v), gama)
+        x1 = (self._np(dd) - self.o.Aty(self._np(y), pn, qn)) / (etafk + tt)        # :70
+        v1 = x1 + (x1 - X) / ak
+        wwk = (ak * PI + W) / (1 + ak)                                               # :61
+        blk2 = L2 + (ak / bk) * (v1 - PI)                                            # :72
+        w1 = prox(wwk - (ak ** 2 / etagk) * (-blk2))                                 # :73
+        pi1 = w1 + (w1 - W) / ak
+        l2 = L2 + (ak / bk) * (v1 - pi1)                                             # :75
+        for t, a in ((xk, x1), (vk, v1), (wk, w1), (pik, pi1), (lk2, l2)):
+            t.copy_(torch.from_numpy(a))
+        return torch.from_numpy(self.o.Ax(v1, pn, qn)), torch.from_numpy(self.o.Ax(x1, pn, qn))
+
 
 def make_state(m, n, seed):
     rs = np.random.RandomState(seed)
@@ -180,7 +208,7 @@ def _solve_worker(rank, world, port, g, outdir):
     dist.destroy_process_group()
 
 
-def _run_sharded_solve(rank, world, g, dist, inner_solver=4):
+def _run_sharded_solve(rank, world, g, dist, inner_solver=4, fused_warmup=True):
     sd = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded_driver")
     sharded = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.sharded")
     P = _grid(g)
@@ -190,7 +218,7 @@ def _run_sharded_solve(rank, world, g, dist, inner_solver=4):
     c_loc = sharded.shard_plan_vector(t(P["c"]), m, n, r0, r1)
     ops = OracleOps(); ops.rng_reset()
     return sd.APD_SsN_Class1_sharded(c_loc, t(P["r"]), t(P["l"]), t(P["p"]), t(P["q"]), rank, world, ops=ops, dist=dist,
-                                     amg_options=AMG_OPTS, warm_maxit=30, max_outer=4, inner_solver=inner_solver)
+                                     amg_options=AMG_OPTS, warm_maxit=30, max_outer=4, inner_solver=inner_solver, fused_warmup=fused_warmup)
 
 
 def test_sharded_outer_loop_matches_oracle_driver_and_two_ranks():
@@ -231,6 +259,17 @@ def test_sharded_outer_loop_matches_oracle_driver_and_two_ranks():
     m = g * g
     full = np.concatenate([o["xk"].reshape(m, -1) for o in outs], axis=1)       # slabs are (n, m_loc) row-major
     assert np.allclose(full.reshape(-1), one["xk"].numpy(), rtol=1e-8, atol=1e-11)
+
+
+def test_fused_and_operator_by_operator_sharded_warm_start_agree():
+    """The staged warm start (two fused stages per iteration with the column sums exchanged in between)
+    against the operator-by-operator warm start of the same driver."""
+    g = 5
+    a = _run_sharded_solve(0, 1, g, None, fused_warmup=True)
+    b = _run_sharded_solve(0, 1, g, None, fused_warmup=False)
+    assert a["stats"]["ssn_its"] == b["stats"]["ssn_its"]
+    assert np.allclose(a["fxk"], b["fxk"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(a["lk"].numpy(), b["lk"].numpy(), rtol=1e-8, atol=1e-11)
 
 
 def test_sharded_outer_loop_with_the_two_grid_solver():
