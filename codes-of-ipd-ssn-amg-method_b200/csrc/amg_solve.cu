@@ -965,6 +965,12 @@ struct PcgArgs {
     double* part;            // [3][gridDim]
     double* resk;            // maxit
     int* it_out; double* scal_out;   // scal_out[0] = delta_new, [1] = delta_0
+    // precd 3 / 4: w = Uf \ (mid .* (Lf \ r)) with level-scheduled sparse triangular solves
+    const int* lp; const int* li; const double* lv;     // Lf, CSR, columns ascending, diagonal LAST in its row
+    const int* up; const int* ui; const double* uv;     // Uf, CSR, columns ascending, diagonal FIRST in its row
+    const double* mid;                                  // optional diagonal scaling between the solves
+    const int* lrows; const int* llev; int nlev_l;      // rows of Lf grouped by dependency level, level pointers
+    const int* urows; const int* ulev; int nlev_u;
 };
 
 __device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, double* part, double* red) {
@@ -984,6 +990,33 @@ __device__ double pcg_precond(cg::grid_group& grid, const PcgArgs& a, int gtid, 
         for (int i = gtid; i < a.n; i += gsize) { const double ri = a.r[i]; a.w[i] = ri; dn = fma(ri, ri, dn); }
     } else if (a.precd == 2) {
         for (int i = gtid; i < a.n; i += gsize) { const double ri = a.r[i]; const double wi = ri / a.diag[i]; a.w[i] = wi; dn = fma(ri, wi, dn); }
+    } else if (a.precd == 3 || a.precd == 4) {
+        // SSOR (PCG.m:96-99) / incomplete Cholesky (:100-101): forward solve into a.a, backward solve into a.w.
+        // Rows of one dependency level are independent: a warp per row, a grid barrier per level.
+        const int lane = threadIdx.x & 31, gwarp = gtid >> 5, nwarps = gsize >> 5;
+        for (int lev = 0; lev < a.nlev_l; ++lev) {
+            for (int t = a.llev[lev] + gwarp; t < a.llev[lev + 1]; t += nwarps) {
+                const int row = a.lrows[t];
+                const int e0 = a.lp[row], e1 = a.lp[row + 1] - 1;           // e1: the diagonal entry
+                double s = 0.0;
+                for (int e = e0 + lane; e < e1; e += 32) s = fma(a.lv[e], a.a[a.li[e]], s);
+                s = warp_sum(s);
+                if (lane == 0) a.a[row] = (a.r[row] - s) / a.lv[e1];
+            }
+            grid.sync();
+        }
+        for (int lev = 0; lev < a.nlev_u; ++lev) {
+            for (int t = a.ulev[lev] + gwarp; t < a.ulev[lev + 1]; t += nwarps) {
+                const int row = a.urows[t];
+                const int e0 = a.up[row], e1 = a.up[row + 1];               // e0: the diagonal entry
+                double s = 0.0;
+                for (int e = e0 + 1 + lane; e < e1; e += 32) s = fma(a.uv[e], a.w[a.ui[e]], s);
+                s = warp_sum(s);
+                if (lane == 0) { const double rhs = a.mid ? a.mid[row] * a.a[row] : a.a[row]; a.w[row] = (rhs - s) / a.uv[e0]; }
+            }
+            grid.sync();
+        }
+        for (int i = gtid; i < a.n; i += gsize) dn = fma(a.r[i], a.w[i], dn);
     } else {
         // bi-SSOR, w = 1.5:  P r = w(2-w) [ aa - w invV U b ; b ],  aa = invV r_c,  b = invT (r_r - w U' aa)
         const double om = 1.5, sc = om * (2.0 - om);
@@ -1043,7 +1076,7 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs a) {
         qp = grid_sum(grid, qp, part1, red);
         const double alpha = delta_old / qp;
         for (int i = gtid; i < a.n; i += gsize) { a.d[i] += alpha * a.p[i]; a.r[i] -= alpha * a.q[i]; }
-        if (a.precd == 5) grid.sync();
+        if (a.precd >= 3) grid.sync();
         dn = pcg_precond(grid, a, gtid, gsize);
         delta_new = grid_sum(grid, dn, (it & 1) ? part0 : part2, red);
         const double beta = delta_new / delta_old;
@@ -1891,8 +1924,7 @@ void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_opti
         if (opts->precd > 0) precd = opts->precd;
         nf = opts->nf; guess = opts->guess_dev;
     }
-    SSN_REQUIRE(precd == 1 || precd == 2 || precd == 5, SSN_E_UNSUPPORTED,
-                "PCG: precd 3 (SSOR) and 4 (ichol) are not supported (SURVEY.md 8f)");
+    SSN_REQUIRE(precd >= 1 && precd <= 5, SSN_E_UNSUPPORTED, "PCG: precd must be 1..5");
     if (precd == 5) SSN_REQUIRE(nf > 0 && nf < n, SSN_E_PCG_NF, "SSOR for bigraph requires pcg_options.nf!!!");
     Buf<double> r(c, n), p(c, n), q(c, n), w(c, n), aux(c, n), diag(c, n), resk(c, maxit > 0 ? maxit : 1), scal(c, 2);
     Buf<int> itd(c, 1);
@@ -1903,6 +1935,86 @@ void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_opti
     a.d = d; a.r = r; a.p = p; a.q = q; a.w = w; a.a = aux; a.diag = diag;
     a.precd = precd; a.nf = nf; a.maxit = maxit; a.tol2 = retol * retol;
     a.resk = resk; a.it_out = itd; a.scal_out = scal;
+    // precd 3 (SSOR, PCG.m:39-44,96-99) and 4 (ichol, :45-51,100-101): the triangular factors and their
+    // dependency levels are built once per call on the host (one pass over the pattern; the incomplete
+    // factorisation is inherently sequential), the solves of every iteration run in the kernel.
+    Buf<int> lp_d, li_d, up_d, ui_d, lrows_d, llev_d, urows_d, ulev_d;
+    Buf<double> lv_d, uv_d, mid_d;
+    if (precd == 3 || precd == 4) {
+        const int64_t nnz = H.nnz;
+        std::vector<int> hp((size_t)n + 1), hi((size_t)nnz); std::vector<double> hv((size_t)nnz);
+        SSN_CUDA(cudaMemcpyAsync(hp.data(), H.ptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(hi.data(), H.idx, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(hv.data(), H.val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int> lp(1, 0), li, up(1, 0), ui; std::vector<double> lv, uv, mid;
+        if (precd == 3) {
+            const double om = 1.5, sc = om * (2.0 - om);
+            mid.resize(n);
+            for (int i = 0; i < n; ++i) {
+                double dii = 0.0;
+                for (int e = hp[i]; e < hp[i + 1]; ++e) if (hi[e] == i) dii = hv[e];
+                mid[i] = dii;                                                   // p2 = D*p1            :97
+                for (int e = hp[i]; e < hp[i + 1]; ++e) if (hi[e] < i) { li.push_back(hi[e]); lv.push_back(om * hv[e]); }
+                li.push_back(i); lv.push_back(dii);                             // D + w*L              :96
+                ui.push_back(i); uv.push_back(sc * dii);                        // (w*(2-w))*(D + w*U)  :99 (as MATLAB parses it)
+                for (int e = hp[i]; e < hp[i + 1]; ++e) if (hi[e] > i) { ui.push_back(hi[e]); uv.push_back(sc * (om * hv[e])); }
+                lp.push_back((int)li.size()); up.push_back((int)ui.size());
+            }
+        } else {
+            // IC(0): L has the pattern of tril(H); row i: L_ij = (a_ij - sum_{t<j} L_it L_jt)/L_jj, L_ii = sqrt(a_ii - sum L_it^2)
+            for (int i = 0; i < n; ++i) {
+                const int r0 = (int)li.size();
+                bool has_diag = false;
+                for (int e = hp[i]; e < hp[i + 1]; ++e) {
+                    const int j = hi[e];
+                    if (j > i) continue;
+                    double sacc = hv[e];
+                    int a0 = r0, a1 = (int)li.size();                           // row i so far (columns < j)
+                    int b0 = (j < i) ? lp[j] : r0, b1 = (j < i) ? lp[j + 1] - 1 : a1;   // row j without its diagonal
+                    while (a0 < a1 && b0 < b1) {
+                        if (li[a0] == li[b0]) { sacc -= lv[a0] * lv[b0]; ++a0; ++b0; }
+                        else if (li[a0] < li[b0]) ++a0; else ++b0;
+                    }
+                    if (j < i) { li.push_back(j); lv.push_back(sacc / lv[lp[j + 1] - 1]); }
+                    else { SSN_REQUIRE(sacc > 0.0, SSN_E_NOT_SPD, "ichol: encountered nonpositive pivot"); li.push_back(i); lv.push_back(std::sqrt(sacc)); has_diag = true; }
+                }
+                SSN_REQUIRE(has_diag, SSN_E_NOT_SPD, "ichol: zero on the diagonal");
+                lp.push_back((int)li.size());
+            }
+            // Uf = L'
+            std::vector<int> cnt((size_t)n + 1, 0);
+            for (int v : li) ++cnt[(size_t)v + 1];
+            for (int i = 0; i < n; ++i) cnt[(size_t)i + 1] += cnt[i];
+            up.assign(cnt.begin(), cnt.end());
+            ui.resize(li.size()); uv.resize(li.size());
+            std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+            for (int i = 0; i < n; ++i) for (int e = lp[i]; e < lp[i + 1]; ++e) { const int j = li[e]; ui[pos[j]] = i; uv[pos[j]] = lv[e]; ++pos[j]; }
+        }
+        // dependency levels: forward (columns < row), backward (columns > row)
+        std::vector<int> levl(n, 0), levu(n, 0);
+        int nl = 0, nu = 0;
+        for (int i = 0; i < n; ++i) { int l = 0; for (int e = lp[i]; e < lp[i + 1] - 1; ++e) l = std::max(l, levl[li[e]] + 1); levl[i] = l; nl = std::max(nl, l + 1); }
+        for (int i = n - 1; i >= 0; --i) { int l = 0; for (int e = up[i] + 1; e < up[i + 1]; ++e) l = std::max(l, levu[ui[e]] + 1); levu[i] = l; nu = std::max(nu, l + 1); }
+        auto bucket = [&](const std::vector<int>& lev, int nlev, std::vector<int>& rows, std::vector<int>& ptr) {
+            ptr.assign((size_t)nlev + 1, 0);
+            for (int i = 0; i < n; ++i) ++ptr[(size_t)lev[i] + 1];
+            for (int l = 0; l < nlev; ++l) ptr[(size_t)l + 1] += ptr[l];
+            rows.resize(n);
+            std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+            for (int i = 0; i < n; ++i) rows[pos[lev[i]]++] = i;
+        };
+        std::vector<int> lrows, llev, urows, ulev;
+        bucket(levl, nl, lrows, llev); bucket(levu, nu, urows, ulev);
+        auto up_i = [&](Buf<int>& d, const std::vector<int>& h) { d.alloc(c, std::max<size_t>(h.size(), 1)); if (!h.empty()) SSN_CUDA(cudaMemcpyAsync(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, c->stream)); };
+        auto up_d2 = [&](Buf<double>& d, const std::vector<double>& h) { d.alloc(c, std::max<size_t>(h.size(), 1)); if (!h.empty()) SSN_CUDA(cudaMemcpyAsync(d.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, c->stream)); };
+        up_i(lp_d, lp); up_i(li_d, li); up_d2(lv_d, lv); up_i(up_d, up); up_i(ui_d, ui); up_d2(uv_d, uv);
+        up_i(lrows_d, lrows); up_i(llev_d, llev); up_i(urows_d, urows); up_i(ulev_d, ulev);
+        if (!mid.empty()) up_d2(mid_d, mid);
+        SSN_CUDA(cudaStreamSynchronize(c->stream));          // the host vectors go out of scope
+        a.lp = lp_d; a.li = li_d; a.lv = lv_d; a.up = up_d; a.ui = ui_d; a.uv = uv_d; a.mid = mid.empty() ? nullptr : mid_d.p;
+        a.lrows = lrows_d; a.llev = llev_d; a.nlev_l = nl; a.urows = urows_d; a.ulev = ulev_d; a.nlev_u = nu;
+    }
     int per_sm = 0;
     SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;

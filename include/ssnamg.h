@@ -91,7 +91,7 @@ typedef struct ssn_amg_options {
 typedef struct ssn_pcg_options {
     double  retol;     /* default 1e-11 */
     int32_t maxit;     /* default 10000 */
-    int32_t precd;     /* 1 none, 2 Jacobi (default), 5 bi-SSOR (needs nf); 3,4 unsupported */
+    int32_t precd;     /* 1 none, 2 Jacobi (default), 3 SSOR, 4 ichol (IC(0)), 5 bi-SSOR (needs nf) */
     int32_t nf;        /* <= 0: absent */
     const double *guess_dev;  /* NULL -> zeros */
 } ssn_pcg_options;
@@ -355,7 +355,9 @@ SSN_API int ssn_twogrid(ssn_ctx *ctx, const ssn_csr *A, const double *b_dev, con
 /* ------------------------------------------------------------------ L2: Krylov */
 
 /* [d,it,res,resk] = PCG(H,e,pcg_options) -- PCG.m:18-105.  resk_host: caller buffer of
- * maxit doubles (optional). */
+ * maxit doubles (optional).  precd 3 (SSOR) and 4 (ichol, MATLAB's default IC(0); a nonpositive pivot is
+ * SSN_E_NOT_SPD) apply their two sparse triangular solves level by level inside the persistent kernel;
+ * the factors and their dependency levels are built once per call on the host. */
 SSN_API int ssn_pcg(ssn_ctx *ctx, const ssn_csr *H, const double *e_dev, const ssn_pcg_options *opts,
             double *d_dev, int *it_out, double *res_out, double *resk_host);
 

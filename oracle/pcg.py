@@ -12,6 +12,42 @@ def _is_empty(v):
     return v is None or (hasattr(v, "__len__") and len(v) == 0)
 
 
+def ichol0(H):
+    """``ichol(H)`` with MATLAB's default options (type 'nofill', no diagonal compensation): the lower-triangular
+    IC(0) factor ``L`` with the pattern of ``tril(H)``, ``L_ij = (h_ij - sum_{t<j} L_it L_jt) / L_jj``,
+    ``L_ii = sqrt(h_ii - sum_t L_it^2)``, rows in order.  MATLAB's ``ichol`` is a built-in (its summation order
+    is not documented); a nonpositive pivot is its error 'Encountered nonpositive pivot'."""
+    A = sp.csr_matrix(sp.tril(H)); A.sort_indices()
+    n = A.shape[0]
+    indptr, indices, data = A.indptr, A.indices, A.data
+    Lp = [0]; Li = []; Lv = []
+    for i in range(n):
+        r0 = len(Li)
+        has_diag = False
+        for e in range(indptr[i], indptr[i + 1]):
+            j = int(indices[e])
+            s = float(data[e])
+            a0, a1 = r0, len(Li)
+            b0, b1 = (Lp[j], Lp[j + 1] - 1) if j < i else (r0, a1)
+            while a0 < a1 and b0 < b1:
+                if Li[a0] == Li[b0]:
+                    s -= Lv[a0] * Lv[b0]; a0 += 1; b0 += 1
+                elif Li[a0] < Li[b0]:
+                    a0 += 1
+                else:
+                    b0 += 1
+            if j < i:
+                Li.append(j); Lv.append(s / Lv[Lp[j + 1] - 1])
+            else:
+                if not s > 0.0:
+                    raise ValueError("Encountered nonpositive pivot.")
+                Li.append(i); Lv.append(float(np.sqrt(s))); has_diag = True
+        if not has_diag:
+            raise ValueError("Encountered nonpositive pivot.")
+        Lp.append(len(Li))
+    return sp.csr_matrix((np.array(Lv), np.array(Li, dtype=np.int64), np.array(Lp, dtype=np.int64)), shape=(n, n))
+
+
 def PCG(H, e, pcg_options=None):
     """``[d,it,res,resk] = PCG(H,e[,pcg_options])`` -- reference PCG.m:1-105.
 
@@ -41,8 +77,10 @@ def PCG(H, e, pcg_options=None):
     elif ii == 3:                                             # PCG.m:40-41
         D = sp.diags(Hs.diagonal()).tocsc()
         P = (D, sp.tril(Hs, -1).tocsc(), sp.triu(Hs, 1).tocsc())
-    elif ii == 4:
-        raise NotImplementedError("precd=4 (ichol, PCG.m:46) is not restated; SURVEY.md 8f row 3")
+    elif ii == 4:                                             # PCG.m:45-51
+        if not sp.issparse(H):
+            raise ValueError("iC requires H is sparse!")      # PCG.m:50
+        P = ichol0(Hs)
     elif ii == 5:                                             # PCG.m:55-62
         if "nf" not in opts:
             raise ValueError("SSOR for bigraph requires pcg_options.nf!!!")      # PCG.m:64
@@ -65,6 +103,9 @@ def PCG(H, e, pcg_options=None):
             p2 = P[0] @ p1
             # PCG.m:99: `w*(2-w) * (D+wU) \ p2` parses as ((w*(2-w))*(D+wU)) \ p2
             return spla.spsolve_triangular((w * (2 - w) * (P[0] + w * P[2])).tocsr(), p2, lower=False)
+        if ii == 4:                                           # PCG.m:100-101  p = P\r; p = P'\p
+            p1 = spla.spsolve_triangular(P, r, lower=True)
+            return spla.spsolve_triangular(P.T.tocsr(), p1, lower=False)
         return P @ r
 
     it = 0

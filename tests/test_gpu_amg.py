@@ -276,8 +276,11 @@ def test_pcg_errors(gpu):
         gpu.PCG(A, np.ones(10), {"precd": 5, "retol": None, "maxit": None, "guess": None})
     assert ei.value.status == "SSN_E_PCG_NF"
     with pytest.raises(gpu.SsnError) as ei:
-        gpu.PCG(A, np.ones(10), {"precd": 4, "retol": None, "maxit": None, "guess": None})
+        gpu.PCG(A, np.ones(10), {"precd": 7, "retol": None, "maxit": None, "guess": None})
     assert ei.value.status == "SSN_E_UNSUPPORTED"
+    with pytest.raises(gpu.SsnError) as ei:
+        gpu.PCG(-A, np.ones(10), {"precd": 4, "retol": None, "maxit": None, "guess": None})      # ichol: nonpositive pivot
+    assert ei.value.status == "SSN_E_NOT_SPD"
     with pytest.raises(gpu.SsnError) as ei:
         gpu.Class_AMG(A, np.ones(10), {"bigph": 1, "retol": None, "maxit": None, "theta": None, "smoth": None,
                                         "cycle": None, "isnsp": None, "inter": None, "guess": None})

@@ -294,3 +294,32 @@ def test_generic_twogrid_matches_oracle(gpu, oracle):
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
     with pytest.raises(Exception):
         gpu.twogrid(B, b2, {"retol": 1e-10, "bigph": 1, "maxit": 4, "smoth": 3, "isnsp": 0, "guess": None})   # fnode missing
+
+
+@pytest.mark.parametrize("precd", [3, 4])
+def test_pcg_ssor_and_ichol_match_oracle(gpu, oracle, precd):
+    """PCG.m precd 3 (SSOR) and 4 (ichol) through the C ABI (level-scheduled sparse triangular solves inside
+    the persistent PCG kernel) against the oracle: a grid Laplacian (many dependency levels) and a KKT matrix
+    Jk = bk1*I + H0/tk of the path (two levels); iteration counts, residual histories, solutions."""
+    import scipy.sparse as sp
+    g = 24
+    T = sp.diags([-np.ones(g - 1), 2 * np.ones(g), -np.ones(g - 1)], [-1, 0, 1])
+    A = (sp.kron(sp.identity(g), T) + sp.kron(T, sp.identity(g)) + 0.05 * sp.identity(g * g)).tocsc()
+    rs = np.random.RandomState(6)
+    m, n = 130, 110
+    s = rs.random_sample(m * n) < 0.05
+    H0 = oracle.ASAt(s, rs.random_sample(m) + 0.5, rs.random_sample(n) + 0.5)
+    Jk = (0.3 * sp.identity(m + n) + H0 / 0.8).tocsc()
+    for M in (A, Jk):
+        b = rs.standard_normal(M.shape[0])
+        o = {"retol": 1e-11, "maxit": 2000, "precd": precd, "guess": None}
+        d_ref, it_ref, res_ref, resk_ref = oracle.PCG(M, b, o)
+        d, it, res, resk = gpu.PCG(M, b, o)
+        assert abs(it - it_ref) <= 1, (it, it_ref)
+        k = min(it, it_ref) - 1
+        assert np.allclose(resk[:k], resk_ref[:k], rtol=1e-5, atol=1e-14)
+        assert np.linalg.norm(d - d_ref) <= 1e-8 * np.linalg.norm(d_ref)
+        assert np.linalg.norm(M @ d - b) <= 1e-9 * np.linalg.norm(b)
+    if precd == 4:
+        with pytest.raises(Exception):
+            gpu.PCG((A - 10 * sp.identity(g * g)).tocsc(), rs.standard_normal(g * g), {"retol": 1e-11, "maxit": 10, "precd": 4, "guess": None})

@@ -294,3 +294,28 @@ def test_generic_twogrid_on_a_grid_laplacian():
     assert rel <= 1e-10 and it < 60 and np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
     with pytest.raises(AMGError):
         oracle.twogrid(A, b, {"retol": 1e-10, "bigph": 1, "maxit": 5, "smoth": 3, "isnsp": 0, "guess": None})
+
+
+def test_pcg_preconditioners_3_and_4():
+    """PCG.m precd 3 (SSOR, :39-44, 96-99) and 4 (ichol, :45-51, 100-101) in the oracle: the IC(0) factor
+    reproduces H on H's pattern, both preconditioners cut the iteration count of plain CG and solve the
+    system; a matrix that is not positive definite is ichol's 'nonpositive pivot' error."""
+    import scipy.sparse as sp
+    import oracle
+    from oracle.pcg import ichol0
+    g = 12
+    T = sp.diags([-np.ones(g - 1), 2 * np.ones(g), -np.ones(g - 1)], [-1, 0, 1])
+    A = (sp.kron(sp.identity(g), T) + sp.kron(T, sp.identity(g)) + 0.05 * sp.identity(g * g)).tocsc()
+    L = ichol0(A)
+    assert (sp.triu(L, 1)).nnz == 0 and L.nnz == sp.tril(A).nnz
+    R = (L @ L.T - A).tocsr(); pat = A.tocsr()
+    assert max(abs(R[i, j]) for i, j in zip(*pat.nonzero())) <= 1e-13
+    b = np.random.RandomState(0).standard_normal(g * g)
+    its = {}
+    for precd in (1, 3, 4):
+        d, it, res, resk = oracle.PCG(A, b, {"retol": 1e-11, "maxit": 1000, "precd": precd, "guess": None})
+        assert np.linalg.norm(A @ d - b) <= 1e-9 * np.linalg.norm(b)
+        its[precd] = it
+    assert its[3] < its[1] and its[4] < its[1]
+    with pytest.raises(ValueError):
+        ichol0((A - 10 * sp.identity(g * g)).tocsc())
