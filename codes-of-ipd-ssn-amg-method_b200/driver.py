@@ -74,7 +74,7 @@ def warmup_class1_unfused(c, r, l, p, q, gama, res=0.0, maxit=100):
 
 
 def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
-                   on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None):
+                   on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None, pcg_options=None):
     """APD outer loop + SsN inner loop -- reference Class1/APD_SsN_Class1.m:32-275, on the device.
 
     ``on_ssn_step(state)`` is called right before every inner linear solve with a dict holding
@@ -88,7 +88,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
     b = torch.cat([r, l])
     bk = 1.0
     SsN_IT = 50; SsN_Tol1 = 1e-11; nu = 0.2; delta = 0.9; ll_max = 500   # :36
-    amg_options = dict(amg_options or CLASS1_AMG_OPTIONS); pcg_options = dict(CLASS1_PCG_OPTIONS)
+    amg_options = dict(amg_options or CLASS1_AMG_OPTIONS); pcg_options = dict(pcg_options or CLASS1_PCG_OPTIONS)
     t_start = time.time()
     xk, lk = warmup_class1(c, r, l, p, q, gama, 0.0, warm_maxit)         # :59
     torch.cuda.synchronize(); t_warm = time.time() - t_start
@@ -131,7 +131,15 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
                              "s": s, "Fk": Fk_old, "H0": H0, "E": ev["count"]})
             t0 = time.time()
             prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
-            if inner_solver == 3:
+            if inner_solver == 2:                                       # :149-152, PCG on Jk = bk1*I + (T+H0)/tk
+                import scipy.sparse as sp
+                po = dict(pcg_options)
+                if po.get("precd") == 5:
+                    po["nf"] = n
+                Jk = (bk1 * sp.identity(m + n, format="csr") + H0.to_scipy() / tk).tocsr()      # assembled on the host: not the default path
+                zeta, itpcg, respcg, _ = api.PCG(api.DeviceCSR.from_scipy(Jk), -Fk_old, po)
+                info = [0, 0]
+            elif inner_solver == 3:
                 zeta, itpcg, respcg, info = api.aug_PCG(prob_data, pcg_options)
             elif inner_solver == 4:
                 zeta, itpcg, respcg, info = api.Hybrid_AMG(prob_data, amg_options)
@@ -140,7 +148,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
                 zeta, itpcg, respcg, info = api.Hybrid_twogrid(prob_data, amg_options)          # :178
                 stats["amg_calls"] += 1
             else:
-                raise ValueError("inner_solver must be 3 (aug_PCG), 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
+                raise ValueError("inner_solver must be 2 (PCG), 3 (aug_PCG), 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
             torch.cuda.synchronize(); stats["solve_s"] += time.time() - t0
             stats["solve_calls"].append((int(ev["count"]), time.time() - t0, int(itpcg), int(info[0])))
             its.append(itpcg)

@@ -143,3 +143,22 @@ def test_staged_warm_start_equals_the_fused_warm_start(gpu, m, n, gama):
     x, lk = sd.warmup_class1_sharded_fused(A, c, torch.cat([r, l]), gama, 25)
     assert torch.allclose(x, x_ref, rtol=1e-10, atol=1e-13)
     assert torch.allclose(lk, lk_ref, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("inner_solver,precd", [(2, 2), (2, 4), (3, 2), (5, None)])
+def test_every_selectable_inner_solver_reaches_the_same_optimum(gpu, inner_solver, precd):
+    """Class1/APD_SsN_Class1.m:66-70: inner_solver 2 (PCG on Jk, here with the Jacobi and the ichol
+    preconditioner), 3 (aug_PCG) and 5 (Hybrid_twogrid) against the default 4 (Hybrid_AMG) on a small grid
+    problem: all solve the same Newton systems to 1e-11, so the solves converge to the same objective."""
+    import importlib
+    drv = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+    P = gpu.problems.grid_problem(8, seed=0)
+    gpu.rng_reset()
+    ref = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"])
+    gpu.rng_reset()
+    po = None if precd is None else {"retol": 1e-11, "maxit": 10000, "precd": precd, "guess": None}
+    out = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], inner_solver=inner_solver, pcg_options=po)
+    assert ref["stats"]["converged"] and out["stats"]["converged"]
+    assert abs(out["fxk"][-1] - ref["fxk"][-1]) <= 1e-6 * max(abs(ref["fxk"][-1]), 1e-3)
+    k = min(3, len(ref["fxk"]), len(out["fxk"]))
+    assert np.allclose(out["fxk"][:k], ref["fxk"][:k], rtol=1e-7)
