@@ -156,7 +156,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             f0 = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old)  # :182
             cFk_old = f0 + 0.5 * tk * n2_old
             ress = abs(float(Fk_old @ zeta))
-            # :189-211, ll = 0 alone, then eight backtracking steps per read of wk (api.linesearch)
+            # :189-211, ll = 0 alone, then 8-128 backtracking steps per read of wk (adaptive, api.linesearch)
             lk_new, ll, _, _, passes = api.linesearch(wk, lk_old, zeta, wlk, p, q, tk, bk1, cFk_old, ress, gam, nu, delta, ll_max)
             stats["ls_trials"] += ll + 1; stats["ls_passes"] += passes
             ev = api.prox_residual(wk, lk_new, p, q, tk, gam, want=("Axprox", "s"))

@@ -170,25 +170,25 @@ class ShardedStep:
         torch = self.torch
         lams, f0s, parts = [], [], []
         per = 128 if screened else 8
-        votes = None
+        cands = None
         for t0 in range(0, nt, per):
             k = min(per, nt - t0)
             lamT, f0 = self.ops.trial_vectors(lk, zeta, self.wlk, delta, ll0 + t0, k)
             if screened:
                 out = self.ops.prox_trials_lin(self.w_loc, self._lam_loc(lk), self._lam_loc(zeta), self.p_loc, self.q, self.tk,
                                                delta, ll0 + t0, k)
-                parts.append(out[:k]); votes = out[k:k + 1] if votes is None else votes + out[k:k + 1]
+                parts.append(out[:k]); cands = out[k:k + 1] if cands is None else cands + out[k:k + 1]
             else:
                 lt_loc = torch.cat([lamT[:, : self.n], lamT[:, self.n + self.r0: self.n + self.r1]], dim=1).contiguous()
                 parts.append(self.ops.prox_trials(self.w_loc, lt_loc, self.p_loc, self.q, self.tk, self.gama))
             lams.append(lamT); f0s.append(f0)
-        if votes is not None:
-            parts.append(votes)
+        if cands is not None:
+            parts.append(cands)
         part = torch.cat(parts) if len(parts) > 1 else parts[0]
         self._all_reduce(part)
         vals = torch.cat([part[:nt]] + f0s).cpu().tolist()
         dens = None
-        if votes is not None:
+        if cands is not None:
             launches = (nt + per - 1) // per
             dens = float(part[nt]) / launches / max(1.0, float(self.m) * self.n)
         return (torch.cat(lams) if len(lams) > 1 else lams[0]), vals, dens
@@ -236,7 +236,7 @@ class ShardedStep:
         cFk_old = f0 + 0.5 * tk * n2_old
         ress = abs(float(Fk_old @ zeta))
         # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
-        # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernel, whose vote
+        # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernels, whose candidate
         # count says how sparse the trial plans are -- 64, then 128 steps per read while under 10 % of the
         # entries survive the screen, 16 under 25 %, else the dense 8-step kernel (as ssn_linesearch does)
         screened = np.isinf(self.gama) and self.gama > 0 and hasattr(self.ops, "prox_trials_lin") and self.screen
