@@ -6,7 +6,7 @@ repository root (``import ssnamg``) or ``importlib.import_module``.  ``csrc/`` h
 kernels and the C ABI (``include/ssnamg.h``); ``api.py`` mirrors the reference's MATLAB function
 signatures on top of it; ``problems.py`` has the synthetic configurations of BASELINE.json.
 """
-from . import problems, driver                                            # noqa: F401
+from . import problems, driver, matio                                            # noqa: F401
 from ._lib import LIB_PATH, SIGNATURES, SsnError, load                    # noqa: F401
 from .api import (Ax, Aty, ASAt, ASAtz, ASAt_coo, active_coo, invAAt, invHHt, prox_residual, prox_trials, prox_trials_lin, trial_vectors, linesearch, warmup_class1, warm_stage, apd_begin, apd_end,    # noqa: F401
                   strength, mis_set, cf_split, transfer, amg_setup, amg_clear,

@@ -66,14 +66,20 @@ def random_problem(m, n, seed=0):
 
 
 def load_bundled_class1(path):
-    """Reads the reference's Class1/InputData/data1-500.mat (MAT v5; needs ``mat_dtype=True``,
-    otherwise p, q come back uint8 and m, n uint16)."""
-    import scipy.io
+    """Reads the reference's Class1/InputData/data1-500.mat (MAT v5 with integer-compressed doubles:
+    p, q stored as uint8 and m, n as uint16) through the C-side reader (``matio.py``, libssnmat.so)."""
+    from . import matio
     if not os.path.exists(path):
         raise FileNotFoundError(path)
-    d = scipy.io.loadmat(path, mat_dtype=True)
-    f = lambda k: np.ascontiguousarray(d[k], dtype=np.float64).reshape(-1)
-    gama = f("gama")
-    return {"c": f("c"), "r": f("r"), "l": f("l"), "p": f("p"), "q": f("q"),
-            "gama": np.inf if np.all(np.isinf(gama)) else gama,
-            "m": int(d["m"][0, 0]), "n": int(d["n"][0, 0])}
+    P = matio.load_problem(path)
+    return {k: P[k] for k in ("c", "r", "l", "p", "q", "gama", "m", "n")}
+
+
+def load_bundled_class2(path):
+    """Class2/InputData/data4-500.mat: as above plus ``phi`` and ``mu`` (no ``gama``; the m x n matrix
+    ``C`` of the file is ``c`` reshaped and is not returned)."""
+    from . import matio
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    P = matio.load_problem(path)
+    return {k: P[k] for k in ("c", "r", "l", "p", "q", "phi", "mu", "m", "n")}
