@@ -61,6 +61,7 @@ SIGNATURES = {
     "ssn_profile_enable": (_int, [_vp, _int]),
     "ssn_set_dense_tail": (_int, [_vp, _int, _int]),
     "ssn_set_persistent": (_int, [_vp, _int]),
+    "ssn_set_device_setup": (_int, [_vp, _int]),
     "ssn_debug_barrier_bench": (_int, [_vp, _int, _int, _pdbl]),
     "ssn_kernel_timer": (_int, [_vp, _int]),
     "ssn_kernel_timer_read": (_int, [_vp, _pdbl, _pi64]),
@@ -120,6 +121,7 @@ SIGNATURES = {
     "ssn_amg4pot": (_int, [_vp, C.POINTER(ProbData), C.POINTER(AmgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_pcg4pot": (_int, [_vp, C.POINTER(ProbData), C.POINTER(PcgOptions), _vp, _pint, _pdbl, _pint]),
     "ssn_rescaled_system": (_int, [_vp, C.POINTER(ProbData), _pcsr, _vp]),
+    "ssn_jk_system": (_int, [_vp, C.POINTER(ProbData), _pcsr]),
     "ssn_spmv": (_int, [_vp, _pcsr, _vp, _vp]),
     "ssn_spgemm": (_int, [_vp, _pcsr, _pcsr, _pcsr]),
     "ssn_transpose": (_int, [_vp, _pcsr, _pcsr]),

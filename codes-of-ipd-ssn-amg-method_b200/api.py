@@ -670,6 +670,16 @@ def rescaled_system(prob_data):
     return DeviceCSR(ctx, st), f.cpu().numpy()
 
 
+def jk_system(prob_data):
+    """``Jk = bk1*speye(m+n) + (T+H0)/tk`` of Class1/APD_SsN_Class1.m:147,151, assembled on the device
+    (``prob_data`` as for ``Hybrid_AMG``: ``bk1, tk, p, q, H0, z`` and optionally ``T``; only ``bk1, tk, T, H0`` are read)."""
+    ctx = context(); keep = []
+    pd, m, n = _prob_data(prob_data, ctx, keep)
+    st = CSR()
+    ctx.call("ssn_jk_system", C.byref(pd), C.byref(st))
+    return DeviceCSR(ctx, st)
+
+
 # ------------------------------------------------------------------ sparse utilities
 
 def spmv(A, x):
@@ -710,6 +720,11 @@ def kernel_timer_read():
 def set_persistent(enable=True):
     """Class_AMG's solve loop as one persistent cooperative kernel (default) or kernel by kernel."""
     ctx = context(); ctx.call("ssn_set_persistent", 1 if enable else 0)
+
+
+def set_device_setup(enable=True):
+    """PCG's SSOR / IC(0) factors and dependency levels built on the device (``True``) or on the host (default)."""
+    ctx = context(); ctx.call("ssn_set_device_setup", 1 if enable else 0)
 
 
 def set_dense_tail(enable=True, max_n=0):

@@ -90,6 +90,15 @@ void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptio
 void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_options* opts, double* d, int* it_out,
                double* res_out, double* resk_host);
 
+// ---- triangular preconditioner setup and Jk assembly on the device (trifactor.cu)
+struct TriFactors {
+    Buf<int> lp, li, up, ui, lrows, llev, urows, ulev; Buf<double> lv, uv, mid;
+    int nl = 0, nu = 0; bool has_mid = false;
+};
+void build_tri_factors_device(ssn_ctx* c, const CsrView& H, int precd, TriFactors& F);
+// Jk = bk1*speye(m+n) + (T + H0)/tk -- Class1/APD_SsN_Class1.m:147,151
+void jk_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Jk);
+
 void debug_cycles(unsigned long long* out64, bool reset);
 double barrier_bench(ssn_ctx* c, int iters, int which);
 void build_cluster_plan(ssn_ctx* c, Hierarchy& H);

@@ -1940,7 +1940,13 @@ void pcg_solve(ssn_ctx* c, const CsrView& H, const double* e, const ssn_pcg_opti
     // factorisation is inherently sequential), the solves of every iteration run in the kernel.
     Buf<int> lp_d, li_d, up_d, ui_d, lrows_d, llev_d, urows_d, ulev_d;
     Buf<double> lv_d, uv_d, mid_d;
-    if (precd == 3 || precd == 4) {
+    TriFactors F;
+    if ((precd == 3 || precd == 4) && c->device_setup) {
+        // SSN_DEVICE_SETUP=1: the same factors, levels and row groups built on the device (trifactor.cu)
+        build_tri_factors_device(c, H, precd, F);
+        a.lp = F.lp; a.li = F.li; a.lv = F.lv; a.up = F.up; a.ui = F.ui; a.uv = F.uv; a.mid = F.has_mid ? F.mid.p : nullptr;
+        a.lrows = F.lrows; a.llev = F.llev; a.nlev_l = F.nl; a.urows = F.urows; a.ulev = F.ulev; a.nlev_u = F.nu;
+    } else if (precd == 3 || precd == 4) {
         const int64_t nnz = H.nnz;
         std::vector<int> hp((size_t)n + 1), hi((size_t)nnz); std::vector<double> hv((size_t)nnz);
         SSN_CUDA(cudaMemcpyAsync(hp.data(), H.ptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));

@@ -54,6 +54,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = (e && e[0] == '1'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
         SSN_CUDA(cudaSetDevice(device));
@@ -105,6 +106,7 @@ int ssn_debug_barrier_bench(ssn_ctx* c, int iters, int which, double* cycles_per
     return guarded(c, [&] { *cycles_per_barrier = barrier_bench(c, iters, which); });
 }
 int ssn_set_persistent(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->persist = on != 0; return SSN_OK; }
+int ssn_set_device_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->device_setup = on != 0; return SSN_OK; }
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;
@@ -414,6 +416,13 @@ int ssn_rescaled_system(ssn_ctx* c, const ssn_prob_data* pd, ssn_csr* Ae, double
         SSN_REQUIRE(Ae, SSN_E_INVALID, "rescaled_system: null");
         Csr ae; Buf<double> qp, Kd;
         rescaled_system(c, pd, ae, f, qp, Kd); sync(c); ae.release_to(Ae);
+    });
+}
+
+int ssn_jk_system(ssn_ctx* c, const ssn_prob_data* pd, ssn_csr* Jk) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(Jk, SSN_E_INVALID, "jk_system: null");
+        Csr jk; jk_system(c, pd, jk); sync(c); jk.release_to(Jk);
     });
 }
 

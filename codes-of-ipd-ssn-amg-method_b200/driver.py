@@ -10,6 +10,7 @@ semismooth-Newton residual, the active set and the line-search objective use the
 ``Aty`` -> prox -> ``Ax`` chain; the arithmetic per entry is identical.
 """
 import math
+import os
 import time
 
 import numpy as np
@@ -136,8 +137,11 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
                 po = dict(pcg_options)
                 if po.get("precd") == 5:
                     po["nf"] = n
-                Jk = (bk1 * sp.identity(m + n, format="csr") + H0.to_scipy() / tk).tocsr()      # assembled on the host: not the default path
-                zeta, itpcg, respcg, _ = api.PCG(api.DeviceCSR.from_scipy(Jk), -Fk_old, po)
+                if os.environ.get("SSN_DEVICE_SETUP") == "1":
+                    Jk = api.jk_system(prob_data)                       # ssn_jk_system: assembled on the device
+                else:                                                   # on the host (not the default solver) until ssn_jk_system has run on a B200
+                    Jk = api.DeviceCSR.from_scipy((bk1 * sp.identity(m + n, format="csr") + H0.to_scipy() / tk).tocsr())
+                zeta, itpcg, respcg, _ = api.PCG(Jk, -Fk_old, po)
                 info = [0, 0]
             elif inner_solver == 3:
                 zeta, itpcg, respcg, info = api.aug_PCG(prob_data, pcg_options)

