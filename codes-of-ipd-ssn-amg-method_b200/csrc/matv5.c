@@ -84,7 +84,7 @@ static void parse_matrix(const uint8_t* p, uint32_t n, ssn_mat_var* v) {
     { const uint32_t len = nb < sizeof(v->name) - 1 ? nb : (uint32_t)sizeof(v->name) - 1; memcpy(v->name, d, len); v->name[len] = 0; }
     p += adv;
     v->rows = dims[0]; v->cols = dims[1];
-    if (cls < mxDOUBLE_CLASS || cls > mxUINT64_CLASS || is_complex || dims[0] < 0) return;   /* cell, struct, char, sparse, complex, N-D */
+    if (cls < mxDOUBLE_CLASS || cls > mxUINT64_CLASS || is_complex || dims[0] < 0 || dims[1] < 0) return;   /* cell, struct, char, sparse, complex, N-D */
     d = read_tag(p, end, &type, &nb, &adv);                                /* real part */
     if (!d) return;
     const int ts = type_size(type);
@@ -139,7 +139,7 @@ int ssn_mat_open(const char* path, ssn_mat** out) {
             zs.next_out = buf + 8; zs.avail_out = inb;
             zr = inflate(&zs, Z_FINISH);
             inflateEnd(&zs);
-            if (zr != Z_STREAM_END && !(zr == Z_OK && zs.avail_out == 0) && !(zr == Z_BUF_ERROR && zs.avail_out == 0)) { free(buf); ssn_mat_close(m); return SSN_MAT_E_ZLIB; }
+            if (zs.avail_out != 0 || (zr != Z_STREAM_END && zr != Z_OK && zr != Z_BUF_ERROR)) { free(buf); ssn_mat_close(m); return SSN_MAT_E_ZLIB; }   /* the element must inflate to exactly the size its tag states */
             v.buf = buf;
             if (itype == miMATRIX) parse_matrix(buf + 8, inb, &v);
             else { free(buf); p += adv; continue; }
