@@ -164,11 +164,12 @@ void build_tri_factors_device(ssn_ctx* c, const CsrView& H, int precd, TriFactor
     levels_and_buckets(c, n, F.up.p, F.ui.p, 1, lev, F.urows, F.ulev, F.nu);
 }
 
-// Jk = bk1*speye(m+n) + (T + H0)/tk -- Class1/APD_SsN_Class1.m:147,151 (the matrix PCG is given for inner_solver = 2)
+// Jk = bk1*speye(m+n) + (T + H0)/tk -- Class1/APD_SsN_Class1.m:147,151 (the matrix PCG is given for inner_solver = 2);
+// `/tk` is a product with 1/tk like everywhere on the path (the oracle's frozen convention)
 namespace {
 
 __global__ void jk_fill_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-                               const double* __restrict__ t, double bk1, double tk, const int* __restrict__ optr,
+                               const double* __restrict__ t, double bk1, double inv_tk, const int* __restrict__ optr,
                                int* __restrict__ oidx, double* __restrict__ oval) {
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -185,13 +186,13 @@ __global__ void jk_fill_kernel(int N, const int* __restrict__ ptr, const int* __
         if (e < e1) {
             const int pos = o + (e - e0) + ((!has && j > row) ? 1 : 0);
             oidx[pos] = j;
-            oval[pos] = (j == row) ? __dadd_rn(bk1, __ddiv_rn(__dadd_rn(tv, h), tk)) : __ddiv_rn(h, tk);
+            oval[pos] = (j == row) ? __dadd_rn(bk1, __dmul_rn(inv_tk, __dadd_rn(tv, h))) : __dmul_rn(inv_tk, h);
         }
         nlow += __popc(lowmask);
     }
     if (!has && lane == 0) {
         oidx[o + nlow] = row;
-        oval[o + nlow] = __dadd_rn(bk1, __ddiv_rn(tv, tk));
+        oval[o + nlow] = __dadd_rn(bk1, __dmul_rn(inv_tk, tv));
     }
 }
 
@@ -215,7 +216,7 @@ void jk_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Jk) {
     Buf<int> len(c, N);
     SSN_LAUNCH(c, jk_count_kernel, cdiv((int64_t)N * 32, 256), 256, 0, N, H0.ptr, H0.idx, len.p);
     Jk = csr_alloc_from_counts(c, N, N, len);
-    SSN_LAUNCH(c, jk_fill_kernel, cdiv((int64_t)N * 32, 256), 256, 0, N, H0.ptr, H0.idx, H0.val, pd->t_dev, pd->bk1, pd->tk,
+    SSN_LAUNCH(c, jk_fill_kernel, cdiv((int64_t)N * 32, 256), 256, 0, N, H0.ptr, H0.idx, H0.val, pd->t_dev, pd->bk1, 1.0 / pd->tk,
                Jk.ptr.p, Jk.idx.p, Jk.val.p);
 }
 

@@ -400,7 +400,8 @@ SSN_API int ssn_rescaled_system(ssn_ctx *ctx, const ssn_prob_data *pd, ssn_csr *
 
 /* Jk = bk1*speye(m+n) + (T + H0)/tk -- Class1/APD_SsN_Class1.m:147,151: the assembled KKT matrix that
  * inner_solver 1 / 2 hand to `\` / PCG (pd->t_dev may be NULL = T is zero; p, q, z are not read).  The diagonal of
- * Jk is always stored, also where H0 has none.  Release with ssn_csr_free. */
+ * Jk is always stored, also where H0 has none; `/tk` is a product with 1/tk (the oracle's frozen convention,
+ * as in ssn_rescaled_system).  Release with ssn_csr_free. */
 SSN_API int ssn_jk_system(ssn_ctx *ctx, const ssn_prob_data *pd, ssn_csr *Jk_out);
 
 /* ------------------------------------------------------------------ sparse utilities
