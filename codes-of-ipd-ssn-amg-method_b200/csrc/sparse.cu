@@ -11,10 +11,12 @@ namespace ssn {
 // ------------------------------------------------------------------ scans / sorts
 
 namespace {
-constexpr int kSmallScanMax = 1 << 18;
 // out[i] = in[0] + ... + in[i-1] for i < n (and out[n] = total when with_total): ONE block, one launch, no
 // temporary storage -- the AMG setup runs ~70 scans of a few thousand counts per hierarchy, where the two
 // kernels + temporary allocation of cub::DeviceScan cost more than the scan itself.  In-place safe.
+// Used up to ssn_ctx::small_scan_max counts (16384; env SSN_SMALL_SCAN_MAX): every thread walks its own
+// contiguous chunk, so beyond that the single block loses to cub (launch list of round 1: 3-4 us up to 8k
+// counts, 10 us at 16k, 18 us at 32k, 59 us at 130k+).
 __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* out, int n, int with_total) {
     __shared__ int wsum[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* ou
 
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
     if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return 0; }
-    if (n <= kSmallScanMax) {
+    if (n <= c->small_scan_max) {
         SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1);
         return (int64_t)read_scalar(c, ptr + n);
     }
@@ -57,7 +59,7 @@ int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
 
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n) {
     if (n == 0) return;
-    if (n <= kSmallScanMax) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, in, out, (int)n, 0); return; }
+    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, in, out, (int)n, 0); return; }
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, c->stream));
     Buf<unsigned char> tmp(c, tmp_bytes);
