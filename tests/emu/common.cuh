@@ -1,24 +1,29 @@
 // tests/emu/common.cuh -- HOST stand-in for csrc/common.cuh (test infrastructure only).
 //
-// There is no GPU in the build container.  Kernels that use nothing but thread indices, plain loads / stores,
-// integer atomics, the *_rn arithmetic intrinsics and the warp votes can still be executed on the CPU: this header
-// gives them the names they expect (blockIdx, threadIdx, __ballot_sync, ...), a Buf / Csr / CsrView with the same
-// members as the real ones (backed by malloc), and an SSN_LAUNCH that runs every thread of the grid -- one after the
-// other, or, when emu::warp_mode is set, the 32 lanes of each warp as 32 host threads that meet at the votes.
-// A test copies the real .cu (and the real amg.cuh / sparse.cuh) next to this file and compiles it with g++, so the
-// text that is checked is the text nvcc compiles.  It checks indexing, ordering and arithmetic; it does not check
-// what only the hardware can (memory ordering between blocks, occupancy, cooperative launches).
+// There is no GPU in the build container.  Kernels that use thread indices, plain loads / stores, shared memory,
+// __syncthreads, warp votes / shuffles, atomics and the *_rn arithmetic intrinsics can still be executed on the CPU:
+// this header gives them the names they expect, a Buf / Csr / CsrView with the same members as the real ones (backed
+// by malloc), stubs of the few CUDA runtime calls the host code makes, and an SSN_LAUNCH that runs every thread of
+// the grid: one after the other (emu::threaded = false: kernels without barriers, votes or shuffles), or block by
+// block with one host thread per CUDA thread that meet at the barriers (emu::threaded = true).
+// A test copies the real .cu / .cuh files next to this file and compiles them with g++, so the text that is checked
+// is the text nvcc compiles (one mechanical edit: `extern __shared__ T x[];` becomes a pointer to emu::dyn_smem).
+// It checks indexing, ordering and arithmetic; it does not check what only the hardware can (memory ordering between
+// blocks, occupancy, cooperative launches, shared-memory capacity).
 #pragma once
 
 #include <algorithm>
 #include <barrier>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <numeric>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,17 +37,45 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __shared__ static            /* blocks run one at a time, so one static instance is the block's shared memory */
 
 typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 namespace emu {
 struct Dim { int x = 1, y = 1, z = 1; };
-struct WarpShared { std::barrier<> bar{32}; unsigned votes[32]; };
-inline bool warp_mode = false;                    // set by the harness before launching a kernel that votes
+struct WarpShared {
+    std::barrier<> bar; unsigned long long slots[32];
+    explicit WarpShared(int lanes) : bar(lanes) {}
+};
+struct BlockShared {
+    std::barrier<> bar;
+    explicit BlockShared(int threads) : bar(threads) {}
+};
+inline bool threaded = false;                     // set by the harness: one host thread per CUDA thread, block by block
 inline thread_local WarpShared* warp = nullptr;
+inline thread_local BlockShared* block = nullptr;
+alignas(64) inline unsigned char dyn_smem[256 * 1024];
+inline void need_threads(const char* what) {
+    if (!warp) { std::fprintf(stderr, "emu: %s needs emu::threaded = true\n", what); std::abort(); }
+}
 }
 inline thread_local emu::Dim blockIdx, threadIdx;
 inline thread_local emu::Dim blockDim, gridDim;
+
+using std::max;
+using std::min;
+inline int min(int a, unsigned b) { return a < (int)b ? a : (int)b; }
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline long long max(long long a, int b) { return a > b ? a : b; }
 
 // ---- arithmetic intrinsics: one IEEE operation each (compile with -ffp-contract=off)
 inline double __dmul_rn(double a, double b) { return a * b; }
@@ -50,21 +83,64 @@ inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
-inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }     // launches are sequential or one warp at a time
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 
-// ---- warp votes (warp_mode only: the 32 lanes are 32 host threads)
-inline unsigned __ballot_sync(unsigned, bool pred) {
+// ---- atomics (real ones: the threads of a block are host threads)
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline double atomicAdd(double* p, double v) {
+    unsigned long long* q = (unsigned long long*)p; unsigned long long o = __atomic_load_n(q, __ATOMIC_SEQ_CST), n;
+    double od;
+    do { std::memcpy(&od, &o, 8); const double nd = od + v; std::memcpy(&n, &nd, 8); } while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return od;
+}
+inline int atomicMax(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+inline int atomicMin(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int* p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+// ---- block barrier, warp votes and shuffles (emu::threaded only)
+inline void __syncthreads() { emu::need_threads("__syncthreads"); emu::block->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::need_threads("__syncwarp"); emu::warp->bar.arrive_and_wait(); emu::warp->bar.arrive_and_wait(); }
+template <class T> inline T emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    emu::need_threads("a warp shuffle / vote");
     emu::WarpShared* w = emu::warp;
-    w->votes[threadIdx.x & 31] = pred ? 1u : 0u;
+    unsigned long long bits = 0; std::memcpy(&bits, &v, sizeof(T));
+    w->slots[threadIdx.x & 31] = bits;
+    w->bar.arrive_and_wait();
+    T r; std::memcpy(&r, &w->slots[src_lane & 31], sizeof(T));
+    w->bar.arrive_and_wait();
+    return r;
+}
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_exchange(v, (threadIdx.x & 31) ^ o); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned o) { const int l = threadIdx.x & 31; return emu_exchange(v, l >= (int)o ? l - (int)o : l); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned o) { const int l = threadIdx.x & 31; return emu_exchange(v, l + (int)o < 32 ? l + (int)o : l); }
+inline unsigned __ballot_sync(unsigned, bool pred) {
+    emu::need_threads("__ballot_sync");
+    emu::WarpShared* w = emu::warp;
+    w->slots[threadIdx.x & 31] = pred ? 1ull : 0ull;
     w->bar.arrive_and_wait();
     unsigned m = 0;
-    for (int l = 0; l < 32; ++l) m |= w->votes[l] << l;
+    const int lanes = std::min(32, blockDim.x - (threadIdx.x & ~31));
+    for (int l = 0; l < lanes; ++l) m |= (unsigned)w->slots[l] << l;
     w->bar.arrive_and_wait();
     return m;
 }
 inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
+inline bool __all_sync(unsigned mask, bool pred) { return __ballot_sync(mask, !pred) == 0u; }
 
 namespace ssn {
 
@@ -79,11 +155,28 @@ struct Error : std::exception {
 struct Hierarchy;
 }  // namespace ssn
 
+// the fields of the real ssn_ctx that the emulated sources read
 struct ssn_ctx {
+    int device = 0;
     cudaStream_t stream = nullptr;
+    std::string err;
     int64_t launches = 0;
-    int num_sms = 148;
+    int num_sms = 2;                      // small grids: every block costs host threads
+    size_t smem_optin = 227 * 1024;
+    uint32_t* mt_state = nullptr;
+    int64_t rng_drawn = 0;
+    ssn::Hierarchy* hier = nullptr;
+    bool no_cluster = true;
+    int64_t persist_max_nnz = (int64_t)1 << 40;
+    bool persist = true, dense_tail = true;
+    int ls_max_nt = 128; bool ls_screen = true;
+    int small_scan_max = 1 << 14;
     bool device_setup = true;
+    int dense_max_n = 2048;
+    bool ktimer = false, prof = false;
+    ssn_ctx() { mt_state = (uint32_t*)std::calloc(625, sizeof(uint32_t)); }
+    ~ssn_ctx() { std::free(mt_state); }
+    ssn_ctx(const ssn_ctx&) = delete; ssn_ctx& operator=(const ssn_ctx&) = delete;
 };
 
 namespace ssn {
@@ -98,10 +191,10 @@ struct Buf {
     Buf& operator=(Buf&& o) noexcept { if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~Buf() { reset(); }
     // filled with 0xA5 so that a read of something never written shows up as garbage, not as a lucky zero
-    void alloc(ssn_ctx* ctx, size_t count) { reset(); c = ctx; n = count; p = (T*)std::malloc((count ? count : 1) * sizeof(T)); std::memset(p, 0xA5, (count ? count : 1) * sizeof(T)); }
-    void reset() { if (p) { std::free(p); p = nullptr; n = 0; } }
+    void alloc(ssn_ctx* ctx, size_t count) { reset(); c = ctx; n = count; p = (T*)std::malloc((count ? count : 1) * sizeof(T)); std::memset((void*)p, 0xA5, (count ? count : 1) * sizeof(T)); }
+    void reset() { if (p) { std::free((void*)p); p = nullptr; n = 0; } }
     T* release() { T* r = p; p = nullptr; n = 0; return r; }
-    void zero() { std::memset(p, 0, (n ? n : 1) * sizeof(T)); }
+    void zero() { std::memset((void*)p, 0, (n ? n : 1) * sizeof(T)); }
     operator T*() const { return p; }
     T* get() const { return p; }
 };
@@ -112,6 +205,10 @@ struct Csr {
     Buf<int> ptr; Buf<int> idx; Buf<double> val;
     Csr() = default;
     Csr(Csr&&) = default; Csr& operator=(Csr&&) = default;
+    ssn_csr view() const {
+        ssn_csr v; v.nrows = nrows; v.ncols = ncols; v.nnz = nnz;
+        v.rowptr_dev = ptr.p; v.colidx_dev = idx.p; v.val_dev = val.p; return v;
+    }
 };
 
 struct CsrView {
@@ -125,54 +222,72 @@ struct CsrView {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+struct Phase { Phase(ssn_ctx*, const char*) {} };
+struct KernelTimer { explicit KernelTimer(ssn_ctx*) {} };
+
 template <class K, class... A>
 inline void emu_launch(ssn_ctx* c, K kernel, int grid, int block, A... args) {
     c->launches++;
     for (int b = 0; b < grid; ++b) {
-        if (!emu::warp_mode) {
+        if (!emu::threaded) {
             for (int t = 0; t < block; ++t) {
                 blockIdx.x = b; threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
                 kernel(args...);
             }
         } else {
-            for (int w0 = 0; w0 < block; w0 += 32) {
-                emu::WarpShared ws;
-                std::vector<std::thread> lanes;
-                for (int l = 0; l < 32; ++l)
-                    lanes.emplace_back([&, l] {
-                        emu::warp = &ws;
-                        blockIdx.x = b; threadIdx.x = w0 + l; blockDim.x = block; gridDim.x = grid;
-                        kernel(args...);
-                        ws.bar.arrive_and_drop();          // a lane that has returned no longer takes part in votes
-                    });
-                for (auto& th : lanes) th.join();
-            }
+            emu::BlockShared bs(block);
+            std::vector<std::unique_ptr<emu::WarpShared>> ws;
+            for (int w0 = 0; w0 < block; w0 += 32) ws.emplace_back(new emu::WarpShared(std::min(32, block - w0)));
+            std::vector<std::thread> threads;
+            threads.reserve((size_t)block);
+            for (int t = 0; t < block; ++t)
+                threads.emplace_back([&, t] {
+                    emu::block = &bs; emu::warp = ws[(size_t)t / 32].get();
+                    blockIdx.x = b; threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
+                    kernel(args...);
+                    emu::warp->bar.arrive_and_drop();       // a thread that has returned no longer takes part in barriers
+                    bs.bar.arrive_and_drop();
+                });
+            for (auto& th : threads) th.join();
         }
     }
 }
-#define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, (grid), (block), __VA_ARGS__)
+#define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, (int)(grid), (int)(block), __VA_ARGS__)
 
 template <class T>
 inline void read_back(ssn_ctx*, const T* dev, T* host, size_t count) { std::memcpy(host, dev, count * sizeof(T)); }
 template <class T>
 inline T read_scalar(ssn_ctx*, const T* dev) { return *dev; }
 
-// the plumbing of sparse.cu that trifactor.cu calls, restated on the host (same contracts)
-inline int64_t scan_counts_to_ptr(ssn_ctx*, const int* counts, int* ptr, int64_t n) {
-    int64_t run = 0;
-    for (int64_t i = 0; i < n; ++i) { const int v = counts[i]; ptr[i] = (int)run; run += v; }
-    ptr[n] = (int)run;
-    return run;
+// scans / sorts: declared here like in the real common.cuh.  Defined by the emulated sparse.cu when a harness compiles
+// it (over tests/emu/cub), else by tests/emu/sparse_host.h.
+void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n);
+int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
+void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int* vals_in, int* vals_out, int64_t n, int key_limit);
+
+inline double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
-inline void exclusive_scan_int(ssn_ctx*, const int* in, int* out, int64_t n) { int run = 0; for (int64_t i = 0; i < n; ++i) { const int v = in[i]; out[i] = run; run += v; } }
-inline void stable_sort_pairs(ssn_ctx*, const int* keys_in, int* keys_out, const int* vals_in, int* vals_out, int64_t n, int key_limit) {
-    std::vector<int64_t> order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys_in[a] < keys_in[b]; });
-    for (int64_t i = 0; i < n; ++i) {
-        if (keys_in[order[i]] < 0 || keys_in[order[i]] >= key_limit) throw Error(SSN_E_INVALID, "stable_sort_pairs: key out of range");
-        keys_out[i] = keys_in[order[i]]; vals_out[i] = vals_in[order[i]];
+inline int warp_sum_int(int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+inline double block_sum(double v, double* smem32) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (lane < nw) ? smem32[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) smem32[0] = t;
     }
+    __syncthreads();
+    t = smem32[0];
+    return t;
 }
 
 }  // namespace ssn

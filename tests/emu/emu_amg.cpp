@@ -1,0 +1,83 @@
+// tests/emu/emu_amg.cpp -- runs the REAL csrc/sparse.cu and csrc/amg_setup.cu on the host through tests/emu/common.cuh
+// (the test copies them, with amg.cuh / sparse.cuh, next to this file; cub is tests/emu/cub).  Test infrastructure only.
+#include "common.cuh"
+#include "amg.cuh"
+
+namespace ssn {
+// referenced by amg_setup.cu, defined in translation units that are not emulated (never reached: no_cluster = true)
+void build_cluster_plan(ssn_ctx*, Hierarchy&) { throw Error(SSN_E_UNSUPPORTED, "emu: build_cluster_plan"); }
+}
+
+namespace {
+ssn_ctx* g_ctx = nullptr;
+ssn::Csr g_out[4];                                  // results of the last call, fetched with emu_fetch
+std::vector<uint8_t> g_flags[2];
+std::string g_err;
+
+ssn_ctx* ctx() { if (!g_ctx) { g_ctx = new ssn_ctx(); emu::threaded = true; ssn::rng_reset(g_ctx, 5489u); } return g_ctx; }
+ssn::CsrView view(int64_t nr, int64_t nc, int64_t nnz, const int* ptr, const int* idx, const double* val) {
+    ssn::CsrView A; A.nrows = (int)nr; A.ncols = (int)nc; A.nnz = nnz; A.ptr = ptr; A.idx = idx; A.val = val; return A;
+}
+template <class F> int guarded(F f) {
+    try { emu::threaded = true; f(); return 0; }
+    catch (const ssn::Error& e) { g_err = e.msg; return e.code; }
+}
+}
+
+extern "C" {
+const char* emu_error() { return g_err.c_str(); }
+void emu_sizes(int k, int64_t* out) { out[0] = g_out[k].nrows; out[1] = g_out[k].ncols; out[2] = g_out[k].nnz; }
+void emu_fetch(int k, int* ptr, int* idx, double* val) {
+    std::memcpy(ptr, g_out[k].ptr.p, sizeof(int) * (size_t)(g_out[k].nrows + 1));
+    std::memcpy(idx, g_out[k].idx.p, sizeof(int) * (size_t)g_out[k].nnz);
+    std::memcpy(val, g_out[k].val.p, sizeof(double) * (size_t)g_out[k].nnz);
+}
+void emu_fetch_flags(int k, uint8_t* out) { std::memcpy(out, g_flags[k].data(), g_flags[k].size()); }
+int64_t emu_launches() { return ctx()->launches; }
+void emu_set_small_scan_max(int v) { ctx()->small_scan_max = v; }
+
+int emu_rng_reset() { return guarded([&] { ssn::rng_reset(ctx(), 5489u); }); }
+int64_t emu_rng_drawn() { return ctx()->rng_drawn; }
+int emu_rand(int64_t count, double* out) { return guarded([&] { ssn::rng_rand(ctx(), count, out); }); }
+
+int emu_spgemm(int64_t ar, int64_t ac, int64_t annz, const int* ap, const int* ai, const double* av,
+               int64_t br, int64_t bc, int64_t bnnz, const int* bp, const int* bi, const double* bv) {
+    return guarded([&] { g_out[0] = ssn::spgemm(ctx(), view(ar, ac, annz, ap, ai, av), view(br, bc, bnnz, bp, bi, bv)); });
+}
+int emu_transpose(int64_t ar, int64_t ac, int64_t annz, const int* ap, const int* ai, const double* av) {
+    return guarded([&] { g_out[0] = ssn::transpose(ctx(), view(ar, ac, annz, ap, ai, av)); });
+}
+int emu_sparse_add(int64_t ar, int64_t ac, int64_t annz, const int* ap, const int* ai, const double* av, double alpha,
+                   int64_t bnnz, const int* bp, const int* bi, const double* bv) {
+    return guarded([&] { g_out[0] = ssn::sparse_add(ctx(), view(ar, ac, annz, ap, ai, av), alpha, view(ar, ac, bnnz, bp, bi, bv)); });
+}
+int emu_strength(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, int which) {
+    return guarded([&] { g_out[0] = ssn::strength_matrix(ctx(), view(n, n, nnz, ap, ai, av), which == 1 ? 1 : 2); });
+}
+// [isC, isF, As] = mis_set(A, theta): flags 0 / 1 fetched with emu_fetch_flags, As = g_out[0]
+int emu_mis_set(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, double theta) {
+    return guarded([&] {
+        ssn::CsrView A = view(n, n, nnz, ap, ai, av);
+        ssn::Buf<uint8_t> isC(ctx(), (size_t)n), isF(ctx(), (size_t)n), flags;
+        ssn::mis_set(ctx(), A, theta, isC.p, isF.p, flags);
+        g_out[0] = ssn::flags_to_csr(ctx(), A, flags.p);
+        g_flags[0].assign(isC.p, isC.p + n); g_flags[1].assign(isF.p, isF.p + n);
+    });
+}
+// [Ac, Pro, As, indC] = transfer(A, amg_options) with global J = level_J: Ac = g_out[0], Pro = g_out[1], As = g_out[2]
+int emu_transfer(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, double theta, int bigph, int inter,
+                 int isnsp, int fnode, int level_J) {
+    return guarded([&] {
+        ssn::CsrView A = view(n, n, nnz, ap, ai, av);
+        ssn_amg_options o; std::memset(&o, 0, sizeof(o));
+        o.retol = -1; o.maxit = -1; o.smoth = -1; o.cycle = -1;
+        o.theta = theta; o.bigph = bigph; o.inter = inter; o.isnsp = isnsp; o.fnode = fnode;
+        ssn::AmgOptions ro = ssn::resolve_options(&o);
+        ssn::Csr ac, pro; ssn::Buf<uint8_t> isC, flags;
+        ssn::transfer(ctx(), A, ro, level_J, ac, pro, &isC, &flags);
+        g_out[2] = ssn::flags_to_csr(ctx(), A, flags.p);
+        g_flags[0].assign(isC.p, isC.p + n);
+        g_out[0] = std::move(ac); g_out[1] = std::move(pro);
+    });
+}
+}

@@ -22,7 +22,7 @@ extern "C" int emu_tri_factors(int n, int64_t nnz, const int* ptr, const int* id
         ssn_ctx ctx;
         ssn::CsrView H; H.nrows = n; H.ncols = n; H.nnz = nnz; H.ptr = ptr; H.idx = idx; H.val = val;
         ssn::TriFactors F;
-        emu::warp_mode = false;
+        emu::threaded = false;
         ssn::build_tri_factors_device(&ctx, H, precd, F);
         const size_t nl_ = (size_t)F.lp.p[n], nu_ = (size_t)F.up.p[n];
         sizes[0] = (int64_t)nl_; sizes[1] = (int64_t)nu_; sizes[2] = F.nl; sizes[3] = F.nu; sizes[4] = F.has_mid ? 1 : 0; sizes[5] = ctx.launches;
@@ -45,13 +45,13 @@ extern "C" int emu_jk_system(int64_t m, int64_t n, int64_t nnz, const int* ptr, 
         ssn_prob_data pd; std::memset(&pd, 0, sizeof(pd));
         pd.bk1 = bk1; pd.tk = tk; pd.m = m; pd.n = n; pd.t_dev = t; pd.H0 = &H0;
         ssn::Csr Jk;
-        emu::warp_mode = true;                               // jk_count_kernel / jk_fill_kernel vote inside the warp
+        emu::threaded = true;                                // jk_count_kernel / jk_fill_kernel vote inside the warp
         ssn::jk_system(&ctx, &pd, Jk);
-        emu::warp_mode = false;
+        emu::threaded = false;
         *onnz = Jk.nnz;
         std::memcpy(optr, Jk.ptr.p, sizeof(int) * (size_t)(m + n + 1));
         std::memcpy(oidx, Jk.idx.p, sizeof(int) * (size_t)Jk.nnz);
         std::memcpy(oval, Jk.val.p, sizeof(double) * (size_t)Jk.nnz);
         return 0;
-    } catch (const ssn::Error& e) { emu::warp_mode = false; return fail(e, err, errlen); }
+    } catch (const ssn::Error& e) { emu::threaded = false; return fail(e, err, errlen); }
 }

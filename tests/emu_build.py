@@ -1,0 +1,37 @@
+"""Builds a host emulation library: the real csrc/ sources copied next to tests/emu/common.cuh (the stand-in for the
+CUDA names) and compiled with g++.  Test infrastructure only."""
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+
+from conftest import ROOT
+
+CSRC = os.path.join(ROOT, "codes-of-ipd-ssn-amg-method_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+def build(tmpdir, harness, sources, so_name):
+    """Copies tests/emu/* and the named real sources into ``tmpdir``, compiles ``harness`` (+ every ``.cu`` in
+    ``sources`` that the harness does not #include itself is compiled as its own translation unit) and loads it."""
+    d = str(tmpdir)
+    shutil.copytree(EMU, d, dirs_exist_ok=True)
+    units = [harness]
+    for f in sources:
+        txt = open(os.path.join(CSRC, f)).read()
+        # the one mechanical edit: dynamic shared memory becomes a pointer to the emulator's buffer
+        txt = re.sub(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem;", txt)
+        open(os.path.join(d, f), "w").write(txt)
+    harness_txt = open(os.path.join(d, harness)).read()
+    for f in sources:
+        if f.endswith(".cu") and f'#include "{f}"' not in harness_txt:
+            units.append(f)
+    so = os.path.join(d, so_name)
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-I" + d,
+           "-I" + os.path.join(ROOT, "include")]
+    for u in units:
+        cmd += ["-x", "c++", u]
+    r = subprocess.run(cmd + ["-o", so], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-6000:]
+    return ctypes.CDLL(so)

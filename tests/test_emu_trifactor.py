@@ -5,8 +5,6 @@ kernels that vote).  This checks indexing, ordering and arithmetic of the source
 hardware can show; the GPU run of the same paths is tests/test_zz_device_setup.py."""
 import ctypes as C
 import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
@@ -14,22 +12,12 @@ import scipy.sparse as sp
 
 from conftest import ROOT
 
-CSRC = os.path.join(ROOT, "codes-of-ipd-ssn-amg-method_b200", "csrc")
-EMU = os.path.join(ROOT, "tests", "emu")
 
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    d = tmp_path_factory.mktemp("emu")
-    for f in os.listdir(EMU):
-        shutil.copy(os.path.join(EMU, f), d)
-    for f in ("trifactor.cu", "amg.cuh", "sparse.cuh"):                  # the real sources, next to the stand-in common.cuh
-        shutil.copy(os.path.join(CSRC, f), d)
-    so = str(d / "libemu_trifactor.so")
-    r = subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-x", "c++",
-                        "-I" + os.path.join(ROOT, "include"), "emu_trifactor.cpp", "-o", so], cwd=d, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    return C.CDLL(so)
+    import emu_build
+    return emu_build.build(tmp_path_factory.mktemp("emu"), "emu_trifactor.cpp", ["trifactor.cu", "amg.cuh", "sparse.cuh"], "libemu_trifactor.so")
 
 
 def _p(a):
