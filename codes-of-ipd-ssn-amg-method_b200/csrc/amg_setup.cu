@@ -577,9 +577,11 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     Buf<int> cflag(c, n), fflag(c, n), cidx(c, (size_t)n + 1), fidx(c, (size_t)n + 1), counts(c, 2);
     counts.zero();
     SSN_LAUNCH(c, cf_count_kernel, g, 256, 0, n, isC.p, isF.p, cflag.p, fflag.p, counts.p);
-    const int Nc = (int)scan_counts_to_ptr(c, cflag, cidx, n);
-    const int Nf = (int)scan_counts_to_ptr(c, fflag, fidx, n);
-    const int overlap = read_scalar(c, counts.p);
+    scan_counts_async(c, cflag, cidx, n);
+    scan_counts_async(c, fflag, fidx, n);
+    int h3[3];
+    read_ints(c, {cidx.p + n, fidx.p + n, counts.p}, h3);                // one synchronisation for the three
+    const int Nc = h3[0], Nf = h3[1], overlap = h3[2];
     SSN_REQUIRE(Nc + Nf == n && overlap == 0, SSN_E_CF_PARTITION,
                 "C/F split does not partition the nodes (AMG/transfer.m:46 would index out of range)");
     SSN_REQUIRE(Nf > 0 && Nc > 0, SSN_E_COARSEN_STALL, "coarsening stalled (no F or no C node)");
@@ -589,10 +591,15 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     notdiag.zero();
     SSN_LAUNCH(c, interp_parts_kernel<0>, gw, 256, 0, n, A.ptr, A.idx, A.val, flags.p, isC.p, isF.p, cidx.p, fidx.p, want_m,
                w1cnt.p, mcnt.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, notdiag.p);
-    if (bigraph) SSN_REQUIRE(read_scalar(c, notdiag.p) == 0, SSN_E_NOT_BIGRAPH, "A(1:Nf,1:Nf) is not diagonal");
-    Csr W1 = csr_alloc_from_counts(c, Nf, Nc, w1cnt);
-    Csr M;
-    if (want_m) M = csr_alloc_from_counts(c, Nf, Nf, mcnt);
+    // row pointers of W1 and M, then their sizes and the bigraph check with one synchronisation
+    Csr W1, M;
+    W1.c = c; W1.nrows = Nf; W1.ncols = Nc; W1.ptr.alloc(c, (size_t)Nf + 1);
+    scan_counts_async(c, w1cnt, W1.ptr, Nf);
+    if (want_m) { M.c = c; M.nrows = Nf; M.ncols = Nf; M.ptr.alloc(c, (size_t)Nf + 1); scan_counts_async(c, mcnt, M.ptr, Nf); }
+    read_ints(c, {W1.ptr.p + Nf, want_m ? M.ptr.p + Nf : W1.ptr.p + Nf, notdiag.p}, h3);
+    if (bigraph) SSN_REQUIRE(h3[2] == 0, SSN_E_NOT_BIGRAPH, "A(1:Nf,1:Nf) is not diagonal");
+    W1.nnz = h3[0]; W1.idx.alloc(c, W1.nnz); W1.val.alloc(c, W1.nnz);
+    if (want_m) { M.nnz = h3[1]; M.idx.alloc(c, M.nnz); M.val.alloc(c, M.nnz); }
     SSN_LAUNCH(c, interp_parts_kernel<1>, gw, 256, 0, n, A.ptr, A.idx, A.val, flags.p, isC.p, isF.p, cidx.p, fidx.p, want_m,
                nullptr, nullptr, W1.ptr.p, W1.idx.p, W1.val.p, want_m ? M.ptr.p : nullptr, want_m ? M.idx.p : nullptr,
                want_m ? M.val.p : nullptr, nullptr);
@@ -611,7 +618,7 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
     // Pro
     Buf<int> pcnt(c, n);
     SSN_LAUNCH(c, pro_count_kernel, g, 256, 0, n, isF.p, fidx.p, W.ptr.p, pcnt.p);
-    Pro = csr_alloc_from_counts(c, n, Nc, pcnt);
+    Pro = csr_alloc_known(c, n, Nc, pcnt, W.nnz + Nc);                   // every F row is its W row, every C row one entry
     SSN_LAUNCH(c, pro_fill_kernel, gw, 256, 0, n, isF.p, fidx.p, cidx.p, W.ptr.p, W.idx.p, W.val.p, Pro.ptr.p, Pro.idx.p, Pro.val.p);
     // Ac = (Pro'*A)*Pro                                                  // transfer.m:66
     Csr Pt, T1;
@@ -638,7 +645,8 @@ void amg_clear(ssn_ctx* c) {
 static constexpr int kSmallN = 2048;
 static constexpr int64_t kSmallNnz = 1 << 17;
 
-static void finish_level(ssn_ctx* c, Level& L, bool bigph_level, int Nf) {
+// xx_dev: where ones'*A*ones of this level is left on the device (amg_setup reads all levels' sums at once)
+static void finish_level(ssn_ctx* c, Level& L, bool bigph_level, int Nf, double* xx_dev) {
     Phase ph(c, "setup.finish_level");
     const int n = L.N = (int)L.A.nrows;
     L.bigph = bigph_level ? 1 : 0; L.Nf = bigph_level ? Nf : 0;
@@ -648,7 +656,7 @@ static void finish_level(ssn_ctx* c, Level& L, bool bigph_level, int Nf) {
     if (n) SSN_LAUNCH(c, dinv_kernel, cdiv(n, 256), 256, 0, n, diag.p, bigph_level ? 0.0 : 1.0, L.dinv.p);
     L.Axi.alloc(c, n);
     if (n) SSN_LAUNCH(c, rowsum_kernel, cdiv((int64_t)n * 32, 256), 256, 0, n, L.A.ptr.p, L.A.val.p, L.Axi.p);
-    L.xx = dev_sum(c, L.Axi, n);
+    dev_sum_async(c, L.Axi, n, xx_dev);
     L.r.alloc(c, n); L.e.alloc(c, n); L.g.alloc(c, n);
 }
 
@@ -661,7 +669,8 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
     H->smoth = o.smoth;
     H->lv.emplace_back();
     H->lv[0].A = csr_copy(c, A);
-    finish_level(c, H->lv[0], o.bigph != 0, o.fnode);
+    Buf<double> xxd(c, 64);                                             // J < 64 (checked in the loop)
+    finish_level(c, H->lv[0], o.bigph != 0, o.fnode, xxd.p);
     const int thr = coarsest_threshold(A.nrows);
     int J = 1;
     // Class_AMG.m:76 coarsens down to the threshold; twogrid_bigph.m:41-47 (max_levels = 2) coarsens exactly once
@@ -672,11 +681,16 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
         transfer(c, H->lv[J - 1].A, o, J, nl.A, nl.P, &isC, nullptr, &nl.Pt);
         SSN_REQUIRE(nl.A.nrows < H->lv[J - 1].N, SSN_E_COARSEN_STALL, "coarsening stalled (no F nodes)");
         H->lv[J - 1].isC = std::move(isC);
-        finish_level(c, nl, false, 0);
+        finish_level(c, nl, false, 0, xxd.p + J);
         H->lv.push_back(std::move(nl));
         ++J;
     }
     H->J = J;
+    {   // ones'*A_k*ones of every level: one host read for the hierarchy
+        double hxx[64];
+        read_back(c, xxd.p, hxx, (size_t)J);
+        for (int k = 0; k < J; ++k) H->lv[k].xx = hxx[k];
+    }
     // tail of small levels handled by the single-block cycle kernel
     int sf = J - 1;
     while (sf > 0 && H->lv[sf - 1].N <= kSmallN && H->lv[sf - 1].A.nnz <= kSmallNnz) --sf;

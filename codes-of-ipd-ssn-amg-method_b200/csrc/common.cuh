@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <initializer_list>
 #include <string>
 #include <vector>
 #include <memory>
@@ -195,11 +196,22 @@ inline void read_back(ssn_ctx* c, const T* dev, T* host, size_t count) {
 }
 template <class T>
 inline T read_scalar(ssn_ctx* c, const T* dev) { T v; read_back(c, dev, &v, 1); return v; }
+// several device ints with ONE stream synchronisation (the copies queue up behind the kernels that produce them)
+inline void read_ints(ssn_ctx* c, std::initializer_list<const int*> src, int* out) {
+    int* pin = reinterpret_cast<int*>(c->h_pin);
+    size_t k = 0;
+    for (const int* s : src) SSN_CUDA(cudaMemcpyAsync(pin + k++, s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SSN_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < k; ++i) out[i] = pin[i];
+}
 
 // ---- scans / sorts (CUB plumbing, sparse.cu) ----
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n);   // out[n] = total if out has n+1: see impl
 // out has n+1 entries: out[0]=0, out[i+1]=sum_{k<=i} in[k]; returns total (host, synchronises)
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
+// the same scan without the host read of the total (ptr[n] holds it on the device): for callers that know the
+// total already, or that read several totals with one synchronisation (read_ints)
+void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
 // stable sort of (key,value) int pairs by key, keys < key_limit
 void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int* vals_in,
                        int* vals_out, int64_t n, int key_limit);

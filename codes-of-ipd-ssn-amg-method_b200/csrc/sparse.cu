@@ -42,18 +42,20 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* ou
 }
 }  // namespace
 
-int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
-    if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return 0; }
-    if (n <= c->small_scan_max) {
-        SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1);
-        return (int64_t)read_scalar(c, ptr + n);
-    }
+void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
+    if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return; }
+    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1); return; }
     SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream));
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
     Buf<unsigned char> tmp(c, tmp_bytes);
     SSN_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
     c->launches++;
+}
+
+int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
+    scan_counts_async(c, counts, ptr, n);
+    if (n == 0) return 0;
     return (int64_t)read_scalar(c, ptr + n);
 }
 
@@ -138,6 +140,13 @@ double dev_sum(ssn_ctx* c, const double* x, int64_t n) {
     SSN_LAUNCH(c, reduce_stage1<0>, g, 256, 0, x, nullptr, n, part.p);
     SSN_LAUNCH(c, reduce_stage2, 1, 256, 0, part.p, g, part.p + kRedBlocks);
     return read_scalar(c, part.p + kRedBlocks);
+}
+void dev_sum_async(ssn_ctx* c, const double* x, int64_t n, double* out_dev) {
+    if (n <= 0) { SSN_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), c->stream)); return; }
+    Buf<double> part(c, kRedBlocks + 1);
+    const int g = grid_for(n, 256, kRedBlocks);
+    SSN_LAUNCH(c, reduce_stage1<0>, g, 256, 0, x, nullptr, n, part.p);
+    SSN_LAUNCH(c, reduce_stage2, 1, 256, 0, part.p, g, out_dev);
 }
 double dev_dot(ssn_ctx* c, const double* x, const double* y, int64_t n) {
     if (n <= 0) return 0.0;
@@ -320,6 +329,15 @@ Csr csr_alloc_from_counts(ssn_ctx* c, int nrows, int ncols, const int* counts) {
     return C;
 }
 
+Csr csr_alloc_known(ssn_ctx* c, int nrows, int ncols, const int* counts, int64_t nnz) {
+    Csr C; C.c = c; C.nrows = nrows; C.ncols = ncols;
+    C.ptr.alloc(c, (size_t)nrows + 1);
+    scan_counts_async(c, counts, C.ptr, nrows);
+    C.nnz = nnz;
+    C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
+    return C;
+}
+
 Csr csr_copy(ssn_ctx* c, const CsrView& A) {
     Csr C; C.c = c; C.nrows = A.nrows; C.ncols = A.ncols; C.nnz = A.nnz;
     C.ptr.alloc(c, (size_t)A.nrows + 1); C.idx.alloc(c, A.nnz); C.val.alloc(c, A.nnz);
@@ -344,7 +362,7 @@ Csr transpose(ssn_ctx* c, const CsrView& A) {
     Buf<int> counts(c, (size_t)A.ncols); counts.zero();
     T.ptr.alloc(c, (size_t)A.ncols + 1);
     if (A.nnz > 0) SSN_LAUNCH(c, hist_kernel, grid_for(A.nnz), 256, 0, A.idx, A.nnz, counts.p);
-    scan_counts_to_ptr(c, counts, T.ptr, A.ncols);
+    scan_counts_async(c, counts, T.ptr, A.ncols);                    // the total is A.nnz: no host read
     T.idx.alloc(c, A.nnz); T.val.alloc(c, A.nnz);
     if (A.nnz == 0) return T;
     Buf<int> rowidx(c, A.nnz), ent(c, A.nnz), keys_out(c, A.nnz), perm(c, A.nnz);
@@ -712,8 +730,11 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
         int grid = cdiv(nrows, 4); if (grid > c->num_sms * 16) grid = c->num_sms * 16;
         SSN_LAUNCH(c, spgemm_small_kernel, grid, 128, 0, nrows, A.ptr, A.idx, A.val, B.ptr, B.idx, B.val, 1, nullptr, tidx.p, tval.p,
                    cnt.p, nbig.p);
-        const int64_t nnz = scan_counts_to_ptr(c, cnt, cptr, nrows);
-        if (read_scalar(c, nbig.p) == 0) {
+        scan_counts_async(c, cnt, cptr, nrows);
+        int h2[2];
+        read_ints(c, {cptr.p + nrows, nbig.p}, h2);                       // the product's size and the fallback flag: one synchronisation
+        const int64_t nnz = h2[0];
+        if (h2[1] == 0) {
             C.nnz = nnz;
             C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);
             if (C.nnz) SSN_LAUNCH(c, compact_items_kernel, cdiv((int64_t)nrows * 32, 256), 256, 0, (int64_t)nrows, nullptr, cptr.p, tidx.p,

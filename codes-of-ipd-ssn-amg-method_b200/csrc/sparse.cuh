@@ -29,6 +29,8 @@ void expand_rows(ssn_ctx* c, const CsrView& A, int* rowidx);
 Csr csr_copy(ssn_ctx* c, const CsrView& A);
 // allocate a CSR from per-row counts (fills ptr, allocates idx/val)
 Csr csr_alloc_from_counts(ssn_ctx* c, int nrows, int ncols, const int* counts);
+// the same when the caller knows the total already (no host read)
+Csr csr_alloc_known(ssn_ctx* c, int nrows, int ncols, const int* counts, int64_t nnz);
 
 // generic device helpers
 void fill_double(ssn_ctx* c, double* p, int64_t n, double v);
@@ -36,6 +38,8 @@ void fill_int(ssn_ctx* c, int* p, int64_t n, int v);
 void iota_int(ssn_ctx* c, int* p, int64_t n);
 // deterministic sum / dot / norm (two-stage, fixed order); result on host (synchronises)
 double dev_sum(ssn_ctx* c, const double* x, int64_t n);
+// the same sum (same order, same value) left in *out_dev: no host read
+void dev_sum_async(ssn_ctx* c, const double* x, int64_t n, double* out_dev);
 double dev_dot(ssn_ctx* c, const double* x, const double* y, int64_t n);
 int64_t dev_count_nonzero_u8(ssn_ctx* c, const uint8_t* x, int64_t n);
 

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -64,6 +65,7 @@ inline bool threaded = false;                     // set by the harness: one hos
 inline thread_local WarpShared* warp = nullptr;
 inline thread_local BlockShared* block = nullptr;
 alignas(64) inline unsigned char dyn_smem[256 * 1024];
+inline long host_reads = 0;                       // device->host reads (each one a stream synchronisation on the GPU)
 inline void need_threads(const char* what) {
     if (!warp) { std::fprintf(stderr, "emu: %s needs emu::threaded = true\n", what); std::abort(); }
 }
@@ -222,7 +224,13 @@ struct CsrView {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-struct Phase { Phase(ssn_ctx*, const char*) {} };
+// the library's phase profiler, counting instead of timing: launches and device->host reads per named phase
+inline std::map<std::string, std::pair<long, long>> phase_counts;
+struct Phase {
+    ssn_ctx* c; const char* name; long l0, r0;
+    Phase(ssn_ctx* ctx, const char* n) : c(ctx), name(n), l0((long)ctx->launches), r0(emu::host_reads) {}
+    ~Phase() { auto& a = phase_counts[name]; a.first += (long)c->launches - l0; a.second += emu::host_reads - r0; }
+};
 struct KernelTimer { explicit KernelTimer(ssn_ctx*) {} };
 
 template <class K, class... A>
@@ -255,14 +263,16 @@ inline void emu_launch(ssn_ctx* c, K kernel, int grid, int block, A... args) {
 #define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, (int)(grid), (int)(block), __VA_ARGS__)
 
 template <class T>
-inline void read_back(ssn_ctx*, const T* dev, T* host, size_t count) { std::memcpy(host, dev, count * sizeof(T)); }
+inline void read_back(ssn_ctx*, const T* dev, T* host, size_t count) { ++emu::host_reads; std::memcpy(host, dev, count * sizeof(T)); }
 template <class T>
-inline T read_scalar(ssn_ctx*, const T* dev) { return *dev; }
+inline T read_scalar(ssn_ctx*, const T* dev) { ++emu::host_reads; return *dev; }
+inline void read_ints(ssn_ctx*, std::initializer_list<const int*> src, int* out) { ++emu::host_reads; size_t k = 0; for (const int* s : src) out[k++] = *s; }
 
 // scans / sorts: declared here like in the real common.cuh.  Defined by the emulated sparse.cu when a harness compiles
 // it (over tests/emu/cub), else by tests/emu/sparse_host.h.
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n);
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
+void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
 void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int* vals_in, int* vals_out, int64_t n, int key_limit);
 
 inline double warp_sum(double v) {

@@ -34,7 +34,33 @@ void emu_fetch(int k, int* ptr, int* idx, double* val) {
 }
 void emu_fetch_flags(int k, uint8_t* out) { std::memcpy(out, g_flags[k].data(), g_flags[k].size()); }
 int64_t emu_launches() { return ctx()->launches; }
+int64_t emu_host_reads() { return emu::host_reads; }
+// "phase launches host_reads" lines of everything run so far (static buffer)
+const char* emu_phase_counts() {
+    static std::string out; out.clear();
+    for (auto& kv : ssn::phase_counts) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+    return out.c_str();
+}
+void emu_phase_reset() { ssn::phase_counts.clear(); }
 void emu_set_small_scan_max(int v) { ctx()->small_scan_max = v; }
+
+// Class_AMG's setup phase (AMG/Class_AMG.m:41-85): returns the number of levels; level k's matrix, prolongation and
+// ones'*A_k*ones are fetched with emu_level
+int emu_amg_setup(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, double theta, int smoth, int isnsp, int fnode, int* levels) {
+    return guarded([&] {
+        ssn_amg_options o; std::memset(&o, 0, sizeof(o));
+        o.retol = 1e-11; o.maxit = 30; o.smoth = smoth; o.cycle = 'w'; o.theta = theta; o.bigph = 1; o.inter = 1; o.isnsp = isnsp; o.fnode = fnode;
+        ssn::amg_setup(ctx(), view(n, n, nnz, ap, ai, av), ssn::resolve_options(&o));
+        *levels = ctx()->hier->J;
+    });
+}
+// which = 0: A_k -> g_out[0]; 1: Pro_k -> g_out[0] (k >= 1); returns xx of the level
+double emu_level(int k, int which) {
+    ssn::Level& L = ctx()->hier->lv[(size_t)k];
+    g_out[0] = ssn::csr_copy(ctx(), which == 0 ? ssn::CsrView(L.A) : ssn::CsrView(L.P));
+    return L.xx;
+}
+void emu_amg_clear() { ssn::amg_clear(ctx()); }
 
 int emu_rng_reset() { return guarded([&] { ssn::rng_reset(ctx(), 5489u); }); }
 int64_t emu_rng_drawn() { return ctx()->rng_drawn; }

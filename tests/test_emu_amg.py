@@ -168,6 +168,35 @@ def test_strength_mis_set_and_transfer_bit_exact(emu, oracle, m, n, density, wei
         assert_same_matrix(A3, A3_ref, f"Ac level 3 isnsp={isnsp}")
 
 
+def test_hierarchy_bit_exact(emu, oracle):
+    """amg_setup (Class_AMG.m:41-85) on the emulated sources: level sizes, every A_k and Pro_k bit for bit, the random
+    draws consumed, and ones'*A_k*ones of every level (read back once for the whole hierarchy)."""
+    from oracle.amg import setup_hierarchy, amg_state
+    m, n = 60, 50
+    Ae = ssn_matrix(oracle, m, n, 0.06, seed=3 * m)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    o = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": 1, "inter": 1, "guess": None, "fnode": n}
+    oracle.rng_reset(); _check(emu, emu.emu_rng_reset())
+    st = setup_hierarchy(Ae, o)
+    ref = [(A.copy(), P) for A, P in zip(st.Ack, st.Prok)]
+    A1, a1 = _csr_args(Ae)
+    J = C.c_int(0)
+    _check(emu, emu.emu_amg_setup(C.c_int64(m + n), C.c_int64(A1.nnz), _p(a1[0]), _p(a1[1]), _p(a1[2]), C.c_double(0.25), C.c_int(5), C.c_int(1),
+                                  C.c_int(n), C.byref(J)))
+    assert J.value == len(ref) and J.value >= 3
+    emu.emu_level.restype = C.c_double
+    for k, (A, P) in enumerate(ref):
+        xx = emu.emu_level(C.c_int(k), C.c_int(0))
+        assert_same_matrix(_fetch(emu), A, f"A level {k + 1}")
+        assert abs(xx - A.sum()) <= 1e-12 * abs(A).sum(), f"ones'*A*ones level {k + 1}"
+        if k > 0:
+            emu.emu_level(C.c_int(k), C.c_int(1))
+            assert_same_matrix(_fetch(emu), P, f"Pro level {k + 1}")
+    assert emu.emu_rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    amg_state.clear(); emu.emu_amg_clear()
+
+
 def test_scan_paths_agree(emu, oracle):
     """scan_counts_to_ptr through the one-block kernel and through cub::DeviceScan (what arrays above
     ssn_ctx::small_scan_max take): the same product either way."""
