@@ -85,7 +85,7 @@ void build_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Active
     Buf<int> rowcount;
     a.E = plan_active_set(c, s, m, n, a.colptr, a.yrow, a.ycol, rowcount);
     a.rowptr.alloc(c, m + 1);
-    scan_counts_to_ptr(c, rowcount, a.rowptr, m);
+    scan_counts_async(c, rowcount, a.rowptr, m);                     // the total is a.E: no host read
     a.ycolT.alloc(c, a.E);
     if (a.E > 0) {
         Buf<int> keys_out(c, a.E);
@@ -144,8 +144,8 @@ Csr asat_coo(ssn_ctx* c, const long long* lin_sorted, int64_t E, const double* p
     colcount.zero(); rowcount.zero();
     a.yrow.alloc(c, E); a.ycol.alloc(c, E); a.colptr.alloc(c, n + 1); a.rowptr.alloc(c, m + 1); a.ycolT.alloc(c, E);
     if (E) SSN_LAUNCH(c, coo_from_lin_kernel, 592, 256, 0, E, lin_sorted, m, a.yrow.p, a.ycol.p, colcount.p, rowcount.p);
-    scan_counts_to_ptr(c, colcount, a.colptr, n);
-    scan_counts_to_ptr(c, rowcount, a.rowptr, m);
+    scan_counts_async(c, colcount, a.colptr, n);                     // both totals are E: no host reads
+    scan_counts_async(c, rowcount, a.rowptr, m);
     if (E) {
         Buf<int> keys_out(c, E);
         stable_sort_pairs(c, a.yrow, keys_out, a.ycol, a.ycolT, E, (int)(m > 1 ? m : 2));
@@ -318,7 +318,7 @@ void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm
     SSN_LAUNCH(c, cc_label_kernel, g, 256, 0, n, comp.p, rootrank.p, blocks0.p, blocks, sizes);
     iota_int(c, ids, n);
     stable_sort_pairs(c, blocks0, keys_out, ids, perm, n, ncomp > 1 ? ncomp : 2);
-    scan_counts_to_ptr(c, sizes, r, ncomp);
+    scan_counts_async(c, sizes, r, ncomp);                           // the total is n: no host read
     if (ncomp_out) *ncomp_out = ncomp;
 }
 
