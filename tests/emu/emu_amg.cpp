@@ -1,6 +1,7 @@
 // tests/emu/emu_amg.cpp -- runs the REAL csrc/sparse.cu and csrc/amg_setup.cu on the host through tests/emu/common.cuh
 // (the test copies them, with amg.cuh / sparse.cuh, next to this file; cub is tests/emu/cub).  Test infrastructure only.
 #include "common.cuh"
+#include "emu_probe.h"
 #include "amg.cuh"
 
 namespace ssn {

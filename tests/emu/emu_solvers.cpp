@@ -3,6 +3,7 @@
 // translation units that are not emulated is stubbed: the iterative solvers (cooperative kernels, amg_solve.cu) throw,
 // the active-set compaction of plan_ops.cu is restated on the host with the same contract.  Test infrastructure only.
 #include "common.cuh"
+#include "emu_probe.h"
 #include "amg.cuh"
 #include "solvers.cuh"
 #include "plan_ops.cuh"

@@ -1,6 +1,7 @@
 // tests/emu/emu_trifactor.cpp -- runs the REAL csrc/trifactor.cu on the host through tests/emu/common.cuh
 // (the test copies trifactor.cu, amg.cuh and sparse.cuh next to this file before compiling).  Test infrastructure only.
 #include "common.cuh"
+#include "emu_probe.h"
 #include "amg.cuh"
 #include "sparse_host.h"
 #include "trifactor.cu"
