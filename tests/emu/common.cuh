@@ -40,6 +40,17 @@
 #define __grid_constant__
 #define __shared__ static            /* blocks run one at a time, so one static instance is the block's shared memory */
 
+#define __align__(n) alignas(n)
+
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct uchar2 { unsigned char x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline uchar2 make_uchar2(unsigned char x, unsigned char y) { return uchar2{x, y}; }
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
@@ -58,7 +69,7 @@ struct WarpShared {
     explicit WarpShared(int lanes) : bar(lanes) {}
 };
 struct BlockShared {
-    std::barrier<> bar;
+    std::barrier<> bar; int vote = 0;
     explicit BlockShared(int threads) : bar(threads) {}
 };
 inline bool threaded = false;                     // set by the harness: one host thread per CUDA thread, block by block
@@ -91,6 +102,11 @@ inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline void __stcs(T* p, T v) { *p = v; }
+inline int __double2hiint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b >> 32); }
+inline int __double2loint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b & 0xffffffffll); }
+inline double __hiloint2double(int hi, int lo) { const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &b, 8); return d; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
 
@@ -114,6 +130,17 @@ inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- block barrier, warp votes and shuffles (emu::threaded only)
 inline void __syncthreads() { emu::need_threads("__syncthreads"); emu::block->bar.arrive_and_wait(); }
+inline int __syncthreads_or(int pred) {
+    emu::need_threads("__syncthreads_or");
+    emu::BlockShared* b = emu::block;
+    if (pred) __atomic_store_n(&b->vote, 1, __ATOMIC_SEQ_CST);
+    b->bar.arrive_and_wait();
+    const int r = __atomic_load_n(&b->vote, __ATOMIC_SEQ_CST);
+    b->bar.arrive_and_wait();
+    if (threadIdx.x == 0) __atomic_store_n(&b->vote, 0, __ATOMIC_SEQ_CST);
+    b->bar.arrive_and_wait();
+    return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::need_threads("__syncwarp"); emu::warp->bar.arrive_and_wait(); emu::warp->bar.arrive_and_wait(); }
 template <class T> inline T emu_exchange(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
@@ -176,8 +203,10 @@ struct ssn_ctx {
     bool device_setup = true;
     int dense_max_n = 2048;
     bool ktimer = false, prof = false;
-    ssn_ctx() { mt_state = (uint32_t*)std::calloc(625, sizeof(uint32_t)); }
-    ~ssn_ctx() { std::free(mt_state); }
+    double* h_pin = nullptr;
+    static constexpr int kPinDoubles = 4096;
+    ssn_ctx() { mt_state = (uint32_t*)std::calloc(625, sizeof(uint32_t)); h_pin = (double*)std::calloc(kPinDoubles, sizeof(double)); }
+    ~ssn_ctx() { std::free(mt_state); std::free(h_pin); }
     ssn_ctx(const ssn_ctx&) = delete; ssn_ctx& operator=(const ssn_ctx&) = delete;
 };
 
@@ -234,14 +263,15 @@ struct Phase {
 struct KernelTimer { explicit KernelTimer(ssn_ctx*) {} };
 
 template <class K, class... A>
-inline void emu_launch(ssn_ctx* c, K kernel, int grid, int block, A... args) {
+inline void emu_launch(ssn_ctx* c, K kernel, dim3 grid, int block, A... args) {
     c->launches++;
-    for (int b = 0; b < grid; ++b) {
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned b = 0; b < grid.x; ++b) {
+        auto set_ids = [&](int t) {
+            blockIdx.x = (int)b; blockIdx.y = (int)by; threadIdx.x = t; blockDim.x = block; gridDim.x = (int)grid.x; gridDim.y = (int)grid.y;
+        };
         if (!emu::threaded) {
-            for (int t = 0; t < block; ++t) {
-                blockIdx.x = b; threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
-                kernel(args...);
-            }
+            for (int t = 0; t < block; ++t) { set_ids(t); kernel(args...); }
         } else {
             emu::BlockShared bs(block);
             std::vector<std::unique_ptr<emu::WarpShared>> ws;
@@ -251,7 +281,7 @@ inline void emu_launch(ssn_ctx* c, K kernel, int grid, int block, A... args) {
             for (int t = 0; t < block; ++t)
                 threads.emplace_back([&, t] {
                     emu::block = &bs; emu::warp = ws[(size_t)t / 32].get();
-                    blockIdx.x = b; threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
+                    set_ids(t);
                     kernel(args...);
                     emu::warp->bar.arrive_and_drop();       // a thread that has returned no longer takes part in barriers
                     bs.bar.arrive_and_drop();
@@ -260,7 +290,7 @@ inline void emu_launch(ssn_ctx* c, K kernel, int grid, int block, A... args) {
         }
     }
 }
-#define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, (int)(grid), (int)(block), __VA_ARGS__)
+#define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, dim3(grid), (int)(block), __VA_ARGS__)
 
 template <class T>
 inline void read_back(ssn_ctx*, const T* dev, T* host, size_t count) { ++emu::host_reads; std::memcpy(host, dev, count * sizeof(T)); }

@@ -21,7 +21,7 @@ def build(tmpdir, harness, sources, so_name):
     for f in sources:
         txt = open(os.path.join(CSRC, f)).read()
         # the one mechanical edit: dynamic shared memory becomes a pointer to the emulator's buffer
-        txt = re.sub(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem;", txt)
+        txt = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];", r"\1* \2 = (\1*)emu::dyn_smem;", txt)
         open(os.path.join(d, f), "w").write(txt)
     harness_txt = open(os.path.join(d, harness)).read()
     for f in sources:
