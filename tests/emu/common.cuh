@@ -299,7 +299,7 @@ inline T read_scalar(ssn_ctx*, const T* dev) { ++emu::host_reads; return *dev; }
 inline void read_ints(ssn_ctx*, std::initializer_list<const int*> src, int* out) { ++emu::host_reads; size_t k = 0; for (const int* s : src) out[k++] = *s; }
 
 // scans / sorts: declared here like in the real common.cuh.  Defined by the emulated sparse.cu when a harness compiles
-// it (over tests/emu/cub), else by tests/emu/sparse_host.h.
+// it (over tests/emu/cub).
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n);
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n);
 void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n);

@@ -1,10 +1,9 @@
 // tests/emu/emu_trifactor.cpp -- runs the REAL csrc/trifactor.cu on the host through tests/emu/common.cuh
-// (the test copies trifactor.cu, amg.cuh and sparse.cuh next to this file before compiling).  Test infrastructure only.
+// (the test copies trifactor.cu, sparse.cu, amg.cuh and sparse.cuh next to this file before compiling).  Test infrastructure only.
 #include "common.cuh"
 #include "emu_probe.h"
 #include "amg.cuh"
-#include "sparse_host.h"
-#include "trifactor.cu"
+#include "trifactor.cu"          // scans, sorts, transpose: the real sparse.cu, compiled as its own translation unit
 
 namespace {
 int fail(const ssn::Error& e, char* err, int errlen) {
@@ -23,7 +22,7 @@ extern "C" int emu_tri_factors(int n, int64_t nnz, const int* ptr, const int* id
         ssn_ctx ctx;
         ssn::CsrView H; H.nrows = n; H.ncols = n; H.nnz = nnz; H.ptr = ptr; H.idx = idx; H.val = val;
         ssn::TriFactors F;
-        emu::threaded = false;
+        emu::threaded = true;                                // the scans of sparse.cu use __syncthreads and shuffles
         ssn::build_tri_factors_device(&ctx, H, precd, F);
         const size_t nl_ = (size_t)F.lp.p[n], nu_ = (size_t)F.up.p[n];
         sizes[0] = (int64_t)nl_; sizes[1] = (int64_t)nu_; sizes[2] = F.nl; sizes[3] = F.nu; sizes[4] = F.has_mid ? 1 : 0; sizes[5] = ctx.launches;
@@ -48,11 +47,10 @@ extern "C" int emu_jk_system(int64_t m, int64_t n, int64_t nnz, const int* ptr, 
         ssn::Csr Jk;
         emu::threaded = true;                                // jk_count_kernel / jk_fill_kernel vote inside the warp
         ssn::jk_system(&ctx, &pd, Jk);
-        emu::threaded = false;
         *onnz = Jk.nnz;
         std::memcpy(optr, Jk.ptr.p, sizeof(int) * (size_t)(m + n + 1));
         std::memcpy(oidx, Jk.idx.p, sizeof(int) * (size_t)Jk.nnz);
         std::memcpy(oval, Jk.val.p, sizeof(double) * (size_t)Jk.nnz);
         return 0;
-    } catch (const ssn::Error& e) { emu::threaded = false; return fail(e, err, errlen); }
+    } catch (const ssn::Error& e) { return fail(e, err, errlen); }
 }

@@ -17,7 +17,7 @@ from conftest import ROOT
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     import emu_build
-    return emu_build.build(tmp_path_factory.mktemp("emu"), "emu_trifactor.cpp", ["trifactor.cu", "amg.cuh", "sparse.cuh"], "libemu_trifactor.so")
+    return emu_build.build(tmp_path_factory.mktemp("emu"), "emu_trifactor.cpp", ["trifactor.cu", "sparse.cu", "amg.cuh", "sparse.cuh"], "libemu_trifactor.so")
 
 
 def _p(a):
