@@ -2,11 +2,16 @@
 CUDA names) and compiled with g++.  Test infrastructure only."""
 import ctypes
 import os
+
+import pytest
 import re
 import shutil
 import subprocess
 
 from conftest import ROOT
+
+FULL = os.environ.get("SSN_EMU_FULL") == "1"          # the larger cases cost minutes of host-thread emulation: on request
+slow = pytest.mark.skipif(not FULL, reason="set SSN_EMU_FULL=1 (minutes of host-thread emulation)")
 
 CSRC = os.path.join(ROOT, "codes-of-ipd-ssn-amg-method_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
@@ -28,7 +33,7 @@ def build(tmpdir, harness, sources, so_name):
         if f.endswith(".cu") and f'#include "{f}"' not in harness_txt:
             units.append(f)
     so = os.path.join(d, so_name)
-    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-I" + d,
+    cmd = ["g++", "-std=c++20", "-O0", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-I" + d,
            "-I" + os.path.join(ROOT, "include")]
     for u in units:
         cmd += ["-x", "c++", u]
@@ -36,6 +41,5 @@ def build(tmpdir, harness, sources, so_name):
     assert r.returncode == 0, r.stderr[-6000:]
     lib = ctypes.CDLL(so)
     if not lib.emu_probe_threads(ctypes.c_int(1024)):                # one host thread per CUDA thread of a block
-        import pytest
         pytest.skip("this machine cannot create 1024 host threads (ulimit -u?): the kernel emulation needs them")
     return lib

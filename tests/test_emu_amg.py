@@ -122,7 +122,7 @@ def test_transpose_and_sparse_add(emu):
     assert_same_matrix(_fetch(emu), R, "A + 0.5*B")
 
 
-@pytest.mark.parametrize("m,n,density,weights", [(40, 30, 0.1, False), (70, 60, 0.05, True)])
+@pytest.mark.parametrize("m,n,density,weights", [(40, 30, 0.1, False), pytest.param(70, 60, 0.05, True, marks=__import__("emu_build").slow)])
 def test_strength_mis_set_and_transfer_bit_exact(emu, oracle, m, n, density, weights):
     """The sequence of tests/test_gpu_amg.py::test_mis_set_and_transfer_bit_exact on the emulated sources: level 1 (bigraph
     branch, transfer.m:19-29), strength of both levels, level 2 through mis_set (same random stream) and the standard

@@ -4,14 +4,12 @@ updates and the fused A-ADMM warm start -- compiled with g++ against tests/emu/c
 as tests/test_gpu_plan.py / tests/test_gpu_driver.py do on the device.  Small plans only (every CUDA thread is a host
 thread); shapes chosen to reach the vectorised (m % 16 == 0) and the ragged code paths."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
 
 RTOL = 1e-10
-_FULL = os.environ.get("SSN_EMU_FULL") == "1"        # the adaptive (screened) loop costs minutes of host threads: on request
-_slow = pytest.mark.skipif(not _FULL, reason="set SSN_EMU_FULL=1 (minutes of host-thread emulation)")
+from emu_build import slow as _slow                      # SSN_EMU_FULL=1: the cases that cost minutes of host threads
 SHAPES = [(1, 1), (7, 5), (64, 48), (45, 130)]
 
 

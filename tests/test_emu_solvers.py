@@ -30,7 +30,8 @@ def asat(lib, s, p, q):
     return _fetch(lib)
 
 
-@pytest.mark.parametrize("m,n,density,unit", [(40, 24, 0.1, True), (33, 47, 0.05, False), (64, 16, 0.3, False)])
+@pytest.mark.parametrize("m,n,density,unit", [pytest.param(40, 24, 0.1, True, marks=__import__("emu_build").slow), (33, 47, 0.05, False),
+                                                pytest.param(64, 16, 0.3, False, marks=__import__("emu_build").slow)])
 def test_asat_pattern_and_values_exact(emu, oracle, m, n, density, unit):
     s, p, q = random_active_problem(m, n, density, seed=m + n, weights=not unit)
     H_ref = oracle.ASAt(s, p, q)
