@@ -53,6 +53,9 @@ _pcsr, _pint, _pdbl, _pi64 = C.POINTER(CSR), C.POINTER(C.c_int), C.POINTER(C.c_d
 SIGNATURES = {
     "ssn_create": (_int, [C.POINTER(_vp), _int]),
     "ssn_destroy": (_int, [_vp]),
+    "ssn_default_ctx_acquire": (_int, [C.POINTER(_vp)]),
+    "ssn_default_ctx_release": (_int, []),
+    "ssn_default_ctx_refcount": (_int, []),
     "ssn_last_error": (C.c_char_p, [_vp]),
     "ssn_set_stream": (_int, [_vp, _vp]),
     "ssn_synchronize": (_int, [_vp]),

@@ -40,7 +40,10 @@ def _dev(x, dtype=None, count=None):
             t = t.to(dtype)
         if not t.is_cuda:
             t = t.cuda()
-        t = t.reshape(-1) if t.dim() != 1 else t
+        if t.dim() == 2:
+            t = t.t().reshape(-1)                  # column-major, like MATLAB's X(:) and like the NumPy branch below
+        elif t.dim() != 1:
+            raise ValueError("expected a vector or a matrix (flattened column-major)")
         t = t.contiguous()
     else:
         a = np.asarray(x)

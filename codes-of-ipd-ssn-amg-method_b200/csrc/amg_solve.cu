@@ -1715,7 +1715,7 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
     read_back(c, hist.p, hh.data(), hh.size());
     relk.assign(hh.begin(), hh.begin() + len);
     rho.assign(hh.begin() + hl, hh.begin() + hl + len);
-    rel_res = (len > 1) ? relk[len - 1] : (relk[0] == 0.0 ? 0.0 : 0.0);
+    rel_res = (len > 1) ? relk[len - 1] : 0.0;            // no cycle ran (zero right-hand side): Class_AMG's rel_res stays 0
     return true;
 }
 

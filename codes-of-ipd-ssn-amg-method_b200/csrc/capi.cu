@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary of libssnamg.so (include/ssnamg.h).  Every entry point
 // converts internal exceptions into status codes; nothing C++ crosses the ABI.
 #include "amg.cuh"
+#include <mutex>
 #include "plan_ops.cuh"
 #include "solvers.cuh"
 #include <cstdlib>
@@ -55,7 +56,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_SMALL_SCAN_MAX"); if (e && atoi(e) >= 0) c->small_scan_max = atoi(e); }
-    { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = (e && e[0] == '1'); }
+    { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
         SSN_CUDA(cudaSetDevice(device));
@@ -89,6 +90,34 @@ int ssn_destroy(ssn_ctx* c) {
     if (c->mt_state) cudaFree(c->mt_state);
     delete c;
     return SSN_OK;
+}
+
+// process-wide default context (the MEX shims' shared hidden state: hierarchy handle + MATLAB random stream)
+static std::mutex g_default_mu;
+static ssn_ctx* g_default_ctx = nullptr;
+static int g_default_refs = 0;
+
+int ssn_default_ctx_acquire(ssn_ctx** out) {
+    if (!out) return SSN_E_INVALID;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        const int st = ssn_create(&g_default_ctx, -1);
+        if (st != SSN_OK) { g_default_ctx = nullptr; *out = nullptr; return st; }
+        g_default_refs = 0;
+    }
+    ++g_default_refs;
+    *out = g_default_ctx;
+    return SSN_OK;
+}
+int ssn_default_ctx_release(void) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (g_default_refs <= 0) return SSN_E_INVALID;
+    if (--g_default_refs == 0) { ssn_destroy(g_default_ctx); g_default_ctx = nullptr; }
+    return SSN_OK;
+}
+int ssn_default_ctx_refcount(void) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    return g_default_refs;
 }
 
 const char* ssn_last_error(ssn_ctx* c) { return c ? c->err.c_str() : "null context"; }

@@ -64,7 +64,7 @@ struct ssn_ctx {
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
-    bool device_setup = false;            // SSN_DEVICE_SETUP=1: SSOR / IC(0) factors and their levels built on the device (trifactor.cu)
+    bool device_setup = true;             // SSN_DEVICE_SETUP=0: SSOR / IC(0) factors and their levels built on the host instead of the device (trifactor.cu)
     int small_scan_max = 1 << 14;         // SSN_SMALL_SCAN_MAX: largest array scanned by the one-block kernel (cub::DeviceScan above)
     int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
     // CUDA-event timer around the launches of the plan-wide kernels (ssn_kernel_timer): bench.py's roofline

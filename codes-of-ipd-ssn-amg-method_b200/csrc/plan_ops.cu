@@ -130,7 +130,9 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
                 }
                 px[k] = pz; zz[k] = z; sb[k] = act ? 1 : 0;
                 cnt += act ? 1 : 0;
-                n2 = fma(pz, pz, n2);
+                // the line-search term of APD_SsN_Class1.m:183-187: ||prox(z)||^2 for gama = Inf (prob < 3);
+                // ||z||^2 - ||z - prox(z)||^2 = sum prox(z)*(2z - prox(z)) for finite capacities (prob = 3)
+                n2 = (GM == G_INF) ? fma(pz, pz, n2) : fma(pz, __dsub_rn(__dadd_rn(z, z), pz), n2);
                 if (a.want_sums) { csum = fma(pz, pv[k], csum); rs[k] = fma(pz, qj, rs[k]); }
             }
             if (a.prox_out || a.z_out || a.s_out) {
@@ -380,7 +382,7 @@ __device__ __forceinline__ void trials_body(const TrialArgs& a, double* dsm) {
                         const double gm = (GM == G_VECTOR) ? g[GM == G_VECTOR ? cc : 0][k] : a.gama_s;
                         pz = nonneg ? ((z <= gm) ? z : gm) : (live ? fmin(0.0, gm) : 0.0);
                     }
-                    n2[t] = fma(pz, pz, n2[t]);
+                    n2[t] = (GM == G_INF) ? fma(pz, pz, n2[t]) : fma(pz, __dsub_rn(__dadd_rn(z, z), pz), n2[t]);   // APD_SsN_Class1.m:193-197
                 }
             }
         }

@@ -10,8 +10,8 @@
 // Rows of one dependency level of Lf only read rows of lower levels, so the factorisation runs level by level
 // (one launch per level, a thread per row: the order inside a row is sequential by definition).
 //
-// Selected with SSN_DEVICE_SETUP=1 (ssn_ctx::device_setup); the host construction stays the default until this
-// path has been run against the oracle on a B200 (tests/test_zz_device_setup.py).
+// The default (ssn_ctx::device_setup; run against the host construction and the oracle on a B200 by
+// tests/test_zz_device_setup.py); SSN_DEVICE_SETUP=0 / ssn_set_device_setup(ctx, 0) selects the host construction.
 #include "amg.cuh"
 #include "sparse.cuh"
 

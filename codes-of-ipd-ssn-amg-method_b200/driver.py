@@ -104,7 +104,8 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
     kx0, kl0 = kkt(xk, lk)
     fxk = [float(c @ xk)]; KKT_xk = [kx0]; KKT_lk = [kl0]
     stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm,
-             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0, "ls_passes": 0, "solve_calls": []}
+             "solve_s": 0.0, "asat_s": 0.0, "plan_s": 0.0, "ls_passes": 0, "solve_calls": [],
+             "steps": []}                 # (k, ssn_it, E, components, inner its, ll, |Fk_new|) per SsN step, as the oracle records them
     t_loop = time.time()
     rr = [np.inf]
     k = 0
@@ -133,14 +134,10 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             t0 = time.time()
             prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
             if inner_solver == 2:                                       # :149-152, PCG on Jk = bk1*I + (T+H0)/tk
-                import scipy.sparse as sp
                 po = dict(pcg_options)
                 if po.get("precd") == 5:
                     po["nf"] = n
-                if os.environ.get("SSN_DEVICE_SETUP") == "1":
-                    Jk = api.jk_system(prob_data)                       # ssn_jk_system: assembled on the device
-                else:                                                   # on the host (not the default solver) until ssn_jk_system has run on a B200
-                    Jk = api.DeviceCSR.from_scipy((bk1 * sp.identity(m + n, format="csr") + H0.to_scipy() / tk).tocsr())
+                Jk = api.jk_system(prob_data)                           # ssn_jk_system: assembled on the device
                 zeta, itpcg, respcg, _ = api.PCG(Jk, -Fk_old, po)
                 info = [0, 0]
             elif inner_solver == 3:
@@ -155,7 +152,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
                 raise ValueError("inner_solver must be 2 (PCG), 3 (aug_PCG), 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
             torch.cuda.synchronize(); stats["solve_s"] += time.time() - t0
             stats["solve_calls"].append((int(ev["count"]), time.time() - t0, int(itpcg), int(info[0])))
-            its.append(itpcg)
+            its.append(itpcg); E_step = int(ev["count"])
             t0 = time.time()
             f0 = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old)  # :182
             cFk_old = f0 + 0.5 * tk * n2_old
@@ -167,6 +164,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             Fk_new = bk1 * lk_new - ev["Axprox"] - wlk                  # :212
             nFo = float(torch.linalg.norm(Fk_old)); nF = float(torch.linalg.norm(Fk_new))
             torch.cuda.synchronize(); stats["plan_s"] += time.time() - t0
+            stats["steps"].append((k, ssn_it, E_step, int(info[0]), int(itpcg), int(ll), nF))
             if verbose:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={ll:3d} info={list(info)} its={itpcg} res={respcg:.2e} E={ev['count']}")
             if nF <= SsN_Tol:
@@ -280,7 +278,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
                 nrm(Hmul(u) - b))
 
     KKT = [kkts(uk, lk)]; fxk = [float(c @ uk[:mn])]
-    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm}
+    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "warmup_s": t_warm, "steps": []}
     t_loop = time.time(); rr = [np.inf]; k = 0
     for k in range(1, maxit + 1):                                       # :95
         resk = max(KKT[k - 1])
@@ -323,6 +321,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
             stats["ls_trials"] += ll + 1
             Fk_new = bk1 * lk_new - Hmul(pz) - wlk                      # :217
             nFo = nrm(Fk_old); nF = nrm(Fk_new)
+            stats["steps"].append((k, ssn_it, int(s.sum()), int(info[0]), int(itpcg), int(ll), nF))
             if verbose:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={ll:3d} info={list(info)} its={itpcg} res={respcg:.2e}")
             if nF <= SsN_Tol:

@@ -80,6 +80,15 @@ class SlabAlgebra:
         self.collectives += 1
         return [float(v) for v in t]
 
+    def maxs(self, *vals):
+        """all_reduce(max) of a few host scalars."""
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.p.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.collectives += 1
+        return [float(v) for v in t]
+
 
 def warmup_class1_sharded_fused(A, c, b, gama, maxit):
     """Class1/warmup_class1.m:43-95 on row slabs with the fused stage kernels (``ops.warm_stage``): two
@@ -151,11 +160,16 @@ def warmup_class1_sharded(A, c, b, gama, maxit):
 
 def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
                            ops=None, dist=None, amg_options=None, max_outer=None, max_seconds=None, verbose=False, inner_solver=4,
-                           fused_warmup=True):
+                           fused_warmup=True, stop_on_amg_divergence=False):
     """APD outer loop + SsN inner loop of Class1/APD_SsN_Class1.m:32-275 on a row-sharded plan.
     ``c_loc``: this rank's slab of the cost (column-major ``m_loc x n``); ``r, l, p, q``: full vectors,
     replicated; ``inner_solver``: 4 = Hybrid_AMG (the reference's default), 5 = Hybrid_twogrid
-    (Class1/APD_SsN_Class1.m:70,161,178).  Returns the same dictionary on every rank (``xk`` is the rank's slab)."""
+    (Class1/APD_SsN_Class1.m:70,161,178).  Returns the same dictionary on every rank (``xk`` is the rank's slab).
+
+    A divergent W-cycle solve (``Class_AMG`` leaving its loop on ``rho > 1``, AMG/Class_AMG.m:106) is recorded in
+    ``stats["amg_diverged"]`` (first occurrence) and the iteration carries on with that direction, exactly like the
+    reference (Class1/APD_SsN_Class1.m:161-212, where the line search decides) and like ``driver.APD_SsN_Class1``;
+    ``stop_on_amg_divergence=True`` (off by default, a convenience for long multi-GPU runs) ends the solve there instead."""
     import torch
     if dist is None:
         import torch.distributed as dist
@@ -201,7 +215,7 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
         wlk = bk1 * (lk - 1 / bk * (axk - b)) - b                       # :126
         step = ShardedStep({"wk": wk, "lk": lk, "wlk": wlk, "p": p, "q": q, "bk1": bk1, "tk": tk, "gama": gam}, rank, world,
                            ops=ops, dist=dist, amg_options=amg_options, already_sharded=True, inner_solver=inner_solver)
-        ssn_it = 0; lk_new = lk.clone()
+        ssn_it = 0; lk_new = lk.clone(); stopped = False
         ev = step.residual(lk_new, True)                                # :129-130 (+ s for :140)
         Fk_new = bk1 * lk_new - ev[0] - wlk
         nF = float(torch.linalg.norm(Fk_new))
@@ -222,10 +236,13 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
             if not (info["resamg"] <= 1.0) or not math.isfinite(nF):
                 # Class_AMG left its loop on rho > 1 (AMG/Class_AMG.m:106) with a residual above the initial one: the
                 # W-cycle of the reference diverges on this system (the oracle reproduces it: the damped-Jacobi smoother
-                # 0.5*D^-1 of a coarse Galerkin level has lambda_max(R*A) > 2).  The reference would carry on with the
-                # useless direction; the solve is stopped here and says so.
-                stats["amg_diverged"] = {"k": k, "ssn_it": ssn_it, "E": int(info["E"]), "amg_res": float(info["resamg"]), "Fk": nF}
-                break
+                # 0.5*D^-1 of a coarse Galerkin level has lambda_max(R*A) > 2).  The reference carries on with the
+                # direction it got and so does this loop; the event is recorded.
+                if stats["amg_diverged"] is None:
+                    stats["amg_diverged"] = {"k": k, "ssn_it": ssn_it, "E": int(info["E"]), "amg_res": float(info["resamg"]), "Fk": nF}
+                if stop_on_amg_divergence or not math.isfinite(nF):
+                    stopped = True
+                    break
             if verbose and rank == 0:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nF:.2e} ll={info['ll']:3d} info={list(info['info'])} its={info['itamg']} "
                       f"res={info['resamg']:.2e} E={info['E']}", flush=True)
@@ -238,7 +255,7 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
             if Fk_res / nF >= 2:
                 Fk_res = nF
         A.collectives += step.collectives
-        if stats["amg_diverged"] is not None:
+        if stopped:
             stats["ssn_its"].append(ssn_it); stats["lin_its"].append(its)
             break
         lk1 = lk_new
@@ -263,9 +280,8 @@ def APD_SsN_Class1_sharded(c_loc, r, l, p, q, rank, world, gama=np.inf, maxit=10
         if max_outer is not None and k >= max_outer:
             break
         if max_seconds is not None:
-            # every rank must take the same branch: the slowest clock decides
-            (elapsed,) = A.sums(time.time() - t_loop)
-            if elapsed / world > max_seconds:
+            # every rank must take the same branch: the slowest clock decides (all_reduce MAX)
+            if A.maxs(time.time() - t_loop)[0] > max_seconds:
                 break
     sync()
     stats["collectives"] = A.collectives

@@ -111,6 +111,19 @@ typedef struct ssn_prob_data {
 /* ------------------------------------------------------------------ context */
 SSN_API int  ssn_create(ssn_ctx **ctx, int device);           /* device < 0: current device */
 SSN_API int  ssn_destroy(ssn_ctx *ctx);
+/* The process-wide default context, reference counted: every caller of ssn_default_ctx_acquire gets the SAME
+ * context (created on the current device by the first one), ssn_default_ctx_release drops one reference and
+ * the last one destroys it.  This is what the MEX shims use (mex/ssn_mex_common.h): the reference keeps the AMG
+ * hierarchy in MATLAB globals (`global Ack Prok J smoth_it Rk`, AMG/Class_AMG.m:43,110; AMG/MG_Vcycle.m:8;
+ * AMG/MG_Wcycle.m:9; AMG/transfer.m:17) and draws from ONE global `rand` stream (AMG/mis_set.m:31,35;
+ * Hybrid_AMG.m:40,69; Class1/APD_SsN_Class1.m:246), both shared by all functions of the process -- so
+ * Class_AMG.mex, MG_Wcycle.mex, transfer.mex, mis_set.mex and Hybrid_AMG.mex must share one hierarchy handle
+ * and one MT19937 stream, which live in this context.  libssnamg.so is mapped once per process however many
+ * MEX files link it.  Thread-safe; the entry points themselves are not re-entrant (MATLAB calls MEX files on
+ * its interpreter thread). */
+SSN_API int  ssn_default_ctx_acquire(ssn_ctx **ctx);
+SSN_API int  ssn_default_ctx_release(void);
+SSN_API int  ssn_default_ctx_refcount(void);
 SSN_API const char *ssn_last_error(ssn_ctx *ctx);
 SSN_API int  ssn_set_stream(ssn_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = default stream */
 SSN_API int  ssn_synchronize(ssn_ctx *ctx);
@@ -135,8 +148,8 @@ SSN_API int  ssn_set_dense_tail(ssn_ctx *ctx, int dense_tail, int dense_max_n);
 /* on != 0 (default; env SSN_PERSIST): Class_AMG's solve loop runs as one persistent cooperative kernel
  * (grid barriers between the dependent steps); 0 launches it kernel by kernel. */
 SSN_API int  ssn_set_persistent(ssn_ctx *ctx, int on);
-/* on != 0 (env SSN_DEVICE_SETUP=1): PCG's SSOR / IC(0) factors (precd 3 / 4), their dependency levels and row
- * groups are built on the device; 0 (default until that path has been checked on a B200): on the host, once per call. */
+/* on != 0 (default): PCG's SSOR / IC(0) factors (precd 3 / 4), their dependency levels and row groups are built on
+ * the device; 0 (env SSN_DEVICE_SETUP=0): on the host, once per call (kept as the cross-check of the device path). */
 SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
 /* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
  * 1 = the library's own barrier (development aid) */
@@ -183,7 +196,8 @@ SSN_API int ssn_aty_host(ssn_ctx *ctx, const double *y_host, const double *p_hos
  *   s   = (z >= 0) & (z <= gama)             -> s_out_dev   (uint8, m*n)       [optional]
  *   px  = min(max(0,z),gama)                 -> prox_out_dev (m*n)             [optional]
  *   Ax(px)                                   -> axp_out_dev  (n+m)             [optional]
- *   ||px||^2                                 -> *norm2_out (host)              [optional]
+ *   the line-search term of :183-187         -> *norm2_out (host)              [optional]
+ *       gama = Inf (prob < 3): ||px||^2;  finite gama (prob = 3): ||z||^2 - ||z - px||^2 = sum px*(2z - px)
  *   nnz(s)                                   -> *count_out (host)              [optional]
  * gama_dev == NULL means gama = gama_scalar for every entry (Inf for plain OT). */
 SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *lam_dev,
@@ -192,7 +206,8 @@ SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *l
                       double *axp_out_dev, double *prox_out_dev, double *z_out_dev,
                       uint8_t *s_out_dev, double *norm2_out, int64_t *count_out);
 
-/* Batched line-search trials: n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 for the nt <= 8
+/* Batched line-search trials: n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 (finite gama: the prob = 3
+ * term of ssn_prox_residual's norm2_out) for the nt <= 8
  * trial dual vectors lamT_dev[t*(n+m) .. ] in ONE read of w (Class1/APD_SsN_Class1.m:193-207
  * evaluates one trial per Aty + prox + norm pass).  Per-entry arithmetic as ssn_prox_residual. */
 SSN_API int ssn_prox_trials(ssn_ctx *ctx, const double *w_dev, const double *lamT_dev, int nt,

@@ -10,16 +10,18 @@
 #include "matrix.h"
 #include "../include/ssnamg.h"
 
+/* This MEX file's reference to the PROCESS-WIDE default context of libssnamg.so.  Every shim (Class_AMG.mex,
+ * MG_Wcycle.mex, transfer.mex, mis_set.mex, Hybrid_AMG.mex, ...) holds the same handle, so they share one AMG
+ * hierarchy and one MT19937 stream exactly like the reference's functions share `global Ack Prok J smoth_it Rk`
+ * (AMG/Class_AMG.m:43,110; AMG/MG_Wcycle.m:9; AMG/transfer.m:17) and MATLAB's global `rand`. */
 static ssn_ctx *g_ctx = NULL;
 
-static void ssn_mex_cleanup(void) { if (g_ctx) { ssn_destroy(g_ctx); g_ctx = NULL; } }
+static void ssn_mex_cleanup(void) { if (g_ctx) { ssn_default_ctx_release(); g_ctx = NULL; } }
 
-/* library-owned persistent state (hierarchy handle, random stream) lives in the context:
- * keep the MEX file locked, free at exit (the reference keeps it in globals,
- * AMG/Class_AMG.m:42-43) */
+/* keep the MEX file locked while it holds a reference, drop it at exit (the last shim to exit frees the context) */
 static ssn_ctx *ssn_mex_ctx(void) {
     if (!g_ctx) {
-        if (ssn_create(&g_ctx, -1) != SSN_OK) mexErrMsgIdAndTxt("ssnamg:nogpu", "no CUDA device (no CPU fallback)");
+        if (ssn_default_ctx_acquire(&g_ctx) != SSN_OK) mexErrMsgIdAndTxt("ssnamg:nogpu", "no CUDA device (no CPU fallback)");
         mexAtExit(ssn_mex_cleanup);
         mexLock();
     }

@@ -49,7 +49,7 @@ def warmup_class1(c, r, l, p, q, gama, res=1e-1, maxit=np.inf):
 
 
 def APD_SsN_Class1(c, r, l, p, q, gama, inner_solver=4, maxit=100, KKT_Tol=1e-6,
-                   warm_maxit=100, on_ssn_step=None, verbose=False, max_seconds=None):
+                   warm_maxit=100, on_ssn_step=None, verbose=False, max_seconds=None, max_outer=None):
     """The APD outer loop with SsN inner loop -- reference Class1/APD_SsN_Class1.m:32-275.
 
     ``on_ssn_step(state_dict)`` is called before every inner linear solve with everything the
@@ -58,6 +58,10 @@ def APD_SsN_Class1(c, r, l, p, q, gama, inner_solver=4, maxit=100, KKT_Tol=1e-6,
     """
     m, n = l.size, r.size
     prox = lambda x: np.minimum(np.maximum(0.0, x), gama)               # :32
+    if np.all(np.isinf(gama)):                                          # prob < 3   :183-184
+        ls_term = lambda z: np.linalg.norm(prox(z)) ** 2
+    else:                                                               # prob = 3 (capacities)   :185-186
+        ls_term = lambda z: np.linalg.norm(z) ** 2 - np.linalg.norm(z - prox(z)) ** 2
     b = np.concatenate([r, l])
     bk = 1.0
     SsN_IT = 50; SsN_Tol1 = 1e-11; nu = 0.2; delta = 0.9; ll_max = 500  # :36
@@ -67,7 +71,8 @@ def APD_SsN_Class1(c, r, l, p, q, gama, inner_solver=4, maxit=100, KKT_Tol=1e-6,
     KKT_lk = [np.linalg.norm(Ax(xk, p, q) - b)]
     KKT_xk = [np.linalg.norm(xk - prox(xk - c - Aty(lk, p, q)))]
     amg_options = dict(CLASS1_AMG_OPTIONS); pcg_options = dict(CLASS1_PCG_OPTIONS)
-    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0}
+    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0,
+             "steps": []}                 # steps: (k, ssn_it, E, ncomp, its, ll, |Fk_new|) per SsN step
     t0 = time.time()
     for k in range(1, maxit + 1):                                       # :101
         resk = max(KKT_xk[k - 1], KKT_lk[k - 1])
@@ -102,22 +107,23 @@ def APD_SsN_Class1(c, r, l, p, q, gama, inner_solver=4, maxit=100, KKT_Tol=1e-6,
                     stats["amg_calls"] += 1
             its.append(itpcg)
             f0 = bk1 / 2 * np.linalg.norm(lk_old) ** 2 - wlk @ lk_old   # :182
-            cFk_old = f0 + 0.5 * tk * np.linalg.norm(prox(zk)) ** 2
+            cFk_old = f0 + 0.5 * tk * ls_term(zk)
             ll = 0; lk_new = lk_old + delta ** ll * zeta
             f0 = bk1 / 2 * np.linalg.norm(lk_new) ** 2 - wlk @ lk_new
             zk = 1 / tk * (wk - Aty(lk_new, p, q))
-            cFk_new = f0 + 0.5 * tk * np.linalg.norm(prox(zk)) ** 2
+            cFk_new = f0 + 0.5 * tk * ls_term(zk)
             ress = abs(Fk_old @ zeta)
             while cFk_new > cFk_old - nu * delta ** ll * ress:          # :199-211
                 ll += 1; lk_new = lk_old + delta ** ll * zeta
                 f0 = bk1 / 2 * np.linalg.norm(lk_new) ** 2 - wlk @ lk_new
                 zk = 1 / tk * (wk - Aty(lk_new, p, q))
-                cFk_new = f0 + 0.5 * tk * np.linalg.norm(prox(zk)) ** 2
+                cFk_new = f0 + 0.5 * tk * ls_term(zk)
                 if ll == ll_max:
                     break
             stats["ls_trials"] += ll + 1
             Fk_new = bk1 * lk_new - Ax(prox(zk), p, q) - wlk            # :212
             nFn = np.linalg.norm(Fk_new)
+            stats["steps"].append((k, ssn_it, int(np.count_nonzero(s)), int(info[0]), int(itpcg), ll, float(nFn)))
             if verbose:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nFn:.2e} ll={ll:3d} info={list(info)} "
                       f"its={itpcg} res={respcg:.2e}")
@@ -145,6 +151,8 @@ def APD_SsN_Class1(c, r, l, p, q, gama, inner_solver=4, maxit=100, KKT_Tol=1e-6,
                   f"t={time.time() - t0:.1f}s")
         if max(rr) <= KKT_Tol:                                          # :266
             stats["converged"] = True
+            break
+        if max_outer is not None and k >= max_outer:
             break
         if max_seconds is not None and time.time() - t0 > max_seconds:
             break
@@ -200,7 +208,7 @@ def warmup_class2(c, r, l, p, q, mu, phi, res=1e-1, maxit=np.inf):
 
 
 def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
-                   on_ssn_step=None, verbose=False, max_seconds=None):
+                   on_ssn_step=None, verbose=False, max_seconds=None, max_outer=None):
     """APD + SsN for partial OT -- reference Class2/APD_SsN_Class2.m:25-285 (inner solvers 3 =
     PCG4POT, 4 = AMG4POT).  Unknowns u = [x (mn); y (n); z (m)], duals lk (n+m+1)."""
     from .solvers import AMG4POT, PCG4POT
@@ -224,7 +232,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
     k0 = kkts(uk, lk)
     fxk = [float(c @ uk[:mn])]; KKT = [k0]
     amg_options = dict(CLASS2_AMG_OPTIONS); pcg_options = dict(CLASS1_PCG_OPTIONS)
-    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0}
+    stats = {"ssn_its": [], "lin_its": [], "ls_trials": 0, "converged": False, "amg_calls": 0, "steps": []}
     t0 = time.time()
     rr = [np.inf]
     for k in range(1, maxit + 1):                                       # :95
@@ -271,6 +279,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
             pzk = prox(zk)
             Fk_new = bk1 * lk_new - Hmul(pzk) - wlk                     # :217
             nFn = np.linalg.norm(Fk_new)
+            stats["steps"].append((k, ssn_it, int(np.count_nonzero(s)), int(info[0]), int(itpcg), ll, float(nFn)))
             if verbose:
                 print(f"   SsN: it={ssn_it:3d} |Fk|={nFn:.2e} ll={ll:3d} info={list(info)} its={itpcg} res={respcg:.2e}")
             if nFn <= SsN_Tol:
@@ -294,6 +303,8 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
             print(f"APD: it={k:3d} KKT(x,y,z,l)={['%.2e' % v for v in rr]} fk={fxk[-1]:.8e} t={time.time() - t0:.1f}s")
         if max(rr) <= KKT_Tol:                                          # :274
             stats["converged"] = True
+            break
+        if max_outer is not None and k >= max_outer:
             break
         if max_seconds is not None and time.time() - t0 > max_seconds:
             break

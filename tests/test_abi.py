@@ -73,3 +73,60 @@ def test_mex_shims_type_check_against_the_header():
                             "-I" + os.path.join(root, "tests", "mex_stub"), "-I" + os.path.join(root, "mex"), f],
                            capture_output=True, text=True)
         assert r.returncode == 0, f"{os.path.basename(f)}:\n{r.stderr}"
+
+
+def _build_mex_host(tmp_path):
+    """Compiles the functional MEX runtime stand-in, three shims as separate shared objects (two of them the REAL
+    mex/MG_Wcycle.c and mex/mis_set.c) and the C host that dlopens them like MATLAB loads .mex files."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "codes-of-ipd-ssn-amg-method_b200")
+    stub = os.path.join(root, "tests", "mex_stub")
+    out = str(tmp_path)
+    run = lambda cmd: subprocess.run(cmd, capture_output=True, text=True)
+    r = run([gcc, "-std=c99", "-D_GNU_SOURCE", "-O1", "-Wall", "-Werror", "-fPIC", "-shared", "-I" + stub,
+             os.path.join(stub, "mex_runtime.c"), "-o", os.path.join(out, "libmexrt.so")])
+    assert r.returncode == 0, r.stderr
+    link = ["-L" + out, "-lmexrt", "-L" + lib, "-lssnamg", "-Wl,-rpath," + out, "-Wl,-rpath," + lib]
+    for name, src in (("keep", os.path.join(root, "tests", "c", "shim_keep.c")), ("MG_Wcycle", os.path.join(root, "mex", "MG_Wcycle.c")),
+                      ("mis_set", os.path.join(root, "mex", "mis_set.c"))):
+        r = run([gcc, "-std=c99", "-O1", "-Wall", "-Werror", "-Wno-unused-function", "-fPIC", "-shared", "-I" + stub,
+                 "-I" + os.path.join(root, "mex"), src, "-o", os.path.join(out, name + ".mex.so")] + link)
+        assert r.returncode == 0, f"{name}:\n{r.stderr}"
+    exe = os.path.join(out, "mex_host")
+    r = run([gcc, "-std=c99", "-D_GNU_SOURCE", "-O1", "-Wall", "-Werror", "-I" + stub, os.path.join(root, "tests", "c", "mex_host.c"),
+             "-o", exe] + link + ["-ldl", "-lm"])
+    assert r.returncode == 0, r.stderr
+    return exe, out
+
+
+def test_mex_shims_link_and_report_a_missing_device(tmp_path, ssnamg):
+    """The real shim sources compile and LINK against libssnamg.so (a functional stand-in for MATLAB's MEX runtime
+    replaces mex.h's library); without a CUDA device the first shim raises ssnamg:nogpu -- no CPU fallback."""
+    import subprocess
+    import torch
+    exe, out = _build_mex_host(tmp_path)
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present: covered by test_mex_shims_share_one_context")
+    r = subprocess.run([exe, out], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr, (r.returncode, r.stdout, r.stderr)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_mex_shims_share_one_context(tmp_path, gpu):
+    """C host (tests/c/mex_host.c), no Python between the shims: three shim shared objects, each with its own static
+    handle, share ONE library context -- Class_AMG's hierarchy kept by one shim is cycled by the real MG_Wcycle shim,
+    mis_set's random draws are seen through another shim, a clear through one is an error in the other
+    (the reference's `global Ack Prok J smoth_it Rk`, AMG/Class_AMG.m:43,110; AMG/MG_Wcycle.m:9; rand, AMG/mis_set.m:35)."""
+    import subprocess
+    exe, out = _build_mex_host(tmp_path)
+    r = subprocess.run([exe, out], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("OK:") and "3 shims, one context" in r.stdout

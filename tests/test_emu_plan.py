@@ -84,7 +84,8 @@ def test_prox_residual(emu, oracle, m, n, gmode):
     assert np.array_equal(out["z"], z) and np.array_equal(out["s"], s) and np.array_equal(out["prox"], px)
     assert out["count"] == int(s.sum())
     assert close(out["Axprox"], oracle.Ax(px, p, q))
-    assert abs(out["norm2"] - float(px @ px)) <= 1e-12 * float(px @ px) + 1e-300
+    term = float(px @ px) if gmode == "inf" else float(z @ z) - float((z - px) @ (z - px))    # APD_SsN_Class1.m:183-187
+    assert abs(out["norm2"] - term) <= 1e-12 * float(z @ z) + 1e-300
     lite = prox_residual(emu, w, lam, p, q, tk, gama, full=False)        # line-search form: norm only
     assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
 
@@ -144,8 +145,11 @@ def test_linesearch_matches_the_reference_loop(emu, oracle, m, n, gama, batch):
     an over-long steepest-descent direction, which needs a handful of backtracking steps."""
     p, q, w, lam, _, wlk = _ls_state(oracle, m, n, 9)
     tk, bk1, nu, delta, ll_max = 0.6, 0.25, 0.2, 0.9, 500
-    prox = lambda l: np.minimum(np.maximum((w - oracle.Aty(l, p, q)) / tk, 0.0), gama)
-    cF = lambda l: bk1 / 2 * (l @ l) - wlk @ l + 0.5 * tk * np.sum(prox(l) ** 2)
+    zof = lambda l: (w - oracle.Aty(l, p, q)) / tk
+    prox = lambda l: np.minimum(np.maximum(zof(l), 0.0), gama)
+    # APD_SsN_Class1.m:183-187: ||prox(z)||^2 for gama = Inf (prob < 3), ||z||^2 - ||z - prox(z)||^2 with capacities (prob = 3)
+    term = (lambda l: np.sum(prox(l) ** 2)) if np.isinf(gama) else (lambda l: np.sum(zof(l) ** 2) - np.sum((zof(l) - prox(l)) ** 2))
+    cF = lambda l: bk1 / 2 * (l @ l) - wlk @ l + 0.5 * tk * term(l)
     cF_old = cF(lam)
     Fk = bk1 * lam - oracle.Ax(prox(lam), p, q) - wlk                      # the gradient of cF at lam (where no entry sits at its capacity)
     zeta = -0.1 * Fk

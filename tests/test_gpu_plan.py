@@ -83,7 +83,9 @@ def test_prox_residual_matches_oracle(gpu, oracle, m, n, gmode):
     assert np.array_equal(out["prox"], px)
     assert out["count"] == int(s.sum())
     assert close(out["Axprox"], oracle.Ax(px, p, q))
-    assert abs(out["norm2"] - float(px @ px)) <= 1e-12 * float(px @ px) + 1e-300
+    # the line-search term of APD_SsN_Class1.m:183-187: prob < 3 (gama = Inf) and prob = 3 (capacities)
+    term = float(px @ px) if gmode == "inf" else float(z @ z) - float((z - px) @ (z - px))
+    assert abs(out["norm2"] - term) <= 1e-12 * float(z @ z) + 1e-300
     lite = gpu.prox_residual(w, lam, p, q, tk, gama, want=())      # line-search form: norm only
     assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
 
@@ -299,6 +301,38 @@ def test_linesearch_matches_trial_by_trial_loop(gpu, oracle):
         out, ll_dev, n2, cF_new, passes = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, np.inf, nu, delta, ll_max, batch=8)
         assert ll_dev == ll, (scale, ll_dev, ll)
         assert passes == 1 + (ll + 7) // 8
+        assert np.array_equal(out.cpu().numpy(), lk_new)
+        assert abs(cF_new - cF(lk_new)) <= 1e-10 * max(1.0, abs(cF_new))
+
+
+@pytest.mark.parametrize("gama", [0.8, "vector"])
+def test_linesearch_with_capacities_uses_the_prob3_merit(gpu, oracle, gama):
+    """Finite gama (prob = 3): the Armijo function is f0 + tk/2*(||z||^2 - ||z - prox(z)||^2)
+    (Class1/APD_SsN_Class1.m:185-186,194-197,203-207), not tk/2*||prox(z)||^2."""
+    m, n = 130, 90
+    rs = np.random.RandomState(11)
+    p, q = np.ones(m), np.ones(n)
+    w = rs.standard_normal(m * n) + 0.3; lam = 0.2 * rs.standard_normal(n + m); wlk = rs.standard_normal(n + m)
+    if isinstance(gama, str):
+        gama = rs.random_sample(m * n) + 0.2
+    tk, bk1, nu, delta, ll_max = 0.7, 0.3, 0.2, 0.9, 500
+    zof = lambda l: (w - oracle.Aty(l, p, q)) / tk
+    prox = lambda z: np.minimum(np.maximum(z, 0.0), gama)
+    cF = lambda l: bk1 / 2 * (l @ l) - wlk @ l + 0.5 * tk * (np.sum(zof(l) ** 2) - np.sum((zof(l) - prox(zof(l))) ** 2))
+    grad = bk1 * lam - wlk - oracle.Ax(prox(zof(lam)), p, q)          # gradient of cF at lam
+    for scale in (0.5, 40.0, 900.0):
+        zeta = -scale * grad
+        cF_old = cF(lam); ress = abs(float(grad @ zeta))
+        ll = 0
+        while True:
+            lk_new = lam + delta ** ll * zeta
+            if not (cF(lk_new) > cF_old - nu * delta ** ll * ress) or ll == ll_max:
+                break
+            ll += 1
+        ev = gpu.prox_residual(w, lam, p, q, tk, gama, want=())
+        assert abs(bk1 / 2 * (lam @ lam) - wlk @ lam + 0.5 * tk * ev["norm2"] - cF_old) <= 1e-11 * abs(cF_old)
+        out, ll_dev, n2, cF_new, passes = gpu.linesearch(w, lam, zeta, wlk, p, q, tk, bk1, cF_old, ress, gama, nu, delta, ll_max)
+        assert ll_dev == ll, (scale, ll_dev, ll)
         assert np.array_equal(out.cpu().numpy(), lk_new)
         assert abs(cF_new - cF(lk_new)) <= 1e-10 * max(1.0, abs(cF_new))
 

@@ -1,0 +1,161 @@
+"""GPU end-to-end parity at BASELINE.json's own configurations: the device-resident drivers against the CPU oracle's
+recorded runs (tests/golden/trace_*.npz, made by tests/golden/make_traces.py in the build container -- MATLAB/Octave
+are absent, so the oracle's restatement of Class1/APD_SsN_Class1.m:101-275 / Class2/APD_SsN_Class2.m:95-285 is the
+ground truth: parity unpinned w.r.t. MATLAB).
+
+  config 1  bundled 500 x 500 problem (Class1/InputData/data1-500.mat), whole solve: 58 outer iterations,
+            objective 1.1260464956, nnz(x) = m+n-1 = 999
+  config 2  64 x 64 grids (m = n = 4096), Class 1, first 4 outer iterations
+  config 3  64 x 64 grids, Class 2 (partial OT through AMG4POT / invHHt), first 3 outer iterations;
+            small fixture: Class2/InputData/data4-500.mat, whole solve
+
+North star: objective <= 1e-8 relative, plan <= 1e-8 (inf-norm, relative); discrete quantities (SsN step counts,
+active-set sizes, component counts, W-cycle counts, accepted backtracking exponents) equal.  The achieved figures are
+printed (pytest -s) and asserted.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+OBJ_TOL = 1e-8          # BASELINE.json north_star: objective <= 1e-8 relative
+PLAN_TOL = 1e-8         # plan <= 1e-8 relative in the inf-norm
+
+
+def _drv():
+    return importlib.import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+
+
+def _trace(name):
+    path = os.path.join(GOLDEN, f"trace_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} missing (python tests/golden/make_traces.py)")
+    return dict(np.load(path))
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def _check_steps(got, ref, upto=None):
+    """per SsN step: (k, ssn_it, E, components, inner iterations, ll, |F|)"""
+    got = np.array(got, dtype=np.float64).reshape(-1, 7); ref = np.asarray(ref).reshape(-1, 7)
+    n = len(ref) if upto is None else upto
+    assert len(got) >= n, (len(got), n)
+    g, r = got[:n], ref[:n]
+    assert np.array_equal(g[:, :2], r[:, :2]), "outer / SsN step numbering differs"
+    assert np.array_equal(g[:, 2], r[:, 2]), ("active-set sizes differ", g[:, 2], r[:, 2])
+    assert np.array_equal(g[:, 3], r[:, 3]), ("component counts differ", g[:, 3], r[:, 3])
+    assert np.array_equal(g[:, 4], r[:, 4]), ("inner iteration counts differ", g[:, 4], r[:, 4])
+    assert np.array_equal(g[:, 5], r[:, 5]), ("accepted backtracking exponents differ", g[:, 5], r[:, 5])
+    return float(np.max(_rel(g[:, 6], r[:, 6]) * (r[:, 6] > 1e-9)))
+
+
+def _check_plan(x, T):
+    xv = x[np.asarray(T["x_idx"])]
+    scale = float(T["x_inf"])
+    err = float(np.max(np.abs(xv - T["x_val"]))) / scale
+    assert err <= PLAN_TOL, err
+    assert abs(float(np.abs(x).max()) - scale) <= PLAN_TOL * scale
+    assert abs(float(x.sum()) - float(T["x_sum"])) <= 1e-8 * abs(float(T["x_sum"]))
+    return err
+
+
+def test_config2_class1_grid64_first_outer_iterations(gpu):
+    T = _trace("class1_grid64_outer4")
+    drv = _drv()
+    P = gpu.problems.grid_problem(64, seed=0)
+    gpu.rng_reset()
+    out = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], max_outer=int(T["outer_its"]))
+    k = int(T["outer_its"])
+    assert out["outer_its"] == k and out["stats"]["ssn_its"] == T["ssn_its"].tolist()
+    e_f = float(np.max(_rel(out["fxk"], T["fxk"])))
+    e_kx = float(np.max(_rel(out["KKT_xk"], T["KKT_xk"]))); e_kl = float(np.max(_rel(out["KKT_lk"], T["KKT_lk"])))
+    e_F = _check_steps(out["stats"]["steps"], T["steps"])
+    lk = out["lk"].cpu().numpy()
+    e_l = float(np.max(np.abs(lk - T["lk"])) / np.max(np.abs(T["lk"])))
+    x = out["xk"].cpu().numpy()
+    assert int(np.count_nonzero(x)) == int(T["x_nnz"])
+    e_x = _check_plan(x, T)
+    print(f"config 2 (64x64 Class 1, {k} outer its, {len(T['steps'])} SsN steps): objective {e_f:.1e}, KKT_x {e_kx:.1e}, KKT_l {e_kl:.1e}, "
+          f"|F| {e_F:.1e}, duals {e_l:.1e}, plan(inf) {e_x:.1e}")
+    assert e_f <= OBJ_TOL and e_l <= 1e-8 and e_kx <= 1e-6 and e_kl <= 1e-6 and e_F <= 1e-6
+
+
+def test_config3_class2_grid64_first_outer_iterations(gpu):
+    T = _trace("class2_grid64_outer3")
+    drv = _drv()
+    P = gpu.problems.grid_problem_pot(64, seed=0)
+    gpu.rng_reset()
+    out = drv.APD_SsN_Class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], max_outer=int(T["outer_its"]))
+    k = int(T["outer_its"])
+    assert out["outer_its"] == k and out["stats"]["ssn_its"] == T["ssn_its"].tolist()
+    e_f = float(np.max(_rel(out["fxk"], T["fxk"])))
+    e_k = float(np.max(_rel(np.array(out["KKT"]), T["KKT"]) * (T["KKT"] > 1e-9)))
+    e_F = _check_steps(out["stats"]["steps"], T["steps"])
+    lk = out["lk"].cpu().numpy()
+    e_l = float(np.max(np.abs(lk - T["lk"])) / np.max(np.abs(T["lk"])))
+    x = out["xk"].cpu().numpy()
+    e_x = _check_plan(x, T)
+    print(f"config 3 (64x64 Class 2, {k} outer its, {len(T['steps'])} SsN steps): objective {e_f:.1e}, KKT {e_k:.1e}, |F| {e_F:.1e}, "
+          f"duals {e_l:.1e}, plan(inf) {e_x:.1e}")
+    assert e_f <= OBJ_TOL and e_l <= 1e-8 and e_k <= 1e-6 and e_F <= 1e-6
+
+
+def test_config1_bundled500_full_solve(gpu):
+    """The reference's own example input, whole solve: same 58 outer iterations, same SsN step counts, objective
+    1.1260464956 to <= 1e-8, a basic optimal plan with m+n-1 = 999 nonzeros (tests/golden/bundled500_summary.npz)."""
+    T = _trace("bundled500")
+    inp = os.path.join(GOLDEN, "bundled500_inputs.npz")
+    if not os.path.exists(inp):
+        pytest.skip("bundled500_inputs.npz missing")
+    D = np.load(inp)
+    m, n = int(D["m"]), int(D["n"])
+    drv = _drv()
+    gpu.rng_reset()
+    out = drv.APD_SsN_Class1(D["c"], D["r"], D["l"], np.ones(m), np.ones(n), np.inf)
+    S = np.load(os.path.join(GOLDEN, "bundled500_summary.npz"))
+    assert out["stats"]["converged"] and out["rel_kkt"] <= 1e-6
+    assert out["outer_its"] == int(T["outer_its"]) == int(S["outer_its"]) == 58
+    assert out["stats"]["ssn_its"] == T["ssn_its"].tolist()
+    f, f_ref = out["fxk"][-1], float(T["fxk"][-1])
+    assert abs(f_ref - 1.1260464956) < 1e-9
+    x = out["xk"].cpu().numpy()
+    assert int(np.count_nonzero(x)) == int(T["x_nnz"]) == int(S["nnz"]) == m + n - 1
+    e_f = float(np.max(_rel(out["fxk"], T["fxk"])))
+    e_F = _check_steps(out["stats"]["steps"], T["steps"])
+    e_x = _check_plan(x, T)
+    e_l = float(np.max(np.abs(out["lk"].cpu().numpy() - T["lk"])) / np.max(np.abs(T["lk"])))
+    print(f"config 1 (bundled 500x500, 58 outer its, {len(T['steps'])} SsN steps): final objective {abs(f - f_ref) / f_ref:.1e}, "
+          f"objective history {e_f:.1e}, |F| {e_F:.1e}, duals {e_l:.1e}, plan(inf) {e_x:.1e}")
+    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= OBJ_TOL
+
+
+def test_config3_fixture_class2_bundled500_full_solve(gpu):
+    T = _trace("class2_bundled500")
+    inp = os.path.join(GOLDEN, "bundled500_class2_inputs.npz")
+    if not os.path.exists(inp):
+        pytest.skip("bundled500_class2_inputs.npz missing")
+    D = np.load(inp)
+    m, n = int(D["m"]), int(D["n"])
+    drv = _drv()
+    gpu.rng_reset()
+    out = drv.APD_SsN_Class2(D["c"], D["r"], D["l"], np.ones(m), np.ones(n), float(D["mu"]), np.ones(m * n))
+    assert out["stats"]["converged"] and out["rel_kkt"] <= 1e-6
+    assert out["outer_its"] == int(T["outer_its"])
+    assert out["stats"]["ssn_its"] == T["ssn_its"].tolist()
+    f, f_ref = out["fxk"][-1], float(T["fxk"][-1])
+    e_f = float(np.max(_rel(out["fxk"], T["fxk"])))
+    e_F = _check_steps(out["stats"]["steps"], T["steps"])
+    x = out["xk"].cpu().numpy()
+    e_x = _check_plan(x, T)
+    assert abs(float(x.sum()) - float(D["mu"])) <= 1e-5 * (1 + float(D["mu"]))        # transported mass = mu (phi = 1)
+    print(f"config 3 fixture (data4-500, {int(T['outer_its'])} outer its): final objective {abs(f - f_ref) / abs(f_ref):.1e}, "
+          f"history {e_f:.1e}, |F| {e_F:.1e}, plan(inf) {e_x:.1e}")
+    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= OBJ_TOL

@@ -271,7 +271,7 @@ def test_standalone_c_program_links_and_fails_loudly_without_a_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_standalone_c_program_on_the_gpu(tmp_path):
+def test_standalone_c_program_on_the_gpu(tmp_path, gpu):
     """The same program on the device against the oracle's warm start (Class1/warmup_class1.m) of the same file."""
     import subprocess
     import oracle

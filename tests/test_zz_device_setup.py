@@ -1,16 +1,12 @@
-"""Device-side setup paths written after the round's GPU budget was spent: SSOR / IC(0) factors and their dependency
-levels built on the device (csrc/trifactor.cu, ``ssn_set_device_setup``) and the assembled KKT matrix
-``ssn_jk_system``.  They are OFF by default in the library; these tests run them against the host construction (bit for
-bit) and the oracle.  Until they have passed once on a B200 they only run with SSN_UNVERIFIED=1, so that the regular
-``-m gpu`` suite keeps testing exactly what has been measured (this file sorts last for the same reason)."""
-import os
-
+"""Device-side setup paths of the non-default solvers: SSOR / IC(0) factors and their dependency levels built on the
+device (csrc/trifactor.cu; the library's default since round 2, ``ssn_set_device_setup(0)`` / SSN_DEVICE_SETUP=0 selects
+the host construction that is kept as the cross-check) and the assembled KKT matrix ``ssn_jk_system``.  These tests run
+them against the host construction (bit for bit) and the oracle."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSN_UNVERIFIED") != "1", reason="device setup paths not yet run on a B200 (set SSN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _systems(oracle):
@@ -50,7 +46,7 @@ def test_device_factors_equal_host_factors(gpu, oracle, precd):
                         {"retol": 1e-11, "maxit": 10, "precd": 4, "guess": None})
             assert "SSN_E_NOT_SPD" in str(e.value)
     finally:
-        gpu.set_device_setup(False)
+        gpu.set_device_setup(True)
 
 
 def test_device_factors_deep_dependency_chain(gpu, oracle):
@@ -69,7 +65,7 @@ def test_device_factors_deep_dependency_chain(gpu, oracle):
             if precd == 4:
                 assert it1 <= 3                                       # IC(0) of a tridiagonal matrix is its exact Cholesky factor
     finally:
-        gpu.set_device_setup(False)
+        gpu.set_device_setup(True)
 
 
 @pytest.mark.parametrize("with_T,drop_diag", [(False, False), (True, False), (True, True)])
@@ -96,17 +92,25 @@ def test_jk_system(gpu, oracle, with_T, drop_diag):
         assert Hc[n + 5, n + 5] == 0 and Jk[n + 5, n + 5] == bk1 + (0.0 if t is None else t[n + 5]) / tk
 
 
-def test_driver_inner_solver_2_with_device_jk(gpu, monkeypatch):
-    """The Class 1 driver with inner_solver = 2 (PCG on Jk) gives the same iterates whether Jk is assembled on the host
-    (default) or by ssn_jk_system."""
+def test_driver_inner_solver_2_runs_pcg_on_the_device_assembled_jk(gpu, oracle):
+    """The Class 1 driver with inner_solver = 2 (Class1/APD_SsN_Class1.m:149-152) assembles Jk with ssn_jk_system: its
+    first Newton direction equals PCG on bk1*speye + (T+H0)/tk formed with SciPy from the same state."""
     import importlib
     drv = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.driver")
     P = gpu.problems.grid_problem(8, seed=0)
     po = {"retol": 1e-11, "maxit": 10000, "precd": 2, "guess": None}
-    run = lambda: drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], inner_solver=2, pcg_options=po, max_outer=5)
-    monkeypatch.delenv("SSN_DEVICE_SETUP", raising=False)
-    gpu.rng_reset(); a = run()
-    monkeypatch.setenv("SSN_DEVICE_SETUP", "1")
-    gpu.rng_reset(); b = run()
-    assert a["fxk"] == b["fxk"]
-    assert np.array_equal(a["xk"].cpu().numpy(), b["xk"].cpu().numpy())
+    seen = []
+
+    def hook(st):
+        if not seen:
+            seen.append({"H0": st["H0"].to_scipy().tocsr(), "Fk": st["Fk"].cpu().numpy().copy(), "bk1": st["bk1"], "tk": st["tk"]})
+    gpu.rng_reset()
+    out = drv.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], inner_solver=2, pcg_options=po, max_outer=2,
+                             on_ssn_step=hook)
+    st = seen[0]
+    N = st["H0"].shape[0]
+    Jk = (st["bk1"] * sp.identity(N, format="csr") + st["H0"] / st["tk"]).tocsc()
+    d_ref, it_ref, _, _ = oracle.PCG(Jk, -st["Fk"], po)
+    d, it, _, _ = gpu.PCG(Jk, -st["Fk"], po)
+    assert abs(it - it_ref) <= 1 and np.linalg.norm(np.asarray(d) - d_ref) <= 1e-8 * np.linalg.norm(d_ref)
+    assert out["stats"]["lin_its"][0][0] == it

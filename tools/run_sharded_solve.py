@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warm-maxit", type=int, default=100)
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--inner-solver", type=int, default=4, help="4 = Hybrid_AMG (reference default), 5 = Hybrid_twogrid")
+    ap.add_argument("--stop-on-amg-divergence", action="store_true", help="end the solve when a W-cycle solve diverges (the reference carries on)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -48,7 +49,8 @@ def main():
     ssnamg.rng_reset()
     res = sd.APD_SsN_Class1_sharded(c_loc, dev(r), dev(l), dev(np.ones(m)), dev(np.ones(n)), rank, world,
                                     dist=dist if world > 1 else None, warm_maxit=args.warm_maxit, max_outer=args.max_outer,
-                                    max_seconds=args.max_seconds, verbose=args.verbose, inner_solver=args.inner_solver)
+                                    max_seconds=args.max_seconds, verbose=args.verbose, inner_solver=args.inner_solver,
+                                    stop_on_amg_divergence=args.stop_on_amg_divergence)
     st = res["stats"]
     peak = torch.cuda.max_memory_allocated() / 2 ** 30
     # ---- slab kernels of the plan operators at this size (CUDA events around the launches, rank-local)
