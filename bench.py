@@ -8,7 +8,8 @@ A "step" is one pass of the hot path (Class1/APD_SsN_Class1.m:137-212 of the ref
   Hybrid_AMG (AMG setup + W-cycles to 1e-11)  ->  Armijo line-search trial(s)  ->  new residual.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
-  python bench.py --impl reference ...                     (the CPU oracle port on the host cores)
+  python bench.py --impl reference ...                     (the CPU oracle port on the host cores: the same step at full
+                                                            size from tests/golden/bench_state_g128_k30.npz, one step, no GPU)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
@@ -84,66 +85,57 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------ CPU oracle arm
 
-def cpu_step_sample(sample, reps=1):
-    """The oracle (CPU port of the reference; MATLAB/Octave are absent) on a bounded sample of the
-    same step: the plan-wide part on a row slab of the plan (scaled to the full plan) -- two
-    residual evaluations (Aty, prox, Ax; APD_SsN_Class1.m:139-144,212), the line-search trials of
-    the step (Aty, prox, norm; :189-211; at most 8 are run and scaled to the step's count) and
-    ASAt -- and the AMG solve on the full (n+m) system.  The plan-wide part runs on ALL host threads
-    (one slab evaluation per thread at the same time: NumPy releases the GIL inside its kernels, so
-    this is the throughput a multi-threaded element-wise implementation such as MATLAB's gets out
-    of the socket); the AMG solve is SciPy's, single-threaded like MATLAB's sparse kernels.
-    Returns full-problem-equivalent ms per step, and the thread count."""
-    import concurrent.futures as cf
-    import oracle
-    from oracle import driver as odrv
-    w, lam, p_s, q = sample["w_slab"], sample["lam_slab"], sample["p_slab"], sample["q"]
-    tk, bk1, scale, trials = sample["tk"], sample["bk1"], sample["scale"], sample["trials"]
-    threads = max(1, os.cpu_count() or 1)
-    run_trials = min(trials, 8)
-
-    def fixed_part(_):
-        for _ev in range(2):                               # residual + active set, new residual
-            z = 1 / tk * (w - oracle.Aty(lam, p_s, q))
-            s = (z >= 0) & (z <= np.inf)
-            px = np.maximum(z, 0.0)
-            oracle.Ax(px, p_s, q); float(px @ px)
-        oracle.ASAt(s, p_s, q)
-
-    def trial_part(_):
-        for _tr in range(run_trials):                      # one Armijo trial: Aty + prox + norm
-            z = 1 / tk * (w - oracle.Aty(lam, p_s, q))
-            px = np.maximum(z, 0.0)
-            float(px @ px)
-
-    t_plan = t_amg = 0.0
-    with cf.ThreadPoolExecutor(max_workers=threads) as pool:
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            list(pool.map(fixed_part, range(threads)))
-            t_fixed = (time.perf_counter() - t0) / threads            # per slab evaluation at full-socket throughput
-            t0 = time.perf_counter()
-            list(pool.map(trial_part, range(threads)))
-            t_trials = (time.perf_counter() - t0) / threads * (trials / max(run_trials, 1))
-            t_plan += t_fixed + t_trials
-            t0 = time.perf_counter()
-            oracle.rng_reset()
-            pd = {"bk1": bk1, "tk": tk, "p": sample["p"], "q": q, "T": sample["T"], "H0": sample["H0"], "z": sample["z"]}
-            oracle.Hybrid_AMG(pd, odrv.CLASS1_AMG_OPTIONS)
-            t_amg += time.perf_counter() - t0
-    return 1e3 * (scale * t_plan + t_amg) / reps, 1e3 * scale * t_plan / reps, 1e3 * t_amg / reps, threads
+FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_state_g{g}_k{k}.npz")
 
 
-def make_cpu_sample(state, H0_scipy, z_host, m, n, slab_rows, trials):
-    import scipy.sparse as sp
-    import torch
-    wk = state["wk"].view(n, m)                             # column-major m x n == row-major n x m
-    w_slab = wk[:, :slab_rows].contiguous().cpu().numpy().reshape(-1)      # column-major slab (slab_rows x n)
-    lam = state["lk"].cpu().numpy()
-    lam_slab = np.concatenate([lam[:n], lam[n:n + slab_rows]])
-    return {"w_slab": w_slab, "lam_slab": lam_slab, "wlk": state["wlk"].cpu().numpy(), "p_slab": np.ones(slab_rows),
-            "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "scale": m / slab_rows, "trials": int(trials),
-            "T": sp.diags(np.zeros(m + n)), "H0": H0_scipy.tocsc(), "z": z_host}
+def load_problems_module():
+    """problems.py (NumPy only) loaded by path: the CPU arm never imports the product package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ssn_problems", os.path.join(ROOT, "codes-of-ipd-ssn-amg-method_b200", "problems.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_step_full(host_state):
+    """The oracle (CPU port of the reference; MATLAB/Octave are absent) on the SAME step at FULL size: the whole
+    m x n plan, every line-search trial, nothing sampled or scaled (oracle/bench_step.py).  Returns
+    (ms, info, sample text)."""
+    from oracle import bench_step
+    ms, lk_new, Fk_new, info = bench_step.timed_step(host_state)
+    ph = info["phases_s"]
+    txt = (f"oracle (NumPy/SciPy port of the reference; MATLAB/Octave absent), the WHOLE step once, nothing sampled or extrapolated: "
+           f"{host_state['m']}x{host_state['n']} plan, residual + active set {ph['residual_s']:.1f} s, ASAt {ph['asat_s']:.1f} s, "
+           f"Hybrid_AMG on the {host_state['m'] + host_state['n']}-node system {ph['hybrid_amg_s']:.1f} s (single-threaded SciPy), all "
+           f"{info['ll'] + 1} Armijo trials {ph['line_search_s']:.1f} s, new residual {ph['new_residual_s']:.1f} s; plan-wide expressions "
+           f"on {info['threads']} column blocks at the same time ({info['threads']} host threads)")
+    return ms, lk_new, Fk_new, info, txt
+
+
+def device_state_from_fixture(torch, ssnamg, path, P):
+    """The benchmarked APD state on the device, from the fixture's sparse plans (Class1/APD_SsN_Class1.m:113-126)."""
+    d = np.load(path)
+    m, n = int(d["m"]), int(d["n"])
+    ak, bk = float(d["ak"]), float(d["bk"])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    xk = torch.zeros(m * n, dtype=torch.float64, device="cuda"); xk[dev(d["xk_idx"])] = dev(d["xk_val"])
+    vk = torch.zeros(m * n, dtype=torch.float64, device="cuda"); vk[dev(d["vk_idx"])] = dev(d["vk_val"])
+    p = dev(P["p"]); q = dev(P["q"]); c = dev(P["c"])
+    wk, axk = ssnamg.apd_begin(c, xk, vk, p, q, ak, bk)                 # :125 and Ax(xk) of :126
+    del xk, vk, c
+    b = dev(np.concatenate([P["r"], P["l"]]))
+    lk = dev(d["lk"])
+    bk1, tk = float(d["bk1"]), float(d["tk"])
+    wlk = bk1 * (lk - 1 / bk * (axk - b)) - b                           # :126
+    return {"wk": wk, "lk": lk, "wlk": wlk, "bk1": bk1, "tk": tk, "k": int(d["k"]), "ssn_it": int(d["ssn_it"]), "p": p, "q": q,
+            "gama": float("inf"), "E": int(d["expect_E"])}
+
+
+def step_config(workload, info, n_ll):
+    """What both arms report under `config`: the workload and the discrete facts of the step, which the device
+    path and the CPU oracle compute independently (equal dictionaries = the two arms did the same work)."""
+    return {"workload": workload, "E_active": int(info["E"]), "nnz_H0": int(info["nnzH"]), "amg_cycles": int(info["itamg"]),
+            "components": int(info["components"]), "line_search_trials": int(n_ll) + 1,
+            "l2_flush": "inputs larger than L2 (2.1 GB plan vector per pass)"}
 
 
 # ------------------------------------------------------------------------------ main
@@ -156,13 +148,13 @@ def main():
     global _REAL_STDOUT
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
-    import torch
-    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        return 0 if rank != 0 else run_reference(args)
+    import torch
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -175,24 +167,29 @@ def main():
     m = n = g * g
     peak, peak_src = peaks()
 
-    # ---- the APD state of the benchmarked step (identical on every rank: deterministic solve)
+    # ---- the APD state of the benchmarked step: rebuilt on the device from the committed fixture (the same file the CPU
+    # arm reads; tests/test_gpu_traces.py checks that the device solve passes through exactly this state); without the
+    # fixture the solve is run up to that step.  Identical on every rank.
     t0 = time.time()
     P = ssnamg.problems.grid_problem(g, seed=0)
-    ssnamg.rng_reset()
-    full = None
-    if args.impl == "ours" and world == 1 and not args.no_full_solve:
-        # the whole Class1 solve (the metric's "solve time"), with the benchmarked state captured on the way
-        state, full = drv.capture_state(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], outer=args.state_outer, ssn_it=1,
-                                        run_to_end=True)
+    fixture = FIXTURE.format(g=g, k=args.state_outer)
+    if os.path.exists(fixture):
+        state = device_state_from_fixture(torch, ssnamg, fixture, P)
+        state_src = os.path.relpath(fixture, ROOT)
     else:
+        ssnamg.rng_reset()
         state = drv.capture_state(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], outer=args.state_outer, ssn_it=1)
-    del P
+        state_src = "device solve run up to the step (fixture missing)"
     torch.cuda.synchronize()
     t_state = time.time() - t0
+    full = None
+    if world == 1 and not args.no_full_solve:
+        # the whole Class 1 solve (the metric's "solve time") through the library's one-call entry point ssn_apd_ssn_class1
+        ssnamg.rng_reset()
+        full = ssnamg.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"])
+        full.pop("xk", None); torch.cuda.empty_cache()
+    del P
     workload = f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}_outer{state['k']}_ssn{state['ssn_it']}"
-
-    if args.impl == "reference":
-        return run_reference(args, state, m, n, workload)
 
     if world > 1:
         from importlib import import_module
@@ -272,10 +269,9 @@ def main():
     out = {"metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "ours",
-           "config": {"workload": workload, "E_active": int(info["E"]), "nnz_H0": int(info["nnzH"]), "amg_cycles": int(info["itamg"]),
-                      "components": int(info["info"][0]), "line_search_trials": int(info["ll"]) + 1, "line_search_passes": int(info.get("ls_passes", 0)),
-                      "l2_flush": "inputs larger than L2 (2.1 GB plan vector per pass)", "state_build_s": round(t_state, 1),
-                      "sharding": "plan rows over ranks; AMG replicated" if world > 1 else "single GPU"},
+           "config": step_config(workload, dict(info, components=info["info"][0]), info["ll"]),
+           "run": {"line_search_passes": int(info.get("ls_passes", 0)), "state_build_s": round(t_state, 1), "state_source": state_src,
+                   "sharding": "plan rows over ranks; AMG replicated" if world > 1 else "single GPU"},
            "breakdown_ms": {"plan_wide_kernels_and_collectives": info.get("ms_plan"), "asat_assembly": info.get("ms_asat"),
                             "hybrid_amg_replicated": info.get("ms_amg"),
                             "note": "host-timed phases of the last step (each closed by a device synchronise): the plan-wide "
@@ -338,23 +334,23 @@ def main():
             out["full_solve"] = {"total_s": full["seconds"] + full["warmup_seconds"], "loop_s": full["seconds"],
                                  "warmup_s": full["warmup_seconds"], "outer_its": full["outer_its"], "converged": bool(fs["converged"]),
                                  "rel_kkt": full["rel_kkt"], "objective": full["fxk"][-1], "ssn_steps": int(sum(fs["ssn_its"])),
+                                 "entry_point": "ssn_apd_ssn_class1 (one library call: warm start + outer loop + SsN steps)",
                                  "line_search_trials": int(fs["ls_trials"]), "amg_solves": int(fs["amg_calls"]),
                                  "amg_s": fs["solve_s"], "plan_s": fs["plan_s"], "asat_s": fs["asat_s"],
-                                 "note": "Class1/APD_SsN_Class1.m with its own limits (maxit = 100 outer iterations, KKT_Tol 1e-6)"}
+                                 "status": ("converged to rel-KKT <= 1e-6" if fs["converged"] else
+                                            f"STOPPED AT maxit = {full['outer_its']} outer iterations (Class1/APD_SsN_Class1.m:35), NOT converged: "
+                                            f"rel-KKT {full['rel_kkt']:.1e} > KKT_Tol 1e-6"),
+                                 "note": "Class1/APD_SsN_Class1.m with its own limits (maxit = 100 outer iterations, KKT_Tol 1e-6); a time to "
+                                         "the iteration cap is not a time to solution"}
         if not args.no_cpu_baseline:
-            ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
-            H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
-            z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
-            slab = max(64, m // 32)
-            trials = int(info["ll"]) + 1
-            sample = make_cpu_sample(state, H0, z_host, m, n, slab, trials)
-            cpu_ms, cpu_plan, cpu_amg, cpu_threads = cpu_step_sample(sample)
-            out["cpu_baseline"] = {"value": cpu_ms, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                                   "sample": f"oracle (NumPy/SciPy port; MATLAB/Octave absent): plan-wide part (2 residual "
-                                             f"evaluations, ASAt, {trials} line-search trials of which at most 8 are run and scaled) "
-                                             f"on a {slab}-row slab of the {m}x{n} plan, one evaluation per host thread at the same time "
-                                             f"({cpu_threads} threads), scaled x{m // slab} to the full plan ({cpu_plan:.0f} ms), AMG "
-                                             f"solve on the full {m + n}-node system, single-threaded SciPy ({cpu_amg:.0f} ms)"}
+            host_state = {"wk": state["wk"].cpu().numpy(), "lk": state["lk"].cpu().numpy(), "wlk": state["wlk"].cpu().numpy(),
+                          "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "m": m, "n": n}
+            del state["wk"]; torch.cuda.empty_cache()
+            cpu_ms, lk_cpu, Fk_cpu, cinfo, cpu_txt = cpu_step_full(host_state)
+            out["cpu_baseline"] = {"value": cpu_ms, "unit": UNIT, "cores": cinfo["threads"], "kind": "port", "sample": cpu_txt,
+                                   "same_step_as_device": {"config_equal": step_config(workload, cinfo, cinfo["ll"]) == out["config"],
+                                                           "lk_new_max_rel_diff": float(np.max(np.abs(lk_cpu - lk_new.cpu().numpy())) / np.max(np.abs(lk_cpu))),
+                                                           "Fk_new_norm_cpu": cinfo["Fk_new_norm"], "Fk_new_norm_device": info["Fk_new_norm"]}}
     if rank == 0:
         emit(out)
     if world > 1:
@@ -437,34 +433,39 @@ def secondary_metrics(ssnamg, drv, state, m, n):
             "hybrid_amg_ms": dta * 1e3, "wcycles_per_s_incl_setup": itamg / dta}
 
 
-def run_reference(args, state, m, n, workload):
-    """--impl reference: the reference's CPU path (oracle port; MATLAB/Octave are absent) on the host cores."""
-    import torch
-    import ssnamg
-    ev = ssnamg.prox_residual(state["wk"], state["lk"], state["p"], state["q"], state["tk"], float("inf"), want=("Axprox", "s"))
-    H0 = ssnamg.ASAt(ev["s"], state["p"], state["q"]).to_scipy()
-    z_host = (-(state["bk1"] * state["lk"] - ev["Axprox"] - state["wlk"])).cpu().numpy()
-    slab = max(64, m // 32)
-    ssnamg.rng_reset()
-    _, _, info = ssnamg.driver.ssn_step(state)               # only to learn the step's line-search length
-    trials = int(info["ll"]) + 1
-    sample = make_cpu_sample(state, H0, z_host, m, n, slab, trials)
-    del state; torch.cuda.empty_cache()
-    for _ in range(min(args.warmup, 1)):
-        cpu_step_sample(sample)
-    steps = max(1, min(args.steps, 3))
-    vals = [cpu_step_sample(sample) for _ in range(steps)]
-    ms = float(np.mean([v[0] for v in vals]))
-    threads = vals[0][3]
-    sample_txt = (f"oracle (NumPy/SciPy port of the reference; MATLAB/Octave absent): plan-wide part (2 residual evaluations, "
-                  f"ASAt, {trials} line-search trials of which at most 8 are run and scaled) on a {slab}-row slab of the {m}x{n} "
-                  f"plan, one evaluation per host thread at the same time ({threads} threads), scaled x{m // slab} to the full plan; "
-                  f"AMG solve on the full {m + n}-node system, single-threaded SciPy")
-    out = {"metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+def run_reference(args):
+    """--impl reference: the reference's CPU path (the oracle port; MATLAB/Octave are absent) on the host cores --
+    the SAME step at full size, built from the committed state fixture and the problem generator only.  This
+    process never imports torch or the product package and never loads libssnamg.so; nothing is sampled or
+    extrapolated, so it runs ONE step whatever --steps / --warmup say, and says so."""
+    g = args.grid
+    m = n = g * g
+    fixture = FIXTURE.format(g=g, k=args.state_outer)
+    if not os.path.exists(fixture):
+        emit({"impl": "reference", "unavailable": f"state fixture {os.path.relpath(fixture, ROOT)} missing (tools/save_bench_state.py writes it on a B200)"})
+        return 0
+    from oracle import bench_step
+    t0 = time.time()
+    P = load_problems_module().grid_problem(g, seed=0)
+    st = bench_step.state_from_fixture(fixture, P)
+    del P
+    t_state = time.time() - t0
+    workload = f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}_outer{st['k']}_ssn{st['ssn_it']}"
+    ms, lk_new, Fk_new, info, txt = cpu_step_full(st)
+    ex = st["expect"]
+    check = {"device_step_recorded_in_fixture": {k: (int(v) if np.ndim(v) == 0 and float(v).is_integer() else float(v)) for k, v in ex.items() if np.ndim(v) == 0}}
+    if "lk_new" in ex:
+        check["lk_new_max_rel_diff_vs_device"] = float(np.max(np.abs(lk_new - ex["lk_new"])) / np.max(np.abs(ex["lk_new"])))
+    if "wlk" in ex:
+        check["wlk_max_rel_diff_vs_device"] = float(np.max(np.abs(st["wlk"] - ex["wlk"])) / np.max(np.abs(ex["wlk"])))
+    out = {"metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "impl": "reference", "config": {"workload": workload},
-           "cpu_baseline": {"value": ms, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
-           "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "data": "synthetic", "impl": "reference", "config": step_config(workload, info, info["ll"]),
+           "run": {"state_build_s": round(t_state, 1), "requested_steps": args.steps, "requested_warmup": args.warmup,
+                   "note": "one full-size step is about two minutes of host time: it is run ONCE, not sampled and scaled"},
+           "cpu_baseline": {"value": ms, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": txt},
+           "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "parity_with_device_step": check}
     emit(out)
     return 0
 

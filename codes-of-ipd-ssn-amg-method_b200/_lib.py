@@ -47,6 +47,19 @@ class ProbData(C.Structure):
                 ("H0", C.POINTER(CSR)), ("z_dev", C.c_void_p), ("s_dev", C.c_void_p), ("phi_dev", C.c_void_p)]
 
 
+class ApdOptions(C.Structure):
+    _fields_ = [("inner_solver", C.c_int32), ("maxit", C.c_int32), ("KKT_Tol", C.c_double), ("warm_maxit", C.c_int32),
+                ("max_outer", C.c_int32), ("max_seconds", C.c_double), ("verbose", C.c_int32),
+                ("amg", C.POINTER(AmgOptions)), ("pcg", C.POINTER(PcgOptions))]
+
+
+class ApdResult(C.Structure):
+    _fields_ = [("outer_its", C.c_int32), ("converged", C.c_int32), ("rel_kkt", C.c_double), ("objective", C.c_double),
+                ("ssn_steps", C.c_int32), ("ls_trials", C.c_int32), ("ls_passes", C.c_int32), ("amg_calls", C.c_int32),
+                ("warmup_s", C.c_double), ("loop_s", C.c_double), ("solve_s", C.c_double), ("asat_s", C.c_double),
+                ("plan_s", C.c_double), ("hist_len", C.c_int32), ("steps_len", C.c_int64)]
+
+
 # every symbol include/ssnamg.h declares, with its ctypes signature
 _vp, _i64, _i32, _dbl, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int
 _pcsr, _pint, _pdbl, _pi64 = C.POINTER(CSR), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int64)
@@ -70,6 +83,7 @@ SIGNATURES = {
     "ssn_kernel_timer_read": (_int, [_vp, _pdbl, _pi64]),
     "ssn_profile_dump": (C.c_char_p, [_vp]),
     "ssn_debug_cycles": (_int, [_vp, _vp, _int]),
+    "ssn_debug_cycles_persist": (_int, [_vp, _vp, _int]),
     "ssn_rng_reset": (_int, [_vp, C.c_uint32]),
     "ssn_rng_drawn": (_i64, [_vp]),
     "ssn_rand": (_int, [_vp, _i64, _vp]),
@@ -97,6 +111,10 @@ SIGNATURES = {
     "ssn_trial_vectors": (_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp]),
     "ssn_linesearch": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _int, _dbl, _dbl,
                               _int, _vp, C.POINTER(_int), _pdbl, _pdbl, C.POINTER(_int)]),
+    "ssn_apd_ssn_class1": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, C.POINTER(ApdOptions), _vp, _vp,
+                                  C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _vp, _i64]),
+    "ssn_apd_ssn_class1_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, C.POINTER(ApdOptions), _vp, _vp,
+                                       C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _vp, _i64]),
     "ssn_asat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_asat_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_active_coo": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_vp), _pi64]),

@@ -273,6 +273,48 @@ def prox_trials_lin(w, lam, zeta, p, q, tk, delta, ll0, nt):
     return out
 
 
+def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100, max_outer=None,
+                   max_seconds=None, verbose=False, amg_options=None, pcg_options=None, host_call=False):
+    """The reference's Class 1 script (Class1/APD_SsN_Class1.m:32-275 + Class1/warmup_class1.m) as ONE call into the
+    library (``ssn_apd_ssn_class1``): warm start, APD outer loop, SsN inner loop, line search, KKT bookkeeping, with no
+    Python between the kernels.  ``host_call=True`` goes through ``ssn_apd_ssn_class1_host`` with NumPy arrays (inputs
+    copied to the device once, plan and duals copied back once).  Returns the dictionary of ``driver.APD_SsN_Class1``."""
+    from ._lib import ApdOptions, ApdResult
+    torch = _torch(); ctx = context()
+    keep = []
+    ao = _amg_options(amg_options, keep); po = _pcg_options(pcg_options, keep)
+    o = ApdOptions(inner_solver=int(inner_solver), maxit=int(maxit), KKT_Tol=float(KKT_Tol), warm_maxit=int(warm_maxit),
+                   max_outer=int(max_outer or 0), max_seconds=float(max_seconds or 0.0), verbose=1 if verbose else 0,
+                   amg=C.pointer(ao) if ao is not None else None, pcg=C.pointer(po) if po is not None else None)
+    res = ApdResult()
+    hist = np.zeros((3, int(maxit) + 1)); its = np.zeros(int(maxit), dtype=np.int32)
+    cap = 64 * int(maxit)
+    steps = np.zeros((cap, 7))
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    if host_call:
+        f = lambda a: np.ascontiguousarray(np.asarray(a.cpu() if hasattr(a, "cpu") else a, dtype=np.float64).reshape(-1))
+        ch, rh, lh, ph, qh = f(c), f(r), f(l), f(p), f(q); m, n = ph.size, qh.size
+        scalar = np.isscalar(gama) or np.size(gama) == 1
+        gh = None if scalar else f(gama)
+        xk = np.empty(m * n); lk = np.empty(m + n)
+        ctx.call("ssn_apd_ssn_class1_host", hp(ch), hp(rh), hp(lh), hp(ph), hp(qh), m, n, hp(gh) if gh is not None else None,
+                 float(gama) if scalar else float("inf"), C.byref(o), hp(xk), hp(lk), C.byref(res), hp(hist[0]), hp(hist[1]), hp(hist[2]),
+                 hp(its), hp(steps), cap)
+    else:
+        pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+        cd = _dev(c, count=m * n); rd = _dev(r, count=n); ld = _dev(l, count=m)
+        gvec, gs = _gama_args(gama, m, n)
+        xk = torch.empty(m * n, dtype=torch.float64, device="cuda"); lk = torch.empty(n + m, dtype=torch.float64, device="cuda")
+        ctx.call("ssn_apd_ssn_class1", _ptr(cd), _ptr(rd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, _ptr(gvec), gs, C.byref(o), _ptr(xk), _ptr(lk),
+                 C.byref(res), hp(hist[0]), hp(hist[1]), hp(hist[2]), hp(its), hp(steps), cap)
+    L = res.hist_len; ns = min(int(res.steps_len), cap)
+    stats = {"ssn_its": its[:res.outer_its].tolist(), "ls_trials": res.ls_trials, "ls_passes": res.ls_passes, "converged": bool(res.converged),
+             "amg_calls": res.amg_calls, "warmup_s": res.warmup_s, "solve_s": res.solve_s, "asat_s": res.asat_s, "plan_s": res.plan_s,
+             "steps": [tuple(row) for row in steps[:ns].tolist()]}
+    return {"xk": xk, "lk": lk, "fxk": hist[0, :L].tolist(), "KKT_xk": hist[1, :L].tolist(), "KKT_lk": hist[2, :L].tolist(),
+            "outer_its": res.outer_its, "rel_kkt": res.rel_kkt, "stats": stats, "seconds": res.loop_s, "warmup_seconds": res.warmup_s}
+
+
 def warmup_class1(c, r, l, p, q, gama=np.inf, res=None, maxit=None):
     """``[xk,lk] = warmup_class1(c,r,l,p,q,gama,res,maxit)`` -- reference Class1/warmup_class1.m:2-96
     (A-ADMM warm start), device resident.  ``nargin`` rules of :3-20: ``res`` defaults to 1e-1 and

@@ -100,6 +100,7 @@ void build_tri_factors_device(ssn_ctx* c, const CsrView& H, int precd, TriFactor
 void jk_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Jk);
 
 void debug_cycles(unsigned long long* out64, bool reset);
+void debug_cycles_persist(unsigned long long* out256, bool reset);
 double barrier_bench(ssn_ctx* c, int iters, int which);
 void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
 

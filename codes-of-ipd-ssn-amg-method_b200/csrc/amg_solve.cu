@@ -192,8 +192,11 @@ constexpr int kBT = 4;                                    // lanes per row insid
 // cycle counters of the single-block kernel (development aid; read through ssn_debug_cycles)
 __device__ unsigned long long g_dbg_cycles[64];
 #define DBG_T0() const long long dbg_t0 = clock64()
+// per (operation, level) cycle counters of the persistent solve kernels: [op*16 + level] cycles, [128 + op*16 + level] calls
+// (op: 0 resid, 1 gs_apply, 2 jacobi, 3 spmv, 4 dense, 7 whole kernel); built with -DSSN_PERSIST_DEBUG only
+__device__ unsigned long long g_pdbg[256];
 #ifdef SSN_PERSIST_DEBUG
-#define PDBG(slot, call) do { const long long t0__ = clock64(); call; if (blockIdx.x == 0 && threadIdx.x == 0) { g_dbg_cycles[(slot)] += (unsigned long long)(clock64() - t0__); g_dbg_cycles[32 + (slot)] += 1ull; } } while (0)
+#define PDBG(slot, call) do { const long long t0__ = clock64(); call; if (blockIdx.x == 0 && threadIdx.x == 0) { g_pdbg[((slot) - 25) * 16 + dbg_level__] += (unsigned long long)(clock64() - t0__); g_pdbg[128 + ((slot) - 25) * 16 + dbg_level__] += 1ull; } } while (0)
 #else
 #define PDBG(slot, call) do { call; } while (0)
 #endif
@@ -1116,6 +1119,7 @@ struct PersistArgs {
     int* it_out;                  // [0] = it, [1] = history length
     int tpr[kPLevels];            // lanes per row of A_k (k < kd)
     int tpr_p[kPLevels];          // lanes per row of Pro_k / Pro_k' (k <= kd)
+    int tpr_gs;                   // lanes per row of the coupled block Gauss-Seidel update (0: tpr[0])
     size_t smem_budget;           // dynamic shared memory available for staged matrix slices
 };
 
@@ -1124,15 +1128,17 @@ struct PersistArgs {
 struct PSlice {
     int r0, r1, rbase; const int* rp; const int* ci; const double* cv;
     int inter;     // 1: rows interleaved over the whole grid (in-place matrices only); 0: the block's contiguous slice
-    __device__ __forceinline__ int first(int rows_per_pass) const { return inter ? (int)blockIdx.x * rows_per_pass : r0; }
-    __device__ __forceinline__ int step(int rows_per_pass) const { return inter ? (int)gridDim.x * rows_per_pass : rows_per_pass; }
+    __device__ __forceinline__ int first(int rows_per_pass, int blk) const { return inter ? blk * rows_per_pass : r0; }
+    __device__ __forceinline__ int step(int rows_per_pass, int nblk) const { return inter ? nblk * rows_per_pass : rows_per_pass; }
 };
 struct PLevelS { PSlice A, Pu, Td; };      // A_t ; Pro_{t+1} (rows of level t) ; Pro_t' (rows of level t)
 
-__device__ void stage_slice(PSlice* S, int N, const int* ptr, const int* idx, const double* val, unsigned char* smem,
+template <class TM>
+__device__ void stage_slice(const TM& G, PSlice* S, int N, const int* ptr, const int* idx, const double* val, unsigned char* smem,
                             size_t& used, size_t budget) {
-    const int rpb = (N + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int r0 = min(N, (int)blockIdx.x * rpb), r1 = min(N, r0 + rpb);
+    constexpr int kPT = TM::T;
+    const int rpb = (N + G.nblk() - 1) / G.nblk();
+    const int r0 = min(N, G.blk() * rpb), r1 = min(N, r0 + rpb);
     const int nrows = r1 - r0;
     const int base = (ptr && nrows > 0) ? ptr[r0] : 0;
     const int cnt = (ptr && nrows > 0) ? (ptr[r1] - base) : 0;
@@ -1175,6 +1181,7 @@ __device__ __forceinline__ double row_dot_s(const PSlice& S, const double* x, in
 template <class F>
 __device__ __forceinline__ void with_tpr(int tpr, F&& f) {
     switch (tpr) {
+        case 1: f(std::integral_constant<int, 1>()); break;
         case 2: f(std::integral_constant<int, 2>()); break;
         case 4: f(std::integral_constant<int, 4>()); break;
         case 8: f(std::integral_constant<int, 8>()); break;
@@ -1213,8 +1220,19 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) barrier_bench_kernel(unsig
     if (blockIdx.x == 0 && threadIdx.x == 0) cycles_out[0] = clock64() - t0;
 }
 
-struct PGrid {
+// The "team" that runs the persistent solve body: either the whole cooperative grid (GridTeam, one grid barrier per
+// dependent pass) or ONE thread-block cluster (ClusterTeam: hardware cluster barrier, reductions through distributed
+// shared memory).  Same interface: T threads per block, blk() / nblk(), sync(), sum2().
+struct GridTeam {
+    static constexpr int T = kPT;
+    static constexpr int U = 1;               // rows per thread in flight (row_dots)
     cg::grid_group grid; double* part; double* red; int flip;
+    double* xs = nullptr;
+    // vectors that change during the kernel are read from L2, never through a stale L1 line
+    static __device__ __forceinline__ double ld(const double* p) { return __ldcg(p); }
+    __device__ __forceinline__ int blk() const { return (int)blockIdx.x; }
+    __device__ __forceinline__ int nblk() const { return (int)gridDim.x; }
+    __device__ __forceinline__ void sync() { grid.sync(); }
     // grid-wide sums of two per-thread values; one grid barrier; results identical in every thread
     __device__ __forceinline__ void sum2(double& a, double& b) {
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1246,76 +1264,195 @@ struct PGrid {
     }
 };
 
+#ifndef SSN_CTT
+#define SSN_CTT 1024
+#endif
+#ifndef SSN_CU
+#define SSN_CU 4
+#endif
+constexpr int kCTT = SSN_CTT;                 // threads per CTA of the cluster-resident solve kernel
+constexpr int kCMax = 16;                     // largest cluster (non-portable size, opt-in)
+
+__device__ __forceinline__ void cluster_barrier() {
+    // release / acquire at cluster scope: every global and shared::cluster write made before the barrier by any
+    // CTA of the cluster is visible to every thread of the cluster after it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct ClusterTeam {
+    static constexpr int T = kCTT;
+    static constexpr int U = SSN_CU;          // rows per thread in flight: 16 SMs carry the whole level, so a pass is bound by
+                                              // the L2 round trips a thread can overlap, not by the barrier
+    double* red;                              // [2][64] warp partials of this CTA
+    double* slots;                            // [2][2*kCMax]: slot r of every CTA is written by CTA r through DSMEM
+    int rank, ncta, flip;
+    double* xs;                               // 2048 doubles: the input vector of the dense tail operator
+    // Plain (L1-cached) loads: every pass ends in a cluster barrier with release / acquire semantics, for which the
+    // compiler emits CCTL.IVALL -- the L1 is invalidated at every barrier, so a line can only have been filled after
+    // the last write to it by another CTA, and the gathers of a row slice, which mostly hit the slice's own
+    // neighbourhood, are served by the L1 instead of one L2 sector request each.
+    static __device__ __forceinline__ double ld(const double* p) { return *p; }      // ld.global (not .volatile / .cg / .nc)
+    __device__ __forceinline__ int blk() const { return rank; }
+    __device__ __forceinline__ int nblk() const { return ncta; }
+    __device__ __forceinline__ void sync() { cluster_barrier(); }
+    // cluster-wide sums of two per-thread values; ONE cluster barrier, no trip through L2; fixed order
+    __device__ __forceinline__ void sum2(double& a, double& b) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        a = warp_sum(a); b = warp_sum(b);
+        double* sm = red + (flip & 1) * 64;
+        if (lane == 0) { sm[w] = a; sm[32 + w] = b; }
+        __syncthreads();
+        double* sl = slots + (flip & 1) * (2 * kCMax);
+        if (w == 0) {
+            double ta = (lane < T / 32) ? sm[lane] : 0.0, tb = (lane < T / 32) ? sm[32 + lane] : 0.0;
+            ta = warp_sum(ta); tb = warp_sum(tb);
+            if (lane < ncta) {
+                cg::cluster_group cl = cg::this_cluster();
+                double* remote = cl.map_shared_rank(sl + 2 * rank, lane);
+                remote[0] = ta; remote[1] = tb;
+            }
+        }
+        cluster_barrier();
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r < ncta; ++r) { s0 += sl[2 * r]; s1 += sl[2 * r + 1]; }
+        a = s0; b = s1;
+        ++flip;
+    }
+};
+
+// d[u] = A(row_u,:)*x for the U rows row0 + u*RP of a thread (TPR lanes per row), all U rows in flight at once: every
+// round issues one index/value load and one gather per row before any of them is consumed, so a thread has U
+// independent L2 round trips outstanding instead of one.  U == 1 keeps the 4-deep batching inside the row.
+template <int TPR, int U, class TM>
+__device__ __forceinline__ void row_dots(const PSlice& S, const double* x, int row0, int RP, int sub, double (&d)[U]) {
+    if constexpr (U == 1) {
+        d[0] = row_dot_s<TPR>(S, x, row0, sub, row0 < S.r1);
+    } else {
+        int e[U], e1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = row0 + u * RP;
+            const bool valid = row < S.r1;
+            e[u] = valid ? S.rp[row - S.rbase] + sub : 0; e1[u] = valid ? S.rp[row - S.rbase + 1] : 0; d[u] = 0.0;
+        }
+        bool more;
+        do {
+            int i[U]; double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const bool has = e[u] < e1[u]; i[u] = has ? S.ci[e[u]] : -1; v[u] = has ? S.cv[e[u]] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = (i[u] >= 0) ? TM::ld(x + i[u]) : 0.0;
+            more = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { d[u] = fma(v[u], xv[u], d[u]); e[u] += TPR; more |= (e[u] < e1[u]); }
+        } while (more);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+    }
+}
+
 // g = r - A e on the block's rows (e == nullptr: g = r); sum g and sum g^2 when want (else just the barrier)
-__device__ void p_resid(PGrid& G, const PSlice& S, int tpr, const double* r, const double* e, double* g, bool want,
+template <class TM>
+__device__ void p_resid(TM& G, const PSlice& S, int tpr, const double* r, const double* e, double* g, bool want,
                         double& sg, double& sg2) {
     sg = 0.0; sg2 = 0.0;
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
+        constexpr int U = TM::U, RP = TM::T / TPR;
         const int sub = threadIdx.x % TPR;
-        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
-            const int row = base + threadIdx.x / TPR;
-            const bool valid = row < S.r1;
-            double ri = 0.0;
-            if (valid && sub == 0) ri = __ldcg(r + row);
-            double d = 0.0;
-            if (e != nullptr) d = row_dot_s<TPR>(S, e, row, sub, valid);
-            if (valid && sub == 0) { const double gi = ri - d; g[row] = gi; sg += gi; sg2 = fma(gi, gi, sg2); }
+        for (int base = S.first(U * RP, G.blk()); base < S.r1; base += S.step(U * RP, G.nblk())) {
+            const int row0 = base + threadIdx.x / TPR;
+            double d[U];
+            if (e != nullptr) row_dots<TPR, U, TM>(S, e, row0, RP, sub, d);
+            else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) d[u] = 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * RP;
+                if (row < S.r1 && sub == 0) { const double gi = TM::ld(r + row) - d[u]; g[row] = gi; sg += gi; sg2 = fma(gi, gi, sg2); }
+            }
         }
     });
-    if (want) G.sum2(sg, sg2); else G.grid.sync();
+    if (want) G.sum2(sg, sg2); else G.sync();
 }
 
 // block Gauss-Seidel coupled update (Class_AMG.m:56-59 / MG_Wcycle.m:19,37): e (+)= coef + R(g - Axi*coef)
-__device__ void p_gs_apply(PGrid& G, const LevelDev& L, const PSlice& S, int tpr, const double* g, double* e, double coef, int post,
+template <class TM>
+__device__ void p_gs_apply(TM& G, const LevelDev& L, const PSlice& S, int tpr, const double* g, double* e, double coef, int post,
                            bool e_zero) {
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
         const int sub = threadIdx.x % TPR;
-        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
+        for (int base = S.first(TM::T / TPR, G.blk()); base < S.r1; base += S.step(TM::T / TPR, G.nblk())) {
             const int row = base + threadIdx.x / TPR;
             const bool valid = row < S.r1;
             double hi = 0.0, di = 0.0;
-            if (valid) { hi = __ldcg(g + row) - L.Axi[row] * coef; di = L.dinv[row]; }
+            if (valid) { hi = TM::ld(g + row) - L.Axi[row] * coef; di = L.dinv[row]; }
             double s = 0.0;
             const bool coupled = valid && (post ? (row < L.Nf) : (row >= L.Nf));
             if (coupled) {
+                // 4 entries per batch: all index loads, then all gathers, then the arithmetic (one dependent L2 round
+                // trip per batch instead of one per entry)
                 const int e1 = S.rp[row - S.rbase + 1];
-                for (int q = S.rp[row - S.rbase] + sub; q < e1; q += TPR) {
+                int q = S.rp[row - S.rbase] + sub;
+                for (; q + 3 * TPR < e1; q += 4 * TPR) {
+                    int j[4]; double av[4], gj[4], dj[4], xj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { j[u] = S.ci[q + u * TPR]; av[u] = S.cv[q + u * TPR]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { gj[u] = TM::ld(g + j[u]); dj[u] = L.dinv[j[u]]; xj[u] = L.Axi[j[u]]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool other = post ? (j[u] >= L.Nf) : (j[u] < L.Nf);
+                        if (other) s = fma(av[u], dj[u] * (gj[u] - xj[u] * coef), s);
+                    }
+                }
+                for (; q < e1; q += TPR) {
                     const int j = S.ci[q];
                     const bool other = post ? (j >= L.Nf) : (j < L.Nf);
-                    if (other) s = fma(S.cv[q], L.dinv[j] * (__ldcg(g + j) - L.Axi[j] * coef), s);
+                    if (other) s = fma(S.cv[q], L.dinv[j] * (TM::ld(g + j) - L.Axi[j] * coef), s);
                 }
             }
 #pragma unroll
             for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const double inc = coef + di * (hi - s);
-            if (valid && sub == 0) e[row] = e_zero ? inc : (__ldcg(e + row) + inc);
+            if (valid && sub == 0) e[row] = e_zero ? inc : (TM::ld(e + row) + inc);
         }
     });
-    G.grid.sync();
+    G.sync();
 }
 
 // one fused damped-Jacobi step (kernel correction through coef); returns Axi'ealt
-__device__ double p_jacobi(PGrid& G, const LevelDev& L, const PSlice& S, int tpr, const double* r, const double* ecur, double* ealt,
+template <class TM>
+__device__ double p_jacobi(TM& G, const LevelDev& L, const PSlice& S, int tpr, const double* r, const double* ecur, double* ealt,
                            double coef, bool e_zero) {
     double part = 0.0, dummy = 0.0;
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
+        constexpr int U = TM::U, RP = TM::T / TPR;
         const int sub = threadIdx.x % TPR;
-        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
-            const int row = base + threadIdx.x / TPR;
-            const bool valid = row < S.r1;
-            // own-row operands first, so that their L2 latency overlaps the gathers of the row product
-            double axi = 0.0, di = 0.0, ri = 0.0, ei = 0.0;
-            if (valid && sub == 0) { axi = L.Axi[row]; di = L.dinv[row]; ri = __ldcg(r + row); ei = e_zero ? 0.0 : __ldcg(ecur + row); }
-            double d = 0.0;
-            if (!e_zero) d = row_dot_s<TPR>(S, ecur, row, sub, valid);
-            if (valid && sub == 0) {
-                const double gi = ri - d;
-                const double en = ei + coef + di * (gi - axi * coef);
-                ealt[row] = en;
-                part = fma(axi, en, part);
+        for (int base = S.first(U * RP, G.blk()); base < S.r1; base += S.step(U * RP, G.nblk())) {
+            const int row0 = base + threadIdx.x / TPR;
+            double d[U];
+            if (!e_zero) row_dots<TPR, U, TM>(S, ecur, row0, RP, sub, d);
+            else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) d[u] = 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * RP;
+                if (row < S.r1 && sub == 0) {
+                    const double axi = L.Axi[row], di = L.dinv[row], ri = TM::ld(r + row), ei = e_zero ? 0.0 : TM::ld(ecur + row);
+                    const double gi = ri - d[u];
+                    const double en = ei + coef + di * (gi - axi * coef);
+                    ealt[row] = en;
+                    part = fma(axi, en, part);
+                }
             }
         }
     });
@@ -1324,54 +1461,66 @@ __device__ double p_jacobi(PGrid& G, const LevelDev& L, const PSlice& S, int tpr
 }
 
 // y (+)= M x on the block's rows of M; returns sum(y) and wvec'y (wvec optional)
-__device__ void p_spmv(PGrid& G, const PSlice& S, int tpr, const double* x, double* y, bool add, const double* wvec,
+template <class TM>
+__device__ void p_spmv(TM& G, const PSlice& S, int tpr, const double* x, double* y, bool add, const double* wvec,
                        double& sy, double& swy) {
     sy = 0.0; swy = 0.0;
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
+        constexpr int U = TM::U, RP = TM::T / TPR;
         const int sub = threadIdx.x % TPR;
-        for (int base = S.first(kPT / TPR); base < S.r1; base += S.step(kPT / TPR)) {
-            const int row = base + threadIdx.x / TPR;
-            const bool valid = row < S.r1;
-            double yi = 0.0, wi = 0.0;
-            if (valid && sub == 0) { if (add) yi = __ldcg(y + row); if (wvec) wi = wvec[row]; }
-            const double d = row_dot_s<TPR>(S, x, row, sub, valid);
-            if (valid && sub == 0) {
-                const double v = yi + d;
-                y[row] = v; sy += v;
-                swy = fma(wi, v, swy);
+        for (int base = S.first(U * RP, G.blk()); base < S.r1; base += S.step(U * RP, G.nblk())) {
+            const int row0 = base + threadIdx.x / TPR;
+            double d[U];
+            row_dots<TPR, U, TM>(S, x, row0, RP, sub, d);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int row = row0 + u * RP;
+                if (row < S.r1 && sub == 0) {
+                    const double v = (add ? TM::ld(y + row) : 0.0) + d[u];
+                    y[row] = v; sy += v;
+                    swy = fma(wvec ? wvec[row] : 0.0, v, swy);
+                }
             }
         }
     });
     G.sum2(sy, swy);
 }
 
-// y (+)= B x, dense row-major n x n (n <= 2048), one warp per row, all loads of a row in flight at once
-__device__ void p_dense(PGrid& G, int n, const double* __restrict__ B, const double* x, double* y, bool add) {
+// y (+)= B x, dense row-major n x n (n <= 2048), one warp per row, all loads of a row in flight at once.  xs: a
+// 2048-double shared-memory buffer of the team (or null): x is read once per CTA instead of once per row.
+template <class TM>
+__device__ void p_dense(TM& G, int n, const double* __restrict__ B, const double* x, double* y, bool add) {
     const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * kPT + threadIdx.x) >> 5, nw = gridDim.x * (kPT / 32);
+    const int gw = (G.blk() * TM::T + (int)threadIdx.x) >> 5, nw = G.nblk() * (TM::T / 32);
+    double* xs = G.xs;
+    if (xs != nullptr) {
+        for (int j = threadIdx.x; j < n; j += TM::T) xs[j] = TM::ld(x + j);
+        __syncthreads();
+    }
     for (int row = gw; row < n; row += nw) {
         const double* Br = B + (size_t)row * n;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j0 = 0; j0 < n; j0 += 256) {
             double bv[8], xv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int j = j0 + u * 32 + lane; bv[u] = (j < n) ? Br[j] : 0.0; xv[u] = (j < n) ? __ldcg(x + j) : 0.0; }
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 32 + lane;
+                bv[u] = (j < n) ? Br[j] : 0.0;
+                xv[u] = (j < n) ? (xs != nullptr ? xs[j] : TM::ld(x + j)) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc[u & 3] = fma(bv[u], xv[u], acc[u & 3]);
         }
         const double s = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
-        if (lane == 0) y[row] = add ? (__ldcg(y + row) + s) : s;
+        if (lane == 0) y[row] = add ? (TM::ld(y + row) + s) : s;
     }
-    G.grid.sync();
+    G.sync();
 }
 
-__global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const PersistArgs a) {
-    extern __shared__ __align__(16) unsigned char p_dsm[];
-    __shared__ double red[128];
-    __shared__ LevelDev sl[kPLevels];
-    __shared__ PLevelS ps[kPLevels];
-    PGrid G{cg::this_grid(), a.part, red, 0};
+template <class TM>
+__device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsigned char* p_dsm, LevelDev* sl, PLevelS* ps) {
+    constexpr int kPT = TM::T;
     const int kd = a.kd;                                   // levels 0..kd-1 explicit, level kd = dense leaf
     for (int t = threadIdx.x; t <= kd && t < kPLevels; t += kPT) sl[t] = a.levels[t];
     __syncthreads();
@@ -1380,19 +1529,20 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
         size_t used = 0;
         for (int t = kd; t >= 0; --t) {
             const LevelDev& L = sl[t];
-            if (t < kd) stage_slice(&ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, a.smem_budget);
-            else        stage_slice(&ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, 0);              // leaf: residual only, in place
-            if (t < kd) stage_slice(&ps[t].Pu, L.N, sl[t + 1].pp, sl[t + 1].pi, sl[t + 1].pv, p_dsm, used, a.smem_budget);
-            if (t >= 1) stage_slice(&ps[t].Td, L.N, L.tp, L.ti, L.tv, p_dsm, used, a.smem_budget);
+            if (t < kd) stage_slice(G, &ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, a.smem_budget);
+            else        stage_slice(G, &ps[t].A, L.N, L.ap, L.ai, L.av, p_dsm, used, 0);              // leaf: residual only, in place
+            if (t < kd) stage_slice(G, &ps[t].Pu, L.N, sl[t + 1].pp, sl[t + 1].pi, sl[t + 1].pv, p_dsm, used, a.smem_budget);
+            if (t >= 1) stage_slice(G, &ps[t].Td, L.N, L.tp, L.ti, L.tv, p_dsm, used, a.smem_budget);
         }
         __syncthreads();
     }
-    const bool lead = (blockIdx.x == 0 && threadIdx.x == 0);
+    const bool lead = (G.blk() == 0 && threadIdx.x == 0);
     int phase[kPLevels]; bool zero[kPLevels]; double* ecur[kPLevels]; double* ealt[kPLevels];
     double sum_r[kPLevels], dot_e[kPLevels];
     for (int t = 0; t < kPLevels; ++t) { phase[t] = 0; zero[t] = true; ecur[t] = nullptr; ealt[t] = nullptr; sum_r[t] = 0.0; dot_e[t] = 0.0; }
     const long long t_kernel0 = clock64();
     const int tpr0 = kd > 0 ? a.tpr[0] : 32;
+    int dbg_level__ = 0; (void)dbg_level__;
 
     // r = b - A*x ; res0 = norm(r)                                      Class_AMG.m:89
     double s1, s2;
@@ -1415,6 +1565,7 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
         while (true) {
             const LevelDev& L = sl[k];
             const PLevelS& P = ps[k];
+            dbg_level__ = k;
             if (k == kd) {                                              // dense tail operator
                 if (zero[k]) PDBG(29, p_dense(G, L.N, L.B, L.r, L.e, false));
                 else { double d1, d2; PDBG(25, p_resid(G, P.A, 32, L.r, L.e, L.g, false, d1, d2)); PDBG(29, p_dense(G, L.N, L.B, L.g, L.e, true)); }
@@ -1427,15 +1578,15 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
                 const int post = (phase[k] == 3) ? 1 : 0;
                 bool ez = (phase[k] == 0) ? zero[k] : false;
                 if (a.smoth == 0 && ez) {
-                    for (int i = P.A.first(kPT) + threadIdx.x; i < P.A.r1; i += P.A.step(kPT)) ecur[k][i] = 0.0;
-                    G.grid.sync();
+                    for (int i = P.A.first(kPT, G.blk()) + threadIdx.x; i < P.A.r1; i += P.A.step(kPT, G.nblk())) ecur[k][i] = 0.0;
+                    G.sync();
                 }
                 if (L.bigph) {
                     for (int s = 0; s < a.smoth; ++s) {
                         double sg, sg2;
                         PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ecur[k], L.g, a.isnsp != 0, sg, sg2));
                         const double coef = a.isnsp ? sg / L.xx : 0.0;
-                        PDBG(26, p_gs_apply(G, L, P.A, tpr, L.g, ecur[k], coef, post, ez));
+                        PDBG(26, p_gs_apply(G, L, P.A, a.tpr_gs > 0 ? a.tpr_gs : tpr, L.g, ecur[k], coef, post, ez));
                         ez = false;
                     }
                 } else {
@@ -1469,9 +1620,10 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
                 phase[k] = 3; continue;
             }
         }
+        dbg_level__ = 0;
         // ---------------- x += e ; r = b - A*x ; res = norm(r)          Class_AMG.m:96-104
-        for (int i = ps[0].A.first(kPT) + threadIdx.x; i < ps[0].A.r1; i += ps[0].A.step(kPT)) a.x[i] = __ldcg(a.x + i) + __ldcg(ecur[0] + i);
-        G.grid.sync();
+        for (int i = ps[0].A.first(kPT, G.blk()) + threadIdx.x; i < ps[0].A.r1; i += ps[0].A.step(kPT, G.nblk())) a.x[i] = __ldcg(a.x + i) + __ldcg(ecur[0] + i);
+        G.sync();
         PDBG(25, p_resid(G, ps[0].A, tpr0, a.b, a.x, sl[0].r, true, s1, s2));
         sum_r[0] = s1;
         const double res = sqrt(s2);
@@ -1482,8 +1634,35 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
         ++it; ++hist;
         if (rho > 1.0) break;                                           // Class_AMG.m:106
     }
-    if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; a.it_out[2] = 0; g_dbg_cycles[31] += (unsigned long long)(clock64() - t_kernel0); g_dbg_cycles[63] += 1ull; }
+    if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; a.it_out[2] = 0; g_pdbg[7 * 16] += (unsigned long long)(clock64() - t_kernel0); g_pdbg[128 + 7 * 16] += 1ull; }
     (void)rel_res;
+}
+
+__global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char p_dsm[];
+    __shared__ double red[128];
+    __shared__ LevelDev sl[kPLevels];
+    __shared__ PLevelS ps[kPLevels];
+    GridTeam G{cg::this_grid(), a.part, red, 0, nullptr};
+    persist_body(a, G, p_dsm, sl, ps);
+}
+
+// The same solve loop inside ONE thread-block cluster (launched with a runtime cluster dimension of 16, or 8 where
+// the non-portable size is not available): with the whole late-phase hierarchy (N ~ 3e4, 1e5 nonzeros per level)
+// the dependent passes are latency, not throughput, so 16 SMs are enough and the hardware cluster barrier
+// (~0.2 us) replaces the grid-wide barrier (>= 1.2 us + the skew of 296 blocks) and the L2 round trip of the
+// reduction partials; each CTA keeps its row slices of the level matrices in its 200 KB of shared memory.
+__global__ void __launch_bounds__(kCTT, 1) cluster_solve_kernel(const PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char p_dsm[];
+    __shared__ double red[128];
+    __shared__ double slots[2 * 2 * kCMax];
+    __shared__ LevelDev sl[kPLevels];
+    __shared__ PLevelS ps[kPLevels];
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ double xs[2048];
+    ClusterTeam G{red, slots, (int)cl.block_rank(), (int)cl.num_blocks(), 0, xs};
+    persist_body(a, G, p_dsm, sl, ps);
+    cluster_barrier();                                     // no CTA exits while a peer may still write into its shared memory
 }
 
 template <class F>
@@ -1671,19 +1850,18 @@ void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_
 
 int tpr_for(double avg) { return avg <= 3.0 ? 2 : (avg <= 6.0 ? 4 : (avg <= 12.0 ? 8 : (avg <= 24.0 ? 16 : 32))); }
 
-// Runs Class_AMG's solve loop in the persistent kernel.  Returns false when the hierarchy does not
-// qualify (no dense tail / too many large levels), in which case the caller launches kernel by kernel.
+// Runs Class_AMG's solve loop in ONE kernel: inside a single thread-block cluster when the hierarchy is small
+// enough for 16 SMs (late-phase systems: always), else as the grid-wide cooperative kernel.  Returns false when the
+// hierarchy does not qualify (no dense tail / too many large levels), in which case the caller launches kernel by kernel.
 bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, int& it,
                    double& rel_res, std::vector<double>& relk, std::vector<double>& rho) {
     if (H.dense_from >= H.J || H.dense_from >= kPLevels) return false;
-    {   // the persistent kernel trades occupancy for latency: with large level matrices (early SsN steps,
-        // millions of nonzeros) the cycle is bandwidth-bound and the multi-block kernels win
-        int64_t nnz = 0;
-        for (int k = 0; k < H.dense_from; ++k) nnz += H.lv[k].A.nnz;
-        if (nnz > c->persist_max_nnz) return false;
-    }
+    int64_t nnz = 0;
+    for (int k = 0; k < H.dense_from; ++k) nnz += H.lv[k].A.nnz;
+    // the persistent kernels trade occupancy for latency: with large level matrices (early SsN steps,
+    // millions of nonzeros) the cycle is bandwidth-bound and the multi-block kernels win
+    if (nnz > c->persist_max_nnz) return false;
     for (int k = 0; k < H.dense_from; ++k) if (H.lv[k].bigph && k != 0) return false;
-    Phase ph(c, "solve.persist_solve_kernel");
     PersistArgs a{};
     a.levels = H.dev.p; a.J = H.J; a.kd = H.dense_from; a.smoth = H.smoth; a.isnsp = o.isnsp; a.wcycle = wcycle ? 1 : 0;
     a.b = b; a.x = x; a.retol = o.retol; a.maxit = o.maxit;
@@ -1692,21 +1870,72 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
         a.tpr[k] = tpr_for(L.N ? (double)L.A.nnz / L.N : 0.0);
         a.tpr_p[k] = (k > 0) ? tpr_for(L.N ? (double)L.P.nnz / std::max(1, L.N) : 0.0) : 2;
     }
-    const size_t smem = (size_t)(200 / kPBlocksPerSM - 6) * 1024;
-    SSN_CUDA(cudaFuncSetAttribute(persist_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_solve_kernel, kPT, smem));
-    if (per_sm < kPBlocksPerSM) return false;
-    const int grid = c->num_sms * kPBlocksPerSM;
-    a.smem_budget = smem;
-    { const char* e = getenv("SSN_PERSIST_SMEM"); if (e && e[0] == '0') a.smem_budget = 0; }
     const int hl = o.maxit + 2;
-    Buf<double> part(c, (size_t)4 * grid), hist(c, (size_t)2 * hl);
+    Buf<double> hist(c, (size_t)2 * hl);
     Buf<int> iout(c, 4);
-    a.part = part.p; a.relk = hist.p; a.rho = hist.p + hl; a.it_out = iout.p;
-    void* args[] = {&a};
-    SSN_CUDA(cudaLaunchCooperativeKernel((void*)persist_solve_kernel, dim3(grid), dim3(kPT), args, smem, c->stream));
-    c->launches++;
+    a.relk = hist.p; a.rho = hist.p + hl; a.it_out = iout.p;
+    bool launched = false;
+    if (c->cluster_solve && nnz <= c->cluster_max_nnz) {
+        // ---- one cluster: 16 CTAs (non-portable size) where the device can co-schedule them, else 8
+        static int cluster_ctas = -1;                       // probed once per process
+        const size_t smem = (size_t)200 * 1024;              // + 22 KB static (reduction slots, level tables, the dense tail input)
+        if (cluster_ctas < 0) {
+            cluster_ctas = 0;
+            if (cudaFuncSetAttribute(cluster_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                const bool np_ok = cudaFuncSetAttribute(cluster_solve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+                for (int want : {np_ok ? kCMax : 8, 8}) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(want); cfg.blockDim = dim3(kCTT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    int nclusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nclusters, cluster_solve_kernel, &cfg) == cudaSuccess && nclusters >= 1) { cluster_ctas = want; break; }
+                }
+            }
+            (void)cudaGetLastError();
+            { const char* e = getenv("SSN_CLUSTER_CTAS"); if (e && (atoi(e) == 8 || atoi(e) == 4 || atoi(e) == 2) && cluster_ctas >= atoi(e)) cluster_ctas = atoi(e); }
+        }
+        if (cluster_ctas > 0) {
+            Phase ph(c, "solve.cluster_solve_kernel");
+            a.part = nullptr;
+            a.smem_budget = smem;
+            { const char* e = getenv("SSN_PERSIST_SMEM"); if (e && e[0] == '0') a.smem_budget = 0; }
+            // lanes per row: as few as keep every row of a CTA's slice in flight at once -- with 16 SMs a pass is
+            // bound by the dependent L2 round trips of its row loop, so one pass over the slice beats wide rows
+            auto fit = [&](int t, int rows, int u) { const int per = (rows + cluster_ctas - 1) / cluster_ctas; while (t > 1 && (int64_t)per * t > (int64_t)kCTT * u) t >>= 1; return t; };
+            for (int k = 0; k <= H.dense_from && k < kPLevels; ++k) {
+                a.tpr[k] = fit(a.tpr[k], H.lv[k].N, ClusterTeam::U);
+                if (k > 0) a.tpr_p[k] = fit(a.tpr_p[k], H.lv[k - 1].N, ClusterTeam::U);
+            }
+            a.tpr_gs = fit(a.tpr[0], H.lv[0].N, 1);         // the coupled block Gauss-Seidel update walks one row per thread group
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cluster_ctas); cfg.blockDim = dim3(kCTT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            SSN_CUDA(cudaLaunchKernelEx(&cfg, cluster_solve_kernel, a));
+            c->launches++;
+            launched = true;
+        }
+    }
+    Buf<double> part;
+    if (!launched) {
+        Phase ph(c, "solve.persist_solve_kernel");
+        const size_t smem = (size_t)(200 / kPBlocksPerSM - 6) * 1024;
+        SSN_CUDA(cudaFuncSetAttribute(persist_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_solve_kernel, kPT, smem));
+        if (per_sm < kPBlocksPerSM) return false;
+        const int grid = c->num_sms * kPBlocksPerSM;
+        a.smem_budget = smem;
+        { const char* e = getenv("SSN_PERSIST_SMEM"); if (e && e[0] == '0') a.smem_budget = 0; }
+        part.alloc(c, (size_t)4 * grid);
+        a.part = part.p;
+        void* args[] = {&a};
+        SSN_CUDA(cudaLaunchCooperativeKernel((void*)persist_solve_kernel, dim3(grid), dim3(kPT), args, smem, c->stream));
+        c->launches++;
+    }
     int hi[4];
     read_back(c, iout.p, hi, 4);
     it = hi[0];
@@ -1760,6 +1989,11 @@ double barrier_bench(ssn_ctx* c, int iters, int which) {
     SSN_CUDA(cudaLaunchCooperativeKernel((void*)barrier_bench_kernel, dim3(c->num_sms * kPBlocksPerSM), dim3(kPT), args, 0, c->stream));
     long long cyc = read_scalar(c, out.p);
     return (double)cyc / (double)iters;
+}
+
+void debug_cycles_persist(unsigned long long* out256, bool reset) {
+    cudaMemcpyFromSymbol(out256, g_pdbg, sizeof(unsigned long long) * 256);
+    if (reset) { unsigned long long z[256] = {0}; cudaMemcpyToSymbol(g_pdbg, z, sizeof(z)); }
 }
 
 void debug_cycles(unsigned long long* out64, bool reset) {

@@ -52,6 +52,8 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_CLUSTER"); c->no_cluster = !(e && e[0] == '1'); }
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
+    { const char* e = getenv("SSN_CLUSTER_SOLVE"); c->cluster_solve = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_CLUSTER_MAXNNZ"); if (e && atoll(e) > 0) c->cluster_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
@@ -158,6 +160,9 @@ const char* ssn_profile_dump(ssn_ctx* c) {
 
 int ssn_debug_cycles(ssn_ctx* c, unsigned long long* out64, int reset) {
     return guarded(c, [&] { sync(c); debug_cycles(out64, reset != 0); });
+}
+int ssn_debug_cycles_persist(ssn_ctx* c, unsigned long long* out256, int reset) {
+    return guarded(c, [&] { sync(c); debug_cycles_persist(out256, reset != 0); });
 }
 
 int ssn_rng_reset(ssn_ctx* c, uint32_t seed) { return guarded(c, [&] { rng_reset(c, seed); sync(c); }); }
@@ -300,6 +305,37 @@ int ssn_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const dou
     return guarded(c, [&] {
         plan_linesearch(c, w, lam_old, zeta, wlk, p, q, m, n, tk, bk1, gama, gama_s, nu, delta, ll_max, cF_old, ress, batch,
                         lam_new, ll_out, n2_out, cF_out, passes_out);
+        sync(c);
+    });
+}
+
+int ssn_apd_ssn_class1(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
+                       int64_t n, const double* gama, double gama_s, const ssn_apd_options* op, double* xk_out, double* lk_out,
+                       ssn_apd_result* res, double* fxk_hist, double* kktx_hist, double* kktl_hist, int32_t* ssn_its_hist,
+                       double* steps_host, int64_t steps_cap) {
+    return guarded(c, [&] {
+        apd_ssn_class1(c, cost, r, l, p, q, m, n, gama, gama_s, op, xk_out, lk_out, res, fxk_hist, kktx_hist, kktl_hist, ssn_its_hist,
+                       steps_host, steps_cap);
+    });
+}
+int ssn_apd_ssn_class1_host(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
+                            int64_t n, const double* gama, double gama_s, const ssn_apd_options* op, double* xk_out, double* lk_out,
+                            ssn_apd_result* res, double* fxk_hist, double* kktx_hist, double* kktl_hist, int32_t* ssn_its_hist,
+                            double* steps_host, int64_t steps_cap) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(cost && r && l && p && q && xk_out && lk_out && m > 0 && n > 0, SSN_E_INVALID, "apd_ssn_class1: bad arguments");
+        const size_t mn = (size_t)m * n;
+        Buf<double> dc(c, mn), dr(c, n), dl(c, m), dp(c, m), dq(c, n), dx(c, mn), dlk(c, m + n), dg;
+        SSN_CUDA(cudaMemcpyAsync(dc.p, cost, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dr.p, r, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dl.p, l, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        if (gama) { dg.alloc(c, mn); SSN_CUDA(cudaMemcpyAsync(dg.p, gama, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream)); }
+        apd_ssn_class1(c, dc, dr, dl, dp, dq, m, n, gama ? dg.p : nullptr, gama_s, op, dx, dlk, res, fxk_hist, kktx_hist, kktl_hist,
+                       ssn_its_hist, steps_host, steps_cap);
+        SSN_CUDA(cudaMemcpyAsync(xk_out, dx.p, sizeof(double) * mn, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(lk_out, dlk.p, sizeof(double) * (m + n), cudaMemcpyDeviceToHost, c->stream));
         sync(c);
     });
 }

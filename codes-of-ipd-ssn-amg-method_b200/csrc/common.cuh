@@ -61,6 +61,8 @@ struct ssn_ctx {
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
     int64_t persist_max_nnz = (int64_t)1 << 40;   // SSN_PERSIST_MAXNNZ: above this the cycle is launched kernel by kernel
     bool persist = true;                  // SSN_PERSIST=0: launch the large-level cycle kernel by kernel
+    bool cluster_solve = true;            // SSN_CLUSTER_SOLVE=0: the persistent solve always runs grid-wide (cooperative launch)
+    int64_t cluster_max_nnz = (int64_t)1 << 20;   // SSN_CLUSTER_MAXNNZ: larger hierarchies (explicit levels) use the grid-wide kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only

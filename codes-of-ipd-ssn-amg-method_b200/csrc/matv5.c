@@ -91,9 +91,11 @@ static void parse_matrix(const uint8_t* p, uint32_t n, ssn_mat_var* v) {
     if (!ts) return;
     {   /* file-supplied dimensions: bound each by the element count before multiplying (no int64 overflow) */
         const int64_t nel = (int64_t)nb / ts;
-        if (dims[0] > nel || dims[1] > nel) return;
-        if (dims[0] != 0 && dims[1] > nel / dims[0]) return;
-        if ((int64_t)nb != dims[0] * dims[1] * ts) return;
+        if (dims[0] == 0 || dims[1] == 0) { if (nb != 0) return; }
+        else {
+            if (dims[0] > nel || dims[1] > nel / dims[0]) return;
+            if ((int64_t)nb != dims[0] * dims[1] * ts) return;
+        }
     }
     v->dtype = type; v->data = d; v->nbytes = nb; v->supported = 1;
 }

@@ -11,4 +11,9 @@ void invaat(ssn_ctx* c, const double* x, const double* p, const double* q, int64
 void invhht(ssn_ctx* c, const double* v, const double* p, const double* q, int64_t m, int64_t n, double sg, const double* phi, double* y);
 void amg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info);
 void pcg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_pcg_options* opts, double* zeta, int* it, double* res, int* info);
+// the Class 1 script as one call (apd_driver.cu)
+void apd_ssn_class1(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
+                    int64_t n, const double* gama, double gama_s, const ssn_apd_options* op, double* xk_out, double* lk_out,
+                    ssn_apd_result* res, double* fxk_hist, double* kktx_hist, double* kktl_hist, int32_t* ssn_its_hist,
+                    double* steps_host, int64_t steps_cap);
 }  // namespace ssn

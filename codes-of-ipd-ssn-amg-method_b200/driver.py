@@ -130,7 +130,7 @@ def APD_SsN_Class1(c, r, l, p, q, gama=np.inf, inner_solver=4, maxit=100, KKT_To
             torch.cuda.synchronize(); stats["asat_s"] += time.time() - t0
             if on_ssn_step is not None:
                 on_ssn_step({"k": k, "ssn_it": ssn_it, "wk": wk, "lk": lk_old, "wlk": wlk, "bk1": bk1, "tk": tk,
-                             "s": s, "Fk": Fk_old, "H0": H0, "E": ev["count"]})
+                             "s": s, "Fk": Fk_old, "H0": H0, "E": ev["count"], "xk": xk, "vk": vk, "ak": ak, "bk": bk})
             t0 = time.time()
             prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "T": None, "H0": H0, "z": -Fk_old}
             if inner_solver == 2:                                       # :149-152, PCG on Jk = bk1*I + (T+H0)/tk
@@ -400,7 +400,7 @@ def ssn_step_host(hstate, amg_options=None):
     return lk_new.cpu(), Fk_new.cpu(), info
 
 
-def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100, run_to_end=False):
+def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100, run_to_end=False, keep_plans=False):
     """Runs the Class1 solve on the device until SsN step ``ssn_it`` of outer iteration ``outer`` and
     returns the APD state that step reads (a realistic system for benchmarks / parity tests).
     ``run_to_end`` lets the solve finish instead of stopping there and returns ``(state, solve_result)``."""
@@ -413,7 +413,11 @@ def capture_state(c, r, l, p, q, gama=np.inf, outer=30, ssn_it=1, warm_maxit=100
     def hook(st):
         if not box and st["k"] >= outer and st["ssn_it"] >= ssn_it:
             box.update({"wk": st["wk"].clone(), "lk": st["lk"].clone(), "wlk": st["wlk"].clone(), "bk1": st["bk1"],
-                        "tk": st["tk"], "k": st["k"], "ssn_it": st["ssn_it"], "E": st["E"]})
+                        "tk": st["tk"], "k": st["k"], "ssn_it": st["ssn_it"], "E": st["E"], "ak": st["ak"], "bk": st["bk"]})
+            if keep_plans:                                  # sparse at late APD states: tools/save_bench_state.py
+                for key in ("xk", "vk"):
+                    nz = torch.nonzero(st[key]).reshape(-1)
+                    box[key + "_idx"] = nz.cpu().numpy().astype(np.int64); box[key + "_val"] = st[key][nz].cpu().numpy()
             if not run_to_end:
                 raise _Stop()
     res = None

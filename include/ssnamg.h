@@ -156,6 +156,10 @@ SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
 SSN_API int  ssn_debug_barrier_bench(ssn_ctx *ctx, int iters, int which, double *cycles_per_barrier);
 /* cycle counters of the small-level cycle kernel: out64[0..63] (development aid) */
 SSN_API int  ssn_debug_cycles(ssn_ctx *ctx, unsigned long long *out64, int reset);
+/* per (operation, level) cycle counters of the persistent / cluster-resident solve kernels, filled only by a
+ * library built with -DSSN_PERSIST_DEBUG: out256[op*16 + level] cycles, out256[128 + op*16 + level] calls
+ * (op 0 residual, 1 block Gauss-Seidel update, 2 Jacobi step, 3 restriction / prolongation, 4 dense tail, 7 kernel) */
+SSN_API int  ssn_debug_cycles_persist(ssn_ctx *ctx, unsigned long long *out256, int reset);
 
 /* The library-owned MATLAB random stream (mt19937ar, init_genrand(5489), genrand_res53):
  * stands for MATLAB's global `rand` state consumed at AMG/mis_set.m:31,35 and
@@ -243,6 +247,50 @@ SSN_API int ssn_linesearch(ssn_ctx *ctx, const double *w_dev, const double *lam_
                    double tk, double bk1, const double *gama_dev, double gama_scalar, double nu, double delta,
                    int ll_max, double cF_old, double ress, int batch, double *lam_new_dev, int *ll_out,
                    double *norm2_out, double *cF_out, int *passes_out);
+
+/* The reference's Class 1 SCRIPT as one entry point: the warm start
+ * (Class1/warmup_class1.m), the APD outer loop (Class1/APD_SsN_Class1.m:101-275) and the semismooth-Newton inner
+ * loop (:137-238) with the inner linear solve selected by `inner_solver` (:66-70: 2 = PCG on Jk, 3 = aug_PCG,
+ * 4 = Hybrid_AMG, 5 = Hybrid_twogrid), the Armijo line search (:182-211), the KKT bookkeeping (:239-274) and the
+ * restart (:245-249) -- every plan-sized array stays on the device, nothing runs in an interpreter between the
+ * kernels.  A zero / negative option field means "the script's value" (maxit 100, KKT_Tol 1e-6, 100 warm-start
+ * iterations, inner_solver 4, amg_options / pcg_options of :81,:87-88). */
+typedef struct ssn_apd_options {
+    int32_t inner_solver;            /* 2, 3, 4 (default) or 5 */
+    int32_t maxit;                   /* outer iterations, default 100 (:35) */
+    double  KKT_Tol;                 /* default 1e-6 (:35) */
+    int32_t warm_maxit;              /* A-ADMM iterations, default 100 (:59); < 0 = default, 0 = none */
+    int32_t max_outer;               /* > 0: stop after this many outer iterations (tests / traces) */
+    double  max_seconds;             /* > 0: stop once the outer loop ran this long */
+    int32_t verbose;                 /* != 0: the script's progress lines on stderr */
+    const ssn_amg_options *amg;      /* NULL: Class1/APD_SsN_Class1.m:87-88 */
+    const ssn_pcg_options *pcg;      /* NULL: :81 */
+} ssn_apd_options;
+typedef struct ssn_apd_result {
+    int32_t outer_its, converged;
+    double  rel_kkt, objective;
+    int32_t ssn_steps, ls_trials, ls_passes, amg_calls;
+    double  warmup_s, loop_s, solve_s, asat_s, plan_s;     /* host wall clock: warm start, outer loop, and inside it
+                                                              the inner solves / ASAt / the plan-wide part of the SsN steps */
+    int32_t hist_len;                /* outer_its + 1 entries written to the history buffers */
+    int64_t steps_len;               /* SsN steps taken (7 doubles each in steps_host, up to steps_cap) */
+} ssn_apd_result;
+/* c, r, l, p, q (and gama_dev, or NULL + gama_scalar) on the device; xk_out_dev (m*n), lk_out_dev (n+m) on the
+ * device.  Optional HOST buffers: fxk / KKT_xk / KKT_lk histories (maxit+1 doubles each), SsN steps per outer
+ * iteration (maxit ints), and per SsN step {k, ssn_it, nnz(s), components, inner iterations, ll, |F|}. */
+SSN_API int ssn_apd_ssn_class1(ssn_ctx *ctx, const double *c_dev, const double *r_dev, const double *l_dev,
+                       const double *p_dev, const double *q_dev, int64_t m, int64_t n, const double *gama_dev,
+                       double gama_scalar, const ssn_apd_options *opts, double *xk_out_dev, double *lk_out_dev,
+                       ssn_apd_result *result, double *fxk_hist_host, double *kkt_xk_hist_host,
+                       double *kkt_lk_hist_host, int32_t *ssn_its_hist_host, double *steps_host, int64_t steps_cap);
+/* The same solve for a caller that holds HOST arrays (a MATLAB script without gpuArray): inputs are copied to
+ * the device once, the plan xk (m*n) and the duals lk (n+m) are copied back once -- one plugin call per solve
+ * instead of one host<->device round trip of plan-sized arrays per operator call. */
+SSN_API int ssn_apd_ssn_class1_host(ssn_ctx *ctx, const double *c_host, const double *r_host, const double *l_host,
+                            const double *p_host, const double *q_host, int64_t m, int64_t n, const double *gama_host,
+                            double gama_scalar, const ssn_apd_options *opts, double *xk_out_host, double *lk_out_host,
+                            ssn_apd_result *result, double *fxk_hist_host, double *kkt_xk_hist_host,
+                            double *kkt_lk_hist_host, int32_t *ssn_its_hist_host, double *steps_host, int64_t steps_cap);
 
 /* [xk,lk] = warmup_class1(c,r,l,p,q,gama,0,maxit) -- Class1/warmup_class1.m:18-96, the A-ADMM warm start
  * called at Class1/APD_SsN_Class1.m:59, device resident: two fused plan-wide kernels per iteration

@@ -185,13 +185,29 @@ def test_class_amg_matches_oracle(gpu, oracle, m, n, density, cycle):
     o = dict(AMG_OPTS, fnode=n, cycle=cycle, guess=guess)
     oracle.rng_reset(); gpu.rng_reset()
     x_ref, it_ref, rel_ref, relk_ref, rho_ref = oracle.Class_AMG(Ae, f, o)
-    x, it, rel, relk, rho = gpu.Class_AMG(Ae, f, o)
-    assert it == it_ref
-    assert len(relk) == len(relk_ref)
-    big = relk_ref > 1e-9                      # histories <= 1e-8 relative until they hit the noise floor
-    assert np.allclose(relk[big], relk_ref[big], rtol=1e-6)
-    assert np.linalg.norm(Ae @ x - f) <= 1e-10 * np.linalg.norm(Ae @ guess - f) * 10
-    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+    # SURVEY 8d asks for residual histories <= 1e-8 relative per entry until they reach 1e-10 absolute.  An entry relk of
+    # the history is ||b - A x_k|| / ||b - A x_0||: the residual itself is only known to about eps*||A||*||x_k||, i.e. to
+    # eps*||A||*||x|| / ||r_0|| in the units of the history -- the `floor` below -- so the gate is 1e-8*relk + 50*floor
+    # (1e-8 relative wherever the entry is above the rounding floor of its own evaluation).
+    res0 = np.linalg.norm(Ae @ guess - f)
+    floor = np.finfo(float).eps * abs(Ae).sum(axis=1).max() * np.linalg.norm(x_ref) / res0
+    for dense in (True, False):                # default: dense tail operators; False: MG_Wcycle.m:44's PCG(A,r) on every visit
+        try:
+            gpu.set_dense_tail(dense)
+            gpu.rng_reset()
+            x, it, rel, relk, rho = gpu.Class_AMG(Ae, f, o)
+        finally:
+            gpu.set_dense_tail(True)
+        assert it == it_ref
+        assert len(relk) == len(relk_ref)
+        dev = np.abs(relk - relk_ref)
+        worst = float(np.max(dev / (1e-8 * relk_ref + 50 * floor)))
+        print(f"Class_AMG {m}x{n} {cycle}-cycle, dense tail {dense}: {it} cycles, history max rel dev "
+              f"{float(np.max(dev[relk_ref > 1e-9] / relk_ref[relk_ref > 1e-9])):.1e}, gate usage {worst:.2f}, rounding floor {floor:.1e}, "
+              f"solution {np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref):.1e}")
+        assert worst <= 1.0
+        assert np.linalg.norm(Ae @ x - f) <= 1e-10 * res0 * 10
+        assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
 
 
 @pytest.mark.parametrize("cycle", ["w", "v"])

@@ -41,9 +41,16 @@ def main():
     lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
     ctx = lib.context(); buf = (ctypes.c_ulonglong * 64)()
     ctx.call("ssn_debug_cycles", ctypes.cast(buf, ctypes.c_void_p), 1)
-    for slot, nm in {25: "persist.resid", 26: "persist.gs_apply", 27: "persist.jacobi", 28: "persist.spmv", 29: "persist.dense", 31: "persist.kernel"}.items():
-        if buf[32 + slot]:
-            print(f"  dbg {nm:18s}: {buf[slot] / 1e3:10.1f} kcycles over {buf[32 + slot]} calls -> {buf[slot] / buf[32 + slot]:9.0f} cyc/call")
+    pb = (ctypes.c_ulonglong * 256)()
+    ctx.call("ssn_debug_cycles_persist", ctypes.cast(pb, ctypes.c_void_p), 1)
+    ops = {0: "resid", 1: "gs_apply", 2: "jacobi", 3: "spmv(P)", 4: "dense", 7: "kernel"}
+    tot = pb[7 * 16] or 1
+    for op, nm in ops.items():
+        for lv in range(16):
+            cnt = pb[128 + op * 16 + lv]
+            if cnt:
+                cyc = pb[op * 16 + lv]
+                print(f"  pdbg {nm:9s} level {lv}: {cyc / 1e3:10.1f} kcycles ({100.0 * cyc / tot:5.1f} %) over {cnt:6d} calls -> {cyc / cnt:8.0f} cyc/call")
     names = {0: "smooth", 8: "resid+restrict", 16: "prolong", 24: "pcg"}
     for base, nm in names.items():
         for k in range(8 if base < 24 else 1):
