@@ -767,6 +767,16 @@ def set_persistent(enable=True):
     ctx = context(); ctx.call("ssn_set_persistent", 1 if enable else 0)
 
 
+def set_fused_setup(enable=True):
+    """Small AMG levels coarsened by one kernel (default) or kernel by kernel -- ``ssn_set_fused_setup``."""
+    context().call("ssn_set_fused_setup", 1 if enable else 0)
+
+
+def set_cluster_solve(enable=True):
+    """Class_AMG's solve loop inside one thread-block cluster (default) or grid-wide -- ``ssn_set_cluster_solve``."""
+    context().call("ssn_set_cluster_solve", 1 if enable else 0)
+
+
 def set_device_setup(enable=True):
     """PCG's SSOR / IC(0) factors and dependency levels built on the device (``True``) or on the host (default)."""
     ctx = context(); ctx.call("ssn_set_device_setup", 1 if enable else 0)

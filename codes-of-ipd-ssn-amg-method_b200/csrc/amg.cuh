@@ -25,6 +25,7 @@ struct Level {
     Csr A, P, Pt;
     Buf<double> dinv, Axi, r, e, g, pcg;
     double xx = 0.0;
+    bool xx_known = false;         // xx was computed with the level (fused setup kernel); else amg_setup reads it back
     // setup trace (kept for parity tests: C/F split and strength flags that produced level k+1)
     Buf<uint8_t> isC;
     // dense cycle operator of this level (tail levels only; amg_solve.cu "dense tail")
@@ -41,7 +42,19 @@ struct ClusterPlan {
     int cap[kClusterLevels];                   // capacity (entries) of the staged slice
 };
 
+// ---- fused coarsening of the small levels (amg_setup_fused.cu)
+constexpr int kFusedMaxN = 4096;               // levels with at most this many rows ...
+constexpr int64_t kFusedMaxNnz = 1 << 18;      // ... and nonzeros are coarsened by one kernel
+constexpr int kFusedMaxLevels = 24;
+constexpr int kFusedOverflow = 1;              // status: out of arena / a product row wider than the accumulator
+struct FusedLevel {                            // one level built by the kernel: arrays inside the arena
+    int N, nnzA, nnzP, parentN; double xx;
+    int* ap; int* ai; double* av; int* pp; int* pi; double* pv; int* tp; int* ti; double* tv;
+    double* dinv; double* Axi; uint8_t* parent_isC;
+};
+
 struct Hierarchy {
+    std::vector<Buf<unsigned char>> arenas;    // memory of the levels built by the fused kernel (declared first: freed last)
     std::vector<Level> lv;
     int J = 0;
     int smoth = 0;
@@ -78,6 +91,8 @@ void transfer(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int level_J, Cs
 // max_levels > 0 stops the coarsening after that many levels (twogrid_bigph builds exactly two)
 void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels = 0);
 void amg_clear(ssn_ctx* c);
+// coarsens below the last level of H in one kernel while N <= kFusedMaxN; false: not applicable, H and the random stream untouched
+bool fused_small_levels(ssn_ctx* c, Hierarchy& H, const AmgOptions& o, int thr, int max_new_levels);
 int coarsest_threshold(int64_t N);
 
 // ---- solve (amg_solve.cu)

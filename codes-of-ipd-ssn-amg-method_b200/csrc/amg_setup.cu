@@ -676,6 +676,11 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
     // Class_AMG.m:76 coarsens down to the threshold; twogrid_bigph.m:41-47 (max_levels = 2) coarsens exactly once
     while (max_levels > 0 ? (J < max_levels) : (H->lv[J - 1].N > thr)) {
         SSN_REQUIRE(J < 64, SSN_E_COARSEN_STALL, "coarsening stalled");
+        // the small levels: all remaining coarsening steps in one kernel (amg_setup_fused.cu)
+        if (J >= 2 && fused_small_levels(c, *H, o, max_levels > 0 ? -1 : thr, max_levels > 0 ? max_levels - J : kFusedMaxLevels)) {
+            J = (int)H->lv.size();
+            continue;
+        }
         Level nl;
         Buf<uint8_t> isC;
         transfer(c, H->lv[J - 1].A, o, J, nl.A, nl.P, &isC, nullptr, &nl.Pt);
@@ -689,7 +694,7 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
     {   // ones'*A_k*ones of every level: one host read for the hierarchy
         double hxx[64];
         read_back(c, xxd.p, hxx, (size_t)J);
-        for (int k = 0; k < J; ++k) H->lv[k].xx = hxx[k];
+        for (int k = 0; k < J; ++k) if (!H->lv[k].xx_known) H->lv[k].xx = hxx[k];
     }
     // tail of small levels handled by the single-block cycle kernel
     int sf = J - 1;

@@ -1132,6 +1132,9 @@ struct PSlice {
     __device__ __forceinline__ int step(int rows_per_pass, int nblk) const { return inter ? nblk * rows_per_pass : rows_per_pass; }
 };
 struct PLevelS { PSlice A, Pu, Td; };      // A_t ; Pro_{t+1} (rows of level t) ; Pro_t' (rows of level t)
+struct PState {                            // control state of the cycle, one entry per level (shared memory)
+    int phase[kPLevels]; int zero[kPLevels]; double* ecur[kPLevels]; double* ealt[kPLevels]; double sum_r[kPLevels]; double dot_e[kPLevels];
+};
 
 template <class TM>
 __device__ void stage_slice(const TM& G, PSlice* S, int N, const int* ptr, const int* idx, const double* val, unsigned char* smem,
@@ -1519,7 +1522,7 @@ __device__ void p_dense(TM& G, int n, const double* __restrict__ B, const double
 }
 
 template <class TM>
-__device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsigned char* p_dsm, LevelDev* sl, PLevelS* ps) {
+__device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsigned char* p_dsm, LevelDev* sl, PLevelS* ps, PState* pst) {
     constexpr int kPT = TM::T;
     const int kd = a.kd;                                   // levels 0..kd-1 explicit, level kd = dense leaf
     for (int t = threadIdx.x; t <= kd && t < kPLevels; t += kPT) sl[t] = a.levels[t];
@@ -1537,9 +1540,15 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
         __syncthreads();
     }
     const bool lead = (G.blk() == 0 && threadIdx.x == 0);
-    int phase[kPLevels]; bool zero[kPLevels]; double* ecur[kPLevels]; double* ealt[kPLevels];
-    double sum_r[kPLevels], dot_e[kPLevels];
-    for (int t = 0; t < kPLevels; ++t) { phase[t] = 0; zero[t] = true; ecur[t] = nullptr; ealt[t] = nullptr; sum_r[t] = 0.0; dot_e[t] = 0.0; }
+    // Per-level control state of the cycle (phase machine instead of recursion).  It lives in SHARED memory, not in
+    // per-thread arrays: dynamically indexed thread-local arrays are local memory, and every barrier of this kernel
+    // invalidates the L1 (grid.sync / barrier.cluster imply CCTL.IVALL), so each access would be an L2 round trip.
+    // Every thread executes the same control flow and writes the same values; an iteration first snapshots what it
+    // needs into registers, then passes a block barrier, and writes only after it -- so no thread can overwrite a
+    // value another thread has not read yet, and a late write only repeats the value that is already there.
+    PState& st = *pst;
+    for (int t = threadIdx.x; t < kPLevels; t += kPT) { st.phase[t] = 0; st.zero[t] = 1; st.ecur[t] = nullptr; st.ealt[t] = nullptr; st.sum_r[t] = 0.0; st.dot_e[t] = 0.0; }
+    __syncthreads();
     const long long t_kernel0 = clock64();
     const int tpr0 = kd > 0 ? a.tpr[0] : 32;
     int dbg_level__ = 0; (void)dbg_level__;
@@ -1548,7 +1557,7 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
     double s1, s2;
     PDBG(25, p_resid(G, ps[0].A, tpr0, a.b, a.x, sl[0].r, true, s1, s2));
     const double res0 = sqrt(s2);
-    sum_r[0] = s1;
+    double sum_r0 = s1;
     double res_prev = res0, rel_prev = 1.0, rel_res = 0.0;
     int it = 0, hist = 1;
     if (lead) { a.relk[0] = 1.0; a.rho[0] = NAN; }
@@ -1559,73 +1568,84 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
     it = 1;
     while (rel_prev > a.retol && it <= a.maxit) {                       // Class_AMG.m:95
         // ---------------- one cycle on level 0: rhs sl[0].r -> ecur[0]
-        for (int t = 0; t <= kd; ++t) { ecur[t] = sl[t].e; ealt[t] = sl[t].pcg; }
+        __syncthreads();
+        for (int t = threadIdx.x; t <= kd; t += kPT) { st.ecur[t] = sl[t].e; st.ealt[t] = sl[t].pcg; }
+        if (threadIdx.x == 0) { st.phase[0] = 0; st.zero[0] = 1; st.sum_r[0] = sum_r0; }
+        __syncthreads();
         int k = 0;
-        phase[0] = 0; zero[0] = true;
+        double* e_top = nullptr;
         while (true) {
             const LevelDev& L = sl[k];
             const PLevelS& P = ps[k];
             dbg_level__ = k;
+            // snapshot of this level's state (and of the child's correction), then the barrier that orders it before any write
+            const int ph = st.phase[k];
+            const bool zk = st.zero[k] != 0;
+            double* ec = st.ecur[k]; double* ea = st.ealt[k];
+            const double sr = st.sum_r[k], de = st.dot_e[k];
+            double* ec_child = (k < kd) ? st.ecur[k + 1] : nullptr;
+            __syncthreads();
             if (k == kd) {                                              // dense tail operator
-                if (zero[k]) PDBG(29, p_dense(G, L.N, L.B, L.r, L.e, false));
+                if (zk) PDBG(29, p_dense(G, L.N, L.B, L.r, L.e, false));
                 else { double d1, d2; PDBG(25, p_resid(G, P.A, 32, L.r, L.e, L.g, false, d1, d2)); PDBG(29, p_dense(G, L.N, L.B, L.g, L.e, true)); }
-                ecur[k] = L.e;
-                if (k == 0) break;
+                st.ecur[k] = L.e;
+                if (k == 0) { e_top = L.e; break; }
                 --k; continue;
             }
             const int tpr = a.tpr[k];
-            if (phase[k] == 0 || phase[k] == 3) {                       // pre- (0) or post-smoothing (3)
-                const int post = (phase[k] == 3) ? 1 : 0;
-                bool ez = (phase[k] == 0) ? zero[k] : false;
+            if (ph == 0 || ph == 3) {                                   // pre- (0) or post-smoothing (3)
+                const int post = (ph == 3) ? 1 : 0;
+                bool ez = (ph == 0) ? zk : false;
                 if (a.smoth == 0 && ez) {
-                    for (int i = P.A.first(kPT, G.blk()) + threadIdx.x; i < P.A.r1; i += P.A.step(kPT, G.nblk())) ecur[k][i] = 0.0;
+                    for (int i = P.A.first(kPT, G.blk()) + threadIdx.x; i < P.A.r1; i += P.A.step(kPT, G.nblk())) ec[i] = 0.0;
                     G.sync();
                 }
+                double dotAe = ez ? 0.0 : de;
                 if (L.bigph) {
                     for (int s = 0; s < a.smoth; ++s) {
                         double sg, sg2;
-                        PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ecur[k], L.g, a.isnsp != 0, sg, sg2));
+                        PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ec, L.g, a.isnsp != 0, sg, sg2));
                         const double coef = a.isnsp ? sg / L.xx : 0.0;
-                        PDBG(26, p_gs_apply(G, L, P.A, a.tpr_gs > 0 ? a.tpr_gs : tpr, L.g, ecur[k], coef, post, ez));
+                        PDBG(26, p_gs_apply(G, L, P.A, a.tpr_gs > 0 ? a.tpr_gs : tpr, L.g, ec, coef, post, ez));
                         ez = false;
                     }
                 } else {
-                    double dotAe = ez ? 0.0 : dot_e[k];
                     for (int s = 0; s < a.smoth; ++s) {
-                        const double coef = a.isnsp ? (sum_r[k] - dotAe) / L.xx : 0.0;
-                        PDBG(27, dotAe = p_jacobi(G, L, P.A, tpr, L.r, ecur[k], ealt[k], coef, ez));
-                        double* t = ecur[k]; ecur[k] = ealt[k]; ealt[k] = t;
+                        const double coef = a.isnsp ? (sr - dotAe) / L.xx : 0.0;
+                        PDBG(27, dotAe = p_jacobi(G, L, P.A, tpr, L.r, ec, ea, coef, ez));
+                        double* t = ec; ec = ea; ea = t;
                         ez = false;
                     }
-                    dot_e[k] = dotAe;
                 }
                 if (post) {                                             // this level's visit is complete
-                    if (k == 0) break;
+                    st.ecur[k] = ec; st.ealt[k] = ea; st.dot_e[k] = dotAe;
+                    if (k == 0) { e_top = ec; break; }
                     --k; continue;
                 }
                 // restriction: r_{k+1} = Pro' (r - A e)                  MG_Wcycle.m:26
                 double d1, d2;
-                PDBG(25, p_resid(G, P.A, tpr, L.r, (ez ? nullptr : ecur[k]), L.g, false, d1, d2));
+                PDBG(25, p_resid(G, P.A, tpr, L.r, (ez ? nullptr : ec), L.g, false, d1, d2));
                 PDBG(28, p_spmv(G, ps[k + 1].Td, a.tpr_p[k + 1], L.g, sl[k + 1].r, false, nullptr, d1, d2));
-                sum_r[k + 1] = d1;
-                phase[k] = 1; phase[k + 1] = 0; zero[k + 1] = true; ++k; continue;
+                st.ecur[k] = ec; st.ealt[k] = ea; st.dot_e[k] = dotAe;
+                st.sum_r[k + 1] = d1;
+                st.phase[k] = 1; st.phase[k + 1] = 0; st.zero[k + 1] = 1; ++k; continue;
             }
-            if (phase[k] == 1 && a.wcycle && (k + 1 != a.J - 1)) {      // second coarse visit   :30
-                phase[k] = 2; phase[k + 1] = 0; zero[k + 1] = false; ++k; continue;
+            if (ph == 1 && a.wcycle && (k + 1 != a.J - 1)) {            // second coarse visit   :30
+                st.phase[k] = 2; st.phase[k + 1] = 0; st.zero[k + 1] = 0; ++k; continue;
             }
             {   // prolongation e += Pro e_{k+1}, with Axi'e for the post-smoother        :32
                 double d1, d2;
-                PDBG(28, p_spmv(G, P.Pu, a.tpr_p[k + 1], ecur[k + 1], ecur[k], true, L.Axi, d1, d2));
-                dot_e[k] = d2;
-                phase[k] = 3; continue;
+                PDBG(28, p_spmv(G, P.Pu, a.tpr_p[k + 1], ec_child, ec, true, L.Axi, d1, d2));
+                st.dot_e[k] = d2;
+                st.phase[k] = 3; continue;
             }
         }
         dbg_level__ = 0;
         // ---------------- x += e ; r = b - A*x ; res = norm(r)          Class_AMG.m:96-104
-        for (int i = ps[0].A.first(kPT, G.blk()) + threadIdx.x; i < ps[0].A.r1; i += ps[0].A.step(kPT, G.nblk())) a.x[i] = __ldcg(a.x + i) + __ldcg(ecur[0] + i);
+        for (int i = ps[0].A.first(kPT, G.blk()) + threadIdx.x; i < ps[0].A.r1; i += ps[0].A.step(kPT, G.nblk())) a.x[i] = __ldcg(a.x + i) + __ldcg(e_top + i);
         G.sync();
         PDBG(25, p_resid(G, ps[0].A, tpr0, a.b, a.x, sl[0].r, true, s1, s2));
-        sum_r[0] = s1;
+        sum_r0 = s1;
         const double res = sqrt(s2);
         rel_res = res / res0;
         const double rho = res / res_prev;
@@ -1643,8 +1663,9 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
     __shared__ double red[128];
     __shared__ LevelDev sl[kPLevels];
     __shared__ PLevelS ps[kPLevels];
+    __shared__ PState pst;
     GridTeam G{cg::this_grid(), a.part, red, 0, nullptr};
-    persist_body(a, G, p_dsm, sl, ps);
+    persist_body(a, G, p_dsm, sl, ps, &pst);
 }
 
 // The same solve loop inside ONE thread-block cluster (launched with a runtime cluster dimension of 16, or 8 where
@@ -1660,8 +1681,9 @@ __global__ void __launch_bounds__(kCTT, 1) cluster_solve_kernel(const PersistArg
     __shared__ PLevelS ps[kPLevels];
     cg::cluster_group cl = cg::this_cluster();
     __shared__ double xs[2048];
+    __shared__ PState pst;
     ClusterTeam G{red, slots, (int)cl.block_rank(), (int)cl.num_blocks(), 0, xs};
-    persist_body(a, G, p_dsm, sl, ps);
+    persist_body(a, G, p_dsm, sl, ps, &pst);
     cluster_barrier();                                     // no CTA exits while a peer may still write into its shared memory
 }
 

@@ -53,6 +53,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_CLUSTER_SOLVE"); c->cluster_solve = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_FUSED_SETUP"); c->fused_setup = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_CLUSTER_MAXNNZ"); if (e && atoll(e) > 0) c->cluster_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
@@ -139,6 +140,8 @@ int ssn_debug_barrier_bench(ssn_ctx* c, int iters, int which, double* cycles_per
 }
 int ssn_set_persistent(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->persist = on != 0; return SSN_OK; }
 int ssn_set_device_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->device_setup = on != 0; return SSN_OK; }
+int ssn_set_fused_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->fused_setup = on != 0; return SSN_OK; }
+int ssn_set_cluster_solve(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->cluster_solve = on != 0; return SSN_OK; }
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;

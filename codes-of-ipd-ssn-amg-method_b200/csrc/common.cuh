@@ -61,6 +61,7 @@ struct ssn_ctx {
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
     int64_t persist_max_nnz = (int64_t)1 << 40;   // SSN_PERSIST_MAXNNZ: above this the cycle is launched kernel by kernel
     bool persist = true;                  // SSN_PERSIST=0: launch the large-level cycle kernel by kernel
+    bool fused_setup = true;              // SSN_FUSED_SETUP=0: the small levels of the hierarchy are coarsened kernel by kernel too
     bool cluster_solve = true;            // SSN_CLUSTER_SOLVE=0: the persistent solve always runs grid-wide (cooperative launch)
     int64_t cluster_max_nnz = (int64_t)1 << 20;   // SSN_CLUSTER_MAXNNZ: larger hierarchies (explicit levels) use the grid-wide kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
@@ -82,24 +83,37 @@ namespace ssn {
 template <class T>
 struct Buf {
     ssn_ctx* c = nullptr; T* p = nullptr; size_t n = 0;
+    bool owned = true;                    // false: a view into memory somebody else owns (an arena of the fused setup kernel)
     Buf() = default;
     Buf(ssn_ctx* ctx, size_t count) { alloc(ctx, count); }
     Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete;
-    Buf(Buf&& o) noexcept : c(o.c), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    Buf(Buf&& o) noexcept : c(o.c), p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; }
     Buf& operator=(Buf&& o) noexcept {
-        if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~Buf() { reset(); }
+    static Buf view(ssn_ctx* ctx, T* ptr, size_t count) { Buf b; b.c = ctx; b.p = ptr; b.n = count; b.owned = false; return b; }
     void alloc(ssn_ctx* ctx, size_t count) {
-        reset(); c = ctx; n = count;
+        reset(); c = ctx; n = count; owned = true;
         size_t bytes = (count ? count : 1) * sizeof(T);
         SSN_CUDA(cudaMallocAsync((void**)&p, bytes, ctx->stream));
     }
     void reset() {
-        if (p) { cudaFreeAsync(p, c->stream); p = nullptr; n = 0; }
+        if (p && owned) cudaFreeAsync(p, c->stream);
+        p = nullptr; n = 0; owned = true;
     }
-    T* release() { T* r = p; p = nullptr; n = 0; return r; }
+    // hands the pointer to a caller that will cudaFreeAsync it: a view is copied into an owned allocation first
+    T* release() {
+        if (p && !owned) {
+            T* q = nullptr;
+            SSN_CUDA(cudaMallocAsync((void**)&q, (n ? n : 1) * sizeof(T), c->stream));
+            if (n) SSN_CUDA(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+            p = nullptr; n = 0; owned = true;
+            return q;
+        }
+        T* r = p; p = nullptr; n = 0; return r;
+    }
     void zero() { SSN_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), c->stream)); }
     operator T*() const { return p; }
     T* get() const { return p; }

@@ -151,6 +151,13 @@ SSN_API int  ssn_set_persistent(ssn_ctx *ctx, int on);
 /* on != 0 (default): PCG's SSOR / IC(0) factors (precd 3 / 4), their dependency levels and row groups are built on
  * the device; 0 (env SSN_DEVICE_SETUP=0): on the host, once per call (kept as the cross-check of the device path). */
 SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
+/* on != 0 (default; env SSN_FUSED_SETUP): the levels of the Class_AMG hierarchy with N <= 4096 rows are coarsened by ONE
+ * kernel (strength, MIS rounds, interpolation, Galerkin products, smoother data; sizes never leave the device);
+ * 0: kernel by kernel like the large levels.  Same hierarchy bit for bit. */
+SSN_API int  ssn_set_fused_setup(ssn_ctx *ctx, int on);
+/* on != 0 (default; env SSN_CLUSTER_SOLVE): Class_AMG's solve loop of a late-phase hierarchy (<= 2^20 nonzeros on the
+ * explicit levels, env SSN_CLUSTER_MAXNNZ) runs inside ONE thread-block cluster; 0: always as the grid-wide kernel. */
+SSN_API int  ssn_set_cluster_solve(ssn_ctx *ctx, int on);
 /* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
  * 1 = the library's own barrier (development aid) */
 SSN_API int  ssn_debug_barrier_bench(ssn_ctx *ctx, int iters, int which, double *cycles_per_barrier);

@@ -201,6 +201,8 @@ struct ssn_ctx {
     int ls_max_nt = 128; bool ls_screen = true;
     int small_scan_max = 1 << 14;
     bool device_setup = true;
+    bool fused_setup = true, cluster_solve = true;
+    int64_t cluster_max_nnz = (int64_t)1 << 20;
     int dense_max_n = 2048;
     bool ktimer = false, prof = false;
     double* h_pin = nullptr;
@@ -215,15 +217,17 @@ namespace ssn {
 template <class T>
 struct Buf {
     ssn_ctx* c = nullptr; T* p = nullptr; size_t n = 0;
+    bool owned = true;                    // false: a view (Buf::view), never freed here
     Buf() = default;
     Buf(ssn_ctx* ctx, size_t count) { alloc(ctx, count); }
     Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete;
-    Buf(Buf&& o) noexcept : c(o.c), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    Buf& operator=(Buf&& o) noexcept { if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    Buf(Buf&& o) noexcept : c(o.c), p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; }
+    Buf& operator=(Buf&& o) noexcept { if (this != &o) { reset(); c = o.c; p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; } return *this; }
     ~Buf() { reset(); }
+    static Buf view(ssn_ctx* ctx, T* ptr, size_t count) { Buf b; b.c = ctx; b.p = ptr; b.n = count; b.owned = false; return b; }
     // filled with 0xA5 so that a read of something never written shows up as garbage, not as a lucky zero
-    void alloc(ssn_ctx* ctx, size_t count) { reset(); c = ctx; n = count; p = (T*)std::malloc((count ? count : 1) * sizeof(T)); std::memset((void*)p, 0xA5, (count ? count : 1) * sizeof(T)); }
-    void reset() { if (p) { std::free((void*)p); p = nullptr; n = 0; } }
+    void alloc(ssn_ctx* ctx, size_t count) { reset(); c = ctx; n = count; owned = true; p = (T*)std::malloc((count ? count : 1) * sizeof(T)); std::memset((void*)p, 0xA5, (count ? count : 1) * sizeof(T)); }
+    void reset() { if (p && owned) std::free((void*)p); p = nullptr; n = 0; owned = true; }
     T* release() { T* r = p; p = nullptr; n = 0; return r; }
     void zero() { std::memset((void*)p, 0, (n ? n : 1) * sizeof(T)); }
     operator T*() const { return p; }

@@ -15,7 +15,7 @@ from conftest import random_active_problem
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     import emu_build
-    lib = emu_build.build(tmp_path_factory.mktemp("emu_amg"), "emu_amg.cpp", ["sparse.cu", "amg_setup.cu", "amg.cuh", "sparse.cuh"],
+    lib = emu_build.build(tmp_path_factory.mktemp("emu_amg"), "emu_amg.cpp", ["sparse.cu", "amg_setup.cu", "amg_setup_fused.cu", "amg.cuh", "sparse.cuh"],
                           "libemu_amg.so")
     lib.emu_error.restype = C.c_char_p
     lib.emu_rng_drawn.restype = C.c_int64
@@ -194,6 +194,40 @@ def test_hierarchy_bit_exact(emu, oracle):
             emu.emu_level(C.c_int(k), C.c_int(1))
             assert_same_matrix(_fetch(emu), P, f"Pro level {k + 1}")
     assert emu.emu_rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    emu.emu_phase_counts.restype = C.c_char_p
+    assert b"setup.fused_small_levels" in emu.emu_phase_counts(), "the levels below level 2 were not built by the fused kernel"
+    amg_state.clear(); emu.emu_amg_clear()
+
+
+@pytest.mark.parametrize("m,n,density,isnsp", [(90, 70, 0.05, 0), pytest.param(400, 300, 0.01, 1, marks=__import__("emu_build").slow)])
+def test_fused_small_levels_equal_the_oracle(emu, oracle, m, n, density, isnsp):
+    """amg_setup_fused.cu (all levels below level 2 in ONE kernel: strength, MIS rounds, interpolation, transposes, the two
+    sparse products in their frozen summation order, smoother data) against the oracle's hierarchy, bit for bit."""
+    from oracle.amg import setup_hierarchy, amg_state
+    Ae = ssn_matrix(oracle, m, n, density, seed=7 * m)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    o = {"retol": 1e-11, "bigph": 1, "maxit": 30, "theta": 0.25, "smoth": 5, "cycle": "w", "isnsp": isnsp, "inter": 1, "guess": None, "fnode": n}
+    oracle.rng_reset(); _check(emu, emu.emu_rng_reset())
+    st = setup_hierarchy(Ae, o)
+    ref = [(A.copy(), P) for A, P in zip(st.Ack, st.Prok)]
+    A1, a1 = _csr_args(Ae)
+    J = C.c_int(0)
+    emu.emu_phase_reset()
+    _check(emu, emu.emu_amg_setup(C.c_int64(m + n), C.c_int64(A1.nnz), _p(a1[0]), _p(a1[1]), _p(a1[2]), C.c_double(0.25), C.c_int(5), C.c_int(isnsp),
+                                  C.c_int(n), C.byref(J)))
+    assert J.value == len(ref) and J.value >= 3
+    emu.emu_level.restype = C.c_double
+    for k, (A, P) in enumerate(ref):
+        emu.emu_level(C.c_int(k), C.c_int(0))
+        assert_same_matrix(_fetch(emu), A, f"A level {k + 1}")
+        if k > 0:
+            emu.emu_level(C.c_int(k), C.c_int(1))
+            assert_same_matrix(_fetch(emu), P, f"Pro level {k + 1}")
+    assert emu.emu_rng_drawn() == oracle.GLOBAL_STREAM.drawn
+    emu.emu_phase_counts.restype = C.c_char_p
+    counts = dict((ln.split("\t")[0], ln.split("\t")[1:]) for ln in emu.emu_phase_counts().decode().splitlines())
+    assert "setup.fused_small_levels" in counts and "setup.mis_set" not in counts, counts.keys()
     amg_state.clear(); emu.emu_amg_clear()
 
 

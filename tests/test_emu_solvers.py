@@ -17,7 +17,7 @@ from test_emu_amg import _check, _csr_args, _fetch, _p, assert_same_matrix
 def emu(tmp_path_factory):
     import emu_build
     lib = emu_build.build(tmp_path_factory.mktemp("emu_solvers"), "emu_solvers.cpp",
-                          ["solvers.cu", "sparse.cu", "amg_setup.cu", "amg.cuh", "sparse.cuh", "solvers.cuh", "plan_ops.cuh"], "libemu_solvers.so")
+                          ["solvers.cu", "sparse.cu", "amg_setup.cu", "amg_setup_fused.cu", "amg.cuh", "sparse.cuh", "solvers.cuh", "plan_ops.cuh"], "libemu_solvers.so")
     lib.emu_error.restype = C.c_char_p
     lib.emu_host_reads.restype = C.c_int64
     return lib

@@ -350,3 +350,39 @@ def test_wcycle_behaviour_on_large_disc_systems_matches_oracle(gpu, oracle, g, e
         assert res_o <= 1e-11 and res_g <= 1e-11
     else:
         assert it_o == 1 and res_o > 1e6 and res_g > 1e6
+
+
+@pytest.mark.parametrize("m,n,density,isnsp", [(400, 300, 0.01, 1), (900, 1000, 0.004, 1), (2500, 2300, 0.0015, 1), (2500, 2300, 0.0015, 0),
+                                               (6000, 5000, 0.0008, 1)])
+def test_fused_small_level_setup_equals_piecewise(gpu, oracle, m, n, density, isnsp):
+    """The levels with N <= 4096 coarsened by ONE kernel (amg_setup_fused.cu, the default) against the same levels
+    built kernel by kernel: identical level sizes, A_k and Pro_k bit for bit, the same number of random draws, and
+    the same Class_AMG run (cycle counts, histories, solution)."""
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=11 * m)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    o = dict(AMG_OPTS, fnode=n, isnsp=isnsp)
+    res = {}
+    try:
+        for fused in (False, True):
+            gpu.set_fused_setup(fused)
+            gpu.rng_reset()
+            levels = gpu.amg_setup(Ae, o)
+            res[fused] = ([(a.to_scipy().tocsr(), None if p is None else p.to_scipy().tocsr()) for a, p in levels], gpu.rng_drawn())
+            gpu.amg_clear()
+            gpu.rng_reset()
+            res[fused] += (gpu.Class_AMG(Ae, f, dict(o, guess=0.01 * np.random.RandomState(2).random_sample(m + n))),)
+    finally:
+        gpu.set_fused_setup(True)
+    (lv0, drawn0, run0), (lv1, drawn1, run1) = res[False], res[True]
+    assert [a.shape[0] for a, _ in lv1] == [a.shape[0] for a, _ in lv0]
+    assert min(a.shape[0] for a, _ in lv0[1:]) <= 4096, "no small level: nothing was fused"
+    for k, ((a1, p1), (a0, p0)) in enumerate(zip(lv1, lv0)):
+        assert_same_matrix(a1, a0, what=f"A level {k + 1}")
+        if k > 0:
+            assert_same_matrix(p1, p0, what=f"Pro level {k + 1}")
+    assert drawn1 == drawn0
+    x0, it0, rel0, relk0, _ = run0; x1, it1, rel1, relk1, _ = run1
+    assert it1 == it0 and len(relk1) == len(relk0)
+    assert np.allclose(relk1[relk0 > 1e-9], relk0[relk0 > 1e-9], rtol=1e-7)
+    assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
