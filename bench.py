@@ -207,7 +207,7 @@ def main():
     else:
         k3_w, k3_lam, k3_p, k3_rows = state["wk"], state["lk"], state["p"], m
 
-    lam8 = torch.stack([k3_lam + 0.9 ** t * 1e-3 for t in range(8)]).contiguous()      # eight trial vectors
+    lam8 = torch.stack([k3_lam + 0.9 ** t * 1e-3 for t in range(8)]).contiguous()      # eight trial vectors (rows)
 
     def kernel_ms(fn, reps=10):
         """Mean duration of the plan-wide kernel inside fn(), CUDA events on the launching stream
@@ -219,7 +219,17 @@ def main():
             fn()
         ms, cnt = ssnamg.kernel_timer_read()
         ssnamg.kernel_timer(False)
-        return ms / max(cnt, 1)
+        if cnt > 0 and ms > 0:
+            return ms / cnt
+        # the library's timer did not fire: CUDA events around the whole call (the plan-wide kernel + its small finish
+        # kernels and the host read of the call, i.e. slightly pessimistic)
+        print(f"bench: ssn_kernel_timer returned ({ms}, {cnt}); timing the calls with torch events instead", file=sys.stderr)
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record(); torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
 
     for _ in range(max(args.warmup, 3)):
         lk_new, Fk_new, info = step_fn()

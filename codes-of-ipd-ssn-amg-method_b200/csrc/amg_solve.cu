@@ -2002,8 +2002,47 @@ void build_cluster_plan(ssn_ctx* c, Hierarchy& H) {
     SSN_CUDA(cudaFuncSetAttribute(cluster_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(used ? used : 16)));
 }
 
+// one cluster of 16 (or 8) CTAs x 1024 threads: which = 2 release/acquire barrier alone, 3 a global store per thread
+// before every barrier, 4 relaxed arrive (no MEMBAR) + wait, 5 store + barrier + a dependent L2 gather (ld.cg) per thread,
+// 6 as 5 with a plain (L1-cached) gather
+__global__ void __launch_bounds__(1024, 1) cluster_barrier_bench_kernel(double* buf, int iters, int which, long long* cycles_out) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int gt = (int)cl.block_rank() * 1024 + threadIdx.x, nt = (int)cl.num_blocks() * 1024;
+    cluster_barrier();
+    const long long t0 = clock64();
+    double acc = 0.0;
+    for (int i = 0; i < iters; ++i) {
+        if (which == 3 || which >= 5) buf[gt] = acc + i;
+        if (which == 4) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+        else cluster_barrier();
+        if (which == 5) acc += __ldcg(buf + ((gt * 7 + i * 131) % nt));
+        if (which == 6) acc += buf[(gt * 7 + i * 131) % nt];
+    }
+    if (cl.block_rank() == 0 && threadIdx.x == 0) cycles_out[0] = clock64() - t0;
+    if (acc == 123.456) buf[0] = acc;
+    cluster_barrier();
+}
+
 // cycles per grid barrier: which = 0 cooperative-groups grid.sync(), 1 = grid_barrier() (development aid)
 double barrier_bench(ssn_ctx* c, int iters, int which) {
+    if (which >= 2) {
+        Buf<double> buf(c, 16 * 1024); buf.zero();
+        Buf<long long> out(c, 1);
+        (void)cudaFuncSetAttribute(cluster_barrier_bench_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        for (int want : {16, 8}) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(want); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, cluster_barrier_bench_kernel, buf.p, iters, which, out.p) == cudaSuccess) {
+                long long cyc = read_scalar(c, out.p);
+                return (double)cyc / (double)iters;
+            }
+            (void)cudaGetLastError();
+        }
+        return -1.0;
+    }
     Buf<unsigned> bar(c, 64); bar.zero();
     Buf<long long> out(c, 1);
     unsigned* bp = bar.p; long long* op = out.p;

@@ -53,7 +53,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_CLUSTER_SOLVE"); c->cluster_solve = !(e && e[0] == '0'); }
-    { const char* e = getenv("SSN_FUSED_SETUP"); c->fused_setup = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_FUSED_SETUP"); c->fused_setup = (e && e[0] == '1'); }
     { const char* e = getenv("SSN_CLUSTER_MAXNNZ"); if (e && atoll(e) > 0) c->cluster_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
@@ -72,6 +72,11 @@ int ssn_create(ssn_ctx** out, int device) {
         uint64_t thr = UINT64_MAX;
         SSN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         SSN_CUDA(cudaMallocHost((void**)&c->h_pin, sizeof(double) * ssn_ctx::kPinDoubles));
+        { const char* e = getenv("SSN_POLL_READS"); c->poll_reads = !(e && e[0] == '0'); }
+        if (cudaHostAlloc((void**)&c->h_poll, sizeof(double) * (ssn_ctx::kPinDoubles + 2), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&c->d_poll, c->h_poll, 0) == cudaSuccess) {
+            std::memset(c->h_poll, 0, sizeof(double) * (ssn_ctx::kPinDoubles + 2));
+        } else { (void)cudaGetLastError(); if (c->h_poll) cudaFreeHost(c->h_poll); c->h_poll = nullptr; c->d_poll = nullptr; }
         SSN_CUDA(cudaMalloc((void**)&c->mt_state, sizeof(uint32_t) * 625));
         rng_reset(c, 5489u);
         SSN_CUDA(cudaStreamSynchronize(c->stream));
@@ -90,6 +95,7 @@ int ssn_destroy(ssn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->hier) { delete c->hier; c->hier = nullptr; }
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_poll) cudaFreeHost(c->h_poll);
     if (c->mt_state) cudaFree(c->mt_state);
     delete c;
     return SSN_OK;

@@ -52,6 +52,12 @@ struct ssn_ctx {
     // pinned host scratch for scalar read-backs
     double* h_pin = nullptr;              // 4096 doubles
     static constexpr int kPinDoubles = 4096;
+    // small device->host reads without a copy-engine transfer and a stream synchronise: a one-block kernel stores the values
+    // into MAPPED pinned memory, then a sequence number; the host spins on the number (SSN_POLL_READS=0: memcpy + synchronise)
+    bool poll_reads = true;
+    double* h_poll = nullptr;             // kPinDoubles doubles + 1 flag word, cudaHostAlloc(mapped)
+    double* d_poll = nullptr;             // the same memory as the device sees it
+    unsigned long long poll_seq = 0;
     // MATLAB random stream (device-resident MT19937 state)
     uint32_t* mt_state = nullptr;         // 624 words + 1 index word
     int64_t rng_drawn = 0;
@@ -61,12 +67,14 @@ struct ssn_ctx {
     bool no_cluster = true;               // SSN_CLUSTER=1 enables the 8-CTA cluster cycle kernel
     int64_t persist_max_nnz = (int64_t)1 << 40;   // SSN_PERSIST_MAXNNZ: above this the cycle is launched kernel by kernel
     bool persist = true;                  // SSN_PERSIST=0: launch the large-level cycle kernel by kernel
-    bool fused_setup = true;              // SSN_FUSED_SETUP=0: the small levels of the hierarchy are coarsened kernel by kernel too
+    bool fused_setup = false;             // SSN_FUSED_SETUP=1: the small levels of the hierarchy are coarsened by ONE kernel (one CTA; same
+                                          // hierarchy bit for bit, but slower than kernel by kernel on a B200: opt-in)
     bool cluster_solve = true;            // SSN_CLUSTER_SOLVE=0: the persistent solve always runs grid-wide (cooperative launch)
     int64_t cluster_max_nnz = (int64_t)1 << 20;   // SSN_CLUSTER_MAXNNZ: larger hierarchies (explicit levels) use the grid-wide kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
+    double ls_last_density = -1.0;        // share of the plan's entries that survived the screen in the last screened batch (< 0: none yet)
     bool device_setup = true;             // SSN_DEVICE_SETUP=0: SSOR / IC(0) factors and their levels built on the host instead of the device (trifactor.cu)
     int small_scan_max = 1 << 14;         // SSN_SMALL_SCAN_MAX: largest array scanned by the one-block kernel (cub::DeviceScan above)
     int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator
@@ -164,20 +172,24 @@ inline void check_launch(ssn_ctx* c, const char* what) {
 // Times ONE kernel launch with CUDA events on the launching stream when ssn_kernel_timer is on.
 struct KernelTimer {
     ssn_ctx* c;
+    bool armed = false;
     explicit KernelTimer(ssn_ctx* ctx) : c(ctx) {
         if (c->ktimer) {
-            if (!c->kt0) { cudaEventCreate(&c->kt0); cudaEventCreate(&c->kt1); }
-            cudaEventRecord(c->kt0, c->stream);
+            if (!c->kt0) { if (cudaEventCreate(&c->kt0) != cudaSuccess || cudaEventCreate(&c->kt1) != cudaSuccess) { c->kt0 = c->kt1 = nullptr; note("cudaEventCreate"); return; } }
+            armed = cudaEventRecord(c->kt0, c->stream) == cudaSuccess;
+            if (!armed) note("cudaEventRecord(start)");
         }
     }
     ~KernelTimer() {
-        if (c->ktimer) {
-            cudaEventRecord(c->kt1, c->stream);
-            cudaEventSynchronize(c->kt1);
-            float ms = 0.f; cudaEventElapsedTime(&ms, c->kt0, c->kt1);
+        if (c->ktimer && armed) {
+            float ms = 0.f;
+            if (cudaEventRecord(c->kt1, c->stream) != cudaSuccess) { note("cudaEventRecord(stop)"); return; }
+            if (cudaEventSynchronize(c->kt1) != cudaSuccess) { note("cudaEventSynchronize"); return; }
+            if (cudaEventElapsedTime(&ms, c->kt0, c->kt1) != cudaSuccess) { note("cudaEventElapsedTime"); return; }
             c->kt_ms += ms; c->kt_n += 1;
         }
     }
+    void note(const char* what) { const cudaError_t e = cudaGetLastError(); c->err = std::string("kernel timer: ") + what + ": " + cudaGetErrorString(e); fprintf(stderr, "%s\n", c->err.c_str()); }
 };
 
 struct Phase {
@@ -197,10 +209,20 @@ struct Phase {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// values of up to 4 device ints / one device array -> the context's mapped pinned buffer, visible to the host when the
+// sequence word changes (sparse.cu); returns after the values have arrived
+void poll_read(ssn_ctx* c, const void* dev, size_t bytes);
+void poll_read_ints(ssn_ctx* c, const int* const* src, int k);
+
 // read `count` elements (<= pinned scratch) back to the host, synchronously
 template <class T>
 inline void read_back(ssn_ctx* c, const T* dev, T* host, size_t count) {
     size_t bytes = count * sizeof(T);
+    if (c->poll_reads && c->h_poll && bytes > 0 && bytes <= sizeof(double) * ssn_ctx::kPinDoubles && bytes % 4 == 0) {
+        poll_read(c, dev, bytes);
+        std::memcpy(host, c->h_poll, bytes);
+        return;
+    }
     if (bytes <= sizeof(double) * ssn_ctx::kPinDoubles) {
         SSN_CUDA(cudaMemcpyAsync(c->h_pin, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
         SSN_CUDA(cudaStreamSynchronize(c->stream));
@@ -214,6 +236,15 @@ template <class T>
 inline T read_scalar(ssn_ctx* c, const T* dev) { T v; read_back(c, dev, &v, 1); return v; }
 // several device ints with ONE stream synchronisation (the copies queue up behind the kernels that produce them)
 inline void read_ints(ssn_ctx* c, std::initializer_list<const int*> src, int* out) {
+    if (c->poll_reads && c->h_poll && src.size() <= 4) {
+        const int* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+        int k = 0;
+        for (const int* s : src) ptrs[k++] = s;
+        poll_read_ints(c, ptrs, k);
+        const int* got = reinterpret_cast<const int*>(c->h_poll);
+        for (int i = 0; i < k; ++i) out[i] = got[i];
+        return;
+    }
     int* pin = reinterpret_cast<int*>(c->h_pin);
     size_t k = 0;
     for (const int* s : src) SSN_CUDA(cudaMemcpyAsync(pin + k++, s, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -1366,17 +1366,19 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
     const double slots = std::max(1.0, (double)m * (double)n);
     int ll = 0, passes = 0;
     double dens = 1.0;                                                      // surviving share of the entries, last pass
+    // most steps accept the full step (ll = 0): the first read of w evaluates that trial alone -- unless the trial plans
+    // of the previous line search of this context were sparse (late phase, where line searches are long): a screened
+    // batch of 64 steps costs the same one read of w then, and saves a pass.  Every later read evaluates a batch.
+    const int first = (screened && c->ls_last_density >= 0.0 && c->ls_last_density <= 0.10) ? std::min(64, c->ls_max_nt) : 1;
     while (true) {
-        // most steps accept the full step (ll = 0): the first read of w evaluates that trial alone,
-        // every later read evaluates a batch of backtracking steps at once
         int want = batch;
         bool lin = screened;
         if (screened && passes > 0) {
-            if (dens <= 0.10) want = std::min(c->ls_max_nt, passes == 1 ? 64 : 128);
+            if (dens <= 0.10) want = std::min(c->ls_max_nt, (passes == 1 && first == 1) ? 64 : 128);
             else if (dens <= 0.25) want = std::min(16, c->ls_max_nt);
             else { want = kMaxTrials; lin = false; }
         }
-        const int nt = std::min(passes == 0 ? 1 : want, ll_max - ll + 1);
+        const int nt = std::min(passes == 0 ? first : want, ll_max - ll + 1);
         double al[kMaxLinBatch];
         for (int t = 0; t < nt; ++t) al[t] = std::pow(delta, (double)(ll + t));
         for (int t = 0; t < nt; ++t) c->h_pin[1024 + t] = al[t];
@@ -1387,7 +1389,7 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         else     plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, res.p, nonunit);
         double h[3 * kMaxLinBatch + 1];
         read_back(c, res.p, h, 3 * (size_t)cap + 1);
-        if (lin) dens = h[nt] / slots;
+        if (lin) { dens = h[nt] / slots; c->ls_last_density = dens; }
         ++passes;
         int acc = -1;
         double n2a = 0.0, cFa = 0.0;

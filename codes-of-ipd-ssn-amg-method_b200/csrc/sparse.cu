@@ -42,6 +42,54 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* ou
 }
 }  // namespace
 
+// ------------------------------------------------------------------ polled device->host reads
+namespace {
+__global__ void __launch_bounds__(256) poll_publish_kernel(const unsigned* __restrict__ src, int nwords, unsigned* dst_host,
+                                                           volatile unsigned long long* flag_host, unsigned long long seq) {
+    for (int i = threadIdx.x; i < nwords; i += 256) dst_host[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag_host = seq;
+}
+__global__ void poll_publish_ints_kernel(const int* a, const int* b, const int* c2, const int* d, int k, int* dst_host,
+                                         volatile unsigned long long* flag_host, unsigned long long seq) {
+    if (threadIdx.x == 0) {
+        if (k > 0) dst_host[0] = *a;
+        if (k > 1) dst_host[1] = *b;
+        if (k > 2) dst_host[2] = *c2;
+        if (k > 3) dst_host[3] = *d;
+        __threadfence_system();
+        *flag_host = seq;
+    }
+}
+void poll_wait(ssn_ctx* c, unsigned long long seq) {
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c->h_poll + ssn_ctx::kPinDoubles);
+    unsigned long spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0xffffu) == 0) {                    // a failed kernel upstream would never publish: ask the stream
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) throw Error(SSN_E_CUDA, std::string("device read: ") + cudaGetErrorString(e));
+            if (e == cudaSuccess && *flag != seq) { SSN_CUDA(cudaStreamSynchronize(c->stream)); if (*flag != seq) throw Error(SSN_E_CUDA, "device read: the values never arrived"); }
+        }
+    }
+}
+}  // namespace
+
+void poll_read(ssn_ctx* c, const void* dev, size_t bytes) {
+    const unsigned long long seq = ++c->poll_seq;
+    unsigned long long* dflag = reinterpret_cast<unsigned long long*>(c->d_poll + ssn_ctx::kPinDoubles);
+    SSN_LAUNCH(c, poll_publish_kernel, 1, 256, 0, reinterpret_cast<const unsigned*>(dev), (int)(bytes / 4), reinterpret_cast<unsigned*>(c->d_poll), dflag, seq);
+    c->launches--;                                         // plumbing, not a kernel of the path
+    poll_wait(c, seq);
+}
+void poll_read_ints(ssn_ctx* c, const int* const* src, int k) {
+    const unsigned long long seq = ++c->poll_seq;
+    unsigned long long* dflag = reinterpret_cast<unsigned long long*>(c->d_poll + ssn_ctx::kPinDoubles);
+    SSN_LAUNCH(c, poll_publish_ints_kernel, 1, 32, 0, src[0], src[1], src[2], src[3], k, reinterpret_cast<int*>(c->d_poll), dflag, seq);
+    c->launches--;
+    poll_wait(c, seq);
+}
+
 void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
     if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return; }
     if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1); return; }

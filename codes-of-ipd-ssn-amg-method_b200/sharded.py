@@ -107,6 +107,9 @@ class ShardedStep:
         self.counts = [row_range(g, world, m)[1] - row_range(g, world, m)[0] for g in range(world)]
         self.collectives = 0
         self.screen = True
+        self.gather_cap_limit = 1 << 20                            # above this many active entries: sizes first, then payloads
+        self.profile = False                                       # True: device-synchronised phase times (ms_plan / ms_asat / ms_amg)
+        self.last_density = None                                   # share of entries that survived the last screened batch
         if inner_solver not in (4, 5):
             raise ValueError("inner_solver must be 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
         self.inner_solver = inner_solver
@@ -133,6 +136,29 @@ class ShardedStep:
         self.collectives += 1
         return torch.cat([o[:c] for o, c in zip(out, self.counts)])
 
+    def _gather_active(self, v, E):
+        """The ascending union of the ranks' active linear indices (``E`` of them in all, known from the residual's
+        all_reduce) with ONE collective and no host round trip: every rank contributes a fixed-capacity block padded
+        with INT64_MAX -- capacity = E rounded up to a power of two, which no rank's share can exceed -- and the sorted
+        gather's first ``E`` entries are ``find(s)``.  Early SsN steps with millions of active entries (the block would
+        be ``world`` times larger than the payload) take the two-phase path."""
+        torch = self.torch
+        if self.world == 1:
+            return v
+        if E > self.gather_cap_limit or v.numel() > E:
+            return torch.sort(self._all_gather_var(v))[0]
+        cap = 1 << max(10, int(E - 1).bit_length())
+        pad = torch.full((cap,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=v.device)
+        pad[: v.numel()] = v
+        out = torch.empty(self.world * cap, dtype=torch.int64, device=v.device)
+        if hasattr(self.dist, "all_gather_into_tensor"):
+            self.dist.all_gather_into_tensor(out, pad)
+        else:
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            self.dist.all_gather(parts, pad); out = torch.cat(parts)
+        self.collectives += 1
+        return torch.sort(out)[0][:E]
+
     def _all_gather_var(self, v):
         """all-gather of int64 vectors of different lengths (sizes first, then padded payloads)."""
         if self.world == 1:
@@ -156,10 +182,18 @@ class ShardedStep:
         want = ("Axprox", "s") if want_s else ("Axprox",)
         ev = self.ops.prox_residual(self.w_loc, self._lam_loc(lam), self.p_loc, self.q, self.tk, self.gama, want)
         ax = ev["Axprox"]
-        buf = torch.cat([ax[: self.n], torch.tensor([ev["norm2"], float(ev["count"])], dtype=ax.dtype, device=ax.device)])
-        self._all_reduce(buf)                                    # the path's one O(n) collective
-        rows = self._all_gather_rows(ax[self.n:])
-        return torch.cat([buf[: self.n], rows]), float(buf[self.n]), int(round(float(buf[self.n + 1]))), ev.get("s")
+        if self.world == 1:
+            return ax, float(ev["norm2"]), int(ev["count"]), ev.get("s")
+        # ONE collective per residual: column partials (n), this rank's row sums in their place of a zero-padded
+        # m-vector, and the two scalars, summed over the ranks
+        n, m = self.n, self.m
+        buf = torch.zeros(n + m + 2, dtype=ax.dtype, device=ax.device)
+        buf[:n] = ax[:n]
+        buf[n + self.r0: n + self.r1] = ax[n:]
+        buf[n + m:] = torch.tensor([ev["norm2"], float(ev["count"])], dtype=ax.dtype, device=ax.device)
+        self._all_reduce(buf)
+        tail = buf[n + m:].tolist()                              # the one device->host read of the evaluation
+        return buf[: n + m], float(tail[0]), int(round(tail[1])), ev.get("s")
 
     def trial_batch(self, lk, zeta, delta, ll0, nt, screened=False):
         """One read-sweep of the slab for nt Armijo trials: returns (lamT, values, density) with values
@@ -193,12 +227,16 @@ class ShardedStep:
             dens = float(part[nt]) / launches / max(1.0, float(self.m) * self.n)
         return (torch.cat(lams) if len(lams) > 1 else lams[0]), vals, dens
 
-    def assemble(self, s_loc):
-        """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged."""
+    def assemble(self, s_loc, E=None):
+        """H0 = ASAt(s,p,q) from the row-sharded active set: O(E) integers are exchanged.  ``E`` = nnz(s) over all
+        ranks when the caller knows it (it rides in the residual's all_reduce): one collective instead of two."""
         lin = self.ops.active_lin(s_loc, self.m_loc, self.n, self.r0, self.m)
-        lin_all = self._all_gather_var(lin)
-        if self.world > 1:
-            lin_all = self.torch.sort(lin_all)[0]                # global column-major order == find(s)
+        if self.world == 1:
+            lin_all = lin
+        elif E is not None:
+            lin_all = self._gather_active(lin, int(E))           # sorted: global column-major order == find(s)
+        else:
+            lin_all = self.torch.sort(self._all_gather_var(lin))[0]
         return self.ops.asat_from_lin(lin_all, self.p, self.q)
 
     def __call__(self):
@@ -217,7 +255,7 @@ class ShardedStep:
         import time as _time
         tm = {"plan": 0.0, "asat": 0.0, "amg": 0.0}
         def _lap(key, t0):
-            if torch.cuda.is_available():
+            if self.profile and torch.cuda.is_available():       # off in the timed path: a device synchronise per phase
                 torch.cuda.synchronize()
             tm[key] += (_time.perf_counter() - t0) * 1e3
         if reset_rng:
@@ -226,7 +264,7 @@ class ShardedStep:
         Axp, n2_old, E, s_loc = pre if pre is not None else self.residual(lk, True)  # :139-144
         Fk_old = bk1 * lk - Axp - wlk
         _lap("plan", t0); t0 = _time.perf_counter()
-        H0 = self.assemble(s_loc)                                                    # :142
+        H0 = self.assemble(s_loc, E)                                                 # :142
         _lap("asat", t0); t0 = _time.perf_counter()
         prob_data = {"bk1": bk1, "tk": tk, "q": self.q, "p": self.p, "T": None, "H0": H0, "z": -Fk_old}
         solve = self.ops.hybrid_amg if self.inner_solver == 4 else self.ops.hybrid_twogrid                # :161 / :178
@@ -241,16 +279,20 @@ class ShardedStep:
         # entries survive the screen, 16 under 25 %, else the dense 8-step kernel (as ssn_linesearch does)
         screened = np.isinf(self.gama) and self.gama > 0 and hasattr(self.ops, "prox_trials_lin") and self.screen
         ll, done, passes, dens = 0, False, 0, 1.0
-        while not done:                                                              # :189-211, ll = 0 alone, then a batch per pass
+        # the first read evaluates ll = 0 alone (most steps accept it) -- unless the previous step's trial plans were
+        # sparse (late phase: < 10 % of the entries survive the screen, long line searches): then a screened batch of
+        # 64 steps costs the same one read of the slab and saves a pass and a collective
+        first = 64 if (screened and self.last_density is not None and self.last_density <= 0.10) else 1
+        while not done:                                                              # :189-211
             lin = screened and (passes == 0 or dens <= 0.25)
             if lin and passes > 0:
-                nt = (64 if passes == 1 else 128) if dens <= 0.10 else 16
+                nt = (64 if passes == 1 and first == 1 else 128) if dens <= 0.10 else 16
             else:
                 nt = 8 * min(self.world, 4)
-            nt = min(1 if passes == 0 else nt, max_ll - ll + 1)
+            nt = min(first if passes == 0 else nt, max_ll - ll + 1)
             lamT, vals, d = self.trial_batch(lk, zeta, delta, ll, nt, screened=lin); passes += 1
             if d is not None:
-                dens = d
+                dens = d; self.last_density = d
             for t in range(nt):
                 f0 = bk1 / 2 * vals[nt + 2 * t] - vals[nt + 2 * t + 1]
                 if not (f0 + 0.5 * tk * vals[t] > cFk_old - nu * delta ** (ll + t) * ress) or ll + t == max_ll:

@@ -151,9 +151,10 @@ SSN_API int  ssn_set_persistent(ssn_ctx *ctx, int on);
 /* on != 0 (default): PCG's SSOR / IC(0) factors (precd 3 / 4), their dependency levels and row groups are built on
  * the device; 0 (env SSN_DEVICE_SETUP=0): on the host, once per call (kept as the cross-check of the device path). */
 SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
-/* on != 0 (default; env SSN_FUSED_SETUP): the levels of the Class_AMG hierarchy with N <= 4096 rows are coarsened by ONE
+/* on != 0 (env SSN_FUSED_SETUP=1): the levels of the Class_AMG hierarchy with N <= 4096 rows are coarsened by ONE
  * kernel (strength, MIS rounds, interpolation, Galerkin products, smoother data; sizes never leave the device);
- * 0: kernel by kernel like the large levels.  Same hierarchy bit for bit. */
+ * 0 (default): kernel by kernel like the large levels.  Same hierarchy bit for bit; the one-CTA kernel is
+ * latency-bound on a single SM and loses to the piecewise path on a B200, so it is opt-in. */
 SSN_API int  ssn_set_fused_setup(ssn_ctx *ctx, int on);
 /* on != 0 (default; env SSN_CLUSTER_SOLVE): Class_AMG's solve loop of a late-phase hierarchy (<= 2^20 nonzeros on the
  * explicit levels, env SSN_CLUSTER_MAXNNZ) runs inside ONE thread-block cluster; 0: always as the grid-wide kernel. */

@@ -59,6 +59,10 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum { cudaErrorNotReady = 600 };
+inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
+inline void __threadfence_system() {}
+inline long long clock64() { return (long long)std::chrono::steady_clock::now().time_since_epoch().count(); }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 
@@ -198,15 +202,16 @@ struct ssn_ctx {
     bool no_cluster = true;
     int64_t persist_max_nnz = (int64_t)1 << 40;
     bool persist = true, dense_tail = true;
-    int ls_max_nt = 128; bool ls_screen = true;
+    int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
     int small_scan_max = 1 << 14;
     bool device_setup = true;
-    bool fused_setup = true, cluster_solve = true;
+    bool fused_setup = true, cluster_solve = true;     // the emulated hierarchies go through the fused kernel (opt-in in the library)
     int64_t cluster_max_nnz = (int64_t)1 << 20;
     int dense_max_n = 2048;
     bool ktimer = false, prof = false;
     double* h_pin = nullptr;
     static constexpr int kPinDoubles = 4096;
+    bool poll_reads = false; double* h_poll = nullptr; double* d_poll = nullptr; unsigned long long poll_seq = 0;   // polled reads: GPU only
     ssn_ctx() { mt_state = (uint32_t*)std::calloc(625, sizeof(uint32_t)); h_pin = (double*)std::calloc(kPinDoubles, sizeof(double)); }
     ~ssn_ctx() { std::free(mt_state); std::free(h_pin); }
     ssn_ctx(const ssn_ctx&) = delete; ssn_ctx& operator=(const ssn_ctx&) = delete;

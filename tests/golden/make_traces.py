@@ -66,6 +66,14 @@ def main():
         P = problems.grid_problem_pot(64, seed=0)
         out = driver.APD_SsN_Class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], max_outer=outer or 3, verbose=True)
         record(f"class2_grid64_outer{outer or 3}", out, {"g": 64, "mu": P["mu"], "mass": float(P["phi"] @ out["xk"])})
+    elif what == "class2_grid64_nowarm":
+        # the APD / SsN loop of Class 2 from the trivial start (no A-ADMM iterations): the closed-form inverse of the warm
+        # start (Class2/invHHt.m:8-9, s = t - l'*Vl with t ~ m*n: "not robust", invAAt.m:6) loses ~eps*m*n, so two
+        # implementations leave the 100-iteration warm start of a 64x64 problem ~1e-3 apart in the duals and the loop
+        # cannot be compared step by step from there; from a common start it can
+        P = problems.grid_problem_pot(64, seed=0)
+        out = driver.APD_SsN_Class2(P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"], max_outer=outer or 3, warm_maxit=0, verbose=True)
+        record(f"class2_grid64_nowarm_outer{outer or 3}", out, {"g": 64, "mu": P["mu"], "mass": float(P["phi"] @ out["xk"])})
     elif what == "class1_grid":
         g = int(sys.argv[2]); outer = int(sys.argv[3]) if len(sys.argv) > 3 else None
         P = problems.grid_problem(g, seed=0)

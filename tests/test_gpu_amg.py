@@ -355,7 +355,7 @@ def test_wcycle_behaviour_on_large_disc_systems_matches_oracle(gpu, oracle, g, e
 @pytest.mark.parametrize("m,n,density,isnsp", [(400, 300, 0.01, 1), (900, 1000, 0.004, 1), (2500, 2300, 0.0015, 1), (2500, 2300, 0.0015, 0),
                                                (6000, 5000, 0.0008, 1)])
 def test_fused_small_level_setup_equals_piecewise(gpu, oracle, m, n, density, isnsp):
-    """The levels with N <= 4096 coarsened by ONE kernel (amg_setup_fused.cu, the default) against the same levels
+    """The levels with N <= 4096 coarsened by ONE kernel (amg_setup_fused.cu, opt-in) against the same levels
     built kernel by kernel: identical level sizes, A_k and Pro_k bit for bit, the same number of random draws, and
     the same Class_AMG run (cycle counts, histories, solution)."""
     pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=11 * m)
@@ -373,7 +373,7 @@ def test_fused_small_level_setup_equals_piecewise(gpu, oracle, m, n, density, is
             gpu.rng_reset()
             res[fused] += (gpu.Class_AMG(Ae, f, dict(o, guess=0.01 * np.random.RandomState(2).random_sample(m + n))),)
     finally:
-        gpu.set_fused_setup(True)
+        gpu.set_fused_setup(False)
     (lv0, drawn0, run0), (lv1, drawn1, run1) = res[False], res[True]
     assert [a.shape[0] for a, _ in lv1] == [a.shape[0] for a, _ in lv0]
     assert min(a.shape[0] for a, _ in lv0[1:]) <= 4096, "no small level: nothing was fused"

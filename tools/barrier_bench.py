@@ -9,7 +9,9 @@ from importlib import import_module
 
 lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
 ctx = lib.context()
-for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"), (1, "grid_barrier")):
+for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"), (1, "grid_barrier"),
+                    (2, "cluster barrier (release/acquire)"), (3, "global store + cluster barrier"), (4, "cluster barrier, relaxed arrive"),
+                    (5, "store + barrier + ld.cg gather"), (6, "store + barrier + L1-cached gather"), (2, "cluster barrier (release/acquire)")):
     v = ctypes.c_double(0.0)
     ctx.call("ssn_debug_barrier_bench", 2000, which, ctypes.byref(v))
-    print(f"{name:14s}: {v.value:8.0f} cycles per barrier")
+    print(f"{name:38s}: {v.value:8.0f} cycles per iteration", flush=True)
