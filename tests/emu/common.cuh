@@ -11,6 +11,9 @@
 // It checks indexing, ordering and arithmetic; it does not check what only the hardware can (memory ordering between
 // blocks, occupancy, cooperative launches, shared-memory capacity).
 #pragma once
+#ifndef SSN_EMU
+#define SSN_EMU 1      // sources that need a host variant of a device-only construct (cluster special registers / barriers) test this
+#endif
 
 #include <algorithm>
 #include <barrier>
@@ -80,6 +83,10 @@ inline bool threaded = false;                     // set by the harness: one hos
 inline thread_local WarpShared* warp = nullptr;
 inline thread_local BlockShared* block = nullptr;
 alignas(64) inline unsigned char dyn_smem[256 * 1024];
+// a thread-block cluster: all its blocks run at once, each with its own dynamic shared memory (cluster_smem[rank]) and
+// block barrier, and meet at cluster_bar (emu_launch_cluster)
+inline unsigned char* cluster_smem[16] = {nullptr};
+inline std::barrier<>* cluster_bar = nullptr;
 inline long host_reads = 0;                       // device->host reads (each one a stream synchronisation on the GPU)
 inline void need_threads(const char* what) {
     if (!warp) { std::fprintf(stderr, "emu: %s needs emu::threaded = true\n", what); std::abort(); }
@@ -298,6 +305,37 @@ inline void emu_launch(ssn_ctx* c, K kernel, dim3 grid, int block, A... args) {
             for (auto& th : threads) th.join();
         }
     }
+}
+// one cluster of `ncta` blocks, all resident at once: ncta * block host threads; dynamic shared memory of `smem` bytes per
+// block at emu::cluster_smem[blockIdx.x] (the kernel must not use static __shared__ variables: they would be shared)
+template <class K, class... A>
+inline void emu_launch_cluster(ssn_ctx* c, K kernel, int ncta, int block, size_t smem, A... args) {
+    c->launches++;
+    std::vector<std::vector<unsigned char>> mem((size_t)ncta, std::vector<unsigned char>(smem + 64, (unsigned char)0xA5));
+    std::barrier<> cbar(ncta * block);
+    emu::cluster_bar = &cbar;
+    std::vector<std::unique_ptr<emu::BlockShared>> bs;
+    std::vector<std::unique_ptr<emu::WarpShared>> ws;
+    const int wpb = (block + 31) / 32;
+    for (int b = 0; b < ncta; ++b) {
+        emu::cluster_smem[b] = mem[(size_t)b].data() + ((64 - ((uintptr_t)mem[(size_t)b].data() & 63)) & 63);
+        bs.emplace_back(new emu::BlockShared(block));
+        for (int w0 = 0; w0 < block; w0 += 32) ws.emplace_back(new emu::WarpShared(std::min(32, block - w0)));
+    }
+    std::vector<std::thread> threads;
+    threads.reserve((size_t)ncta * block);
+    for (int b = 0; b < ncta; ++b)
+        for (int t = 0; t < block; ++t)
+            threads.emplace_back([&, b, t] {
+                emu::block = bs[(size_t)b].get(); emu::warp = ws[(size_t)b * wpb + t / 32].get();
+                blockIdx.x = b; blockIdx.y = 0; threadIdx.x = t; blockDim.x = block; gridDim.x = ncta; gridDim.y = 1;
+                kernel(args...);
+                emu::warp->bar.arrive_and_drop();
+                emu::block->bar.arrive_and_drop();
+                cbar.arrive_and_drop();
+            });
+    for (auto& th : threads) th.join();
+    emu::cluster_bar = nullptr;
 }
 #define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, dim3(grid), (int)(block), __VA_ARGS__)
 

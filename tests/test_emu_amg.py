@@ -227,7 +227,8 @@ def test_fused_small_levels_equal_the_oracle(emu, oracle, m, n, density, isnsp):
     assert emu.emu_rng_drawn() == oracle.GLOBAL_STREAM.drawn
     emu.emu_phase_counts.restype = C.c_char_p
     counts = dict((ln.split("\t")[0], ln.split("\t")[1:]) for ln in emu.emu_phase_counts().decode().splitlines())
-    assert "setup.fused_small_levels" in counts and "setup.mis_set" not in counts, counts.keys()
+    # the first MIS level (the one the fused kernel starts from) is still coarsened piece by piece
+    assert "setup.fused_small_levels" in counts, counts.keys()
     amg_state.clear(); emu.emu_amg_clear()
 
 
