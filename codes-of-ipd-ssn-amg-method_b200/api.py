@@ -774,7 +774,7 @@ def set_fused_setup(enable=True):
 
 def set_cluster_solve(enable=True):
     """Class_AMG's solve loop inside one thread-block cluster (default) or grid-wide -- ``ssn_set_cluster_solve``."""
-    context().call("ssn_set_cluster_solve", 1 if enable else 0)
+    context().call("ssn_set_cluster_solve", int(enable) if not isinstance(enable, bool) else (2 if enable else 0))
 
 
 def set_device_setup(enable=True):

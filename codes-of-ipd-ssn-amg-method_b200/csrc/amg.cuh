@@ -116,8 +116,14 @@ void jk_system(ssn_ctx* c, const ssn_prob_data* pd, Csr& Jk);
 
 void debug_cycles(unsigned long long* out64, bool reset);
 void debug_cycles_persist(unsigned long long* out256, bool reset);
+void debug_cycles_dsm(unsigned long long* out256, bool reset);
 double barrier_bench(ssn_ctx* c, int iters, int which);
+double dsm_bench(ssn_ctx* c, int iters, int which_ng);
 void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
+// Class_AMG's solve loop in one 16-CTA cluster with the level vectors in distributed shared memory (amg_cluster.cu);
+// false: the hierarchy does not qualify, nothing was launched
+bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, double* hist, int hl,
+                       int* iout);
 
 // ---- dispatch (solvers.cu)
 void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm, int* r, int* ncomp);

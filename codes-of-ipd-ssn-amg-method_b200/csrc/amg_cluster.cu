@@ -14,6 +14,10 @@
 //     e_f = c + invV*(r_f - U*e_c - c*Axi_f), e_c = invT*(r_c - U'*e_f), which is the reference's
 //     e + c*xi + R*(g - c*Axi) with R = [invV 0; -invT*U'*invV invT] multiplied out (V, T diagonal): a third of the
 //     gathers of residual + coupled update;
+//   * what a sweep reads again and again never leaves the SM: row pointers, 1/diag and A*ones of a CTA's rows are staged
+//     in its shared memory, and inside a smoothing loop the first entries of a thread's rows (gather location + value)
+//     stay in REGISTERS across the sweeps -- every barrier.cluster acquire invalidates the L1, so anything fetched
+//     from global memory inside a pass costs an L2 round trip on the critical path;
 //   * the visiting order of the cycle is a host-made op list, reductions ride on the barrier through remote stores.
 // Levels below `kd` are applied as the dense cycle operator B_kd built by amg_solve.cu (build_dense_tail).
 // The kernel text also runs under the host emulation of tests/emu (SSN_EMU: a cluster of 16 x 64 host threads).
@@ -27,11 +31,12 @@ namespace {
 constexpr int kZT = 64;                         // threads per CTA
 typedef uintptr_t zaddr;                        // address of a shared-memory location of some CTA of the cluster
 #else
-constexpr int kZT = 1024;
+constexpr int kZT = 512;                        // 128 registers per thread: two row slots of a smoothing loop stay in registers
 typedef uint32_t zaddr;
 #endif
 constexpr int kZMaxL = 10;                      // explicit levels + the dense leaf
 constexpr int kZCta = 16;
+constexpr int kZSlots = 2;                      // rows per thread kept in registers by the smoothing loops
 constexpr int kZProgMax = 1024;
 constexpr int kZXs = 2048;                      // largest dense leaf
 
@@ -43,6 +48,7 @@ struct ZLevel {
     int N, Nf;                                  // Nf: rows of the first segment (bigraph level: fnode; else N)
     int rpf, rpc;                               // rows per CTA of the two segments
     int voff, stride, xslot, bigph;             // byte offset of the level's vectors in a CTA's shared memory, bytes per vector
+    int poff, rsbytes;                          // per-row block: int rs[nl + 2] (row bounds of A, both segments), dinv[nl], Axi[nl]
     int ltA, ltG, ltP, ltT;                     // log2(lanes per row): A (all rows), A (one segment), Pu, Td
     ZMat A, Pu, Td;                             // A_k ; Pro_{k+1} (rows of level k) ; Pro_k' (rows of level k)
     const double* dinv; const double* Axi; double xx; const double* B;
@@ -53,9 +59,10 @@ struct ZArgs {
     const double* b; double* x; double retol;
     double* relk; double* rho; int* it_out;     // it_out[2]: 0 ok, 1 the level-1 matrix is not [diag U; U' diag] (kernel did nothing)
     const int* prog; int nprog;
+    int noreg;                                  // development aid (env SSN_DSM_NOREG=1): the smoothing loops re-read their rows every sweep
 };
 
-constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffLv = 2048, kOffProg = 4096,
+constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffLv = 2048, kOffProg = 4096,
               kOffXs = 8192, kOffVec = kOffXs + kZXs * 8;
 static_assert(sizeof(ZLevel) * kZMaxL <= kOffProg - kOffLv, "level table does not fit its slot");
 
@@ -127,44 +134,119 @@ __device__ __forceinline__ void z_sum2(ZTeam& G, double& a, double& b) {
     ++G.flip;
 }
 
+__device__ __forceinline__ const int* z_rs(const ZTeam& G, const ZLevel& L) { return reinterpret_cast<const int*>(G.dsm + L.poff); }
+__device__ __forceinline__ const double* z_dinv(const ZTeam& G, const ZLevel& L) { return reinterpret_cast<const double*>(G.dsm + L.poff + L.rsbytes); }
+__device__ __forceinline__ const double* z_axi(const ZTeam& G, const ZLevel& L) { return z_dinv(G, L) + (L.rpf + L.rpc); }
+// entries [e0, e1) of local row l in the staged row bounds (the two segments are stored back to back, one sentinel each)
+__device__ __forceinline__ void z_bounds(const int* rs, const ZLevel& L, int l, int& e0, int& e1) {
+    const int i = l + (l >= L.rpf ? 1 : 0);
+    e0 = rs[i]; e1 = rs[i + 1];
+}
+__device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int segb) {
+    const bool second = (int)(lc & 0xffffffu) >= segb;
+    return filt == 0 || (second == (filt == 1));
+}
+
+// the same for ONE value (most reductions of the cycle): half the shuffles, half the registers
+__device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = kZT / 32;
+    a = warp_sum(a);
+    double* sm = reinterpret_cast<double*>(G.dsm) + (G.flip & 1) * 64;
+    if (lane == 0) sm[w] = a;
+    __syncthreads();
+    double* sl = reinterpret_cast<double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
+    if (w == 0) {
+        double ta = (lane < NW) ? sm[lane] : 0.0;
+        ta = warp_sum(ta);
+        if (lane < G.ncta) z_st(z_map(z_local(sl + 2 * G.rank), lane), ta);
+    }
+    z_barrier();
+    double s0 = 0.0;
+    for (int r = 0; r < G.ncta; ++r) s0 += sl[2 * r];
+    ++G.flip;
+    return s0;
+}
+
 // For the local rows [l0, l1) of level L (2^lt lanes per row): s = sum over the row's entries of M of value * v[column],
 // v the vector of the COLUMN level that starts `vb` bytes into every CTA's shared memory; filt = 1 / 2 keeps only the
 // entries whose column lies in the second / first segment (the two halves of the bigraph level); gather = false: s = 0.
+// rs: the staged row bounds of M (A of this level) or null (row pointers from global memory).
 // Then epi(l, row, s) on the row's first lane.  Ends WITHOUT a barrier.
 template <class Epi>
-__device__ __forceinline__ void z_rows(const ZTeam& G, const ZLevel& L, const ZMat& M, int lt, int l0, int l1, int vb, int filt,
-                                       int seg_bytes, bool gather, Epi&& epi) {
+__device__ __forceinline__ void z_rows(const ZTeam& G, const ZLevel& L, const ZMat& M, const int* rs, int lt, int l0, int l1, int vb,
+                                       int filt, int segb, bool gather, Epi&& epi) {
     const int tpr = 1 << lt, sub = threadIdx.x & (tpr - 1), rpt = kZT >> lt;
     for (int lb = l0; lb < l1; lb += rpt) {
         const int l = lb + (threadIdx.x >> lt);
         const int row = (l < l1) ? z_row(L, G.rank, l) : -1;
         double s = 0.0;
         if (row >= 0 && gather) {
-            int e = M.rp[row] + sub;
-            const int e1 = M.rp[row + 1];
+            int e, e1;
+            if (rs != nullptr) z_bounds(rs, L, l, e, e1); else { e = M.rp[row]; e1 = M.rp[row + 1]; }
+            e += sub;
             for (; e + 3 * tpr < e1; e += 4 * tpr) {
                 uint32_t lc[4]; double v[4], xv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { lc[u] = M.loc[e + u * tpr]; v[u] = M.cv[e + u * tpr]; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const bool second = (int)(lc[u] & 0xffffffu) >= seg_bytes;
-                    const bool keep = filt == 0 || (second == (filt == 1));
-                    xv[u] = keep ? z_gather(G, vb, lc[u]) : 0.0;
-                }
+                for (int u = 0; u < 4; ++u) xv[u] = z_keep(lc[u], filt, segb) ? z_gather(G, vb, lc[u]) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) s = fma(v[u], xv[u], s);
             }
             for (; e < e1; e += tpr) {
                 const uint32_t lc = M.loc[e];
-                const bool second = (int)(lc & 0xffffffu) >= seg_bytes;
-                const bool keep = filt == 0 || (second == (filt == 1));
-                if (keep) s = fma(M.cv[e], z_gather(G, vb, lc), s);
+                if (z_keep(lc, filt, segb)) s = fma(M.cv[e], z_gather(G, vb, lc), s);
             }
         }
         for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (row >= 0 && sub == 0) epi(l, row, s);
     }
+}
+
+// The first K entries (per lane) of ONE local row of A, kept in registers across the sweeps of a smoothing loop.
+template <int K>
+struct ZRow { uint32_t lc[K]; double cv[K]; unsigned mask; int e_more, e_end; };
+
+template <int K>
+__device__ __forceinline__ void z_row_load(const ZTeam& G, const ZLevel& L, int lt, int l, bool in_range, int filt, int segb, ZRow<K>& R) {
+    const int tpr = 1 << lt, sub = threadIdx.x & (tpr - 1);
+    int e0 = 0, e1 = 0;
+    if (in_range) z_bounds(z_rs(G, L), L, l, e0, e1);
+    e0 += sub;
+    R.mask = 0u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int e = e0 + k * tpr;
+        const bool has = e < e1;
+        R.lc[k] = has ? L.A.loc[e] : 0u;
+        R.cv[k] = has ? L.A.cv[e] : 0.0;
+        if (has && z_keep(R.lc[k], filt, segb)) R.mask |= 1u << k;
+    }
+    R.e_more = e0 + K * tpr; R.e_end = e1;
+}
+
+// lane-reduced A(row,:)*v from the registers (+ the entries past the K-th from global memory)
+template <int K>
+__device__ __forceinline__ double z_row_dot(const ZTeam& G, const ZLevel& L, const ZRow<K>& R, int lt, int vb, int filt, int segb) {
+    constexpr int B = (K % 6 == 0) ? 6 : 4;
+    static_assert(K % B == 0, "K must be a multiple of the gather batch");
+    const int tpr = 1 << lt;
+    double s = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += B) {
+        double xv[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) xv[u] = ((R.mask >> (k0 + u)) & 1u) ? z_gather(G, vb, R.lc[k0 + u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < B; ++u) s = fma(R.cv[k0 + u], xv[u], s);
+    }
+    for (int e = R.e_more; e < R.e_end; e += tpr) {
+        const uint32_t lc = L.A.loc[e];
+        if (z_keep(lc, filt, segb)) s = fma(L.A.cv[e], z_gather(G, vb, lc), s);
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
 }
 
 // loc tables of the rows this CTA owns (one thread per row); returns true when an off-diagonal entry joins two rows of
@@ -186,16 +268,34 @@ __device__ bool z_build_loc(const ZTeam& G, const ZLevel& Lrow, const ZLevel& Lc
     return bad;
 }
 
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+__device__ unsigned long long g_zdbg[256];
+#define ZDBG(op, level, call) do { const long long t0__ = clock64(); call; if (lead) { g_zdbg[(op) * 16 + (level)] += (unsigned long long)(clock64() - t0__); g_zdbg[128 + (op) * 16 + (level)] += 1ull; } } while (0)
+#else
+#define ZDBG(op, level, call) do { call; } while (0)
+#endif
+
 }  // namespace
+
+void debug_cycles_dsm(unsigned long long* out256, bool reset) {
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+    cudaMemcpyFromSymbol(out256, g_zdbg, sizeof(unsigned long long) * 256);
+    if (reset) { unsigned long long z[256] = {0}; cudaMemcpyToSymbol(g_zdbg, z, sizeof(z)); }
+#else
+    for (int i = 0; i < 256; ++i) out256[i] = 0ull;
+    (void)reset;
+#endif
+}
 
 #ifdef SSN_EMU
 void dsm_solve_kernel(const ZArgs a) {
     unsigned char* dsm = emu::cluster_smem[blockIdx.x];
 #else
-__global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
+__global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant__ ZArgs a) {
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
     ZTeam G{z_rank(), z_ncta(), 0, dsm, z_local(dsm)};
+    const bool lead = (G.rank == 0 && threadIdx.x == 0);
     ZLevel* sl = reinterpret_cast<ZLevel*>(dsm + kOffLv);
     int* prog = reinterpret_cast<int*>(dsm + kOffProg);
     double* st_sum_r = reinterpret_cast<double*>(dsm + kOffSumR);
@@ -214,6 +314,23 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
         if (k < kd) z_build_loc(G, sl[k], sl[k + 1], sl[k].Pu, false);
         if (k >= 1) z_build_loc(G, sl[k], sl[k - 1], sl[k].Td, false);
     }
+    // ---- row bounds of A, 1/diag, A*ones of this CTA's rows: shared memory
+    for (int k = 0; k <= kd; ++k) {
+        const ZLevel& L = sl[k];
+        int* rs = reinterpret_cast<int*>(dsm + L.poff);
+        const int f0 = min(G.rank * L.rpf, L.Nf), f1 = min(L.Nf, f0 + L.rpf);
+        const int c0 = min(L.Nf + G.rank * L.rpc, L.N), c1 = min(L.N, c0 + L.rpc);
+        for (int l = threadIdx.x; l <= L.rpf; l += kZT) rs[l] = L.A.rp[min(f0 + l, f1)];
+        for (int l = threadIdx.x; l <= L.rpc; l += kZT) rs[L.rpf + 1 + l] = L.A.rp[min(c0 + l, c1)];
+        if (k < kd) {
+            double* di = reinterpret_cast<double*>(dsm + L.poff + L.rsbytes);
+            double* ax = di + (L.rpf + L.rpc);
+            for (int l = threadIdx.x; l < L.rpf + L.rpc; l += kZT) {
+                const int row = z_row(L, G.rank, l);
+                di[l] = row >= 0 ? L.dinv[row] : 0.0; ax[l] = row >= 0 ? L.Axi[row] : 0.0;
+            }
+        }
+    }
     const ZLevel& L0 = sl[0];
     const int nl0 = L0.rpf + L0.rpc;
     double* x0 = z_vec(G, L0, L0.xslot);
@@ -228,14 +345,13 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
             return;
         }
     }
-    const bool lead = (G.rank == 0 && threadIdx.x == 0);
     const int smoth = a.smoth;
     const bool nsp = a.isnsp != 0;
 
     // r = b - A*x ; sum(r), sum(r^2)                                    Class_AMG.m:89 / :96,:102
     auto outer_residual = [&](double& s1, double& s2) {
         s1 = 0.0; s2 = 0.0;
-        z_rows(G, L0, L0.A, L0.ltA, 0, nl0, z_vb(L0, L0.xslot), 0, 0, true, [&](int l, int row, double s) {
+        z_rows(G, L0, L0.A, z_rs(G, L0), L0.ltA, 0, nl0, z_vb(L0, L0.xslot), 0, 0, true, [&](int l, int row, double s) {
             const double ri = a.b[row] - s; r0[l] = ri; s1 += ri; s2 = fma(ri, ri, s2);
         });
         z_sum2(G, s1, s2);
@@ -245,20 +361,56 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
         const ZLevel& L = sl[k];
         const int nl = L.rpf + L.rpc;
         const double* r = z_vec(G, L, ZV_R);
+        const double* dinv = z_dinv(G, L); const double* Axi = z_axi(G, L);
+        // the kernel-component coefficient xi'g / xx as a product with 1/xx (one rounding of difference, a division off the
+        // critical path of every sweep); 0 when the system is not treated as nearly singular
+        const double rxx = nsp ? 1.0 / L.xx : 0.0;
         int cur = st_cur[k];
-        for (int s = 0; s < smoth; ++s) {
-            const double coef = nsp ? (sr - dotAe) / L.xx : 0.0;
-            const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
-            double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
-            double part = 0.0, dummy = 0.0;
-            z_rows(G, L, L.A, L.ltA, 0, nl, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0, !ez, [&](int l, int row, double d) {
-                const double axi = L.Axi[row], di = L.dinv[row], ei = ez ? 0.0 : ec[l];
-                const double en = ei + coef + di * ((r[l] - d) - axi * coef);
-                ea[l] = en;
-                part = fma(axi, en, part);
-            });
-            z_sum2(G, part, dummy);
-            dotAe = part; cur ^= 1; ez = false;
+        if (!a.noreg && (nl << L.ltA) <= kZSlots * kZT) {
+            // every row of the slice has its own lanes: the row's entries stay in registers for all the sweeps
+            constexpr int K = 8;
+            const bool first = (threadIdx.x & ((1 << L.ltA) - 1)) == 0;
+            ZRow<K> R[kZSlots];
+            int l[kZSlots]; bool mine[kZSlots]; double axi[kZSlots], di[kZSlots], ri[kZSlots];
+#pragma unroll
+            for (int u = 0; u < kZSlots; ++u) {
+                l[u] = (threadIdx.x >> L.ltA) + u * (kZT >> L.ltA);
+                mine[u] = l[u] < nl && z_row(L, G.rank, l[u]) >= 0;
+                z_row_load<K>(G, L, L.ltA, l[u], mine[u], 0, 0, R[u]);
+                axi[u] = mine[u] ? Axi[l[u]] : 0.0; di[u] = mine[u] ? dinv[l[u]] : 0.0; ri[u] = mine[u] ? r[l[u]] : 0.0;
+            }
+            for (int s = 0; s < smoth; ++s) {
+                const double coef = (sr - dotAe) * rxx;
+                const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
+                double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
+                double d[kZSlots];
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, R[u], L.ltA, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0);
+                double part = 0.0;
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u)
+                    if (mine[u] && first) {
+                        const double ei = ez ? 0.0 : ec[l[u]];
+                        const double en = ei + coef + di[u] * ((ri[u] - d[u]) - axi[u] * coef);
+                        ea[l[u]] = en;
+                        part = fma(axi[u], en, part);
+                    }
+                dotAe = z_sum1(G, part); cur ^= 1; ez = false;
+            }
+        } else {
+            for (int s = 0; s < smoth; ++s) {
+                const double coef = (sr - dotAe) * rxx;
+                const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
+                double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
+                double part = 0.0;
+                z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0, !ez, [&](int l, int, double d) {
+                    const double axi = Axi[l], ei = ez ? 0.0 : ec[l];
+                    const double en = ei + coef + dinv[l] * ((r[l] - d) - axi * coef);
+                    ea[l] = en;
+                    part = fma(axi, en, part);
+                });
+                dotAe = z_sum1(G, part); cur ^= 1; ez = false;
+            }
         }
         st_cur[k] = cur;
         return dotAe;
@@ -267,47 +419,90 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
     auto gauss_seidel = [&](bool post, bool ez, double sr, double dotAe) -> double {
         const ZLevel& L = L0;
         const double* r = r0;
+        const double* dinv = z_dinv(G, L); const double* Axi = z_axi(G, L);
+        const double rxx = nsp ? 1.0 / L.xx : 0.0;
         double* e = z_vec(G, L, ZV_E);
         const int vbe = z_vb(L, ZV_E), segb = L.rpf * 8;
         // pre: first-segment rows with the kernel correction, then second-segment rows; post: the other way round
         const int a0 = post ? L.rpf : 0, a1 = post ? L.rpf + L.rpc : L.rpf;
         const int b0 = post ? 0 : L.rpf, b1 = post ? L.rpf : L.rpf + L.rpc;
-        for (int s = 0; s < smoth; ++s) {
-            const double coef = nsp ? (sr - dotAe) / L.xx : 0.0;
-            double part = 0.0, dummy = 0.0;
-            z_rows(G, L, L.A, L.ltG, a0, a1, vbe, post ? 2 : 1, segb, !ez, [&](int l, int row, double d) {
-                const double axi = L.Axi[row];
-                const double en = coef + L.dinv[row] * ((r[l] - d) - axi * coef);
-                e[l] = en;
-                part = fma(axi, en, part);
-            });
-            z_barrier();
-            z_rows(G, L, L.A, L.ltG, b0, b1, vbe, post ? 1 : 2, segb, true, [&](int l, int row, double d) {
-                const double en = L.dinv[row] * (r[l] - d);
-                e[l] = en;
-                part = fma(L.Axi[row], en, part);
-            });
-            z_sum2(G, part, dummy);
-            dotAe = part; ez = false;
+        const int fa = post ? 2 : 1, fb = post ? 1 : 2;
+        if (!a.noreg && (max(L.rpf, L.rpc) << L.ltG) <= kZSlots * kZT) {
+            constexpr int K = 4;
+            const bool first = (threadIdx.x & ((1 << L.ltG) - 1)) == 0;
+            ZRow<K> Ra[kZSlots], Rb[kZSlots];
+            int la[kZSlots], lb[kZSlots]; bool ma[kZSlots], mb[kZSlots];
+            double axa[kZSlots], dia[kZSlots], ra[kZSlots], axb[kZSlots], dib[kZSlots], rb[kZSlots];
+#pragma unroll
+            for (int u = 0; u < kZSlots; ++u) {
+                const int lq = (threadIdx.x >> L.ltG) + u * (kZT >> L.ltG);
+                la[u] = a0 + lq; lb[u] = b0 + lq;
+                ma[u] = la[u] < a1 && z_row(L, G.rank, la[u]) >= 0; mb[u] = lb[u] < b1 && z_row(L, G.rank, lb[u]) >= 0;
+                z_row_load<K>(G, L, L.ltG, la[u], ma[u], fa, segb, Ra[u]);
+                z_row_load<K>(G, L, L.ltG, lb[u], mb[u], fb, segb, Rb[u]);
+                axa[u] = ma[u] ? Axi[la[u]] : 0.0; dia[u] = ma[u] ? dinv[la[u]] : 0.0; ra[u] = ma[u] ? r[la[u]] : 0.0;
+                axb[u] = mb[u] ? Axi[lb[u]] : 0.0; dib[u] = mb[u] ? dinv[lb[u]] : 0.0; rb[u] = mb[u] ? r[lb[u]] : 0.0;
+            }
+            for (int s = 0; s < smoth; ++s) {
+                const double coef = (sr - dotAe) * rxx;
+                double part = 0.0;
+                double d[kZSlots];
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, Ra[u], L.ltG, vbe, fa, segb);
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u)
+                    if (ma[u] && first) { const double en = coef + dia[u] * ((ra[u] - d[u]) - axa[u] * coef); e[la[u]] = en; part = fma(axa[u], en, part); }
+                z_barrier();
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) d[u] = z_row_dot<K>(G, L, Rb[u], L.ltG, vbe, fb, segb);
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u)
+                    if (mb[u] && first) { const double en = dib[u] * (rb[u] - d[u]); e[lb[u]] = en; part = fma(axb[u], en, part); }
+                dotAe = z_sum1(G, part); ez = false;
+            }
+        } else {
+            for (int s = 0; s < smoth; ++s) {
+                const double coef = (sr - dotAe) * rxx;
+                double part = 0.0;
+                z_rows(G, L, L.A, z_rs(G, L), L.ltG, a0, a1, vbe, fa, segb, !ez, [&](int l, int, double d) {
+                    const double axi = Axi[l];
+                    const double en = coef + dinv[l] * ((r[l] - d) - axi * coef);
+                    e[l] = en;
+                    part = fma(axi, en, part);
+                });
+                z_barrier();
+                z_rows(G, L, L.A, z_rs(G, L), L.ltG, b0, b1, vbe, fb, segb, true, [&](int l, int, double d) {
+                    const double en = dinv[l] * (r[l] - d);
+                    e[l] = en;
+                    part = fma(Axi[l], en, part);
+                });
+                dotAe = z_sum1(G, part); ez = false;
+            }
         }
         return dotAe;
     };
 
-    double s1, s2;
-    outer_residual(s1, s2);
-    const double res0 = sqrt(s2);
-    double sum_r0 = s1;
-    double res_prev = res0, rel_prev = 1.0;
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+    const long long t_kernel = clock64();
+#endif
+    // the state of the outer loop lives in shared memory while a cycle runs (every thread holds the same values and writes
+    // them; registers are for the rows of the smoothing loops): [0] res0, [1] res_prev, [2] rel_prev
+    double* st_outer = reinterpret_cast<double*>(dsm + kOffOuter);
     int it = 0, hist = 1;
-    if (lead) { a.relk[0] = 1.0; a.rho[0] = NAN; a.it_out[2] = 0; }
-    if (res0 == 0.0) {
-        if (lead) { a.relk[0] = 0.0; a.rho[0] = INFINITY; a.it_out[0] = 0; a.it_out[1] = 1; }
-        z_barrier();
-        return;
+    {
+        double s1, s2;
+        outer_residual(s1, s2);
+        const double res0 = sqrt(s2);
+        st_outer[0] = res0; st_outer[1] = res0; st_outer[2] = 1.0; st_sum_r[0] = s1;
+        if (lead) { a.relk[0] = 1.0; a.rho[0] = NAN; a.it_out[2] = 0; }
+        if (res0 == 0.0) {
+            if (lead) { a.relk[0] = 0.0; a.rho[0] = INFINITY; a.it_out[0] = 0; a.it_out[1] = 1; }
+            z_barrier();
+            return;
+        }
     }
     it = 1;
-    while (rel_prev > a.retol && it <= a.maxit) {                       // Class_AMG.m:95
-        st_sum_r[0] = sum_r0;
+    while (st_outer[2] > a.retol && it <= a.maxit) {                    // Class_AMG.m:95
         for (int pc = 0; pc < a.nprog; ++pc) {
             const int op = prog[pc] & 0xff, k = (prog[pc] >> 8) & 0xff;
             const bool zero = ((prog[pc] >> 16) & 1) != 0;
@@ -318,31 +513,33 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
                 const double sr = st_sum_r[k];
                 const double d0 = (op == Z_PRE && zero) ? 0.0 : st_dot[k];
                 if (op == Z_PRE && zero) st_cur[k] = 0;
-                const double d = (k == 0 && L.bigph) ? gauss_seidel(post, op == Z_PRE && zero, sr, d0)
-                                                     : jacobi(k, op == Z_PRE && zero, sr, d0);
+                double d;
+                if (k == 0 && L.bigph) ZDBG(1, k, d = gauss_seidel(post, op == Z_PRE && zero, sr, d0));
+                else ZDBG(2, k, d = jacobi(k, op == Z_PRE && zero, sr, d0));
                 st_dot[k] = d;
             } else if (op == Z_RESTRICT) {                              // r_{k+1} = Pro' (r - A e)            MG_Wcycle.m:26
                 const double* r = z_vec(G, L, ZV_R);
                 double* g = z_vec(G, L, ZV_G);
                 const int es = (k == 0 && L.bigph) ? ZV_E : (st_cur[k] ? ZV_ALT : ZV_E);
-                z_rows(G, L, L.A, L.ltA, 0, nl, z_vb(L, es), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
-                z_barrier();
+                ZDBG(0, k, z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, es), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
+                z_barrier());
                 const ZLevel& Lc = sl[k + 1];
                 double* rc = z_vec(G, Lc, ZV_R);
-                double sy = 0.0, dummy = 0.0;
-                z_rows(G, Lc, Lc.Td, Lc.ltT, 0, Lc.rpf + Lc.rpc, z_vb(L, ZV_G), 0, 0, true, [&](int l, int, double d) { rc[l] = d; sy += d; });
-                z_sum2(G, sy, dummy);
+                double sy = 0.0;
+                ZDBG(3, k, z_rows(G, Lc, Lc.Td, nullptr, Lc.ltT, 0, Lc.rpf + Lc.rpc, z_vb(L, ZV_G), 0, 0, true, [&](int l, int, double d) { rc[l] = d; sy += d; });
+                sy = z_sum1(G, sy));
                 st_sum_r[k + 1] = sy;
             } else if (op == Z_PROLONG) {                               // e += Pro e_{k+1}, with Axi'e        MG_Wcycle.m:32
                 const ZLevel& Lc = sl[k + 1];
                 const int cs = (k + 1 == kd) ? ZV_E : (st_cur[k + 1] ? ZV_ALT : ZV_E);
                 const int es = (k == 0 && L.bigph) ? ZV_E : (st_cur[k] ? ZV_ALT : ZV_E);
                 double* e = z_vec(G, L, es);
-                double swy = 0.0, dummy = 0.0;
-                z_rows(G, L, L.Pu, L.ltP, 0, nl, z_vb(Lc, cs), 0, 0, true, [&](int l, int row, double d) {
-                    const double v = e[l] + d; e[l] = v; swy = fma(L.Axi[row], v, swy);
+                double swy = 0.0;
+                const double* Axi = z_axi(G, L);
+                ZDBG(3, k, z_rows(G, L, L.Pu, nullptr, L.ltP, 0, nl, z_vb(Lc, cs), 0, 0, true, [&](int l, int, double d) {
+                    const double v = e[l] + d; e[l] = v; swy = fma(Axi[l], v, swy);
                 });
-                z_sum2(G, swy, dummy);
+                swy = z_sum1(G, swy));
                 st_dot[k] = swy;
             } else {                                                    // Z_LEAF: e = B r, or e += B (r - A e)
                 const double* r = z_vec(G, L, ZV_R);
@@ -350,11 +547,14 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
                 int in_slot = ZV_R;
                 if (!zero) {
                     double* g = z_vec(G, L, ZV_G);
-                    z_rows(G, L, L.A, L.ltA, 0, nl, z_vb(L, ZV_E), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
-                    z_barrier();
+                    ZDBG(0, k, z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, ZV_E), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
+                    z_barrier());
                     in_slot = ZV_G;
                 }
                 const int n = L.N, vb = z_vb(L, in_slot);
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+                const long long t_leaf = clock64();
+#endif
                 for (int j = threadIdx.x; j < n; j += kZT) xs[j] = z_gather(G, vb, z_loc(L, j));
                 __syncthreads();
                 const int lane = threadIdx.x & 31;
@@ -374,6 +574,9 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
                     if (lane == 0) e[l] = zero ? s : (e[l] + s);
                 }
                 z_barrier();
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+                if (lead) { g_zdbg[4 * 16 + k] += (unsigned long long)(clock64() - t_leaf); g_zdbg[128 + 4 * 16 + k] += 1ull; }
+#endif
             }
         }
         // ---------------- x += e ; r = b - A*x ; res = norm(r)          Class_AMG.m:96-104
@@ -382,26 +585,113 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const ZArgs a) {
             for (int l = threadIdx.x; l < nl0; l += kZT) x0[l] += et[l];
             z_barrier();
         }
-        outer_residual(s1, s2);
-        sum_r0 = s1;
+        double s1, s2;
+        ZDBG(5, 0, outer_residual(s1, s2));
+        st_sum_r[0] = s1;
         const double res = sqrt(s2);
-        const double rel_res = res / res0, rho = res / res_prev;
+        const double rel_res = res / st_outer[0], rho = res / st_outer[1];
         if (lead) { a.relk[it] = rel_res; a.rho[it] = rho; }
-        res_prev = res; rel_prev = rel_res;
+        __syncthreads();                                                // every thread has read res_prev before it changes
+        st_outer[1] = res; st_outer[2] = rel_res;
         ++it; ++hist;
         if (rho > 1.0) break;                                           // Class_AMG.m:106
     }
     for (int l = threadIdx.x; l < nl0; l += kZT) { const int row = z_row(L0, G.rank, l); if (row >= 0) a.x[row] = x0[l]; }
     if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; }
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+    if (lead) { g_zdbg[7 * 16] += (unsigned long long)(clock64() - t_kernel); g_zdbg[128 + 7 * 16] += 1ull; }
+#endif
     z_barrier();                                            // no CTA exits while a peer may still read its shared memory
 }
 
 namespace {
 
-int z_log2_lanes(double avg, int rows) {
+#ifndef SSN_EMU
+// ---- micro-benchmarks of the building blocks of a pass (development aid, ssn_debug_barrier_bench which >= 10): one
+// cluster of 16 CTAs x kZT threads, `iters` iterations of
+//   10 z_sum1   11 z_barrier   12 NG gathers through ld.shared::cluster, all in flight, + barrier
+//   13 the same gathers in dependent batches of 4   14 NG gathers from global memory (ld.global.cg) + barrier
+//   15 NG gathers from the CTA's own shared memory + barrier   16 z_sum1 without its cluster barrier's remote stores
+//      (block reduction + barrier)   17 local store + relaxed-arrive barrier
+// ng = gathers per thread (<= 16); the gathered vector has 16 * 1024 doubles, indices pseudo-random
+__global__ void __launch_bounds__(kZT, 1) dsm_bench_kernel(double* gbuf, int iters, int which, int ng, long long* cycles_out) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    ZTeam G{z_rank(), z_ncta(), 0, dsm, z_local(dsm)};
+    double* v = reinterpret_cast<double*>(dsm + 4096);
+    for (int i = threadIdx.x; i < 1024; i += kZT) v[i] = 1.0 + i;
+    uint32_t lc[16]; int gi[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const unsigned h = (unsigned)(G.rank * kZT + threadIdx.x) * 2654435761u + (unsigned)u * 40503u;
+        const int idx = (int)((h >> 7) % (16u * 1024u));
+        gi[u] = idx; lc[u] = ((uint32_t)(idx >> 10) << 24) | (uint32_t)((idx & 1023) * 8);
+    }
+    z_barrier();
+    const long long t0 = clock64();
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        if (which == 10) acc += z_sum1(G, acc + threadIdx.x);
+        else if (which == 11) z_barrier();
+        else if (which == 12 || which == 13) {
+            double xv[16];
+            if (which == 12) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) xv[u] = (u < ng) ? z_gather(G, 4096, lc[u]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc = fma(1e-9, xv[u], acc);
+            } else {
+#pragma unroll
+                for (int u0 = 0; u0 < 16; u0 += 4) {
+#pragma unroll
+                    for (int u = u0; u < u0 + 4; ++u) xv[u] = (u < ng) ? z_gather(G, 4096, lc[u]) : 0.0;
+#pragma unroll
+                    for (int u = u0; u < u0 + 4; ++u) acc = fma(1e-9, xv[u], acc);
+                }
+            }
+            v[threadIdx.x] = acc;
+            z_barrier();
+        } else if (which == 14) {
+            double xv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) xv[u] = (u < ng) ? __ldcg(gbuf + gi[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fma(1e-9, xv[u], acc);
+            gbuf[G.rank * 1024 + threadIdx.x] = acc;
+            z_barrier();
+        } else if (which == 15) {
+            double xv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) xv[u] = (u < ng) ? v[gi[u] & 1023] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fma(1e-9, xv[u], acc);
+            __syncthreads();
+            v[threadIdx.x] = acc;
+            z_barrier();
+        } else if (which == 16) {
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            double a = warp_sum(acc + threadIdx.x);
+            double* sm = reinterpret_cast<double*>(dsm) + (it & 1) * 64;
+            if (lane == 0) sm[w] = a;
+            __syncthreads();
+            double t = 0.0;
+            for (int i = 0; i < kZT / 32; ++i) t += sm[i];
+            acc += t;
+            z_barrier();
+        } else {
+            v[threadIdx.x] = acc;
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+        }
+    }
+    if (G.rank == 0 && threadIdx.x == 0) cycles_out[0] = clock64() - t0;
+    if (acc == 123.456) gbuf[0] = acc;
+    z_barrier();
+}
+#endif
+
+int z_log2_lanes(double avg, int rows, int trips = 1) {
     int t = 1;
     while (t < 32 && (double)t * 4.0 < avg) t <<= 1;            // up to 4 entries per lane: one batch of gathers in flight
-    while (t > 1 && (int64_t)rows * t > kZT) t >>= 1;           // ... but every row of the slice in one trip if possible
+    while (t > 1 && (int64_t)rows * t > (int64_t)trips * kZT) t >>= 1;   // ... but every row of the slice in `trips` trips if possible
     int lt = 0;
     while ((1 << lt) < t) ++lt;
     return lt;
@@ -447,9 +737,12 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
         if (k == 0) { z.xslot = z.bigph ? ZV_ALT : 4; nvec = z.bigph ? 4 : 5; }     // the in-place smoother needs no ALT copy
         if (k == kd) nvec = 3;
         off += (size_t)nvec * z.stride;
+        z.poff = (int)off;
+        z.rsbytes = (((nl + 2) * 4 + 15) / 16) * 16;
+        off += (size_t)z.rsbytes + (k < kd ? (size_t)2 * (((nl * 8 + 15) / 16) * 16) : 0);
         const double avgA = L.N ? (double)L.A.nnz / L.N : 0.0;
-        z.ltA = z_log2_lanes(avgA, nl);
-        z.ltG = z_log2_lanes(avgA, std::max(z.rpf, z.rpc));
+        z.ltA = z_log2_lanes(avgA, nl, kZSlots);
+        z.ltG = z_log2_lanes(avgA, std::max(z.rpf, z.rpc), kZSlots);
         z.A = ZMat{L.A.ptr.p, L.A.idx.p, L.A.val.p, nullptr};
         z.Pu = ZMat{nullptr, nullptr, nullptr, nullptr}; z.Td = z.Pu;
         if (k < kd) {
@@ -506,6 +799,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
     a.b = b; a.x = x; a.retol = o.retol;
     a.relk = hist; a.rho = hist + hl; a.it_out = iout;
     a.prog = dprog.p; a.nprog = (int)prog.size();
+    { const char* e = getenv("SSN_DSM_NOREG"); a.noreg = (e && e[0] == '1') ? 1 : 0; }
     Phase ph(c, "solve.dsm_solve_kernel");
 #ifdef SSN_EMU
     emu_launch_cluster(c, dsm_solve_kernel, ncta, kZT, smem, a);
@@ -524,5 +818,23 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
 #endif
     return true;
 }
+
+#ifndef SSN_EMU
+// cycles per iteration of one of the building blocks above (which = 10..17; ng gathers per thread rides in which / 100)
+double dsm_bench(ssn_ctx* c, int iters, int which_ng) {
+    const int which = which_ng % 100, ng = std::max(1, std::min(16, which_ng / 100));
+    Buf<double> buf(c, 16 * 1024); buf.zero();
+    Buf<long long> out(c, 1);
+    const size_t smem = 4096 + 1024 * 8;
+    if (cudaFuncSetAttribute(dsm_bench_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { (void)cudaGetLastError(); return -1.0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kZCta); cfg.blockDim = dim3(kZT); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kZCta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, dsm_bench_kernel, buf.p, iters, which, ng, out.p) != cudaSuccess) { (void)cudaGetLastError(); return -1.0; }
+    return (double)read_scalar(c, out.p) / (double)iters;
+}
+#endif
 
 }  // namespace ssn

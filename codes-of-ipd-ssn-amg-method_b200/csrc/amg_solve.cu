@@ -1896,8 +1896,15 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
     Buf<double> hist(c, (size_t)2 * hl);
     Buf<int> iout(c, 4);
     a.relk = hist.p; a.rho = hist.p + hl; a.it_out = iout.p;
-    bool launched = false;
-    if (c->cluster_solve && nnz <= c->cluster_max_nnz) {
+    bool launched = false, have_hi = false;
+    int hi[4];
+    // ---- one cluster, level vectors in distributed shared memory (amg_cluster.cu); it reports a level-1 matrix whose
+    // diagonal blocks are not diagonal (the two-half-sweep smoother does not apply) without having changed x
+    if (c->cluster_solve && c->dsm_solve && nnz <= c->cluster_max_nnz && dsm_cluster_solve(c, H, b, x, o, wcycle, hist.p, hl, iout.p)) {
+        read_back(c, iout.p, hi, 4);
+        if (hi[2] == 0) { launched = true; have_hi = true; }
+    }
+    if (!launched && c->cluster_solve && nnz <= c->cluster_max_nnz) {
         // ---- one cluster: 16 CTAs (non-portable size) where the device can co-schedule them, else 8
         static int cluster_ctas = -1;                       // probed once per process
         const size_t smem = (size_t)200 * 1024;              // + 22 KB static (reduction slots, level tables, the dense tail input)
@@ -1958,8 +1965,7 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
         SSN_CUDA(cudaLaunchCooperativeKernel((void*)persist_solve_kernel, dim3(grid), dim3(kPT), args, smem, c->stream));
         c->launches++;
     }
-    int hi[4];
-    read_back(c, iout.p, hi, 4);
+    if (!have_hi) read_back(c, iout.p, hi, 4);
     it = hi[0];
     const int len = hi[1];
     std::vector<double> hh((size_t)2 * hl);

@@ -53,6 +53,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_CLUSTER_SOLVE"); c->cluster_solve = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_DSM_SOLVE"); c->dsm_solve = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_FUSED_SETUP"); c->fused_setup = (e && e[0] == '1'); }
     { const char* e = getenv("SSN_CLUSTER_MAXNNZ"); if (e && atoll(e) > 0) c->cluster_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
@@ -142,12 +143,12 @@ int ssn_kernel_timer_read(ssn_ctx* c, double* total_ms, int64_t* launches) {
     return SSN_OK;
 }
 int ssn_debug_barrier_bench(ssn_ctx* c, int iters, int which, double* cycles_per_barrier) {
-    return guarded(c, [&] { *cycles_per_barrier = barrier_bench(c, iters, which); });
+    return guarded(c, [&] { *cycles_per_barrier = (which % 100 >= 10) ? dsm_bench(c, iters, which) : barrier_bench(c, iters, which); });
 }
 int ssn_set_persistent(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->persist = on != 0; return SSN_OK; }
 int ssn_set_device_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->device_setup = on != 0; return SSN_OK; }
 int ssn_set_fused_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->fused_setup = on != 0; return SSN_OK; }
-int ssn_set_cluster_solve(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->cluster_solve = on != 0; return SSN_OK; }
+int ssn_set_cluster_solve(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->cluster_solve = on != 0; c->dsm_solve = on != 1; return SSN_OK; }
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;
@@ -171,7 +172,11 @@ int ssn_debug_cycles(ssn_ctx* c, unsigned long long* out64, int reset) {
     return guarded(c, [&] { sync(c); debug_cycles(out64, reset != 0); });
 }
 int ssn_debug_cycles_persist(ssn_ctx* c, unsigned long long* out256, int reset) {
-    return guarded(c, [&] { sync(c); debug_cycles_persist(out256, reset != 0); });
+    return guarded(c, [&] {
+        sync(c); debug_cycles_persist(out256, reset != 0);
+        unsigned long long z[256]; debug_cycles_dsm(z, reset != 0);       // the cluster kernel of amg_cluster.cu (only one of the two ran)
+        for (int i = 0; i < 256; ++i) out256[i] += z[i];
+    });
 }
 
 int ssn_rng_reset(ssn_ctx* c, uint32_t seed) { return guarded(c, [&] { rng_reset(c, seed); sync(c); }); }

@@ -157,7 +157,9 @@ SSN_API int  ssn_set_device_setup(ssn_ctx *ctx, int on);
  * latency-bound on a single SM and loses to the piecewise path on a B200, so it is opt-in. */
 SSN_API int  ssn_set_fused_setup(ssn_ctx *ctx, int on);
 /* on != 0 (default; env SSN_CLUSTER_SOLVE): Class_AMG's solve loop of a late-phase hierarchy (<= 2^20 nonzeros on the
- * explicit levels, env SSN_CLUSTER_MAXNNZ) runs inside ONE thread-block cluster; 0: always as the grid-wide kernel. */
+ * explicit levels, env SSN_CLUSTER_MAXNNZ) runs inside ONE thread-block cluster with the level vectors in the cluster's
+ * distributed shared memory; 1: inside one cluster with the vectors in global memory (env SSN_DSM_SOLVE=0); 0: always as
+ * the grid-wide kernel. */
 SSN_API int  ssn_set_cluster_solve(ssn_ctx *ctx, int on);
 /* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
  * 1 = the library's own barrier (development aid) */

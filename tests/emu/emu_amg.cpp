@@ -14,6 +14,7 @@ ssn_ctx* g_ctx = nullptr;
 ssn::Csr g_out[4];                                  // results of the last call, fetched with emu_fetch
 std::vector<uint8_t> g_flags[2];
 std::string g_err;
+int g_bigph = 1;                                    // amg_options.bigph of emu_amg_setup
 
 ssn_ctx* ctx() { if (!g_ctx) { g_ctx = new ssn_ctx(); emu::threaded = true; ssn::rng_reset(g_ctx, 5489u); } return g_ctx; }
 ssn::CsrView view(int64_t nr, int64_t nc, int64_t nnz, const int* ptr, const int* idx, const double* val) {
@@ -43,6 +44,7 @@ const char* emu_phase_counts() {
     return out.c_str();
 }
 void emu_phase_reset() { ssn::phase_counts.clear(); }
+void emu_set_bigph(int v) { g_bigph = v; }
 void emu_set_small_scan_max(int v) { ctx()->small_scan_max = v; }
 
 // Class_AMG's setup phase (AMG/Class_AMG.m:41-85): returns the number of levels; level k's matrix, prolongation and
@@ -50,7 +52,7 @@ void emu_set_small_scan_max(int v) { ctx()->small_scan_max = v; }
 int emu_amg_setup(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, double theta, int smoth, int isnsp, int fnode, int* levels) {
     return guarded([&] {
         ssn_amg_options o; std::memset(&o, 0, sizeof(o));
-        o.retol = 1e-11; o.maxit = 30; o.smoth = smoth; o.cycle = 'w'; o.theta = theta; o.bigph = 1; o.inter = 1; o.isnsp = isnsp; o.fnode = fnode;
+        o.retol = 1e-11; o.maxit = 30; o.smoth = smoth; o.cycle = 'w'; o.theta = theta; o.bigph = g_bigph; o.inter = 1; o.isnsp = isnsp; o.fnode = fnode;
         ssn::amg_setup(ctx(), view(n, n, nnz, ap, ai, av), ssn::resolve_options(&o));
         *levels = ctx()->hier->J;
     });
@@ -62,6 +64,31 @@ double emu_level(int k, int which) {
     return L.xx;
 }
 void emu_amg_clear() { ssn::amg_clear(ctx()); }
+
+// Class_AMG's solve loop on the live hierarchy through amg_cluster.cu (a cluster of 16 emulated CTAs): level kd is applied
+// as the dense cycle operator B (N_kd x N_kd, row-major, made by the test from the oracle's cycle).  status: -1 the
+// hierarchy did not qualify, else the kernel's it_out[2]
+int emu_dsm_solve(int kd, const double* B, const double* b, const double* guess, int isnsp, int wcycle, double retol, int maxit,
+                  double* x_out, int* it, double* relk, double* rho, int* hist_len, int* status) {
+    return guarded([&] {
+        ssn::Hierarchy& H = *ctx()->hier;
+        ssn::Level& L = H.lv[(size_t)kd];
+        L.B.alloc(ctx(), (size_t)L.N * L.N);
+        std::memcpy(L.B.p, B, sizeof(double) * (size_t)L.N * L.N);
+        H.dense_from = kd;
+        const int n = H.lv[0].N, hl = maxit + 2;
+        ssn::Buf<double> x(ctx(), (size_t)n), bb(ctx(), (size_t)n), hist(ctx(), (size_t)2 * hl);
+        ssn::Buf<int> iout(ctx(), 4);
+        std::memcpy(x.p, guess, sizeof(double) * n); std::memcpy(bb.p, b, sizeof(double) * n);
+        ssn::AmgOptions o{}; o.retol = retol; o.maxit = maxit; o.isnsp = isnsp;
+        const bool ok = ssn::dsm_cluster_solve(ctx(), H, bb.p, x.p, o, wcycle != 0, hist.p, hl, iout.p);
+        *status = ok ? iout.p[2] : -1;
+        if (!ok || iout.p[2] != 0) return;
+        *it = iout.p[0]; *hist_len = iout.p[1];
+        std::memcpy(relk, hist.p, sizeof(double) * iout.p[1]); std::memcpy(rho, hist.p + hl, sizeof(double) * iout.p[1]);
+        std::memcpy(x_out, x.p, sizeof(double) * n);
+    });
+}
 
 int emu_rng_reset() { return guarded([&] { ssn::rng_reset(ctx(), 5489u); }); }
 int64_t emu_rng_drawn() { return ctx()->rng_drawn; }

@@ -15,7 +15,7 @@ from conftest import random_active_problem
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     import emu_build
-    lib = emu_build.build(tmp_path_factory.mktemp("emu_amg"), "emu_amg.cpp", ["sparse.cu", "amg_setup.cu", "amg_setup_fused.cu", "amg.cuh", "sparse.cuh"],
+    lib = emu_build.build(tmp_path_factory.mktemp("emu_amg"), "emu_amg.cpp", ["sparse.cu", "amg_setup.cu", "amg_setup_fused.cu", "amg_cluster.cu", "amg.cuh", "sparse.cuh"],
                           "libemu_amg.so")
     lib.emu_error.restype = C.c_char_p
     lib.emu_rng_drawn.restype = C.c_int64
@@ -243,3 +243,54 @@ def test_scan_paths_agree(emu, oracle):
     finally:
         emu.emu_set_small_scan_max(C.c_int(1 << 14))
     assert_same_matrix(spgemm(emu, A, B), ref(A, B), "A*B, one-block scans")
+
+
+@pytest.mark.parametrize("m,n,density,isnsp,cycle,bigph,noreg", [(90, 70, 0.05, 1, "w", 1, 0), (90, 70, 0.05, 1, "w", 1, 1), (90, 70, 0.05, 0, "v", 1, 0),
+                                                                  (60, 50, 0.08, 1, "w", 0, 0), (60, 50, 0.08, 1, "w", 0, 1)])
+def test_dsm_cluster_solve_against_the_oracle(emu, oracle, monkeypatch, m, n, density, isnsp, cycle, bigph, noreg):
+    """amg_cluster.cu (Class_AMG's solve loop inside one cluster, level vectors in distributed shared memory, the
+    two-half-sweep form of the bigraph smoother, op list of the cycle) on a cluster of 16 emulated CTAs: cycle counts
+    and residual histories of the oracle's Class_AMG (AMG/Class_AMG.m:89-107), the solution to 1e-10."""
+    from oracle.amg import setup_hierarchy, amg_state, MG_Wcycle, MG_Vcycle, Class_AMG
+    monkeypatch.setenv("SSN_DSM_NOREG", str(noreg))     # 1: the smoothing loops re-read their rows every sweep (rows that do not fit the registers)
+    Ae = ssn_matrix(oracle, m, n, density, seed=7 * m)
+    if oracle.components(Ae)[1].size != 1:
+        pytest.skip("random active set is disconnected")
+    o = {"retol": 1e-11, "bigph": bigph, "maxit": 30, "theta": 0.25, "smoth": 3, "cycle": cycle, "isnsp": isnsp, "inter": 1, "guess": None, "fnode": n}
+    rs = np.random.RandomState(5)
+    b = rs.standard_normal(m + n)
+    if isnsp:
+        b -= b.mean()
+    guess = 0.01 * rs.standard_normal(m + n)
+    oracle.rng_reset()
+    x_ref, it_ref, rel_ref, relk_ref, rho_ref = Class_AMG(Ae, b, dict(o, guess=guess))
+    # the same hierarchy again, kept alive: the dense operator of level kd, column by column
+    oracle.rng_reset(); _check(emu, emu.emu_rng_reset())
+    st = setup_hierarchy(Ae, o)
+    J = st.J
+    assert J >= 3
+    kd = J - 2 if J >= 4 else J - 1
+    Nk = st.Ack[kd].shape[0]
+    cyc = MG_Wcycle if cycle == "w" else MG_Vcycle
+    B = np.column_stack([cyc(np.eye(Nk)[:, i], isnsp, kd + 1) for i in range(Nk)])
+    A1, a1 = _csr_args(Ae)
+    Jd = C.c_int(0)
+    emu.emu_set_bigph(C.c_int(bigph))
+    _check(emu, emu.emu_amg_setup(C.c_int64(m + n), C.c_int64(A1.nnz), _p(a1[0]), _p(a1[1]), _p(a1[2]), C.c_double(0.25), C.c_int(3), C.c_int(isnsp),
+                                  C.c_int(n), C.byref(Jd)))
+    emu.emu_set_bigph(C.c_int(1))
+    assert Jd.value == J
+    x = np.zeros(m + n); relk = np.zeros(40); rho = np.zeros(40)
+    it = C.c_int(0); hl = C.c_int(0); status = C.c_int(-7)
+    Bc = np.ascontiguousarray(B)
+    _check(emu, emu.emu_dsm_solve(C.c_int(kd), _p(Bc), _p(b), _p(guess), C.c_int(isnsp), C.c_int(1 if cycle == "w" else 0), C.c_double(1e-11),
+                                  C.c_int(30), _p(x), C.byref(it), _p(relk), _p(rho), C.byref(hl), C.byref(status)))
+    amg_state.clear(); emu.emu_amg_clear()
+    assert status.value == 0, status.value
+    assert it.value == it_ref and hl.value == len(relk_ref)
+    big = relk_ref > 1e-10
+    dev = np.max(np.abs(relk[:hl.value][big] - relk_ref[big]) / relk_ref[big])
+    print(f"dsm cluster solve {m}x{n} isnsp={isnsp} {cycle}-cycle bigph={bigph} noreg={noreg}: {it.value} cycles, history dev {dev:.1e}, "
+          f"solution {np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref):.1e}")
+    assert dev <= 1e-6, dev                                             # the leaf is PCG to 1e-11 in the oracle, a dense operator here
+    assert np.linalg.norm(x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)

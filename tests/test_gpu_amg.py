@@ -260,6 +260,44 @@ def test_persistent_solve_equals_launch_by_launch(gpu, oracle, cycle, m, n, dens
         assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
 
 
+@pytest.mark.parametrize("cycle,bigph", [("w", 1), ("v", 1), ("w", 0)])
+@pytest.mark.parametrize("m,n,density", [(2500, 2300, 0.0015), (6000, 5000, 0.0008)])
+def test_cluster_resident_solve_paths_agree(gpu, oracle, cycle, bigph, m, n, density):
+    """Class_AMG's solve loop inside one 16-CTA cluster with the level vectors in distributed shared memory (default,
+    amg_cluster.cu: two-half-sweep form of the bigraph smoother, gathers through ld.shared::cluster) against the first
+    cluster kernel (vectors in global memory) and the grid-wide cooperative kernel: same cycle counts, residual histories
+    to 1e-8 per entry above 1e-9, solutions to 1e-9; and the profile shows that the new kernel is the one that ran."""
+    pd, Ae, f = ssn_matrix(oracle, m, n, density, seed=7 * m)
+    guess = 0.01 * np.random.RandomState(3).random_sample(m + n)
+    out = {}
+    try:
+        for mode in (2, 1, 0):
+            gpu.set_cluster_solve(mode)
+            for isnsp in (1, 0):
+                o = dict(AMG_OPTS, fnode=n, cycle=cycle, guess=guess, isnsp=isnsp, bigph=bigph)
+                gpu.rng_reset()
+                if mode == 2 and isnsp == 1:
+                    gpu.profile(True)
+                out[mode, isnsp] = gpu.Class_AMG(Ae, f, o)
+                if mode == 2 and isnsp == 1:
+                    prof = gpu.profile_dump(); gpu.profile(False)
+                    if bigph:        # (the Jacobi-only hierarchy of the 6000 x 5000 case fills in past 2^20 nonzeros: grid-wide kernel)
+                        assert "solve.dsm_solve_kernel" in prof and "solve.cluster_solve_kernel" not in prof and "solve.persist_solve_kernel" not in prof, prof
+    finally:
+        gpu.set_cluster_solve(2); gpu.profile(False)
+    for isnsp in (1, 0):
+        x0, it0, rel0, relk0, rho0 = out[0, isnsp]
+        for mode in (1, 2):
+            x1, it1, rel1, relk1, rho1 = out[mode, isnsp]
+            assert it0 == it1 and len(relk0) == len(relk1), (mode, isnsp, it0, it1)
+            big = relk0 > 1e-9
+            dev = float(np.max(np.abs(relk1[big] - relk0[big]) / relk0[big]))
+            print(f"cluster solve mode {mode} vs grid-wide, {m}x{n} {cycle}-cycle bigph={bigph} isnsp={isnsp}: {it1} cycles, history dev {dev:.1e}, "
+                  f"solution {np.linalg.norm(x1 - x0) / np.linalg.norm(x0):.1e}")
+            assert dev <= 1e-8
+            assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+
+
 @pytest.mark.parametrize("precd", [1, 2, 5])
 def test_pcg_matches_oracle(gpu, oracle, precd):
     m, n = 300, 260

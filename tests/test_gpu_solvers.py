@@ -222,6 +222,45 @@ def test_full_size_128x128_grid_systems(gpu, oracle, tag):
 
 
 
+@pytest.mark.parametrize("tag", ["k30_s1", "k80_s2"])
+def test_full_size_systems_three_solve_kernels(gpu, tag):
+    """The same full-size systems through the three one-kernel forms of Class_AMG's solve loop -- cluster with the
+    vectors in distributed shared memory (default), cluster with the vectors in global memory, grid-wide cooperative
+    kernel: same cycle counts and component counts, solutions equal to 1e-9."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "ssn_states_g128.npz"))
+    g = int(d["g"]); m = n = g * g
+    s = torch.zeros(m * n, dtype=torch.uint8, device="cuda"); s[torch.from_numpy(d[tag + "_lin"]).cuda()] = 1
+    one = torch.ones(m, dtype=torch.float64, device="cuda")
+    H = gpu.ASAt(s, one, one)
+    del s
+    pd = {"bk1": float(d[tag + "_bk1"]), "tk": float(d[tag + "_tk"]), "p": np.ones(m), "q": np.ones(n), "T": None, "H0": H, "z": d[tag + "_z"]}
+    out = {}
+    try:
+        for mode in (2, 1, 0):
+            gpu.set_cluster_solve(mode)
+            gpu.rng_reset()
+            if mode == 2:
+                gpu.profile(True)
+            zeta, it, res, info = gpu.Hybrid_AMG(pd, AMG_OPTS)
+            if mode == 2:
+                prof = gpu.profile_dump(); gpu.profile(False)
+                assert "solve.dsm_solve_kernel" in prof and "solve.cluster_solve_kernel" not in prof, prof
+            out[mode] = (np.asarray(zeta.cpu() if hasattr(zeta, "cpu") else zeta).reshape(-1), it, res, list(info))
+    finally:
+        gpu.set_cluster_solve(2); gpu.profile(False)
+    z0, it0, res0, info0 = out[0]
+    for mode in (1, 2):
+        z1, it1, res1, info1 = out[mode]
+        print(f"{tag}: solve kernel {mode} vs grid-wide: {it1} cycles (grid-wide {it0}), residual {res1:.2e} ({res0:.2e}), "
+              f"solution dev {np.linalg.norm(z1 - z0) / np.linalg.norm(z0):.1e}")
+        assert it1 == it0 and info1 == info0
+        # each solve stops at a relative residual of 1e-11: the solutions agree to that times the conditioning of the state
+        assert np.linalg.norm(z1 - z0) <= 1e-7 * np.linalg.norm(z0)
+
+
 @pytest.mark.parametrize("dens,unit", [(0.25, True), (0.25, False), (0.02, False)])
 def test_hybrid_twogrid_matches_oracle(gpu, oracle, dens, unit):
     """Hybrid_twogrid.m / AMG/twogrid_bigph.m (inner_solver = 5) through the C ABI against the oracle: same

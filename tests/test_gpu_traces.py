@@ -79,14 +79,22 @@ def _check_steps(got, ref, k_strict=None):
     # accepted step lengths 0.9^ll: equal, or both below 1e-13 (a line search that backtracks to the rounding level)
     dstep = np.abs(0.9 ** g[:, 5] - 0.9 ** r[:, 5])
     assert np.all(dstep <= 1e-13), ("accepted backtracking exponents differ", g[:, 5], r[:, 5])
-    # |F| after each step: 1e-6 relative, plus what the inner solve leaves -- it stops at a relative residual of
-    # retol = 1e-11 of its right-hand side -F_old, and the two implementations stop at different residuals below that
-    # bound, so |F_new| carries an absolute term of that size times the conditioning of the step (bounded here by
-    # 1e-9 of the largest |F| of the same outer iteration).  Returns the worst deviation in units of that tolerance.
+    # |F| after each step.  The step solves J*zeta = -F_old to a relative RESIDUAL of retol = 1e-11, and J = bk1*I + H/tk is
+    # nearly singular (bk1 ~ 1e-4 against entries of H/tk ~ 1e3: condition 1e5..1e6), so two correct implementations agree
+    # in zeta -- and in |F_new| -- to retol*cond = 1e-6..1e-5 of the size of the step, not to 1e-8; the deviation does not
+    # accumulate (the next Newton step corrects it: the objective and duals above are at 1e-8).  Gate: 5e-6 of
+    # (|F| + the largest |F| of the same outer iteration); achieved on the B200: 2.0e-6 of |F| at config 2 (k=2, step 8),
+    # 1.6e-6 at config 1 (k=35).  Returns the worst deviation in units of the gate.
     fmax = np.array([r[r[:, 0] == k, 6].max() for k in r[:, 0]])
-    tol = 1e-6 * r[:, 6] + 1e-9 * fmax
+    tol = 5e-6 * (r[:, 6] + fmax)
     big = r[:, 6] > 1e-9
-    return float(np.max(np.abs(g[big, 6] - r[big, 6]) / tol[big])) if big.any() else 0.0
+    if not big.any():
+        return 0.0
+    use = np.abs(g[:, 6] - r[:, 6]) / tol * big
+    w = int(np.argmax(use))
+    print(f"   |F| worst step: k={int(r[w, 0])} it={int(r[w, 1])} |F| {g[w, 6]:.9e} vs {r[w, 6]:.9e} (rel {abs(g[w, 6] - r[w, 6]) / r[w, 6]:.1e}), "
+          f"largest |F| of that outer iteration {fmax[w]:.3e}, inner its {int(g[w, 4])} vs {int(r[w, 4])}")
+    return float(use[w])
 
 
 def _check_plan(x, T):
@@ -201,8 +209,8 @@ def test_config1_bundled500_full_solve(gpu, native):
     e_x = _check_plan(x, T)
     e_l = float(np.max(np.abs(_np(out["lk"]) - T["lk"])) / np.max(np.abs(T["lk"])))
     print(f"config 1 (bundled 500x500, 58 outer its, {len(T['steps'])} SsN steps): final objective {abs(f - f_ref) / f_ref:.1e}, "
-          f"objective history {e_f:.1e}, |F| {e_F:.1e}, duals {e_l:.1e}, plan(inf) {e_x:.1e}")
-    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= HIST_TOL
+          f"objective history {e_f:.1e}, |F| {e_F:.1e} of its tolerance, duals {e_l:.1e}, plan(inf) {e_x:.1e}")
+    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= HIST_TOL and e_F <= 1.0 and e_l <= 1e-8
 
 
 def test_config3_fixture_class2_bundled500_full_solve(gpu):
@@ -229,7 +237,7 @@ def test_config3_fixture_class2_bundled500_full_solve(gpu):
     assert abs(float(x.sum()) - float(D["mu"])) <= 1e-5 * (1 + float(D["mu"]))        # transported mass = mu (phi = 1)
     print(f"config 3 fixture (data4-500, {int(T['outer_its'])} outer its): final objective {abs(f - f_ref) / abs(f_ref):.1e}, "
           f"history {e_f:.1e}, |F| {e_F:.1e} of its tolerance, plan(inf) {e_x:.1e}")
-    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= HIST_TOL
+    assert abs(f - f_ref) <= OBJ_TOL * abs(f_ref) and e_f <= HIST_TOL and e_F <= 1.0
 
 
 def test_bench_state_fixture_is_the_state_of_the_device_solve(gpu):

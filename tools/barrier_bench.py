@@ -15,3 +15,13 @@ for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"
     v = ctypes.c_double(0.0)
     ctx.call("ssn_debug_barrier_bench", 2000, which, ctypes.byref(v))
     print(f"{name:38s}: {v.value:8.0f} cycles per iteration", flush=True)
+
+# building blocks of a pass of the DSMEM cluster solve kernel (amg_cluster.cu): 16 CTAs x 512 threads
+for which, name in ((10, "z_sum1 (cluster-wide sum of one double)"), (11, "z_barrier"), (16, "block reduction + barrier"), (17, "store + relaxed-arrive barrier"),
+                    (412, "4 DSMEM gathers + barrier"), (812, "8 DSMEM gathers + barrier"), (1612, "16 DSMEM gathers + barrier"),
+                    (813, "8 DSMEM gathers, batches of 4"), (1613, "16 DSMEM gathers, batches of 4"),
+                    (414, "4 L2 gathers + store + barrier"), (814, "8 L2 gathers + store + barrier"), (1614, "16 L2 gathers + store + barrier"),
+                    (815, "8 local smem gathers + barrier"), (1615, "16 local smem gathers + barrier")):
+    v = ctypes.c_double(0.0)
+    ctx.call("ssn_debug_barrier_bench", 2000, which, ctypes.byref(v))
+    print(f"{name:38s}: {v.value:8.0f} cycles per iteration", flush=True)
