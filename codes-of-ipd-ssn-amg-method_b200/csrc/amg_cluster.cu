@@ -108,7 +108,13 @@ __device__ __forceinline__ uint32_t z_loc(const ZLevel& L, int j) {
 }
 __device__ __forceinline__ double* z_vec(const ZTeam& G, const ZLevel& L, int slot) { return reinterpret_cast<double*>(G.dsm + L.voff + slot * L.stride); }
 __device__ __forceinline__ int z_vb(const ZLevel& L, int slot) { return L.voff + slot * L.stride; }
-__device__ __forceinline__ double z_gather(const ZTeam& G, int vb, uint32_t lc) { return z_ld(z_map(G.base + (zaddr)(vb + (int)(lc & 0xffffffu)), (int)(lc >> 24))); }
+// One element of a level vector: mapa + ld.shared::cluster.  (Measured on a B200, tools/barrier_bench.py: with 16 random
+// owner CTAs per warp instruction a 512-thread CTA completes only ~0.3 such loads per cycle -- against ~1 from L2 and ~10
+// from its own shared memory -- so what makes this kernel work is the locality of the OT graphs in the natural order:
+// most lanes of a warp instruction hit one or two owners.)
+__device__ __forceinline__ double z_gather(const ZTeam& G, int vb, uint32_t lc) {
+    return z_ld(z_map(G.base + (zaddr)(vb + (int)(lc & 0xffffffu)), (int)(lc >> 24)));
+}
 
 // cluster-wide sums of two per-thread values: ONE cluster barrier; fixed order, identical in every thread of the cluster
 __device__ __forceinline__ void z_sum2(ZTeam& G, double& a, double& b) {
@@ -147,7 +153,10 @@ __device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int segb) {
     return filt == 0 || (second == (filt == 1));
 }
 
-// the same for ONE value (most reductions of the cycle): half the shuffles, half the registers
+// the same for ONE value (most reductions of the cycle).  Stage 1: warp sums into shared memory, every thread of warp 0
+// adds the NW partials itself; stage 2: lanes 0..15 of warp 0 put the CTA's sum into slot [rank] of every CTA, ONE
+// cluster barrier, every thread adds the 16 slots.  (Sending the warp partials straight to every CTA -- no stage 1 --
+// was measured slower: 256 remote 8-byte stores per CTA cost more than the __syncthreads they save.)
 __device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = kZT / 32;
@@ -156,13 +165,15 @@ __device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
     if (lane == 0) sm[w] = a;
     __syncthreads();
     double* sl = reinterpret_cast<double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
-    if (w == 0) {
-        double ta = (lane < NW) ? sm[lane] : 0.0;
-        ta = warp_sum(ta);
-        if (lane < G.ncta) z_st(z_map(z_local(sl + 2 * G.rank), lane), ta);
+    if (w == 0 && lane < G.ncta) {
+        double ta = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ta += sm[i];
+        z_st(z_map(z_local(sl + 2 * G.rank), lane), ta);
     }
     z_barrier();
     double s0 = 0.0;
+#pragma unroll 4
     for (int r = 0; r < G.ncta; ++r) s0 += sl[2 * r];
     ++G.flip;
     return s0;
@@ -204,9 +215,10 @@ __device__ __forceinline__ void z_rows(const ZTeam& G, const ZLevel& L, const ZM
     }
 }
 
-// The first K entries (per lane) of ONE local row of A, kept in registers across the sweeps of a smoothing loop.
+// The first K entries (per lane) of ONE local row of A, kept in registers across the sweeps of a smoothing loop: value and
+// RESOLVED shared-window address of the column's element in vector slot 0 of the level, so a gather is an add and a load.
 template <int K>
-struct ZRow { uint32_t lc[K]; double cv[K]; unsigned mask; int e_more, e_end; };
+struct ZRow { zaddr ad[K]; double cv[K]; unsigned mask; int e_more, e_end; };
 
 template <int K>
 __device__ __forceinline__ void z_row_load(const ZTeam& G, const ZLevel& L, int lt, int l, bool in_range, int filt, int segb, ZRow<K>& R) {
@@ -219,31 +231,29 @@ __device__ __forceinline__ void z_row_load(const ZTeam& G, const ZLevel& L, int 
     for (int k = 0; k < K; ++k) {
         const int e = e0 + k * tpr;
         const bool has = e < e1;
-        R.lc[k] = has ? L.A.loc[e] : 0u;
+        const uint32_t lc = has ? L.A.loc[e] : 0u;
         R.cv[k] = has ? L.A.cv[e] : 0.0;
-        if (has && z_keep(R.lc[k], filt, segb)) R.mask |= 1u << k;
+        R.ad[k] = z_map(G.base + (zaddr)(L.voff + (int)(lc & 0xffffffu)), (int)(lc >> 24));
+        if (has && z_keep(lc, filt, segb)) R.mask |= 1u << k;
     }
     R.e_more = e0 + K * tpr; R.e_end = e1;
 }
 
-// lane-reduced A(row,:)*v from the registers (+ the entries past the K-th from global memory)
+// lane-reduced A(row,:)*v from the registers (+ the entries past the K-th from global memory); vrel: byte offset of the
+// gathered vector from vector slot 0 of the level.  All K gathers are issued before the first product.
 template <int K>
-__device__ __forceinline__ double z_row_dot(const ZTeam& G, const ZLevel& L, const ZRow<K>& R, int lt, int vb, int filt, int segb) {
-    constexpr int B = (K % 6 == 0) ? 6 : 4;
-    static_assert(K % B == 0, "K must be a multiple of the gather batch");
+__device__ __forceinline__ double z_row_dot(const ZTeam& G, const ZLevel& L, const ZRow<K>& R, int lt, int vrel, int filt, int segb) {
     const int tpr = 1 << lt;
+    double xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = ((R.mask >> k) & 1u) ? z_ld(R.ad[k] + (zaddr)vrel) : 0.0;
     double s = 0.0;
 #pragma unroll
-    for (int k0 = 0; k0 < K; k0 += B) {
-        double xv[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) xv[u] = ((R.mask >> (k0 + u)) & 1u) ? z_gather(G, vb, R.lc[k0 + u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < B; ++u) s = fma(R.cv[k0 + u], xv[u], s);
-    }
+    for (int k = 0; k < K; ++k) s = fma(R.cv[k], xv[k], s);
+#pragma unroll 1
     for (int e = R.e_more; e < R.e_end; e += tpr) {
         const uint32_t lc = L.A.loc[e];
-        if (z_keep(lc, filt, segb)) s = fma(L.A.cv[e], z_gather(G, vb, lc), s);
+        if (z_keep(lc, filt, segb)) s = fma(L.A.cv[e], z_gather(G, L.voff + vrel, lc), s);
     }
     for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -251,7 +261,7 @@ __device__ __forceinline__ double z_row_dot(const ZTeam& G, const ZLevel& L, con
 
 // loc tables of the rows this CTA owns (one thread per row); returns true when an off-diagonal entry joins two rows of
 // the same segment (the two-half-sweep smoother needs V and T diagonal)
-__device__ bool z_build_loc(const ZTeam& G, const ZLevel& Lrow, const ZLevel& Lcol, const ZMat& M, bool check) {
+__device__ __noinline__ bool z_build_loc(const ZTeam& G, const ZLevel& Lrow, const ZLevel& Lcol, const ZMat& M, bool check) {
     bool bad = false;
     if (M.rp == nullptr) return false;
     const int nl = Lrow.rpf + Lrow.rpc;
@@ -266,6 +276,58 @@ __device__ bool z_build_loc(const ZTeam& G, const ZLevel& Lrow, const ZLevel& Lc
         }
     }
     return bad;
+}
+
+// The smoothing loops for slices that do not fit the register slots (larger systems; the host emulation's small CTAs):
+// every sweep re-reads its rows.  Out of line: the cycle's hot code stays small enough for the instruction cache.
+struct ZStream { double dot; int cur, flip; };
+
+__device__ __noinline__ ZStream z_jacobi_stream(ZTeam G, const ZLevel& L, int smoth, double rxx, bool ez, double sr, double dotAe, int cur) {
+    const int nl = L.rpf + L.rpc;
+    const double* r = z_vec(G, L, ZV_R);
+    const double* dinv = z_dinv(G, L); const double* Axi = z_axi(G, L);
+    for (int s = 0; s < smoth; ++s) {
+        const double coef = (sr - dotAe) * rxx;
+        const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
+        double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
+        double part = 0.0;
+        z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0, !ez, [&](int l, int, double d) {
+            const double axi = Axi[l], ei = ez ? 0.0 : ec[l];
+            const double en = ei + coef + dinv[l] * ((r[l] - d) - axi * coef);
+            ea[l] = en;
+            part = fma(axi, en, part);
+        });
+        dotAe = z_sum1(G, part); cur ^= 1; ez = false;
+    }
+    return ZStream{dotAe, cur, G.flip};
+}
+
+__device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth, double rxx, bool post, bool ez, double sr, double dotAe) {
+    const double* r = z_vec(G, L, ZV_R);
+    const double* dinv = z_dinv(G, L); const double* Axi = z_axi(G, L);
+    double* e = z_vec(G, L, ZV_E);
+    const int vbe = z_vb(L, ZV_E), segb = L.rpf * 8;
+    const int a0 = post ? L.rpf : 0, a1 = post ? L.rpf + L.rpc : L.rpf;
+    const int b0 = post ? 0 : L.rpf, b1 = post ? L.rpf : L.rpf + L.rpc;
+    const int fa = post ? 2 : 1, fb = post ? 1 : 2;
+    for (int s = 0; s < smoth; ++s) {
+        const double coef = (sr - dotAe) * rxx;
+        double part = 0.0;
+        z_rows(G, L, L.A, z_rs(G, L), L.ltG, a0, a1, vbe, fa, segb, !ez, [&](int l, int, double d) {
+            const double axi = Axi[l];
+            const double en = coef + dinv[l] * ((r[l] - d) - axi * coef);
+            e[l] = en;
+            part = fma(axi, en, part);
+        });
+        z_barrier();
+        z_rows(G, L, L.A, z_rs(G, L), L.ltG, b0, b1, vbe, fb, segb, true, [&](int l, int, double d) {
+            const double en = dinv[l] * (r[l] - d);
+            e[l] = en;
+            part = fma(Axi[l], en, part);
+        });
+        dotAe = z_sum1(G, part); ez = false;
+    }
+    return ZStream{dotAe, 0, G.flip};
 }
 
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
@@ -385,7 +447,7 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
                 double d[kZSlots];
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, R[u], L.ltA, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0);
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, R[u], L.ltA, (cur ? ZV_ALT : ZV_E) * L.stride, 0, 0);
                 double part = 0.0;
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
@@ -398,19 +460,8 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 dotAe = z_sum1(G, part); cur ^= 1; ez = false;
             }
         } else {
-            for (int s = 0; s < smoth; ++s) {
-                const double coef = (sr - dotAe) * rxx;
-                const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
-                double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
-                double part = 0.0;
-                z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0, !ez, [&](int l, int, double d) {
-                    const double axi = Axi[l], ei = ez ? 0.0 : ec[l];
-                    const double en = ei + coef + dinv[l] * ((r[l] - d) - axi * coef);
-                    ea[l] = en;
-                    part = fma(axi, en, part);
-                });
-                dotAe = z_sum1(G, part); cur ^= 1; ez = false;
-            }
+            const ZStream o = z_jacobi_stream(G, L, smoth, rxx, ez, sr, dotAe, cur);
+            dotAe = o.dot; cur = o.cur; G.flip = o.flip;
         }
         st_cur[k] = cur;
         return dotAe;
@@ -448,36 +499,21 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 double part = 0.0;
                 double d[kZSlots];
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, Ra[u], L.ltG, vbe, fa, segb);
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, Ra[u], L.ltG, ZV_E * L.stride, fa, segb);
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
                     if (ma[u] && first) { const double en = coef + dia[u] * ((ra[u] - d[u]) - axa[u] * coef); e[la[u]] = en; part = fma(axa[u], en, part); }
                 z_barrier();
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = z_row_dot<K>(G, L, Rb[u], L.ltG, vbe, fb, segb);
+                for (int u = 0; u < kZSlots; ++u) d[u] = z_row_dot<K>(G, L, Rb[u], L.ltG, ZV_E * L.stride, fb, segb);
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
                     if (mb[u] && first) { const double en = dib[u] * (rb[u] - d[u]); e[lb[u]] = en; part = fma(axb[u], en, part); }
                 dotAe = z_sum1(G, part); ez = false;
             }
         } else {
-            for (int s = 0; s < smoth; ++s) {
-                const double coef = (sr - dotAe) * rxx;
-                double part = 0.0;
-                z_rows(G, L, L.A, z_rs(G, L), L.ltG, a0, a1, vbe, fa, segb, !ez, [&](int l, int, double d) {
-                    const double axi = Axi[l];
-                    const double en = coef + dinv[l] * ((r[l] - d) - axi * coef);
-                    e[l] = en;
-                    part = fma(axi, en, part);
-                });
-                z_barrier();
-                z_rows(G, L, L.A, z_rs(G, L), L.ltG, b0, b1, vbe, fb, segb, true, [&](int l, int, double d) {
-                    const double en = dinv[l] * (r[l] - d);
-                    e[l] = en;
-                    part = fma(Axi[l], en, part);
-                });
-                dotAe = z_sum1(G, part); ez = false;
-            }
+            const ZStream o = z_gs_stream(G, L, smoth, rxx, post, ez, sr, dotAe);
+            dotAe = o.dot; G.flip = o.flip;
         }
         return dotAe;
     };
