@@ -459,7 +459,7 @@ constexpr int kDTW = kDT / 32;
 
 // row stride (in doubles) of the [row][column] multi-vector layout in shared memory: C + 1 keeps the
 // gathers x[idx[e]][c] of a warp spread over the banks (a stride of C = 8 doubles maps them onto 2)
-template <int C> struct MV { static constexpr int S = (C == 1) ? 1 : C + 1; };
+template <int C> struct MV { static constexpr int S = (C == 1) ? 1 : ((C % 2 == 0) ? C + 1 : C + 2); };   // an odd stride
 
 template <int C>
 __device__ __forceinline__ void block_sumC(double (&v)[C], double* red, int& flip) {
@@ -1814,9 +1814,13 @@ void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
         Level& Lc = H.lv[k + 1];
         const LevelDev Lcd = level_dev(Lc);
         const int twice = (wcycle && (k + 1 != J - 1)) ? 1 : 0;
-        int C = N > 592 ? 8 : (N > 296 ? 4 : (N > 148 ? 2 : 1));
-        auto smem_for = [&](int cc) { return sizeof(double) * (size_t)(cc == 1 ? 1 : cc + 1) * (3 * (size_t)N + 3 * (size_t)Lc.N); };
-        while (C > 1 && smem_for(C) > 200 * 1024) C >>= 1;
+        // columns per CTA: the fewest that still cover the level in ONE wave of CTAs (a CTA's time grows with its columns,
+        // and a level of 651 rows at 8 columns per CTA would use 82 of the 148 SMs)
+        auto stride_of = [](int cc) { return cc == 1 ? 1 : (cc % 2 == 0 ? cc + 1 : cc + 2); };
+        auto smem_for = [&](int cc) { return sizeof(double) * (size_t)stride_of(cc) * (3 * (size_t)N + 3 * (size_t)Lc.N); };
+        int C = 8;
+        for (int cc : {1, 2, 3, 4, 5, 6, 8}) if (cdiv(N, cc) <= c->num_sms) { C = cc; break; }
+        while (C > 1 && smem_for(C) > 200 * 1024) C = (C == 8) ? 6 : C - 1;
         const size_t smem = smem_for(C);
         const int grid = cdiv(N, C);
         auto go = [&](auto T) {
@@ -1824,10 +1828,15 @@ void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
             SSN_CUDA(cudaFuncSetAttribute(dense_build_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SSN_LAUNCH(c, dense_build_kernel<CC>, grid, kDT, smem, Ld, Lcd, Lc.B.p, H.smoth, isnsp, twice, L.B.p);
         };
-        if (C == 8) go(std::integral_constant<int, 8>());
-        else if (C == 4) go(std::integral_constant<int, 4>());
-        else if (C == 2) go(std::integral_constant<int, 2>());
-        else go(std::integral_constant<int, 1>());
+        switch (C) {
+            case 8: go(std::integral_constant<int, 8>()); break;
+            case 6: go(std::integral_constant<int, 6>()); break;
+            case 5: go(std::integral_constant<int, 5>()); break;
+            case 4: go(std::integral_constant<int, 4>()); break;
+            case 3: go(std::integral_constant<int, 3>()); break;
+            case 2: go(std::integral_constant<int, 2>()); break;
+            default: go(std::integral_constant<int, 1>()); break;
+        }
     }
     H.dense_from = from;
     H.hdev.resize(J);

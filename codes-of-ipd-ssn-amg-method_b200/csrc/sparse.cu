@@ -17,7 +17,10 @@ namespace {
 // Used up to ssn_ctx::small_scan_max counts (16384; env SSN_SMALL_SCAN_MAX): every thread walks its own
 // contiguous chunk, so beyond that the single block loses to cub (launch list of round 1: 3-4 us up to 8k
 // counts, 10 us at 16k, 18 us at 32k, 59 us at 130k+).
-__global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* out, int n, int with_total) {
+// pub_host != null: the total also goes to mapped pinned host memory, followed by the sequence word the host polls
+// (scan_counts_to_ptr: the read of the total rides in the scan instead of a publish kernel of its own).
+__global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* out, int n, int with_total, int* pub_host,
+                                                          volatile unsigned long long* flag_host, unsigned long long seq) {
     __shared__ int wsum[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (n + 1023) / 1024;
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* ou
     int run = wsum[warp] + incl - s;
     for (int i = i0; i < i1; ++i) { const int v = in[i]; out[i] = run; run += v; }
     if (with_total && threadIdx.x == 1023) out[n] = run;
+    if (pub_host != nullptr && threadIdx.x == 1023) { pub_host[0] = run; __threadfence_system(); *flag_host = seq; }
 }
 }  // namespace
 
@@ -92,7 +96,7 @@ void poll_read_ints(ssn_ctx* c, const int* const* src, int k) {
 
 void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
     if (n == 0) { SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream)); return; }
-    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1); return; }
+    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1, (int*)nullptr, (volatile unsigned long long*)nullptr, 0ull); return; }
     SSN_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int), c->stream));
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, counts, ptr + 1, (int)n, c->stream));
@@ -102,6 +106,14 @@ void scan_counts_async(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
 }
 
 int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
+    if (n > 0 && n <= c->small_scan_max && c->poll_reads && c->h_poll) {
+        // one launch: the scan publishes its total to the host itself
+        const unsigned long long seq = ++c->poll_seq;
+        unsigned long long* dflag = reinterpret_cast<unsigned long long*>(c->d_poll + ssn_ctx::kPinDoubles);
+        SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, counts, ptr, (int)n, 1, reinterpret_cast<int*>(c->d_poll), (volatile unsigned long long*)dflag, seq);
+        poll_wait(c, seq);
+        return (int64_t)*reinterpret_cast<const int*>(c->h_poll);
+    }
     scan_counts_async(c, counts, ptr, n);
     if (n == 0) return 0;
     return (int64_t)read_scalar(c, ptr + n);
@@ -109,7 +121,7 @@ int64_t scan_counts_to_ptr(ssn_ctx* c, const int* counts, int* ptr, int64_t n) {
 
 void exclusive_scan_int(ssn_ctx* c, const int* in, int* out, int64_t n) {
     if (n == 0) return;
-    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, in, out, (int)n, 0); return; }
+    if (n <= c->small_scan_max) { SSN_LAUNCH(c, small_scan_kernel, 1, 1024, 0, in, out, (int)n, 0, (int*)nullptr, (volatile unsigned long long*)nullptr, 0ull); return; }
     size_t tmp_bytes = 0;
     SSN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, c->stream));
     Buf<unsigned char> tmp(c, tmp_bytes);
