@@ -305,6 +305,13 @@ def main():
                                  "frac_of_n_gpus_x_peak": plan_reads * 8.0 * m * n / (info["ms_plan"] * 1e-3) / 1e9 / (peak * world),
                                  "note": "device-synchronised lap of one step (max over ranks), kernels + collectives + the host reads of the "
                                          "line search; the replicated AMG solve is not in it"}
+    if "plan_operators" in out:
+        # the same reads counted by their kernels alone (CUDA events around each launch, this rank's slab): what scales with
+        # the number of GPUs; the lap above adds the collectives, the Python between the kernels and the host reads
+        kern_ms = 2 * k3_ms + max(plan_reads - 2, 0) * lin_ms
+        out["plan_operators"].update({"kernels_ms_per_step": kern_ms,
+                                      "kernels_aggregate_GBps": plan_reads * 8.0 * m * n / (kern_ms * 1e-3) / 1e9,
+                                      "kernels_frac_of_n_gpus_x_peak": plan_reads * 8.0 * m * n / (kern_ms * 1e-3) / 1e9 / (peak * world)})
     bytes_pass = 8.0 * k3_rows * n                          # one read of the (slab of the) plan-sized wk
     passes = int(info.get("ls_passes", 0))
     slab_txt = f", rank 0's {k3_rows}-row slab" if world > 1 else ""
