@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=128, help="grid side g (m = n = g*g); 128 is the headline config")
     ap.add_argument("--state-outer", type=int, default=30, help="APD outer iteration whose first SsN step is benchmarked")
+    ap.add_argument("--config", default="class1_128", choices=["class1_128", "class2_64"],
+                    help="class1_128: the headline (BASELINE configs[3]); class2_64: one SsN step of partial OT on 64x64 grids (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true", help="skip the timing of the whole Class1 solve (N=1 only)")
     return ap.parse_args()
@@ -152,7 +154,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return 0 if rank != 0 else run_reference(args)
+        return 0 if rank != 0 else (run_reference_class2(args) if args.config == "class2_64" else run_reference(args))
+    if args.config == "class2_64":
+        return 0 if rank != 0 else run_class2(args)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -475,6 +479,115 @@ def secondary_metrics(ssnamg, drv, state, m, n):
     torch.cuda.synchronize(); dta = time.perf_counter() - t0
     return {"pcg_iters_per_s": it / dt, "pcg_iters": it, "pcg_rel_res": res, "pcg_system": f"Jk {m + n}x{m + n}, nnz {Jk.nnz}",
             "hybrid_amg_ms": dta * 1e3, "wcycles_per_s_incl_setup": itamg / dta}
+
+
+METRIC2 = "ssn_amg_inner_solve_step_time_class2_64x64_grid"
+
+
+def class2_config(info):
+    return {"workload": "partial_OT_grid64x64_vs_64x64_m4096_n4096_outer1_ssn2_from_trivial_start", "E_active": int(info["E"]),
+            "nnz_H0": int(info["nnzH"]), "amg_cycles": int(info["itamg"]), "line_search_trials": int(info["ll"]) + 1,
+            "l2_flush": "inputs larger than L2 (wk and phi: 2 x 134 MB per pass)"}
+
+
+def run_class2(args):
+    """--config class2_64 (BASELINE configs[2]): one SsN step of Class2/APD_SsN_Class2.m:137-217 on the 64x64 grids (m = n =
+    4096, 16.8M-entry plan, phi = 1, mu = 0.65 of the mass) at outer iteration 1, SsN step 2 from the trivial start: fused
+    residual of partial OT (ssn_prox_residual_pot) -> ASAt -> AMG4POT -> line search -> new residual."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    import ssnamg
+    drv = ssnamg.driver
+    peak, peak_src = peaks()
+    P = ssnamg.problems.grid_problem_pot(64, seed=0)
+    m = n = 64 * 64
+    ssnamg.rng_reset()
+    st = drv.class2_trivial_state(P)
+    st["lk"], _, _ = drv.ssn_step_class2(st)                 # SsN step 1 (untimed): the state of step 2
+
+    def step_fn():
+        ssnamg.rng_reset()
+        return drv.ssn_step_class2(st)
+    for _ in range(max(args.warmup, 3)):
+        lk_new, Fk_new, info = step_fn()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    l0 = ssnamg.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lk_new, Fk_new, info = step_fn()
+    e1.record(); torch.cuda.synchronize()
+    launches = ssnamg.launch_count() - l0
+    ms_step = e0.elapsed_time(e1) / args.steps
+    # the plan-wide kernel of this path, timed alone (CUDA events around the launch, ssn_kernel_timer)
+    call = lambda: ssnamg.prox_residual_pot(st["wk"], st["lk"], st["p"], st["q"], st["tk"], st["phi"], want=("Hprox", "s", "t"))
+    for _ in range(3):
+        call()
+    ssnamg.kernel_timer(True)
+    for _ in range(20):
+        call()
+    kms, kcnt = ssnamg.kernel_timer_read(); ssnamg.kernel_timer(False)
+    k_ms = kms / max(kcnt, 1)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    bytes_pass = 16.0 * m * n + 1.0 * m * n                  # wk and phi read, s written
+    ach = bytes_pass / (k_ms * 1e-3) / 1e9
+    out = {"metric": METRIC2, "value": ms_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "ours", "config": class2_config(info),
+           "breakdown_ms": {"plan_wide_kernels": info["ms_plan"], "asat_assembly": info["ms_asat"], "amg4pot": info["ms_amg"]},
+           "gpu_launches": int(launches), "clocks": sampler.summary(),
+           "roofline": {"bound": "hbm", "kernel": "plan_reduce_kernel<PROX, G_PHI> (fused residual of partial OT: z, prox, H*prox, ||prox||^2, "
+                                                   "active flags; one read of wk and one of phi)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": bytes_pass, "avg_launch_ms": k_ms, "launches_per_step": int(info["ll"]) + 2,
+                        "share_of_step": (int(info["ll"]) + 2) * k_ms / ms_step, "traffic": None,
+                        "note": "285 MB per launch: the kernel lasts ~50 us, so launch ramp and tail weigh more than at 128x128"}}
+    # e2e: the same step with wk, phi and the duals copied from pinned host memory every step
+    host = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in st.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
+
+    def e2e_step():
+        dst = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+        ssnamg.rng_reset()
+        a, b, _ = drv.ssn_step_class2(dst)
+        return a.cpu(), b.cpu()
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ke = max(3, min(args.steps, 5))
+    for _ in range(ke):
+        lk_h, Fk_h = e2e_step()
+    torch.cuda.synchronize()
+    out["e2e"] = {"value": (time.perf_counter() - t0) * 1e3 / ke, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                  "d2h_bytes_per_step": int(lk_h.numel() * 8 + Fk_h.numel() * 8)}
+    if not args.no_cpu_baseline:
+        from oracle import bench_step
+        Pn = load_problems_module().grid_problem_pot(64, seed=0)
+        cms, lk_c, Fk_c, cinfo, t_state = bench_step.timed_step_class2(Pn)
+        out["cpu_baseline"] = {"value": cms, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"oracle (NumPy/SciPy port of the reference), the WHOLE step once: residual {cinfo['phases_s']['residual_s']:.2f} s, "
+                                         f"ASAt {cinfo['phases_s']['asat_s']:.2f} s, AMG4POT {cinfo['phases_s']['amg4pot_s']:.2f} s, line search "
+                                         f"{cinfo['phases_s']['line_search_s']:.2f} s (whole-vector expressions; state built by {t_state:.1f} s of SsN step 1)",
+                               "same_step_as_device": {"config_equal": class2_config(cinfo) == out["config"],
+                                                       "lk_new_max_rel_diff": float(np.max(np.abs(lk_c - lk_new.cpu().numpy())) / np.max(np.abs(lk_c)))}}
+    emit(out)
+    return 0
+
+
+def run_reference_class2(args):
+    """--impl reference --config class2_64: the oracle's step on the host, never importing torch or the product."""
+    from oracle import bench_step
+    P = load_problems_module().grid_problem_pot(64, seed=0)
+    ms, lk_new, Fk_new, info, t_state = bench_step.timed_step_class2(P)
+    emit({"metric": METRIC2, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms,
+          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+          "config": class2_config(info), "run": {"state_build_s": round(t_state, 1), "requested_steps": args.steps},
+          "cpu_baseline": {"value": ms, "unit": UNIT, "cores": 1, "kind": "port", "sample": "the whole step once, nothing sampled"},
+          "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return 0
 
 
 def run_reference(args):

@@ -236,6 +236,27 @@ def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count
     return out
 
 
+def prox_residual_pot(w, lam, p, q, tk, phi, want=("Hprox", "norm2", "count")):
+    """Fused SsN residual pieces of PARTIAL OT in one read of ``w`` and one of ``phi`` (Class2/APD_SsN_Class2.m:124-130,
+    137-150, 196-217; ``u = [x (m*n); y (n); z (m)]``, ``lam`` of n+m+1 entries):
+    ``zk = (wk - [Aty(lam[:N]) + lam[N]*phi ; lam[:N]])/tk``, ``s = zk[:mn] >= 0`` (uint8), ``t = zk[mn:] >= 0`` (0/1 doubles),
+    ``prox = max(zk, 0)``, ``Hprox = [Ax(prox x) + [prox y; prox z] ; phi'prox x]``, ``||prox||^2``, ``nnz(s)``."""
+    torch = _torch(); ctx = context(); host = _is_host(w, lam, p, q)
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel(); N = m + n
+    wd, ld, fd = _dev(w, count=m * n + N), _dev(lam, count=N + 1), _dev(phi, count=m * n)
+    mk = lambda name, shape, dt: torch.empty(shape, dtype=dt, device="cuda") if name in want else None
+    hp = mk("Hprox", N + 1, torch.float64); px = mk("prox", m * n + N, torch.float64)
+    s = mk("s", m * n, torch.uint8); t = mk("t", N, torch.float64)
+    n2 = C.c_double(0.0); cnt = C.c_int64(0)
+    ctx.call("ssn_prox_residual_pot", _ptr(wd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(fd),
+             _ptr(hp), _ptr(px), _ptr(s), _ptr(t), C.byref(n2), C.byref(cnt))
+    out = {"norm2": n2.value, "count": cnt.value}
+    for k, v in (("Hprox", hp), ("prox", px), ("s", s), ("t", t)):
+        if v is not None:
+            out[k] = _ret(v, host)
+    return out
+
+
 def _gama_args(gama, m, n):
     if np.isscalar(gama) or (hasattr(gama, "numel") and gama.numel() == 1) or np.size(gama) == 1:
         gs = float(gama if np.isscalar(gama) else np.asarray(gama.cpu() if hasattr(gama, "cpu") else gama).reshape(-1)[0])

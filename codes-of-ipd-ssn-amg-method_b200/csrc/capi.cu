@@ -276,6 +276,18 @@ int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const doub
     });
 }
 
+int ssn_prox_residual_pot(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
+                          double tk, const double* phi, double* hp, double* prox, uint8_t* s, double* t, double* norm2_out,
+                          int64_t* count_out) {
+    return guarded(c, [&] {
+        Buf<double> scal(c, 3);
+        plan_prox_residual_pot(c, w, lam, p, q, m, n, tk, phi, hp, prox, s, t, scal);
+        double h[3]; read_back(c, scal.p, h, 3);
+        if (norm2_out) *norm2_out = h[0];
+        if (count_out) *count_out = (int64_t)h[1];
+    });
+}
+
 int ssn_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, const double* p, const double* q, int64_t m, int64_t n,
                     double tk, const double* gama, double gama_s, double* n2_out) {
     return guarded(c, [&] { plan_prox_trials(c, w, lamT, nt, p, q, m, n, tk, gama, gama_s, n2_out); sync(c); });

@@ -37,6 +37,7 @@ struct PlanArgs {
     double* rowpart;        // [num_chunks][m]
     double* colpart;        // [num_groups][n]
     double* scalpart;       // [num_blocks][2]  (norm2, count)
+    double* phipart;        // G_PHI: [num_blocks] partial sums of phi .* prox(z) (Class 2: gama = phi array, gama_s = lam(m+n+1))
     double* prox_out;
     double* z_out;
     uint8_t* s_out;
@@ -62,7 +63,9 @@ __device__ __forceinline__ double butterfly4(double v0, double v1, double v2, do
     return b;
 }
 
-enum { G_INF = 0, G_SCALAR = 1, G_VECTOR = 2 };
+// G_PHI (Class2/APD_SsN_Class2.m:124-129): gama = Inf, and the array passed as `gama` is phi, `gama_s` the last dual:
+// z = (1/tk)*(w - (Aty(lam) + lam(m+n+1)*phi)); the kernel also sums phi .* prox(z)
+enum { G_INF = 0, G_SCALAR = 1, G_VECTOR = 2, G_PHI = 3 };
 
 // element offset of row slot k relative to row slot 0 of the lane
 template <bool VEC> __device__ __forceinline__ constexpr int roff(int k) { return VEC ? (64 * (k >> 1) + (k & 1)) : (32 * k); }
@@ -72,10 +75,11 @@ template <bool VEC> __device__ __forceinline__ constexpr int roff(int k) { retur
 template <int MODE, bool VEC, int GM, bool FULL>
 __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_t c, int64_t c1, const bool (&rok)[4],
                                            const double (&pv)[4], const double (&y2v)[4], double (&rs)[4], double& n2,
-                                           int& cnt, double (&cs)[4]) {
+                                           int& cnt, double (&cs)[4], double& ps, double mu) {
     const size_t m = (size_t)a.m;
+    constexpr bool GARR = (GM == G_VECTOR || GM == G_PHI);         // a second plan-sized array rides along
     double v[4][4];
-    double g[GM == G_VECTOR ? 4 : 1][4];
+    double g[GARR ? 4 : 1][4];
     // ---- issue all loads of the batch first (8 x 16 B per lane in flight)
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
@@ -92,10 +96,10 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[cc][k] = (FULL || (cok && rok[k])) ? __ldcs(xp + roff<VEC>(k)) : 0.0;
         }
-        if (MODE == MODE_PROX && GM == G_VECTOR) {
+        if (MODE == MODE_PROX && GARR) {
             const double* gp = a.gama + off + (size_t)cc * m;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) g[GM == G_VECTOR ? cc : 0][k] = (FULL || (cok && rok[k])) ? __ldcs(gp + roff<VEC>(k)) : 0.0;
+            for (int k = 0; k < 4; ++k) g[GARR ? cc : 0][k] = (FULL || (cok && rok[k])) ? __ldcs(gp + roff<VEC>(k)) : 0.0;
         }
     }
 #pragma unroll
@@ -116,14 +120,16 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
             for (int k = 0; k < 4; ++k) {
                 // z = (1/tk) * (w - (p_i*y1_j + y2_i*q_j)), rounded like the reference expression
                 // `1/tk*(wk-Aty(lk,p,q))` (mul, mul, add, sub, mul; no FMA contraction).
-                const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                // Class 2: Htlk = Aty(lk(1:m+n),p,q) + lk(m+n+1)*phi                       APD_SsN_Class2.m:124,138
+                if (GM == G_PHI) aty = __dadd_rn(aty, __dmul_rn(mu, g[GARR ? cc : 0][k]));
                 const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
                 const bool live = FULL || (cok && rok[k]);
                 const bool nonneg = live && (z >= 0.0);
                 bool act; double pz;
-                if (GM == G_INF) { act = nonneg; pz = nonneg ? z : 0.0; }                 // min(max(0,z),Inf)
+                if (GM == G_INF || GM == G_PHI) { act = nonneg; pz = nonneg ? z : 0.0; } // min(max(0,z),Inf)
                 else {
-                    const double gm = (GM == G_VECTOR) ? g[GM == G_VECTOR ? cc : 0][k] : a.gama_s;
+                    const double gm = (GM == G_VECTOR) ? g[GARR ? cc : 0][k] : a.gama_s;
                     const bool below = (z <= gm);
                     act = nonneg && below;
                     pz = nonneg ? (below ? z : gm) : (live ? fmin(0.0, gm) : 0.0);       // min(max(0,z),gama)
@@ -132,7 +138,8 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
                 cnt += act ? 1 : 0;
                 // the line-search term of APD_SsN_Class1.m:183-187: ||prox(z)||^2 for gama = Inf (prob < 3);
                 // ||z||^2 - ||z - prox(z)||^2 = sum prox(z)*(2z - prox(z)) for finite capacities (prob = 3)
-                n2 = (GM == G_INF) ? fma(pz, pz, n2) : fma(pz, __dsub_rn(__dadd_rn(z, z), pz), n2);
+                n2 = (GM == G_INF || GM == G_PHI) ? fma(pz, pz, n2) : fma(pz, __dsub_rn(__dadd_rn(z, z), pz), n2);
+                if (GM == G_PHI) ps = fma(g[GARR ? cc : 0][k], pz, ps);                   // phi'*prox(z)
                 if (a.want_sums) { csum = fma(pz, pv[k], csum); rs[k] = fma(pz, qj, rs[k]); }
             }
             if (a.prox_out || a.z_out || a.s_out) {
@@ -190,7 +197,8 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
         y2v[k] = (MODE == MODE_PROX && rok[k]) ? a.lam[n + r] : 0.0;
     }
     double rs[4] = {0.0, 0.0, 0.0, 0.0};
-    double n2 = 0.0;
+    double n2 = 0.0, ps = 0.0;
+    const double mu = (MODE == MODE_PROX && GM == G_PHI) ? a.lam[n + m] : 0.0;       // lk(m+n+1), the multiplier of phi
     int cnt = 0;
     const bool strip_full = (rbase + kStripRows <= m);     // warp-uniform
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
@@ -198,8 +206,8 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
 
     for (int64_t c = c0; c < c1; c += 4, off += step) {
         double cs[4];
-        if (strip_full && c + 4 <= c1) plan_batch<MODE, VEC, GM, true>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs);
-        else                           plan_batch<MODE, VEC, GM, false>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs);
+        if (strip_full && c + 4 <= c1) plan_batch<MODE, VEC, GM, true>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
+        else                           plan_batch<MODE, VEC, GM, false>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
         if (a.want_sums) {
             const double tot = butterfly4(cs[0], cs[1], cs[2], cs[3], lane);
             const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
@@ -225,6 +233,10 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
         if (threadIdx.x == 0) {
             const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
             a.scalpart[2 * b] = t2; a.scalpart[2 * b + 1] = tc;
+        }
+        if (GM == G_PHI) {
+            const double t3 = block_sum(ps, red);
+            if (threadIdx.x == 0) a.phipart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t3;
         }
     }
 }
@@ -1219,6 +1231,67 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
 #undef SSN_PROX_LAUNCH
     SSN_LAUNCH(c, plan_finish_kernel, axp_out ? cdiv(m + n, 256) : 1, 256, 0, rowpart.p, colpart.p, scalpart.p,
                t.chunks, t.groups, m, n, nblocks, axp_out, scal2_dev);
+}
+
+// ---- Class 2 (partial OT): u = [x (m*n) ; y (n) ; z (m)], lk = [lambda (n+m) ; last dual], H = [A  I ; phi' 0]
+namespace {
+// the slack blocks y, z (N = n + m entries; H'lk there is lk(1:N)) and the last row of H*prox(z): one block
+__global__ void __launch_bounds__(1024) pot_slack_kernel(const double* __restrict__ w_s, const double* __restrict__ lam, int N, double inv_tk,
+                                                         double* __restrict__ hp, double* __restrict__ prox_s, double* __restrict__ t_out,
+                                                         const double* __restrict__ phipart, int nblocks, double* __restrict__ scal3) {
+    __shared__ double red[32];
+    double n2 = 0.0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double z = __dmul_rn(inv_tk, __dsub_rn(w_s[i], lam[i]));                     // 1/tk*(wk - Htlk), slack part
+        const bool nonneg = z >= 0.0;
+        const double pz = nonneg ? z : 0.0;
+        if (hp) hp[i] += pz;                                                                // Ax(prox x) + [prox y ; prox z]
+        if (prox_s) prox_s[i] = pz;
+        if (t_out) t_out[i] = nonneg ? 1.0 : 0.0;
+        n2 = fma(pz, pz, n2);
+    }
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 1024) s += phipart[b];
+    const double t2 = block_sum(n2, red);
+    const double t3 = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        scal3[0] += t2;                                                                     // ||prox(z)||^2 over x, y and z
+        scal3[2] = t3;                                                                      // phi'*prox(z_x)
+        if (hp) hp[N] = t3;
+    }
+}
+}  // namespace
+
+// Fused Class 2 residual pieces, one read of w and one of phi (Class2/APD_SsN_Class2.m:124-130, 137-150, 196-217):
+//   zk = 1/tk*(wk - [Aty(lk(1:N),p,q) + lk(N+1)*phi ; lk(1:N)]),  s = zk(1:mn) >= 0,  t = zk(mn+1:end) >= 0,
+//   Hpzk = [Ax(prox x) + [prox y ; prox z] ; phi'*prox x]  -> hp_out (N+1),  ||prox(zk)||^2, nnz(s)  -> scal3_dev[0..1]
+void plan_prox_residual_pot(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
+                            double tk, const double* phi, double* hp_out, double* prox_out, uint8_t* s_out, double* t_out,
+                            double* scal3_dev) {
+    SSN_REQUIRE(m > 0 && n > 0 && w && lam && p && q && phi && scal3_dev, SSN_E_INVALID, "prox_residual_pot: bad arguments");
+    SSN_REQUIRE(m + n < (int64_t)1 << 30, SSN_E_TOO_LARGE, "prox_residual_pot: m + n too large");
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    const int64_t mn = m * n, N = m + n;
+    Buf<double> rowpart, colpart, scalpart(c, (size_t)2 * nblocks), phipart(c, (size_t)nblocks);
+    if (hp_out) { rowpart.alloc(c, (size_t)t.chunks * m); colpart.alloc(c, (size_t)t.groups * n); }
+    PlanArgs a{};
+    a.x = w; a.p = p; a.q = q; a.lam = lam; a.gama = phi; a.gama_s = 0.0; a.inv_tk = 1.0 / tk;       // the kernel reads lk(N+1) itself
+    a.m = m; a.n = n; a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart.p; a.colpart = colpart.p; a.scalpart = scalpart.p; a.phipart = phipart.p;
+    a.prox_out = prox_out; a.z_out = nullptr; a.s_out = s_out; a.want_sums = hp_out ? 1 : 0;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(w, m) && vec_ok(phi, m) && (!prox_out || vec_ok(prox_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
+    {
+        KernelTimer kt(c);
+        if (vec) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, true, G_PHI>), grid, kThreads, smem, a);
+        else     SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, false, G_PHI>), grid, kThreads, smem, a);
+    }
+    SSN_LAUNCH(c, plan_finish_kernel, hp_out ? cdiv(N, 256) : 1, 256, 0, rowpart.p, colpart.p, scalpart.p, t.chunks, t.groups, m, n, nblocks,
+               hp_out, scal3_dev);
+    SSN_LAUNCH(c, pot_slack_kernel, 1, 1024, 0, w + mn, lam, (int)N, 1.0 / tk, hp_out, prox_out ? prox_out + mn : nullptr, t_out,
+               phipart.p, nblocks, scal3_dev);
 }
 
 // n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 for t < nt (nt <= kMaxTrials), one read of w

@@ -31,6 +31,9 @@ void plan_apd_begin(ssn_ctx* c, const double* cost, const double* xk, const doub
 void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double* xk, const double* lam, const double* p,
                   const double* q, int64_t m, int64_t n, double tk, double ak, const double* gama, double gama_s, double* xk1,
                   double* vk1, double* axk1_out, double* scal2_dev);
+void plan_prox_residual_pot(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
+                            double tk, const double* phi, double* hp_out, double* prox_out, uint8_t* s_out, double* t_out,
+                            double* scal3_dev);
 int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
                         Buf<int>& ycol, Buf<int>& rowcount);
 }  // namespace ssn

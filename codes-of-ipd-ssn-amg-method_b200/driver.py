@@ -288,13 +288,15 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
         wk = -wc + bk * (uk + ak * vk) / ak ** 2                        # :121
         wlk = bk1 * (lk - 1 / bk * (Hmul(uk) - b)) - b                  # :122
         ssn_it = 0; lk_new = lk.clone()
-        zk = 1 / tk * (wk - Htmul(lk_new))                              # :127
-        Fk_new = bk1 * lk_new - Hmul(torch.clamp_min(zk, 0.0)) - wlk    # :130
+        # zk = 1/tk*(wk - Htmul(lk)), prox, H*prox, ||prox||^2 and the active flags in ONE fused pass over wk and phi
+        # (ssn_prox_residual_pot) instead of ~10 plan-sized element-wise passes                          :127-130
+        ev = api.prox_residual_pot(wk, lk_new, p, q, tk, phi, want=("Hprox", "s", "t"))
+        Fk_new = bk1 * lk_new - ev["Hprox"] - wlk                       # :130
         nF = nrm(Fk_new); Fk_res = nF
         its = []
         while nF > SsN_Tol:                                             # :136
-            ssn_it += 1; lk_old = lk_new; Fk_old = Fk_new               # zk is already z(lk_old)
-            s = (zk[:mn] >= 0).to(torch.uint8); t = (zk[mn:] >= 0).to(torch.float64)   # :139
+            ssn_it += 1; lk_old = lk_new; Fk_old = Fk_new               # ev is already the evaluation at lk_old
+            s = ev["s"]; t = ev["t"]                                    # :139
             H0 = api.ASAt(s, p, q)                                      # :146
             prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "s": s, "T": t, "H0": H0, "z": -Fk_old, "phi": phi}
             if on_ssn_step is not None:
@@ -307,19 +309,18 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
             else:
                 raise ValueError("inner_solver must be 3 (PCG4POT) or 4 (AMG4POT)")
             its.append(itpcg)
-            pz = torch.clamp_min(zk, 0.0)
-            cFk_old = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old) + 0.5 * tk * float(pz @ pz)   # :196-197
+            cFk_old = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old) + 0.5 * tk * ev["norm2"]   # :196-197
             ress = abs(float(Fk_old @ zeta))
             ll = 0
-            while True:                                                 # :199-213
+            while True:                                                 # :199-213, one fused pass per trial
                 lk_new = lk_old + delta ** ll * zeta
                 f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
-                zk = 1 / tk * (wk - Htmul(lk_new)); pz = torch.clamp_min(zk, 0.0)
-                if not (f0 + 0.5 * tk * float(pz @ pz) > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
+                ev = api.prox_residual_pot(wk, lk_new, p, q, tk, phi, want=("Hprox", "s", "t"))
+                if not (f0 + 0.5 * tk * ev["norm2"] > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
                     break
                 ll += 1
             stats["ls_trials"] += ll + 1
-            Fk_new = bk1 * lk_new - Hmul(pz) - wlk                      # :217
+            Fk_new = bk1 * lk_new - ev["Hprox"] - wlk                   # :217
             nFo = nrm(Fk_old); nF = nrm(Fk_new)
             stats["steps"].append((k, ssn_it, int(s.sum()), int(info[0]), int(itpcg), int(ll), nF))
             if verbose:
@@ -332,7 +333,9 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
                 break
             if Fk_res / nF >= 2:
                 Fk_res = nF
-        lk1 = lk_new; uk1 = torch.clamp_min(zk, 0.0); vk1 = uk1 + (uk1 - uk) / ak      # :244
+        lk1 = lk_new
+        uk1 = api.prox_residual_pot(wk, lk_new, p, q, tk, phi, want=("prox",))["prox"]   # prox(zk) at the accepted duals
+        vk1 = uk1 + (uk1 - uk) / ak                                     # :244
         kk = kkts(uk1, lk1)
         rr = [kk[i] / (1 + KKT[0][i]) for i in range(4)]
         if bk1 < 1e-8 and max(rr) > resk:                               # :253-257
@@ -354,6 +357,59 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
     torch.cuda.synchronize()
     return {"uk": uk, "xk": uk[:mn], "lk": lk, "fxk": fxk, "KKT": KKT, "outer_its": k, "rel_kkt": max(rr), "stats": stats,
             "seconds": time.time() - t_loop, "warmup_seconds": t_warm}
+
+
+def class2_trivial_state(P):
+    """The APD state of outer iteration 1 of Class2/APD_SsN_Class2.m from the trivial start (``uk = vk = 0, lk = 0, bk = 1``;
+    :116-122), on the device: what ``ssn_step_class2`` takes."""
+    import torch
+    f64 = dict(dtype=torch.float64, device="cuda")
+    c, r, l, p, q, phi = (_t(P[k], torch) for k in ("c", "r", "l", "p", "q", "phi"))
+    m, n = l.numel(), r.numel()
+    b = torch.cat([r, l, torch.tensor([float(P["mu"])], **f64)])
+    ak = 1.0; bk = 1.0
+    bk1 = bk / (1 + ak); tk = bk * (1 + ak) / ak ** 2
+    wk = -torch.cat([c, torch.zeros(m + n, **f64)])
+    wlk = bk1 * (torch.zeros(m + n + 1, **f64) - 1 / bk * (0.0 - b)) - b
+    return {"wk": wk, "lk": torch.zeros(m + n + 1, **f64), "wlk": wlk, "p": p, "q": q, "phi": phi, "tk": tk, "bk1": bk1, "m": m, "n": n, "k": 1}
+
+
+def ssn_step_class2(state, amg_options=None, max_ll=500):
+    """One semismooth-Newton step of Class2/APD_SsN_Class2.m:137-217 at a fixed APD state: fused residual + active
+    flags (``ssn_prox_residual_pot``) -> ASAt -> AMG4POT -> Armijo line search (one fused pass per trial) -> new residual.
+    Returns ``(lk_new, Fk_new, info)``."""
+    import torch
+    wk, lk, wlk, p, q, phi = state["wk"], state["lk"], state["wlk"], state["p"], state["q"], state["phi"]
+    bk1, tk = state["bk1"], state["tk"]
+    nu, delta = 0.2, 0.9
+    tm = {"plan": 0.0, "asat": 0.0, "amg": 0.0}
+
+    def lap(key, t0):
+        torch.cuda.synchronize(); tm[key] += (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    ev = api.prox_residual_pot(wk, lk, p, q, tk, phi, want=("Hprox", "s", "t"))      # :139-150
+    Fk_old = bk1 * lk - ev["Hprox"] - wlk
+    lap("plan", t0); t0 = time.perf_counter()
+    H0 = api.ASAt(ev["s"], p, q)                                                     # :146
+    lap("asat", t0); t0 = time.perf_counter()
+    prob_data = {"bk1": bk1, "tk": tk, "q": q, "p": p, "s": ev["s"], "T": ev["t"], "H0": H0, "z": -Fk_old, "phi": phi}
+    zeta, itamg, resamg, info = api.AMG4POT(prob_data, amg_options or CLASS2_AMG_OPTIONS, "amg")   # :171
+    lap("amg", t0); t0 = time.perf_counter()
+    cFk_old = bk1 / 2 * float(lk @ lk) - float(wlk @ lk) + 0.5 * tk * ev["norm2"]    # :196-197
+    ress = abs(float(Fk_old @ zeta))
+    ll = 0
+    while True:                                                                      # :199-213
+        lk_new = lk + delta ** ll * zeta
+        f0 = bk1 / 2 * float(lk_new @ lk_new) - float(wlk @ lk_new)
+        ev2 = api.prox_residual_pot(wk, lk_new, p, q, tk, phi, want=("Hprox",))
+        if not (f0 + 0.5 * tk * ev2["norm2"] > cFk_old - nu * delta ** ll * ress) or ll == max_ll:
+            break
+        ll += 1
+    Fk_new = bk1 * lk_new - ev2["Hprox"] - wlk                                       # :217
+    lap("plan", t0)
+    return lk_new, Fk_new, {"E": ev["count"], "ms_plan": tm["plan"], "ms_asat": tm["asat"], "ms_amg": tm["amg"], "itamg": itamg,
+                            "resamg": resamg, "info": info, "ll": ll, "ls_passes": ll + 1, "nnzH": H0.nnz,
+                            "Fk_old_norm": float(torch.linalg.norm(Fk_old)), "Fk_new_norm": float(torch.linalg.norm(Fk_new))}
 
 
 def ssn_step(state, amg_options=None, max_ll=500):

@@ -220,6 +220,19 @@ SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *l
                       double *axp_out_dev, double *prox_out_dev, double *z_out_dev,
                       uint8_t *s_out_dev, double *norm2_out, int64_t *count_out);
 
+/* The same for partial OT (Class2/APD_SsN_Class2.m:124-130, 137-150, 196-217; u = [x (m*n); y (n); z (m)], lk of n+m+1
+ * entries, H = [A I; phi' 0]), one read of w and one of phi:
+ *   zk  = (1/tk) * (wk - [Aty(lk(1:n+m)) + lk(n+m+1)*phi ; lk(1:n+m)])     (rounded like the reference expression)
+ *   s   = zk(1:m*n) >= 0                         -> s_out_dev   (uint8, m*n)       [optional]
+ *   t   = zk(m*n+1:end) >= 0                     -> t_out_dev   (n+m doubles, 0/1) [optional]
+ *   prox(zk) = max(zk,0)                         -> prox_out_dev (m*n+n+m)         [optional]
+ *   [Ax(prox x) + [prox y; prox z] ; phi'*prox x] -> hp_out_dev  (n+m+1)           [optional]
+ *   ||prox(zk)||^2 -> *norm2_out, nnz(s) -> *count_out (host)                      [optional] */
+SSN_API int ssn_prox_residual_pot(ssn_ctx *ctx, const double *w_dev, const double *lam_dev, const double *p_dev,
+                      const double *q_dev, int64_t m, int64_t n, double tk, const double *phi_dev,
+                      double *hp_out_dev, double *prox_out_dev, uint8_t *s_out_dev, double *t_out_dev,
+                      double *norm2_out, int64_t *count_out);
+
 /* Batched line-search trials: n2_out_dev[t] = ||prox((w - Aty(lamT[t]))/tk)||^2 (finite gama: the prob = 3
  * term of ssn_prox_residual's norm2_out) for the nt <= 8
  * trial dual vectors lamT_dev[t*(n+m) .. ] in ONE read of w (Class1/APD_SsN_Class1.m:193-207

@@ -121,3 +121,76 @@ def timed_step(state, threads=None):
     t0 = time.perf_counter()
     lk_new, Fk_new, info = ssn_step(state, threads)
     return (time.perf_counter() - t0) * 1e3, lk_new, Fk_new, info
+
+
+# ------------------------------------------------------------------ Class 2 (partial OT), config 3 of BASELINE.json
+
+def class2_trivial_state(problem):
+    """The APD state of outer iteration 1 from the trivial start ``uk = vk = 0, lk = 0, bk = 1`` (``warm_maxit = 0``, the
+    common start of tests/golden/trace_class2_grid64_nowarm_outer3.npz): Class2/APD_SsN_Class2.m:116-122."""
+    c, r, l = problem["c"], problem["r"], problem["l"]
+    m, n = l.size, r.size
+    b = np.concatenate([r, l, [problem["mu"]]])
+    ak = 1.0; bk = 1.0
+    bk1 = bk / (1 + ak); tk = bk * (1 + ak) / ak ** 2                   # :117
+    wk = -np.concatenate([c, np.zeros(m + n)])                          # :121 with uk = vk = 0
+    wlk = bk1 * (np.zeros(m + n + 1) - 1 / bk * (0.0 - b)) - b          # :122
+    return {"wk": wk, "lk": np.zeros(m + n + 1), "wlk": wlk, "p": problem["p"], "q": problem["q"], "phi": problem["phi"],
+            "tk": tk, "bk1": bk1, "m": m, "n": n, "k": 1}
+
+
+def ssn_step_class2(state, amg_options=None, ll_max=500):
+    """One SsN step of Class2/APD_SsN_Class2.m:137-217 on the host (whole-vector NumPy expressions, like the reference's
+    MATLAB lines; AMG4POT = the oracle's SciPy restatement).  Returns ``(lk_new, Fk_new, info)``."""
+    from .solvers import AMG4POT
+    from .driver import CLASS2_AMG_OPTIONS
+    wk, lk_old, wlk, p, q, phi = state["wk"], state["lk"], state["wlk"], state["p"], state["q"], state["phi"]
+    tk, bk1, m, n = state["tk"], state["bk1"], state["m"], state["n"]
+    N = m + n; mn = m * n
+    nu, delta = 0.2, 0.9
+    prox = lambda x: np.maximum(0.0, x)
+    Hmul = lambda u: np.concatenate([Ax(u[:mn], p, q) + u[mn:], [phi @ u[:mn]]])
+    Htmul = lambda lam: np.concatenate([Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])
+    tm = {}
+    t0 = time.perf_counter()
+    zk = 1 / tk * (wk - Htmul(lk_old))                                  # :139
+    s = zk[:mn] >= 0; t = (zk[mn:] >= 0).astype(np.float64)
+    pzk = prox(zk)
+    Fk_old = bk1 * lk_old - Hmul(pzk) - wlk                             # :150
+    tm["residual_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+    T = sp.diags(t, format="csc"); H0 = ASAt(s, p, q)                   # :146
+    tm["asat_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+    pd = {"bk1": bk1, "tk": tk, "q": q, "p": p, "s": s, "T": T, "H0": H0, "z": -Fk_old, "phi": phi}
+    zeta, itamg, resamg, info = AMG4POT(pd, amg_options or CLASS2_AMG_OPTIONS, "amg")     # :171
+    tm["amg4pot_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+    f0 = bk1 / 2 * np.linalg.norm(lk_old) ** 2 - wlk @ lk_old           # :196
+    cFk_old = f0 + 0.5 * tk * np.linalg.norm(pzk) ** 2
+    ress = abs(Fk_old @ zeta)
+    ll = 0
+    while True:                                                         # :199-213
+        lk_new = lk_old + delta ** ll * zeta
+        f0 = bk1 / 2 * np.linalg.norm(lk_new) ** 2 - wlk @ lk_new
+        zk = 1 / tk * (wk - Htmul(lk_new)); pzk = prox(zk)
+        if not (f0 + 0.5 * tk * np.linalg.norm(pzk) ** 2 > cFk_old - nu * delta ** ll * ress) or ll == ll_max:
+            break
+        ll += 1
+    tm["line_search_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+    Fk_new = bk1 * lk_new - Hmul(pzk) - wlk                             # :217
+    tm["new_residual_s"] = time.perf_counter() - t0
+    return lk_new, Fk_new, {"E": int(np.count_nonzero(s)), "nnzH": int(H0.nnz), "components": int(info[0]), "itamg": int(itamg),
+                            "resamg": float(resamg), "ll": int(ll), "threads": 1, "phases_s": tm,
+                            "Fk_old_norm": float(np.linalg.norm(Fk_old)), "Fk_new_norm": float(np.linalg.norm(Fk_new))}
+
+
+def timed_step_class2(problem, warm_steps=1):
+    """State of SsN step ``warm_steps + 1`` of outer iteration 1 from the trivial start (the first ``warm_steps`` steps are
+    run untimed to get there), then ONE timed step.  Returns ``(ms, lk_new, Fk_new, info, seconds of the state build)``."""
+    _rng.rng_reset()
+    st = class2_trivial_state(problem)
+    t0 = time.perf_counter()
+    for _ in range(warm_steps):
+        st["lk"], _, _ = ssn_step_class2(st)
+    t_state = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lk_new, Fk_new, info = ssn_step_class2(st)
+    return (time.perf_counter() - t0) * 1e3, lk_new, Fk_new, info, t_state

@@ -30,6 +30,10 @@ int emu_prox_residual(const double* w, const double* lam, const double* p, const
                       const double* gama, double gama_s, double* axp, double* prox, double* z, uint8_t* s, double* scal2) {
     return guarded([&] { ssn::plan_prox_residual(ctx(), w, lam, p, q, m, n, tk, gama, gama_s, axp, prox, z, s, scal2); });
 }
+int emu_prox_residual_pot(const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n, double tk,
+                          const double* phi, double* hp, double* prox, uint8_t* s, double* t, double* scal3) {
+    return guarded([&] { ssn::plan_prox_residual_pot(ctx(), w, lam, p, q, m, n, tk, phi, hp, prox, s, t, scal3); });
+}
 int emu_active_set(const uint8_t* s, int64_t m, int64_t n, int* colptr, int* yrow, int* ycol, int* rowcount, int64_t* E_out) {
     return guarded([&] {
         ssn::Buf<int> cp, yr, yc, rc;

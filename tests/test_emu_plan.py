@@ -90,6 +90,33 @@ def test_prox_residual(emu, oracle, m, n, gmode):
     assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
 
 
+@pytest.mark.parametrize("m,n", [(7, 5), (64, 48), (45, 130)])
+@pytest.mark.parametrize("unit_phi", [True, False])
+def test_prox_residual_pot(emu, oracle, m, n, unit_phi):
+    """The fused residual of partial OT (plan_reduce_kernel<PROX, G_PHI> + the slack kernel): z-derived flags and prox bit
+    for bit against Class2/APD_SsN_Class2.m:124-130, H*prox to rounding."""
+    rs = np.random.RandomState(5 * m + n)
+    p, q = weights(m, n, 6, False)
+    N = m + n; mn = m * n
+    w = rs.standard_normal(mn + N); lam = 0.5 * rs.standard_normal(N + 1); tk = 0.41
+    phi = np.ones(mn) if unit_phi else rs.random_sample(mn) + 0.5
+    z = 1 / tk * (w - np.concatenate([oracle.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]]))
+    pz = np.maximum(z, 0.0)
+    Hp = np.concatenate([oracle.Ax(pz[:mn], p, q) + pz[mn:], [phi @ pz[:mn]]])
+    hp = np.zeros(N + 1); prox = np.zeros(mn + N); s = np.zeros(mn, np.uint8); t = np.zeros(N); scal = np.zeros(3)
+    _ok(emu, emu.emu_prox_residual_pot(_p(w), _p(lam), _p(p), _p(q), C.c_int64(m), C.c_int64(n), C.c_double(tk), _p(phi),
+                                       _p(hp), _p(prox), _p(s), _p(t), _p(scal)))
+    assert np.array_equal(s.astype(bool), z[:mn] >= 0) and np.array_equal(t > 0.5, z[mn:] >= 0)
+    assert np.array_equal(prox, pz)
+    assert int(scal[1]) == int((z[:mn] >= 0).sum())
+    assert close(hp, Hp)
+    assert abs(scal[0] - float(pz @ pz)) <= 1e-12 * float(pz @ pz)
+    scal2 = np.zeros(3)
+    _ok(emu, emu.emu_prox_residual_pot(_p(w), _p(lam), _p(p), _p(q), C.c_int64(m), C.c_int64(n), C.c_double(tk), _p(phi),
+                                       None, None, None, None, _p(scal2)))
+    assert abs(scal2[0] - scal[0]) <= 1e-14 * abs(scal[0])
+
+
 @pytest.mark.parametrize("m,n,density", [(5, 4, 0.5), (64, 48, 0.1), (45, 130, 0.05), (48, 7, 1.0), (33, 20, 0.0)])
 def test_active_set_compaction(emu, m, n, density):
     """Y = sparse(reshape(s,m,n)) as CSC coordinate lists, rows ascending inside a column (ASAt.m:15)"""

@@ -90,6 +90,31 @@ def test_prox_residual_matches_oracle(gpu, oracle, m, n, gmode):
     assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
 
 
+@pytest.mark.parametrize("m,n", [(7, 5), (128, 64), (500, 500), (1027, 517), (2048, 300)])
+@pytest.mark.parametrize("unit_phi", [True, False])
+def test_prox_residual_pot_matches_oracle(gpu, oracle, m, n, unit_phi):
+    """Fused residual of partial OT (Class2/APD_SsN_Class2.m:124-130,137-150): z, the active flags s and t and prox(z) bit
+    for bit against the reference expression, H*prox(z) to 1e-10."""
+    rs = np.random.RandomState(5 * m + n)
+    p, q = weights(m, n, 6, False)
+    N = m + n; mn = m * n
+    w = rs.standard_normal(mn + N); lam = 0.5 * rs.standard_normal(N + 1); tk = 0.41
+    phi = np.ones(mn) if unit_phi else rs.random_sample(mn) + 0.5
+    Htlk = np.concatenate([oracle.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])      # :124
+    z = 1 / tk * (w - Htlk)                                                        # :127
+    pz = np.maximum(z, 0.0)
+    Hp = np.concatenate([oracle.Ax(pz[:mn], p, q) + pz[mn:], [phi @ pz[:mn]]])      # :128-129
+    out = gpu.prox_residual_pot(w, lam, p, q, tk, phi, want=("Hprox", "prox", "s", "t"))
+    assert np.array_equal(out["s"].astype(bool), z[:mn] >= 0)
+    assert np.array_equal(out["t"] > 0.5, z[mn:] >= 0)
+    assert np.array_equal(out["prox"], pz)
+    assert out["count"] == int((z[:mn] >= 0).sum())
+    assert close(out["Hprox"], Hp)
+    assert abs(out["norm2"] - float(pz @ pz)) <= 1e-12 * float(pz @ pz)
+    lite = gpu.prox_residual_pot(w, lam, p, q, tk, phi, want=())                   # line-search form: the norm only
+    assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
+
+
 @pytest.mark.parametrize("m,n,density", [(5, 4, 0.5), (64, 48, 0.1), (300, 500, 0.02), (512, 512, 0.004),
                                            (1000, 37, 0.3), (130, 2100, 0.01)])
 @pytest.mark.parametrize("unit", [True, False])
