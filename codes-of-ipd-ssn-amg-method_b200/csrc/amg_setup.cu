@@ -310,6 +310,88 @@ __global__ void mis_isolated_kernel(int n, const int* __restrict__ rowcnt, uint8
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && rowcnt[i] == 0) { isC[i] = 1; isF[i] = 0; }   // mis_set.m:67
 }
+// ---- all the rounds of mis_set.m:36-67 in ONE launch: a thread-block cluster of 16 CTAs walks init / mark / kill /
+// select / mark-F / update round after round with the hardware cluster barrier (release / acquire: global writes of a
+// phase are visible to the next) and decides itself when the loop of :42 ends -- 1 launch and no host read instead of
+// 5 launches + 1 read per round.  The phases are the kernels above, statement for statement (same flags, same benign
+// write races), so isC / isF are the same bit for bit.  counts: 2 ints per round, zeroed by the host.
+constexpr int kMisCta = 16;
+#ifdef SSN_EMU
+constexpr int kMisT = 64;
+__device__ __forceinline__ int mis_rank() { return blockIdx.x; }
+__device__ __forceinline__ void mis_sync() { emu::cluster_bar->arrive_and_wait(); }
+#else
+constexpr int kMisT = 1024;
+__device__ __forceinline__ int mis_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ void mis_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+#endif
+constexpr int kMisMaxRounds = 256;
+
+#ifdef SSN_EMU
+void mis_rounds_kernel(
+#else
+__global__ void __launch_bounds__(kMisT, 1) mis_rounds_kernel(
+#endif
+        int n, int N0, const int* __restrict__ ptr, const int* __restrict__ idx, const uint8_t* __restrict__ flags,
+        const int* __restrict__ deg, const int* __restrict__ rank, const double* __restrict__ rnd, const int* __restrict__ rowcnt,
+        double* __restrict__ degf, uint8_t* __restrict__ isS, uint8_t* __restrict__ kill, uint8_t* __restrict__ isC,
+        uint8_t* __restrict__ isF, int* __restrict__ counts) {
+    const int gt = mis_rank() * kMisT + (int)threadIdx.x, nt = kMisCta * kMisT;
+    const int lane = threadIdx.x & 31, gw = gt >> 5, nw = nt >> 5;
+    for (int i = gt; i < n; i += nt) {                                   // mis_init_kernel
+        const int d = deg[i];
+        degf[i] = (d > 0) ? __dadd_rn((double)d, __dmul_rn(0.1, rnd[rank[i]])) : 0.0;
+        isC[i] = 0;
+        isF[i] = (d == 0) ? 1 : 0;
+    }
+    mis_sync();
+    int sumC = 0, sumU = n, round = 0;
+    while ((double)sumC < (double)n / 2.0 && sumU > N0 && round < kMisMaxRounds) {      // mis_set.m:42
+        for (int i = gt; i < n; i += nt) { isS[i] = degf[i] > 0.0 ? 1 : 0; kill[i] = 0; }        // mis_mark_kernel
+        mis_sync();
+        for (int row = gw; row < n; row += nw) {                         // mis_kill_kernel
+            if (!isS[row]) continue;
+            const double di = degf[row];
+            bool kill_me = false;
+            for (int e = ptr[row] + lane; e < ptr[row + 1]; e += 32) {
+                const int j = idx[e];
+                if (flags[e] && j > row && isS[j]) {
+                    if (di >= degf[j]) kill[j] = 1; else kill_me = true;
+                }
+            }
+            if (kill_me) kill[row] = 1;
+        }
+        mis_sync();
+        for (int i = gt; i < n; i += nt) if (isS[i] && !kill[i]) isC[i] = 1;                       // mis_select_kernel
+        mis_sync();
+        for (int row = gw; row < n; row += nw) {                         // mis_markf_kernel
+            bool hit = false;
+            for (int e = ptr[row] + lane; e < ptr[row + 1]; e += 32) hit |= (flags[e] && isC[idx[e]]);
+            if (__any_sync(0xffffffffu, hit) && lane == 0) isF[row] = 1;
+        }
+        mis_sync();
+        {                                                                // mis_update_kernel
+            int cC = 0, cU = 0;
+            for (int i = gt; i < n; i += nt) {
+                const bool u = !(isF[i] || isC[i]);
+                if (!u) degf[i] = 0.0;
+                cC += isC[i] ? 1 : 0; cU += u ? 1 : 0;
+            }
+            cC = warp_sum_int(cC); cU = warp_sum_int(cU);
+            if (lane == 0) { if (cC) atomicAdd(counts + 2 * round, cC); if (cU) atomicAdd(counts + 2 * round + 1, cU); }
+        }
+        mis_sync();
+        sumC = *reinterpret_cast<volatile int*>(counts + 2 * round); sumU = *reinterpret_cast<volatile int*>(counts + 2 * round + 1);
+        if (sumU <= N0) {                                                // mis_leftover_kernel   mis_set.m:61-64
+            for (int i = gt; i < n; i += nt) if (!(isF[i] || isC[i])) isC[i] = 1;
+            sumU = 0;
+            mis_sync();
+        }
+        ++round;
+    }
+    for (int i = gt; i < n; i += nt) if (rowcnt[i] == 0) { isC[i] = 1; isF[i] = 0; }               // mis_isolated_kernel  :67
+}
+
 __global__ void mis_random_kernel(int n0, int n, const double* __restrict__ rnd, uint8_t* __restrict__ isC) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n0) {
@@ -323,6 +405,37 @@ __global__ void not_kernel(int n, const uint8_t* __restrict__ a, uint8_t* __rest
 }
 
 }  // namespace
+
+// launches mis_rounds_kernel on one 16-CTA cluster; false when the device cannot co-schedule it (the caller goes round by round)
+static bool mis_rounds_cluster(ssn_ctx* c, const CsrView& A, int N0, const uint8_t* flags, const int* deg, const int* rank, const double* rnd,
+                               const int* rowcnt, double* degf, uint8_t* isS, uint8_t* kill, uint8_t* isC, uint8_t* isF) {
+    Buf<int> counts(c, (size_t)2 * kMisMaxRounds);
+    counts.zero();
+#ifdef SSN_EMU
+    emu_launch_cluster(c, mis_rounds_kernel, kMisCta, kMisT, 0, A.nrows, N0, A.ptr, A.idx, flags, deg, rank, rnd, rowcnt, degf, isS, kill, isC, isF,
+                       counts.p);
+    return true;
+#else
+    static int ok16 = -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kMisCta); cfg.blockDim = dim3(kMisT); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kMisCta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (ok16 < 0) {
+        ok16 = 0;
+        int nclusters = 0;
+        if (cudaFuncSetAttribute(mis_rounds_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaOccupancyMaxActiveClusters(&nclusters, mis_rounds_kernel, &cfg) == cudaSuccess && nclusters >= 1) ok16 = 1;
+        (void)cudaGetLastError();
+    }
+    if (!ok16) return false;
+    const int n = A.nrows;
+    SSN_CUDA(cudaLaunchKernelEx(&cfg, mis_rounds_kernel, n, N0, A.ptr, A.idx, flags, deg, rank, rnd, rowcnt, degf, isS, kill, isC, isF, counts.p));
+    c->launches++;
+    return true;
+#endif
+}
 
 void mis_set(ssn_ctx* c, const CsrView& A, double theta, uint8_t* isC, uint8_t* isF, Buf<uint8_t>& flags) {
     SSN_REQUIRE(A.nrows == A.ncols, SSN_E_NOT_SQUARE, "mis_set: matrix must be square");
@@ -348,8 +461,10 @@ void mis_set(ssn_ctx* c, const CsrView& A, double theta, uint8_t* isC, uint8_t* 
     }
     Buf<double> rnd(c, nconn), degf(c, n);
     rng_rand(c, nconn, rnd);
-    SSN_LAUNCH(c, mis_init_kernel, g, 256, 0, n, deg.p, rank.p, rnd.p, degf.p, isC, isF);
     Buf<uint8_t> isS(c, n), kill(c, n);
+    if (c->mis_cluster && n <= (1 << 16) && A.nnz <= ((int64_t)1 << 21) && mis_rounds_cluster(c, A, N0, flags.p, deg.p, rank.p, rnd.p, rowcnt.p,
+                                                                                              degf.p, isS.p, kill.p, isC, isF)) return;
+    SSN_LAUNCH(c, mis_init_kernel, g, 256, 0, n, deg.p, rank.p, rnd.p, degf.p, isC, isF);
     Buf<int> counts(c, 2);
     int sumC = 0, sumU = n;
     while ((double)sumC < (double)n / 2.0 && sumU > N0) {                 // mis_set.m:42
