@@ -157,7 +157,10 @@ __device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int segb) {
 // adds the NW partials itself; stage 2: lanes 0..15 of warp 0 put the CTA's sum into slot [rank] of every CTA, ONE
 // cluster barrier, every thread adds the 16 slots.  (Sending the warp partials straight to every CTA -- no stage 1 --
 // was measured slower: 256 remote 8-byte stores per CTA cost more than the __syncthreads they save.)
-__device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
+// The two halves of z_sum1: post = everything up to and including the barrier, read = the sum of the 16 slots.  (Issuing the
+// gathers of the next sweep between the two -- they need the barrier, not the sum -- was measured: slower, the slot reads
+// then queue behind the remote loads in the load / store unit.)
+__device__ __forceinline__ void z_sum1_post(ZTeam& G, double a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = kZT / 32;
     a = warp_sum(a);
@@ -172,11 +175,18 @@ __device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
         z_st(z_map(z_local(sl + 2 * G.rank), lane), ta);
     }
     z_barrier();
+}
+__device__ __forceinline__ double z_sum1_read(ZTeam& G) {
+    const double* sl = reinterpret_cast<const double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
     double s0 = 0.0;
 #pragma unroll 4
     for (int r = 0; r < G.ncta; ++r) s0 += sl[2 * r];
     ++G.flip;
     return s0;
+}
+__device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
+    z_sum1_post(G, a);
+    return z_sum1_read(G);
 }
 
 // For the local rows [l0, l1) of level L (2^lt lanes per row): s = sum over the row's entries of M of value * v[column],
@@ -594,20 +604,37 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 for (int j = threadIdx.x; j < n; j += kZT) xs[j] = z_gather(G, vb, z_loc(L, j));
                 __syncthreads();
                 const int lane = threadIdx.x & 31;
-                for (int l = threadIdx.x >> 5; l < nl; l += kZT / 32) {
-                    const int row = z_row(L, G.rank, l);
-                    if (row < 0) continue;
-                    const double* Br = L.B + (size_t)row * n;
-                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    for (int j0 = 0; j0 < n; j0 += 256) {
-                        double bv[8], xv[8];
+                // a warp owns up to RW rows of the slice and streams them TOGETHER: RW x 8 loads of B in flight per lane
+                // instead of 8 (the rows are read from L2; one row after the other was 9 dependent round trips at N = 651)
+                constexpr int RW = 3, NWZ = kZT / 32;
+                for (int l0 = (threadIdx.x >> 5); l0 < nl; l0 += RW * NWZ) {
+                    int rowv[RW]; const double* Br[RW]; double acc[RW][4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { const int j = j0 + u * 32 + lane; bv[u] = (j < n) ? Br[j] : 0.0; xv[u] = (j < n) ? xs[j] : 0.0; }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) acc[u & 3] = fma(bv[u], xv[u], acc[u & 3]);
+                    for (int w = 0; w < RW; ++w) {
+                        const int l = l0 + w * NWZ;
+                        rowv[w] = (l < nl) ? z_row(L, G.rank, l) : -1;
+                        Br[w] = L.B + (size_t)(rowv[w] >= 0 ? rowv[w] : 0) * n;
+                        acc[w][0] = acc[w][1] = acc[w][2] = acc[w][3] = 0.0;
                     }
-                    const double s = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
-                    if (lane == 0) e[l] = zero ? s : (e[l] + s);
+                    for (int j0 = 0; j0 < n; j0 += 256) {
+                        double bv[RW][8], xv[8];
+#pragma unroll
+                        for (int w = 0; w < RW; ++w)
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { const int j = j0 + u * 32 + lane; bv[w][u] = (j < n && rowv[w] >= 0) ? Br[w][j] : 0.0; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int j = j0 + u * 32 + lane; xv[u] = (j < n) ? xs[j] : 0.0; }
+#pragma unroll
+                        for (int w = 0; w < RW; ++w)
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc[w][u & 3] = fma(bv[w][u], xv[u], acc[w][u & 3]);
+                    }
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) {
+                        const double sdot = warp_sum((acc[w][0] + acc[w][1]) + (acc[w][2] + acc[w][3]));
+                        const int l = l0 + w * NWZ;
+                        if (lane == 0 && rowv[w] >= 0) e[l] = zero ? sdot : (e[l] + sdot);
+                    }
                 }
                 z_barrier();
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
