@@ -710,6 +710,37 @@ def Hybrid_twogrid(prob_data, amg_options):
     return _solve("ssn_hybrid_twogrid", prob_data, amg_options, _amg_options)
 
 
+def ssn_step_class1(wk, lk, wlk, p, q, bk1, tk, gama=np.inf, inner_solver=4, amg_options=None, host_call=False):
+    """One semismooth-Newton step of Class1/APD_SsN_Class1.m:137-212 at a fixed APD state as ONE library call
+    (``ssn_ssn_step_class1``; ``host_call``: ``ssn_ssn_step_class1_host`` on host arrays, copies inside the call).
+    Returns ``(lk_new, Fk_new, info)``."""
+    torch = _torch(); ctx = context()
+    keep = []
+    o = _amg_options(amg_options, keep)
+    info = (C.c_double * 12)()
+    if host_call:
+        arr = lambda v: v if (isinstance(v, torch.Tensor) and not v.is_cuda and v.dtype == torch.float64 and v.is_contiguous()) else \
+            torch.from_numpy(np.ascontiguousarray(np.asarray(v.cpu() if hasattr(v, "cpu") else v, dtype=np.float64)))
+        wh, lh, wlh, ph, qh = (arr(v) for v in (wk, lk, wlk, p, q))
+        m, n = ph.numel(), qh.numel()
+        gs = float(gama) if np.isscalar(gama) else float("inf")
+        gh = None if np.isscalar(gama) else arr(gama)
+        lk_new = torch.empty(n + m, dtype=torch.float64).pin_memory(); Fk_new = torch.empty(n + m, dtype=torch.float64).pin_memory()
+        ctx.call("ssn_ssn_step_class1_host", wh.data_ptr(), lh.data_ptr(), wlh.data_ptr(), ph.data_ptr(), qh.data_ptr(), m, n, float(bk1),
+                 float(tk), gh.data_ptr() if gh is not None else None, gs, int(inner_solver), _byref_or_null(o), lk_new.data_ptr(),
+                 Fk_new.data_ptr(), C.cast(info, C.c_void_p))
+    else:
+        pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+        wd, ld, wld = _dev(wk, count=m * n), _dev(lk, count=n + m), _dev(wlk, count=n + m)
+        gvec, gs = _gama_args(gama, m, n)
+        lk_new = torch.empty(n + m, dtype=torch.float64, device="cuda"); Fk_new = torch.empty_like(lk_new)
+        ctx.call("ssn_ssn_step_class1", _ptr(wd), _ptr(ld), _ptr(wld), _ptr(pd), _ptr(qd), m, n, float(bk1), float(tk), _ptr(gvec), gs,
+                 int(inner_solver), _byref_or_null(o), _ptr(lk_new), _ptr(Fk_new), C.cast(info, C.c_void_p))
+    v = list(info)
+    return lk_new, Fk_new, {"E": int(v[0]), "nnzH": int(v[1]), "info": [int(v[2]), int(v[3])], "itamg": int(v[4]), "resamg": v[5], "ll": int(v[6]),
+                            "ls_passes": int(v[7]), "Fk_old_norm": v[8], "Fk_new_norm": v[9], "ms_plan": v[10], "ms_amg": v[11], "ms_asat": None}
+
+
 def aug_PCG(prob_data, pcg_options):
     """``[zeta,itpcg,respcg,info] = aug_PCG(prob_data,pcg_options)`` -- aug_PCG.m:1-38."""
     return _solve("ssn_aug_pcg", prob_data, pcg_options, _pcg_options)

@@ -63,6 +63,62 @@ struct Clock {
 
 }  // namespace
 
+// ONE semismooth-Newton step of Class1/APD_SsN_Class1.m:137-212 at a fixed APD state (wk, wlk, bk1, tk) from the duals lk:
+// fused residual + active set -> ASAt -> the inner solve -> Armijo line search -> new residual, with no interpreter and
+// no plan-sized host traffic between them.  info (host, 12 doubles): E, nnz(H0), components, it_num, inner iterations,
+// relative residual of the inner solve, ll, reads of wk by the line search, ||F(lk)||, ||F(lk_new)||, ms of the plan-wide
+// part / of the inner solve (host clock; device-synchronised only when the phase profiler is on).
+void ssn_step_class1(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                     int64_t n, double bk1, double tk, const double* gama, double gama_s, int inner_solver, const ssn_amg_options* amg_in,
+                     double* lk_new, double* Fk_new, double* info12) {
+    SSN_REQUIRE(wk && lk && wlk && p && q && lk_new && Fk_new && m > 0 && n > 0, SSN_E_INVALID, "ssn_step_class1: bad arguments");
+    SSN_REQUIRE(inner_solver == 4 || inner_solver == 5, SSN_E_UNSUPPORTED, "ssn_step_class1: inner_solver must be 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)");
+    const int64_t N = m + n, mn = m * n;
+    const double nu = 0.2, delta = 0.9; const int ll_max = 500;                                      // :36
+    ssn_amg_options amg{}; amg.retol = 1e-11; amg.bigph = 1; amg.maxit = 30; amg.theta = 0.25; amg.smoth = 5; amg.cycle = 'w';
+    amg.isnsp = 1; amg.inter = 1; amg.fnode = 0; amg.guess_dev = nullptr;                           // :87-88
+    if (amg_in) amg = *amg_in;
+    const int gN = cdiv(N, 256);
+    Buf<double> axp(c, N), Fk(c, N), mFk(c, N), zeta(c, N), scal(c, 8);
+    Buf<uint8_t> s(c, mn);
+    double h[4];
+    Clock tp0;
+    plan_prox_residual(c, wk, lk, p, q, m, n, tk, gama, gama_s, axp, nullptr, nullptr, s, scal.p + 4);   // :139-144
+    SSN_LAUNCH(c, fk_kernel, gN, 256, 0, N, lk, axp.p, wlk, bk1, Fk.p, mFk.p);
+    double n2_old, Ecount;
+    { double hh[2]; read_back(c, scal.p + 4, hh, 2); n2_old = hh[0]; Ecount = hh[1]; }
+    double plan_ms = tp0.s() * 1e3;
+    Csr H0 = asat(c, s, p, q, m, n);                                                                  // :142
+    Clock ts;
+    ssn_csr Hv = H0.view();
+    ssn_prob_data pd{}; pd.bk1 = bk1; pd.tk = tk; pd.m = m; pd.n = n; pd.p_dev = p; pd.q_dev = q; pd.t_dev = nullptr;
+    pd.H0 = &Hv; pd.z_dev = mFk.p; pd.s_dev = nullptr; pd.phi_dev = nullptr;                          // :154-156
+    int itl = 0, inf2[2] = {0, 0}; double resl = 0.0;
+    hybrid_amg(c, &pd, &amg, zeta.p, &itl, &resl, inf2, inner_solver == 5);                           // :161 / :178
+    if (c->prof) SSN_CUDA(cudaStreamSynchronize(c->stream));
+    const double solve_ms = ts.s() * 1e3;
+    Clock tp1;
+    SSN_LAUNCH(c, dots4_kernel, 1, kVT, 0, N, lk, (const double*)nullptr, wlk, lk, Fk.p, zeta.p, Fk.p, (const double*)nullptr, scal.p);   // :182, :198
+    read_back(c, scal.p, h, 4);
+    const double f0 = bk1 / 2 * h[0] - h[1];
+    const double cFk_old = f0 + 0.5 * tk * n2_old;
+    const double ress = std::fabs(h[2]);
+    const double nFo = std::sqrt(h[3]);
+    int ll = 0, passes = 0; double n2_new = 0.0, cF_new = 0.0;
+    plan_linesearch(c, wk, lk, zeta, wlk, p, q, m, n, tk, bk1, gama, gama_s, nu, delta, ll_max, cFk_old, ress, 0, lk_new, &ll, &n2_new,
+                    &cF_new, &passes);                                                                // :189-211
+    plan_prox_residual(c, wk, lk_new, p, q, m, n, tk, gama, gama_s, axp, nullptr, nullptr, nullptr, scal.p + 4);   // :212
+    SSN_LAUNCH(c, fk_kernel, gN, 256, 0, N, lk_new, axp.p, wlk, bk1, Fk_new, (double*)nullptr);
+    SSN_LAUNCH(c, dots4_kernel, 1, kVT, 0, N, Fk_new, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr,
+               (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, scal.p);
+    read_back(c, scal.p, h, 1);
+    plan_ms += tp1.s() * 1e3;
+    if (info12) {
+        info12[0] = Ecount; info12[1] = (double)H0.nnz; info12[2] = inf2[0]; info12[3] = inf2[1]; info12[4] = itl; info12[5] = resl;
+        info12[6] = ll; info12[7] = passes; info12[8] = nFo; info12[9] = std::sqrt(h[0]); info12[10] = plan_ms; info12[11] = solve_ms;
+    }
+}
+
 void apd_ssn_class1(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
                     int64_t n, const double* gama, double gama_s, const ssn_apd_options* op, double* xk_out, double* lk_out,
                     ssn_apd_result* res, double* fxk_hist, double* kktx_hist, double* kktl_hist, int32_t* ssn_its_hist,

@@ -367,6 +367,31 @@ int ssn_apd_ssn_class1_host(ssn_ctx* c, const double* cost, const double* r, con
     });
 }
 
+int ssn_ssn_step_class1(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                        int64_t n, double bk1, double tk, const double* gama, double gama_s, int inner_solver, const ssn_amg_options* amg,
+                        double* lk_new, double* Fk_new, double* info12) {
+    return guarded(c, [&] { ssn_step_class1(c, wk, lk, wlk, p, q, m, n, bk1, tk, gama, gama_s, inner_solver, amg, lk_new, Fk_new, info12); sync(c); });
+}
+int ssn_ssn_step_class1_host(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                             int64_t n, double bk1, double tk, const double* gama, double gama_s, int inner_solver,
+                             const ssn_amg_options* amg, double* lk_new, double* Fk_new, double* info12) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(wk && lk && wlk && p && q && lk_new && Fk_new && m > 0 && n > 0, SSN_E_INVALID, "ssn_step_class1: bad arguments");
+        const size_t mn = (size_t)m * n, N = (size_t)(m + n);
+        Buf<double> dw(c, mn), dlk(c, N), dwl(c, N), dp(c, m), dq(c, n), dln(c, N), dF(c, N), dg;
+        SSN_CUDA(cudaMemcpyAsync(dw.p, wk, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dlk.p, lk, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dwl.p, wlk, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        if (gama) { dg.alloc(c, mn); SSN_CUDA(cudaMemcpyAsync(dg.p, gama, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream)); }
+        ssn_step_class1(c, dw, dlk, dwl, dp, dq, m, n, bk1, tk, gama ? dg.p : nullptr, gama_s, inner_solver, amg, dln, dF, info12);
+        SSN_CUDA(cudaMemcpyAsync(lk_new, dln.p, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(Fk_new, dF.p, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+
 int ssn_asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, ssn_csr* H) {
     return guarded(c, [&] { SSN_REQUIRE(H, SSN_E_INVALID, "ASAt: null output"); Csr h = asat(c, s, p, q, m, n); sync(c); h.release_to(H); });
 }

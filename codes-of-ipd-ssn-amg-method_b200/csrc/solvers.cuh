@@ -16,4 +16,7 @@ void apd_ssn_class1(ssn_ctx* c, const double* cost, const double* r, const doubl
                     int64_t n, const double* gama, double gama_s, const ssn_apd_options* op, double* xk_out, double* lk_out,
                     ssn_apd_result* res, double* fxk_hist, double* kktx_hist, double* kktl_hist, int32_t* ssn_its_hist,
                     double* steps_host, int64_t steps_cap);
+void ssn_step_class1(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                     int64_t n, double bk1, double tk, const double* gama, double gama_s, int inner_solver, const ssn_amg_options* amg_in,
+                     double* lk_new, double* Fk_new, double* info12);
 }  // namespace ssn

@@ -315,6 +315,22 @@ SSN_API int ssn_apd_ssn_class1_host(ssn_ctx *ctx, const double *c_host, const do
                             ssn_apd_result *result, double *fxk_hist_host, double *kkt_xk_hist_host,
                             double *kkt_lk_hist_host, int32_t *ssn_its_hist_host, double *steps_host, int64_t steps_cap);
 
+/* ONE semismooth-Newton step of the script (Class1/APD_SsN_Class1.m:137-212) at a fixed APD state -- wk (m*n), wlk (n+m),
+ * bk1, tk as :120-126 leave them -- from the duals lk: fused residual + active set -> ASAt -> Hybrid_AMG (inner_solver 4)
+ * or Hybrid_twogrid (5) -> the Armijo loop -> the new residual.  Outputs lk_new, Fk_new (n+m each) and, optionally, 12
+ * doubles on the HOST: nnz(s), nnz(H0), components, it_num, inner iterations, its relative residual, accepted ll, reads
+ * of wk by the line search, ||F(lk)||, ||F(lk_new)||, ms of the plan-wide part, ms of the inner solve.
+ * amg == NULL: the options of :87-88.  The _host variant takes and returns HOST arrays (one plugin call per step for a
+ * MATLAB caller without gpuArray; wk travels over PCIe every call). */
+SSN_API int ssn_ssn_step_class1(ssn_ctx *ctx, const double *wk_dev, const double *lk_dev, const double *wlk_dev,
+                        const double *p_dev, const double *q_dev, int64_t m, int64_t n, double bk1, double tk,
+                        const double *gama_dev, double gama_scalar, int inner_solver, const ssn_amg_options *amg,
+                        double *lk_new_dev, double *Fk_new_dev, double *info12_host);
+SSN_API int ssn_ssn_step_class1_host(ssn_ctx *ctx, const double *wk_host, const double *lk_host, const double *wlk_host,
+                        const double *p_host, const double *q_host, int64_t m, int64_t n, double bk1, double tk,
+                        const double *gama_host, double gama_scalar, int inner_solver, const ssn_amg_options *amg,
+                        double *lk_new_host, double *Fk_new_host, double *info12_host);
+
 /* [xk,lk] = warmup_class1(c,r,l,p,q,gama,0,maxit) -- Class1/warmup_class1.m:18-96, the A-ADMM warm start
  * called at Class1/APD_SsN_Class1.m:59, device resident: two fused plan-wide kernels per iteration
  * (17 plan-sized reads/writes instead of the ~45 of the Ax/Aty/prox/vector-update chain).

@@ -162,3 +162,24 @@ def test_every_selectable_inner_solver_reaches_the_same_optimum(gpu, inner_solve
     assert abs(out["fxk"][-1] - ref["fxk"][-1]) <= 1e-6 * max(abs(ref["fxk"][-1]), 1e-3)
     k = min(3, len(ref["fxk"]), len(out["fxk"]))
     assert np.allclose(out["fxk"][:k], ref["fxk"][:k], rtol=1e-7)
+
+
+def test_one_call_ssn_step_equals_the_operator_level_step(gpu):
+    """ssn_ssn_step_class1 (one library call: residual -> ASAt -> Hybrid_AMG -> Armijo loop -> residual) and its
+    host-buffer variant against driver.ssn_step, which makes the same step out of the operator-level calls: same discrete
+    facts, same duals."""
+    import importlib
+    import torch
+    drv = importlib.import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+    P = gpu.problems.grid_problem(24, seed=1)
+    gpu.rng_reset()
+    st = drv.capture_state(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], outer=3, ssn_it=1)
+    gpu.rng_reset(); lk_a, Fk_a, ia = drv.ssn_step(st)
+    gpu.rng_reset(); lk_b, Fk_b, ib = gpu.ssn_step_class1(st["wk"], st["lk"], st["wlk"], st["p"], st["q"], st["bk1"], st["tk"])
+    gpu.rng_reset(); lk_c, Fk_c, ic = gpu.ssn_step_class1(st["wk"].cpu(), st["lk"].cpu(), st["wlk"].cpu(), st["p"].cpu(), st["q"].cpu(),
+                                                          st["bk1"], st["tk"], host_call=True)
+    for info in (ib, ic):
+        assert (info["E"], info["itamg"], info["ll"], info["info"][0]) == (int(ia["E"]), int(ia["itamg"]), int(ia["ll"]), int(ia["info"][0]))
+    scale = float(lk_a.abs().max())
+    assert float((lk_b - lk_a).abs().max()) <= 1e-13 * scale and float((lk_c.cuda() - lk_a).abs().max()) <= 1e-13 * scale
+    assert float((Fk_b - Fk_a).abs().max()) <= 1e-10 * float(Fk_a.abs().max()) + 1e-14
