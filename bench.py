@@ -269,8 +269,9 @@ def main():
     if world == 1:
         # the same step through the operator-level calls (driver.ssn_step), outside the timed region: its phase laps
         # (each closed by a device synchronise) and the Newton direction the kernel timings below need
-        ssnamg.rng_reset()
-        lk_py, _, info_py = drv.ssn_step(state)
+        for _ in range(3):                                   # the first calls of this path pay its one-time costs
+            ssnamg.rng_reset()
+            lk_py, _, info_py = drv.ssn_step(state)
         assert float((lk_py - lk_new).abs().max()) <= 1e-12 * float(lk_new.abs().max()), "one-call step and operator-level step disagree"
         info = dict(info_py, **{k: info[k] for k in ("E", "nnzH", "itamg", "ll", "ls_passes")})
     # dominant HBM-bound kernel, timed alone with CUDA events on the launching stream (sampler still running)
