@@ -313,7 +313,8 @@ inline void emu_launch(ssn_ctx* c, K kernel, dim3 grid, int block, A... args) {
 template <class K, class... A>
 inline void emu_launch_cluster(ssn_ctx* c, K kernel, int ncta, int block, size_t smem, A... args) {
     c->launches++;
-    std::vector<std::vector<unsigned char>> mem((size_t)ncta, std::vector<unsigned char>(smem + 64, (unsigned char)0xA5));
+    constexpr size_t kCanary = 4096;                      // untouched bytes behind every block's shared memory, checked after the kernel
+    std::vector<std::vector<unsigned char>> mem((size_t)ncta, std::vector<unsigned char>(smem + 64 + kCanary, (unsigned char)0xA5));
     std::barrier<> cbar(ncta * block);
     emu::cluster_bar = &cbar;
     std::vector<std::unique_ptr<emu::BlockShared>> bs;
@@ -337,6 +338,12 @@ inline void emu_launch_cluster(ssn_ctx* c, K kernel, int ncta, int block, size_t
                 cbar.arrive_and_drop();
             });
     for (auto& th : threads) th.join();
+    for (int b = 0; b < ncta; ++b)
+        for (size_t i = 0; i < kCanary; ++i)
+            if (emu::cluster_smem[b][smem + i] != (unsigned char)0xA5) {
+                std::fprintf(stderr, "emu: block %d wrote %zu bytes past its %zu bytes of shared memory\n", b, i, smem);
+                std::abort();
+            }
     emu::cluster_bar = nullptr;
 }
 #define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, dim3(grid), (int)(block), __VA_ARGS__)

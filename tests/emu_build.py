@@ -35,6 +35,8 @@ def build(tmpdir, harness, sources, so_name):
     so = os.path.join(d, so_name)
     cmd = ["g++", "-std=c++20", "-O0", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-I" + d,
            "-I" + os.path.join(ROOT, "include")]
+    if os.environ.get("SSN_EMU_ASAN") == "1":              # out-of-bounds accesses of the emulated kernels (run with LD_PRELOAD=libasan.so)
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
     for u in units:
         cmd += ["-x", "c++", u]
     r = subprocess.run(cmd + ["-o", so], cwd=d, capture_output=True, text=True)
