@@ -519,8 +519,6 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
     __shared__ double s_a[4][kSmallT];
     __shared__ unsigned s_key[4][kSmallT];
     __shared__ double s_val[4][kSmallT];
-    __shared__ unsigned s_skey[4][kSmallT];
-    __shared__ double s_sval[4][kSmallT];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int row = blockIdx.x * 4 + w; row < nrows; row += gridDim.x * 4) {
         const int a0 = ap[row], a1 = ap[row + 1], lenA = a1 - a0;
@@ -554,25 +552,39 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
             s_key[w][t] = ((unsigned)bi[src] << 8) | (unsigned)t;
             s_val[w][t] = __dmul_rn(s_a[w][j], bv[src]);
         }
+        // sort the products by (column, order of formation): the keys are distinct, so any sorting network gives THE order --
+        // a bitonic network over the next power of two (log^2 steps; the rank sort it replaces was T^2/32 steps per lane)
+        int Pw = 32;
+        while (Pw < T) Pw <<= 1;
+        for (int t = T + lane; t < Pw; t += 32) s_key[w][t] = 0xffffffffu;
         __syncwarp();
-        for (int t = lane; t < T; t += 32) {                // rank sort (keys are distinct)
-            const unsigned key = s_key[w][t];
-            int r = 0;
-            for (int u = 0; u < T; ++u) r += (s_key[w][u] < key) ? 1 : 0;
-            s_skey[w][r] = key; s_sval[w][r] = s_val[w][t];
+        for (int kk = 2; kk <= Pw; kk <<= 1) {
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                for (int i = lane; i < Pw; i += 32) {
+                    const int ixj = i ^ jj;
+                    if (ixj > i) {
+                        const unsigned ka = s_key[w][i], kb = s_key[w][ixj];
+                        const bool up = (i & kk) == 0;
+                        if ((ka > kb) == up) {
+                            s_key[w][i] = kb; s_key[w][ixj] = ka;
+                            const double va = s_val[w][i]; s_val[w][i] = s_val[w][ixj]; s_val[w][ixj] = va;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
         const int out0 = ubptr ? ubptr[(size_t)row * nwin] : row * kSmallT;
         int written = 0;
         for (int base = 0; base < T; base += 32) {
             const int i = base + lane;
             bool keep = false; double acc = 0.0; int col = 0;
             if (i < T) {
-                col = (int)(s_skey[w][i] >> 8);
-                const bool head = (i == 0) || ((int)(s_skey[w][i - 1] >> 8) != col);
+                col = (int)(s_key[w][i] >> 8);
+                const bool head = (i == 0) || ((int)(s_key[w][i - 1] >> 8) != col);
                 if (head) {
-                    acc = __dadd_rn(0.0, s_sval[w][i]);
-                    for (int j = i + 1; j < T && (int)(s_skey[w][j] >> 8) == col; ++j) acc = __dadd_rn(acc, s_sval[w][j]);
+                    acc = __dadd_rn(0.0, s_val[w][i]);
+                    for (int j = i + 1; j < T && (int)(s_key[w][j] >> 8) == col; ++j) acc = __dadd_rn(acc, s_val[w][j]);
                     keep = (acc != 0.0);
                 }
             }
