@@ -245,8 +245,10 @@ def test_scan_paths_agree(emu, oracle):
     assert_same_matrix(spgemm(emu, A, B), ref(A, B), "A*B, one-block scans")
 
 
-@pytest.mark.parametrize("m,n,density,isnsp,cycle,bigph,noreg", [(90, 70, 0.05, 1, "w", 1, 0), (90, 70, 0.05, 1, "w", 1, 1), (90, 70, 0.05, 0, "v", 1, 0),
-                                                                  (60, 50, 0.08, 1, "w", 0, 0), (60, 50, 0.08, 1, "w", 0, 1)])
+_slow = __import__("emu_build").slow
+@pytest.mark.parametrize("m,n,density,isnsp,cycle,bigph,noreg", [(90, 70, 0.05, 1, "w", 1, 0), pytest.param(90, 70, 0.05, 1, "w", 1, 1, marks=_slow),
+                                                                  pytest.param(90, 70, 0.05, 0, "v", 1, 0, marks=_slow),
+                                                                  pytest.param(60, 50, 0.08, 1, "w", 0, 0, marks=_slow), (60, 50, 0.08, 1, "w", 0, 1)])
 def test_dsm_cluster_solve_against_the_oracle(emu, oracle, monkeypatch, m, n, density, isnsp, cycle, bigph, noreg):
     """amg_cluster.cu (Class_AMG's solve loop inside one cluster, level vectors in distributed shared memory, the
     two-half-sweep form of the bigraph smoother, op list of the cycle) on a cluster of 16 emulated CTAs: cycle counts
