@@ -1110,6 +1110,7 @@ __global__ void __launch_bounds__(256) pcg_kernel(PcgArgs a) {
 constexpr int kPT = SSN_PT;                   // threads per block of the persistent kernel
 constexpr int kPBlocksPerSM = SSN_PBPS;       // resident blocks per SM (the grid is num_sms * kPBlocksPerSM)
 constexpr int kPLevels = 16;
+constexpr int kGridXs = 8192;                  // doubles of shared memory per block of the grid-wide kernel for the copy of a gathered vector
 
 struct PersistArgs {
     const LevelDev* levels; int J, kd, smoth, isnsp, wcycle;
@@ -1120,6 +1121,7 @@ struct PersistArgs {
     int tpr[kPLevels];            // lanes per row of A_k (k < kd)
     int tpr_p[kPLevels];          // lanes per row of Pro_k / Pro_k' (k <= kd)
     int tpr_gs;                   // lanes per row of the coupled block Gauss-Seidel update (0: tpr[0])
+    int xs_ok[kPLevels];          // 1: A_k is dense enough that its passes read the gathered vector from a shared-memory copy
     size_t smem_budget;           // dynamic shared memory available for staged matrix slices
 };
 
@@ -1161,7 +1163,8 @@ __device__ void stage_slice(const TM& G, PSlice* S, int N, const int* ptr, const
     }
 }
 
-template <int TPR>
+// SM: x is a shared-memory copy of the vector (plain loads) instead of the vector in global memory (ld.global.cg)
+template <int TPR, bool SM = false>
 __device__ __forceinline__ double row_dot_s(const PSlice& S, const double* x, int row, int sub, bool valid) {
     double s = 0.0;
     if (valid) {
@@ -1171,10 +1174,10 @@ __device__ __forceinline__ double row_dot_s(const PSlice& S, const double* x, in
         for (; e + 3 * TPR < e1; e += 4 * TPR) {
             const int i0 = ci[e], i1 = ci[e + TPR], i2 = ci[e + 2 * TPR], i3 = ci[e + 3 * TPR];
             const double v0 = cv[e], v1 = cv[e + TPR], v2 = cv[e + 2 * TPR], v3 = cv[e + 3 * TPR];
-            const double x0 = __ldcg(x + i0), x1 = __ldcg(x + i1), x2 = __ldcg(x + i2), x3 = __ldcg(x + i3);
+            const double x0 = SM ? x[i0] : __ldcg(x + i0), x1 = SM ? x[i1] : __ldcg(x + i1), x2 = SM ? x[i2] : __ldcg(x + i2), x3 = SM ? x[i3] : __ldcg(x + i3);
             s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
         }
-        for (; e < e1; e += TPR) s = fma(cv[e], __ldcg(x + ci[e]), s);
+        for (; e < e1; e += TPR) s = fma(cv[e], SM ? x[ci[e]] : __ldcg(x + ci[e]), s);
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -1230,7 +1233,8 @@ struct GridTeam {
     static constexpr int T = kPT;
     static constexpr int U = 1;               // rows per thread in flight (row_dots)
     cg::grid_group grid; double* part; double* red; int flip;
-    double* xs = nullptr;
+    double* xs = nullptr;                     // shared-memory copy of a gathered vector (dense levels, the dense tail input)
+    int xs_cap = 0;
     // vectors that change during the kernel are read from L2, never through a stale L1 line
     static __device__ __forceinline__ double ld(const double* p) { return __ldcg(p); }
     __device__ __forceinline__ int blk() const { return (int)blockIdx.x; }
@@ -1290,6 +1294,7 @@ struct ClusterTeam {
     double* slots;                            // [2][2*kCMax]: slot r of every CTA is written by CTA r through DSMEM
     int rank, ncta, flip;
     double* xs;                               // 2048 doubles: the input vector of the dense tail operator
+    int xs_cap = 2048;
     // Plain (L1-cached) loads: every pass ends in a cluster barrier with release / acquire semantics, for which the
     // compiler emits CCTL.IVALL -- the L1 is invalidated at every barrier, so a line can only have been filled after
     // the last write to it by another CTA, and the gathers of a row slice, which mostly hit the slice's own
@@ -1326,10 +1331,10 @@ struct ClusterTeam {
 // d[u] = A(row_u,:)*x for the U rows row0 + u*RP of a thread (TPR lanes per row), all U rows in flight at once: every
 // round issues one index/value load and one gather per row before any of them is consumed, so a thread has U
 // independent L2 round trips outstanding instead of one.  U == 1 keeps the 4-deep batching inside the row.
-template <int TPR, int U, class TM>
+template <int TPR, int U, class TM, bool SM = false>
 __device__ __forceinline__ void row_dots(const PSlice& S, const double* x, int row0, int RP, int sub, double (&d)[U]) {
     if constexpr (U == 1) {
-        d[0] = row_dot_s<TPR>(S, x, row0, sub, row0 < S.r1);
+        d[0] = row_dot_s<TPR, SM>(S, x, row0, sub, row0 < S.r1);
     } else {
         int e[U], e1[U];
 #pragma unroll
@@ -1344,7 +1349,7 @@ __device__ __forceinline__ void row_dots(const PSlice& S, const double* x, int r
 #pragma unroll
             for (int u = 0; u < U; ++u) { const bool has = e[u] < e1[u]; i[u] = has ? S.ci[e[u]] : -1; v[u] = has ? S.cv[e[u]] : 0.0; }
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = (i[u] >= 0) ? TM::ld(x + i[u]) : 0.0;
+            for (int u = 0; u < U; ++u) xv[u] = (i[u] >= 0) ? (SM ? x[i[u]] : TM::ld(x + i[u])) : 0.0;
             more = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) { d[u] = fma(v[u], xv[u], d[u]); e[u] += TPR; more |= (e[u] < e1[u]); }
@@ -1356,11 +1361,25 @@ __device__ __forceinline__ void row_dots(const PSlice& S, const double* x, int r
     }
 }
 
+// A level whose matrix is dense (hundreds of entries per row: early-phase SsN systems, the coarse levels of partial OT)
+// re-reads every element of the gathered vector many times per pass: each block copies the n <= xs_cap doubles into its
+// shared memory once and gathers from there (its own L2 traffic drops from 20 to 12 bytes per entry and the gathers stop
+// being dependent L2 round trips).  Returns the copy, or null when the level does not qualify.
+template <class TM>
+__device__ __forceinline__ const double* p_stage_x(TM& G, const double* x, int n, bool on) {
+    if (!on || x == nullptr || G.xs == nullptr || n > G.xs_cap) return nullptr;
+    __syncthreads();                                        // nobody still reads the previous copy
+    for (int i = threadIdx.x; i < n; i += TM::T) G.xs[i] = TM::ld(x + i);
+    __syncthreads();
+    return G.xs;
+}
+
 // g = r - A e on the block's rows (e == nullptr: g = r); sum g and sum g^2 when want (else just the barrier)
 template <class TM>
 __device__ void p_resid(TM& G, const PSlice& S, int tpr, const double* r, const double* e, double* g, bool want,
-                        double& sg, double& sg2) {
+                        double& sg, double& sg2, int n_stage = 0) {
     sg = 0.0; sg2 = 0.0;
+    const double* xs = p_stage_x(G, e, n_stage, n_stage > 0);
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
         constexpr int U = TM::U, RP = TM::T / TPR;
@@ -1368,7 +1387,8 @@ __device__ void p_resid(TM& G, const PSlice& S, int tpr, const double* r, const 
         for (int base = S.first(U * RP, G.blk()); base < S.r1; base += S.step(U * RP, G.nblk())) {
             const int row0 = base + threadIdx.x / TPR;
             double d[U];
-            if (e != nullptr) row_dots<TPR, U, TM>(S, e, row0, RP, sub, d);
+            if (xs != nullptr) row_dots<TPR, U, TM, true>(S, xs, row0, RP, sub, d);
+            else if (e != nullptr) row_dots<TPR, U, TM>(S, e, row0, RP, sub, d);
             else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) d[u] = 0.0;
@@ -1432,8 +1452,9 @@ __device__ void p_gs_apply(TM& G, const LevelDev& L, const PSlice& S, int tpr, c
 // one fused damped-Jacobi step (kernel correction through coef); returns Axi'ealt
 template <class TM>
 __device__ double p_jacobi(TM& G, const LevelDev& L, const PSlice& S, int tpr, const double* r, const double* ecur, double* ealt,
-                           double coef, bool e_zero) {
+                           double coef, bool e_zero, bool stage = false) {
     double part = 0.0, dummy = 0.0;
+    const double* xs = p_stage_x(G, e_zero ? nullptr : ecur, L.N, stage);
     with_tpr(tpr, [&](auto T) {
         constexpr int TPR = decltype(T)::value;
         constexpr int U = TM::U, RP = TM::T / TPR;
@@ -1441,7 +1462,8 @@ __device__ double p_jacobi(TM& G, const LevelDev& L, const PSlice& S, int tpr, c
         for (int base = S.first(U * RP, G.blk()); base < S.r1; base += S.step(U * RP, G.nblk())) {
             const int row0 = base + threadIdx.x / TPR;
             double d[U];
-            if (!e_zero) row_dots<TPR, U, TM>(S, ecur, row0, RP, sub, d);
+            if (xs != nullptr) row_dots<TPR, U, TM, true>(S, xs, row0, RP, sub, d);
+            else if (!e_zero) row_dots<TPR, U, TM>(S, ecur, row0, RP, sub, d);
             else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) d[u] = 0.0;
@@ -1604,7 +1626,7 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
                 if (L.bigph) {
                     for (int s = 0; s < a.smoth; ++s) {
                         double sg, sg2;
-                        PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ec, L.g, a.isnsp != 0, sg, sg2));
+                        PDBG(25, p_resid(G, P.A, tpr, L.r, ez ? nullptr : ec, L.g, a.isnsp != 0, sg, sg2, a.xs_ok[k] ? L.N : 0));
                         const double coef = a.isnsp ? sg / L.xx : 0.0;
                         PDBG(26, p_gs_apply(G, L, P.A, a.tpr_gs > 0 ? a.tpr_gs : tpr, L.g, ec, coef, post, ez));
                         ez = false;
@@ -1612,7 +1634,7 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
                 } else {
                     for (int s = 0; s < a.smoth; ++s) {
                         const double coef = a.isnsp ? (sr - dotAe) / L.xx : 0.0;
-                        PDBG(27, dotAe = p_jacobi(G, L, P.A, tpr, L.r, ec, ea, coef, ez));
+                        PDBG(27, dotAe = p_jacobi(G, L, P.A, tpr, L.r, ec, ea, coef, ez, a.xs_ok[k] != 0));
                         double* t = ec; ec = ea; ea = t;
                         ez = false;
                     }
@@ -1624,7 +1646,7 @@ __device__ __forceinline__ void persist_body(const PersistArgs& a, TM& G, unsign
                 }
                 // restriction: r_{k+1} = Pro' (r - A e)                  MG_Wcycle.m:26
                 double d1, d2;
-                PDBG(25, p_resid(G, P.A, tpr, L.r, (ez ? nullptr : ec), L.g, false, d1, d2));
+                PDBG(25, p_resid(G, P.A, tpr, L.r, (ez ? nullptr : ec), L.g, false, d1, d2, a.xs_ok[k] ? L.N : 0));
                 PDBG(28, p_spmv(G, ps[k + 1].Td, a.tpr_p[k + 1], L.g, sl[k + 1].r, false, nullptr, d1, d2));
                 st.ecur[k] = ec; st.ealt[k] = ea; st.dot_e[k] = dotAe;
                 st.sum_r[k + 1] = d1;
@@ -1664,8 +1686,9 @@ __global__ void __launch_bounds__(kPT, kPBlocksPerSM) persist_solve_kernel(const
     __shared__ LevelDev sl[kPLevels];
     __shared__ PLevelS ps[kPLevels];
     __shared__ PState pst;
-    GridTeam G{cg::this_grid(), a.part, red, 0, nullptr};
-    persist_body(a, G, p_dsm, sl, ps, &pst);
+    // the first kGridXs doubles of the dynamic shared memory hold the copy of a gathered vector, the rest the staged slices
+    GridTeam G{cg::this_grid(), a.part, red, 0, reinterpret_cast<double*>(p_dsm), kGridXs};
+    persist_body(a, G, p_dsm + sizeof(double) * kGridXs, sl, ps, &pst);
 }
 
 // The same solve loop inside ONE thread-block cluster (launched with a runtime cluster dimension of 16, or 8 where
@@ -1901,6 +1924,11 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
         a.tpr[k] = tpr_for(L.N ? (double)L.A.nnz / L.N : 0.0);
         a.tpr_p[k] = (k > 0) ? tpr_for(L.N ? (double)L.P.nnz / std::max(1, L.N) : 0.0) : 2;
     }
+    for (int k = 0; k < kPLevels; ++k) a.xs_ok[k] = 0;
+    for (int k = 0; k < H.dense_from && k < kPLevels; ++k) {
+        const Level& L = H.lv[k];
+        a.xs_ok[k] = (c->stage_dense && L.N > 0 && L.N <= kGridXs && (double)L.A.nnz / L.N >= 48.0) ? 1 : 0;
+    }
     const int hl = o.maxit + 2;
     Buf<double> hist(c, (size_t)2 * hl);
     Buf<int> iout(c, 4);
@@ -1966,7 +1994,7 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
         SSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_solve_kernel, kPT, smem));
         if (per_sm < kPBlocksPerSM) return false;
         const int grid = c->num_sms * kPBlocksPerSM;
-        a.smem_budget = smem;
+        a.smem_budget = smem - sizeof(double) * kGridXs;      // what is left for staged matrix slices
         { const char* e = getenv("SSN_PERSIST_SMEM"); if (e && e[0] == '0') a.smem_budget = 0; }
         part.alloc(c, (size_t)4 * grid);
         a.part = part.p;

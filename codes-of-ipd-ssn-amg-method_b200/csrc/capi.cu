@@ -53,6 +53,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_PERSIST"); c->persist = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PERSIST_MAXNNZ"); if (e && atoll(e) > 0) c->persist_max_nnz = atoll(e); }
     { const char* e = getenv("SSN_CLUSTER_SOLVE"); c->cluster_solve = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_STAGE_DENSE"); c->stage_dense = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_MIS_CLUSTER"); c->mis_cluster = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DSM_SOLVE"); c->dsm_solve = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_FUSED_SETUP"); c->fused_setup = (e && e[0] == '1'); }

@@ -70,6 +70,7 @@ struct ssn_ctx {
     bool fused_setup = false;             // SSN_FUSED_SETUP=1: the small levels of the hierarchy are coarsened by ONE kernel (one CTA; same
                                           // hierarchy bit for bit, but slower than kernel by kernel on a B200: opt-in)
     bool cluster_solve = true;            // SSN_CLUSTER_SOLVE=0: the persistent solve always runs grid-wide (cooperative launch)
+    bool stage_dense = true;              // SSN_STAGE_DENSE=0: the grid-wide solve kernel gathers from L2 on dense levels too
     bool mis_cluster = true;              // SSN_MIS_CLUSTER=0: the MIS rounds of mis_set.m launch by launch (one host read per round)
     bool dsm_solve = true;                // SSN_DSM_SOLVE=0: the cluster solve keeps its vectors in global memory (first cluster kernel)
     int64_t cluster_max_nnz = (int64_t)1 << 20;   // SSN_CLUSTER_MAXNNZ: larger hierarchies (explicit levels) use the grid-wide kernel

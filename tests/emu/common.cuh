@@ -213,6 +213,7 @@ struct ssn_ctx {
     int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
     int small_scan_max = 1 << 14;
     bool device_setup = true;
+    bool stage_dense = true;              // SSN_STAGE_DENSE=0: the grid-wide solve kernel gathers from L2 on dense levels too
     bool mis_cluster = true;              // SSN_MIS_CLUSTER=0: the MIS rounds of mis_set.m launch by launch (one host read per round)
     bool fused_setup = true, cluster_solve = true;     // the emulated hierarchies go through the fused kernel (opt-in in the library)
     int64_t cluster_max_nnz = (int64_t)1 << 20;
