@@ -857,7 +857,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
         if (k < kd) { a.lv[k].Pu.loc = loc.p + at_loc; at_loc += (size_t)H.lv[k + 1].P.nnz; }
         if (k >= 1) { a.lv[k].Td.loc = loc.p + at_loc; at_loc += (size_t)H.lv[k].Pt.nnz; }
     }
-    SSN_CUDA(cudaMemcpyAsync(dprog.p, prog.data(), sizeof(int) * prog.size(), cudaMemcpyHostToDevice, c->stream));
+    upload_small(c, dprog.p, prog.data(), sizeof(int) * prog.size());
     a.kd = kd; a.smoth = H.smoth; a.isnsp = o.isnsp; a.maxit = o.maxit;
     a.b = b; a.x = x; a.retol = o.retol;
     a.relk = hist; a.rho = hist + hl; a.it_out = iout;

@@ -830,7 +830,7 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
         hd[k] = d;
     }
     H->dev.alloc(c, J);
-    SSN_CUDA(cudaMemcpyAsync(H->dev.p, hd.data(), sizeof(LevelDev) * J, cudaMemcpyHostToDevice, c->stream));
+    upload_small(c, H->dev.p, hd.data(), sizeof(LevelDev) * J);
     SSN_CUDA(cudaStreamSynchronize(c->stream));
     H->part.alloc(c, 4096);
     H->scal.alloc(c, 64);

@@ -1864,7 +1864,7 @@ void build_dense_tail(ssn_ctx* c, Hierarchy& H, int isnsp, bool wcycle) {
     H.dense_from = from;
     H.hdev.resize(J);
     for (int k = 0; k < J; ++k) H.hdev[k] = level_dev(H.lv[k]);
-    SSN_CUDA(cudaMemcpyAsync(H.dev.p, H.hdev.data(), sizeof(LevelDev) * J, cudaMemcpyHostToDevice, c->stream));
+    upload_small(c, H.dev.p, H.hdev.data(), sizeof(LevelDev) * J);
 }
 
 void cycle_host(ssn_ctx* c, Hierarchy& H, int k, int isnsp, bool wcycle, bool e_zero) {

@@ -75,6 +75,7 @@ int ssn_create(ssn_ctx** out, int device) {
         uint64_t thr = UINT64_MAX;
         SSN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         SSN_CUDA(cudaMallocHost((void**)&c->h_pin, sizeof(double) * ssn_ctx::kPinDoubles));
+        SSN_CUDA(cudaMallocHost((void**)&c->h_up, (size_t)ssn_ctx::kUpSlots * ssn_ctx::kUpBytes));
         { const char* e = getenv("SSN_POLL_READS"); c->poll_reads = !(e && e[0] == '0'); }
         if (cudaHostAlloc((void**)&c->h_poll, sizeof(double) * (ssn_ctx::kPinDoubles + 2), cudaHostAllocMapped) == cudaSuccess &&
             cudaHostGetDevicePointer((void**)&c->d_poll, c->h_poll, 0) == cudaSuccess) {
@@ -98,6 +99,7 @@ int ssn_destroy(ssn_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->hier) { delete c->hier; c->hier = nullptr; }
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_up) cudaFreeHost(c->h_up);
     if (c->h_poll) cudaFreeHost(c->h_poll);
     if (c->mt_state) cudaFree(c->mt_state);
     delete c;

@@ -58,6 +58,11 @@ struct ssn_ctx {
     double* h_poll = nullptr;             // kPinDoubles doubles + 1 flag word, cudaHostAlloc(mapped)
     double* d_poll = nullptr;             // the same memory as the device sees it
     unsigned long long poll_seq = 0;
+    // small host->device uploads (level tables, lists) go through a ring of PINNED slots: cudaMemcpyAsync from pageable
+    // memory synchronises the stream before it copies, i.e. every such upload was a host wait for all queued kernels
+    static constexpr int kUpSlots = 32, kUpBytes = 4096;
+    unsigned char* h_up = nullptr;        // kUpSlots * kUpBytes bytes, cudaMallocHost
+    int up_next = 0;
     // MATLAB random stream (device-resident MT19937 state)
     uint32_t* mt_state = nullptr;         // 624 words + 1 index word
     int64_t rng_drawn = 0;
@@ -216,6 +221,19 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // sequence word changes (sparse.cu); returns after the values have arrived
 void poll_read(ssn_ctx* c, const void* dev, size_t bytes);
 void poll_read_ints(ssn_ctx* c, const int* const* src, int k);
+
+// asynchronous upload of a few KB from any host memory (staged through the pinned ring; larger blocks: plain copy)
+inline void upload_small(ssn_ctx* c, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes == 0) return;
+    if (c->h_up && bytes <= (size_t)ssn_ctx::kUpBytes) {
+        unsigned char* slot = c->h_up + (size_t)c->up_next * ssn_ctx::kUpBytes;
+        c->up_next = (c->up_next + 1) % ssn_ctx::kUpSlots;
+        std::memcpy(slot, src_host, bytes);
+        SSN_CUDA(cudaMemcpyAsync(dst_dev, slot, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        SSN_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+}
 
 // read `count` elements (<= pinned scratch) back to the host, synchronously
 template <class T>

@@ -492,7 +492,7 @@ void hybrid_amg(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts
         if (!small_multi.empty()) {
             Buf<int> list(c, small_multi.size()), pos(c, N), err(c, 1);
             err.zero();
-            SSN_CUDA(cudaMemcpyAsync(list.p, small_multi.data(), sizeof(int) * small_multi.size(), cudaMemcpyHostToDevice, c->stream));
+            upload_small(c, list.p, small_multi.data(), sizeof(int) * small_multi.size());
             SSN_LAUNCH(c, scatter_pos_kernel, cdiv(N, 256), 256, 0, N, perm.p, nullptr, pos.p);
             int maxsz = 2;
             for (int k : small_multi) maxsz = std::max(maxsz, hs[k]);
@@ -619,7 +619,7 @@ void pot_epilogue(ssn_ctx* c, int N, PotPrologue& P, const double* vv, const dou
     SSN_LAUNCH(c, pot_zeta_kernel, cdiv(N, 256), 256, 0, N, ww, vv, tt * vww, zeta);
     const double vz = dev_dot(c, P.v, zeta, N);
     const double zeta2 = (P.z2 - P.sg * vz) / P.phi_e;
-    SSN_CUDA(cudaMemcpyAsync(zeta + N, &zeta2, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    upload_small(c, zeta + N, &zeta2, sizeof(double));
     SSN_CUDA(cudaStreamSynchronize(c->stream));
 }
 

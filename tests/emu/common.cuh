@@ -349,6 +349,7 @@ inline void emu_launch_cluster(ssn_ctx* c, K kernel, int ncta, int block, size_t
 }
 #define SSN_LAUNCH(ctx, kernel, grid, block, smem, ...) ::ssn::emu_launch((ctx), kernel, dim3(grid), (int)(block), __VA_ARGS__)
 
+inline void upload_small(ssn_ctx*, void* dst_dev, const void* src_host, size_t bytes) { std::memcpy(dst_dev, src_host, bytes); }
 template <class T>
 inline void read_back(ssn_ctx*, const T* dev, T* host, size_t count) { ++emu::host_reads; std::memcpy(host, dev, count * sizeof(T)); }
 template <class T>
