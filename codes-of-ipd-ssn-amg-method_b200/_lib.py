@@ -103,6 +103,7 @@ SIGNATURES = {
     "ssn_aty_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "ssn_prox_residual": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _vp, _vp, _vp,
                                  _pdbl, _pi64]),
+    "ssn_prox_residual_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "ssn_prox_residual_pot": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _pdbl, _pi64]),
     "ssn_ssn_step_class1": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _int, _vp, _vp, _vp, _vp]),
     "ssn_ssn_step_class1_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _dbl, _int, _vp, _vp, _vp, _vp]),

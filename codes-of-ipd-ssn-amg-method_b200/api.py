@@ -211,7 +211,7 @@ def Aty(y, p, q):
     return _ret(z, host)
 
 
-def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count")):
+def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count"), scal_dev=None):
     """Fused SsN residual pieces in one read of ``w`` (Class1/APD_SsN_Class1.m:139-144,184):
     ``z=(w-Aty(lam))/tk``, ``s=(z>=0)&(z<=gama)``, ``prox=min(max(0,z),gama)``, ``Ax(prox)``,
     ``||prox||^2``, ``nnz(s)``.  ``want`` selects the outputs; returns a dict."""
@@ -227,9 +227,15 @@ def prox_residual(w, lam, p, q, tk, gama=np.inf, want=("Axprox", "norm2", "count
     axp = mk("Axprox", n + m, torch.float64); px = mk("prox", m * n, torch.float64)
     z = mk("z", m * n, torch.float64); s = mk("s", m * n, torch.uint8)
     n2 = C.c_double(0.0); cnt = C.c_int64(0)
-    ctx.call("ssn_prox_residual", _ptr(wd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(gvec), gs,
-             _ptr(axp), _ptr(px), _ptr(z), _ptr(s), C.byref(n2), C.byref(cnt))
-    out = {"norm2": n2.value, "count": cnt.value}
+    if scal_dev is not None:
+        # ``scal_dev``: 2 device doubles that receive the norm term and nnz(s); no host read, nothing synchronised
+        ctx.call("ssn_prox_residual_dev", _ptr(wd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(gvec), gs,
+                 _ptr(axp), _ptr(px), _ptr(z), _ptr(s), _ptr(scal_dev))
+        out = {}
+    else:
+        ctx.call("ssn_prox_residual", _ptr(wd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(tk), _ptr(gvec), gs,
+                 _ptr(axp), _ptr(px), _ptr(z), _ptr(s), C.byref(n2), C.byref(cnt))
+        out = {"norm2": n2.value, "count": cnt.value}
     for k, v in (("Axprox", axp), ("prox", px), ("z", z), ("s", s)):
         if v is not None:
             out[k] = _ret(v, host)

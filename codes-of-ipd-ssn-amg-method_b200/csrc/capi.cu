@@ -280,6 +280,14 @@ int ssn_prox_residual(ssn_ctx* c, const double* w, const double* lam, const doub
     });
 }
 
+int ssn_prox_residual_dev(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
+                          double tk, const double* gama, double gama_s, double* axp, double* prox, double* z, uint8_t* s, double* scal2_dev) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(scal2_dev != nullptr, SSN_E_INVALID, "prox_residual_dev: null scalar output");
+        plan_prox_residual(c, w, lam, p, q, m, n, tk, gama, gama_s, axp, prox, z, s, scal2_dev);
+    });
+}
+
 int ssn_prox_residual_pot(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
                           double tk, const double* phi, double* hp, double* prox, uint8_t* s, double* t, double* norm2_out,
                           int64_t* count_out) {

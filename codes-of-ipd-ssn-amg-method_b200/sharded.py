@@ -34,6 +34,10 @@ class _CudaOps:
     def prox_residual(self, w, lam, p, q, tk, gama, want):
         return self.api.prox_residual(w, lam, p, q, tk, gama, want=want)
 
+    def prox_residual_dev(self, w, lam, p, q, tk, gama, want, scal_dev):
+        """the same with the norm term and the count left on the device (``scal_dev``): no host read"""
+        return self.api.prox_residual(w, lam, p, q, tk, gama, want=want, scal_dev=scal_dev)
+
     def prox_trials(self, w, lamT, p, q, tk, gama):
         return self.api.prox_trials(w, lamT, p, q, tk, gama)
 
@@ -180,13 +184,23 @@ class ShardedStep:
         """Ax(prox(z)) (global, n+m), ||prox(z)||^2, nnz(s) and the local slab of s for z=(w-A'lam)/tk."""
         torch = self.torch
         want = ("Axprox", "s") if want_s else ("Axprox",)
+        n, m = self.n, self.m
+        if self.world > 1 and hasattr(self.ops, "prox_residual_dev"):
+            # the kernel leaves the norm term and the count in the tail of the message itself: no host read, no upload
+            buf = torch.zeros(n + m + 2, dtype=torch.float64, device=self.w_loc.device)
+            ev = self.ops.prox_residual_dev(self.w_loc, self._lam_loc(lam), self.p_loc, self.q, self.tk, self.gama, want, buf[n + m:])
+            ax = ev["Axprox"]
+            buf[:n] = ax[:n]
+            buf[n + self.r0: n + self.r1] = ax[n:]
+            self._all_reduce(buf)
+            tail = buf[n + m:].tolist()                          # the one device->host read of the evaluation
+            return buf[: n + m], float(tail[0]), int(round(tail[1])), ev.get("s")
         ev = self.ops.prox_residual(self.w_loc, self._lam_loc(lam), self.p_loc, self.q, self.tk, self.gama, want)
         ax = ev["Axprox"]
         if self.world == 1:
             return ax, float(ev["norm2"]), int(ev["count"]), ev.get("s")
         # ONE collective per residual: column partials (n), this rank's row sums in their place of a zero-padded
         # m-vector, and the two scalars, summed over the ranks
-        n, m = self.n, self.m
         buf = torch.zeros(n + m + 2, dtype=ax.dtype, device=ax.device)
         buf[:n] = ax[:n]
         buf[n + self.r0: n + self.r1] = ax[n:]
@@ -270,9 +284,10 @@ class ShardedStep:
         solve = self.ops.hybrid_amg if self.inner_solver == 4 else self.ops.hybrid_twogrid                # :161 / :178
         zeta, itamg, resamg, info = solve(prob_data, self.amg_options)                # (replicated)
         _lap("amg", t0); t0 = _time.perf_counter()
-        f0 = bk1 / 2 * float(lk @ lk) - float(wlk @ lk)                              # :182-184
+        d3 = torch.stack([lk @ lk, wlk @ lk, Fk_old @ zeta]).tolist()                # one host read for the three dots
+        f0 = bk1 / 2 * d3[0] - d3[1]                                                 # :182-184
         cFk_old = f0 + 0.5 * tk * n2_old
-        ress = abs(float(Fk_old @ zeta))
+        ress = abs(d3[2])
         # the slab pass costs 1/world of the full pass, so more trials are evaluated speculatively per
         # all_reduce / host round trip as the world grows.  gama = Inf: the screened kernels, whose candidate
         # count says how sparse the trial plans are -- 64, then 128 steps per read while under 10 % of the

@@ -220,6 +220,12 @@ SSN_API int ssn_prox_residual(ssn_ctx *ctx, const double *w_dev, const double *l
                       double *axp_out_dev, double *prox_out_dev, double *z_out_dev,
                       uint8_t *s_out_dev, double *norm2_out, int64_t *count_out);
 
+/* ssn_prox_residual without its host read: the norm term and nnz(s) are left in scal2_dev[0..1] (device), nothing is
+ * synchronised -- for a caller that sends them on (the row-sharded step puts them into the message of its all-reduce). */
+SSN_API int ssn_prox_residual_dev(ssn_ctx *ctx, const double *w_dev, const double *lam_dev, const double *p_dev,
+                      const double *q_dev, int64_t m, int64_t n, double tk, const double *gama_dev, double gama_scalar,
+                      double *axp_out_dev, double *prox_out_dev, double *z_out_dev, uint8_t *s_out_dev, double *scal2_dev);
+
 /* The same for partial OT (Class2/APD_SsN_Class2.m:124-130, 137-150, 196-217; u = [x (m*n); y (n); z (m)], lk of n+m+1
  * entries, H = [A I; phi' 0]), one read of w and one of phi:
  *   zk  = (1/tk) * (wk - [Aty(lk(1:n+m)) + lk(n+m+1)*phi ; lk(1:n+m)])     (rounded like the reference expression)
