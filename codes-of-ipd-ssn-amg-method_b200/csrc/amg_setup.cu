@@ -335,7 +335,9 @@ __global__ void __launch_bounds__(kMisT, 1) mis_rounds_kernel(
         int n, int N0, const int* __restrict__ ptr, const int* __restrict__ idx, const uint8_t* __restrict__ flags,
         const int* __restrict__ deg, const int* __restrict__ rank, const double* __restrict__ rnd, const int* __restrict__ rowcnt,
         double* __restrict__ degf, uint8_t* __restrict__ isS, uint8_t* __restrict__ kill, uint8_t* __restrict__ isC,
-        uint8_t* __restrict__ isF, int* __restrict__ counts) {
+        uint8_t* __restrict__ isF, int* __restrict__ counts, int thread_rows) {
+    // thread_rows: rows are short (a few entries): one THREAD per row in the two edge passes -- with a warp per row the 512
+    // warps of the cluster would walk 32 rows each, one dependent L2 round trip after the other
     const int gt = mis_rank() * kMisT + (int)threadIdx.x, nt = kMisCta * kMisT;
     const int lane = threadIdx.x & 31, gw = gt >> 5, nw = nt >> 5;
     for (int i = gt; i < n; i += nt) {                                   // mis_init_kernel
@@ -349,6 +351,20 @@ __global__ void __launch_bounds__(kMisT, 1) mis_rounds_kernel(
     while ((double)sumC < (double)n / 2.0 && sumU > N0 && round < kMisMaxRounds) {      // mis_set.m:42
         for (int i = gt; i < n; i += nt) { isS[i] = degf[i] > 0.0 ? 1 : 0; kill[i] = 0; }        // mis_mark_kernel
         mis_sync();
+        if (thread_rows) {
+            for (int row = gt; row < n; row += nt) {                     // mis_kill_kernel, one thread per row
+                if (!isS[row]) continue;
+                const double di = degf[row];
+                bool kill_me = false;
+                for (int e = ptr[row]; e < ptr[row + 1]; ++e) {
+                    const int j = idx[e];
+                    if (flags[e] && j > row && isS[j]) {
+                        if (di >= degf[j]) kill[j] = 1; else kill_me = true;
+                    }
+                }
+                if (kill_me) kill[row] = 1;
+            }
+        } else
         for (int row = gw; row < n; row += nw) {                         // mis_kill_kernel
             if (!isS[row]) continue;
             const double di = degf[row];
@@ -364,6 +380,13 @@ __global__ void __launch_bounds__(kMisT, 1) mis_rounds_kernel(
         mis_sync();
         for (int i = gt; i < n; i += nt) if (isS[i] && !kill[i]) isC[i] = 1;                       // mis_select_kernel
         mis_sync();
+        if (thread_rows) {
+            for (int row = gt; row < n; row += nt) {                     // mis_markf_kernel, one thread per row
+                bool hit = false;
+                for (int e = ptr[row]; e < ptr[row + 1]; ++e) hit |= (flags[e] && isC[idx[e]]);
+                if (hit) isF[row] = 1;
+            }
+        } else
         for (int row = gw; row < n; row += nw) {                         // mis_markf_kernel
             bool hit = false;
             for (int e = ptr[row] + lane; e < ptr[row + 1]; e += 32) hit |= (flags[e] && isC[idx[e]]);
@@ -411,9 +434,10 @@ static bool mis_rounds_cluster(ssn_ctx* c, const CsrView& A, int N0, const uint8
                                const int* rowcnt, double* degf, uint8_t* isS, uint8_t* kill, uint8_t* isC, uint8_t* isF) {
     Buf<int> counts(c, (size_t)2 * kMisMaxRounds);
     counts.zero();
+    const int thread_rows = (A.nrows > 0 && (double)A.nnz / A.nrows <= 16.0) ? 1 : 0;
 #ifdef SSN_EMU
     emu_launch_cluster(c, mis_rounds_kernel, kMisCta, kMisT, 0, A.nrows, N0, A.ptr, A.idx, flags, deg, rank, rnd, rowcnt, degf, isS, kill, isC, isF,
-                       counts.p);
+                       counts.p, thread_rows);
     return true;
 #else
     static int ok16 = -1;
@@ -431,7 +455,7 @@ static bool mis_rounds_cluster(ssn_ctx* c, const CsrView& A, int N0, const uint8
     }
     if (!ok16) return false;
     const int n = A.nrows;
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, mis_rounds_kernel, n, N0, A.ptr, A.idx, flags, deg, rank, rnd, rowcnt, degf, isS, kill, isC, isF, counts.p));
+    SSN_CUDA(cudaLaunchKernelEx(&cfg, mis_rounds_kernel, n, N0, A.ptr, A.idx, flags, deg, rank, rnd, rowcnt, degf, isS, kill, isC, isF, counts.p, thread_rows));
     c->launches++;
     return true;
 #endif

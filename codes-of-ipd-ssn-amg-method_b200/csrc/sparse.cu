@@ -554,6 +554,19 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
         }
         // sort the products by (column, order of formation): the keys are distinct, so any sorting network gives THE order --
         // a bitonic network over the next power of two (log^2 steps; the rank sort it replaces was T^2/32 steps per lane)
+        __syncwarp();                                       // the products of all lanes are in shared memory
+        if (T <= 64) {
+            // short rows (the common case): rank of each product among the row's products, two per lane held in registers
+            unsigned k0 = 0u, k1 = 0u; double v0 = 0.0, v1 = 0.0; int r0 = 0, r1 = 0;
+            const bool h0 = lane < T, h1 = lane + 32 < T;
+            if (h0) { k0 = s_key[w][lane]; v0 = s_val[w][lane]; }
+            if (h1) { k1 = s_key[w][lane + 32]; v1 = s_val[w][lane + 32]; }
+            for (int u = 0; u < T; ++u) { const unsigned ku = s_key[w][u]; r0 += (ku < k0) ? 1 : 0; r1 += (ku < k1) ? 1 : 0; }
+            __syncwarp();
+            if (h0) { s_key[w][r0] = k0; s_val[w][r0] = v0; }
+            if (h1) { s_key[w][r1] = k1; s_val[w][r1] = v1; }
+            __syncwarp();
+        } else {
         int Pw = 32;
         while (Pw < T) Pw <<= 1;
         for (int t = T + lane; t < Pw; t += 32) s_key[w][t] = 0xffffffffu;
@@ -573,6 +586,7 @@ __global__ void __launch_bounds__(128) spgemm_small_kernel(
                 }
                 __syncwarp();
             }
+        }
         }
         const int out0 = ubptr ? ubptr[(size_t)row * nwin] : row * kSmallT;
         int written = 0;

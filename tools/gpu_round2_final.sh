@@ -1,0 +1,10 @@
+# round 2, final check: full GPU suite, smoke, both bench configurations (with their CPU baselines), launch list of one step
+cd $GRAFT_REPO_ROOT
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_final_r2.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|rror|skipped" gpurun_out/pytest_gpu_final_r2.log | tail -6
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_final_r2.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_final_r2.log
+timeout 1200 python bench.py > gpurun_out/bench_final_r2.json 2> gpurun_out/bench_final_r2.err; echo "bench rc=$?"
+head -c 600 gpurun_out/bench_final_r2.json; echo; tail -2 gpurun_out/bench_final_r2.err
+timeout 900 python bench.py --config class2_64 > gpurun_out/bench_class2_final_r2.json 2> gpurun_out/bench_class2_final_r2.err; echo "bench class2 rc=$?"
+head -c 400 gpurun_out/bench_class2_final_r2.json; echo
+SSN_BENCH_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_r2.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-full-solve > gpurun_out/ncu_step_r2.log 2>&1; echo "ncu launch list rc=$?"
