@@ -14,35 +14,52 @@ namespace {
 // out[i] = in[0] + ... + in[i-1] for i < n (and out[n] = total when with_total): ONE block, one launch, no
 // temporary storage -- the AMG setup runs ~70 scans of a few thousand counts per hierarchy, where the two
 // kernels + temporary allocation of cub::DeviceScan cost more than the scan itself.  In-place safe.
-// Used up to ssn_ctx::small_scan_max counts (16384; env SSN_SMALL_SCAN_MAX): every thread walks its own
-// contiguous chunk, so beyond that the single block loses to cub (launch list of round 1: 3-4 us up to 8k
-// counts, 10 us at 16k, 18 us at 32k, 59 us at 130k+).
+// Used up to ssn_ctx::small_scan_max counts (16384; env SSN_SMALL_SCAN_MAX); beyond that cub::DeviceScan.  (Round 1's form,
+// every thread walking its own contiguous chunk of global memory, took 8 us at 16k counts: uncoalesced.)
 // pub_host != null: the total also goes to mapped pinned host memory, followed by the sequence word the host polls
 // (scan_counts_to_ptr: the read of the total rides in the scan instead of a publish kernel of its own).
 __global__ void __launch_bounds__(1024) small_scan_kernel(const int* in, int* out, int n, int with_total, int* pub_host,
                                                           volatile unsigned long long* flag_host, unsigned long long seq) {
+    // tiles of 4096 counts: coalesced load into shared memory, 4 consecutive counts per thread, warp + block scan, coalesced
+    // store; the running total is carried from tile to tile (a tile's outputs overwrite only that tile's inputs: in-place safe)
+    constexpr int kTile = 4096;
+    __shared__ int tile[kTile];
     __shared__ int wsum[32];
+    __shared__ int tile_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (n + 1023) / 1024;
-    const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
-    int s = 0;
-    for (int i = i0; i < i1; ++i) s += in[i];
-    int incl = s;
+    int carry = 0;
+    for (int base = 0; base < n; base += kTile) {
+        const int cnt = min(kTile, n - base);
+        for (int i = threadIdx.x; i < kTile; i += 1024) tile[i] = (i < cnt) ? in[base + i] : 0;
+        __syncthreads();
+        const int i0 = 4 * (int)threadIdx.x;
+        const int v0 = tile[i0], v1 = tile[i0 + 1], v2 = tile[i0 + 2], v3 = tile[i0 + 3];
+        const int s = v0 + v1 + v2 + v3;
+        int incl = s;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = wsum[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int wi = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
-        wsum[lane] = wi - w;                                 // exclusive prefix of the warp sums
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+            wsum[lane] = wi - w;                             // exclusive prefix of the warp sums
+            if (lane == 31) tile_total = wi;
+        }
+        __syncthreads();
+        int run = carry + wsum[warp] + incl - s;
+        tile[i0] = run; run += v0; tile[i0 + 1] = run; run += v1; tile[i0 + 2] = run; run += v2; tile[i0 + 3] = run;
+        carry += tile_total;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += 1024) out[base + i] = tile[i];
+        __syncthreads();
     }
-    __syncthreads();
-    int run = wsum[warp] + incl - s;
-    for (int i = i0; i < i1; ++i) { const int v = in[i]; out[i] = run; run += v; }
-    if (with_total && threadIdx.x == 1023) out[n] = run;
-    if (pub_host != nullptr && threadIdx.x == 1023) { pub_host[0] = run; __threadfence_system(); *flag_host = seq; }
+    if (threadIdx.x == 0) {
+        if (with_total) out[n] = carry;
+        if (pub_host != nullptr) { pub_host[0] = carry; __threadfence_system(); *flag_host = seq; }
+    }
 }
 }  // namespace
 
