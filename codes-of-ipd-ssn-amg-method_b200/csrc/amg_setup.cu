@@ -804,6 +804,16 @@ void amg_setup(ssn_ctx* c, const CsrView& A, const AmgOptions& o, int max_levels
     if (o.bigph) SSN_REQUIRE(o.fnode > 0, SSN_E_BIGPH_FNODE, "amg_options.bigph = 1 requires Nf > 0");
     amg_clear(c);
     Phase ph_setup(c, "amg_setup total");
+    // per-site memory of the sparse products (sparse.cu: spgemm): forgotten every 16 hierarchies, so a site whose rows
+    // became short again (or a different problem on the same context) is re-learnt at the price of one failed attempt
+    struct SiteScope {
+        ssn_ctx* c;
+        explicit SiteScope(ssn_ctx* cc) : c(cc) {
+            if ((c->spgemm_epoch++ & 15) == 0) std::memset(c->spgemm_big, 0, sizeof(c->spgemm_big));
+            c->spgemm_site = 0;
+        }
+        ~SiteScope() { c->spgemm_site = -1; }
+    } site_scope(c);
     std::unique_ptr<Hierarchy> H(new Hierarchy());
     H->smoth = o.smoth;
     H->lv.emplace_back();

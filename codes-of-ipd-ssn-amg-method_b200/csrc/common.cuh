@@ -75,6 +75,10 @@ struct ssn_ctx {
     bool fused_setup = false;             // SSN_FUSED_SETUP=1: the small levels of the hierarchy are coarsened by ONE kernel (one CTA; same
                                           // hierarchy bit for bit, but slower than kernel by kernel on a B200: opt-in)
     bool cluster_solve = true;            // SSN_CLUSTER_SOLVE=0: the persistent solve always runs grid-wide (cooperative launch)
+    static constexpr int kSpgemmSites = 64;
+    unsigned spgemm_epoch = 0;
+    int spgemm_site = -1;                 // >= 0 inside amg_setup: index of the next sparse product of this hierarchy
+    unsigned char spgemm_big[kSpgemmSites] = {0};   // 1: the optimistic warp-path attempt of that product failed last time
     bool stage_dense = true;              // SSN_STAGE_DENSE=0: the grid-wide solve kernel gathers from L2 on dense levels too
     bool mis_cluster = true;              // SSN_MIS_CLUSTER=0: the MIS rounds of mis_set.m launch by launch (one host read per round)
     bool dsm_solve = true;                // SSN_DSM_SOLVE=0: the cluster solve keeps its vectors in global memory (first cluster kernel)

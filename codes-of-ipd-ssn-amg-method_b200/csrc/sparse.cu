@@ -826,7 +826,14 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     // kSmallT-entry segment, no upper-bound pass and a single host round trip; rows that do not
     // qualify are counted and, if there are any, the general path below redoes the product.
     const double avg_products = ((double)A.nnz / (double)nrows) * ((double)B.nnz / (double)(B.nrows > 0 ? B.nrows : 1));
-    if (ncolsB < (1 << 23) && (int64_t)nrows * kSmallT <= ((int64_t)1 << 24) && avg_products <= 192.0) {
+    // Whether a row exceeds the warp path is only known afterwards; consecutive hierarchies of a solve repeat the same
+    // products with nearly the same matrices, so the outcome of the optimistic attempt is remembered per call site
+    // (ssn_ctx::spgemm_site: the n-th product since amg_setup started) and a site that failed last time goes straight to
+    // the general path -- the attempt it skips costs a kernel over every row plus a host read.  Either path gives the
+    // same product bit for bit.
+    const int site = (c->spgemm_site >= 0 && c->spgemm_site < ssn_ctx::kSpgemmSites) ? c->spgemm_site++ : -1;
+    const bool predicted_big = site >= 0 && c->spgemm_big[site] != 0;
+    if (!predicted_big && ncolsB < (1 << 23) && (int64_t)nrows * kSmallT <= ((int64_t)1 << 24) && avg_products <= 192.0) {
         Buf<int> cnt(c, nrows), cptr(c, (size_t)nrows + 1), nbig(c, 1);
         Buf<int> tidx(c, (size_t)nrows * kSmallT); Buf<double> tval(c, (size_t)nrows * kSmallT);
         cnt.zero(); nbig.zero();
@@ -837,6 +844,7 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
         int h2[2];
         read_ints(c, {cptr.p + nrows, nbig.p}, h2);                       // the product's size and the fallback flag: one synchronisation
         const int64_t nnz = h2[0];
+        if (site >= 0) c->spgemm_big[site] = (h2[1] != 0) ? 1 : 0;
         if (h2[1] == 0) {
             C.nnz = nnz;
             C.idx.alloc(c, C.nnz); C.val.alloc(c, C.nnz);

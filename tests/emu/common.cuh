@@ -213,6 +213,10 @@ struct ssn_ctx {
     int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
     int small_scan_max = 1 << 14;
     bool device_setup = true;
+    static constexpr int kSpgemmSites = 64;
+    unsigned spgemm_epoch = 0;
+    int spgemm_site = -1;                 // >= 0 inside amg_setup: index of the next sparse product of this hierarchy
+    unsigned char spgemm_big[kSpgemmSites] = {0};   // 1: the optimistic warp-path attempt of that product failed last time
     bool stage_dense = true;              // SSN_STAGE_DENSE=0: the grid-wide solve kernel gathers from L2 on dense levels too
     bool mis_cluster = true;              // SSN_MIS_CLUSTER=0: the MIS rounds of mis_set.m launch by launch (one host read per round)
     bool fused_setup = true, cluster_solve = true;     // the emulated hierarchies go through the fused kernel (opt-in in the library)
