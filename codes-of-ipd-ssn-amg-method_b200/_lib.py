@@ -121,6 +121,16 @@ SIGNATURES = {
                                   C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _vp, _i64]),
     "ssn_apd_ssn_class1_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _dbl, C.POINTER(ApdOptions), _vp, _vp,
                                        C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _vp, _i64]),
+    "ssn_warmup_class2": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
+    "ssn_apd_begin_pot": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
+    "ssn_apd_end_pot": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp, _vp]),
+    "ssn_apd_ssn_class2": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, C.POINTER(ApdOptions), _vp, _vp,
+                                  C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _i64]),
+    "ssn_apd_ssn_class2_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, C.POINTER(ApdOptions), _vp, _vp,
+                                       C.POINTER(ApdResult), _vp, _vp, _vp, _vp, _i64]),
+    "ssn_ssn_step_class2": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "ssn_ssn_step_class2_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "ssn_amg4pot_str": (_int, [_vp, C.POINTER(ProbData), C.POINTER(AmgOptions), _int, _vp, _pint, _pdbl, _pint]),
     "ssn_asat": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_asat_host": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _pcsr]),
     "ssn_active_coo": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_vp), _pi64]),

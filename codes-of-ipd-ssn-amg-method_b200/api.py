@@ -694,14 +694,14 @@ def _prob_data(prob_data, ctx, keep, pot=False):
     return pd, m, n
 
 
-def _solve(entry, prob_data, options, conv, pot=False):
+def _solve(entry, prob_data, options, conv, pot=False, extra=()):
     torch = _torch(); ctx = context(); keep = []
     host = _is_host(prob_data["z"])
     pd, m, n = _prob_data(prob_data, ctx, keep, pot)
     o = conv(options, keep)
     zeta = torch.empty(n + m + (1 if pot else 0), dtype=torch.float64, device="cuda")
     it = C.c_int(0); res = C.c_double(0.0); info = (C.c_int * 2)()
-    ctx.call(entry, C.byref(pd), _byref_or_null(o), _ptr(zeta), C.byref(it), C.byref(res), info)
+    ctx.call(entry, C.byref(pd), _byref_or_null(o), *extra, _ptr(zeta), C.byref(it), C.byref(res), info)
     return _ret(zeta, host), it.value, res.value, np.array([info[0], info[1]])
 
 
@@ -747,16 +747,131 @@ def ssn_step_class1(wk, lk, wlk, p, q, bk1, tk, gama=np.inf, inner_solver=4, amg
                             "ls_passes": int(v[7]), "Fk_old_norm": v[8], "Fk_new_norm": v[9], "ms_plan": v[10], "ms_amg": v[11], "ms_asat": None}
 
 
+def warmup_class2(c, r, l, p, q, mu, phi, res=None, maxit=None):
+    """``[uk,lk] = warmup_class2(c,r,l,p,q,mu,phi,res,maxit)`` -- reference Class2/warmup_class2.m:2-108 (A-ADMM warm start
+    of partial OT), device resident (``ssn_warmup_class2``: two fused plan-wide kernels per iteration).  ``nargin`` rules of
+    :3-18 as ``warmup_class1``; the residual test itself is commented out in the reference, so ``maxit`` iterations run."""
+    torch = _torch(); ctx = context(); host = _is_host(c, r, l, p, q)
+    if res is None:
+        res = 1e-1
+    if maxit is None:
+        maxit = np.inf
+    elif res == 0 and maxit == np.inf:
+        raise ValueError("res = 0 and maxit = inf")
+    if maxit == np.inf:
+        maxit = 500
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+    cd = _dev(c, count=m * n); phid = _dev(phi, count=m * n)
+    b = torch.cat([_dev(r), _dev(l), torch.tensor([float(mu)], dtype=torch.float64, device="cuda")])
+    uk = torch.empty(m * n + n + m, dtype=torch.float64, device="cuda"); lk = torch.empty(n + m + 1, dtype=torch.float64, device="cuda")
+    ctx.call("ssn_warmup_class2", _ptr(cd), _ptr(b), _ptr(pd), _ptr(qd), m, n, _ptr(phid), int(maxit), _ptr(uk), _ptr(lk))
+    return _ret(uk, host), _ret(lk, host)
+
+
+def apd_begin_pot(c, uk, vk, p, q, phi, b, lk, ak, bk, bk1):
+    """``wk, huk, wlk`` of Class2/APD_SsN_Class2.m:121-122 in one pass over the x block."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel(); L = m * n + n + m
+    cd, phid = _dev(c, count=m * n), _dev(phi, count=m * n)
+    ud, vd, bd, ld = _dev(uk, count=L), _dev(vk, count=L), _dev(b, count=n + m + 1), _dev(lk, count=n + m + 1)
+    wk = torch.empty(L, dtype=torch.float64, device="cuda"); huk = torch.empty(n + m + 1, dtype=torch.float64, device="cuda")
+    wlk = torch.empty_like(huk)
+    ctx.call("ssn_apd_begin_pot", _ptr(cd), _ptr(ud), _ptr(vd), _ptr(pd), _ptr(qd), m, n, _ptr(phid), _ptr(bd), _ptr(ld), float(ak), float(bk),
+             float(bk1), _ptr(wk), _ptr(huk), _ptr(wlk))
+    return wk, huk, wlk
+
+
+def apd_end_pot(c, wk, uk, lk, p, q, phi, b, tk, ak):
+    """``uk1, vk1, huk1`` and ``{c'xk1, KKT_xk^2, KKT_yk^2, KKT_zk^2, KKT_lk^2}`` of Class2/APD_SsN_Class2.m:231-238 in one pass."""
+    torch = _torch(); ctx = context()
+    pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel(); L = m * n + n + m
+    cd, phid = _dev(c, count=m * n), _dev(phi, count=m * n)
+    wd, ud, bd, ld = _dev(wk, count=L), _dev(uk, count=L), _dev(b, count=n + m + 1), _dev(lk, count=n + m + 1)
+    uk1 = torch.empty(L, dtype=torch.float64, device="cuda"); vk1 = torch.empty_like(uk1)
+    huk1 = torch.empty(n + m + 1, dtype=torch.float64, device="cuda")
+    scal = (C.c_double * 5)()
+    ctx.call("ssn_apd_end_pot", _ptr(cd), _ptr(wd), _ptr(ud), _ptr(ld), _ptr(pd), _ptr(qd), m, n, _ptr(phid), _ptr(bd), float(tk), float(ak),
+             _ptr(uk1), _ptr(vk1), _ptr(huk1), C.cast(scal, C.c_void_p))
+    return uk1, vk1, huk1, list(scal)
+
+
+def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100, max_outer=None,
+                   max_seconds=None, verbose=False, amg_options=None, pcg_options=None, host_call=False):
+    """The reference's Class 2 script (Class2/APD_SsN_Class2.m:25-285 + Class2/warmup_class2.m) as ONE call into the library
+    (``ssn_apd_ssn_class2``; ``host_call=True``: ``ssn_apd_ssn_class2_host`` on NumPy arrays).  Returns the dictionary of
+    ``driver.APD_SsN_Class2``: ``KKT`` is the list of ``(KKT_xk, KKT_yk, KKT_zk, KKT_lk)`` per outer iteration."""
+    from ._lib import ApdOptions, ApdResult
+    torch = _torch(); ctx = context()
+    keep = []
+    ao = _amg_options(amg_options, keep); po = _pcg_options(pcg_options, keep)
+    o = ApdOptions(inner_solver=int(inner_solver), maxit=int(maxit), KKT_Tol=float(KKT_Tol), warm_maxit=int(warm_maxit),
+                   max_outer=int(max_outer or 0), max_seconds=float(max_seconds or 0.0), verbose=1 if verbose else 0,
+                   amg=C.pointer(ao) if ao is not None else None, pcg=C.pointer(po) if po is not None else None)
+    res = ApdResult()
+    fx = np.zeros(int(maxit) + 1); kk = np.zeros((int(maxit) + 1, 4)); its = np.zeros(int(maxit), dtype=np.int32)
+    cap = 64 * int(maxit)
+    steps = np.zeros((cap, 7))
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)
+    if host_call:
+        f = lambda a: np.ascontiguousarray(np.asarray(a.cpu() if hasattr(a, "cpu") else a, dtype=np.float64).reshape(-1))
+        ch, rh, lh, ph, qh, phih = f(c), f(r), f(l), f(p), f(q), f(phi); m, n = ph.size, qh.size
+        uk = np.empty(m * n + n + m); lk = np.empty(m + n + 1)
+        ctx.call("ssn_apd_ssn_class2_host", hp(ch), hp(rh), hp(lh), hp(ph), hp(qh), m, n, float(mu), hp(phih), C.byref(o), hp(uk), hp(lk),
+                 C.byref(res), hp(fx), hp(kk), hp(its), hp(steps), cap)
+    else:
+        pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+        cd = _dev(c, count=m * n); rd = _dev(r, count=n); ld = _dev(l, count=m); phid = _dev(phi, count=m * n)
+        uk = torch.empty(m * n + n + m, dtype=torch.float64, device="cuda"); lk = torch.empty(n + m + 1, dtype=torch.float64, device="cuda")
+        ctx.call("ssn_apd_ssn_class2", _ptr(cd), _ptr(rd), _ptr(ld), _ptr(pd), _ptr(qd), m, n, float(mu), _ptr(phid), C.byref(o), _ptr(uk),
+                 _ptr(lk), C.byref(res), hp(fx), hp(kk), hp(its), hp(steps), cap)
+    L = res.hist_len; ns = min(int(res.steps_len), cap)
+    stats = {"ssn_its": its[:res.outer_its].tolist(), "ls_trials": res.ls_trials, "converged": bool(res.converged),
+             "amg_calls": res.amg_calls, "warmup_s": res.warmup_s, "solve_s": res.solve_s, "asat_s": res.asat_s, "plan_s": res.plan_s,
+             "steps": [(int(a), int(b_), int(e), int(i0), int(it), int(ll), nf) for a, b_, e, i0, it, ll, nf in steps[:ns].tolist()]}
+    return {"uk": uk, "xk": uk[:m * n], "lk": lk, "fxk": fx[:L].tolist(), "KKT": [tuple(row) for row in kk[:L].tolist()],
+            "outer_its": res.outer_its, "rel_kkt": res.rel_kkt, "stats": stats, "seconds": res.loop_s, "warmup_seconds": res.warmup_s}
+
+
+def ssn_step_class2(wk, lk, wlk, p, q, bk1, tk, phi, inner_solver=4, amg_options=None, pcg_options=None, host_call=False):
+    """One semismooth-Newton step of Class2/APD_SsN_Class2.m:137-217 at a fixed APD state as ONE library call
+    (``ssn_ssn_step_class2``; ``host_call``: ``ssn_ssn_step_class2_host`` on host arrays, copies inside the call).
+    Returns ``(lk_new, Fk_new, info)``."""
+    torch = _torch(); ctx = context()
+    keep = []
+    o = _amg_options(amg_options, keep); po = _pcg_options(pcg_options, keep)
+    info = (C.c_double * 12)()
+    if host_call:
+        arr = lambda v: v if (isinstance(v, torch.Tensor) and not v.is_cuda and v.dtype == torch.float64 and v.is_contiguous()) else \
+            torch.from_numpy(np.ascontiguousarray(np.asarray(v.cpu() if hasattr(v, "cpu") else v, dtype=np.float64)))
+        wh, lh, wlh, ph, qh, phih = (arr(v) for v in (wk, lk, wlk, p, q, phi))
+        m, n = ph.numel(), qh.numel()
+        lk_new = torch.empty(n + m + 1, dtype=torch.float64).pin_memory(); Fk_new = torch.empty(n + m + 1, dtype=torch.float64).pin_memory()
+        ctx.call("ssn_ssn_step_class2_host", wh.data_ptr(), lh.data_ptr(), wlh.data_ptr(), ph.data_ptr(), qh.data_ptr(), m, n, float(bk1),
+                 float(tk), phih.data_ptr(), int(inner_solver), _byref_or_null(o), _byref_or_null(po), lk_new.data_ptr(), Fk_new.data_ptr(),
+                 C.cast(info, C.c_void_p))
+    else:
+        pd, qd = _dev(p), _dev(q); m, n = pd.numel(), qd.numel()
+        wd, ld, wld = _dev(wk, count=m * n + n + m), _dev(lk, count=n + m + 1), _dev(wlk, count=n + m + 1)
+        phid = _dev(phi, count=m * n)
+        lk_new = torch.empty(n + m + 1, dtype=torch.float64, device="cuda"); Fk_new = torch.empty_like(lk_new)
+        ctx.call("ssn_ssn_step_class2", _ptr(wd), _ptr(ld), _ptr(wld), _ptr(pd), _ptr(qd), m, n, float(bk1), float(tk), _ptr(phid),
+                 int(inner_solver), _byref_or_null(o), _byref_or_null(po), _ptr(lk_new), _ptr(Fk_new), C.cast(info, C.c_void_p))
+    v = list(info)
+    return lk_new, Fk_new, {"E": int(v[0]), "nnzH": int(v[1]), "info": [int(v[2]), int(v[3])], "itamg": int(v[4]), "resamg": v[5], "ll": int(v[6]),
+                            "ls_passes": int(v[7]), "Fk_old_norm": v[8], "Fk_new_norm": v[9], "ms_plan": v[10], "ms_amg": v[11], "ms_asat": None}
+
+
 def aug_PCG(prob_data, pcg_options):
     """``[zeta,itpcg,respcg,info] = aug_PCG(prob_data,pcg_options)`` -- aug_PCG.m:1-38."""
     return _solve("ssn_aug_pcg", prob_data, pcg_options, _pcg_options)
 
 
 def AMG4POT(prob_data, amg_options, str_="amg"):
-    """``[zeta,it,res,info] = AMG4POT(prob_data,amg_options,str)`` -- Class2/AMG4POT.m:1-56."""
-    if str_ != "amg":
-        raise SsnError(-10, "Hybrid_twogrid (inner_solver 5) is out of scope (SURVEY.md 8f)")
-    return _solve("ssn_amg4pot", prob_data, amg_options, _amg_options, pot=True)
+    """``[zeta,it,res,info] = AMG4POT(prob_data,amg_options,str)`` -- Class2/AMG4POT.m:1-56 (``str = 'amg'``: the two
+    solves through Hybrid_AMG; anything else, e.g. ``'twogrid'``: through Hybrid_twogrid, :45-51)."""
+    if str_ == "amg":
+        return _solve("ssn_amg4pot", prob_data, amg_options, _amg_options, pot=True)
+    return _solve("ssn_amg4pot_str", prob_data, amg_options, _amg_options, pot=True, extra=(1,))
 
 
 def PCG4POT(prob_data, pcg_options):

@@ -403,6 +403,82 @@ int ssn_ssn_step_class1_host(ssn_ctx* c, const double* wk, const double* lk, con
     });
 }
 
+// ---- Class 2 (partial OT): the script, its warm start and one SsN step as single calls
+int ssn_warmup_class2(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n,
+                      const double* phi, int maxit, double* uk_out, double* lk_out) {
+    return guarded(c, [&] { plan_warmup_class2(c, cost, b, p, q, m, n, phi, maxit, uk_out, lk_out); sync(c); });
+}
+int ssn_apd_begin_pot(ssn_ctx* c, const double* cost, const double* uk, const double* vk, const double* p, const double* q, int64_t m,
+                      int64_t n, const double* phi, const double* b, const double* lk, double ak, double bk, double bk1, double* wk_out,
+                      double* huk_out, double* wlk_out) {
+    return guarded(c, [&] { plan_apd_begin_pot(c, cost, uk, vk, p, q, m, n, phi, b, lk, ak, bk, bk1, wk_out, huk_out, wlk_out); sync(c); });
+}
+int ssn_apd_end_pot(ssn_ctx* c, const double* cost, const double* wk, const double* uk, const double* lk, const double* p, const double* q,
+                    int64_t m, int64_t n, const double* phi, const double* b, double tk, double ak, double* uk1, double* vk1,
+                    double* huk1_out, double* scal5_host) {
+    return guarded(c, [&] {
+        Buf<double> scal(c, 5);
+        plan_apd_end_pot(c, cost, wk, uk, lk, p, q, m, n, phi, b, tk, ak, uk1, vk1, huk1_out, scal);
+        double h[5]; read_back(c, scal.p, h, 5);
+        if (scal5_host) for (int i = 0; i < 5; ++i) scal5_host[i] = h[i];
+    });
+}
+int ssn_apd_ssn_class2(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
+                       int64_t n, double mu, const double* phi, const ssn_apd_options* op, double* uk_out, double* lk_out,
+                       ssn_apd_result* res, double* fxk_hist, double* kkt4_hist, int32_t* ssn_its_hist, double* steps_host,
+                       int64_t steps_cap) {
+    return guarded(c, [&] {
+        apd_ssn_class2(c, cost, r, l, p, q, m, n, mu, phi, op, uk_out, lk_out, res, fxk_hist, kkt4_hist, ssn_its_hist, steps_host, steps_cap);
+    });
+}
+int ssn_apd_ssn_class2_host(ssn_ctx* c, const double* cost, const double* r, const double* l, const double* p, const double* q, int64_t m,
+                            int64_t n, double mu, const double* phi, const ssn_apd_options* op, double* uk_out, double* lk_out,
+                            ssn_apd_result* res, double* fxk_hist, double* kkt4_hist, int32_t* ssn_its_hist, double* steps_host,
+                            int64_t steps_cap) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(cost && r && l && p && q && phi && uk_out && lk_out && m > 0 && n > 0, SSN_E_INVALID, "apd_ssn_class2: bad arguments");
+        const size_t mn = (size_t)m * n, N = (size_t)(m + n);
+        Buf<double> dc(c, mn), dphi(c, mn), dr(c, n), dl(c, m), dp(c, m), dq(c, n), du(c, mn + N), dlk(c, N + 1);
+        SSN_CUDA(cudaMemcpyAsync(dc.p, cost, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dphi.p, phi, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dr.p, r, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dl.p, l, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        apd_ssn_class2(c, dc, dr, dl, dp, dq, m, n, mu, dphi, op, du, dlk, res, fxk_hist, kkt4_hist, ssn_its_hist, steps_host, steps_cap);
+        SSN_CUDA(cudaMemcpyAsync(uk_out, du.p, sizeof(double) * (mn + N), cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(lk_out, dlk.p, sizeof(double) * (N + 1), cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+int ssn_ssn_step_class2(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                        int64_t n, double bk1, double tk, const double* phi, int inner_solver, const ssn_amg_options* amg,
+                        const ssn_pcg_options* pcg, double* lk_new, double* Fk_new, double* info12) {
+    return guarded(c, [&] { ssn_step_class2(c, wk, lk, wlk, p, q, m, n, bk1, tk, phi, inner_solver, amg, pcg, lk_new, Fk_new, info12); sync(c); });
+}
+int ssn_ssn_step_class2_host(ssn_ctx* c, const double* wk, const double* lk, const double* wlk, const double* p, const double* q, int64_t m,
+                             int64_t n, double bk1, double tk, const double* phi, int inner_solver, const ssn_amg_options* amg,
+                             const ssn_pcg_options* pcg, double* lk_new, double* Fk_new, double* info12) {
+    return guarded(c, [&] {
+        SSN_REQUIRE(wk && lk && wlk && p && q && phi && lk_new && Fk_new && m > 0 && n > 0, SSN_E_INVALID, "ssn_step_class2: bad arguments");
+        const size_t mn = (size_t)m * n, N = (size_t)(m + n);
+        Buf<double> dw(c, mn + N), dphi(c, mn), dlk(c, N + 1), dwl(c, N + 1), dp(c, m), dq(c, n), dln(c, N + 1), dF(c, N + 1);
+        SSN_CUDA(cudaMemcpyAsync(dw.p, wk, sizeof(double) * (mn + N), cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dphi.p, phi, sizeof(double) * mn, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dlk.p, lk, sizeof(double) * (N + 1), cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dwl.p, wlk, sizeof(double) * (N + 1), cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dp.p, p, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(dq.p, q, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        ssn_step_class2(c, dw, dlk, dwl, dp, dq, m, n, bk1, tk, dphi, inner_solver, amg, pcg, dln, dF, info12);
+        SSN_CUDA(cudaMemcpyAsync(lk_new, dln.p, sizeof(double) * (N + 1), cudaMemcpyDeviceToHost, c->stream));
+        SSN_CUDA(cudaMemcpyAsync(Fk_new, dF.p, sizeof(double) * (N + 1), cudaMemcpyDeviceToHost, c->stream));
+        sync(c);
+    });
+}
+int ssn_amg4pot_str(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, int twogrid, double* zeta, int* it, double* res, int* info) {
+    return guarded(c, [&] { amg4pot(c, pd, opts, zeta, it, res, info, twogrid != 0); });
+}
+
 int ssn_asat(ssn_ctx* c, const uint8_t* s, const double* p, const double* q, int64_t m, int64_t n, ssn_csr* H) {
     return guarded(c, [&] { SSN_REQUIRE(H, SSN_E_INVALID, "ASAt: null output"); Csr h = asat(c, s, p, q, m, n); sync(c); h.release_to(H); });
 }

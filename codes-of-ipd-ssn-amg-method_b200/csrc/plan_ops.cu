@@ -12,6 +12,7 @@
 //   rowpart[chunk][m] / colpart[group][n]; a tiny finish kernel sums them in fixed order.
 #include "common.cuh"
 #include "plan_ops.cuh"
+#include "sparse.cuh"
 
 namespace ssn {
 
@@ -779,6 +780,8 @@ struct WarmArgs {
     int64_t m, n; int cols_per_chunk, num_chunks, num_groups;
     double* rowpart; double* colpart;                       // A: Ax(dd)   B: Ax(vk1)
     double* rowpart2; double* colpart2;                     //             B: Ax(xk1)
+    // PHI (Class 2, warmup_class2.m): H = [A I; phi' 0]; b, lk1, axk (= H*uk) and y (= invHHt(H*dd)) have n+m+1 entries
+    const double* phi; double* phipart;                     // A: [blocks] phi'*dd_x   B: [blocks][2] phi'*vk1_x, phi'*uk1_x
 };
 
 template <bool VEC>
@@ -807,9 +810,10 @@ __device__ __forceinline__ void st4(double* base, const bool (&rok)[4], bool ful
     }
 }
 
-template <int STAGE, bool VEC, int GM>
+template <int STAGE, bool VEC, int GM, bool PHI = false>
 __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
     extern __shared__ double colbuf[];                 // [2][kWarps][cols_per_chunk]
+    __shared__ double red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x, group = blockIdx.y;
     const int64_t m = a.m, n = a.n;
@@ -834,11 +838,18 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
     double* colbuf2 = colbuf + (size_t)kWarps * cpc;
     const double ak = a.ak, bk = a.bk, ak2 = a.ak * a.ak;
+    // PHI: the last entries of b, of h1 = lk1 - (H*uk - b)/bk (stage A) and of y (stage B) multiply phi
+    double bl = 0.0, hl = 0.0, ps = 0.0, ps2 = 0.0;
+    if (PHI) {
+        bl = a.b[n + m];
+        hl = (STAGE == 0) ? (a.lk1[n + m] - (1.0 / a.bk) * (a.axk[n + m] - bl)) : a.y[n + m];
+    }
     for (int64_t c = c0; c < c1; ++c, off += (size_t)m) {
         const double qj = __ldg(a.q + c);
-        double xk[4], wk[4], pik[4], lk2[4];
+        double xk[4], wk[4], pik[4], lk2[4], ph[4] = {0.0, 0.0, 0.0, 0.0};
         ld4<VEC>(a.xk + off, rok, full, xk); ld4<VEC>(a.wk + off, rok, full, wk);
         ld4<VEC>(a.pik + off, rok, full, pik); ld4<VEC>(a.lk2 + off, rok, full, lk2);
+        if (PHI) ld4<VEC>(a.phi + off, rok, full, ph);
         double cs = 0.0, cs2 = 0.0;
         if (STAGE == 0) {
             double vk[4], cc[4], dd[4];
@@ -847,8 +858,9 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
             const double ucj = __ldg(a.lk1 + c) - (1.0 / bk) * (__ldg(a.axk + c) - b1j);      // h1, column part
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double atb = pv[k] * b1j + b2[k] * qj;                                  // Aty(b)
-                const double ath = pv[k] * ucj + ur[k] * qj;                                  // Aty(h1)
+                double atb = pv[k] * b1j + b2[k] * qj;                                        // Aty(b)
+                double ath = pv[k] * ucj + ur[k] * qj;                                        // Aty(h1)
+                if (PHI) { atb += bl * ph[k]; ath += hl * ph[k]; }                            // + b(end)*phi, + hlk(m+n+1)*phi  warmup_class2.m:22,68
                 const double wxk = (ak * a.gk * vk[k] + (a.gk + a.muf * ak) * xk[k]) / a.etafk;   // :61
                 const double h2 = lk2[k] - (1.0 / bk) * (xk[k] - wk[k]) + (ak / bk) * (-(pik[k] - wk[k]));   // :63
                 const double cAw = -atb - wk[k];                                              // :64
@@ -856,6 +868,7 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
                 const double d = a.etafk * wxk - ak2 * (cc[k] + cAlk + a.sgk * cAw);          // :65
                 dd[k] = (full || rok[k]) ? d : 0.0;
                 cs = fma(dd[k], pv[k], cs); rs[k] = fma(dd[k], qj, rs[k]);
+                if (PHI) ps = fma(ph[k], dd[k], ps);                                          // phi'*dd, warmup_class2.m:72
             }
             st4<VEC>(a.dd + off, rok, full, dd);
         } else {
@@ -866,7 +879,8 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
             const double ycj = __ldg(a.y + c);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double aty = pv[k] * ycj + ur[k] * qj;                                  // Aty(invAAt(Ax(dd)))
+                double aty = pv[k] * ycj + ur[k] * qj;                                        // Aty(invAAt(Ax(dd)))
+                if (PHI) aty += hl * ph[k];                                                   // + ff(end)*phi, warmup_class2.m:74
                 const double x1 = (dd[k] - aty) / (a.etafk + a.tt);                           // :70
                 const double v1 = x1 + (x1 - xk[k]) / ak;                                     // :71
                 const double wwk = (ak * pik[k] + wk[k]) / (1.0 + ak);                        // :60
@@ -881,6 +895,7 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
                 xn[k] = live ? x1 : 0.0; vn[k] = live ? v1 : 0.0; wn[k] = w1; pn[k] = p1; ln[k] = l1;
                 cs = fma(vn[k], pv[k], cs); rs[k] = fma(vn[k], qj, rs[k]);
                 cs2 = fma(xn[k], pv[k], cs2); rs2[k] = fma(xn[k], qj, rs2[k]);
+                if (PHI) { ps = fma(ph[k], vn[k], ps); ps2 = fma(ph[k], xn[k], ps2); }        // phi'*vk1, phi'*uk1 (x block)
             }
             st4<VEC>(a.xk + off, rok, full, xn); st4<VEC>(a.vk + off, rok, full, vn); st4<VEC>(a.wk + off, rok, full, wn);
             st4<VEC>(a.pik + off, rok, full, pn); st4<VEC>(a.lk2 + off, rok, full, ln);
@@ -904,6 +919,15 @@ __global__ void __launch_bounds__(kThreads, 2) warm_kernel(const WarmArgs a) {
         a.colpart[(size_t)group * (size_t)n + c0 + j] = s;
         if (STAGE == 1) a.colpart2[(size_t)group * (size_t)n + c0 + j] = s2;
     }
+    if (PHI) {
+        const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const double t1 = block_sum(ps, red);
+        if (STAGE == 0) { if (threadIdx.x == 0) a.phipart[b] = t1; }
+        else {
+            const double t2 = block_sum(ps2, red);
+            if (threadIdx.x == 0) { a.phipart[2 * b] = t1; a.phipart[2 * b + 1] = t2; }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ fused APD outer-iteration updates
@@ -920,6 +944,8 @@ struct ApdArgs {
     double ak, bk, inv_tk;
     int64_t m, n; int cols_per_chunk, num_chunks, num_groups;
     double* rowpart; double* colpart; double* scalpart;
+    // PHI (Class 2, APD_SsN_Class2.m:121-122, 231-238): lam has n+m+1 entries, H'lam = Aty(lam(1:n+m)) + lam(n+m+1)*phi
+    const double* phi; double* phipart;                     // [blocks] phi'*xk (stage 0) / phi'*xk1 (stage 1)
 };
 
 template <int GM>
@@ -928,7 +954,7 @@ __device__ __forceinline__ double prox_of(double z, double gm) {
     return (z >= 0.0) ? ((z <= gm) ? z : gm) : fmin(0.0, gm);
 }
 
-template <int STAGE, bool VEC, int GM>
+template <int STAGE, bool VEC, int GM, bool PHI = false>
 __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
     extern __shared__ double colbuf[];                 // [kWarps][cols_per_chunk]
     __shared__ double red[32];
@@ -950,14 +976,16 @@ __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
         y2v[k] = (STAGE == 1 && rok[k]) ? a.lam[n + r] : 0.0;
     }
     double rs[4] = {0.0, 0.0, 0.0, 0.0};
-    double s_cx = 0.0, s_kx = 0.0;
+    double s_cx = 0.0, s_kx = 0.0, ps = 0.0;
     const bool full = (rbase + kStripRows <= m);
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
     const double ak = a.ak, ak2 = a.ak * a.ak;
+    const double mu = (PHI && STAGE == 1) ? a.lam[n + m] : 0.0;
     for (int64_t c = c0; c < c1; ++c, off += (size_t)m) {
         const double qj = __ldg(a.q + c);
-        double cc[4], xk[4];
+        double cc[4], xk[4], ph[4] = {0.0, 0.0, 0.0, 0.0};
         ld4<VEC>(a.c + off, rok, full, cc); ld4<VEC>(a.xk + off, rok, full, xk);
+        if (PHI) ld4<VEC>(a.phi + off, rok, full, ph);
         double cs = 0.0;
         if (STAGE == 0) {
             double vk[4], w[4];
@@ -967,6 +995,7 @@ __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
                 // rounded exactly like the reference expression (no FMA contraction): wk decides the active set
                 w[k] = __dadd_rn(-cc[k], __ddiv_rn(__dmul_rn(a.bk, __dadd_rn(xk[k], __dmul_rn(ak, vk[k]))), ak2));   // :125
                 cs = fma(xk[k], pv[k], cs); rs[k] = fma(xk[k], qj, rs[k]);                      // Ax(xk), :126
+                if (PHI) ps = fma(ph[k], xk[k], ps);                                            // phi'*xk, APD_SsN_Class2.m:122
             }
             st4<VEC>(a.wk_out + off, rok, full, w);
         } else {
@@ -977,7 +1006,8 @@ __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const double gm = (GM == G_VECTOR) ? g[k] : a.gama_s;
-                const double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                if (PHI) aty = __dadd_rn(aty, __dmul_rn(mu, ph[k]));                            // the fused residual's rounding (plan_batch, G_PHI)
                 const double z = __dmul_rn(a.inv_tk, __dsub_rn(w[k], aty));                    // zk, :139 arithmetic
                 const bool live = full || rok[k];
                 const double xn = live ? prox_of<GM>(z, gm) : 0.0;                              // xk1 = prox(zk), :239
@@ -988,6 +1018,7 @@ __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
                 s_kx = fma(dk, dk, s_kx);
                 s_cx = fma(cc[k], xn, s_cx);                                                    // c'*xk, :253
                 cs = fma(xn, pv[k], cs); rs[k] = fma(xn, qj, rs[k]);                            // Ax(xk1), :241
+                if (PHI) ps = fma(ph[k], xn, ps);                                               // phi'*xk1
             }
             st4<VEC>(a.xk1 + off, rok, full, x1); st4<VEC>(a.vk1 + off, rok, full, v1);
         }
@@ -1011,6 +1042,10 @@ __global__ void __launch_bounds__(kThreads, 2) apd_kernel(const ApdArgs a) {
             const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
             a.scalpart[2 * b] = t1; a.scalpart[2 * b + 1] = t2;
         }
+    }
+    if (PHI) {
+        const double t3 = block_sum(ps, red);
+        if (threadIdx.x == 0) a.phipart[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t3;
     }
 }
 
@@ -1048,6 +1083,157 @@ __global__ void plan_finish2_kernel(const double* __restrict__ rowpart, const do
         double s = 0.0, s2 = 0.0;
         for (int c = 0; c < num_chunks; ++c) { s += rowpart[(size_t)c * m + i]; if (y2) s2 += rowpart2[(size_t)c * m + i]; }
         y[gid] = s; if (y2) y2[gid] = s2;
+    }
+}
+
+
+// ------------------------------------------------------------------ Class 2 (partial OT): slack blocks and (n+m+1)-vectors
+// u = [x (m*n) ; y (n) ; z (m)], H = [A I ; phi' 0].  The plan-wide kernels above (PHI variants) handle the x block; the
+// slack blocks [y ; z] (N = n + m entries, where H' acts as the identity and wc = 0) and the last entries of the
+// (N+1)-vectors are one block of work each, run after the stage kernel and its finish kernel.
+struct PotWarmSlack {
+    double* us; double* vs; double* ws; double* pis; double* lkBs; double* dds;      // slack blocks of uk vk wk pik lk(N+2:end) dd
+    const double* b; double* lkA; double* huk;             // N+1 each: b = [r;l;mu], lk(1:N+1), H*uk
+    double* hdd;                                            // N+1: stage A, in: Ax(dd_x) (N entries) -> out: H*dd
+    const double* ff;                                       // N+1: stage B, invHHt(H*dd)
+    const double* av; const double* au;                     // N each: stage B, Ax(vk1_x) and Ax(uk1_x)
+    const double* phipart; int nblocks;
+    double ak, bk, gk, muf, etafk, sgk, etagk, tt;
+    int N;
+};
+template <int STAGE>
+__global__ void __launch_bounds__(1024) pot_warm_slack_kernel(const PotWarmSlack a) {
+    __shared__ double red[32];
+    const int N = a.N;
+    const double ak = a.ak, bk = a.bk, ak2 = a.ak * a.ak;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double uk = a.us[i], wk = a.ws[i], pik = a.pis[i], lkB = a.lkBs[i];
+        if (STAGE == 0) {
+            const double vk = a.vs[i];
+            const double hA = a.lkA[i] - (1.0 / bk) * (a.huk[i] - a.b[i]);                    // warmup_class2.m:66, first block
+            const double wuk = (ak * a.gk * vk + (a.gk + a.muf * ak) * uk) / a.etafk;         // :64
+            const double hB = lkB - (1.0 / bk) * (uk - wk) + (ak / bk) * (-(pik - wk));       // :66, second block
+            const double cAw = -a.b[i] - wk;                                                  // :67 (Htb = b(1:n+m) here)
+            const double cAlk = hA + hB;                                                      // :68
+            const double d = a.etafk * wuk - ak2 * (cAlk + a.sgk * cAw);                      // :69 (wc = 0 here)
+            a.dds[i] = d;
+            a.hdd[i] += d;                                                                    // :72: Ax(dd_x) + dd_s
+        } else {
+            const double d = a.dds[i];
+            const double u1 = (d - a.ff[i]) / (a.etafk + a.tt);                               // :74
+            const double v1 = u1 + (u1 - uk) / ak;                                            // :76
+            const double wwk = (ak * pik + wk) / (1.0 + ak);                                  // :63
+            const double blk = lkB + (ak / bk) * (v1 - pik);                                  // :78
+            const double w1 = fmax(0.0, wwk - (ak2 / a.etagk) * (-blk));                      // :79
+            const double p1 = w1 + (w1 - wk) / ak;                                            // :81
+            const double l1 = lkB + (ak / bk) * (v1 - p1);                                    // :82
+            a.us[i] = u1; a.vs[i] = v1; a.ws[i] = w1; a.pis[i] = p1; a.lkBs[i] = l1;
+            a.lkA[i] += (ak / bk) * (a.av[i] + v1 - a.b[i]);                                  // :77, :82
+            a.huk[i] = a.au[i] + u1;                                                          // H*uk1: the next iteration's :66
+        }
+    }
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = threadIdx.x; b < a.nblocks; b += 1024) {
+        if (STAGE == 0) s1 += a.phipart[b];
+        else { s1 += a.phipart[2 * b]; s2 += a.phipart[2 * b + 1]; }
+    }
+    s1 = block_sum(s1, red);
+    if (STAGE == 1) s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        if (STAGE == 0) a.hdd[N] = s1;                                                        // phi'*dd_x
+        else { a.lkA[N] += (ak / bk) * (s1 - a.b[N]); a.huk[N] = s2; }                        // phi'*vk1_x - mu ; phi'*uk1_x
+    }
+}
+
+// y = invHHt(v,p,q,sg,phi) = (sg*I + H*H') \ v (Class2/invHHt.m:8-17) in one block, no host round trip;
+// l = Ax(phi,p,q) (n+m) and ||phi||^2 are formed once per warm start
+__global__ void __launch_bounds__(1024) invhht_block_kernel(int64_t n, int64_t m, const double* __restrict__ v, const double* __restrict__ p,
+                                                            const double* __restrict__ q, double sg, const double* __restrict__ l,
+                                                            double nphi2, double* __restrict__ y) {
+    __shared__ double red[32];
+    const int64_t N = n + m;
+    const double sg1 = sg + 1.0;                                                              // invAAt(.,p,q,sg+1), :9,:12
+    double s_np = 0.0, s_nq = 0.0, s_ql = 0.0, s_pl = 0.0, s_qv = 0.0, s_pv = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const double pi = p[i]; s_np = fma(pi, pi, s_np); s_pl = fma(pi, l[n + i], s_pl); s_pv = fma(pi, v[n + i], s_pv);
+    }
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double qj = q[j]; s_nq = fma(qj, qj, s_nq); s_ql = fma(qj, l[j], s_ql); s_qv = fma(qj, v[j], s_qv);
+    }
+    const double np_ = block_sum(s_np, red), nq = block_sum(s_nq, red);
+    const double ql = block_sum(s_ql, red), pl = block_sum(s_pl, red), qv = block_sum(s_qv, red), pvv = block_sum(s_pv, red);
+    const double den = sg1 * sg1 + sg1 * nq + sg1 * np_;
+    auto inv_aat = [&](double x, int64_t i, double qx, double px) {                           // invAAt.m:17-18
+        return (i < n) ? (x / (sg1 + np_) + (np_ / (sg1 + np_) * qx - px) * q[i] / den)
+                       : (x / (sg1 + nq) + (nq / (sg1 + nq) * px - qx) * p[i - n] / den);
+    };
+    double s_lVl = 0.0, s_lVv = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const double li = l[i];
+        s_lVl = fma(li, inv_aat(li, i, ql, pl), s_lVl);
+        s_lVv = fma(li, inv_aat(v[i], i, qv, pvv), s_lVv);
+    }
+    const double lVl = block_sum(s_lVl, red), lVv = block_sum(s_lVv, red);
+    const double s = (sg + nphi2) - lVl;                                                      // :8-9
+    const double v2 = v[N];
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        const double Vl = inv_aat(l[i], i, ql, pl), Vv = inv_aat(v[i], i, qv, pvv);
+        y[i] = (s * Vv + lVv * Vl - v2 * Vl) / s;                                             // :14,:17
+    }
+    if (threadIdx.x == 0) y[N] = (v2 - lVv) / s;                                              // :15,:17
+}
+
+// The slack blocks and the (N+1)-vectors of the APD outer iteration of Class 2.
+//   stage 0 (APD_SsN_Class2.m:121-122): wk_s = bk*(us+ak*vs)/ak^2, huk = [Ax(xk)+us ; phi'xk], wlk = bk1*(lk-(huk-b)/bk)-b
+//   stage 1 (:231-238): us1 = prox((wk_s - lk(1:N))/tk), vs1, huk1 = [Ax(xk1)+us1 ; phi'xk1] and the squared KKT residuals
+//           scal[2..4] = ||y1-max(y1-lk(1:n),0)||^2, ||z1-max(z1-lk(n+1:N),0)||^2, ||huk1-b||^2 (scal[0..1] = c'xk1 and the x residual
+//           come from the plan-wide kernel)
+struct PotApdSlack {
+    const double* us; const double* vs; const double* ws_in; double* ws_out; double* us1; double* vs1;
+    const double* lk; const double* b; double* axk;         // axk: in Ax(x) (N entries) -> out huk (N+1)
+    double* wlk; double* scal;
+    const double* phipart; int nblocks;
+    double ak, bk, bk1, inv_tk;
+    int N, n;
+};
+template <int STAGE>
+__global__ void __launch_bounds__(1024) pot_apd_slack_kernel(const PotApdSlack a) {
+    __shared__ double red[32];
+    const int N = a.N;
+    const double ak = a.ak, ak2 = a.ak * a.ak, inv_bk = 1.0 / a.bk;
+    double ky = 0.0, kz = 0.0, kl = 0.0, pp = 0.0;
+    for (int b = threadIdx.x; b < a.nblocks; b += 1024) pp += a.phipart[b];
+    pp = block_sum(pp, red);                                                                  // phi'*x
+    for (int i = threadIdx.x; i <= N; i += 1024) {
+        if (STAGE == 0) {
+            double h;
+            if (i < N) {
+                a.ws_out[i] = __ddiv_rn(__dmul_rn(a.bk, __dadd_rn(a.us[i], __dmul_rn(ak, a.vs[i]))), ak2);   // :121 (wc = 0 here)
+                h = __dadd_rn(a.axk[i], a.us[i]);
+            } else h = pp;
+            a.axk[i] = h;
+            const double t = __dsub_rn(a.lk[i], __dmul_rn(inv_bk, __dsub_rn(h, a.b[i])));      // :122
+            a.wlk[i] = __dsub_rn(__dmul_rn(a.bk1, t), a.b[i]);
+        } else {
+            double h;
+            if (i < N) {
+                const double z = __dmul_rn(a.inv_tk, __dsub_rn(a.ws_in[i], a.lk[i]));          // zk on the slack blocks, :124-126
+                const double s1 = (z >= 0.0) ? z : 0.0;                                        // uk1 = prox(zk), :231
+                a.us1[i] = s1;
+                a.vs1[i] = __dadd_rn(s1, __ddiv_rn(__dsub_rn(s1, a.us[i]), ak));
+                const double t = s1 - a.lk[i];
+                const double d = s1 - ((t >= 0.0) ? t : 0.0);                                  // :234-235
+                if (i < a.n) ky = fma(d, d, ky); else kz = fma(d, d, kz);
+                h = __dadd_rn(a.axk[i], s1);
+            } else h = pp;
+            a.axk[i] = h;
+            const double e = h - a.b[i];                                                       // :233
+            kl = fma(e, e, kl);
+        }
+    }
+    if (STAGE == 1) {
+        ky = block_sum(ky, red); kz = block_sum(kz, red); kl = block_sum(kl, red);
+        if (threadIdx.x == 0) { a.scal[2] = ky; a.scal[3] = kz; a.scal[4] = kl; }
     }
 }
 
@@ -1618,6 +1804,119 @@ void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double
 #undef SSN_APD_E
     SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, scalpart.p, t.chunks, t.groups, m, n, nblocks,
                axk1_out, scal2_dev);
+}
+
+// [uk, lk] = warmup_class2(c,r,l,p,q,mu,phi,0,maxit) -- Class2/warmup_class2.m:18-108 (the call of Class2/APD_SsN_Class2.m:50),
+// device resident: per A-ADMM iteration two plan-wide kernels over the x block (the PHI variants of warm_kernel: phi rides
+// along as one more streamed array, the rank-2 terms and lk(N+1)*phi are formed on the fly), one block for the slack blocks
+// and the (N+1)-vectors, invHHt in one block.  b = [r ; l ; mu] (N+1); uk_out has m*n + N entries, lk_out N+1.
+void plan_warmup_class2(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n,
+                        const double* phi, int maxit, double* uk_out, double* lk_out) {
+    SSN_REQUIRE(cost && b && p && q && phi && uk_out && lk_out && m > 0 && n > 0 && maxit >= 0, SSN_E_INVALID, "warmup_class2: bad arguments");
+    SSN_REQUIRE(m + n < (int64_t)1 << 30, SSN_E_TOO_LARGE, "warmup_class2: m + n too large");
+    const int64_t N = m + n; const size_t mn = (size_t)m * (size_t)n, L = mn + (size_t)N;
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> vk(c, L), wk(c, L), pik(c, L), lkB(c, L), dd(c, L);
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), rowpart2(c, (size_t)t.chunks * m), colpart2(c, (size_t)t.groups * n);
+    Buf<double> huk(c, N + 1), hdd(c, N + 1), ff(c, N + 1), av(c, N), au(c, N), lphi(c, N), phipart(c, (size_t)2 * nblocks);
+    double* uk = uk_out; double* lkA = lk_out;
+    SSN_CUDA(cudaMemsetAsync(uk, 0, sizeof(double) * L, c->stream));
+    vk.zero(); wk.zero(); pik.zero(); lkB.zero(); huk.zero();
+    SSN_CUDA(cudaMemsetAsync(lkA, 0, sizeof(double) * (N + 1), c->stream));
+    plan_ax(c, phi, p, q, m, n, lphi);                                      // invHHt.m:8: l = Ax(phi), norm(phi)^2
+    const double nphi2 = dev_dot(c, phi, phi, (int64_t)mn);
+    WarmArgs a{};
+    a.xk = uk; a.vk = vk; a.wk = wk; a.pik = pik; a.lk2 = lkB; a.dd = dd; a.c = cost; a.p = p; a.q = q; a.b = b;
+    a.lk1 = lkA; a.axk = huk; a.y = ff; a.gama = nullptr; a.gama_s = INFINITY; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
+    a.rowpart = rowpart; a.colpart = colpart; a.rowpart2 = rowpart2; a.colpart2 = colpart2; a.phi = phi; a.phipart = phipart;
+    PotWarmSlack sl{};
+    sl.us = uk + mn; sl.vs = vk.p + mn; sl.ws = wk.p + mn; sl.pis = pik.p + mn; sl.lkBs = lkB.p + mn; sl.dds = dd.p + mn;
+    sl.b = b; sl.lkA = lkA; sl.huk = huk; sl.hdd = hdd; sl.ff = ff; sl.av = av; sl.au = au; sl.phipart = phipart; sl.nblocks = nblocks; sl.N = (int)N;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)2 * kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(uk, m) && vec_ok(cost, m) && vec_ok(phi, m) && vec_ok(vk.p, m) && vec_ok(dd.p, m);
+    const double muf = 0.0;
+    double gk = 1.0, bk = 1.0;                                              // warmup_class2.m:26
+    for (int k = 1; k <= maxit; ++k) {
+        const double ak = bk, bk1 = bk / (1 + ak);                          // :59-62
+        const double gk1 = (gk + muf * ak) / (1 + ak);
+        const double etafk = (1 + ak) * gk + muf * ak;
+        const double sgk = 1 / bk1, etagk = (1 + ak) * bk;
+        const double tt = sgk * ak * ak, sg = 1 + etafk / tt;               // :71
+        a.ak = ak; a.bk = bk; a.gk = gk; a.muf = muf; a.etafk = etafk; a.sgk = sgk; a.etagk = etagk; a.tt = tt;
+        sl.ak = ak; sl.bk = bk; sl.gk = gk; sl.muf = muf; sl.etafk = etafk; sl.sgk = sgk; sl.etagk = etagk; sl.tt = tt;
+        if (vec) SSN_LAUNCH(c, (warm_kernel<0, true, G_INF, true>), grid, kThreads, smem / 2, a);
+        else     SSN_LAUNCH(c, (warm_kernel<0, false, G_INF, true>), grid, kThreads, smem / 2, a);
+        SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, nullptr, nullptr, t.chunks, t.groups, m, n, hdd.p, nullptr);
+        SSN_LAUNCH(c, pot_warm_slack_kernel<0>, 1, 1024, 0, sl);
+        SSN_LAUNCH(c, invhht_block_kernel, 1, 1024, 0, n, m, hdd.p, p, q, sg, lphi.p, nphi2, ff.p);   // :73
+        if (vec) {
+            if (k == 1) SSN_CUDA(cudaFuncSetAttribute((warm_kernel<1, true, G_INF, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSN_LAUNCH(c, (warm_kernel<1, true, G_INF, true>), grid, kThreads, smem, a);
+        } else {
+            if (k == 1) SSN_CUDA(cudaFuncSetAttribute((warm_kernel<1, false, G_INF, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSN_LAUNCH(c, (warm_kernel<1, false, G_INF, true>), grid, kThreads, smem, a);
+        }
+        SSN_LAUNCH(c, plan_finish2_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, rowpart2.p, colpart2.p, t.chunks, t.groups, m, n, av.p, au.p);
+        SSN_LAUNCH(c, pot_warm_slack_kernel<1>, 1, 1024, 0, sl);
+        gk = gk1; bk = bk1;                                                 // :84
+    }
+}
+
+// Class2/APD_SsN_Class2.m:121-122 in one pass over the x block: wk = -wc + bk*(uk+ak*vk)/ak^2 (m*n + N),
+// huk = H*uk = [Ax(xk) + [yk;zk] ; phi'*xk] and wlk = bk1*(lk - 1/bk*(huk - b)) - b (N+1 each)
+void plan_apd_begin_pot(ssn_ctx* c, const double* cost, const double* uk, const double* vk, const double* p, const double* q, int64_t m,
+                        int64_t n, const double* phi, const double* b, const double* lk, double ak, double bk, double bk1, double* wk_out,
+                        double* huk_out, double* wlk_out) {
+    SSN_REQUIRE(cost && uk && vk && p && q && phi && b && lk && wk_out && huk_out && wlk_out && m > 0 && n > 0, SSN_E_INVALID, "apd_begin_pot: bad arguments");
+    const int64_t N = m + n; const size_t mn = (size_t)m * (size_t)n;
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), phipart(c, (size_t)nblocks);
+    ApdArgs a{};
+    a.c = cost; a.xk = uk; a.vk = vk; a.wk_out = wk_out; a.p = p; a.q = q; a.ak = ak; a.bk = bk; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups; a.rowpart = rowpart; a.colpart = colpart;
+    a.phi = phi; a.phipart = phipart;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(cost, m) && vec_ok(uk, m) && vec_ok(vk, m) && vec_ok(wk_out, m) && vec_ok(phi, m);
+    if (vec) SSN_LAUNCH(c, (apd_kernel<0, true, G_INF, true>), grid, kThreads, smem, a);
+    else     SSN_LAUNCH(c, (apd_kernel<0, false, G_INF, true>), grid, kThreads, smem, a);
+    SSN_LAUNCH(c, plan_finish_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, nullptr, t.chunks, t.groups, m, n, 0, huk_out, nullptr);
+    PotApdSlack sl{};
+    sl.us = uk + mn; sl.vs = vk + mn; sl.ws_out = wk_out + mn; sl.lk = lk; sl.b = b; sl.axk = huk_out; sl.wlk = wlk_out;
+    sl.phipart = phipart; sl.nblocks = nblocks; sl.ak = ak; sl.bk = bk; sl.bk1 = bk1; sl.N = (int)N; sl.n = (int)n;
+    SSN_LAUNCH(c, pot_apd_slack_kernel<0>, 1, 1024, 0, sl);
+}
+
+// Class2/APD_SsN_Class2.m:231-238 in one pass over the x block: uk1 = prox(zk) at the duals lk (N+1), vk1 = uk1+(uk1-uk)/ak,
+// huk1 = H*uk1 and scal5 = { c'*xk1, ||xk1 - max(xk1-c-(Aty(lk)+lk(N+1)*phi),0)||^2, the same for y and z, ||huk1 - b||^2 }
+void plan_apd_end_pot(ssn_ctx* c, const double* cost, const double* wk, const double* uk, const double* lk, const double* p, const double* q,
+                      int64_t m, int64_t n, const double* phi, const double* b, double tk, double ak, double* uk1, double* vk1,
+                      double* huk1_out, double* scal5_dev) {
+    SSN_REQUIRE(cost && wk && uk && lk && p && q && phi && b && uk1 && vk1 && huk1_out && scal5_dev && m > 0 && n > 0, SSN_E_INVALID,
+                "apd_end_pot: bad arguments");
+    const int64_t N = m + n; const size_t mn = (size_t)m * (size_t)n;
+    const Tiling t = plan_tiling(c, m, n);
+    const int nblocks = t.chunks * t.groups;
+    Buf<double> rowpart(c, (size_t)t.chunks * m), colpart(c, (size_t)t.groups * n), scalpart(c, (size_t)2 * nblocks), phipart(c, (size_t)nblocks);
+    ApdArgs a{};
+    a.c = cost; a.xk = uk; a.wk_in = wk; a.xk1 = uk1; a.vk1 = vk1; a.p = p; a.q = q; a.lam = lk; a.gama = nullptr; a.gama_s = INFINITY;
+    a.ak = ak; a.inv_tk = 1.0 / tk; a.m = m; a.n = n;
+    a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups; a.rowpart = rowpart; a.colpart = colpart; a.scalpart = scalpart;
+    a.phi = phi; a.phipart = phipart;
+    const dim3 grid(t.chunks, t.groups);
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
+    const bool vec = vec_ok(cost, m) && vec_ok(uk, m) && vec_ok(wk, m) && vec_ok(uk1, m) && vec_ok(vk1, m) && vec_ok(phi, m);
+    if (vec) SSN_LAUNCH(c, (apd_kernel<1, true, G_INF, true>), grid, kThreads, smem, a);
+    else     SSN_LAUNCH(c, (apd_kernel<1, false, G_INF, true>), grid, kThreads, smem, a);
+    SSN_LAUNCH(c, plan_finish_kernel, cdiv(N, 256), 256, 0, rowpart.p, colpart.p, scalpart.p, t.chunks, t.groups, m, n, nblocks, huk1_out, scal5_dev);
+    PotApdSlack sl{};
+    sl.us = uk + mn; sl.ws_in = wk + mn; sl.us1 = uk1 + mn; sl.vs1 = vk1 + mn; sl.lk = lk; sl.b = b; sl.axk = huk1_out; sl.scal = scal5_dev;
+    sl.phipart = phipart; sl.nblocks = nblocks; sl.ak = ak; sl.inv_tk = 1.0 / tk; sl.N = (int)N; sl.n = (int)n;
+    SSN_LAUNCH(c, pot_apd_slack_kernel<1>, 1, 1024, 0, sl);
 }
 
 // Y = sparse(reshape(s,m,n)) as two sorted coordinate lists (ASAt.m:15):

@@ -34,6 +34,15 @@ void plan_apd_end(ssn_ctx* c, const double* cost, const double* wk, const double
 void plan_prox_residual_pot(ssn_ctx* c, const double* w, const double* lam, const double* p, const double* q, int64_t m, int64_t n,
                             double tk, const double* phi, double* hp_out, double* prox_out, uint8_t* s_out, double* t_out,
                             double* scal3_dev);
+// Class 2 (partial OT), u = [x (m*n) ; y (n) ; z (m)], b = [r ; l ; mu], lk of n+m+1 entries
+void plan_warmup_class2(ssn_ctx* c, const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n,
+                        const double* phi, int maxit, double* uk_out, double* lk_out);
+void plan_apd_begin_pot(ssn_ctx* c, const double* cost, const double* uk, const double* vk, const double* p, const double* q, int64_t m,
+                        int64_t n, const double* phi, const double* b, const double* lk, double ak, double bk, double bk1, double* wk_out,
+                        double* huk_out, double* wlk_out);
+void plan_apd_end_pot(ssn_ctx* c, const double* cost, const double* wk, const double* uk, const double* lk, const double* p, const double* q,
+                      int64_t m, int64_t n, const double* phi, const double* b, double tk, double ak, double* uk1, double* vk1,
+                      double* huk1_out, double* scal5_dev);
 int64_t plan_active_set(ssn_ctx* c, const uint8_t* s, int64_t m, int64_t n, Buf<int>& colptr, Buf<int>& yrow,
                         Buf<int>& ycol, Buf<int>& rowcount);
 }  // namespace ssn

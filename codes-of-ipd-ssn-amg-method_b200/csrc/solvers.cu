@@ -625,14 +625,14 @@ void pot_epilogue(ssn_ctx* c, int N, PotPrologue& P, const double* vv, const dou
 
 }  // namespace
 
-void amg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info) {
+void amg4pot(ssn_ctx* c, const ssn_prob_data* pd, const ssn_amg_options* opts, double* zeta, int* it, double* res, int* info, bool twogrid) {
     PotPrologue P; pot_prologue(c, pd, P);
     const int N = (int)(pd->m + pd->n);
     Buf<double> vv(c, N), ww(c, N);
     ssn_prob_data q = *pd;
     int it1, it2, i1[2], i2[2]; double r1, r2;
-    q.z_dev = P.v; hybrid_amg(c, &q, opts, vv, &it1, &r1, i1);               // AMG4POT.m:46
-    q.z_dev = P.w; hybrid_amg(c, &q, opts, ww, &it2, &r2, i2);               // AMG4POT.m:47
+    q.z_dev = P.v; hybrid_amg(c, &q, opts, vv, &it1, &r1, i1, twogrid);      // AMG4POT.m:46 / :49 (str = 'twogrid': Hybrid_twogrid)
+    q.z_dev = P.w; hybrid_amg(c, &q, opts, ww, &it2, &r2, i2, twogrid);      // AMG4POT.m:47 / :50
     pot_epilogue(c, N, P, vv, ww, zeta);
     if (it) *it = std::max(it1, it2);
     if (res) *res = std::max(r1, r2);

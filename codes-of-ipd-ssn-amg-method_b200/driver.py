@@ -208,8 +208,15 @@ CLASS2_AMG_OPTIONS = {"retol": 1e-11, "bigph": 1, "maxit": 40, "theta": 1 / 4, "
 
 
 def warmup_class2(c, r, l, p, q, mu, phi, res=0.0, maxit=100):
-    """A-ADMM warm start for partial OT -- reference Class2/warmup_class2.m:18-108, on the device
-    (operator by operator: Ax, Aty, invHHt and torch vector updates)."""
+    """A-ADMM warm start for partial OT -- reference Class2/warmup_class2.m:18-108, on the device (fused kernels,
+    ``ssn_warmup_class2``)."""
+    import torch
+    c, r, l, p, q, phi = (_t(v, torch) for v in (c, r, l, p, q, phi))
+    return api.warmup_class2(c, r, l, p, q, mu, phi, res, maxit)
+
+
+def warmup_class2_unfused(c, r, l, p, q, mu, phi, res=0.0, maxit=100):
+    """The same warm start operator by operator (Ax, Aty, invHHt and torch vector updates): the cross-check of the fused one."""
     import torch
     c, r, l, p, q, phi = (_t(v, torch) for v in (c, r, l, p, q, phi))
     m, n = l.numel(), r.numel(); N = m + n; mn = m * n
@@ -253,8 +260,22 @@ def warmup_class2(c, r, l, p, q, mu, phi, res=0.0, maxit=100):
 
 def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
                    on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None):
-    """APD outer loop + SsN inner loop for partial OT -- reference Class2/APD_SsN_Class2.m:25-285 on the
-    device (inner solver 3 = PCG4POT, 4 = AMG4POT).  u = [x (mn); y (n); z (m)], duals lk (n+m+1)."""
+    """APD outer loop + SsN inner loop for partial OT -- reference Class2/APD_SsN_Class2.m:25-285 on the device (inner
+    solver 3 = PCG4POT, 4 = AMG4POT, 5 = AMG4POT with 'twogrid').  u = [x (mn); y (n); z (m)], duals lk (n+m+1).  Without
+    an ``on_ssn_step`` hook the whole script is ONE library call (``ssn_apd_ssn_class2``); with one, the Python loop below
+    runs over the fused operators so that the hook can see every state."""
+    import torch
+    if on_ssn_step is None:
+        return api.APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=inner_solver, maxit=maxit, KKT_Tol=KKT_Tol, warm_maxit=warm_maxit,
+                                  max_outer=max_outer, max_seconds=max_seconds, verbose=verbose, amg_options=amg_options)
+    return APD_SsN_Class2_loop(c, r, l, p, q, mu, phi, inner_solver, maxit, KKT_Tol, warm_maxit, on_ssn_step, verbose, max_outer,
+                               max_seconds, amg_options)
+
+
+def APD_SsN_Class2_loop(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e-6, warm_maxit=100,
+                        on_ssn_step=None, verbose=False, max_outer=None, max_seconds=None, amg_options=None, fused_warmup=True):
+    """The script as a Python loop over the library's operators (the form the one-call entry point replaced): kept for the
+    ``on_ssn_step`` hook and as the cross-check of ``ssn_apd_ssn_class2``."""
     import torch
     c, r, l, p, q, phi = (_t(v, torch) for v in (c, r, l, p, q, phi))
     m, n = l.numel(), r.numel(); N = m + n; mn = m * n
@@ -267,7 +288,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
     Htmul = lambda lam: torch.cat([api.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])
     nrm = lambda v: float(torch.linalg.norm(v))
     t_start = time.time()
-    uk, lk = warmup_class2(c, r, l, p, q, mu, phi, 0.0, warm_maxit)     # :50
+    uk, lk = (warmup_class2 if fused_warmup else warmup_class2_unfused)(c, r, l, p, q, mu, phi, 0.0, warm_maxit)     # :50
     torch.cuda.synchronize(); t_warm = time.time() - t_start
     vk = uk.clone()
 
@@ -303,11 +324,11 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
                 on_ssn_step(dict(prob_data, k=k, ssn_it=ssn_it))
             if inner_solver == 3:
                 zeta, itpcg, respcg, info = api.PCG4POT(prob_data, pcg_options)        # :168
-            elif inner_solver == 4:
-                zeta, itpcg, respcg, info = api.AMG4POT(prob_data, amg_options, "amg")   # :171
+            elif inner_solver in (4, 5):
+                zeta, itpcg, respcg, info = api.AMG4POT(prob_data, amg_options, "amg" if inner_solver == 4 else "twogrid")   # :171 / :182
                 stats["amg_calls"] += 1
             else:
-                raise ValueError("inner_solver must be 3 (PCG4POT) or 4 (AMG4POT)")
+                raise ValueError("inner_solver must be 3 (PCG4POT), 4 (AMG4POT) or 5 (AMG4POT, 'twogrid')")
             its.append(itpcg)
             cFk_old = bk1 / 2 * float(lk_old @ lk_old) - float(wlk @ lk_old) + 0.5 * tk * ev["norm2"]   # :196-197
             ress = abs(float(Fk_old @ zeta))
@@ -374,10 +395,16 @@ def class2_trivial_state(P):
     return {"wk": wk, "lk": torch.zeros(m + n + 1, **f64), "wlk": wlk, "p": p, "q": q, "phi": phi, "tk": tk, "bk1": bk1, "m": m, "n": n, "k": 1}
 
 
-def ssn_step_class2(state, amg_options=None, max_ll=500):
-    """One semismooth-Newton step of Class2/APD_SsN_Class2.m:137-217 at a fixed APD state: fused residual + active
-    flags (``ssn_prox_residual_pot``) -> ASAt -> AMG4POT -> Armijo line search (one fused pass per trial) -> new residual.
-    Returns ``(lk_new, Fk_new, info)``."""
+def ssn_step_class2(state, amg_options=None, host_call=False):
+    """One semismooth-Newton step of Class2/APD_SsN_Class2.m:137-217 at a fixed APD state as ONE library call
+    (``ssn_ssn_step_class2``).  Returns ``(lk_new, Fk_new, info)``."""
+    return api.ssn_step_class2(state["wk"], state["lk"], state["wlk"], state["p"], state["q"], state["bk1"], state["tk"], state["phi"],
+                               inner_solver=4, amg_options=amg_options or CLASS2_AMG_OPTIONS, host_call=host_call)
+
+
+def ssn_step_class2_ops(state, amg_options=None, max_ll=500):
+    """The same step operator by operator with host-timed phases: fused residual + active flags (``ssn_prox_residual_pot``)
+    -> ASAt -> AMG4POT -> Armijo line search (one fused pass per trial) -> new residual.  Returns ``(lk_new, Fk_new, info)``."""
     import torch
     wk, lk, wlk, p, q, phi = state["wk"], state["lk"], state["wlk"], state["p"], state["q"], state["phi"]
     bk1, tk = state["bk1"], state["tk"]

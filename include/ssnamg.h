@@ -337,6 +337,58 @@ SSN_API int ssn_ssn_step_class1_host(ssn_ctx *ctx, const double *wk_host, const 
                         const double *gama_host, double gama_scalar, int inner_solver, const ssn_amg_options *amg,
                         double *lk_new_host, double *Fk_new_host, double *info12_host);
 
+/* ------------------------------------------------------------------ Class 2 (partial OT) as single calls
+ * u = [x (m*n, column-major) ; y (n) ; z (m)], b = [r ; l ; mu], duals lk of n+m+1 entries, H = [A I ; phi' 0]. */
+
+/* [uk,lk] = warmup_class2(c,r,l,p,q,mu,phi,0,maxit) -- Class2/warmup_class2.m:18-108, the A-ADMM warm start called at
+ * Class2/APD_SsN_Class2.m:50, device resident: two fused plan-wide kernels per iteration (phi rides along as one more
+ * streamed array), the slack blocks and the (n+m+1)-vectors in one block, invHHt (Class2/invHHt.m) in one block.
+ * b_dev = [r ; l ; mu] (n+m+1).  Outputs uk_out_dev (m*n+n+m) and lk_out_dev (n+m+1).  The reference's stopping test is
+ * commented out (warmup_class2.m:89-102), so exactly maxit iterations run. */
+SSN_API int ssn_warmup_class2(ssn_ctx *ctx, const double *c_dev, const double *b_dev, const double *p_dev, const double *q_dev,
+                      int64_t m, int64_t n, const double *phi_dev, int maxit, double *uk_out_dev, double *lk_out_dev);
+
+/* Class2/APD_SsN_Class2.m:121-122 in one pass over the x block: wk = -wc + bk*(uk+ak*vk)/ak^2 (m*n+n+m),
+ * huk = [Ax(xk)+[yk;zk] ; phi'*xk] and wlk = bk1*(lk - 1/bk*(huk - b)) - b (n+m+1 each). */
+SSN_API int ssn_apd_begin_pot(ssn_ctx *ctx, const double *c_dev, const double *uk_dev, const double *vk_dev, const double *p_dev,
+                      const double *q_dev, int64_t m, int64_t n, const double *phi_dev, const double *b_dev, const double *lk_dev,
+                      double ak, double bk, double bk1, double *wk_out_dev, double *huk_out_dev, double *wlk_out_dev);
+/* Class2/APD_SsN_Class2.m:231-238 in one pass: uk1 = prox(zk) at the duals lk, vk1 = uk1 + (uk1-uk)/ak, huk1 = H*uk1 and, on
+ * the HOST, scal5 = { c'*xk1, ||xk1-max(xk1-c-(Aty(lk)+lk(end)*phi),0)||^2, ||yk1-max(yk1-lk(1:n),0)||^2,
+ * ||zk1-max(zk1-lk(n+1:n+m),0)||^2, ||huk1-b||^2 } (the squares of KKT_xk, KKT_yk, KKT_zk, KKT_lk). */
+SSN_API int ssn_apd_end_pot(ssn_ctx *ctx, const double *c_dev, const double *wk_dev, const double *uk_dev, const double *lk_dev,
+                    const double *p_dev, const double *q_dev, int64_t m, int64_t n, const double *phi_dev, const double *b_dev,
+                    double tk, double ak, double *uk1_dev, double *vk1_dev, double *huk1_out_dev, double *scal5_host);
+
+/* The script Class2/APD_SsN_Class2.m:25-285 as ONE call: warm start, APD outer loop, SsN inner loop with its Armijo line
+ * search and KKT bookkeeping, restart rule (:253-257).  opts as ssn_apd_ssn_class1 (inner_solver 3 = PCG4POT, 4 = AMG4POT
+ * (default), 5 = AMG4POT with str = 'twogrid'; opts->amg NULL: the options of :80-81).  Outputs on the device: uk (m*n+n+m),
+ * lk (n+m+1).  Optional HOST buffers: fxk history (maxit+1), the four KKT histories interleaved {x,y,z,l} (4*(maxit+1)),
+ * SsN steps per outer iteration (maxit ints), per SsN step {k, ssn_it, nnz(s), components, inner iterations, ll, |F|}. */
+SSN_API int ssn_apd_ssn_class2(ssn_ctx *ctx, const double *c_dev, const double *r_dev, const double *l_dev, const double *p_dev,
+                       const double *q_dev, int64_t m, int64_t n, double mu, const double *phi_dev, const ssn_apd_options *opts,
+                       double *uk_out_dev, double *lk_out_dev, ssn_apd_result *result, double *fxk_hist_host,
+                       double *kkt4_hist_host, int32_t *ssn_its_hist_host, double *steps_host, int64_t steps_cap);
+/* The same for a caller that holds HOST arrays (inputs copied to the device once, uk and lk copied back once). */
+SSN_API int ssn_apd_ssn_class2_host(ssn_ctx *ctx, const double *c_host, const double *r_host, const double *l_host,
+                            const double *p_host, const double *q_host, int64_t m, int64_t n, double mu, const double *phi_host,
+                            const ssn_apd_options *opts, double *uk_out_host, double *lk_out_host, ssn_apd_result *result,
+                            double *fxk_hist_host, double *kkt4_hist_host, int32_t *ssn_its_hist_host, double *steps_host,
+                            int64_t steps_cap);
+
+/* ONE semismooth-Newton step of Class2/APD_SsN_Class2.m:137-217 at a fixed APD state -- wk (m*n+n+m), wlk (n+m+1), bk1, tk as
+ * :116-122 leave them -- from the duals lk (n+m+1): fused residual + active flags -> ASAt -> AMG4POT (inner_solver 4; 5: its
+ * 'twogrid' variant; 3: PCG4POT) -> the Armijo loop (one fused pass over wk and phi per trial) -> the new residual.
+ * Outputs lk_new, Fk_new (n+m+1 each) and the 12 HOST doubles of ssn_ssn_step_class1.  amg / pcg NULL: :80-81 / :74. */
+SSN_API int ssn_ssn_step_class2(ssn_ctx *ctx, const double *wk_dev, const double *lk_dev, const double *wlk_dev, const double *p_dev,
+                        const double *q_dev, int64_t m, int64_t n, double bk1, double tk, const double *phi_dev, int inner_solver,
+                        const ssn_amg_options *amg, const ssn_pcg_options *pcg, double *lk_new_dev, double *Fk_new_dev,
+                        double *info12_host);
+SSN_API int ssn_ssn_step_class2_host(ssn_ctx *ctx, const double *wk_host, const double *lk_host, const double *wlk_host,
+                        const double *p_host, const double *q_host, int64_t m, int64_t n, double bk1, double tk,
+                        const double *phi_host, int inner_solver, const ssn_amg_options *amg, const ssn_pcg_options *pcg,
+                        double *lk_new_host, double *Fk_new_host, double *info12_host);
+
 /* [xk,lk] = warmup_class1(c,r,l,p,q,gama,0,maxit) -- Class1/warmup_class1.m:18-96, the A-ADMM warm start
  * called at Class1/APD_SsN_Class1.m:59, device resident: two fused plan-wide kernels per iteration
  * (17 plan-sized reads/writes instead of the ~45 of the Ax/Aty/prox/vector-update chain).
@@ -500,6 +552,10 @@ SSN_API int ssn_aug_pcg(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_opt
 SSN_API int ssn_amg4pot(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts,
                 double *zeta_dev, int *it_out, double *res_out, int *info_out);
 SSN_API int ssn_pcg4pot(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_pcg_options *opts,
+                double *zeta_dev, int *it_out, double *res_out, int *info_out);
+/* AMG4POT(prob_data,amg_options,str) with str = 'twogrid' when twogrid != 0 (Class2/AMG4POT.m:45-51: Hybrid_twogrid in
+ * place of Hybrid_AMG; inner_solver = 5 of Class2/APD_SsN_Class2.m:181-182). */
+SSN_API int ssn_amg4pot_str(ssn_ctx *ctx, const ssn_prob_data *pd, const ssn_amg_options *opts, int twogrid,
                 double *zeta_dev, int *it_out, double *res_out, int *info_out);
 
 /* The assembled rescaled system of Hybrid_AMG.m:17-24 / aug_PCG.m:16-22 (for parity tests):

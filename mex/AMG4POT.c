@@ -1,5 +1,6 @@
-/* [zeta,it,res,info] = AMG4POT(prob_data,amg_options,str)  (str = 'amg'; 'twogrid' is out of scope)
- * -- MEX replacement of the reference's Class2/AMG4POT.m:1-56. */
+/* [zeta,it,res,info] = AMG4POT(prob_data,amg_options,str)  (str = 'amg': the two solves through Hybrid_AMG; any other
+ * string, e.g. 'twogrid': through Hybrid_twogrid, :45-51) -- MEX replacement of the reference's Class2/AMG4POT.m:1-56. */
+#include <string.h>
 #include "ssn_mex_common.h"
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -10,7 +11,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     ssn_amg_options o; double *guess = NULL; ssn_mex_amg_options(c, prhs[1], 0, &o, &guess);
     double *zeta = (double *)ssn_mex_dev_alloc(c, N * sizeof(double));
     int it = 0, info[2] = {0, 0}; double res = 0;
-    int st = ssn_amg4pot(c, &pd.d, &o, zeta, &it, &res, info);
+    int twogrid = 0;
+    if (nrhs > 2 && mxIsChar(prhs[2])) { char buf[16] = {0}; mxGetString(prhs[2], buf, sizeof(buf)); twogrid = strcmp(buf, "amg") != 0; }
+    int st = ssn_amg4pot_str(c, &pd.d, &o, twogrid, zeta, &it, &res, info);
     plhs[0] = ssn_mex_from_device(c, zeta, N, &st);
     if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(it);
     if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(res);

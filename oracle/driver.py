@@ -260,7 +260,7 @@ def APD_SsN_Class2(c, r, l, p, q, mu, phi, inner_solver=4, maxit=100, KKT_Tol=1e
             if inner_solver == 3:
                 zeta, itpcg, respcg, info = PCG4POT(prob_data, pcg_options)            # :168
             else:
-                zeta, itpcg, respcg, info = AMG4POT(prob_data, amg_options, "amg")     # :171
+                zeta, itpcg, respcg, info = AMG4POT(prob_data, amg_options, "amg" if inner_solver == 4 else "twogrid")   # :171 / :182
                 stats["amg_calls"] += 1
             its.append(itpcg)
             f0 = bk1 / 2 * np.linalg.norm(lk_old) ** 2 - wlk @ lk_old   # :196

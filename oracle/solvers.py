@@ -157,13 +157,13 @@ def _pot_combine(z2, sg, phi_e, v, vv, ww):
 
 
 def AMG4POT(prob_data, amg_options, str_="amg"):
-    """Bordered POT solve by two Hybrid_AMG calls -- reference Class2/AMG4POT.m:27-55."""
-    if str_ != "amg":
-        raise NotImplementedError("Hybrid_twogrid (inner_solver 5) is out of scope; SURVEY 8f")
+    """Bordered POT solve by two Hybrid_AMG calls (``str = 'amg'``) or two Hybrid_twogrid calls (any other ``str``, e.g.
+    ``'twogrid'``) -- reference Class2/AMG4POT.m:27-55."""
+    solve = Hybrid_AMG if str_ == "amg" else Hybrid_twogrid             # AMG4POT.m:45-51
     z2, sg, phi_e, v, w = _pot_split(prob_data)
     pd = dict(prob_data)
-    pd["z"] = v; vv, it1, res1, info1 = Hybrid_AMG(pd, amg_options)      # AMG4POT.m:46
-    pd["z"] = w; ww, it2, res2, info2 = Hybrid_AMG(pd, amg_options)      # AMG4POT.m:47
+    pd["z"] = v; vv, it1, res1, info1 = solve(pd, amg_options)           # AMG4POT.m:46 / :49
+    pd["z"] = w; ww, it2, res2, info2 = solve(pd, amg_options)           # AMG4POT.m:47 / :50
     zeta = _pot_combine(z2, sg, phi_e, v, vv, ww)
     return zeta, max(it1, it2), max(res1, res2), np.maximum(info1, info2)
 

@@ -74,4 +74,18 @@ int emu_warmup_class1(const double* cost, const double* b, const double* p, cons
                       double gama_s, int maxit, double* xk, double* lk) {
     return guarded([&] { ssn::plan_warmup_class1(ctx(), cost, b, p, q, m, n, gama, gama_s, maxit, xk, lk); });
 }
+int emu_warmup_class2(const double* cost, const double* b, const double* p, const double* q, int64_t m, int64_t n, const double* phi,
+                      int maxit, double* uk, double* lk) {
+    return guarded([&] { ssn::plan_warmup_class2(ctx(), cost, b, p, q, m, n, phi, maxit, uk, lk); });
+}
+int emu_apd_begin_pot(const double* cost, const double* uk, const double* vk, const double* p, const double* q, int64_t m, int64_t n,
+                      const double* phi, const double* b, const double* lk, double ak, double bk, double bk1, double* wk, double* huk,
+                      double* wlk) {
+    return guarded([&] { ssn::plan_apd_begin_pot(ctx(), cost, uk, vk, p, q, m, n, phi, b, lk, ak, bk, bk1, wk, huk, wlk); });
+}
+int emu_apd_end_pot(const double* cost, const double* wk, const double* uk, const double* lk, const double* p, const double* q, int64_t m,
+                    int64_t n, const double* phi, const double* b, double tk, double ak, double* uk1, double* vk1, double* huk1,
+                    double* scal5) {
+    return guarded([&] { ssn::plan_apd_end_pot(ctx(), cost, wk, uk, lk, p, q, m, n, phi, b, tk, ak, uk1, vk1, huk1, scal5); });
+}
 }

@@ -29,6 +29,7 @@ double *mxGetPr(const mxArray *a);
 void *mxGetData(const mxArray *a);
 mxLogical *mxGetLogicals(const mxArray *a);
 double mxGetScalar(const mxArray *a);
+int mxGetString(const mxArray *a, char *buf, mwSize buflen);
 mwIndex *mxGetJc(const mxArray *a);
 mwIndex *mxGetIr(const mxArray *a);
 mwSize mxGetNzmax(const mxArray *a);

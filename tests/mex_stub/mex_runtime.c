@@ -62,6 +62,14 @@ double *mxGetPr(const mxArray *a) { return a->pr; }
 void *mxGetData(const mxArray *a) { return a->kind == K_CHAR ? (void *)a->ch : (a->kind == K_LOGICAL ? (void *)a->lg : (void *)a->pr); }
 mxLogical *mxGetLogicals(const mxArray *a) { return a->lg; }
 double mxGetScalar(const mxArray *a) { return a->kind == K_LOGICAL ? (double)a->lg[0] : (a->kind == K_CHAR ? (double)a->ch[0] : a->pr[0]); }
+int mxGetString(const mxArray *a, char *buf, mwSize buflen) {
+    if (a->kind != K_CHAR || buflen == 0) return 1;
+    size_t k = a->m * a->n, i;
+    if (k > buflen - 1) k = buflen - 1;
+    for (i = 0; i < k; ++i) buf[i] = (char)a->ch[i];
+    buf[k] = 0;
+    return 0;
+}
 mwIndex *mxGetJc(const mxArray *a) { return a->jc; }
 mwIndex *mxGetIr(const mxArray *a) { return a->ir; }
 mwSize mxGetNzmax(const mxArray *a) { return a->nzmax; }

@@ -66,7 +66,7 @@ def test_mex_shims_type_check_against_the_header():
     names = {os.path.splitext(os.path.basename(f))[0] for f in shims}
     for fn in ("Ax", "Aty", "ASAt", "ASAtz", "PCG", "aug_PCG", "components", "Hybrid_AMG", "Class_AMG", "transfer", "strength",
                "mis_set", "cf_split_mex", "MG_Vcycle", "MG_Wcycle", "AMG4POT", "PCG4POT", "invAAt", "invHHt", "warmup_class1",
-               "Hybrid_twogrid", "twogrid_bigph", "twogrid"):
+               "Hybrid_twogrid", "twogrid_bigph", "twogrid", "warmup_class2", "APD_SsN_Class1_mex", "APD_SsN_Class2_mex"):
         assert fn in names, f"no MEX shim for {fn}"
     for f in shims:
         r = subprocess.run([gcc, "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function",

@@ -238,3 +238,60 @@ def test_fused_warm_start(emu, oracle, m, n, gama, unit):
     _ok(emu, emu.emu_warmup_class1(_p(c), _p(b), _p(p), _p(q), C.c_int64(m), C.c_int64(n), _p(gv), C.c_double(gs), C.c_int(its), _p(xk), _p(lk)))
     assert np.linalg.norm(xk - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
     assert np.linalg.norm(lk - l_ref) <= 1e-9 * np.linalg.norm(l_ref)
+
+
+@pytest.mark.parametrize("m,n,unit_phi", [(64, 48, True), (45, 70, False)])
+def test_fused_outer_loop_updates_partial_ot(emu, oracle, m, n, unit_phi):
+    """ssn_apd_begin_pot / ssn_apd_end_pot against the script lines (Class2/APD_SsN_Class2.m:121-122, 231-238)"""
+    rs = np.random.RandomState(7)
+    p, q = weights(m, n, 3, False)
+    N = m + n; mn = m * n
+    c = rs.random_sample(mn); uk = rs.random_sample(mn + N); vk = rs.random_sample(mn + N); lk = 0.3 * rs.standard_normal(N + 1)
+    phi = np.ones(mn) if unit_phi else rs.random_sample(mn) + 0.5
+    b = np.concatenate([rs.random_sample(N) + 0.1, [0.7]])
+    ak, bk, tk = 1.3, 0.8, 0.55; bk1 = bk / (1 + ak)
+    H = lambda u: np.concatenate([oracle.Ax(u[:mn], p, q) + u[mn:], [phi @ u[:mn]]])
+    Ht = lambda lam: np.concatenate([oracle.Aty(lam[:N], p, q) + lam[N] * phi, lam[:N]])
+    wc = np.concatenate([c, np.zeros(N)])
+    wk = np.zeros(mn + N); huk = np.zeros(N + 1); wlk = np.zeros(N + 1)
+    _ok(emu, emu.emu_apd_begin_pot(_p(c), _p(uk), _p(vk), _p(p), _p(q), C.c_int64(m), C.c_int64(n), _p(phi), _p(b), _p(lk), C.c_double(ak),
+                                   C.c_double(bk), C.c_double(bk1), _p(wk), _p(huk), _p(wlk)))
+    wk_ref = -wc + bk * (uk + ak * vk) / ak ** 2
+    assert np.allclose(wk, wk_ref, rtol=1e-14, atol=1e-15)
+    assert close(huk, H(uk))
+    assert close(wlk, bk1 * (lk - 1 / bk * (H(uk) - b)) - b)
+    uk1 = np.zeros(mn + N); vk1 = np.zeros(mn + N); huk1 = np.zeros(N + 1); scal = np.zeros(5)
+    _ok(emu, emu.emu_apd_end_pot(_p(c), _p(wk), _p(uk), _p(lk), _p(p), _p(q), C.c_int64(m), C.c_int64(n), _p(phi), _p(b), C.c_double(tk),
+                                 C.c_double(ak), _p(uk1), _p(vk1), _p(huk1), _p(scal)))
+    u1 = np.maximum((wk - Ht(lk)) / tk, 0.0)
+    assert np.allclose(uk1, u1, rtol=1e-14, atol=1e-15)
+    assert np.allclose(vk1, u1 + (u1 - uk) / ak, rtol=1e-13, atol=1e-14)
+    assert close(huk1, H(u1))
+    x1, y1, z1 = u1[:mn], u1[mn:mn + n], u1[mn + n:]
+    ref = [c @ x1,
+           np.sum((x1 - np.maximum(x1 - c - Ht(lk)[:mn], 0.0)) ** 2),
+           np.sum((y1 - np.maximum(y1 - lk[:n], 0.0)) ** 2),
+           np.sum((z1 - np.maximum(z1 - lk[n:N], 0.0)) ** 2),
+           np.sum((H(u1) - b) ** 2)]
+    for got, want in zip(scal, ref):
+        assert abs(got - want) <= 1e-10 * max(abs(want), 1e-30)
+
+
+@pytest.mark.parametrize("m,n,unit", [pytest.param(48, 40, True, marks=_slow), (45, 70, False)])
+def test_fused_warm_start_partial_ot(emu, oracle, m, n, unit):
+    """ssn_warmup_class2 (two fused plan-wide kernels + two one-block kernels per A-ADMM iteration) against the oracle's
+    line-by-line restatement of Class2/warmup_class2.m"""
+    from oracle import driver as odrv
+    rs = np.random.RandomState(5)
+    p, q = weights(m, n, 6, unit)
+    mn = m * n; N = m + n
+    c = rs.random_sample(mn); l = rs.random_sample(m) + 0.1; r = rs.random_sample(n) + 0.1
+    phi = np.ones(mn) if unit else rs.random_sample(mn) + 0.5
+    mu = 0.6 * min(l.sum(), r.sum())
+    its = 12
+    u_ref, l_ref = odrv.warmup_class2(c, r, l, p, q, mu, phi, 0, its)
+    b = np.concatenate([r, l, [mu]])
+    uk = np.zeros(mn + N); lk = np.zeros(N + 1)
+    _ok(emu, emu.emu_warmup_class2(_p(c), _p(b), _p(p), _p(q), C.c_int64(m), C.c_int64(n), _p(phi), C.c_int(its), _p(uk), _p(lk)))
+    assert np.linalg.norm(uk - np.asarray(u_ref).ravel()) <= 1e-9 * np.linalg.norm(u_ref)
+    assert np.linalg.norm(lk - np.asarray(l_ref).ravel()) <= 1e-9 * np.linalg.norm(l_ref)

@@ -64,7 +64,7 @@ def test_fused_warmup_matches_oracle(gpu, oracle, m, n, gama, weights):
     assert np.linalg.norm(lam - lam2.cpu().numpy()) <= 1e-7 * np.linalg.norm(l_ref)
 
 
-@pytest.mark.parametrize("kind,size,solver", [("random", (22, 18), 4), ("grid", 6, 4), ("random", (15, 12), 3)])
+@pytest.mark.parametrize("kind,size,solver", [("random", (22, 18), 4), ("grid", 6, 4), ("random", (15, 12), 3), ("random", (20, 17), 5)])
 def test_class2_partial_ot_solve_matches_oracle(gpu, oracle, kind, size, solver):
     """Config 3 of BASELINE.json (Class2/APD_SsN_Class2.m: partial OT through AMG4POT / PCG4POT and
     the invHHt warm start): the device driver against the oracle's restatement, same inputs."""
@@ -183,3 +183,51 @@ def test_one_call_ssn_step_equals_the_operator_level_step(gpu):
     scale = float(lk_a.abs().max())
     assert float((lk_b - lk_a).abs().max()) <= 1e-13 * scale and float((lk_c.cuda() - lk_a).abs().max()) <= 1e-13 * scale
     assert float((Fk_b - Fk_a).abs().max()) <= 1e-10 * float(Fk_a.abs().max()) + 1e-14
+
+
+@pytest.mark.parametrize("m,n", [(64, 48), (45, 70)])
+def test_class2_one_call_entry_points_match_the_operator_loop(gpu, m, n):
+    """ssn_warmup_class2 / ssn_apd_ssn_class2 / ssn_ssn_step_class2 (the Class 2 script, its warm start and one SsN step as
+    single library calls over the fused PHI kernels) against the same script as a Python loop over the operators and the
+    operator-by-operator warm start (driver.APD_SsN_Class2_loop, warmup_class2_unfused, ssn_step_class2_ops)."""
+    import torch
+    drv = __import__("importlib").import_module("codes-of-ipd-ssn-amg-method_b200.driver")
+    rs = np.random.RandomState(m + n)
+    l = rs.random_sample(m) + 0.1; r = rs.random_sample(n) + 0.1
+    P = {"c": rs.random_sample(m * n), "r": r, "l": l, "p": np.ones(m), "q": np.ones(n), "phi": np.ones(m * n),
+         "mu": 0.6 * min(r.sum(), l.sum())}
+    a = (P["c"], P["r"], P["l"], P["p"], P["q"], P["mu"], P["phi"])
+    u1, l1 = drv.warmup_class2(*a, 0.0, 60)
+    u2, l2 = drv.warmup_class2_unfused(*a, 0.0, 60)
+    assert float(torch.linalg.norm(u1 - u2)) <= 1e-9 * float(torch.linalg.norm(u2))
+    assert float(torch.linalg.norm(l1 - l2)) <= 1e-7 * float(torch.linalg.norm(l2))
+    # the loop from the trivial start (the warm start's closed form is ill conditioned, tests/test_gpu_traces.py)
+    gpu.rng_reset()
+    one = gpu.APD_SsN_Class2(*a, warm_maxit=0)
+    gpu.rng_reset()
+    seen = []
+    loop = drv.APD_SsN_Class2_loop(*a, warm_maxit=0, on_ssn_step=lambda st: seen.append(st["k"]))
+    assert one["stats"]["converged"] and loop["stats"]["converged"] and abs(one["outer_its"] - loop["outer_its"]) <= 1
+    # the two callers sum their dot products in different orders: decisions are pinned while |F| is far above SsN_Tol1
+    K = 20
+    i1, i2 = one["stats"]["ssn_its"], loop["stats"]["ssn_its"]
+    assert i1[:K] == i2[:K] and abs(sum(i1) - sum(i2)) <= 4 and len(seen) == sum(i2)
+    assert np.allclose(one["fxk"][:K], loop["fxk"][:K], rtol=1e-9, atol=1e-12)
+    assert abs(one["fxk"][-1] - loop["fxk"][-1]) <= 1e-6 * max(abs(loop["fxk"][-1]), 1e-3)
+    K1, K2 = np.array(one["KKT"][:K]), np.array(loop["KKT"][:K])
+    assert np.allclose(K1, K2, rtol=1e-6, atol=1e-10)
+    ns = sum(i2[:K])
+    assert [s_[:6] for s_ in one["stats"]["steps"][:ns]] == [tuple(int(v) for v in s_[:6]) for s_ in loop["stats"]["steps"][:ns]]
+    assert np.allclose(one["lk"].cpu().numpy(), loop["lk"].cpu().numpy(), rtol=1e-4, atol=1e-6)
+    host = gpu.APD_SsN_Class2(*a, warm_maxit=0, host_call=True, max_outer=3)
+    assert np.allclose(host["fxk"], one["fxk"][:4], rtol=1e-12) and isinstance(host["uk"], np.ndarray)
+    # one SsN step at the trivial state
+    Pt = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)).cuda() if not np.isscalar(v) else v for k, v in P.items()}
+    st = drv.class2_trivial_state(Pt)
+    gpu.rng_reset(); lk_a, Fk_a, ia = drv.ssn_step_class2(st)
+    gpu.rng_reset(); lk_b, Fk_b, ib = drv.ssn_step_class2_ops(st)
+    assert ia["E"] == ib["E"] and ia["ll"] == ib["ll"] and ia["itamg"] == ib["itamg"] and ia["nnzH"] == ib["nnzH"]
+    assert torch.allclose(lk_a, lk_b, rtol=1e-11, atol=1e-13) and torch.allclose(Fk_a, Fk_b, rtol=1e-9, atol=1e-12)
+    hst = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in st.items()}
+    gpu.rng_reset(); lk_h, Fk_h, ih = drv.ssn_step_class2(hst, host_call=True)
+    assert not lk_h.is_cuda and torch.equal(lk_h, lk_a.cpu()) and torch.equal(Fk_h, Fk_a.cpu())
