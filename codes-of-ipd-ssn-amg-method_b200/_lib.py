@@ -80,6 +80,7 @@ SIGNATURES = {
     "ssn_set_device_setup": (_int, [_vp, _int]),
     "ssn_set_fused_setup": (_int, [_vp, _int]),
     "ssn_set_cluster_solve": (_int, [_vp, _int]),
+    "ssn_set_spgemm_slab_limit": (_int, [_vp, _i64]),
     "ssn_debug_barrier_bench": (_int, [_vp, _int, _int, _pdbl]),
     "ssn_kernel_timer": (_int, [_vp, _int]),
     "ssn_kernel_timer_read": (_int, [_vp, _pdbl, _pi64]),

@@ -950,6 +950,11 @@ def set_cluster_solve(enable=True):
     context().call("ssn_set_cluster_solve", int(enable) if not isinstance(enable, bool) else (2 if enable else 0))
 
 
+def set_spgemm_slab_limit(limit=1 << 30):
+    """Intermediate-size limit above which a sparse product is formed in slabs of rows (``ssn_set_spgemm_slab_limit``)."""
+    context().call("ssn_set_spgemm_slab_limit", int(limit))
+
+
 def set_device_setup(enable=True):
     """PCG's SSOR / IC(0) factors and dependency levels built on the device (``True``) or on the host (default)."""
     ctx = context(); ctx.call("ssn_set_device_setup", 1 if enable else 0)

@@ -153,6 +153,11 @@ int ssn_set_persistent(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->pe
 int ssn_set_device_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->device_setup = on != 0; return SSN_OK; }
 int ssn_set_fused_setup(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->fused_setup = on != 0; return SSN_OK; }
 int ssn_set_cluster_solve(ssn_ctx* c, int on) { if (!c) return SSN_E_INVALID; c->cluster_solve = on != 0; c->dsm_solve = on != 1; return SSN_OK; }
+int ssn_set_spgemm_slab_limit(ssn_ctx* c, int64_t limit) {
+    if (!c || limit < 1 || limit > ((int64_t)1 << 30)) return SSN_E_INVALID;
+    c->spgemm_slab_limit = limit;
+    return SSN_OK;
+}
 int ssn_set_dense_tail(ssn_ctx* c, int dense_tail, int dense_max_n) {
     if (!c) return SSN_E_INVALID;
     c->dense_tail = dense_tail != 0;

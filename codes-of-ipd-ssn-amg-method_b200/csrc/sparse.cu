@@ -814,6 +814,65 @@ __global__ void gather_rowptr_kernel(int nrows, int nwin, const int* __restrict_
 
 }  // namespace
 
+namespace {
+// 64-bit sum of the upper bounds of a row's work items
+__global__ void row_ub64_kernel(int nrows, int nwin, const int* __restrict__ ub, long long* __restrict__ rowub) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    long long s = 0;
+    for (int w = 0; w < nwin; ++w) s += ub[(size_t)i * nwin + w];
+    rowub[i] = s;
+}
+__global__ void shift_ptr_kernel(int nrows, const int* __restrict__ src, int base, int* __restrict__ dst, int last) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nrows) dst[i] = src[i] + base;
+    if (last && i == nrows) dst[nrows] = src[nrows] + base;
+}
+}  // namespace
+
+// C = A*B for a product whose intermediate upper bound exceeds ssn_ctx::spgemm_slab_limit: consecutive slabs of rows of A,
+// each small enough for 32-bit offsets, multiplied on their own (same kernels, same per-row arithmetic) and concatenated.
+static Csr spgemm_row_slabs(ssn_ctx* c, const CsrView& A, const CsrView& B, const int* ub, int nwin) {
+    const int nrows = A.nrows;
+    Buf<long long> rowub(c, nrows);
+    SSN_LAUNCH(c, row_ub64_kernel, cdiv(nrows, 256), 256, 0, nrows, nwin, ub, rowub.p);
+    std::vector<long long> h(nrows);
+    SSN_CUDA(cudaMemcpyAsync(h.data(), rowub.p, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, c->stream));
+    SSN_CUDA(cudaStreamSynchronize(c->stream));
+    const int saved_site = c->spgemm_site;
+    c->spgemm_site = -1;                                    // the slabs are not call sites of the hierarchy
+    struct Restore { ssn_ctx* c; int s; ~Restore() { c->spgemm_site = s; } } restore{c, saved_site};
+    std::vector<Csr> parts; std::vector<int> first;
+    int64_t total = 0;
+    for (int r0 = 0; r0 < nrows;) {
+        int r1 = r0 + 1; long long acc = h[r0];
+        while (r1 < nrows && acc + h[r1] < c->spgemm_slab_limit) acc += h[r1++];
+        CsrView Av = A;
+        Av.nrows = r1 - r0; Av.ptr = A.ptr + r0;
+        Av.nnz = std::max<int64_t>(1, (int64_t)((double)A.nnz * (double)(r1 - r0) / (double)nrows));   // heuristics only
+        parts.push_back(spgemm(c, Av, B));
+        first.push_back(r0);
+        total += parts.back().nnz;
+        SSN_REQUIRE(total < ((int64_t)1 << 31), SSN_E_TOO_LARGE, "spgemm: the product itself exceeds the int32 index range");
+        r0 = r1;
+    }
+    Csr C; C.c = c; C.nrows = nrows; C.ncols = B.ncols; C.nnz = total;
+    C.ptr.alloc(c, (size_t)nrows + 1); C.idx.alloc(c, (size_t)total); C.val.alloc(c, (size_t)total);
+    int64_t base = 0;
+    for (size_t k = 0; k < parts.size(); ++k) {
+        Csr& P = parts[k];
+        const int rows = (int)P.nrows, last = (k + 1 == parts.size()) ? 1 : 0;
+        SSN_LAUNCH(c, shift_ptr_kernel, cdiv(rows + 1, 256), 256, 0, rows, P.ptr.p, (int)base, C.ptr.p + first[k], last);
+        if (P.nnz) {
+            SSN_CUDA(cudaMemcpyAsync(C.idx.p + base, P.idx.p, sizeof(int) * P.nnz, cudaMemcpyDeviceToDevice, c->stream));
+            SSN_CUDA(cudaMemcpyAsync(C.val.p + base, P.val.p, sizeof(double) * P.nnz, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        base += P.nnz;
+    }
+    SSN_CUDA(cudaStreamSynchronize(c->stream));             // the parts are released on return
+    return C;
+}
+
 Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     SSN_REQUIRE(A.ncols == B.nrows, SSN_E_INVALID, "spgemm: inner dimensions differ");
     const int nrows = A.nrows, ncolsB = B.ncols;
@@ -881,11 +940,13 @@ Csr spgemm(ssn_ctx* c, const CsrView& A, const CsrView& B) {
     const int small_ok = (ncolsB < (1 << 23)) ? 1 : 0;     // (column << 8 | t) must fit 32 bits
     SSN_LAUNCH(c, spgemm_ub_kernel, cdiv(nitems * 32, 256), 256, 0, nrows, A.ptr, A.idx, B.ptr, splitp, W, nwin, ncolsB, small_ok,
                ub.p, big_list.p, counters.p);
-    if ((int64_t)nrows * (int64_t)ncolsB >= ((int64_t)1 << 31)) {      // the int32 scan could wrap: check in 64 bit
+    if ((int64_t)nrows * (int64_t)ncolsB >= c->spgemm_slab_limit && nrows > 1) {   // the int32 scan could wrap: check in 64 bit
         Buf<unsigned long long> tot(c, 1); tot.zero();
         SSN_LAUNCH(c, sum_int64_kernel, 64, 256, 0, ub.p, nitems, tot.p);
         const unsigned long long t = read_scalar(c, tot.p);
-        SSN_REQUIRE(t < (1ull << 31), SSN_E_TOO_LARGE, "spgemm: intermediate product exceeds the int32 index range");
+        // more intermediate entries than 32-bit offsets (or the workspace) allow: the product is formed slab of rows by
+        // slab of rows -- each slab a product of its own, bit for bit the rows of the whole product -- and concatenated
+        if ((int64_t)t >= c->spgemm_slab_limit) return spgemm_row_slabs(c, A, B, ub.p, nwin);
     }
     const int64_t ub_total = scan_counts_to_ptr(c, ub, ubptr, nitems);
     Buf<int> tidx(c, (size_t)ub_total); Buf<double> tval(c, (size_t)ub_total);

@@ -161,6 +161,10 @@ SSN_API int  ssn_set_fused_setup(ssn_ctx *ctx, int on);
  * distributed shared memory; 1: inside one cluster with the vectors in global memory (env SSN_DSM_SOLVE=0); 0: always as
  * the grid-wide kernel. */
 SSN_API int  ssn_set_cluster_solve(ssn_ctx *ctx, int on);
+/* Sparse products (ssn_spgemm, the Galerkin products of the AMG setup) whose intermediate upper bound exceeds `limit`
+ * entries are formed slab of rows by slab of rows and concatenated (same rows bit for bit).  Default and maximum 2^30:
+ * what 32-bit offsets into the intermediate arrays allow; smaller values bound the workspace (12 bytes per entry). */
+SSN_API int  ssn_set_spgemm_slab_limit(ssn_ctx *ctx, int64_t limit);
 /* cycles per grid-wide barrier of the persistent solve kernel: which = 0 cooperative-groups grid.sync(),
  * 1 = the library's own barrier (development aid) */
 SSN_API int  ssn_debug_barrier_bench(ssn_ctx *ctx, int iters, int which, double *cycles_per_barrier);

@@ -214,6 +214,7 @@ struct ssn_ctx {
     int small_scan_max = 1 << 14;
     bool device_setup = true;
     static constexpr int kSpgemmSites = 64;
+    int64_t spgemm_slab_limit = (int64_t)1 << 30;   // sparse products with more intermediate entries are formed in slabs of rows
     unsigned spgemm_epoch = 0;
     int spgemm_site = -1;                 // >= 0 inside amg_setup: index of the next sparse product of this hierarchy
     unsigned char spgemm_big[kSpgemmSites] = {0};   // 1: the optimistic warp-path attempt of that product failed last time

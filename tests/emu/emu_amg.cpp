@@ -94,6 +94,7 @@ int emu_rng_reset() { return guarded([&] { ssn::rng_reset(ctx(), 5489u); }); }
 int64_t emu_rng_drawn() { return ctx()->rng_drawn; }
 int emu_rand(int64_t count, double* out) { return guarded([&] { ssn::rng_rand(ctx(), count, out); }); }
 
+void emu_set_spgemm_slab(int64_t limit) { ctx()->spgemm_slab_limit = limit; }
 int emu_spgemm(int64_t ar, int64_t ac, int64_t annz, const int* ap, const int* ai, const double* av,
                int64_t br, int64_t bc, int64_t bnnz, const int* bp, const int* bi, const double* bv) {
     return guarded([&] { g_out[0] = ssn::spgemm(ctx(), view(ar, ac, annz, ap, ai, av), view(br, bc, bnnz, bp, bi, bv)); });

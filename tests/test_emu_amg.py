@@ -245,6 +245,20 @@ def test_scan_paths_agree(emu, oracle):
     assert_same_matrix(spgemm(emu, A, B), ref(A, B), "A*B, one-block scans")
 
 
+def test_spgemm_in_slabs_of_rows(emu, oracle):
+    """A product whose intermediate upper bound exceeds ssn_ctx::spgemm_slab_limit (2^30 entries in production: the early
+    SsN steps of the 256x256 grids) is formed slab of rows by slab of rows: same matrix bit for bit."""
+    from oracle.amg import spgemm as ref
+    A = rand_sparse(120, 90, 0.3, 1); B = rand_sparse(90, 150, 0.3, 2)
+    want = ref(A, B)
+    try:
+        for limit in (4000, 700, 1):                       # a few slabs, many slabs, one row per slab
+            emu.emu_set_spgemm_slab(C.c_int64(limit))
+            assert_same_matrix(spgemm(emu, A, B), want, f"A*B in slabs (limit {limit})")
+    finally:
+        emu.emu_set_spgemm_slab(C.c_int64(1 << 30))
+
+
 _slow = __import__("emu_build").slow
 @pytest.mark.parametrize("m,n,density,isnsp,cycle,bigph,noreg", [(90, 70, 0.05, 1, "w", 1, 0), pytest.param(90, 70, 0.05, 1, "w", 1, 1, marks=_slow),
                                                                   pytest.param(90, 70, 0.05, 0, "v", 1, 0, marks=_slow),

@@ -56,6 +56,21 @@ def test_spgemm_fixed_order_bit_exact(gpu, oracle, shape):
     assert_same_matrix(gpu.spgemm(A, B), spgemm(A, B), what="A*B")
 
 
+def test_spgemm_in_slabs_of_rows(gpu, oracle):
+    """ssn_set_spgemm_slab_limit: products above the limit (2^30 intermediate entries by default) are formed slab of rows by
+    slab of rows; the same matrix bit for bit, through both numeric kernels and the hierarchy's Galerkin products."""
+    from oracle.amg import spgemm
+    cases = [(rand_sparse(300, 200, 0.2, 1), rand_sparse(200, 400, 0.2, 2)), (rand_sparse(40, 3000, 0.1, 3), rand_sparse(3000, 20000, 0.1, 4))]
+    try:
+        for A, B in cases:
+            want = spgemm(A, B)
+            for limit in (1 << 18, 1 << 14):
+                gpu.set_spgemm_slab_limit(limit)
+                assert_same_matrix(gpu.spgemm(A, B), want, what=f"A*B in slabs (limit {limit})")
+    finally:
+        gpu.set_spgemm_slab_limit(1 << 30)
+
+
 def test_spgemm_identity_runs_and_cancellation(gpu, oracle):
     from oracle.amg import spgemm
     n = 700
