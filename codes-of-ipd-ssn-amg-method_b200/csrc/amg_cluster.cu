@@ -184,9 +184,42 @@ __device__ __forceinline__ double z_sum1_read(ZTeam& G) {
     ++G.flip;
     return s0;
 }
+// The pull form of the same sum (same order of additions, same value): the CTA's sum goes into its OWN slot (a local
+// store: the release of the cluster barrier has no remote store to drain), after the barrier lanes 0..15 of warp 0 fetch
+// the 16 slots with one ld.shared::cluster each and the total is handed to the other warps through shared memory.
+__device__ __forceinline__ double z_sum1_pull(ZTeam& G, double a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = kZT / 32;
+    a = warp_sum(a);
+    double* sm = reinterpret_cast<double*>(G.dsm) + (G.flip & 1) * 64;
+    if (lane == 0) sm[w] = a;
+    __syncthreads();
+    double* sl = reinterpret_cast<double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
+    if (threadIdx.x == 0) {
+        double ta = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ta += sm[i];
+        sl[0] = ta;
+    }
+    z_barrier();
+    if (w == 0) {
+        const double v = (lane < G.ncta) ? z_ld(z_map(z_local(sl), lane)) : 0.0;
+        double s0 = 0.0;
+        for (int r = 0; r < G.ncta; ++r) s0 += __shfl_sync(0xffffffffu, v, r);
+        if (lane == 0) sl[1] = s0;
+    }
+    __syncthreads();
+    const double tot = sl[1];
+    ++G.flip;
+    return tot;
+}
 __device__ __forceinline__ double z_sum1(ZTeam& G, double a) {
+#ifdef SSN_ZSUM_PULL
+    return z_sum1_pull(G, a);
+#else
     z_sum1_post(G, a);
     return z_sum1_read(G);
+#endif
 }
 
 // For the local rows [l0, l1) of level L (2^lt lanes per row): s = sum over the row's entries of M of value * v[column],
@@ -675,7 +708,7 @@ namespace {
 //   10 z_sum1   11 z_barrier   12 NG gathers through ld.shared::cluster, all in flight, + barrier
 //   13 the same gathers in dependent batches of 4   14 NG gathers from global memory (ld.global.cg) + barrier
 //   15 NG gathers from the CTA's own shared memory + barrier   16 z_sum1 without its cluster barrier's remote stores
-//      (block reduction + barrier)   17 local store + relaxed-arrive barrier
+//      (block reduction + barrier)   17 local store + relaxed-arrive barrier   18 z_sum1_pull
 // ng = gathers per thread (<= 16); the gathered vector has 16 * 1024 doubles, indices pseudo-random
 __global__ void __launch_bounds__(kZT, 1) dsm_bench_kernel(double* gbuf, int iters, int which, int ng, long long* cycles_out) {
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -694,6 +727,7 @@ __global__ void __launch_bounds__(kZT, 1) dsm_bench_kernel(double* gbuf, int ite
     double acc = 0.0;
     for (int it = 0; it < iters; ++it) {
         if (which == 10) acc += z_sum1(G, acc + threadIdx.x);
+        else if (which == 18) acc += z_sum1_pull(G, acc + threadIdx.x);
         else if (which == 11) z_barrier();
         else if (which == 12 || which == 13) {
             double xv[16];

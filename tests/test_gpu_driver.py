@@ -211,7 +211,8 @@ def test_class2_one_call_entry_points_match_the_operator_loop(gpu, m, n):
     # the two callers sum their dot products in different orders: decisions are pinned while |F| is far above SsN_Tol1
     K = 20
     i1, i2 = one["stats"]["ssn_its"], loop["stats"]["ssn_its"]
-    assert i1[:K] == i2[:K] and abs(sum(i1) - sum(i2)) <= 4 and len(seen) == sum(i2)
+    L = min(len(i1), len(i2))
+    assert i1[:K] == i2[:K] and max(abs(a_ - b_) for a_, b_ in zip(i1[:L], i2[:L])) <= 3 and len(seen) == sum(i2)   # late steps: |F| at the rounding level
     assert np.allclose(one["fxk"][:K], loop["fxk"][:K], rtol=1e-9, atol=1e-12)
     assert abs(one["fxk"][-1] - loop["fxk"][-1]) <= 1e-6 * max(abs(loop["fxk"][-1]), 1e-3)
     K1, K2 = np.array(one["KKT"][:K]), np.array(loop["KKT"][:K])

@@ -185,8 +185,13 @@ def test_pot_bordered_solves(gpu, oracle):
     z2_ref, *_ = oracle.PCG4POT(pd, o)
     z2, *_ = gpu.PCG4POT(pd, o)
     assert np.linalg.norm(z2 - z2_ref) <= 1e-7 * np.linalg.norm(z2_ref)
-    with pytest.raises(gpu.SsnError):
-        gpu.AMG4POT(pd, AMG_OPTS, "twogrid")
+    # str = 'twogrid' (Class2/AMG4POT.m:48-51; inner_solver = 5 of the Class 2 script): the two solves through Hybrid_twogrid
+    oracle.rng_reset(); gpu.rng_reset()
+    z3_ref, it3_ref, _, info3_ref = oracle.AMG4POT(pd, dict(AMG_OPTS, maxit=40, smoth=10), "twogrid")
+    z3, it3, _, info3 = gpu.AMG4POT(pd, dict(AMG_OPTS, maxit=40, smoth=10), "twogrid")
+    assert list(info3) == list(info3_ref) and it3 == it3_ref
+    assert np.linalg.norm(z3 - z3_ref) <= 1e-7 * np.linalg.norm(z3_ref)
+    assert np.linalg.norm(He @ z3 - pd["z"]) <= 1e-8 * np.linalg.norm(pd["z"])
 
 
 @pytest.mark.parametrize("tag", ["k12_s2", "k30_s1", "k40_s2", "k80_s2"])

@@ -1,7 +1,7 @@
 """Hybrid_AMG on a synthetic SsN system with the structure of an early-phase grid OT step: the active set is
 s_ij = 1 iff |x_i - y_j| <= r grid cells (a disc neighbourhood), p = q = 1, bk1 = 0.5, tk = 2 (outer iteration 1).
 Development aid: reproduces large (n+m = 131072) systems on ONE GPU without holding the 256 x 256 plan.
-Usage: python tools/amg_synth.py g r [seed]"""
+Usage: python tools/amg_synth.py g r [seed [log2 of the sparse-product slab limit]]"""
 import os
 import sys
 import time
@@ -14,6 +14,8 @@ import ssnamg  # noqa: E402
 
 def main():
     g = int(sys.argv[1]); r = float(sys.argv[2]); seed = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    if len(sys.argv) > 4:
+        ssnamg.set_spgemm_slab_limit(1 << int(sys.argv[4]))
     m = n = g * g
     idx = torch.arange(m, device="cuda")
     xa, xb = torch.div(idx, g, rounding_mode="floor").float(), (idx % g).float()

@@ -17,7 +17,7 @@ for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"
     print(f"{name:38s}: {v.value:8.0f} cycles per iteration", flush=True)
 
 # building blocks of a pass of the DSMEM cluster solve kernel (amg_cluster.cu): 16 CTAs x 512 threads
-for which, name in ((10, "z_sum1 (cluster-wide sum of one double)"), (11, "z_barrier"), (16, "block reduction + barrier"), (17, "store + relaxed-arrive barrier"),
+for which, name in ((10, "z_sum1 (cluster-wide sum of one double)"), (18, "z_sum1_pull (own slot + 16 remote loads)"), (11, "z_barrier"), (16, "block reduction + barrier"), (17, "store + relaxed-arrive barrier"),
                     (412, "4 DSMEM gathers + barrier"), (812, "8 DSMEM gathers + barrier"), (1612, "16 DSMEM gathers + barrier"),
                     (813, "8 DSMEM gathers, batches of 4"), (1613, "16 DSMEM gathers, batches of 4"),
                     (414, "4 L2 gathers + store + barrier"), (814, "8 L2 gathers + store + barrier"), (1614, "16 L2 gathers + store + barrier"),
