@@ -86,6 +86,7 @@ struct ssn_ctx {
     int64_t cluster_max_nnz = (int64_t)1 << 20;   // SSN_CLUSTER_MAXNNZ: larger hierarchies (explicit levels) use the grid-wide kernel
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
+    bool plan_stage = true;               // SSN_PLAN_STAGE=0: the plan-wide reduction kernels load straight into registers (no cp.async staging)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
     double ls_last_density = -1.0;        // share of the plan's entries that survived the screen in the last screened batch (< 0: none yet)
     bool device_setup = true;             // SSN_DEVICE_SETUP=0: SSOR / IC(0) factors and their levels built on the host instead of the device (trifactor.cu)
@@ -290,6 +291,15 @@ void stable_sort_pairs(ssn_ctx* c, const int* keys_in, int* keys_out, const int*
                        int* vals_out, int64_t n, int key_limit);
 
 // ---- device helpers ----
+// 16-byte asynchronous global -> shared copies (LDGSTS): the staging buffers of the plan-wide kernels.  A thread waits for
+// its OWN copies (cp_async_wait<N>: all but the N most recent groups) and reads back only what it copied itself.
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,6 +11,7 @@
 //   in shared memory until the block combines its 8 strips.  Partials go to
 //   rowpart[chunk][m] / colpart[group][n]; a tiny finish kernel sums them in fixed order.
 #include "common.cuh"
+#include <type_traits>
 #include "plan_ops.cuh"
 #include "sparse.cuh"
 
@@ -24,6 +25,8 @@ constexpr int kStripRows = 128;
 constexpr int kGroupRows = kWarps * kStripRows;   // 1024
 constexpr int kMaxChunkCols = 512;
 constexpr int kMaxTrials = 8;
+constexpr size_t kStageBytes = (size_t)kWarps * 2 * 256 * sizeof(double2);        // per-warp double buffer of 4-column batches: 64 KB per block
+constexpr int kStageSmemMax = (int)(kWarps * kMaxChunkCols * sizeof(double) + kStageBytes);
 
 struct PlanArgs {
     const double* x;        // MODE_AX: x ; MODE_PROX: w
@@ -43,6 +46,7 @@ struct PlanArgs {
     double* z_out;
     uint8_t* s_out;
     int want_sums;          // row/col sums wanted
+    int stage;              // 1: full strips stream through a per-warp double buffer in shared memory (cp.async)
 };
 
 enum { MODE_AX = 0, MODE_PROX = 1 };
@@ -73,10 +77,13 @@ template <bool VEC> __device__ __forceinline__ constexpr int roff(int k) { retur
 
 // One batch of 4 columns x 4 rows per lane.  `off` is the element offset of (column c, row slot 0).
 // FULL: every row and column of the batch is inside the plan (no predicates in the hot path).
-template <int MODE, bool VEC, int GM, bool FULL>
+// STAGED: the batch was copied into the lane's slots of a staging buffer (stage[(2*cc + h) * 32 + lane]) by cp.async.
+// UNITW: p == 1 and q == 1 on the block's rows and columns (every configuration the reference ships): p_i*y1_j + y2_i*q_j is
+// y1_j + y2_i and the weighted sums are plain sums bit for bit -- three fp64 operations per entry fewer.
+template <int MODE, bool VEC, int GM, bool FULL, bool STAGED = false, bool UNITW = false>
 __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_t c, int64_t c1, const bool (&rok)[4],
                                            const double (&pv)[4], const double (&y2v)[4], double (&rs)[4], double& n2,
-                                           int& cnt, double (&cs)[4], double& ps, double mu) {
+                                           int& cnt, double (&cs)[4], double& ps, double mu, const double2* stage = nullptr) {
     const size_t m = (size_t)a.m;
     constexpr bool GARR = (GM == G_VECTOR || GM == G_PHI);         // a second plan-sized array rides along
     double v[4][4];
@@ -86,7 +93,13 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
     for (int cc = 0; cc < 4; ++cc) {
         const bool cok = FULL || (c + cc < c1);
         const double* xp = a.x + off + (size_t)cc * m;
-        if (VEC) {
+        if (STAGED) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 t = stage[(2 * cc + h) * 32 + (threadIdx.x & 31)];
+                v[cc][2 * h] = t.x; v[cc][2 * h + 1] = t.y;
+            }
+        } else if (VEC) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 double2 t = make_double2(0.0, 0.0);
@@ -111,8 +124,8 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
         if (MODE == MODE_AX) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                csum = fma(v[cc][k], pv[k], csum);
-                rs[k] = fma(v[cc][k], qj, rs[k]);
+                if (UNITW) { csum += v[cc][k]; rs[k] += v[cc][k]; }
+                else { csum = fma(v[cc][k], pv[k], csum); rs[k] = fma(v[cc][k], qj, rs[k]); }
             }
         } else {
             const double y1j = cok ? __ldg(a.lam + c + cc) : 0.0;
@@ -121,7 +134,7 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
             for (int k = 0; k < 4; ++k) {
                 // z = (1/tk) * (w - (p_i*y1_j + y2_i*q_j)), rounded like the reference expression
                 // `1/tk*(wk-Aty(lk,p,q))` (mul, mul, add, sub, mul; no FMA contraction).
-                double aty = __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
+                double aty = UNITW ? __dadd_rn(y1j, y2v[k]) : __dadd_rn(__dmul_rn(pv[k], y1j), __dmul_rn(y2v[k], qj));
                 // Class 2: Htlk = Aty(lk(1:m+n),p,q) + lk(m+n+1)*phi                       APD_SsN_Class2.m:124,138
                 if (GM == G_PHI) aty = __dadd_rn(aty, __dmul_rn(mu, g[GARR ? cc : 0][k]));
                 const double z = __dmul_rn(a.inv_tk, __dsub_rn(v[cc][k], aty));
@@ -141,7 +154,10 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
                 // ||z||^2 - ||z - prox(z)||^2 = sum prox(z)*(2z - prox(z)) for finite capacities (prob = 3)
                 n2 = (GM == G_INF || GM == G_PHI) ? fma(pz, pz, n2) : fma(pz, __dsub_rn(__dadd_rn(z, z), pz), n2);
                 if (GM == G_PHI) ps = fma(g[GARR ? cc : 0][k], pz, ps);                   // phi'*prox(z)
-                if (a.want_sums) { csum = fma(pz, pv[k], csum); rs[k] = fma(pz, qj, rs[k]); }
+                if (a.want_sums) {
+                    if (UNITW) { csum += pz; rs[k] += pz; }
+                    else { csum = fma(pz, pv[k], csum); rs[k] = fma(pz, qj, rs[k]); }
+                }
             }
             if (a.prox_out || a.z_out || a.s_out) {
                 if (cok) {
@@ -177,7 +193,7 @@ __device__ __forceinline__ void plan_batch(const PlanArgs& a, size_t off, int64_
 
 template <int MODE, bool VEC, int GM>
 __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs a) {
-    extern __shared__ double colbuf[];                 // [kWarps][cols_per_chunk]
+    extern __shared__ __align__(16) double colbuf[];   // [kWarps][cols_per_chunk], then (a.stage) [kWarps][2 stages][256] double2
     __shared__ double red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x, group = blockIdx.y;
@@ -205,16 +221,60 @@ __global__ void __launch_bounds__(kThreads, 2) plan_reduce_kernel(const PlanArgs
     size_t off = (size_t)c0 * (size_t)m + (size_t)row0;
     const size_t step = 4 * (size_t)m;
 
-    for (int64_t c = c0; c < c1; c += 4, off += step) {
-        double cs[4];
-        if (strip_full && c + 4 <= c1) plan_batch<MODE, VEC, GM, true>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
-        else                           plan_batch<MODE, VEC, GM, false>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
-        if (a.want_sums) {
-            const double tot = butterfly4(cs[0], cs[1], cs[2], cs[3], lane);
-            const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-            if ((lane & 7) == 0 && (c + idx) < c1) colbuf[warp * cpc + (int)(c - c0) + idx] = tot;
-        }
+    // unit weights on this block's rows and columns?  (block-uniform; decided from the block's own slices of p and q)
+    bool unitw;
+    {
+        bool u = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u = u && (!rok[k] || pv[k] == 1.0);
+        for (int64_t j = c0 + threadIdx.x; j < c1; j += kThreads) u = u && (a.q[j] == 1.0);
+        unitw = __syncthreads_and(u ? 1 : 0) != 0;
     }
+    auto run = [&](auto unit_tag) {
+        constexpr bool UW = decltype(unit_tag)::value;
+        auto park = [&](int64_t c, const double (&cs)[4]) {     // column partials of a batch -> the block's buffer
+            if (a.want_sums) {
+                const double tot = butterfly4(cs[0], cs[1], cs[2], cs[3], lane);
+                const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+                if ((lane & 7) == 0 && (c + idx) < c1) colbuf[warp * cpc + (int)(c - c0) + idx] = tot;
+            }
+        };
+        int64_t c = c0;
+        constexpr bool kCanStage = VEC && GM != G_VECTOR && GM != G_PHI;
+        if (kCanStage && a.stage && strip_full) {
+            // Full strips: the complete 4-column batches stream through a per-warp double buffer in shared memory.  The copies of
+            // batch b+1 (8 x 16 B per lane, cp.async) are in flight for the whole of the arithmetic of batch b, so a warp keeps 4 KB
+            // outstanding all the time instead of only while it waits -- what the register-loading form loses once the per-entry
+            // arithmetic is no longer small against the memory latency (fused residual: 0.82 of the streaming rate of a bare
+            // read of the plan at the same tiling; tools/micro/ldst256.cu).
+            double2* st = reinterpret_cast<double2*>(colbuf + (size_t)kWarps * cpc) + (size_t)warp * 512;
+            const int nb = (int)((c1 - c0) >> 2);
+            auto issue = [&](int b) {
+                const double* xp = a.x + off + (size_t)b * step;
+                double2* dst = st + (b & 1) * 256 + lane;
+    #pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+    #pragma unroll
+                    for (int h = 0; h < 2; ++h) cp_async16(dst + (2 * cc + h) * 32, xp + (size_t)cc * m + roff<VEC>(2 * h));
+                cp_async_commit();
+            };
+            if (nb > 0) issue(0);
+            for (int b = 0; b < nb; ++b, c += 4) {
+                if (b + 1 < nb) { issue(b + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+                double cs[4];
+                plan_batch<MODE, VEC, GM, true, true, UW>(a, off + (size_t)b * step, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu, st + (b & 1) * 256);
+                park(c, cs);
+            }
+            off += (size_t)nb * step;
+        }
+        for (; c < c1; c += 4, off += step) {
+            double cs[4];
+            if (strip_full && c + 4 <= c1) plan_batch<MODE, VEC, GM, true, false, UW>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
+            else                           plan_batch<MODE, VEC, GM, false, false, UW>(a, off, c, c1, rok, pv, y2v, rs, n2, cnt, cs, ps, mu);
+            park(c, cs);
+        }
+    };
+    if (unitw) run(std::true_type()); else run(std::false_type());
     if (a.want_sums) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -1239,10 +1299,11 @@ __global__ void __launch_bounds__(1024) pot_apd_slack_kernel(const PotApdSlack a
 
 struct Tiling { int groups, chunks, cpc; };
 
-Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n) {
+Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n, int waves = 2) {
     Tiling t;
     t.groups = cdiv(m, kGroupRows);
-    const int64_t target = (int64_t)c->num_sms * 2 * 2;          // two waves at 2 blocks / SM
+    const int64_t target = (int64_t)c->num_sms * 2 * waves;      // `waves` waves at 2 blocks / SM (the reductions: two -- their
+                                                                 // partial arrays grow with the number of chunks)
     int64_t chunks = target / t.groups; if (chunks < 1) chunks = 1;
     int64_t cpc = (n + chunks - 1) / chunks;
     cpc = ((cpc + 3) / 4) * 4;
@@ -1375,16 +1436,23 @@ void plan_ax(ssn_ctx* c, const double* x, const double* p, const double* q, int6
     a.cols_per_chunk = t.cpc; a.num_chunks = t.chunks; a.num_groups = t.groups;
     a.rowpart = rowpart; a.colpart = colpart; a.want_sums = 1;
     const dim3 grid(t.chunks, t.groups);
-    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
-    if (vec_ok(x, m)) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, true, G_INF>), grid, kThreads, smem, a);
-    else              SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, false, G_INF>), grid, kThreads, smem, a);
+    const bool vec = vec_ok(x, m);
+    a.stage = 0;                                            // two FMAs per entry: the register-loading form is the faster one (measured)
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double) + (a.stage ? kStageBytes : 0);
+    if (vec) {
+        static bool attr = false;
+        if (!attr) { SSN_CUDA(cudaFuncSetAttribute((plan_reduce_kernel<MODE_AX, true, G_INF>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemMax)); attr = true; }
+        SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, true, G_INF>), grid, kThreads, smem, a);
+    } else SSN_LAUNCH(c, (plan_reduce_kernel<MODE_AX, false, G_INF>), grid, kThreads, smem, a);
     SSN_LAUNCH(c, plan_finish_kernel, cdiv(m + n, 256), 256, 0, rowpart.p, colpart.p, nullptr, t.chunks,
                t.groups, m, n, 0, y, nullptr);
 }
 
 void plan_aty(ssn_ctx* c, const double* y, const double* p, const double* q, int64_t m, int64_t n, double* z) {
     SSN_REQUIRE(m > 0 && n > 0 && y && p && q && z, SSN_E_INVALID, "Aty: bad arguments");
-    const Tiling t = plan_tiling(c, m, n);
+    // a store-only kernel has no partial arrays: 8 waves of short blocks (a bare write of the plan at this tiling: 6.27 TB/s
+    // with 2 waves, 6.98 TB/s with 8 on a B200; tools/micro/ldst256.cu)
+    const Tiling t = plan_tiling(c, m, n, 8);
     const dim3 grid(t.chunks, t.groups);
     if (vec_ok(z, m)) SSN_LAUNCH(c, (aty_kernel<true>), grid, kThreads, 0, y, p, q, m, n, t.cpc, z);
     else              SSN_LAUNCH(c, (aty_kernel<false>), grid, kThreads, 0, y, p, q, m, n, t.cpc, z);
@@ -1404,10 +1472,19 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
     a.rowpart = rowpart.p; a.colpart = colpart.p; a.scalpart = scalpart.p;
     a.prox_out = prox_out; a.z_out = z_out; a.s_out = s_out; a.want_sums = axp_out ? 1 : 0;
     const dim3 grid(t.chunks, t.groups);
-    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double);
     bool vec = vec_ok(w, m) && (!gama || vec_ok(gama, m)) && (!prox_out || vec_ok(prox_out, m)) &&
                (!z_out || vec_ok(z_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
     const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
+    a.stage = (vec && gm != G_VECTOR && c->plan_stage) ? 1 : 0;
+    const size_t smem = (size_t)kWarps * t.cpc * sizeof(double) + (a.stage ? kStageBytes : 0);
+    if (a.stage) {
+        static bool attr = false;
+        if (!attr) {
+            SSN_CUDA(cudaFuncSetAttribute((plan_reduce_kernel<MODE_PROX, true, G_INF>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemMax));
+            SSN_CUDA(cudaFuncSetAttribute((plan_reduce_kernel<MODE_PROX, true, G_SCALAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStageSmemMax));
+            attr = true;
+        }
+    }
 #define SSN_PROX_LAUNCH(V, G) SSN_LAUNCH(c, (plan_reduce_kernel<MODE_PROX, V, G>), grid, kThreads, smem, a)
     {
     KernelTimer kt(c);

@@ -116,6 +116,10 @@ inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T> inline void __stcs(T* p, T v) { *p = v; }
+// cp.async stand-ins: the copy happens at once
+inline void cp_async16(void* smem, const void* g) { std::memcpy(smem, g, 16); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
 inline int __double2hiint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b >> 32); }
 inline int __double2loint(double d) { long long b; std::memcpy(&b, &d, 8); return (int)(b & 0xffffffffll); }
 inline double __hiloint2double(int hi, int lo) { const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &b, 8); return d; }
@@ -153,6 +157,7 @@ inline int __syncthreads_or(int pred) {
     b->bar.arrive_and_wait();
     return r;
 }
+inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::need_threads("__syncwarp"); emu::warp->bar.arrive_and_wait(); emu::warp->bar.arrive_and_wait(); }
 template <class T> inline T emu_exchange(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
@@ -210,6 +215,7 @@ struct ssn_ctx {
     bool no_cluster = true;
     int64_t persist_max_nnz = (int64_t)1 << 40;
     bool persist = true, dense_tail = true;
+    bool plan_stage = true;
     int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
     int small_scan_max = 1 << 14;
     bool device_setup = true;

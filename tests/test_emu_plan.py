@@ -10,7 +10,7 @@ import pytest
 
 RTOL = 1e-10
 from emu_build import slow as _slow                      # SSN_EMU_FULL=1: the cases that cost minutes of host threads
-SHAPES = [(1, 1), (7, 5), (64, 48), (45, 130)]
+SHAPES = [(1, 1), (7, 5), (64, 48), (45, 130), (258, 9)]     # (258, 9): two full strips -> the cp.async staged batches, and a ragged strip
 
 
 @pytest.fixture(scope="module")
@@ -70,7 +70,7 @@ def test_ax_and_aty(emu, oracle, m, n, unit):
     assert np.array_equal(z, oracle.Aty(yy, p, q))                       # bit for bit
 
 
-@pytest.mark.parametrize("m,n", [(7, 5), (64, 48), (45, 130)])
+@pytest.mark.parametrize("m,n", [(7, 5), (64, 48), (45, 130), (258, 9)])
 @pytest.mark.parametrize("gmode", ["inf", "scalar", "vector"])
 def test_prox_residual(emu, oracle, m, n, gmode):
     rs = np.random.RandomState(m + 3 * n)
@@ -88,6 +88,26 @@ def test_prox_residual(emu, oracle, m, n, gmode):
     assert abs(out["norm2"] - term) <= 1e-12 * float(z @ z) + 1e-300
     lite = prox_residual(emu, w, lam, p, q, tk, gama, full=False)        # line-search form: norm only
     assert abs(lite["norm2"] - out["norm2"]) <= 1e-14 * abs(out["norm2"])
+
+
+@pytest.mark.parametrize("m,n", [(64, 48), (258, 9)])
+def test_prox_residual_unit_weights(emu, oracle, m, n):
+    """p = q = 1 (every shipped configuration): the block-uniform unit-weight path of the fused residual gives the bits of the
+    general expression `1/tk*(wk - Aty(lk,p,q))`; Class 2 likewise."""
+    rs = np.random.RandomState(m + 7 * n)
+    p, q = np.ones(m), np.ones(n)
+    w = rs.standard_normal(m * n); lam = 0.5 * rs.standard_normal(m + n); tk = 0.37
+    z = 1 / tk * (w - oracle.Aty(lam, p, q))
+    out = prox_residual(emu, w, lam, p, q, tk, np.inf)
+    assert np.array_equal(out["z"], z) and np.array_equal(out["s"], z >= 0) and np.array_equal(out["prox"], np.maximum(z, 0.0))
+    assert close(out["Axprox"], oracle.Ax(np.maximum(z, 0.0), p, q))
+    N = m + n; mn = m * n
+    w2 = rs.standard_normal(mn + N); lam2 = 0.5 * rs.standard_normal(N + 1); phi = rs.random_sample(mn) + 0.5
+    z2 = 1 / tk * (w2 - np.concatenate([oracle.Aty(lam2[:N], p, q) + lam2[N] * phi, lam2[:N]]))
+    hp = np.zeros(N + 1); prox = np.zeros(mn + N); s = np.zeros(mn, np.uint8); t = np.zeros(N); scal = np.zeros(3)
+    _ok(emu, emu.emu_prox_residual_pot(_p(w2), _p(lam2), _p(p), _p(q), C.c_int64(m), C.c_int64(n), C.c_double(tk), _p(phi),
+                                       _p(hp), _p(prox), _p(s), _p(t), _p(scal)))
+    assert np.array_equal(s.astype(bool), z2[:mn] >= 0) and np.array_equal(prox, np.maximum(z2, 0.0))
 
 
 @pytest.mark.parametrize("m,n", [(7, 5), (64, 48), (45, 130)])
