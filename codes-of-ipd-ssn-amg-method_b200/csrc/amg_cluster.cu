@@ -47,7 +47,11 @@ struct ZMat { const int* rp; const int* ci; const double* cv; uint32_t* loc; };
 struct ZLevel {
     int N, Nf;                                  // Nf: rows of the first segment (bigraph level: fnode; else N)
     int rpf, rpc;                               // rows per CTA of the two segments
-    int voff, stride, xslot, bigph;             // byte offset of the level's vectors in a CTA's shared memory, bytes per vector
+    int so[5];                                  // byte offset of vector slot s in a CTA's shared memory (slot 0 = E first)
+    int xslot, bigph;
+    int hb, hcap, hn, hoff;                     // halo of the gathered slots: byte offset of the halo area inside such a slot, its capacity
+                                                // (entries), the entries in use (set by the kernel, 0: gathers go to the owners), offset of
+                                                // the source list (uint32 per entry) in shared memory
     int poff, rsbytes;                          // per-row block: int rs[nl + 2] (row bounds of A, both segments), dinv[nl], Axi[nl]
     int ltA, ltG, ltP, ltT;                     // log2(lanes per row): A (all rows), A (one segment), Pu, Td
     ZMat A, Pu, Td;                             // A_k ; Pro_{k+1} (rows of level k) ; Pro_k' (rows of level k)
@@ -62,8 +66,8 @@ struct ZArgs {
     int noreg;                                  // development aid (env SSN_DSM_NOREG=1): the smoothing loops re-read their rows every sweep
 };
 
-constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffLv = 2048, kOffProg = 4096,
-              kOffXs = 8192, kOffVec = kOffXs + kZXs * 8;
+constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffLv = 2048, kOffProg = 5120,
+              kOffXs = 9216, kOffVec = kOffXs + kZXs * 8;
 static_assert(sizeof(ZLevel) * kZMaxL <= kOffProg - kOffLv, "level table does not fit its slot");
 
 struct ZTeam {
@@ -99,21 +103,23 @@ __device__ __forceinline__ int z_row(const ZLevel& L, int rank, int l) {
     const int r = L.Nf + rank * L.rpc + (l - L.rpf);
     return (l < L.rpf + L.rpc && r < L.N) ? r : -1;
 }
-// owner CTA (bits 24..) and byte offset inside the owner's slice (bits 0..23) of element j of a vector of level L
+// owner CTA (bits 24..), second-segment flag of the bigraph level (bit 23) and byte offset inside the owner's vector slot
+// (bits 0..22) of element j of a vector of level L
+constexpr uint32_t kZSeg = 1u << 23, kZOffMask = kZSeg - 1u;
 __device__ __forceinline__ uint32_t z_loc(const ZLevel& L, int j) {
     int owner, l;
     if (j < L.Nf) { owner = j / L.rpf; l = j - owner * L.rpf; }
     else { const int jj = j - L.Nf; owner = jj / L.rpc; l = L.rpf + jj - owner * L.rpc; }
-    return ((uint32_t)owner << 24) | (uint32_t)(l * 8);
+    return ((uint32_t)owner << 24) | ((L.bigph && j >= L.Nf) ? kZSeg : 0u) | (uint32_t)(l * 8);
 }
-__device__ __forceinline__ double* z_vec(const ZTeam& G, const ZLevel& L, int slot) { return reinterpret_cast<double*>(G.dsm + L.voff + slot * L.stride); }
-__device__ __forceinline__ int z_vb(const ZLevel& L, int slot) { return L.voff + slot * L.stride; }
+__device__ __forceinline__ double* z_vec(const ZTeam& G, const ZLevel& L, int slot) { return reinterpret_cast<double*>(G.dsm + L.so[slot]); }
+__device__ __forceinline__ int z_vb(const ZLevel& L, int slot) { return L.so[slot]; }
 // One element of a level vector: mapa + ld.shared::cluster.  (Measured on a B200, tools/barrier_bench.py: with 16 random
 // owner CTAs per warp instruction a 512-thread CTA completes only ~0.3 such loads per cycle -- against ~1 from L2 and ~10
 // from its own shared memory -- so what makes this kernel work is the locality of the OT graphs in the natural order:
 // most lanes of a warp instruction hit one or two owners.)
 __device__ __forceinline__ double z_gather(const ZTeam& G, int vb, uint32_t lc) {
-    return z_ld(z_map(G.base + (zaddr)(vb + (int)(lc & 0xffffffu)), (int)(lc >> 24)));
+    return z_ld(z_map(G.base + (zaddr)(vb + (int)(lc & kZOffMask)), (int)(lc >> 24)));
 }
 
 // cluster-wide sums of two per-thread values: ONE cluster barrier; fixed order, identical in every thread of the cluster
@@ -148,11 +154,19 @@ __device__ __forceinline__ void z_bounds(const int* rs, const ZLevel& L, int l, 
     const int i = l + (l >= L.rpf ? 1 : 0);
     e0 = rs[i]; e1 = rs[i + 1];
 }
-__device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int segb) {
-    const bool second = (int)(lc & 0xffffffu) >= segb;
+__device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int /*segb*/) {
+    const bool second = (lc & kZSeg) != 0u;
     return filt == 0 || (second == (filt == 1));
 }
 
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+__device__ unsigned long long g_zdbg[256];
+#define ZT0() const long long zt0__ = clock64()
+#define ZTACC(slot) do { if (G.rank == 0 && threadIdx.x == 0) { g_zdbg[6 * 16 + (slot)] += (unsigned long long)(clock64() - zt0__); g_zdbg[128 + 6 * 16 + (slot)] += 1ull; } } while (0)
+#else
+#define ZT0() do {} while (0)
+#define ZTACC(slot) do {} while (0)
+#endif
 // the same for ONE value (most reductions of the cycle).  Stage 1: warp sums into shared memory, every thread of warp 0
 // adds the NW partials itself; stage 2: lanes 0..15 of warp 0 put the CTA's sum into slot [rank] of every CTA, ONE
 // cluster barrier, every thread adds the 16 slots.  (Sending the warp partials straight to every CTA -- no stage 1 --
@@ -163,10 +177,12 @@ __device__ __forceinline__ bool z_keep(uint32_t lc, int filt, int segb) {
 __device__ __forceinline__ void z_sum1_post(ZTeam& G, double a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = kZT / 32;
+    ZT0();
     a = warp_sum(a);
     double* sm = reinterpret_cast<double*>(G.dsm) + (G.flip & 1) * 64;
     if (lane == 0) sm[w] = a;
     __syncthreads();
+    ZTACC(0);                                                           // debug build: thread 0 waits for the CTA's slowest thread
     double* sl = reinterpret_cast<double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
     if (w == 0 && lane < G.ncta) {
         double ta = 0.0;
@@ -174,7 +190,9 @@ __device__ __forceinline__ void z_sum1_post(ZTeam& G, double a) {
         for (int i = 0; i < NW; ++i) ta += sm[i];
         z_st(z_map(z_local(sl + 2 * G.rank), lane), ta);
     }
+    ZTACC(1);
     z_barrier();
+    ZTACC(2);                                                           // ... and for the cluster's slowest CTA
 }
 __device__ __forceinline__ double z_sum1_read(ZTeam& G) {
     const double* sl = reinterpret_cast<const double*>(G.dsm + kOffSlots) + (G.flip & 1) * (2 * kZCta);
@@ -276,12 +294,18 @@ __device__ __forceinline__ void z_row_load(const ZTeam& G, const ZLevel& L, int 
         const bool has = e < e1;
         const uint32_t lc = has ? L.A.loc[e] : 0u;
         R.cv[k] = has ? L.A.cv[e] : 0.0;
-        R.ad[k] = z_map(G.base + (zaddr)(L.voff + (int)(lc & 0xffffffu)), (int)(lc >> 24));
+        R.ad[k] = z_map(G.base + (zaddr)(L.so[0] + (int)(lc & kZOffMask)), (int)(lc >> 24));
         if (has && z_keep(lc, filt, segb)) R.mask |= 1u << k;
     }
     R.e_more = e0 + K * tpr; R.e_end = e1;
 }
 
+// the gather table is written once at the start of the launch (before the first cluster barrier) and only read afterwards
+#ifdef SSN_ZLOC_NC
+#define Z_LDRO(p) __ldg(p)
+#else
+#define Z_LDRO(p) (*(p))
+#endif
 // lane-reduced A(row,:)*v from the registers (+ the entries past the K-th from global memory); vrel: byte offset of the
 // gathered vector from vector slot 0 of the level.  All K gathers are issued before the first product.
 template <int K>
@@ -293,10 +317,28 @@ __device__ __forceinline__ double z_row_dot(const ZTeam& G, const ZLevel& L, con
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) s = fma(R.cv[k], xv[k], s);
+    // the entries past the K-th: four at a time, every load of a batch in flight before the first use (one entry per trip
+    // was one dependent L2 round trip per entry -- the longest row of the slice set the time of the whole sweep: level 1 of
+    // the benchmarked state has 7.8 entries per row on average, 21 at most, and 8 in registers)
+    int e = R.e_more;
 #pragma unroll 1
-    for (int e = R.e_more; e < R.e_end; e += tpr) {
-        const uint32_t lc = L.A.loc[e];
-        if (z_keep(lc, filt, segb)) s = fma(L.A.cv[e], z_gather(G, L.voff + vrel, lc), s);
+    for (; e + 3 * tpr < R.e_end; e += 4 * tpr) {
+        uint32_t lc[4]; double v[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { lc[u] = Z_LDRO(L.A.loc + e + u * tpr); v[u] = __ldg(L.A.cv + e + u * tpr); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = z_keep(lc[u], filt, segb) ? z_gather(G, L.so[0] + vrel, lc[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s = fma(v[u], xv[u], s);
+    }
+    if (e < R.e_end) {
+        uint32_t lc[3]; double v[3], xv[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) { const bool has = e + u * tpr < R.e_end; lc[u] = has ? Z_LDRO(L.A.loc + e + u * tpr) : 0u; v[u] = has ? __ldg(L.A.cv + e + u * tpr) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) xv[u] = (e + u * tpr < R.e_end && z_keep(lc[u], filt, segb)) ? z_gather(G, L.so[0] + vrel, lc[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) s = fma(v[u], xv[u], s);
     }
     for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -321,6 +363,88 @@ __device__ __noinline__ bool z_build_loc(const ZTeam& G, const ZLevel& Lrow, con
     return bad;
 }
 
+// ---- halo of the A-gathers.  ld.shared::cluster to the CTA's OWN shared memory runs at the speed of ld.shared (~6 eight-byte
+// gathers per cycle), to another CTA at ~0.25 per cycle when the lanes of a warp instruction read scattered words -- and at ~2
+// per cycle when they read consecutive words (tools/barrier_bench.py, which = 19 / 20 / 22).  The graphs of the path are local in
+// the natural order: a CTA's rows reference few DISTINCT elements of other CTAs' slices.  So each gathered vector slot of a
+// level carries, behind the CTA's own slice, a copy of those elements (the halo, ascending column order = runs of consecutive
+// remote words): the gather tables of A point into it, every gather of a sweep stays inside the SM, and before a pass that
+// gathers slot s the CTA refreshes the halo of s with coalesced remote loads (z_halo_pull; the vector was published by the
+// cluster barrier that ended the pass that wrote it, as the remote gathers needed it).  Built once per launch and per CTA: a
+// bitmap of the referenced remote columns in scratch shared memory, its popcount prefix = the halo slot of a column.  A CTA
+// whose halo does not fit the capacity of the level keeps the owners' locations in its table (hn = 0) -- the decision is
+// local, the pulls involve no cluster-wide step.
+__device__ __noinline__ void z_build_halo(const ZTeam& G, ZLevel& L, unsigned char* scratch) {
+    L.hn = 0;
+    const int N = L.N, nW = (N + 31) >> 5;
+    if (L.hcap <= 0 || N > 65536 || L.A.rp == nullptr) return;      // bitmap (8 KB) + 16-bit word prefixes (4 KB) <= the 16 KB scratch
+    uint32_t* bm = reinterpret_cast<uint32_t*>(scratch);
+    unsigned short* pre = reinterpret_cast<unsigned short*>(scratch + 8192);
+    int* s_tot = reinterpret_cast<int*>(scratch + 12288);              // [kZT / 32 + 1] (no static shared memory in a cluster kernel:
+                                                                       // the host emulation runs the 16 CTAs at the same time)
+    for (int w = threadIdx.x; w < nW; w += kZT) bm[w] = 0u;
+    __syncthreads();
+    const int nl = L.rpf + L.rpc;
+    for (int l = threadIdx.x; l < nl; l += kZT) {
+        const int row = z_row(L, G.rank, l);
+        if (row < 0) continue;
+        const int e1 = L.A.rp[row + 1];
+        for (int e = L.A.rp[row]; e < e1; ++e) {
+            const int j = L.A.ci[e];
+            if ((int)(z_loc(L, j) >> 24) != G.rank) atomicOr(&bm[j >> 5], 1u << (j & 31));
+        }
+    }
+    __syncthreads();
+    // exclusive prefix of the word popcounts: a contiguous run of words per thread, then a scan of the thread totals
+    const int per = (nW + kZT - 1) / kZT, w0 = min((int)threadIdx.x * per, nW), w1 = min(w0 + per, nW);
+    int mine = 0;
+    for (int w = w0; w < w1; ++w) mine += __popc(bm[w]);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_tot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < kZT / 32; ++i) { const int t = s_tot[i]; s_tot[i] = acc; acc += t; } s_tot[kZT / 32] = acc; }
+    __syncthreads();
+    const int H = s_tot[kZT / 32];
+    if (H > L.hcap || H == 0) { __syncthreads(); return; }             // uniform over the CTA
+    int run = s_tot[wid] + incl - mine;
+    uint32_t* hsrc = reinterpret_cast<uint32_t*>(G.dsm + L.hoff);
+    for (int w = w0; w < w1; ++w) {
+        pre[w] = (unsigned short)run;
+        uint32_t bits = bm[w];
+        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1u; hsrc[run++] = z_loc(L, (w << 5) + b); }
+    }
+    __syncthreads();
+    // the table entries of the remote columns now point into the CTA's own halo area
+    for (int l = threadIdx.x; l < nl; l += kZT) {
+        const int row = z_row(L, G.rank, l);
+        if (row < 0) continue;
+        const int e1 = L.A.rp[row + 1];
+        for (int e = L.A.rp[row]; e < e1; ++e) {
+            const int j = L.A.ci[e];
+            const uint32_t lc = z_loc(L, j);
+            if ((int)(lc >> 24) != G.rank) {
+                const int h = (int)pre[j >> 5] + __popc(bm[j >> 5] & ((1u << (j & 31)) - 1u));
+                L.A.loc[e] = ((uint32_t)G.rank << 24) | (lc & kZSeg) | (uint32_t)(L.hb + 8 * h);
+            }
+        }
+    }
+    __syncthreads();
+    L.hn = H;
+}
+
+// refresh the halo of vector slot `slot` from the owners' slices (consecutive threads read consecutive halo entries: runs of
+// consecutive remote words); the slot must have been published by a cluster barrier.  Ends with a CTA barrier.
+__device__ __forceinline__ void z_halo_pull(const ZTeam& G, const ZLevel& L, int slot) {
+    if (L.hn == 0) return;
+    const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(G.dsm + L.hoff);
+    double* halo = reinterpret_cast<double*>(G.dsm + L.so[slot] + L.hb);
+    for (int h = threadIdx.x; h < L.hn; h += kZT) halo[h] = z_gather(G, L.so[slot], hsrc[h]);
+    __syncthreads();
+}
+
 // The smoothing loops for slices that do not fit the register slots (larger systems; the host emulation's small CTAs):
 // every sweep re-reads its rows.  Out of line: the cycle's hot code stays small enough for the instruction cache.
 struct ZStream { double dot; int cur, flip; };
@@ -334,6 +458,7 @@ __device__ __noinline__ ZStream z_jacobi_stream(ZTeam G, const ZLevel& L, int sm
         const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
         double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
         double part = 0.0;
+        if (!ez) z_halo_pull(G, L, cur ? ZV_ALT : ZV_E);
         z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, cur ? ZV_ALT : ZV_E), 0, 0, !ez, [&](int l, int, double d) {
             const double axi = Axi[l], ei = ez ? 0.0 : ec[l];
             const double en = ei + coef + dinv[l] * ((r[l] - d) - axi * coef);
@@ -356,6 +481,7 @@ __device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth,
     for (int s = 0; s < smoth; ++s) {
         const double coef = (sr - dotAe) * rxx;
         double part = 0.0;
+        if (!ez) z_halo_pull(G, L, ZV_E);
         z_rows(G, L, L.A, z_rs(G, L), L.ltG, a0, a1, vbe, fa, segb, !ez, [&](int l, int, double d) {
             const double axi = Axi[l];
             const double en = coef + dinv[l] * ((r[l] - d) - axi * coef);
@@ -363,6 +489,7 @@ __device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth,
             part = fma(axi, en, part);
         });
         z_barrier();
+        z_halo_pull(G, L, ZV_E);
         z_rows(G, L, L.A, z_rs(G, L), L.ltG, b0, b1, vbe, fb, segb, true, [&](int l, int, double d) {
             const double en = dinv[l] * (r[l] - d);
             e[l] = en;
@@ -374,7 +501,6 @@ __device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth,
 }
 
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
-__device__ unsigned long long g_zdbg[256];
 #define ZDBG(op, level, call) do { const long long t0__ = clock64(); call; if (lead) { g_zdbg[(op) * 16 + (level)] += (unsigned long long)(clock64() - t0__); g_zdbg[128 + (op) * 16 + (level)] += 1ull; } } while (0)
 #else
 #define ZDBG(op, level, call) do { call; } while (0)
@@ -419,6 +545,9 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
         if (k < kd) z_build_loc(G, sl[k], sl[k + 1], sl[k].Pu, false);
         if (k >= 1) z_build_loc(G, sl[k], sl[k - 1], sl[k].Td, false);
     }
+    // ---- halos of the A-gathers (each CTA's own decision per level; the scratch is the dense leaf's vector buffer)
+    __syncthreads();                                                    // L.hn is written by all threads with the same value: sl is shared
+    for (int k = 0; k <= kd; ++k) z_build_halo(G, sl[k], dsm + kOffXs);
     // ---- row bounds of A, 1/diag, A*ones of this CTA's rows: shared memory
     for (int k = 0; k <= kd; ++k) {
         const ZLevel& L = sl[k];
@@ -456,6 +585,7 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
     // r = b - A*x ; sum(r), sum(r^2)                                    Class_AMG.m:89 / :96,:102
     auto outer_residual = [&](double& s1, double& s2) {
         s1 = 0.0; s2 = 0.0;
+        z_halo_pull(G, L0, L0.xslot);
         z_rows(G, L0, L0.A, z_rs(G, L0), L0.ltA, 0, nl0, z_vb(L0, L0.xslot), 0, 0, true, [&](int l, int row, double s) {
             const double ri = a.b[row] - s; r0[l] = ri; s1 += ri; s2 = fma(ri, ri, s2);
         });
@@ -489,8 +619,9 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 const double* ec = z_vec(G, L, cur ? ZV_ALT : ZV_E);
                 double* ea = z_vec(G, L, cur ? ZV_E : ZV_ALT);
                 double d[kZSlots];
+                if (!ez) z_halo_pull(G, L, cur ? ZV_ALT : ZV_E);
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, R[u], L.ltA, (cur ? ZV_ALT : ZV_E) * L.stride, 0, 0);
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, R[u], L.ltA, L.so[cur ? ZV_ALT : ZV_E] - L.so[0], 0, 0);
                 double part = 0.0;
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
@@ -541,14 +672,16 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 const double coef = (sr - dotAe) * rxx;
                 double part = 0.0;
                 double d[kZSlots];
+                if (!ez) z_halo_pull(G, L, ZV_E);
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, Ra[u], L.ltG, ZV_E * L.stride, fa, segb);
+                for (int u = 0; u < kZSlots; ++u) d[u] = ez ? 0.0 : z_row_dot<K>(G, L, Ra[u], L.ltG, 0, fa, segb);
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
                     if (ma[u] && first) { const double en = coef + dia[u] * ((ra[u] - d[u]) - axa[u] * coef); e[la[u]] = en; part = fma(axa[u], en, part); }
                 z_barrier();
+                z_halo_pull(G, L, ZV_E);
 #pragma unroll
-                for (int u = 0; u < kZSlots; ++u) d[u] = z_row_dot<K>(G, L, Rb[u], L.ltG, ZV_E * L.stride, fb, segb);
+                for (int u = 0; u < kZSlots; ++u) d[u] = z_row_dot<K>(G, L, Rb[u], L.ltG, 0, fb, segb);
 #pragma unroll
                 for (int u = 0; u < kZSlots; ++u)
                     if (mb[u] && first) { const double en = dib[u] * (rb[u] - d[u]); e[lb[u]] = en; part = fma(axb[u], en, part); }
@@ -600,7 +733,8 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 const double* r = z_vec(G, L, ZV_R);
                 double* g = z_vec(G, L, ZV_G);
                 const int es = (k == 0 && L.bigph) ? ZV_E : (st_cur[k] ? ZV_ALT : ZV_E);
-                ZDBG(0, k, z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, es), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
+                ZDBG(0, k, z_halo_pull(G, L, es);
+                z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, es), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
                 z_barrier());
                 const ZLevel& Lc = sl[k + 1];
                 double* rc = z_vec(G, Lc, ZV_R);
@@ -626,7 +760,8 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 int in_slot = ZV_R;
                 if (!zero) {
                     double* g = z_vec(G, L, ZV_G);
-                    ZDBG(0, k, z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, ZV_E), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
+                    ZDBG(0, k, z_halo_pull(G, L, ZV_E);
+                    z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, ZV_E), 0, 0, true, [&](int l, int, double d) { g[l] = r[l] - d; });
                     z_barrier());
                     in_slot = ZV_G;
                 }
@@ -693,7 +828,7 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
         if (rho > 1.0) break;                                           // Class_AMG.m:106
     }
     for (int l = threadIdx.x; l < nl0; l += kZT) { const int row = z_row(L0, G.rank, l); if (row >= 0) a.x[row] = x0[l]; }
-    if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; }
+    if (lead) { a.it_out[0] = it - 1; a.it_out[1] = hist; int hs = 0; for (int k = 0; k <= kd; ++k) hs += sl[k].hn; a.it_out[3] = hs; }   // [3]: halo entries of CTA 0
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
     if (lead) { g_zdbg[7 * 16] += (unsigned long long)(clock64() - t_kernel); g_zdbg[128 + 7 * 16] += 1ull; }
 #endif
@@ -719,7 +854,14 @@ __global__ void __launch_bounds__(kZT, 1) dsm_bench_kernel(double* gbuf, int ite
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
         const unsigned h = (unsigned)(G.rank * kZT + threadIdx.x) * 2654435761u + (unsigned)u * 40503u;
-        const int idx = (int)((h >> 7) % (16u * 1024u));
+        int idx = (int)((h >> 7) % (16u * 1024u));
+        // 19: every gather goes to the CTA's OWN slice through ld.shared::cluster; 20: to the next CTA's; 21: 3 of 4 own, 1 of 4 next
+        if (which == 19) idx = (G.rank << 10) | (idx & 1023);
+        if (which == 20) idx = (((G.rank + 1) & 15) << 10) | (idx & 1023);
+        if (which == 21) idx = ((((u & 3) == 3 ? G.rank + 1 : G.rank) & 15) << 10) | (idx & 1023);
+        // 22: coalesced remote loads (consecutive lanes read consecutive doubles of the next CTA's slice); 23: the same from 4 owners
+        if (which == 22) idx = (((G.rank + 1) & 15) << 10) | ((threadIdx.x + 512 * u) & 1023);
+        if (which == 23) idx = (((G.rank + 1 + (u & 3)) & 15) << 10) | ((threadIdx.x + 512 * (u >> 2)) & 1023);
         gi[u] = idx; lc[u] = ((uint32_t)(idx >> 10) << 24) | (uint32_t)((idx & 1023) * 8);
     }
     z_barrier();
@@ -729,9 +871,9 @@ __global__ void __launch_bounds__(kZT, 1) dsm_bench_kernel(double* gbuf, int ite
         if (which == 10) acc += z_sum1(G, acc + threadIdx.x);
         else if (which == 18) acc += z_sum1_pull(G, acc + threadIdx.x);
         else if (which == 11) z_barrier();
-        else if (which == 12 || which == 13) {
+        else if (which == 12 || which == 13 || (which >= 19 && which <= 23)) {
             double xv[16];
-            if (which == 12) {
+            if (which != 13) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) xv[u] = (u < ng) ? z_gather(G, 4096, lc[u]) : 0.0;
 #pragma unroll
@@ -817,41 +959,81 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
     for (int k = 1; k <= kd; ++k) if (H.lv[k].bigph) return false;
     const int ncta = kZCta;
     ZArgs a{};
-    size_t off = kOffVec;
-    for (int k = 0; k <= kd; ++k) {
-        Level& L = H.lv[k];
-        ZLevel& z = a.lv[k];
-        z.N = L.N; z.bigph = (k == 0 && L.bigph) ? 1 : 0;
-        z.Nf = z.bigph ? L.Nf : L.N;
-        if (z.bigph && (z.Nf <= 0 || z.Nf >= z.N)) return false;
-        z.rpf = (z.Nf + ncta - 1) / ncta;
-        z.rpc = (z.N - z.Nf + ncta - 1) / ncta;
-        const int nl = z.rpf + z.rpc;
-        z.stride = ((nl * 8 + 15) / 16) * 16;
-        if ((size_t)z.stride >= ((size_t)1 << 24)) return false;
-        z.voff = (int)off;
-        int nvec = 4;                                       // E, R, G, ALT
-        if (k == 0) { z.xslot = z.bigph ? ZV_ALT : 4; nvec = z.bigph ? 4 : 5; }     // the in-place smoother needs no ALT copy
-        if (k == kd) nvec = 3;
-        off += (size_t)nvec * z.stride;
-        z.poff = (int)off;
-        z.rsbytes = (((nl + 2) * 4 + 15) / 16) * 16;
-        off += (size_t)z.rsbytes + (k < kd ? (size_t)2 * (((nl * 8 + 15) / 16) * 16) : 0);
-        const double avgA = L.N ? (double)L.A.nnz / L.N : 0.0;
-        z.ltA = z_log2_lanes(avgA, nl, kZSlots);
-        z.ltG = z_log2_lanes(avgA, std::max(z.rpf, z.rpc), kZSlots);
-        z.A = ZMat{L.A.ptr.p, L.A.idx.p, L.A.val.p, nullptr};
-        z.Pu = ZMat{nullptr, nullptr, nullptr, nullptr}; z.Td = z.Pu;
-        if (k < kd) {
-            Level& Lc = H.lv[k + 1];
-            z.Pu = ZMat{Lc.P.ptr.p, Lc.P.idx.p, Lc.P.val.p, nullptr};
-            z.ltP = z_log2_lanes(L.N ? (double)Lc.P.nnz / L.N : 0.0, nl);
+    // ---- layout of a CTA's shared memory.  Pass 1: without halos, to see what is left; pass 2: with the halo capacities.
+    // SSN_DSM_HALO=1 (opt-in): measured on a B200 at the benchmarked state the halo copies LOSE (4.49 ms against 4.17 per solve):
+    // a CTA references only ~30 distinct remote elements per level there, and the pull adds a remote round trip and a CTA
+    // barrier to every sweep.  What set the time of a sweep was the tail of the longest row (z_row_dot), not the remote gathers.
+    int use_halo = 0;
+    { const char* e = getenv("SSN_DSM_HALO"); if (e && e[0] == '1') use_halo = 1; }
+    int hcap[kZMaxL] = {0};
+    size_t off = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        off = kOffVec;
+        for (int k = 0; k <= kd; ++k) {
+            Level& L = H.lv[k];
+            ZLevel& z = a.lv[k];
+            z.N = L.N; z.bigph = (k == 0 && L.bigph) ? 1 : 0;
+            z.Nf = z.bigph ? L.Nf : L.N;
+            if (z.bigph && (z.Nf <= 0 || z.Nf >= z.N)) return false;
+            z.rpf = (z.Nf + ncta - 1) / ncta;
+            z.rpc = (z.N - z.Nf + ncta - 1) / ncta;
+            const int nl = z.rpf + z.rpc;
+            const int sz0 = ((nl * 8 + 15) / 16) * 16;
+            const int szh = (((nl + hcap[k]) * 8 + 15) / 16) * 16;
+            if ((size_t)szh >= ((size_t)1 << 23)) return false;
+            int nvec = 4;                                       // E, R, G, ALT
+            z.xslot = 0;
+            if (k == 0) { z.xslot = z.bigph ? ZV_ALT : 4; nvec = z.bigph ? 4 : 5; }     // the in-place smoother needs no ALT copy
+            if (k == kd) nvec = 3;
+            // the slots that A-gathers read (E, the ping-pong copy / x) carry a halo area behind the CTA's slice
+            for (int sl_ = 0; sl_ < 5; ++sl_) z.so[sl_] = 0;
+            const int order[5] = {ZV_E, ZV_ALT, 4, ZV_R, ZV_G};
+            for (int q = 0; q < 5; ++q) {
+                const int sl_ = order[q];
+                if (sl_ >= nvec) continue;                       // slots of this level: 0 .. nvec-1
+                const bool gathered = (sl_ == ZV_E || sl_ == ZV_ALT || sl_ == 4);
+                z.so[sl_] = (int)off;
+                off += (size_t)(gathered ? szh : sz0);
+            }
+            z.hb = sz0; z.hcap = hcap[k]; z.hn = 0;
+            z.hoff = (int)off;
+            off += (size_t)(((hcap[k] * 4 + 15) / 16) * 16);
+            z.poff = (int)off;
+            z.rsbytes = (((nl + 2) * 4 + 15) / 16) * 16;
+            off += (size_t)z.rsbytes + (k < kd ? (size_t)2 * (((nl * 8 + 15) / 16) * 16) : 0);
+            const double avgA = L.N ? (double)L.A.nnz / L.N : 0.0;
+            z.ltA = z_log2_lanes(avgA, nl, kZSlots);
+            z.ltG = z_log2_lanes(avgA, std::max(z.rpf, z.rpc), kZSlots);
+            z.A = ZMat{L.A.ptr.p, L.A.idx.p, L.A.val.p, nullptr};
+            z.Pu = ZMat{nullptr, nullptr, nullptr, nullptr}; z.Td = z.Pu;
+            if (k < kd) {
+                Level& Lc = H.lv[k + 1];
+                z.Pu = ZMat{Lc.P.ptr.p, Lc.P.idx.p, Lc.P.val.p, nullptr};
+                z.ltP = z_log2_lanes(L.N ? (double)Lc.P.nnz / L.N : 0.0, nl);
+            }
+            if (k >= 1) {
+                z.Td = ZMat{L.Pt.ptr.p, L.Pt.idx.p, L.Pt.val.p, nullptr};
+                z.ltT = z_log2_lanes(L.N ? (double)L.Pt.nnz / L.N : 0.0, nl);
+            }
+            z.dinv = L.dinv.p; z.Axi = L.Axi.p; z.xx = L.xx; z.B = (k == kd) ? L.B.p : nullptr;
         }
-        if (k >= 1) {
-            z.Td = ZMat{L.Pt.ptr.p, L.Pt.idx.p, L.Pt.val.p, nullptr};
-            z.ltT = z_log2_lanes(L.N ? (double)L.Pt.nnz / L.N : 0.0, nl);
+        if (pass == 0) {
+            if (off > (size_t)c->smem_optin - 1024) return false;
+            if (!use_halo) break;
+            // what is left goes to the halos: up to 1024 entries per level, scaled down together when that is too much
+            const double left = (double)((size_t)c->smem_optin - 1024 - off) - 64.0 * (kd + 1);
+            double need = 0.0; int want[kZMaxL];
+            for (int k = 0; k <= kd; ++k) {
+                const ZLevel& z = a.lv[k];
+                const int ng = (k == kd) ? 1 : ((k == 0 && !z.bigph) ? 3 : 2);
+                want[k] = std::max(0, std::min(1024, z.N - (z.rpf + z.rpc)));
+                need += (double)want[k] * (8.0 * ng + 4.0);
+            }
+            const double fsc = (need > 0.0 && left > 0.0) ? std::min(1.0, left / need) : 0.0;
+            bool any = false;
+            for (int k = 0; k <= kd; ++k) { hcap[k] = ((int)(want[k] * fsc)) & ~1; any = any || hcap[k] > 0; }
+            if (!any) break;
         }
-        z.dinv = L.dinv.p; z.Axi = L.Axi.p; z.xx = L.xx; z.B = (k == kd) ? L.B.p : nullptr;
     }
     const size_t smem = off;
     if (smem > (size_t)c->smem_optin - 1024) return false;

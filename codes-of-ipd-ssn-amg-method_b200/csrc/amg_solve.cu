@@ -1939,7 +1939,10 @@ bool persist_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const A
     // diagonal blocks are not diagonal (the two-half-sweep smoother does not apply) without having changed x
     if (c->cluster_solve && c->dsm_solve && nnz <= c->cluster_max_nnz && dsm_cluster_solve(c, H, b, x, o, wcycle, hist.p, hl, iout.p)) {
         read_back(c, iout.p, hi, 4);
-        if (hi[2] == 0) { launched = true; have_hi = true; }
+        if (hi[2] == 0) {
+            launched = true; have_hi = true; c->last_dsm_halo = hi[3];
+            if (c->prof) c->prof_acc["dsm_solve_kernel: halo entries of CTA 0 over all levels = " + std::to_string(hi[3])].second += 1;
+        }
     }
     if (!launched && c->cluster_solve && nnz <= c->cluster_max_nnz) {
         // ---- one cluster: 16 CTAs (non-portable size) where the device can co-schedule them, else 8

@@ -220,6 +220,7 @@ struct ssn_ctx {
     int small_scan_max = 1 << 14;
     bool device_setup = true;
     static constexpr int kSpgemmSites = 64;
+    int last_dsm_halo = -1;               // halo entries of CTA 0 in the last dsm_solve_kernel launch (diagnostic)
     int64_t spgemm_slab_limit = (int64_t)1 << 30;   // sparse products with more intermediate entries are formed in slabs of rows
     unsigned spgemm_epoch = 0;
     int spgemm_site = -1;                 // >= 0 inside amg_setup: index of the next sparse product of this hierarchy

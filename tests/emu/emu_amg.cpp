@@ -68,6 +68,8 @@ void emu_amg_clear() { ssn::amg_clear(ctx()); }
 // Class_AMG's solve loop on the live hierarchy through amg_cluster.cu (a cluster of 16 emulated CTAs): level kd is applied
 // as the dense cycle operator B (N_kd x N_kd, row-major, made by the test from the oracle's cycle).  status: -1 the
 // hierarchy did not qualify, else the kernel's it_out[2]
+static int g_last_halo = -1;
+int emu_last_halo() { return g_last_halo; }
 int emu_dsm_solve(int kd, const double* B, const double* b, const double* guess, int isnsp, int wcycle, double retol, int maxit,
                   double* x_out, int* it, double* relk, double* rho, int* hist_len, int* status) {
     return guarded([&] {
@@ -83,6 +85,7 @@ int emu_dsm_solve(int kd, const double* B, const double* b, const double* guess,
         ssn::AmgOptions o{}; o.retol = retol; o.maxit = maxit; o.isnsp = isnsp;
         const bool ok = ssn::dsm_cluster_solve(ctx(), H, bb.p, x.p, o, wcycle != 0, hist.p, hl, iout.p);
         *status = ok ? iout.p[2] : -1;
+        g_last_halo = ok ? iout.p[3] : -1;
         if (!ok || iout.p[2] != 0) return;
         *it = iout.p[0]; *hist_len = iout.p[1];
         std::memcpy(relk, hist.p, sizeof(double) * iout.p[1]); std::memcpy(rho, hist.p + hl, sizeof(double) * iout.p[1]);

@@ -269,6 +269,8 @@ def test_dsm_cluster_solve_against_the_oracle(emu, oracle, monkeypatch, m, n, de
     and residual histories of the oracle's Class_AMG (AMG/Class_AMG.m:89-107), the solution to 1e-10."""
     from oracle.amg import setup_hierarchy, amg_state, MG_Wcycle, MG_Vcycle, Class_AMG
     monkeypatch.setenv("SSN_DSM_NOREG", str(noreg))     # 1: the smoothing loops re-read their rows every sweep (rows that do not fit the registers)
+    halo = 1 if (m, noreg) in ((90, 0), (60, 1)) else 0  # the opt-in halo copies of the A-gathers in two of the cases
+    monkeypatch.setenv("SSN_DSM_HALO", str(halo))
     Ae = ssn_matrix(oracle, m, n, density, seed=7 * m)
     if oracle.components(Ae)[1].size != 1:
         pytest.skip("random active set is disconnected")
@@ -303,6 +305,7 @@ def test_dsm_cluster_solve_against_the_oracle(emu, oracle, monkeypatch, m, n, de
                                   C.c_int(30), _p(x), C.byref(it), _p(relk), _p(rho), C.byref(hl), C.byref(status)))
     amg_state.clear(); emu.emu_amg_clear()
     assert status.value == 0, status.value
+    assert (emu.emu_last_halo() > 0) == (halo == 1)                     # the A-gathers of CTA 0 went through its halo copies
     assert it.value == it_ref and hl.value == len(relk_ref)
     big = relk_ref > 1e-10
     dev = np.max(np.abs(relk[:hl.value][big] - relk_ref[big]) / relk_ref[big])

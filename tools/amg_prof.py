@@ -43,7 +43,7 @@ def main():
     ctx.call("ssn_debug_cycles", ctypes.cast(buf, ctypes.c_void_p), 1)
     pb = (ctypes.c_ulonglong * 256)()
     ctx.call("ssn_debug_cycles_persist", ctypes.cast(pb, ctypes.c_void_p), 1)
-    ops = {0: "resid", 1: "gs_apply", 2: "jacobi", 3: "spmv(P)", 4: "dense", 5: "outer res", 7: "kernel"}
+    ops = {0: "resid", 1: "gs_apply", 2: "jacobi", 3: "spmv(P)", 4: "dense", 5: "outer res", 6: "zsum/dots", 7: "kernel"}
     tot = pb[7 * 16] or 1
     for op, nm in ops.items():
         for lv in range(16):

@@ -19,6 +19,10 @@ for which, name in ((0, "cg grid.sync"), (1, "grid_barrier"), (0, "cg grid.sync"
 # building blocks of a pass of the DSMEM cluster solve kernel (amg_cluster.cu): 16 CTAs x 512 threads
 for which, name in ((10, "z_sum1 (cluster-wide sum of one double)"), (18, "z_sum1_pull (own slot + 16 remote loads)"), (11, "z_barrier"), (16, "block reduction + barrier"), (17, "store + relaxed-arrive barrier"),
                     (412, "4 DSMEM gathers + barrier"), (812, "8 DSMEM gathers + barrier"), (1612, "16 DSMEM gathers + barrier"),
+                    (819, "8 ld.shared::cluster gathers, OWN CTA"), (1619, "16 ld.shared::cluster gathers, OWN CTA"),
+                    (820, "8 ld.shared::cluster gathers, next CTA"), (1620, "16 ld.shared::cluster gathers, next CTA"),
+                    (821, "8 gathers, 3 of 4 own CTA"), (1621, "16 gathers, 3 of 4 own CTA"),
+                    (822, "8 COALESCED remote loads, next CTA"), (1622, "16 COALESCED remote loads, next CTA"), (1623, "16 coalesced remote loads, 4 owners"),
                     (813, "8 DSMEM gathers, batches of 4"), (1613, "16 DSMEM gathers, batches of 4"),
                     (414, "4 L2 gathers + store + barrier"), (814, "8 L2 gathers + store + barrier"), (1614, "16 L2 gathers + store + barrier"),
                     (815, "8 local smem gathers + barrier"), (1615, "16 local smem gathers + barrier")):
