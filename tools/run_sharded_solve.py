@@ -69,7 +69,9 @@ def main():
         for _ in range(reps):
             fn()
         ms, cnt = ssnamg.kernel_timer_read(); ssnamg.kernel_timer(False)
-        return ms / max(cnt, 1)
+        if cnt == 0:
+            raise RuntimeError("this operator's kernel is not bracketed by the kernel timer")
+        return ms / cnt
     for name, fn in (("Ax", lambda: ssnamg.Ax(w, p_loc, qd)),
                      ("prox_residual(Axprox)", lambda: ssnamg.prox_residual(w, lam, p_loc, qd, 0.9, float("inf"), want=("Axprox",))),
                      ("trials_screen(64 steps)", lambda: ssnamg.prox_trials_lin(w, lam, zeta, p_loc, qd, 0.9, 0.9, 1, 64))):
