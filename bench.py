@@ -186,12 +186,16 @@ def main():
         state_src = "device solve run up to the step (fixture missing)"
     torch.cuda.synchronize()
     t_state = time.time() - t0
-    full = None
+    full = None; full5 = None
     if world == 1 and not args.no_full_solve:
         # the whole Class 1 solve (the metric's "solve time") through the library's one-call entry point ssn_apd_ssn_class1
         ssnamg.rng_reset()
         full = ssnamg.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"])
         full.pop("xk", None); torch.cuda.empty_cache()
+        # the same script with its other multilevel option, inner_solver = 5 (Hybrid_twogrid, Class1/APD_SsN_Class1.m:70,178)
+        ssnamg.rng_reset()
+        full5 = ssnamg.APD_SsN_Class1(P["c"], P["r"], P["l"], P["p"], P["q"], P["gama"], inner_solver=5)
+        full5.pop("xk", None); torch.cuda.empty_cache()
     del P
     workload = f"grid{g}x{g}_vs_{g}x{g}_m{m}_n{n}_outer{state['k']}_ssn{state['ssn_it']}"
 
@@ -393,8 +397,17 @@ def main():
                                  "status": ("converged to rel-KKT <= 1e-6" if fs["converged"] else
                                             f"STOPPED AT maxit = {full['outer_its']} outer iterations (Class1/APD_SsN_Class1.m:35), NOT converged: "
                                             f"rel-KKT {full['rel_kkt']:.1e} > KKT_Tol 1e-6"),
-                                 "note": "Class1/APD_SsN_Class1.m with its own limits (maxit = 100 outer iterations, KKT_Tol 1e-6); a time to "
-                                         "the iteration cap is not a time to solution"}
+                                 "note": "Class1/APD_SsN_Class1.m with its own limits (maxit = 100 outer iterations, KKT_Tol 1e-6) and its default "
+                                         "inner_solver = 4 (Hybrid_AMG); a time to the iteration cap is not a time to solution"}
+        if full5 is not None:
+            f5 = full5["stats"]
+            out["full_solve_inner_solver5"] = {
+                "total_s": full5["seconds"] + full5["warmup_seconds"], "loop_s": full5["seconds"], "warmup_s": full5["warmup_seconds"],
+                "outer_its": full5["outer_its"], "converged": bool(f5["converged"]), "rel_kkt": full5["rel_kkt"], "objective": full5["fxk"][-1],
+                "ssn_steps": int(sum(f5["ssn_its"])), "line_search_trials": int(f5["ls_trials"]), "inner_solves": int(f5["amg_calls"]),
+                "inner_solve_s": f5["solve_s"], "plan_s": f5["plan_s"], "asat_s": f5["asat_s"],
+                "note": "the same script with inner_solver = 5 (Hybrid_twogrid, the reference's two-level option, "
+                        "Class1/APD_SsN_Class1.m:70,178): a time to solution when `converged` is true"}
         if not args.no_cpu_baseline:
             host_state = {"wk": state["wk"].cpu().numpy(), "lk": state["lk"].cpu().numpy(), "wlk": state["wlk"].cpu().numpy(),
                           "p": np.ones(m), "q": np.ones(n), "tk": state["tk"], "bk1": state["bk1"], "m": m, "n": n}
