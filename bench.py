@@ -362,6 +362,33 @@ def main():
     out["roofline_other"] = other
     if world > 1:
         out["collectives_per_step"] = int(info.get("collectives", 0)) // max(1, args.steps + max(args.warmup, 3))
+    if world > 1:
+        # ---- e2e on N GPUs: every rank copies ITS slab of wk (and the duals) from pinned host memory each step, runs the sharded
+        # step on the copies and reads lk_new / Fk_new back; wall clock between barriers, max over ranks
+        h_w = step_fn.w_loc.cpu().pin_memory(); h_lk = step_fn.lk.cpu().pin_memory(); h_wlk = step_fn.wlk.cpu().pin_memory()
+        keep = (None, step_fn.lk, step_fn.wlk)
+        step_fn.w_loc = None; k3_w = None; lin_call = None; torch.cuda.empty_cache()
+
+        def host_step_sharded():
+            step_fn.w_loc = h_w.cuda(non_blocking=True); step_fn.lk = h_lk.cuda(non_blocking=True); step_fn.wlk = h_wlk.cuda(non_blocking=True)
+            a_, b_, _ = step_fn()
+            return a_.cpu(), b_.cpu()
+        for _ in range(2):
+            host_step_sharded()
+        torch.cuda.synchronize(); dist.barrier()
+        ke = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            lk_h, Fk_h = host_step_sharded()
+        torch.cuda.synchronize()
+        te = torch.tensor([(time.perf_counter() - t0) * 1e3 / ke], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        hb = torch.tensor([float(h_w.numel() * 8 + h_lk.numel() * 8 + h_wlk.numel() * 8)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hb)
+        out["e2e"] = {"value": float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(hb[0]),
+                      "d2h_bytes_per_step": int(world * (lk_h.numel() * 8 + Fk_h.numel() * 8)),
+                      "note": "bytes summed over the ranks: each rank uploads its own row slab over its own PCIe link"}
+        step_fn.w_loc, step_fn.lk, step_fn.wlk = None, keep[1], keep[2]
     if world == 1:
         # ---- e2e: the same step through host buffers (pinned), H2D of the step's inputs + D2H of its result
         hstate = {k: (v.cpu().pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in state.items()}
