@@ -61,6 +61,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_LS_MAXNT"); if (e && atoi(e) >= 8) c->ls_max_nt = atoi(e) > 128 ? 128 : atoi(e); }
     { const char* e = getenv("SSN_LS_SCREEN"); c->ls_screen = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_PLAN_STAGE"); c->plan_stage = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_PLAN_WAVES"); if (e && atoi(e) >= 1 && atoi(e) <= 16) c->plan_waves = atoi(e); }
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_SMALL_SCAN_MAX"); if (e && atoi(e) >= 0) c->small_scan_max = atoi(e); }
     { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = !(e && e[0] == '0'); }

@@ -1302,6 +1302,10 @@ struct Tiling { int groups, chunks, cpc; };
 Tiling plan_tiling(ssn_ctx* c, int64_t m, int64_t n, int waves = 2) {
     Tiling t;
     t.groups = cdiv(m, kGroupRows);
+    // a slab of less than 512 MB (a rank's share of the 128x128 plan on 8 GPUs: 268 MB, a 50 us launch) streams best as ONE wave
+    // of longer blocks (measured, tools/microbench_slab.py: 53 us against 56 with two waves, 61 with four)
+    if (waves == 2 && (double)m * (double)n * 8.0 < 512.0 * 1024 * 1024) waves = 1;
+    if (c->plan_waves > 0 && waves <= 2) waves = c->plan_waves;  // SSN_PLAN_WAVES (development aid)
     const int64_t target = (int64_t)c->num_sms * 2 * waves;      // `waves` waves at 2 blocks / SM (the reductions: two -- their
                                                                  // partial arrays grow with the number of chunks)
     int64_t chunks = target / t.groups; if (chunks < 1) chunks = 1;
@@ -1475,7 +1479,9 @@ void plan_prox_residual(ssn_ctx* c, const double* w, const double* lam, const do
     bool vec = vec_ok(w, m) && (!gama || vec_ok(gama, m)) && (!prox_out || vec_ok(prox_out, m)) &&
                (!z_out || vec_ok(z_out, m)) && (!s_out || (reinterpret_cast<uintptr_t>(s_out) & 1u) == 0);
     const int gm = gama ? G_VECTOR : (std::isinf(gama_s) && gama_s > 0 ? G_INF : G_SCALAR);
-    a.stage = (vec && gm != G_VECTOR && c->plan_stage) ? 1 : 0;
+    // the double buffer pays once a block walks many batches (full-size plan: 111 per block); on the short blocks of a small
+    // slab its prologue costs more than it hides (2048 x 16384 slab: 63 us staged against 56 us)
+    a.stage = (vec && gm != G_VECTOR && c->plan_stage && t.cpc >= 128) ? 1 : 0;
     const size_t smem = (size_t)kWarps * t.cpc * sizeof(double) + (a.stage ? kStageBytes : 0);
     if (a.stage) {
         static bool attr = false;
