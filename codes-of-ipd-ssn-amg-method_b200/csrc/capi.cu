@@ -65,6 +65,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_SMALL_SCAN_MAX"); if (e && atoi(e) >= 0) c->small_scan_max = atoi(e); }
     { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_BUF_CACHE"); c->buf_cache = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {
         SSN_CUDA(cudaSetDevice(device));
@@ -100,6 +101,8 @@ int ssn_destroy(ssn_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->hier) { delete c->hier; c->hier = nullptr; }
+    ssn::ctx_cache_purge(c);
+    cudaStreamSynchronize(c->stream);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_up) cudaFreeHost(c->h_up);
     if (c->h_poll) cudaFreeHost(c->h_poll);
@@ -175,6 +178,9 @@ const char* ssn_profile_dump(ssn_ctx* c) {
         snprintf(line, sizeof(line), "%-44s %12.3f  calls %8ld\n", kv.first.c_str(), kv.second.first, kv.second.second);
         c->prof_text += line;
     }
+    snprintf(line, sizeof(line), "%-44s %12.0f  misses %8ld\n", "device buffers requested since the last dump", (double)c->buf_allocs, (long)c->buf_misses);
+    c->prof_text += line;
+    c->buf_allocs = c->buf_misses = 0;
     c->prof_acc.clear();
     return c->prof_text.c_str();
 }

@@ -13,6 +13,7 @@
 #include <memory>
 #include <stdexcept>
 #include <map>
+#include <unordered_map>
 #include <chrono>
 
 #include "../../include/ssnamg.h"
@@ -97,13 +98,60 @@ struct ssn_ctx {
     // CUDA-event timer around the launches of the plan-wide kernels (ssn_kernel_timer): bench.py's roofline
     bool ktimer = false; cudaEvent_t kt0 = nullptr, kt1 = nullptr; double kt_ms = 0.0; int64_t kt_n = 0;
     bool prof = false;
+    // Recycled device buffers (SSN_BUF_CACHE=0: every Buf is a cudaMallocAsync / cudaFreeAsync pair).  A hierarchy setup makes
+    // several hundred short-lived buffers of a few KB; all work of a context is ordered on ONE stream, so a freed block can be
+    // handed to the next request of its size class without a runtime call.  Blocks of up to 8 MB, power-of-two classes.
+    static constexpr int kCacheMinShift = 9, kCacheMaxShift = 23;
+    bool buf_cache = true;
+    std::vector<void*> cache_free[kCacheMaxShift + 1];
+    std::unordered_map<void*, unsigned char> cache_live;      // blocks handed out by the cache -> size class
+    size_t cache_bytes = 0, cache_cap = (size_t)512 << 20;    // bytes parked in the free lists, and their bound
+    int64_t buf_allocs = 0, buf_misses = 0;                   // requests / requests that went to cudaMallocAsync
     std::map<std::string, std::pair<double, long>> prof_acc;
     std::string prof_text;
 };
 
 namespace ssn {
 
-// Stream-ordered device buffer (cudaMallocAsync pool; frees are stream-ordered too).
+// ---- the context's block cache (see ssn_ctx::buf_cache)
+inline void* ctx_alloc(ssn_ctx* c, size_t bytes) {
+    ++c->buf_allocs;
+    void* p = nullptr;
+    if (c->buf_cache && bytes <= ((size_t)1 << ssn_ctx::kCacheMaxShift)) {
+        int cls = ssn_ctx::kCacheMinShift;
+        while (((size_t)1 << cls) < bytes) ++cls;
+        auto& fl = c->cache_free[cls];
+        if (!fl.empty()) { p = fl.back(); fl.pop_back(); c->cache_bytes -= (size_t)1 << cls; }
+        else {
+            ++c->buf_misses;
+            cudaError_t e = cudaMallocAsync(&p, (size_t)1 << cls, c->stream);
+            if (e != cudaSuccess) throw Error(SSN_E_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        }
+        c->cache_live[p] = (unsigned char)cls;
+        return p;
+    }
+    ++c->buf_misses;
+    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    if (e != cudaSuccess) throw Error(SSN_E_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    return p;
+}
+inline void ctx_free(ssn_ctx* c, void* p) {
+    if (!p) return;
+    auto it = c->cache_live.find(p);
+    if (it == c->cache_live.end()) { cudaFreeAsync(p, c->stream); return; }
+    const int cls = it->second;
+    c->cache_live.erase(it);
+    if (c->cache_bytes + ((size_t)1 << cls) <= c->cache_cap) { c->cache_free[cls].push_back(p); c->cache_bytes += (size_t)1 << cls; }
+    else cudaFreeAsync(p, c->stream);
+}
+// the block leaves the cache's books: its new owner frees it with cudaFreeAsync (ssn_free, ssn_csr_free)
+inline void ctx_untrack(ssn_ctx* c, void* p) { if (p) c->cache_live.erase(p); }
+inline void ctx_cache_purge(ssn_ctx* c) {
+    for (auto& fl : c->cache_free) { for (void* p : fl) cudaFreeAsync(p, c->stream); fl.clear(); }
+    c->cache_bytes = 0;
+}
+
+// Stream-ordered device buffer (the context's block cache over the cudaMallocAsync pool; frees are stream-ordered too).
 template <class T>
 struct Buf {
     ssn_ctx* c = nullptr; T* p = nullptr; size_t n = 0;
@@ -121,10 +169,10 @@ struct Buf {
     void alloc(ssn_ctx* ctx, size_t count) {
         reset(); c = ctx; n = count; owned = true;
         size_t bytes = (count ? count : 1) * sizeof(T);
-        SSN_CUDA(cudaMallocAsync((void**)&p, bytes, ctx->stream));
+        p = static_cast<T*>(ctx_alloc(ctx, bytes));
     }
     void reset() {
-        if (p && owned) cudaFreeAsync(p, c->stream);
+        if (p && owned) ctx_free(c, p);
         p = nullptr; n = 0; owned = true;
     }
     // hands the pointer to a caller that will cudaFreeAsync it: a view is copied into an owned allocation first
@@ -136,7 +184,7 @@ struct Buf {
             p = nullptr; n = 0; owned = true;
             return q;
         }
-        T* r = p; p = nullptr; n = 0; return r;
+        T* r = p; p = nullptr; n = 0; ctx_untrack(c, r); return r;
     }
     void zero() { SSN_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), c->stream)); }
     operator T*() const { return p; }
