@@ -123,7 +123,7 @@ void build_cluster_plan(ssn_ctx* c, Hierarchy& H);
 // Class_AMG's solve loop in one 16-CTA cluster with the level vectors in distributed shared memory (amg_cluster.cu);
 // false: the hierarchy does not qualify, nothing was launched
 bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, double* hist, int hl,
-                       int* iout);
+                       int* iout, const ssn_pcg_options* leaf_pcg = nullptr);
 
 // ---- dispatch (solvers.cu)
 void components(ssn_ctx* c, const CsrView& A, int* blocks, int* sizes, int* perm, int* r, int* ncomp);

@@ -40,7 +40,7 @@ constexpr int kZSlots = 2;                      // rows per thread kept in regis
 constexpr int kZProgMax = 1024;
 constexpr int kZXs = 2048;                      // largest dense leaf
 
-enum { Z_PRE = 0, Z_RESTRICT = 1, Z_LEAF = 2, Z_PROLONG = 3, Z_POST = 4 };
+enum { Z_PRE = 0, Z_RESTRICT = 1, Z_LEAF = 2, Z_PROLONG = 3, Z_POST = 4, Z_PCG = 5 };
 enum { ZV_E = 0, ZV_R = 1, ZV_G = 2, ZV_ALT = 3 };          // vector slots of a level (x: ZLevel::xslot, level 0 only)
 
 struct ZMat { const int* rp; const int* ci; const double* cv; uint32_t* loc; };
@@ -64,6 +64,9 @@ struct ZArgs {
     double* relk; double* rho; int* it_out;     // it_out[2]: 0 ok, 1 the level-1 matrix is not [diag U; U' diag] (kernel did nothing)
     const int* prog; int nprog;
     int noreg;                                  // development aid (env SSN_DSM_NOREG=1): the smoothing loops re-read their rows every sweep
+    // two-level method (twogrid_bigph.m:98-99): the leaf level kd is solved by PCG(A_kd, r, zero guess, Jacobi) instead of a
+    // dense operator; its per-row block then holds diag(A_kd) (not 1/diag) and the level has five vector slots
+    int leaf_pcg, pcg_maxit; double pcg_tol2;
 };
 
 constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffLv = 2048, kOffProg = 5120,
@@ -500,6 +503,72 @@ __device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth,
     return ZStream{dotAe, 0, G.flip};
 }
 
+// (a function of its own, like the streaming smoothers: the solve kernel's register allocation stays what it was)
+// e = PCG(A_k, r) on the leaf level of the two-level method: zero guess, Jacobi preconditioner, stops on
+// delta_new <= tol^2 * delta_0 or after pcg_maxit iterations                                         PCG.m:68-88, twogrid_bigph.m:98-99
+// (the arithmetic of pcg_kernel, amg_solve.cu; p in ALT, q / w in G, the residual in slot 4, the solution in E).  Per iteration:
+// one gathering pass over p, two cluster-wide sums and one plain barrier (p complete before it is gathered again).
+__device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, double pcg_tol2, bool noreg) {
+    const int nl = L.rpf + L.rpc;
+    double* d = z_vec(G, L, ZV_E);
+    const double* rhs = z_vec(G, L, ZV_R);
+    double* q = z_vec(G, L, ZV_G);
+    double* p = z_vec(G, L, ZV_ALT);
+    double* rr = z_vec(G, L, 4);
+    const double* dg = z_dinv(G, L);                                // diag(A_k) here (leaf_pcg)
+    double dn = 0.0;
+    for (int l = threadIdx.x; l < nl; l += kZT) {
+        if (z_row(L, G.rank, l) < 0) continue;
+        const double ri = rhs[l], wi = ri / dg[l];
+        d[l] = 0.0; rr[l] = ri; p[l] = wi; dn = fma(ri, wi, dn);
+    }
+    double delta_new = z_sum1(G, dn);
+    const double delta_0 = delta_new;
+    const bool regs = !noreg && (nl << L.ltA) <= kZSlots * kZT;
+    constexpr int K = 8;
+    const bool first = (threadIdx.x & ((1 << L.ltA) - 1)) == 0;
+    ZRow<K> R[kZSlots];
+    int lr[kZSlots]; bool mine[kZSlots];
+    if (regs) {
+#pragma unroll
+        for (int u = 0; u < kZSlots; ++u) {
+            lr[u] = (threadIdx.x >> L.ltA) + u * (kZT >> L.ltA);
+            mine[u] = lr[u] < nl && z_row(L, G.rank, lr[u]) >= 0;
+            z_row_load<K>(G, L, L.ltA, lr[u], mine[u], 0, 0, R[u]);
+        }
+    }
+    int it = 0;
+    while (it < pcg_maxit && delta_new > pcg_tol2 * delta_0) {  // PCG.m:76
+        const double delta_old = delta_new;
+        double qp = 0.0;
+        if (regs) {
+            double sv[kZSlots];
+#pragma unroll
+            for (int u = 0; u < kZSlots; ++u) sv[u] = z_row_dot<K>(G, L, R[u], L.ltA, L.so[ZV_ALT] - L.so[0], 0, 0);
+#pragma unroll
+            for (int u = 0; u < kZSlots; ++u) if (mine[u] && first) { q[lr[u]] = sv[u]; qp = fma(sv[u], p[lr[u]], qp); }
+        } else {
+            z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, ZV_ALT), 0, 0, true, [&](int l, int, double sdot) { q[l] = sdot; qp = fma(sdot, p[l], qp); });
+        }
+        qp = z_sum1(G, qp);                                         // every gather of p is done behind its barrier
+        const double alpha = delta_old / qp;
+        dn = 0.0;
+        for (int l = threadIdx.x; l < nl; l += kZT) {
+            if (z_row(L, G.rank, l) < 0) continue;
+            d[l] += alpha * p[l];
+            const double ri = rr[l] - alpha * q[l];
+            const double wi = ri / dg[l];
+            rr[l] = ri; q[l] = wi; dn = fma(ri, wi, dn);
+        }
+        delta_new = z_sum1(G, dn);
+        const double beta = delta_new / delta_old;
+        for (int l = threadIdx.x; l < nl; l += kZT) if (z_row(L, G.rank, l) >= 0) p[l] = q[l] + beta * p[l];
+        ++it;
+        z_barrier();
+    }
+    return G.flip;
+}
+
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
 #define ZDBG(op, level, call) do { const long long t0__ = clock64(); call; if (lead) { g_zdbg[(op) * 16 + (level)] += (unsigned long long)(clock64() - t0__); g_zdbg[128 + (op) * 16 + (level)] += 1ull; } } while (0)
 #else
@@ -562,6 +631,15 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
             for (int l = threadIdx.x; l < L.rpf + L.rpc; l += kZT) {
                 const int row = z_row(L, G.rank, l);
                 di[l] = row >= 0 ? L.dinv[row] : 0.0; ax[l] = row >= 0 ? L.Axi[row] : 0.0;
+            }
+        } else if (a.leaf_pcg) {
+            // the PCG leaf divides by the diagonal itself (PCG.m:93, as pcg_kernel does): diag(A_kd) of this CTA's rows
+            double* dg = reinterpret_cast<double*>(dsm + L.poff + L.rsbytes);
+            for (int l = threadIdx.x; l < L.rpf + L.rpc; l += kZT) {
+                const int row = z_row(L, G.rank, l);
+                double dv = 0.0;
+                if (row >= 0) for (int e = L.A.rp[row]; e < L.A.rp[row + 1]; ++e) if (L.A.ci[e] == row) dv = L.A.cv[e];
+                dg[l] = dv;
             }
         }
     }
@@ -754,6 +832,8 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 });
                 swy = z_sum1(G, swy));
                 st_dot[k] = swy;
+            } else if (op == Z_PCG) {                                   // e = PCG(A_k, r)                      twogrid_bigph.m:99
+                ZDBG(4, k, G.flip = z_pcg_leaf(G, L, a.pcg_maxit, a.pcg_tol2, a.noreg != 0));
             } else {                                                    // Z_LEAF: e = B r, or e += B (r - A e)
                 const double* r = z_vec(G, L, ZV_R);
                 double* e = z_vec(G, L, ZV_E);
@@ -952,10 +1032,12 @@ void z_gen(std::vector<int>& prog, int k, int kd, int J, bool wcycle, bool zero)
 // kd >= 1, smoothing on, at most kZMaxL levels, the bigraph smoother on level 0 only, all vectors within the shared
 // memory of 16 CTAs.  hist: 2*hl doubles (relk | rho), iout: 4 ints, as persist_solve reads them back.
 bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, const AmgOptions& o, bool wcycle, double* hist, int hl,
-                       int* iout) {
-    const int kd = H.dense_from, J = H.J;
+                       int* iout, const ssn_pcg_options* leaf_pcg) {
+    // leaf_pcg: the two-level method (twogrid_bigph): the coarsest level is solved by PCG with these options inside the kernel
+    const int J = H.J, kd = leaf_pcg ? J - 1 : H.dense_from;
     if (kd < 1 || kd >= J || kd + 1 > kZMaxL || H.smoth < 1) return false;
-    if (H.lv[kd].N > kZXs || H.lv[kd].B.p == nullptr) return false;
+    if (!leaf_pcg && (H.lv[kd].N > kZXs || H.lv[kd].B.p == nullptr)) return false;
+    if (leaf_pcg && (leaf_pcg->precd != 2 || leaf_pcg->guess_dev != nullptr || leaf_pcg->maxit < 0)) return false;
     for (int k = 1; k <= kd; ++k) if (H.lv[k].bigph) return false;
     const int ncta = kZCta;
     ZArgs a{};
@@ -984,7 +1066,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
             int nvec = 4;                                       // E, R, G, ALT
             z.xslot = 0;
             if (k == 0) { z.xslot = z.bigph ? ZV_ALT : 4; nvec = z.bigph ? 4 : 5; }     // the in-place smoother needs no ALT copy
-            if (k == kd) nvec = 3;
+            if (k == kd) nvec = leaf_pcg ? 5 : 3;               // PCG leaf: E (solution), R (right-hand side), G (q / w), ALT (p), 4 (residual)
             // the slots that A-gathers read (E, the ping-pong copy / x) carry a halo area behind the CTA's slice
             for (int sl_ = 0; sl_ < 5; ++sl_) z.so[sl_] = 0;
             const int order[5] = {ZV_E, ZV_ALT, 4, ZV_R, ZV_G};
@@ -1000,7 +1082,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
             off += (size_t)(((hcap[k] * 4 + 15) / 16) * 16);
             z.poff = (int)off;
             z.rsbytes = (((nl + 2) * 4 + 15) / 16) * 16;
-            off += (size_t)z.rsbytes + (k < kd ? (size_t)2 * (((nl * 8 + 15) / 16) * 16) : 0);
+            off += (size_t)z.rsbytes + ((k < kd || leaf_pcg) ? (size_t)2 * (((nl * 8 + 15) / 16) * 16) : 0);
             const double avgA = L.N ? (double)L.A.nnz / L.N : 0.0;
             z.ltA = z_log2_lanes(avgA, nl, kZSlots);
             z.ltG = z_log2_lanes(avgA, std::max(z.rpf, z.rpc), kZSlots);
@@ -1015,7 +1097,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
                 z.Td = ZMat{L.Pt.ptr.p, L.Pt.idx.p, L.Pt.val.p, nullptr};
                 z.ltT = z_log2_lanes(L.N ? (double)L.Pt.nnz / L.N : 0.0, nl);
             }
-            z.dinv = L.dinv.p; z.Axi = L.Axi.p; z.xx = L.xx; z.B = (k == kd) ? L.B.p : nullptr;
+            z.dinv = L.dinv.p; z.Axi = L.Axi.p; z.xx = L.xx; z.B = (k == kd && !leaf_pcg) ? L.B.p : nullptr;
         }
         if (pass == 0) {
             if (off > (size_t)c->smem_optin - 1024) return false;
@@ -1040,6 +1122,7 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
     std::vector<int> prog;
     z_gen(prog, 0, kd, J, wcycle, true);
     if ((int)prog.size() > kZProgMax) return false;
+    if (leaf_pcg) for (int& op : prog) if ((op & 0xff) == Z_LEAF) { if (!((op >> 16) & 1)) return false; op = (op & ~0xff) | Z_PCG; }
 #ifndef SSN_EMU
     static int ok16 = -1;                                   // can the device co-schedule a 16-CTA cluster of this kernel? (probed once)
     if (ok16 < 0) {
@@ -1078,6 +1161,10 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
     a.b = b; a.x = x; a.retol = o.retol;
     a.relk = hist; a.rho = hist + hl; a.it_out = iout;
     a.prog = dprog.p; a.nprog = (int)prog.size();
+    if (leaf_pcg) {
+        const double retol = (!(leaf_pcg->retol < 0) && leaf_pcg->retol == leaf_pcg->retol) ? leaf_pcg->retol : 1e-11;   // PCG.m: [] -> 1e-11
+        a.leaf_pcg = 1; a.pcg_maxit = leaf_pcg->maxit; a.pcg_tol2 = retol * retol;
+    }
     { const char* e = getenv("SSN_DSM_NOREG"); a.noreg = (e && e[0] == '1') ? 1 : 0; }
     Phase ph(c, "solve.dsm_solve_kernel");
 #ifdef SSN_EMU

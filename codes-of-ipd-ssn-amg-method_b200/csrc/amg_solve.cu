@@ -2214,6 +2214,34 @@ void twogrid_bigph(ssn_ctx* c, const CsrView& A, const double* b, const AmgOptio
     int it = 0;
     double rel_res = 0.0;
     std::vector<double> relk(1, 1.0), rho(1, NAN);
+    // ---- the whole iteration loop in ONE kernel (amg_cluster.cu: one 16-CTA cluster, level vectors in distributed shared
+    // memory, the coarse PCG inside the kernel: ~100 PCG iterations per two-grid iteration at a few microseconds each instead of
+    // the grid-wide pcg_kernel's 16) when both levels fit; the kernel leaves x untouched when it refuses the level-1 matrix
+    if (c->cluster_solve && c->dsm_solve && c->tg_cluster && L.A.nnz + Lc.A.nnz <= c->cluster_max_nnz) {
+        const int hl = o.maxit + 2;
+        Buf<double> hist(c, (size_t)2 * hl);
+        Buf<int> iout(c, 4);
+        if (dsm_cluster_solve(c, H, b, x, o, false, hist.p, hl, iout.p, &po)) {
+            int hi[4];
+            read_back(c, iout.p, hi, 4);
+            if (hi[2] == 0) {
+                it = hi[0];
+                const int len = hi[1];
+                std::vector<double> hh((size_t)2 * hl);
+                read_back(c, hist.p, hh.data(), hh.size());
+                relk.assign(hh.begin(), hh.begin() + len);
+                rho.assign(hh.begin() + hl, hh.begin() + hl + len);
+                rel_res = (len > 1) ? relk[len - 1] : 0.0;
+                if (it_out) *it_out = it;
+                if (rel_res_out) *rel_res_out = rel_res;
+                if (hist_len) *hist_len = (int)relk.size();
+                if (rel_resk) std::memcpy(rel_resk, relk.data(), sizeof(double) * relk.size());
+                if (rhok) std::memcpy(rhok, rho.data(), sizeof(double) * rho.size());
+                amg_clear(c);
+                return;
+            }
+        }
+    }
     double h[2];
     int np = launch_resid(c, L, b, x, L.r, H.part);                          // r = b - A*x ; res0 = norm(A*x-b)   :61
     SSN_LAUNCH(c, reduce_parts_kernel, 1, 256, 0, H.part.p, np, H.scal.p);

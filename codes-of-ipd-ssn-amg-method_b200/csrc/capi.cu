@@ -65,6 +65,7 @@ int ssn_create(ssn_ctx** out, int device) {
     { const char* e = getenv("SSN_DENSE_TAIL"); c->dense_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_SMALL_SCAN_MAX"); if (e && atoi(e) >= 0) c->small_scan_max = atoi(e); }
     { const char* e = getenv("SSN_DEVICE_SETUP"); c->device_setup = !(e && e[0] == '0'); }
+    { const char* e = getenv("SSN_TG_CLUSTER"); c->tg_cluster = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_BUF_CACHE"); c->buf_cache = !(e && e[0] == '0'); }
     { const char* e = getenv("SSN_DENSE_MAXN"); if (e && atoi(e) > 0) c->dense_max_n = atoi(e); }
     try {

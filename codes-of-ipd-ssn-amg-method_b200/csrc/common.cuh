@@ -89,6 +89,7 @@ struct ssn_ctx {
     bool dense_tail = true;               // SSN_DENSE_TAIL=0 falls back to the step-by-step tail kernel
     int ls_max_nt = 128;                  // SSN_LS_MAXNT: largest batch of the screened line search (8..128 steps per read of w)
     int plan_waves = 0;                   // SSN_PLAN_WAVES: waves of blocks of the plan-wide reduction kernels (0: two)
+    bool tg_cluster = true;               // SSN_TG_CLUSTER=0: twogrid_bigph's iteration loop kernel by kernel (coarse PCG: the grid-wide pcg_kernel)
     bool plan_stage = true;               // SSN_PLAN_STAGE=0: the plan-wide reduction kernels load straight into registers (no cp.async staging)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
     double ls_last_density = -1.0;        // share of the plan's entries that survived the screen in the last screened batch (< 0: none yet)

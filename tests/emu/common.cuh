@@ -216,6 +216,7 @@ struct ssn_ctx {
     int64_t persist_max_nnz = (int64_t)1 << 40;
     bool persist = true, dense_tail = true;
     int plan_waves = 0;                   // SSN_PLAN_WAVES: waves of blocks of the plan-wide reduction kernels (0: two)
+    bool tg_cluster = true;               // SSN_TG_CLUSTER=0: twogrid_bigph's iteration loop kernel by kernel (coarse PCG: the grid-wide pcg_kernel)
     bool plan_stage = true;
     int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
     int small_scan_max = 1 << 14;

@@ -93,6 +93,32 @@ int emu_dsm_solve(int kd, const double* B, const double* b, const double* guess,
     });
 }
 
+// twogrid_bigph (AMG/twogrid_bigph.m) through the cluster kernel: the two-level hierarchy (amg_setup with max_levels = 2) and the
+// whole iteration loop with the coarse PCG (retol [] -> 1e-11, maxit 100, Jacobi; :98-99) inside dsm_solve_kernel
+int emu_twogrid_dsm(int64_t n, int64_t nnz, const int* ap, const int* ai, const double* av, int smoth, int isnsp, int fnode, const double* b,
+                    const double* guess, double retol, int maxit, double* x_out, int* it, double* relk, double* rho, int* hist_len, int* status) {
+    return guarded([&] {
+        ssn_amg_options oo; std::memset(&oo, 0, sizeof(oo));
+        oo.retol = retol; oo.maxit = maxit; oo.smoth = smoth; oo.cycle = 'v'; oo.theta = 0.25; oo.bigph = 1; oo.inter = 1; oo.isnsp = isnsp; oo.fnode = fnode;
+        const ssn::AmgOptions o = ssn::resolve_options(&oo);
+        ssn::amg_setup(ctx(), view(n, n, nnz, ap, ai, av), o, 2);
+        ssn::Hierarchy& H = *ctx()->hier;
+        const int N = H.lv[0].N, hl = maxit + 2;
+        ssn::Buf<double> x(ctx(), (size_t)N), bb(ctx(), (size_t)N), hist(ctx(), (size_t)2 * hl);
+        ssn::Buf<int> iout(ctx(), 4);
+        std::memcpy(x.p, guess, sizeof(double) * N); std::memcpy(bb.p, b, sizeof(double) * N);
+        ssn_pcg_options po{}; po.retol = -1.0; po.maxit = 100; po.precd = 2; po.nf = 0; po.guess_dev = nullptr;
+        const bool ok = ssn::dsm_cluster_solve(ctx(), H, bb.p, x.p, o, false, hist.p, hl, iout.p, &po);
+        *status = ok ? iout.p[2] : -1;
+        if (ok && iout.p[2] == 0) {
+            *it = iout.p[0]; *hist_len = iout.p[1];
+            std::memcpy(relk, hist.p, sizeof(double) * iout.p[1]); std::memcpy(rho, hist.p + hl, sizeof(double) * iout.p[1]);
+            std::memcpy(x_out, x.p, sizeof(double) * N);
+        }
+        ssn::amg_clear(ctx());
+    });
+}
+
 int emu_rng_reset() { return guarded([&] { ssn::rng_reset(ctx(), 5489u); }); }
 int64_t emu_rng_drawn() { return ctx()->rng_drawn; }
 int emu_rand(int64_t count, double* out) { return guarded([&] { ssn::rng_rand(ctx(), count, out); }); }

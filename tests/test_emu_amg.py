@@ -313,3 +313,31 @@ def test_dsm_cluster_solve_against_the_oracle(emu, oracle, monkeypatch, m, n, de
           f"solution {np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref):.1e}")
     assert dev <= 1e-6, dev                                             # the leaf is PCG to 1e-11 in the oracle, a dense operator here
     assert np.linalg.norm(x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
+
+
+@pytest.mark.parametrize("m,n,density,isnsp,noreg", [(90, 70, 0.05, 1, 0), pytest.param(60, 50, 0.08, 0, 1, marks=_slow)])
+def test_twogrid_cluster_kernel_against_the_oracle(emu, oracle, monkeypatch, m, n, density, isnsp, noreg):
+    """twogrid_bigph's whole iteration loop inside the cluster kernel (amg_cluster.cu: Z_PCG, the coarse correction
+    PCG(Ac, rrc, {[] -> 1e-11, 100, Jacobi}) of AMG/twogrid_bigph.m:98-99 on the level vectors in distributed shared memory)
+    on 16 emulated CTAs against the oracle's twogrid_bigph: iteration count, residual history, solution."""
+    monkeypatch.setenv("SSN_DSM_NOREG", str(noreg))
+    monkeypatch.setenv("SSN_DSM_HALO", "0")
+    Ae = ssn_matrix(oracle, m, n, density, seed=7 * m)
+    rs = np.random.RandomState(11)
+    b = rs.standard_normal(m + n)
+    if isnsp:
+        b -= b.mean()
+    guess = 0.01 * rs.standard_normal(m + n)
+    o = {"retol": 1e-11, "maxit": 30, "smoth": 3, "isnsp": isnsp, "guess": guess, "fnode": n}
+    x_ref, it_ref, rel_ref, relk_ref, rho_ref = oracle.twogrid_bigph(Ae, b, o)
+    A1, a1 = _csr_args(Ae)
+    x = np.zeros(m + n); relk = np.zeros(40); rho = np.zeros(40)
+    it = C.c_int(0); hl = C.c_int(0); status = C.c_int(-7)
+    _check(emu, emu.emu_twogrid_dsm(C.c_int64(m + n), C.c_int64(A1.nnz), _p(a1[0]), _p(a1[1]), _p(a1[2]), C.c_int(3), C.c_int(isnsp), C.c_int(n),
+                                    _p(b), _p(guess), C.c_double(1e-11), C.c_int(30), _p(x), C.byref(it), _p(relk), _p(rho), C.byref(hl), C.byref(status)))
+    assert status.value == 0, status.value
+    relk_ref = np.asarray(relk_ref, dtype=float).reshape(-1)
+    assert it.value == it_ref and hl.value == len(relk_ref), (it.value, it_ref, hl.value, len(relk_ref))
+    big = relk_ref > 1e-9
+    assert np.allclose(relk[:hl.value][big], relk_ref[big], rtol=1e-6, atol=0)
+    assert np.linalg.norm(x - x_ref) <= 1e-9 * max(1.0, np.linalg.norm(x_ref))
