@@ -67,9 +67,10 @@ struct ZArgs {
     // two-level method (twogrid_bigph.m:98-99): the leaf level kd is solved by PCG(A_kd, r, zero guess, Jacobi) instead of a
     // dense operator; its per-row block then holds diag(A_kd) (not 1/diag) and the level has five vector slots
     int leaf_pcg, pcg_maxit; double pcg_tol2;
+    int tail_off, tail_cap;                     // PCG leaf: shared-memory area (byte offset, entries of 12 bytes) for the row entries past the registers
 };
 
-constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffLv = 2048, kOffProg = 5120,
+constexpr int kOffSlots = 1024, kOffSumR = 1536, kOffDot = 1616, kOffCur = 1696, kOffOuter = 1744, kOffTailCnt = 1792, kOffLv = 2048, kOffProg = 5120,
               kOffXs = 9216, kOffVec = kOffXs + kZXs * 8;
 static_assert(sizeof(ZLevel) * kZMaxL <= kOffProg - kOffLv, "level table does not fit its slot");
 
@@ -508,7 +509,7 @@ __device__ __noinline__ ZStream z_gs_stream(ZTeam G, const ZLevel& L, int smoth,
 // delta_new <= tol^2 * delta_0 or after pcg_maxit iterations                                         PCG.m:68-88, twogrid_bigph.m:98-99
 // (the arithmetic of pcg_kernel, amg_solve.cu; p in ALT, q / w in G, the residual in slot 4, the solution in E).  Per iteration:
 // one gathering pass over p, two cluster-wide sums and one plain barrier (p complete before it is gathered again).
-__device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, double pcg_tol2, bool noreg) {
+__device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, double pcg_tol2, bool noreg, int tail_off, int tail_cap) {
     const int nl = L.rpf + L.rpc;
     double* d = z_vec(G, L, ZV_E);
     const double* rhs = z_vec(G, L, ZV_R);
@@ -537,7 +538,40 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
             z_row_load<K>(G, L, L.ltA, lr[u], mine[u], 0, 0, R[u]);
         }
     }
+    // The entries of a row past the K in registers: one lane per row (the usual case at these row lengths) copies them into
+    // shared memory once per solve -- column location and value, in order -- so that the ~100 passes of the loop below do not
+    // fetch them from L2 (two dependent round trips per batch of a long row: the slowest thread sets the time of a pass).
+    // Same products in the same order as z_row_dot.  Rows that do not fit the area keep reading global memory.
+    int tb[kZSlots], tn[kZSlots];
+#pragma unroll
+    for (int u = 0; u < kZSlots; ++u) { tb[u] = -1; tn[u] = 0; }
+    double* tv = reinterpret_cast<double*>(G.dsm + tail_off);
+    uint32_t* tl = reinterpret_cast<uint32_t*>(G.dsm + tail_off + (size_t)tail_cap * 8);
+    if (regs && L.ltA == 0 && tail_cap > 0) {
+        int* tc = reinterpret_cast<int*>(G.dsm + kOffTailCnt);
+        if (threadIdx.x == 0) *tc = 0;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kZSlots; ++u) {
+            const int len = mine[u] ? R[u].e_end - R[u].e_more : 0;
+            if (len > 0) {
+                const int base = atomicAdd(tc, len);
+                if (base + len <= tail_cap) {
+                    for (int j = 0; j < len; ++j) { tl[base + j] = L.A.loc[R[u].e_more + j]; tv[base + j] = L.A.cv[R[u].e_more + j]; }
+                    tb[u] = base; tn[u] = len; R[u].e_end = R[u].e_more;
+                }
+            }
+        }
+        __syncthreads();
+    }
     int it = 0;
+    // debug build: cycles of the five phases of an iteration (lead thread), slots 8..12 of the 'zsum/dots' row of g_zdbg
+#if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
+#define ZPH(slot) do { if (G.rank == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_zdbg[6 * 16 + (slot)] += (unsigned long long)(t__ - tph); g_zdbg[128 + 6 * 16 + (slot)] += 1ull; tph = t__; } } while (0)
+    long long tph = clock64();
+#else
+#define ZPH(slot) do {} while (0)
+#endif
     while (it < pcg_maxit && delta_new > pcg_tol2 * delta_0) {  // PCG.m:76
         const double delta_old = delta_new;
         double qp = 0.0;
@@ -546,11 +580,25 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
 #pragma unroll
             for (int u = 0; u < kZSlots; ++u) sv[u] = z_row_dot<K>(G, L, R[u], L.ltA, L.so[ZV_ALT] - L.so[0], 0, 0);
 #pragma unroll
+            for (int u = 0; u < kZSlots; ++u) {
+                int e = 0;
+                for (; e + 3 < tn[u]; e += 4) {
+                    double xv[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) xv[w] = z_gather(G, L.so[ZV_ALT], tl[tb[u] + e + w]);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) sv[u] = fma(tv[tb[u] + e + w], xv[w], sv[u]);
+                }
+                for (; e < tn[u]; ++e) sv[u] = fma(tv[tb[u] + e], z_gather(G, L.so[ZV_ALT], tl[tb[u] + e]), sv[u]);
+            }
+#pragma unroll
             for (int u = 0; u < kZSlots; ++u) if (mine[u] && first) { q[lr[u]] = sv[u]; qp = fma(sv[u], p[lr[u]], qp); }
         } else {
             z_rows(G, L, L.A, z_rs(G, L), L.ltA, 0, nl, z_vb(L, ZV_ALT), 0, 0, true, [&](int l, int, double sdot) { q[l] = sdot; qp = fma(sdot, p[l], qp); });
         }
+        ZPH(8);
         qp = z_sum1(G, qp);                                         // every gather of p is done behind its barrier
+        ZPH(9);
         const double alpha = delta_old / qp;
         dn = 0.0;
         for (int l = threadIdx.x; l < nl; l += kZT) {
@@ -560,12 +608,16 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
             const double wi = ri / dg[l];
             rr[l] = ri; q[l] = wi; dn = fma(ri, wi, dn);
         }
+        ZPH(10);
         delta_new = z_sum1(G, dn);
+        ZPH(11);
         const double beta = delta_new / delta_old;
         for (int l = threadIdx.x; l < nl; l += kZT) if (z_row(L, G.rank, l) >= 0) p[l] = q[l] + beta * p[l];
         ++it;
         z_barrier();
+        ZPH(12);
     }
+#undef ZPH
     return G.flip;
 }
 
@@ -833,7 +885,7 @@ __global__ void __launch_bounds__(kZT, 1) dsm_solve_kernel(const __grid_constant
                 swy = z_sum1(G, swy));
                 st_dot[k] = swy;
             } else if (op == Z_PCG) {                                   // e = PCG(A_k, r)                      twogrid_bigph.m:99
-                ZDBG(4, k, G.flip = z_pcg_leaf(G, L, a.pcg_maxit, a.pcg_tol2, a.noreg != 0));
+                ZDBG(4, k, G.flip = z_pcg_leaf(G, L, a.pcg_maxit, a.pcg_tol2, a.noreg != 0, a.tail_off, a.tail_cap));
             } else {                                                    // Z_LEAF: e = B r, or e += B (r - A e)
                 const double* r = z_vec(G, L, ZV_R);
                 double* e = z_vec(G, L, ZV_E);
@@ -1116,6 +1168,19 @@ bool dsm_cluster_solve(ssn_ctx* c, Hierarchy& H, const double* b, double* x, con
             for (int k = 0; k <= kd; ++k) { hcap[k] = ((int)(want[k] * fsc)) & ~1; any = any || hcap[k] > 0; }
             if (!any) break;
         }
+    }
+    if (leaf_pcg) {
+        // what is left of the shared memory holds the long rows' tails of the PCG leaf (12 bytes per entry); at most every entry of
+        // a CTA's slice past the first 8 of each row would be asked for
+        off = (off + 15) / 16 * 16;
+        const size_t left = ((size_t)c->smem_optin - 1024 > off) ? (size_t)c->smem_optin - 1024 - off : 0;
+        int64_t cap = (int64_t)(left / 12) & ~(int64_t)3;
+        const int64_t most = (H.lv[kd].A.nnz + 3) & ~(int64_t)3;
+        if (cap > most) cap = most;
+        { const char* e = getenv("SSN_PCG_TAIL"); if (e && e[0] == '0') cap = 0; }
+        { const char* e = getenv("SSN_PCG_LT0"); if (e && e[0] == '1') a.lv[kd].ltA = 0; }   // tests: one lane per row whatever the row lengths
+        a.tail_off = (int)off; a.tail_cap = (int)cap;
+        off += (size_t)cap * 12;
     }
     const size_t smem = off;
     if (smem > (size_t)c->smem_optin - 1024) return false;

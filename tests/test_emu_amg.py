@@ -322,6 +322,7 @@ def test_twogrid_cluster_kernel_against_the_oracle(emu, oracle, monkeypatch, m, 
     on 16 emulated CTAs against the oracle's twogrid_bigph: iteration count, residual history, solution."""
     monkeypatch.setenv("SSN_DSM_NOREG", str(noreg))
     monkeypatch.setenv("SSN_DSM_HALO", "0")
+    monkeypatch.setenv("SSN_PCG_LT0", "1")               # one lane per row: the entries past the 8 in registers go through the shared-memory tail area
     Ae = ssn_matrix(oracle, m, n, density, seed=7 * m)
     rs = np.random.RandomState(11)
     b = rs.standard_normal(m + n)
