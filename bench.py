@@ -532,8 +532,14 @@ def secondary_metrics(ssnamg, drv, state, m, n):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     ssnamg.rng_reset(); zeta, itamg, resamg, info = ssnamg.Hybrid_AMG(pd, drv.CLASS1_AMG_OPTIONS)
     torch.cuda.synchronize(); dta = time.perf_counter() - t0
+    # inner_solver = 5: Hybrid_twogrid on the same system (its iteration loop, coarse PCG included, is one cluster kernel)
+    ssnamg.rng_reset(); ssnamg.Hybrid_twogrid(pd, drv.CLASS1_AMG_OPTIONS)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ssnamg.rng_reset(); _, ittg, restg, _ = ssnamg.Hybrid_twogrid(pd, drv.CLASS1_AMG_OPTIONS)
+    torch.cuda.synchronize(); dtt = time.perf_counter() - t0
     return {"pcg_iters_per_s": it / dt, "pcg_iters": it, "pcg_rel_res": res, "pcg_system": f"Jk {m + n}x{m + n}, nnz {Jk.nnz}",
-            "hybrid_amg_ms": dta * 1e3, "wcycles_per_s_incl_setup": itamg / dta}
+            "hybrid_amg_ms": dta * 1e3, "wcycles_per_s_incl_setup": itamg / dta,
+            "hybrid_twogrid_ms": dtt * 1e3, "twogrid_iterations": int(ittg), "twogrid_rel_res": float(restg)}
 
 
 METRIC2 = "ssn_amg_inner_solve_step_time_class2_64x64_grid"
