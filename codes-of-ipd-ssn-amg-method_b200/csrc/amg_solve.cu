@@ -1171,13 +1171,36 @@ __device__ __forceinline__ double row_dot_s(const PSlice& S, const double* x, in
         const int e1 = S.rp[row - S.rbase + 1];
         int e = S.rp[row - S.rbase] + sub;
         const int* ci = S.ci; const double* cv = S.cv;
+        // dense rows (hundreds of entries: early-phase systems, the coarse levels of partial OT): eight index / value loads of a
+        // lane in flight per trip -- a lane's trips are dependent L2 round trips and the longest row of a block sets the time of
+        // the pass (Class 2 bench state, 860 entries per row: 9 trips per row with batches of four and a one-by-one tail).
+        // The products are added in entry order whatever the batching: same bits.
+        if constexpr (SM)                                   // (the staged dense levels of the grid-wide kernel only: 128 registers there)
+        for (; e + 7 * TPR < e1; e += 8 * TPR) {
+            int iv[8]; double vv[8], xx[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { iv[u] = ci[e + u * TPR]; vv[u] = cv[e + u * TPR]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xx[u] = SM ? x[iv[u]] : __ldcg(x + iv[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = fma(vv[u], xx[u], s);
+        }
         for (; e + 3 * TPR < e1; e += 4 * TPR) {
             const int i0 = ci[e], i1 = ci[e + TPR], i2 = ci[e + 2 * TPR], i3 = ci[e + 3 * TPR];
             const double v0 = cv[e], v1 = cv[e + TPR], v2 = cv[e + 2 * TPR], v3 = cv[e + 3 * TPR];
             const double x0 = SM ? x[i0] : __ldcg(x + i0), x1 = SM ? x[i1] : __ldcg(x + i1), x2 = SM ? x[i2] : __ldcg(x + i2), x3 = SM ? x[i3] : __ldcg(x + i3);
             s = fma(v0, x0, s); s = fma(v1, x1, s); s = fma(v2, x2, s); s = fma(v3, x3, s);
         }
-        for (; e < e1; e += TPR) s = fma(cv[e], SM ? x[ci[e]] : __ldcg(x + ci[e]), s);
+        if constexpr (!SM) { for (; e < e1; e += TPR) s = fma(cv[e], __ldcg(x + ci[e]), s); }
+        else if (e < e1) {                                  // the last one to three entries together (they were one round trip each)
+            int iv[3]; double vv[3], xx[3]; bool has[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) { has[u] = e + u * TPR < e1; iv[u] = has[u] ? ci[e + u * TPR] : 0; vv[u] = has[u] ? cv[e + u * TPR] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) xx[u] = has[u] ? (SM ? x[iv[u]] : __ldcg(x + iv[u])) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (has[u]) s = fma(vv[u], xx[u], s);
+        }
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -1434,10 +1457,23 @@ __device__ void p_gs_apply(TM& G, const LevelDev& L, const PSlice& S, int tpr, c
                         if (other) s = fma(av[u], dj[u] * (gj[u] - xj[u] * coef), s);
                     }
                 }
-                for (; q < e1; q += TPR) {
-                    const int j = S.ci[q];
-                    const bool other = post ? (j >= L.Nf) : (j < L.Nf);
-                    if (other) s = fma(S.cv[q], L.dinv[j] * (TM::ld(g + j) - L.Axi[j] * coef), s);
+                if constexpr (TM::T != kPT) {               // (the 64-register cluster kernels keep the one-by-one tail)
+                    for (; q < e1; q += TPR) {
+                        const int j = S.ci[q];
+                        const bool other = post ? (j >= L.Nf) : (j < L.Nf);
+                        if (other) s = fma(S.cv[q], L.dinv[j] * (TM::ld(g + j) - L.Axi[j] * coef), s);
+                    }
+                } else if (q < e1) {                        // the last one to three entries together
+                    int j[3]; double av[3], gj[3], dj[3], xj[3]; bool has[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) { has[u] = q + u * TPR < e1; j[u] = has[u] ? S.ci[q + u * TPR] : 0; av[u] = has[u] ? S.cv[q + u * TPR] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) { gj[u] = has[u] ? TM::ld(g + j[u]) : 0.0; dj[u] = has[u] ? L.dinv[j[u]] : 0.0; xj[u] = has[u] ? L.Axi[j[u]] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const bool other = has[u] && (post ? (j[u] >= L.Nf) : (j[u] < L.Nf));
+                        if (other) s = fma(av[u], dj[u] * (gj[u] - xj[u] * coef), s);
+                    }
                 }
             }
 #pragma unroll

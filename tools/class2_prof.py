@@ -19,3 +19,17 @@ for _ in range(3):
 torch.cuda.synchronize()
 print(ssnamg.profile_dump())
 print({k: info[k] for k in ("E", "nnzH", "itamg", "ll", "ms_plan", "ms_asat", "ms_amg")})
+# per-(operation, level) cycles of the grid-wide solve kernel (debug build only: SSN_LIB_PATH=.../libssnamg_dbg.so)
+import ctypes
+from importlib import import_module
+_lib = import_module("codes-of-ipd-ssn-amg-method_b200._lib")
+_pb = (ctypes.c_ulonglong * 256)()
+_lib.context().call("ssn_debug_cycles_persist", ctypes.cast(_pb, ctypes.c_void_p), 1)
+_ops = {0: "resid", 1: "gs_apply", 2: "jacobi", 3: "spmv(P)", 4: "dense", 5: "outer res", 6: "zsum/dots", 7: "kernel"}
+_tot = _pb[7 * 16] or 1
+for _op, _nm in _ops.items():
+    for _lv in range(16):
+        _cnt = _pb[128 + _op * 16 + _lv]
+        if _cnt:
+            _cyc = _pb[_op * 16 + _lv]
+            print(f"  pdbg {_nm:9s} level {_lv}: {_cyc / 1e3:10.1f} kcycles ({100.0 * _cyc / _tot:5.1f} %) over {_cnt:6d} calls -> {_cyc / _cnt:8.0f} cyc/call")
