@@ -266,6 +266,41 @@ def test_full_size_systems_three_solve_kernels(gpu, tag):
         assert np.linalg.norm(z1 - z0) <= 1e-7 * np.linalg.norm(z0)
 
 
+@pytest.mark.parametrize("tag", ["k30_s1", "k80_s2"])
+def test_full_size_twogrid_cluster_kernel_equals_kernel_by_kernel(gpu, tag):
+    """Hybrid_twogrid (inner_solver = 5) on full-size late-phase systems: the whole iteration loop of twogrid_bigph in ONE
+    launch of the cluster kernel -- the coarse correction PCG(Ac, rrc, {[] -> 1e-11, 100, Jacobi}) of AMG/twogrid_bigph.m:98-99
+    on vectors in distributed shared memory (default) -- against the kernel-by-kernel loop with the grid-wide pcg_kernel:
+    same components, same number of two-grid iterations, solutions equal to 1e-9; the profile shows which one ran."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "ssn_states_g128.npz"))
+    g = int(d["g"]); m = n = g * g
+    s = torch.zeros(m * n, dtype=torch.uint8, device="cuda"); s[torch.from_numpy(d[tag + "_lin"]).cuda()] = 1
+    one = torch.ones(m, dtype=torch.float64, device="cuda")
+    H = gpu.ASAt(s, one, one)
+    del s
+    pd = {"bk1": float(d[tag + "_bk1"]), "tk": float(d[tag + "_tk"]), "p": np.ones(m), "q": np.ones(n), "T": None, "H0": H, "z": d[tag + "_z"]}
+    out = {}
+    try:
+        for mode in (2, 0):
+            gpu.set_cluster_solve(mode)
+            gpu.rng_reset()
+            gpu.profile(True)
+            zeta, it, res, info = gpu.Hybrid_twogrid(pd, AMG_OPTS)
+            prof = gpu.profile_dump(); gpu.profile(False)
+            assert ("solve.dsm_solve_kernel" in prof) == (mode == 2), prof
+            out[mode] = (np.asarray(zeta.cpu() if hasattr(zeta, "cpu") else zeta).reshape(-1), it, res, list(info))
+    finally:
+        gpu.set_cluster_solve(2); gpu.profile(False)
+    (z1, it1, res1, info1), (z0, it0, res0, info0) = out[2], out[0]
+    print(f"{tag}: two-grid in the cluster kernel: {it1} iterations (kernel by kernel {it0}), residual {res1:.2e} ({res0:.2e}), "
+          f"solution dev {np.linalg.norm(z1 - z0) / np.linalg.norm(z0):.1e}")
+    assert it1 == it0 and info1 == info0
+    assert np.linalg.norm(z1 - z0) <= 1e-9 * np.linalg.norm(z0)
+
+
 @pytest.mark.parametrize("dens,unit", [(0.25, True), (0.25, False), (0.02, False)])
 def test_hybrid_twogrid_matches_oracle(gpu, oracle, dens, unit):
     """Hybrid_twogrid.m / AMG/twogrid_bigph.m (inner_solver = 5) through the C ABI against the oracle: same
