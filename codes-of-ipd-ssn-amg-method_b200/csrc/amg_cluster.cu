@@ -564,6 +564,16 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
         }
         __syncthreads();
     }
+    // One lane per row and every row of the slice in a register slot: the thread that gathers for a row is the thread that
+    // updates it, so the row's d, r, own p and diagonal stay in registers for the whole solve (q and w are never stored; only p
+    // goes to shared memory, for the other rows' gathers).  Same expressions, same order of the partial sums as the loops below.
+    const bool own = regs && L.ltA == 0;
+    double dR[kZSlots], rR[kZSlots], pR[kZSlots], gR[kZSlots];
+#pragma unroll
+    for (int u = 0; u < kZSlots; ++u) {
+        const bool on = own && mine[u];
+        dR[u] = 0.0; rR[u] = on ? rr[lr[u]] : 0.0; pR[u] = on ? p[lr[u]] : 0.0; gR[u] = on ? dg[lr[u]] : 1.0;
+    }
     int it = 0;
     // debug build: cycles of the five phases of an iteration (lead thread), slots 8..12 of the 'zsum/dots' row of g_zdbg
 #if defined(SSN_PERSIST_DEBUG) && !defined(SSN_EMU)
@@ -590,6 +600,36 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
                     for (int w = 0; w < 4; ++w) sv[u] = fma(tv[tb[u] + e + w], xv[w], sv[u]);
                 }
                 for (; e < tn[u]; ++e) sv[u] = fma(tv[tb[u] + e], z_gather(G, L.so[ZV_ALT], tl[tb[u] + e]), sv[u]);
+            }
+            if (own) {
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) if (mine[u]) qp = fma(sv[u], pR[u], qp);
+                ZPH(8);
+                qp = z_sum1(G, qp);
+                ZPH(9);
+                const double alpha = delta_old / qp;
+                double wR[kZSlots];
+                dn = 0.0;
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) {
+                    wR[u] = 0.0;
+                    if (mine[u]) {
+                        dR[u] += alpha * pR[u];
+                        const double ri = rR[u] - alpha * sv[u];
+                        const double wi = ri / gR[u];
+                        rR[u] = ri; wR[u] = wi; dn = fma(ri, wi, dn);
+                    }
+                }
+                ZPH(10);
+                delta_new = z_sum1(G, dn);
+                ZPH(11);
+                const double beta = delta_new / delta_old;
+#pragma unroll
+                for (int u = 0; u < kZSlots; ++u) if (mine[u]) { pR[u] = wR[u] + beta * pR[u]; p[lr[u]] = pR[u]; }
+                ++it;
+                z_barrier();
+                ZPH(12);
+                continue;
             }
 #pragma unroll
             for (int u = 0; u < kZSlots; ++u) if (mine[u] && first) { q[lr[u]] = sv[u]; qp = fma(sv[u], p[lr[u]], qp); }
@@ -618,6 +658,11 @@ __device__ __noinline__ int z_pcg_leaf(ZTeam G, const ZLevel& L, int pcg_maxit, 
         ZPH(12);
     }
 #undef ZPH
+    if (own) {
+#pragma unroll
+        for (int u = 0; u < kZSlots; ++u) if (mine[u]) d[lr[u]] = dR[u];
+        z_barrier();                                        // the prolongation gathers the solution from every CTA
+    }
     return G.flip;
 }
 
