@@ -286,7 +286,7 @@ def prox_trials(w, lamT, p, q, tk, gama=np.inf):
 
 
 def prox_trials_lin(w, lam, zeta, p, q, tk, delta, ll0, nt):
-    """``||prox((w - Aty(lam + delta**(ll0+t)*zeta))/tk)||^2`` for ``t < nt <= 128`` backtracking steps of one
+    """``||prox((w - Aty(lam + delta**(ll0+t)*zeta))/tk)||^2`` for ``t < nt <= 256`` backtracking steps of one
     search direction in one read of ``w`` (``gama = Inf``), through the screened kernels: the values of
     ``prox_trials`` on the same trial vectors up to the summation order, HBM-bound for any ``nt`` where the
     trial plans are sparse.
@@ -416,7 +416,7 @@ def apd_end(c, wk, xk, lam, p, q, tk, ak, gama=np.inf):
 
 
 def trial_vectors(lam, zeta, wlk, delta, ll0, nt):
-    """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 128) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
+    """``lamT[t] = lam + delta**(ll0+t)*zeta`` (t < nt <= 256) and ``f0[2t] = ||lamT[t]||^2, f0[2t+1] = wlk'lamT[t]``
     as device tensors -- the O(m+n) half of a batch of Armijo trials."""
     torch = _torch(); ctx = context()
     ld, zd, wd = _dev(lam), _dev(zeta), _dev(wlk)

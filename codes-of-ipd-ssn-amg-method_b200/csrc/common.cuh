@@ -93,6 +93,7 @@ struct ssn_ctx {
     bool plan_stage = true;               // SSN_PLAN_STAGE=0: the plan-wide reduction kernels load straight into registers (no cp.async staging)
     bool ls_screen = true;                // SSN_LS_SCREEN=0: the adaptive line search uses the dense 8-trial kernel only
     double ls_last_density = -1.0;        // share of the plan's entries that survived the screen in the last screened batch (< 0: none yet)
+    int ls_last_ll = -1;                  // backtracking steps the last line search of this context accepted at (< 0: none yet)
     bool device_setup = true;             // SSN_DEVICE_SETUP=0: SSOR / IC(0) factors and their levels built on the host instead of the device (trifactor.cu)
     int small_scan_max = 1 << 14;         // SSN_SMALL_SCAN_MAX: largest array scanned by the one-block kernel (cub::DeviceScan above)
     int dense_max_n = 2048;               // SSN_DENSE_MAXN: largest level collapsed into a dense operator

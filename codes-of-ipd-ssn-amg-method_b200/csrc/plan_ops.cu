@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 2) plan_trials_kernel(const TrialArg
 // kernel's by the summation order alone (a few ulp).
 // max(z,0)^2 is accumulated as (z+|z|)^2 = 4*max(z,0)^2 (exact scaling, undone by the finish kernel).
 constexpr int kMaxLinTrials = 32;            // steps per evaluation launch
-constexpr int kMaxLinBatch = 128;            // steps per screened batch (one read of w)
+constexpr int kMaxLinBatch = 256;            // steps per screened batch (one read of w)
 struct TrialLinArgs {
     const double* w; const double* p; const double* q;
     const double* lam; const double* zeta;    // [n+m]: [column part ; row part] of lam_old and of the direction
@@ -1608,13 +1608,13 @@ void plan_prox_trials(ssn_ctx* c, const double* w, const double* lamT, int nt, c
 }
 
 // Screened trials (screen / compact / eval kernels above): out_dev[t] = ||prox((w - Aty(lam + alpha_t*zeta))/tk)||^2
-// for t < nt (nt <= 128, alpha_t = delta^(ll0+t), gama = Inf) and out_dev[nt] = number of entries that
+// for t < nt (nt <= 256, alpha_t = delta^(ll0+t), gama = Inf) and out_dev[nt] = number of entries that
 // survived the screen (candidates) -- out of m*n -- which tells the caller how sparse the trial plans are.
 // No host round trip before the last kernel is enqueued (the candidate list has a fixed capacity; see below).
 void plan_prox_trials_lin(ssn_ctx* c, const double* w, const double* lam, const double* zeta, const double* p, const double* q,
                           int64_t m, int64_t n, double tk, double delta, int ll0, int nt, double* out_dev, const int* nonunit_dev) {
     SSN_REQUIRE(m > 0 && n > 0 && w && lam && zeta && p && q && out_dev, SSN_E_INVALID, "prox_trials_lin: bad arguments");
-    SSN_REQUIRE(nt >= 1 && nt <= kMaxLinBatch, SSN_E_INVALID, "prox_trials_lin: 1 <= nt <= 128");
+    SSN_REQUIRE(nt >= 1 && nt <= kMaxLinBatch, SSN_E_INVALID, "prox_trials_lin: 1 <= nt <= 256");
     SSN_REQUIRE(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), SSN_E_TOO_LARGE, "prox_trials_lin: m or n >= 2^31");
     const Tiling t = plan_tiling(c, m, n);
     const int nblocks = t.chunks * t.groups;
@@ -1711,7 +1711,12 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
     // most steps accept the full step (ll = 0): the first read of w evaluates that trial alone -- unless the trial plans
     // of the previous line search of this context were sparse (late phase, where line searches are long): a screened
     // batch of 64 steps costs the same one read of w then, and saves a pass.  Every later read evaluates a batch.
-    const int first = (screened && c->ls_last_density >= 0.0 && c->ls_last_density <= 0.10) ? std::min(64, c->ls_max_nt) : 1;
+    int first = (screened && c->ls_last_density >= 0.0 && c->ls_last_density <= 0.10) ? std::min(64, c->ls_max_nt) : 1;
+    // ... and when the previous line search of this context backtracked far (late phase: consecutive SsN steps accept at similar
+    // ll, 100 - 200), the first batch reaches past that ll -- up to 256 steps in the one read of w, rounded to the 32 steps of an
+    // evaluation launch -- instead of finding it in a second pass.  The accepted step is the first that passes the Armijo test
+    // whatever the batches are.
+    if (first > 1 && c->ls_max_nt >= 128 && c->ls_last_ll >= 48) first = std::min(kMaxLinBatch, ((c->ls_last_ll + 32 + 31) / 32) * 32);
     while (true) {
         int want = batch;
         bool lin = screened;
@@ -1749,6 +1754,7 @@ void plan_linesearch(ssn_ctx* c, const double* w, const double* lam_old, const d
         }
         ll += nt;
     }
+    c->ls_last_ll = ll;
     if (ll_out) *ll_out = ll;
     if (passes_out) *passes_out = passes;
 }

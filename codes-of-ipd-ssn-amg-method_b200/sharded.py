@@ -114,6 +114,7 @@ class ShardedStep:
         self.gather_cap_limit = 1 << 20                            # above this many active entries: sizes first, then payloads
         self.profile = False                                       # True: device-synchronised phase times (ms_plan / ms_asat / ms_amg)
         self.last_density = None                                   # share of entries that survived the last screened batch
+        self.last_ll = None                                        # backtracking steps the last line search accepted at
         if inner_solver not in (4, 5):
             raise ValueError("inner_solver must be 4 (Hybrid_AMG) or 5 (Hybrid_twogrid)")
         self.inner_solver = inner_solver
@@ -213,11 +214,11 @@ class ShardedStep:
         """One read-sweep of the slab for nt Armijo trials: returns (lamT, values, density) with values
         (host) = [global ||prox(z_t)||^2 (nt) ; ||lam_t||^2, wlk'lam_t pairs (2 nt)].  One all_reduce of nt
         (+1) doubles and one device->host read per batch, however many launches it takes.  screened: the
-        slab goes through the screened kernels (up to 128 steps per read of the slab, gama = Inf), whose count of surviving
+        slab goes through the screened kernels (up to 256 steps per read of the slab, gama = Inf), whose count of surviving
         entries rides in the same all_reduce and comes back as density = share of the plan's entries."""
         torch = self.torch
         lams, f0s, parts = [], [], []
-        per = 128 if screened else 8
+        per = 256 if screened else 8
         cands = None
         for t0 in range(0, nt, per):
             k = min(per, nt - t0)
@@ -298,6 +299,10 @@ class ShardedStep:
         # sparse (late phase: < 10 % of the entries survive the screen, long line searches): then a screened batch of
         # 64 steps costs the same one read of the slab and saves a pass and a collective
         first = 64 if (screened and self.last_density is not None and self.last_density <= 0.10) else 1
+        # ... and past the ll the previous line search accepted at when that was far out (late phase: consecutive steps accept at
+        # similar ll): up to 256 steps in the one read of the slab, as plan_linesearch does (csrc/plan_ops.cu)
+        if first > 1 and self.last_ll is not None and self.last_ll >= 48:
+            first = min(256, ((self.last_ll + 32 + 31) // 32) * 32)
         while not done:                                                              # :189-211
             lin = screened and (passes == 0 or dens <= 0.25)
             if lin and passes > 0:
@@ -315,6 +320,7 @@ class ShardedStep:
                     break
             else:
                 ll += nt
+        self.last_ll = ll
         post = self.residual(lk_new, want_s_new)                                     # :212
         Fk_new = bk1 * lk_new - post[0] - wlk
         _lap("plan", t0)

@@ -252,7 +252,7 @@ SSN_API int ssn_prox_trials(ssn_ctx *ctx, const double *w_dev, const double *lam
                     const double *gama_dev, double gama_scalar, double *n2_out_dev);
 
 /* Screened batched trials of ONE search direction (gama = Inf): out_dev[t] = ||prox((w - Aty(lam +
- * delta^(ll0+t)*zeta))/tk)||^2 for t < nt <= 128 -- the values of ssn_prox_trials on the same trial
+ * delta^(ll0+t)*zeta))/tk)||^2 for t < nt <= 256 -- the values of ssn_prox_trials on the same trial
  * vectors up to the summation order -- and out_dev[nt] = number of entries at which some trial of
  * the batch may be active (out of m*n).  Entries whose first and last trial residuals are both
  * safely negative add exactly 0 and are dropped (the residual is linear in the step); the others are
@@ -263,7 +263,7 @@ SSN_API int ssn_prox_trials_lin(ssn_ctx *ctx, const double *w_dev, const double 
                         double delta, int ll0, int nt, double *out_dev);
 
 /* The O(m+n) half of a batch of Armijo trials (row-sharded callers use it with ssn_prox_trials on
- * their slab): lamT_out_dev[t] = lam + delta^(ll0+t)*zeta for t < nt <= 128 and
+ * their slab): lamT_out_dev[t] = lam + delta^(ll0+t)*zeta for t < nt <= 256 and
  * f0_out_dev[2t] = ||lamT[t]||^2, f0_out_dev[2t+1] = wlk'*lamT[t]  (Class1/APD_SsN_Class1.m:189-190). */
 SSN_API int ssn_trial_vectors(ssn_ctx *ctx, const double *lam_dev, const double *zeta_dev, const double *wlk_dev,
                       int64_t N, double delta, int ll0, int nt, double *lamT_out_dev, double *f0_out_dev);

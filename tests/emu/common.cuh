@@ -218,7 +218,7 @@ struct ssn_ctx {
     int plan_waves = 0;                   // SSN_PLAN_WAVES: waves of blocks of the plan-wide reduction kernels (0: two)
     bool tg_cluster = true;               // SSN_TG_CLUSTER=0: twogrid_bigph's iteration loop kernel by kernel (coarse PCG: the grid-wide pcg_kernel)
     bool plan_stage = true;
-    int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0;
+    int ls_max_nt = 128; bool ls_screen = true; double ls_last_density = -1.0; int ls_last_ll = -1;
     int small_scan_max = 1 << 14;
     bool device_setup = true;
     static constexpr int kSpgemmSites = 64;
